@@ -1,0 +1,163 @@
+#!/usr/bin/env python3
+"""Recipe that compiles the reference's own CPU implementation into oracle/_ref/.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is imported, linked or executed
+by the product path (lammps_le_b200/); only tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs may run what this builds.
+
+What it does (no cmake, none of the reference's own build scripts are run):
+  * compiles the reference sources WHERE THEY LIE under /root/reference/src
+    (core src/*.cpp + MOLECULE/*.cpp + USER-LE/*.cpp + STUBS/mpi.c) with g++ -O2,
+    object files and outputs only into oracle/_ref/;
+  * writes the small style_*.h include lists LAMMPS expects (they are plain
+    lists of `#include "x.h"` lines selected by the *_CLASS marker each style
+    header carries; the reference makes them with src/Make.sh:18-54 or
+    cmake/Modules/StyleHeaderUtils.cmake) into oracle/_ref/gen/;
+  * links oracle/_ref/liblammps_ref.so, oracle/_ref/lmp_ref (src/main.cpp) and
+    oracle/_ref/ref_harness (oracle/ref_harness.cpp, our own state-capture driver).
+
+No reference source is copied into this repository.  oracle/_ref/ is git-ignored
+but travels to the GPU box with the gpurun snapshot.
+"""
+import os
+import re
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("LE_REFERENCE_ROOT", "/root/reference")
+OUT = os.path.join(HERE, "_ref")
+GEN = os.path.join(OUT, "gen")
+OBJ = os.path.join(OUT, "obj")
+
+SRC_DIRS = ["src", "src/MOLECULE", "src/USER-LE"]
+CXXFLAGS = ["-O2", "-std=c++11", "-fPIC", "-DLAMMPS_SMALLBIG", "-DLAMMPS_EXCEPTIONS",
+            "-ffp-contract=off", "-w"]
+
+# (marker in header, filename prefix regex, style_<name>.h)
+STYLES = [
+    ("ANGLE_CLASS", r"angle_", "angle"), ("ATOM_CLASS", r"atom_vec_", "atom"),
+    ("BODY_CLASS", r"body_", "body"), ("BOND_CLASS", r"bond_", "bond"),
+    ("COMMAND_CLASS", r"", "command"), ("COMPUTE_CLASS", r"compute_", "compute"),
+    ("DIHEDRAL_CLASS", r"dihedral_", "dihedral"), ("DUMP_CLASS", r"dump_", "dump"),
+    ("FIX_CLASS", r"fix_", "fix"), ("IMPROPER_CLASS", r"improper_", "improper"),
+    ("INTEGRATE_CLASS", r"", "integrate"), ("KSPACE_CLASS", r"", "kspace"),
+    ("MINIMIZE_CLASS", r"min_", "minimize"), ("NBIN_CLASS", r"nbin_", "nbin"),
+    ("NPAIR_CLASS", r"npair_", "npair"), ("NSTENCIL_CLASS", r"nstencil_", "nstencil"),
+    ("NTOPO_CLASS", r"ntopo_", "ntopo"), ("PAIR_CLASS", r"pair_", "pair"),
+    ("READER_CLASS", r"reader_", "reader"), ("REGION_CLASS", r"region_", "region"),
+]
+
+
+def up_to_date(target, deps):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(d) <= t for d in deps if os.path.exists(d))
+
+
+def write_if_changed(path, text):
+    if os.path.exists(path) and open(path).read() == text:
+        return
+    with open(path, "w") as f:
+        f.write(text)
+
+
+def gen_headers():
+    os.makedirs(GEN, exist_ok=True)
+    headers = []
+    for d in SRC_DIRS:
+        p = os.path.join(REF, d)
+        headers += [os.path.join(p, h) for h in sorted(os.listdir(p)) if h.endswith(".h")]
+    first_lines = {}
+    for h in headers:
+        with open(h, errors="replace") as f:
+            first_lines[h] = f.read()
+    for marker, prefix, name in STYLES:
+        names = []
+        for h in headers:
+            base = os.path.basename(h)
+            if prefix and not base.startswith(prefix):
+                continue
+            if re.search(r"^#ifdef %s" % marker, first_lines[h], re.M):
+                names.append(base)
+        write_if_changed(os.path.join(GEN, "style_%s.h" % name),
+                         "".join('#include "%s"\n' % n for n in sorted(set(names))))
+        # packages_<kind>.h only feeds "which package provides style X" hints in
+        # error messages (src/lammps.cpp:909-1010); an empty list is valid.
+        write_if_changed(os.path.join(GEN, "packages_%s.h" % name), "")
+    write_if_changed(os.path.join(GEN, "lmpinstalledpkgs.h"),
+                     "#ifndef LMP_INSTALLED_PKGS_H\n#define LMP_INSTALLED_PKGS_H\n"
+                     "const char * LAMMPS_NS::LAMMPS::installed_packages[] = "
+                     '{"MOLECULE", "USER-LE", NULL};\n#endif\n')
+    write_if_changed(os.path.join(GEN, "lmpgitversion.h"),
+                     "#ifndef LMP_GIT_VERSION_H\n#define LMP_GIT_VERSION_H\n"
+                     "const bool LAMMPS_NS::LAMMPS::has_git_info = false;\n"
+                     'const char LAMMPS_NS::LAMMPS::git_commit[] = "(unknown)";\n'
+                     'const char LAMMPS_NS::LAMMPS::git_branch[] = "(unknown)";\n'
+                     'const char LAMMPS_NS::LAMMPS::git_descriptor[] = "(unknown)";\n#endif\n')
+
+
+def includes():
+    inc = ["-I" + GEN, "-I" + os.path.join(REF, "src/STUBS")]
+    inc += ["-I" + os.path.join(REF, d) for d in SRC_DIRS]
+    return inc
+
+
+def compile_one(job):
+    src, obj, cc = job
+    if up_to_date(obj, [src]):
+        return 0, src, ""
+    cmd = [cc] + (CXXFLAGS if cc == "g++" else ["-O2", "-fPIC", "-w"]) + includes() + ["-c", src, "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return r.returncode, src, r.stderr
+
+
+def main():
+    if not os.path.isdir(os.path.join(REF, "src")):
+        if os.path.exists(os.path.join(OUT, "ref_harness")):
+            print("oracle/_ref: reference tree absent, using prebuilt files")
+            return 0
+        print("oracle/_ref: reference tree absent and nothing prebuilt", file=sys.stderr)
+        return 1
+    os.makedirs(OBJ, exist_ok=True)
+    gen_headers()
+    jobs = []
+    for d in SRC_DIRS:
+        p = os.path.join(REF, d)
+        for s in sorted(os.listdir(p)):
+            if s.endswith(".cpp") and s != "main.cpp":
+                jobs.append((os.path.join(p, s), os.path.join(OBJ, s[:-4] + ".o"), "g++"))
+    jobs.append((os.path.join(REF, "src/STUBS/mpi.c"), os.path.join(OBJ, "mpi_stubs.o"), "gcc"))
+    nthreads = int(os.environ.get("LE_BUILD_JOBS", str(os.cpu_count() or 4)))
+    failed = []
+    with ThreadPoolExecutor(nthreads) as ex:
+        for rc, src, err in ex.map(compile_one, jobs):
+            if rc:
+                failed.append((src, err))
+    if failed:
+        for src, err in failed:
+            print("FAILED", src, "\n", err[-2000:], file=sys.stderr)
+        return 1
+    objs = [j[1] for j in jobs]
+    lib = os.path.join(OUT, "liblammps_ref.so")
+    if not up_to_date(lib, objs):
+        subprocess.check_call(["g++", "-shared", "-o", lib] + objs)
+    rpath = "-Wl,-rpath,$ORIGIN"
+    lmp = os.path.join(OUT, "lmp_ref")
+    main_cpp = os.path.join(REF, "src/main.cpp")
+    if not up_to_date(lmp, [lib, main_cpp]):
+        subprocess.check_call(["g++"] + CXXFLAGS + includes() + [main_cpp, "-o", lmp, "-L" + OUT,
+                                                                 "-llammps_ref", rpath])
+    harness_src = os.path.join(HERE, "ref_harness.cpp")
+    harness = os.path.join(OUT, "ref_harness")
+    if os.path.exists(harness_src) and not up_to_date(harness, [lib, harness_src]):
+        subprocess.check_call(["g++"] + CXXFLAGS + includes() + [harness_src, "-o", harness, "-L" + OUT,
+                                                                 "-llammps_ref", rpath])
+    print("oracle/_ref built:", lib)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
