@@ -1,0 +1,336 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark: atom-steps/s of the chromatin + loop-extrusion timestep.
+
+Workload (BASELINE.json configs[3] on one GPU): a 1,000,000-bead self-avoiding chromatin chain at number
+density 0.2 with 10,000 extruders, random left/right/roadblock barriers, WCA + FENE/harmonic + Langevin/NVE,
+`fix extrusion 500 / ex_load 100 / ex_unload 100` (SURVEY.md section 8d cadence for throughput runs).
+One bench "step" = `--md-steps` MD timesteps (default 500 = one full USER-LE cycle) issued by ONE le_run call.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our engine (CUDA, through the C ABI)
+  python bench.py --impl reference ...                           the reference's CPU code (oracle/_ref)
+
+value      whole-job atom-steps/s with all state resident in HBM when the timed region starts
+e2e        same metric through the C ABI with HOST buffers: every step uploads positions+velocities from
+           pinned host memory, runs, and downloads positions
+roofline   fused step kernel k_step<0>: algorithmic bytes (72.1 + 4 nbar per atom-step, nbar measured)
+           / CUDA-event time of the step loop, against MEASURED_PEAKS.json hbm_gbs
+cpu_baseline  the compiled reference (oracle/_ref/lmp_ref) on a bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "chromatin chain 1,000,000 beads rho=0.2, 10,000 extruders, random CTCF/roadblock barriers, " \
+           "WCA+FENE/harmonic+Langevin/NVE, extrusion 500 / ex_load 100 / ex_unload 100, dt 0.005"
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([t.strip() for t in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
+
+
+def build_system(n_beads, n_ext, seed):
+    from lammps_le_b200 import systems
+    return systems.chromatin_chain(n_beads, n_ext, rho=0.2, seed=seed, barriers="random")
+
+
+def le_fixes(e):
+    e.fix_extrusion(500, 1, 2, 3, 0.5, 2, 4, 12345)
+    e.fix_ex_load(100, 1, 1, 1.12, 2, 0.02, 684474, (1, 1), (1, 1))
+    e.fix_ex_unload(100, 2, 0.5, 0.05, 456456)
+
+
+REF_LE_LINES = ["fix loop all extrusion 500 1 2 3 0.5 2 4",
+                "fix loading all ex_load 100 1 1 1.12 2 prob 0.02 684474 iparam 1 1 jparam 1 1",
+                "fix unloading all ex_unload 100 2 0.5 prob 0.05 456456"]
+
+
+def prepared_engine(n_beads, n_ext, seed, device, relax_steps):
+    from lammps_le_b200 import systems
+    s = build_system(n_beads, n_ext, seed)
+    v = systems.maxwell_velocities(n_beads, 1.0, np.ones(n_beads), seed)
+    e = systems.make_engine(s, device=device, velocities=v, dt=0.005)
+    systems.relax(e, steps=relax_steps)
+    e.fix_langevin(1.0, 1.0, 1.0, 904297)
+    le_fixes(e)
+    e.reset_timestep(0)
+    return s, e
+
+
+def reference_rate(s, x, image, v, topo, md_steps_per_seg, nseg_warm, nseg_timed, workdir=None):
+    """atom-steps/s of oracle/_ref/lmp_ref on the same (relaxed) state; window placed so that one ex_unload
+    and one ex_load event fall inside the timed segments and no fix extrusion event does."""
+    from oracle import refio
+    wd = workdir or tempfile.mkdtemp(prefix="le_bench_ref_")
+    n = len(s["types"])
+    s2 = dict(s)
+    s2["x"], s2["image"], s2["v"] = x, image, v
+    # bonds from the live topology (each bond once, lower tag first, backbone before extruders like the input)
+    nb, bt, ba = topo["num_bond"], topo["bond_type"], topo["bond_atom"]
+    mask = (np.arange(bt.shape[1])[None, :] < nb[:, None]) & (ba > (np.arange(n) + 1)[:, None])
+    ii, mm = np.nonzero(mask)
+    rows = np.stack([bt[ii, mm], ii + 1, ba[ii, mm]], axis=1)
+    rows = rows[np.lexsort((rows[:, 1], rows[:, 0]))]
+    rows = np.asarray(rows)
+    s2["bonds"] = (rows[:, 0].astype(np.int32), rows[:, 1].astype(np.int32), rows[:, 2].astype(np.int32))
+    refio.write_data_file(os.path.join(wd, "data.le"), s2)
+    deck = refio.deck_header(s2, "data.le", sort=True)
+    start = 100 - nseg_warm * md_steps_per_seg
+    deck += ["reset_timestep %d" % max(start, 0), "fix 1 all nve", "fix 2 all langevin 1.0 1.0 1.0 904297"] + REF_LE_LINES
+    deck += ["thermo_style custom step temp epair emol bonds", "thermo 1000000", "timestep 0.005"]
+    deck += ["run %d" % md_steps_per_seg] * (nseg_warm + nseg_timed)
+    t0 = time.time()
+    out, _ = refio.run_reference(deck, workdir=wd, harness=False, timeout=3000)
+    wall = time.time() - t0
+    import re
+    loops = [(float(a), int(b)) for a, b in re.findall(r"Loop time of ([0-9.eE+-]+) on \d+ procs for (\d+) steps", out)]
+    timed = loops[nseg_warm:]
+    tsum = sum(t for t, _ in timed)
+    steps = sum(k for _, k in timed)
+    return n * steps / tsum, tsum / max(len(timed), 1), wall, steps
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n_beads, n_ext, md = args.beads, args.extruders, args.md_steps
+    # independent objects: every rank owns its own chain(s) (weak scaling, no data-path collective)
+    s, e = prepared_engine(n_beads, n_ext, 12345 + rank, local, args.relax)
+    for _ in range(args.warmup):
+        e.run(md)
+    st0 = e.stats()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    gpu_ms = 0.0
+    for _ in range(args.steps):
+        e.run(md)
+        gpu_ms += e.stats()["last_run_gpu_ms"]
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    st1 = e.stats()
+    tmax = torch.tensor([gpu_ms / 1e3, wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    t_gpu, t_wall = float(tmax[0]), float(tmax[1])
+    total_atom_steps = world * n_beads * md * args.steps
+    value = total_atom_steps / t_gpu
+
+    # ---- end to end through the C ABI with host buffers ----
+    x, im = e.positions()
+    v = e.velocities()
+    xp = torch.from_numpy(x).pin_memory().numpy()
+    vp = torch.from_numpy(v).pin_memory().numpy()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps // 2)):
+        e.set_positions(xp, im)
+        e.set_velocities(vp)
+        e.run(md)
+        xo, im = e.positions()
+        xp[:] = xo
+        vp[:] = e.velocities()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_beads * md * max(1, args.steps // 2) / float(te[0])
+    h2d = n_beads * (24 + 24 + 4)
+    d2h = n_beads * (24 + 24 + 4)
+
+    if rank != 0:
+        e.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel ----
+    nbar_full = st1["full_entries"] / n_beads
+    nbar_half = st1["half_pairs"] / n_beads
+    builds = st1["neigh_builds"] - st0["neigh_builds"]
+    steps_timed = md * args.steps
+    kint = steps_timed / max(builds, 1)
+    bytes_step = 72.1 + 4.0 * nbar_half                      # SURVEY.md 8(d) algorithmic bytes per atom-step
+    bytes_amort = bytes_step + (40.0 + 4.0 * nbar_half) / kint
+    peak, how = measured_peak_gbs()
+    achieved = bytes_amort * n_beads * steps_timed / t_gpu / 1e9
+    line = {
+        "metric": "atom-steps/s", "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_gpu / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 pair math / f64 accumulation / 32-bit fixed-point positions", "data": "synthetic",
+        "config": {"workload": WORKLOAD if n_beads == 1000000 else "same model, %d beads, %d extruders" % (n_beads, n_ext),
+                   "beads_per_gpu": n_beads, "md_steps_per_step": md, "nbar_half": nbar_half, "nbar_full": nbar_full,
+                   "steps_per_rebuild": kint, "l2_note": "working set (%.0f MB per GPU) vs 126 MB L2: inputs %s L2" % (
+                       n_beads * (32 + 16 + 16 + 4 * nbar_full + 12 + 4) / 1e6, "exceed" if n_beads >= 1000000 else "fit in"),
+                   "parallelism": "independent chains per GPU" if world > 1 else "single GPU"},
+        "e2e": {"value": e2e_value, "unit": "atom-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": how, "bytes_per_atom_step": bytes_amort,
+                     "kernel": "k_step<0> (+ amortised rebuild kernels)"},
+        "wall_s": t_wall,
+        "le_events": {"shifts": st1["extrusion_shifts"] - st0["extrusion_shifts"], "loads": st1["loads"] - st0["loads"],
+                      "unloads": st1["unloads"] - st0["unloads"]},
+    }
+    # ---- CPU baseline: the compiled reference on a bounded sample of the same state ----
+    if world == 1 and not args.no_cpu:
+        try:
+            from oracle import refio
+            if refio.have_reference():
+                topo = e.topology()
+                seg = max(4, int(2.0e6 / n_beads * 8))          # ~16 MD steps per segment at 1M beads
+                rate, _, wall_ref, nst = reference_rate(s, xo, im, e.velocities(), topo, seg, 1, 5)
+                line["cpu_baseline"] = {"value": rate, "unit": "atom-steps/s", "cores": 1, "kind": "reference",
+                                        "sample": "%d MD steps of the same relaxed state in oracle/_ref/lmp_ref (1 rank: USER-LE is only "
+                                                  "defined on one rank), window holds one ex_unload and one ex_load event, %.0f s wall incl. setup"
+                                                  % (nst, wall_ref)}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": "atom-steps/s", "cores": 0, "kind": "reference",
+                                        "sample": "oracle/_ref missing on this box"}
+        except Exception as ex:  # the baseline must never take the bench line down
+            line["cpu_baseline"] = {"value": None, "unit": "atom-steps/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % str(ex)[:200]}
+    e.close()
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import refio
+    from lammps_le_b200 import systems
+    n_beads, n_ext = args.beads, args.extruders
+    if not refio.have_reference():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built on this box"}))
+        return
+    # the same relaxed start as our arm (the relaxation is set-up, not the thing measured)
+    try:
+        s, e = prepared_engine(n_beads, n_ext, 12345, 0, args.relax)
+        x, im = e.positions()
+        v = e.velocities()
+        topo = e.topology()
+        e.close()
+        prep = "relaxed with the CUDA engine's push-off run"
+    except Exception:
+        s = build_system(n_beads, n_ext, 12345)
+        x, im, v = s["x"], s["image"], systems.maxwell_velocities(n_beads, 1.0, np.ones(n_beads), 12345)
+        topo = None
+        prep = "unrelaxed generator output"
+    if topo is None:
+        bt, a1, a2 = s["bonds"]
+        n = n_beads
+        nb = np.zeros(n, np.int32)
+        btab = np.zeros((n, 4), np.int32)
+        atab = np.zeros((n, 4), np.int32)
+        for t, a, b in zip(bt, a1, a2):
+            for p, q in ((a, b), (b, a)):
+                btab[p - 1, nb[p - 1]] = t
+                atab[p - 1, nb[p - 1]] = q
+                nb[p - 1] += 1
+        topo = {"num_bond": nb, "bond_type": btab, "bond_atom": atab}
+    seg = max(4, int(2.0e6 / n_beads * 8))
+    rate, t_seg, wall, nst = reference_rate(s, x, im, v, topo, seg, args.warmup, args.steps)
+    line = {"impl": "reference", "metric": "atom-steps/s", "value": rate, "unit": "atom-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_seg, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD if n_beads == 1000000 else "same model, %d beads, %d extruders" % (n_beads, n_ext),
+                       "md_steps_per_step": seg, "parallelism": "1 MPI rank (serial stubs)"},
+            "cpu_baseline": {"value": rate, "unit": "atom-steps/s", "cores": 1, "kind": "reference",
+                             "sample": "%d MD steps in %d `run` segments, %s; window holds one ex_unload + one ex_load event; "
+                                       "Loop time of each segment as LAMMPS prints it" % (nst, args.steps, prep)},
+            "e2e": {"value": rate, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--beads", type=int, default=1000000)
+    ap.add_argument("--extruders", type=int, default=10000)
+    ap.add_argument("--md-steps", type=int, default=500)
+    ap.add_argument("--relax", type=int, default=1500)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

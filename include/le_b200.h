@@ -1,0 +1,178 @@
+/* le_b200.h -- C ABI of the B200-native chromatin / loop-extrusion MD engine.
+ *
+ * This is the drop-in boundary for ONE hot path of polly-code/lammps_le: the
+ * Verlet timestep (src/verlet.cpp:223-354) of a bead-spring system with
+ *   pair_style lj/cut (WCA)          src/pair_lj_cut.cpp:68-140
+ *   bond_style fene | harmonic       src/MOLECULE/bond_fene.cpp:52-128, bond_harmonic.cpp:48-100
+ *   fix nve + fix langevin           src/fix_nve.cpp:64-140, src/fix_langevin.cpp:587-777
+ *   fix extrusion|ex_load|ex_unload  src/USER-LE/fix_extrusion.cpp:256-872,
+ *                                    fix_ex_load.cpp:329-655, fix_ex_unload.cpp:172-372
+ *   binned half neighbor lists       src/npair_half_bin_newton.cpp:35-160
+ * All state lives on one GPU; every entry point takes plain pointers and
+ * sizes (host memory unless stated) and returns 0 on success or a negative
+ * LE_E* code, with the message available from le_last_error().  This mirrors
+ * the only C-ABI precedent in the reference, the GPU package
+ * (src/GPU/pair_lj_cut_gpu.cpp:42-66: ljl_gpu_init/compute/clear).
+ *
+ * Conventions (those of the reference's Atom class, src/atom.h):
+ *   - atom ids ("tags") are 1..N, contiguous; every per-atom array passed in
+ *     or out is in TAG ORDER (entry t-1 belongs to tag t), the order the
+ *     1-rank reference keeps under `atom_modify sort 0 0`;
+ *   - bonds are stored on BOTH atoms (`newton on off`, the only mode in which
+ *     USER-LE works): num_bond[N],
+ *     bond_type[N*bond_per_atom], bond_atom[N*bond_per_atom];
+ *   - special lists as in src/special.cpp: nspecial[N*3] cumulative counts,
+ *     special[N*maxspecial];
+ *   - units lj (boltz = mvv2e = ftm2v = nktv2p = 1).
+ * There is no CPU fallback: every call fails with LE_ENOGPU without a device.
+ */
+#ifndef LE_B200_H
+#define LE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct le_ctx le_ctx;
+
+enum {
+  LE_OK = 0,
+  LE_EINVAL = -1,   /* bad argument (the reference's error->all "Illegal ... command") */
+  LE_ENOGPU = -2,   /* no CUDA device / CUDA runtime failure */
+  LE_ESTATE = -3,   /* call out of order (e.g. run before atoms were uploaded) */
+  LE_ERUN = -4,     /* run-time abort raised on device: "Bad FENE bond", neighbor overflow,
+                       "more than one bond type 2", special list overflow, created != broken */
+  LE_ENOMEM = -5
+};
+
+enum { LE_BOND_NONE = 0, LE_BOND_FENE = 1, LE_BOND_HARMONIC = 2 };
+enum { LE_FIX_EXTRUSION = 1, LE_FIX_EX_UNLOAD = 2, LE_FIX_EX_LOAD = 3 };
+
+/* thermo record, one per thermo output step (thermo_style custom step temp epair emol etotal press
+ * + the f_ID[1] counters of the three USER-LE fixes); energies are per atom (thermo_modify norm yes,
+ * the lj default, src/thermo.cpp). */
+typedef struct le_thermo {
+  int64_t step;
+  double temp, epair, emol, etotal, press;
+  double ke;                /* total kinetic energy (not normalised) */
+  double virial[6];         /* pair + bond virial, xx yy zz xy xz yz (not normalised) */
+  int64_t nbonds;           /* atom->nbonds */
+  int64_t fene_warnings;    /* "FENE bond too long" occurrences in this force evaluation */
+} le_thermo;
+
+/* run statistics, the numbers the reference prints in Finish::end (src/finish.cpp) */
+typedef struct le_stats {
+  int64_t steps;            /* timesteps run so far */
+  int64_t neigh_builds;     /* "Neighbor list builds" */
+  int64_t dangerous_builds; /* "Dangerous builds" */
+  int64_t half_pairs;       /* stored half neighbor pairs at the last build ("Total # of neighbors") */
+  int64_t full_entries;     /* stored full-list entries at the last build */
+  int64_t kernel_launches;  /* kernels this library launched (all calls) */
+  int64_t extrusion_shifts, loads, unloads;         /* cumulative event counters */
+  int64_t last_extrusion_shifts, last_loads, last_unloads; /* f_ID[1] of the three fixes */
+  double last_run_gpu_ms;   /* CUDA-event time of the last le_run's step loop */
+} le_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+int  le_create(le_ctx **out, int device, const double boxlo[3], const double boxhi[3],
+               const int periodic[3]);                      /* Domain::set_initial_box */
+void le_destroy(le_ctx *c);
+const char *le_last_error(const le_ctx *c);                 /* library.h:236-237 precedent */
+const char *le_version(void);
+
+/* ---- force field and run settings (input-script commands) ------------------------------ */
+int le_set_types(le_ctx *c, int ntypes, const double *mass /*[ntypes]*/, int nbondtypes);
+/* pair_style lj/cut + pair_coeff + pair_modify shift; matrices are [ntypes*ntypes], row-major, 0-based
+ * (entry (i-1)*ntypes+(j-1)), already mixed (PairLJCut::init_one, src/pair_lj_cut.cpp:512-535). */
+int le_set_pair_lj(le_ctx *c, int ntypes, const double *epsilon, const double *sigma,
+                   const double *cut, int shift_flag);
+/* bond_coeff: fene params = {K, R0, epsilon, sigma}; harmonic params = {K, r0, -, -} */
+int le_set_bond(le_ctx *c, int btype, int style, const double params[4]);
+int le_set_special(le_ctx *c, const double lj[3]);          /* special_bonds lj a b c (fene = 0 1 1) */
+int le_set_neighbor(le_ctx *c, double skin, int every, int delay, int check);
+int le_set_neighbor_capacity(le_ctx *c, int max_neighbors_per_atom);  /* neigh_modify one (full rows) */
+int le_set_newton(le_ctx *c, int newton_pair, int newton_bond); /* only (1,0) and (1,1) accepted */
+int le_set_capacity(le_ctx *c, int bond_per_atom, int maxspecial); /* data-file "extra ... per atom" */
+int le_set_timestep(le_ctx *c, double dt);                  /* timestep */
+int le_reset_timestep(le_ctx *c, int64_t step);             /* reset_timestep */
+int le_thermo_every(le_ctx *c, int nevery);                 /* thermo N (0 = first/last step only) */
+
+/* ---- fixes ----------------------------------------------------------------------------- */
+int le_fix_nve(le_ctx *c, int enable);
+/* fix nve/limit xmax (src/fix_nve_limit.cpp:70-140): cap the per-step displacement; xmax <= 0 = plain nve */
+int le_fix_nve_limit(le_ctx *c, double xmax);
+/* fix langevin Tstart Tstop damp seed: uniform noise as FixLangevin::post_force_templated<0,...>,
+ * but from a counter-based generator keyed by (seed, step, tag) instead of a sequential RanMars. */
+int le_fix_langevin(le_ctx *c, double t_start, double t_stop, double damp, int seed);
+/* fix ID all extrusion N neutral left right p_through btype [roadblock]; roadblock = -1 if absent.
+ * The reference hard-codes seed 12345 (fix_extrusion.cpp:98); seed <= 0 selects that. */
+int le_fix_extrusion(le_ctx *c, int nevery, int neutral, int left, int right, double p_through,
+                     int btype, int roadblock, int seed);
+/* fix ID all ex_load N itype jtype Rmin btype prob f seed iparam imax inew jparam jmax jnew */
+int le_fix_ex_load(le_ctx *c, int nevery, int itype, int jtype, double rc, int btype, double prob,
+                   int seed, int imaxbond, int inewtype, int jmaxbond, int jnewtype);
+/* fix ID all ex_unload N btype Rmax prob f seed */
+int le_fix_ex_unload(le_ctx *c, int nevery, int btype, double rc, double prob, int seed);
+int le_unfix(le_ctx *c, int which);                         /* unfix */
+
+/* ---- atoms and topology ---------------------------------------------------------------- */
+/* x[N*3], v[N*3] (may be NULL = zero), image[N] LAMMPS-packed (may be NULL = 0), all in tag order */
+int le_upload_atoms(le_ctx *c, int n, const int *tag, const int *type, const double *x,
+                    const double *v, const int *image);
+/* read_data "Bonds" section: each bond once; stored on both atoms in file order, then
+ * the 1-2/1-3/1-4 special lists are built as Special::build does (src/special.cpp:55-154). */
+int le_upload_bonds(le_ctx *c, int nbonds, const int *btype, const int *atom1, const int *atom2);
+/* raw per-atom tables exactly as the reference holds them (state replay) */
+int le_upload_topology(le_ctx *c, const int *num_bond, const int *bond_type, const int *bond_atom,
+                       const int *nspecial, const int *special);
+/* overwrite positions only (x[N*3], image may be NULL = keep); neighbor/bond lists are NOT rebuilt,
+ * which is the state a USER-LE fix sees between reneighborings */
+int le_set_positions(le_ctx *c, const double *x, const int *image);
+int le_set_velocities(le_ctx *c, const double *v);
+
+/* ---- run ------------------------------------------------------------------------------- */
+int le_run(le_ctx *c, int64_t nsteps);                      /* run N */
+int le_force_rebuild(le_ctx *c);                            /* Neighbor::build(1) now */
+/* run one USER-LE fix's post_integrate on the current state, regardless of the step gate */
+int le_run_le_event(le_ctx *c, int which);
+/* skip n draws of that fix's Marsaglia stream / re-seed it (state replay) */
+int le_fix_rng_reset(le_ctx *c, int which, int seed, int64_t ndraws_consumed);
+int le_fix_rng_consumed(le_ctx *c, int which, int64_t *ndraws);
+/* compute forces/energies at the current positions without integrating (run 0 without fixes):
+ * f[N*3] conservative pair+bond force in tag order (may be NULL) */
+int le_compute_forces(le_ctx *c, double *f, le_thermo *out);
+
+/* ---- results --------------------------------------------------------------------------- */
+int le_natoms(const le_ctx *c);
+int64_t le_timestep(const le_ctx *c);
+int le_download_x(le_ctx *c, double *x, int *image);        /* wrapped x[N*3] + image[N] */
+int le_download_v(le_ctx *c, double *v);
+int le_download_types(le_ctx *c, int *type);
+int le_download_topology(le_ctx *c, int *num_bond, int *bond_type, int *bond_atom, int *nspecial,
+                         int *special);
+/* half neighbor list of the last build, CSR over tags: offsets[N+1]; entries = partner tag | which<<30
+ * (the reference's j ^ (which << SBBITS), src/npair_half_bin_newton.cpp:113, with j replaced by tag).
+ * Call with entries == NULL to get the total count in *nentries. */
+int le_download_neighlist(le_ctx *c, int half, int64_t *offsets, int *entries, int64_t *nentries);
+/* neighbor->bondlist of the last build: rows (tag_i, tag_j, type), in the reference's order */
+int le_download_bondlist(le_ctx *c, int *rows, int64_t *nrows);
+int le_thermo_count(const le_ctx *c);
+int le_get_thermo(const le_ctx *c, int index, le_thermo *out); /* index < 0 counts from the end */
+int le_get_stats(le_ctx *c, le_stats *out);
+/* radius of gyration of the whole system from unwrapped coordinates (compute gyration) */
+int le_compute_rg(le_ctx *c, double *rg);
+
+/* ---- synthetic inputs (host only; bench and tests) -------------------------------------------- */
+/* self-avoiding walk(s) of n beads in a periodic cube [0,L)^3: bond length `step`, no two beads closer
+ * than rmin; x[n*3] wrapped coordinates, image[n] LAMMPS-packed image flags (may be NULL) */
+int le_gen_saw_chains(int n, int nchains, double L, double step, double rmin, uint64_t seed,
+                      double *x, int *image);
+/* FENE-melt start: nchains*len beads on a snake path through a simple-cubic lattice at density rho */
+int le_gen_lattice_melt(int nchains, int len, double rho, double *L, double *x, int *image);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LE_B200_H */

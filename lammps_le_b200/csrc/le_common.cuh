@@ -1,0 +1,144 @@
+// le_common.cuh -- device data layout and small helpers shared by every kernel.
+//
+// Layout in HBM (N atoms, all arrays device-resident for the life of the context):
+//   sorted order (index k = position after the last cell sort; rewritten at every rebuild)
+//     pos[2][N]   int4   {ux,uy,uz: 32-bit fixed-point box fractions, w: type-1}   double-buffered
+//     vel[N]      float4 {vx,vy,vz, w: tag bits}
+//     pos_hold[N] int4   positions at the last rebuild (Neighbor::xhold, src/neighbor.cpp:2048-2052)
+//     img[N], img_hold[N]  LAMMPS-packed image flags now / at the last rebuild
+//     counts[N]   nfull | nhalf<<8 | nbond<<16
+//     neigh[maxneigh][N]  ELL full neighbor rows, half-list entries first; entry = k_j | which<<30
+//     bondrow[bpa][N]     ELL bond partner rows; entry = k_j | (bondtype-1)<<28
+//   tag order (index t-1; what the reference's Atom class holds, src/atom.h)
+//     num_bond, bond_type[N][bpa], bond_atom[N][bpa], nspecial[N][3], special[N][maxspecial]
+//     map[N]      tag-1 -> sorted index (Atom::map, src/atom.h:354-358)
+//     bond_cross[N][bpa]  bond straddled the periodic boundary at the last rebuild (=> the reference's
+//                         bondlist holds it twice, src/ntopo_bond_all.cpp:65-66)
+//     ex13[N]     bit0: pair (t,t+2) is in the half list of the last rebuild, bit1: stored on t
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define LE_MAXT 8    // atom types
+#define LE_MAXB 8    // bond types
+#define LE_BIG 1.0e20
+#define NEIGH_IDX_MASK 0x3fffffffu
+#define BOND_IDX_MASK 0x0fffffffu
+
+struct Params {
+  // box and fixed-point mapping: x = lo + u*scale, scale = L/2^32
+  double lo[3], hi[3], L[3], scale[3], half[3];
+  float fscale[3], inv_fscale[3];
+  int periodic[3];
+  // the reference's neighbor bins (NBinStandard::setup_bins, src/nbin_standard.cpp:53-186); used only to
+  // reproduce which atom of a pair stores it in the half list
+  double bininv[3];
+  int nbin[3];
+  // pair lj/cut (PairLJCut::init_one, src/pair_lj_cut.cpp:512-535)
+  int ntypes, nbondtypes;
+  int pair_uniform;     // every type pair has the same lj/cut coefficients -> table index 0
+  double cutneighsq[LE_MAXT * LE_MAXT];
+  float cutneighmaxsq_f;
+  float cutsq[LE_MAXT * LE_MAXT], lj1[LE_MAXT * LE_MAXT], lj2[LE_MAXT * LE_MAXT];
+  float lj3[LE_MAXT * LE_MAXT], lj4[LE_MAXT * LE_MAXT], offset[LE_MAXT * LE_MAXT];
+  float special_lj[4];
+  int special_flag[4];
+  int nscan_tier;       // how many special tiers find_special must scan (0..3)
+  float mass[LE_MAXT];
+  // bonds
+  int bstyle[LE_MAXB];
+  float bk[LE_MAXB], br0[LE_MAXB], beps[LE_MAXB], bsig[LE_MAXB];
+  // integration / thermostat
+  float dt, dtf;
+  float triggersq;
+  float vlimitsq;       // fix nve/limit: (xmax/dt)^2, 0 = off
+  int nve_on, langevin_on;
+  float gfac1[LE_MAXT], gfac2[LE_MAXT];
+  unsigned seed_lo, seed_hi;
+  // neighbor policy
+  int every, delay, check;
+};
+
+struct Ctrl {
+  int moved;          // some atom moved more than skin/2 since the last rebuild
+  int forced;         // a fix asked for a rebuild on this step (Fix::next_reneighbor)
+  int rebuild_now;    // decision of the last k_decide
+  int ago;
+  int err;            // first run-time error code (0 = none)
+  int err_info[4];
+  long long nbuilds, ndanger;
+  long long fene_warn;
+  // USER-LE counters
+  int le_count[8];
+  long long nbonds;
+};
+
+enum {
+  LE_DERR_NONE = 0,
+  LE_DERR_BAD_FENE = 1,
+  LE_DERR_NEIGH_OVERFLOW = 2,
+  LE_DERR_BONDCOUNT = 3,
+  LE_DERR_SPECIAL_OVERFLOW = 4,
+  LE_DERR_BOND_OVERFLOW = 5,
+  LE_DERR_COUNT_MISMATCH = 6,
+  LE_DERR_MISSING_ATOM = 7,
+  LE_DERR_CELL_OVERFLOW = 8,
+  LE_DERR_RNG_OVERFLOW = 9
+};
+
+struct Dev {
+  int N, bpa, maxspecial, maxneigh;
+  int4 *pos[2];
+  int4 *pos_hold;
+  float4 *vel, *vel_tmp;
+  int *img, *img_hold;
+  unsigned *counts, *neigh, *bondrow;
+  // tag order
+  int *num_bond, *bond_type, *bond_atom, *nspecial, *special, *map;
+  unsigned char *bond_cross, *ex13;
+  // cell sort scratch
+  int *cell_count, *cell_start, *cellid, *slot, *order, *blocksum;
+  int ncell[3], ncells, nscanblocks;
+  int cell_rad[3], cell_span[3], cell_abs[3];  // per-dim stencil radius / span / "visit all cells" (k_build)
+  Ctrl *ctrl;
+  double *thermo;   // [slots][LE_THERMO_W]
+  double *fout;     // [N][3] optional force output (tag order)
+};
+
+#define LE_THERMO_W 16
+// thermo slot layout: 0 ke(sum m v^2) 1 evdwl 2 ebond 3..8 virial 9 fene warnings
+
+// one translation unit (le_engine.cu) includes this header; the block is refreshed before every use
+__constant__ Params c_P;
+
+__device__ __forceinline__ void le_raise(Ctrl *c, int code, int a = 0, int b = 0, int e = 0, int f = 0) {
+  if (atomicCAS(&c->err, 0, code) == 0) {
+    c->err_info[0] = a; c->err_info[1] = b; c->err_info[2] = e; c->err_info[3] = f;
+  }
+}
+
+// dequantised coordinate exactly as the host does it: one multiply, one add, no fma contraction
+__device__ __forceinline__ double le_deq(unsigned u, int d) {
+  return __dadd_rn(c_P.lo[d], __dmul_rn((double)u, c_P.scale[d]));
+}
+
+// Philox4x32-10 (Salmon et al. 2011) -- counter-based generator for the Langevin noise
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3,
+                                              unsigned k0, unsigned k1, unsigned out[4]) {
+  const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    unsigned hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    unsigned hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}

@@ -1,0 +1,1053 @@
+// le_engine.cu -- host side of the engine and the C ABI declared in include/le_b200.h.
+//
+// Replaces, for the one hot path, the reference's Verlet driver and the style objects it calls
+// (Verlet::setup/run src/verlet.cpp:87-354; Neighbor::build src/neighbor.cpp:2022-2101).  The host
+// only enqueues kernels: the reneighbor decision, the USER-LE events and their forced rebuilds are
+// all resolved on the device, nothing is read back inside le_run's step loop.
+#include "../../include/le_b200.h"
+#include "le_common.cuh"
+#include "le_md.cuh"
+#include "le_fix.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+static inline float h_int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+static inline int h_float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+
+#define THERMO_SLOTS 4096
+
+struct FixExtrusionCfg { int on, nevery, neutral, left, right, btype, roadblock, seed; double p; };
+struct FixExLoadCfg { int on, nevery, itype, jtype, btype, seed, imax, inew, jmax, jnew; double rc, prob; };
+struct FixExUnloadCfg { int on, nevery, btype, seed; double rc, prob; };
+
+struct le_ctx {
+  int device;
+  cudaStream_t stream;
+  std::string err;
+  // box
+  double lo[3], hi[3];
+  int periodic[3];
+  // force field
+  int ntypes, nbondtypes;
+  double mass[LE_MAXT];
+  double eps[LE_MAXT * LE_MAXT], sigma[LE_MAXT * LE_MAXT], cut[LE_MAXT * LE_MAXT];
+  int pair_set, shift_flag;
+  int bstyle[LE_MAXB];
+  double bparam[LE_MAXB][4];
+  double special_lj[4];
+  double skin;
+  int every, delay, check;
+  int newton_pair, newton_bond;
+  int bpa, maxspecial, maxneigh;
+  double dt;
+  int nve_on, langevin_on;
+  double xlimit;
+  double t_start, t_stop, t_period;
+  int lang_seed;
+  FixExtrusionCfg fx;
+  FixExLoadCfg fl;
+  FixExUnloadCfg fu;
+  std::vector<int> fix_order;   // definition order of the USER-LE fixes (Modify::post_integrate order)
+  int thermo_every;
+  // state
+  int N;
+  int64_t ntimestep;
+  int cur;              // position buffer holding the current coordinates
+  bool atoms_loaded, topo_loaded, lists_valid, params_dirty;
+  Dev d;
+  Params P;
+  std::vector<void *> allocs;
+  LeFixDev lf;          // USER-LE scratch (le_fix.cuh)
+  std::vector<le_thermo> thermo;
+  int64_t nbonds;
+  le_stats stats;
+  cudaEvent_t ev0, ev1;
+  double *h_thermo;     // pinned
+  Ctrl *h_ctrl;         // pinned
+};
+
+static int fail(le_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(c, LE_ENOGPU, "CUDA error %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+#define LAUNCH(c, kern, grid, block, ...)                      \
+  do {                                                         \
+    kern<<<(grid), (block), 0, (c)->stream>>>(__VA_ARGS__);    \
+    (c)->stats.kernel_launches++;                              \
+  } while (0)
+
+template <typename T>
+static int dalloc(le_ctx *c, T **p, size_t n) {
+  void *q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+  if (e != cudaSuccess) return fail(c, LE_ENOMEM, "cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+  cudaMemsetAsync(q, 0, std::max<size_t>(n, 1) * sizeof(T), c->stream);
+  c->allocs.push_back(q);
+  *p = (T *)q;
+  return 0;
+}
+
+static int grid_for(int n, int block) {
+  long long g = ((long long)n + block - 1) / block;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+extern "C" const char *le_version(void) { return "le_b200 0.1 (sm_100a)"; }
+
+extern "C" const char *le_last_error(const le_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+extern "C" int le_create(le_ctx **out, int device, const double boxlo[3], const double boxhi[3], const int periodic[3]) {
+  if (!out) return LE_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return LE_ENOGPU;
+  if (device < 0 || device >= ndev) return LE_EINVAL;
+  le_ctx *c = new le_ctx();
+  c->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete c; return LE_ENOGPU; }
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return LE_ENOGPU; }
+  cudaEventCreate(&c->ev0);
+  cudaEventCreate(&c->ev1);
+  for (int k = 0; k < 3; k++) {
+    c->lo[k] = boxlo[k]; c->hi[k] = boxhi[k]; c->periodic[k] = periodic[k];
+  }
+  c->ntypes = 1; c->nbondtypes = 0;
+  for (int k = 0; k < LE_MAXT; k++) c->mass[k] = 1.0;
+  c->pair_set = 0; c->shift_flag = 0;
+  memset(c->bstyle, 0, sizeof c->bstyle);
+  memset(c->bparam, 0, sizeof c->bparam);
+  c->special_lj[0] = 1.0; c->special_lj[1] = 0.0; c->special_lj[2] = 0.0; c->special_lj[3] = 0.0;
+  c->skin = 0.3; c->every = 1; c->delay = 10; c->check = 1;   // LAMMPS defaults for units lj
+  c->newton_pair = 1; c->newton_bond = 0;
+  c->bpa = 4; c->maxspecial = 16; c->maxneigh = 48;
+  c->dt = 0.005;
+  c->nve_on = 0; c->langevin_on = 0; c->xlimit = 0.0; c->t_start = c->t_stop = 1.0; c->t_period = 1.0; c->lang_seed = 1;
+  memset(&c->fx, 0, sizeof c->fx); memset(&c->fl, 0, sizeof c->fl); memset(&c->fu, 0, sizeof c->fu);
+  c->thermo_every = 0;
+  c->N = 0; c->ntimestep = 0; c->cur = 0;
+  c->atoms_loaded = c->topo_loaded = c->lists_valid = false;
+  c->params_dirty = true;
+  memset(&c->d, 0, sizeof c->d);
+  memset(&c->lf, 0, sizeof c->lf);
+  memset(&c->stats, 0, sizeof c->stats);
+  c->nbonds = 0;
+  cudaMallocHost(&c->h_thermo, sizeof(double) * LE_THERMO_W * THERMO_SLOTS);
+  cudaMallocHost(&c->h_ctrl, sizeof(Ctrl));
+  for (int k = 0; k < 3; k++)
+    if (!periodic[k]) { int r = fail(c, LE_EINVAL, "only fully periodic boxes are supported"); (void)r; }
+  *out = c;
+  for (int k = 0; k < 3; k++)
+    if (!periodic[k] || !(boxhi[k] > boxlo[k])) return LE_EINVAL;
+  return LE_OK;
+}
+
+extern "C" void le_destroy(le_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (void *p : c->allocs) cudaFree(p);
+  cudaFreeHost(c->h_thermo);
+  cudaFreeHost(c->h_ctrl);
+  cudaEventDestroy(c->ev0);
+  cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+// ---- settings -----------------------------------------------------------------------------------
+extern "C" int le_set_types(le_ctx *c, int ntypes, const double *mass, int nbondtypes) {
+  if (!c) return LE_EINVAL;
+  if (ntypes < 1 || ntypes > LE_MAXT) return fail(c, LE_EINVAL, "ntypes must be 1..%d", LE_MAXT);
+  if (nbondtypes < 0 || nbondtypes > LE_MAXB) return fail(c, LE_EINVAL, "nbondtypes must be 0..%d", LE_MAXB);
+  c->ntypes = ntypes; c->nbondtypes = nbondtypes;
+  for (int k = 0; k < ntypes; k++) {
+    c->mass[k] = mass ? mass[k] : 1.0;
+    if (!(c->mass[k] > 0.0)) return fail(c, LE_EINVAL, "Invalid mass value");
+  }
+  c->params_dirty = true;
+  return LE_OK;
+}
+
+extern "C" int le_set_pair_lj(le_ctx *c, int ntypes, const double *epsilon, const double *sigma, const double *cut, int shift_flag) {
+  if (!c) return LE_EINVAL;
+  if (ntypes != c->ntypes) return fail(c, LE_EINVAL, "pair matrices must be ntypes x ntypes (call le_set_types first)");
+  for (int k = 0; k < ntypes * ntypes; k++) {
+    if (cut[k] < 0.0) return fail(c, LE_EINVAL, "Illegal pair_style command");
+    c->eps[k] = epsilon[k]; c->sigma[k] = sigma[k]; c->cut[k] = cut[k];
+  }
+  c->shift_flag = shift_flag; c->pair_set = 1; c->params_dirty = true; c->lists_valid = false;
+  return LE_OK;
+}
+
+extern "C" int le_set_bond(le_ctx *c, int btype, int style, const double params[4]) {
+  if (!c) return LE_EINVAL;
+  if (btype < 1 || btype > c->nbondtypes) return fail(c, LE_EINVAL, "Invalid bond type in bond_coeff");
+  if (style != LE_BOND_NONE && style != LE_BOND_FENE && style != LE_BOND_HARMONIC) return fail(c, LE_EINVAL, "Unknown bond style");
+  c->bstyle[btype - 1] = style;
+  for (int k = 0; k < 4; k++) c->bparam[btype - 1][k] = params ? params[k] : 0.0;
+  c->params_dirty = true;
+  return LE_OK;
+}
+
+extern "C" int le_set_special(le_ctx *c, const double lj[3]) {
+  if (!c) return LE_EINVAL;
+  c->special_lj[0] = 1.0;
+  for (int k = 0; k < 3; k++) {
+    if (lj[k] < 0.0 || lj[k] > 1.0) return fail(c, LE_EINVAL, "Illegal special_bonds command");
+    c->special_lj[k + 1] = lj[k];
+  }
+  c->params_dirty = true; c->lists_valid = false;
+  return LE_OK;
+}
+
+extern "C" int le_set_neighbor(le_ctx *c, double skin, int every, int delay, int check) {
+  if (!c) return LE_EINVAL;
+  if (skin < 0.0 || every <= 0 || delay < 0) return fail(c, LE_EINVAL, "Illegal neighbor/neigh_modify command");
+  if (delay > 0 && (delay % every) != 0) return fail(c, LE_EINVAL, "Neighbor delay must be 0 or multiple of every setting");
+  c->skin = skin; c->every = every; c->delay = delay; c->check = check ? 1 : 0;
+  c->params_dirty = true; c->lists_valid = false;
+  return LE_OK;
+}
+
+extern "C" int le_set_neighbor_capacity(le_ctx *c, int maxn) {
+  if (!c) return LE_EINVAL;
+  if (maxn < 4 || maxn > 255) return fail(c, LE_EINVAL, "max neighbors per atom must be 4..255");
+  if (c->atoms_loaded) return fail(c, LE_ESTATE, "set the neighbor capacity before uploading atoms");
+  c->maxneigh = maxn;
+  return LE_OK;
+}
+
+extern "C" int le_set_newton(le_ctx *c, int newton_pair, int newton_bond) {
+  if (!c) return LE_EINVAL;
+  if (!newton_pair) return fail(c, LE_EINVAL, "newton_pair off is not supported (half/bin/newton lists only)");
+  c->newton_pair = 1; c->newton_bond = newton_bond ? 1 : 0;
+  return LE_OK;
+}
+
+extern "C" int le_set_capacity(le_ctx *c, int bond_per_atom, int maxspecial) {
+  if (!c) return LE_EINVAL;
+  if (bond_per_atom < 1 || bond_per_atom > 15 || maxspecial < 1 || maxspecial > 255) return fail(c, LE_EINVAL, "bad bond_per_atom / maxspecial");
+  if (c->atoms_loaded) return fail(c, LE_ESTATE, "set capacities before uploading atoms");
+  c->bpa = bond_per_atom; c->maxspecial = maxspecial;
+  return LE_OK;
+}
+
+extern "C" int le_set_timestep(le_ctx *c, double dt) {
+  if (!c) return LE_EINVAL;
+  if (!(dt > 0.0)) return fail(c, LE_EINVAL, "Illegal timestep command");
+  c->dt = dt; c->params_dirty = true;
+  return LE_OK;
+}
+
+extern "C" int le_reset_timestep(le_ctx *c, int64_t step) {
+  if (!c || step < 0) return LE_EINVAL;
+  c->ntimestep = step;
+  return LE_OK;
+}
+
+extern "C" int le_thermo_every(le_ctx *c, int nevery) {
+  if (!c || nevery < 0) return LE_EINVAL;
+  c->thermo_every = nevery;
+  return LE_OK;
+}
+
+extern "C" int le_fix_nve(le_ctx *c, int enable) {
+  if (!c) return LE_EINVAL;
+  c->nve_on = enable ? 1 : 0; c->xlimit = 0.0; c->params_dirty = true;
+  return LE_OK;
+}
+
+extern "C" int le_fix_nve_limit(le_ctx *c, double xmax) {
+  if (!c) return LE_EINVAL;
+  c->nve_on = 1; c->xlimit = xmax > 0.0 ? xmax : 0.0; c->params_dirty = true;
+  return LE_OK;
+}
+
+extern "C" int le_fix_langevin(le_ctx *c, double t_start, double t_stop, double damp, int seed) {
+  if (!c) return LE_EINVAL;
+  if (damp <= 0.0) return fail(c, LE_EINVAL, "Fix langevin period must be > 0.0");
+  if (seed <= 0) return fail(c, LE_EINVAL, "Illegal fix langevin command");
+  if (t_start < 0.0 || t_stop < 0.0) return fail(c, LE_EINVAL, "Illegal fix langevin command");
+  c->langevin_on = 1; c->t_start = t_start; c->t_stop = t_stop; c->t_period = damp; c->lang_seed = seed;
+  c->params_dirty = true;
+  return LE_OK;
+}
+
+extern "C" int le_fix_extrusion(le_ctx *c, int nevery, int neutral, int left, int right, double p, int btype, int roadblock, int seed) {
+  if (!c) return LE_EINVAL;
+  if (nevery <= 0) return fail(c, LE_EINVAL, "Illegal fix extrusion command, n_steps <= 0");
+  if (neutral < 1 || neutral > c->ntypes || left < 1 || left > c->ntypes || right < 1 || right > c->ntypes)
+    return fail(c, LE_EINVAL, "Invalid atom type (CTCF) in fix extrusion command");
+  if (p < 0.0 || p > 1.0) return fail(c, LE_EINVAL, "Invalid probability to pass through CTCF in fix extrusion command");
+  if (btype < 1 || btype > c->nbondtypes) return fail(c, LE_EINVAL, "Invalid atom type in fix extrusion command");
+  if (roadblock > c->ntypes) return fail(c, LE_EINVAL, "Invalid atom type in fix extrusion command");
+  if (roadblock >= 1 && (roadblock == left || roadblock == right))
+    return fail(c, LE_EINVAL, "roadblock type equal to a CTCF type is not supported");
+  c->fx.on = 1; c->fx.nevery = nevery; c->fx.neutral = neutral; c->fx.left = left; c->fx.right = right;
+  c->fx.p = p; c->fx.btype = btype; c->fx.roadblock = roadblock >= 1 ? roadblock : -1;
+  c->fx.seed = seed > 0 ? seed : 12345;
+  c->lf.rng[0].seeded = 0;
+  if (std::find(c->fix_order.begin(), c->fix_order.end(), LE_FIX_EXTRUSION) == c->fix_order.end()) c->fix_order.push_back(LE_FIX_EXTRUSION);
+  return LE_OK;
+}
+
+extern "C" int le_fix_ex_load(le_ctx *c, int nevery, int itype, int jtype, double rc, int btype, double prob, int seed,
+                              int imax, int inew, int jmax, int jnew) {
+  if (!c) return LE_EINVAL;
+  if (nevery <= 0) return fail(c, LE_EINVAL, "Illegal fix ex_load command");
+  if (itype < 1 || itype > c->ntypes || jtype < 1 || jtype > c->ntypes) return fail(c, LE_EINVAL, "Invalid atom type in fix ex_load command");
+  if (rc < 0.0) return fail(c, LE_EINVAL, "Illegal fix ex_load command");
+  if (btype < 1 || btype > c->nbondtypes) return fail(c, LE_EINVAL, "Invalid bond type in fix ex_load command");
+  if (prob < 0.0 || prob > 1.0 || seed <= 0) return fail(c, LE_EINVAL, "Illegal fix ex_load command");
+  if (imax < 0 || jmax < 0) return fail(c, LE_EINVAL, "Illegal fix ex_load command");
+  if (inew < 1) inew = itype;
+  if (jnew < 1) jnew = jtype;
+  if (inew > c->ntypes || jnew > c->ntypes) return fail(c, LE_EINVAL, "Invalid atom type in fix ex_load command");
+  if (itype == jtype && (imax != jmax || inew != jnew)) return fail(c, LE_EINVAL, "Inconsistent iparam/jparam values in fix ex_load command");
+  c->fl.on = 1; c->fl.nevery = nevery; c->fl.itype = itype; c->fl.jtype = jtype; c->fl.rc = rc; c->fl.btype = btype;
+  c->fl.prob = prob; c->fl.seed = seed; c->fl.imax = imax; c->fl.inew = inew; c->fl.jmax = jmax; c->fl.jnew = jnew;
+  c->lf.rng[2].seeded = 0;
+  if (std::find(c->fix_order.begin(), c->fix_order.end(), LE_FIX_EX_LOAD) == c->fix_order.end()) c->fix_order.push_back(LE_FIX_EX_LOAD);
+  return LE_OK;
+}
+
+extern "C" int le_fix_ex_unload(le_ctx *c, int nevery, int btype, double rc, double prob, int seed) {
+  if (!c) return LE_EINVAL;
+  if (nevery <= 0) return fail(c, LE_EINVAL, "Illegal fix ex_unload command");
+  if (btype < 1 || btype > c->nbondtypes) return fail(c, LE_EINVAL, "Invalid bond type in fix ex_unload command");
+  if (rc < 0.0) return fail(c, LE_EINVAL, "Illegal fix ex_unload command");
+  if (prob < 0.0 || prob > 1.0 || seed <= 0) return fail(c, LE_EINVAL, "Illegal fix ex_unload command");
+  c->fu.on = 1; c->fu.nevery = nevery; c->fu.btype = btype; c->fu.rc = rc; c->fu.prob = prob; c->fu.seed = seed;
+  c->lf.rng[1].seeded = 0;
+  if (std::find(c->fix_order.begin(), c->fix_order.end(), LE_FIX_EX_UNLOAD) == c->fix_order.end()) c->fix_order.push_back(LE_FIX_EX_UNLOAD);
+  return LE_OK;
+}
+
+extern "C" int le_unfix(le_ctx *c, int which) {
+  if (!c) return LE_EINVAL;
+  if (which == LE_FIX_EXTRUSION) c->fx.on = 0;
+  else if (which == LE_FIX_EX_UNLOAD) c->fu.on = 0;
+  else if (which == LE_FIX_EX_LOAD) c->fl.on = 0;
+  else return fail(c, LE_EINVAL, "unknown fix");
+  return LE_OK;
+}
+
+// ---- parameter block ------------------------------------------------------------------------------
+static int build_params(le_ctx *c) {
+  Params &P = c->P;
+  memset(&P, 0, sizeof P);
+  const double two32 = 4294967296.0;
+  for (int k = 0; k < 3; k++) {
+    P.lo[k] = c->lo[k]; P.hi[k] = c->hi[k];
+    P.L[k] = c->hi[k] - c->lo[k];
+    P.half[k] = 0.5 * P.L[k];
+    P.scale[k] = P.L[k] / two32;
+    P.fscale[k] = (float)P.scale[k];
+    P.inv_fscale[k] = (float)(two32 / P.L[k]);
+    P.periodic[k] = c->periodic[k];
+  }
+  P.ntypes = c->ntypes; P.nbondtypes = c->nbondtypes;
+  const int nt = c->ntypes;
+  double cutneighmax = 0.0;
+  bool uniform = true;
+  for (int i = 0; i < nt; i++)
+    for (int j = 0; j < nt; j++) {
+      const int k = i * nt + j;
+      const double e = c->pair_set ? c->eps[k] : 0.0, s = c->pair_set ? c->sigma[k] : 0.0, rc = c->pair_set ? c->cut[k] : 0.0;
+      // PairLJCut::init_one (src/pair_lj_cut.cpp:521-529)
+      const double lj1 = 48.0 * e * pow(s, 12.0), lj2 = 24.0 * e * pow(s, 6.0);
+      const double lj3 = 4.0 * e * pow(s, 12.0), lj4 = 4.0 * e * pow(s, 6.0);
+      double off = 0.0;
+      if (c->shift_flag && rc > 0.0) { const double ratio = s / rc; off = 4.0 * e * (pow(ratio, 12.0) - pow(ratio, 6.0)); }
+      const double cutsq = rc * rc;                       // Pair::init, src/pair.cpp:251
+      P.cutsq[k] = (float)cutsq; P.lj1[k] = (float)lj1; P.lj2[k] = (float)lj2;
+      P.lj3[k] = (float)lj3; P.lj4[k] = (float)lj4; P.offset[k] = (float)off;
+      // Neighbor::init (src/neighbor.cpp:293-310)
+      const double cutoff = sqrt(cutsq);
+      const double cn = cutoff + (cutoff > 0.0 ? c->skin : 0.0);
+      P.cutneighsq[k] = cn * cn;
+      cutneighmax = std::max(cutneighmax, cn);
+      if (k > 0 && (c->eps[k] != c->eps[0] || c->sigma[k] != c->sigma[0] || c->cut[k] != c->cut[0])) uniform = false;
+    }
+  P.pair_uniform = uniform ? 1 : 0;
+  if (!(cutneighmax > 0.0)) return fail(c, LE_ESTATE, "pair cutoff is zero: set pair_style lj/cut first");
+  P.cutneighmaxsq_f = (float)(cutneighmax * cutneighmax * 1.001 + 1e-6);
+  for (int k = 0; k < 3; k++)
+    if (P.L[k] < 2.0 * cutneighmax) return fail(c, LE_EINVAL, "box length %g < 2 x neighbor cutoff %g: minimum image needs a larger box", P.L[k], cutneighmax);
+  // reference bins: binsize = 1/2 cutneighmax snapped to the box (nbin_standard.cpp:95-131)
+  {
+    const double binsize_optimal = 0.5 * cutneighmax;
+    const double binsizeinv = 1.0 / binsize_optimal;
+    for (int k = 0; k < 3; k++) {
+      int nb = (int)(P.L[k] * binsizeinv);
+      if (nb == 0) nb = 1;
+      const double binsize = P.L[k] / nb;
+      P.nbin[k] = nb;
+      P.bininv[k] = 1.0 / binsize;
+    }
+  }
+  // special_bonds -> Neighbor::init special_flag (src/neighbor.cpp:349-369)
+  P.special_lj[0] = 1.0f;
+  P.nscan_tier = 0;
+  for (int k = 1; k <= 3; k++) {
+    P.special_lj[k] = (float)c->special_lj[k];
+    P.special_flag[k] = c->special_lj[k] == 0.0 ? 0 : c->special_lj[k] == 1.0 ? 1 : 2;
+    if (P.special_flag[k] != 1) P.nscan_tier = k;
+  }
+  for (int k = 0; k < nt; k++) P.mass[k] = (float)c->mass[k];
+  for (int k = 0; k < c->nbondtypes; k++) {
+    P.bstyle[k] = c->bstyle[k];
+    P.bk[k] = (float)c->bparam[k][0]; P.br0[k] = (float)c->bparam[k][1];
+    P.beps[k] = (float)c->bparam[k][2]; P.bsig[k] = (float)c->bparam[k][3];
+  }
+  P.dt = (float)c->dt; P.dtf = (float)(0.5 * c->dt);       // FixNVE::init, ftm2v = 1
+  P.triggersq = (float)(0.25 * c->skin * c->skin);
+  P.vlimitsq = c->xlimit > 0.0 ? (float)((c->xlimit / c->dt) * (c->xlimit / c->dt)) : 0.0f;
+  P.nve_on = c->nve_on; P.langevin_on = c->langevin_on;
+  for (int k = 0; k < nt; k++) {                             // FixLangevin::init (src/fix_langevin.cpp:296-309)
+    P.gfac1[k] = (float)(-c->mass[k] / c->t_period);
+    P.gfac2[k] = (float)(sqrt(c->mass[k]) * sqrt(24.0 / c->t_period / c->dt));
+  }
+  P.seed_lo = (unsigned)c->lang_seed; P.seed_hi = 0x4c414e47u;
+  P.every = c->every; P.delay = c->delay; P.check = c->check;
+
+  // cell grid: cells at least one neighbor cutoff wide
+  Dev &d = c->d;
+  for (int k = 0; k < 3; k++) {
+    int nc = (int)floor(P.L[k] / cutneighmax);
+    if (nc < 1) nc = 1;
+    if (nc > 1024) nc = 1024;
+    d.ncell[k] = nc;
+  }
+  while ((long long)d.ncell[0] * d.ncell[1] * d.ncell[2] > std::max<long long>(4LL * c->N, 64)) {
+    int k = (d.ncell[0] >= d.ncell[1] && d.ncell[0] >= d.ncell[2]) ? 0 : (d.ncell[1] >= d.ncell[2] ? 1 : 2);
+    d.ncell[k] = std::max(1, d.ncell[k] - std::max(1, d.ncell[k] / 16));
+  }
+  for (int k = 0; k < 3; k++) {
+    d.cell_rad[k] = 1;
+    if (d.ncell[k] >= 3) { d.cell_abs[k] = 0; d.cell_span[k] = 3; }
+    else { d.cell_abs[k] = 1; d.cell_span[k] = d.ncell[k]; }
+  }
+  d.ncells = d.ncell[0] * d.ncell[1] * d.ncell[2];
+  d.nscanblocks = (d.ncells + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  return LE_OK;
+}
+
+static int push_params(le_ctx *c) {
+  if (c->params_dirty) {
+    const int old_cells = c->d.ncells;
+    int r = build_params(c);
+    if (r) return r;
+    if (c->atoms_loaded && (c->d.ncells != old_cells || !c->d.cell_count)) {
+      r = dalloc(c, &c->d.cell_count, (size_t)c->d.ncells + 1); if (r) return r;
+      r = dalloc(c, &c->d.cell_start, (size_t)c->d.ncells + 1); if (r) return r;
+      r = dalloc(c, &c->d.blocksum, (size_t)c->d.nscanblocks + 1); if (r) return r;
+    }
+    c->params_dirty = false;
+  }
+  // the constant block is shared by all contexts of this process: refresh it before every use
+  CK(cudaMemcpyToSymbolAsync(c_P, &c->P, sizeof(Params), 0, cudaMemcpyHostToDevice, c->stream));
+  return LE_OK;
+}
+
+// ---- atoms ----------------------------------------------------------------------------------------
+static inline unsigned quantize(double x, double lo, double L, int *wrap) {
+  // nearest grid point; returns the box-image shift applied
+  double f = (x - lo) / L;
+  double fl = floor(f);
+  int w = (int)fl;
+  double u = rint((f - fl) * 4294967296.0);
+  if (u >= 4294967296.0) { u -= 4294967296.0; w += 1; }
+  *wrap = w;
+  return (unsigned)u;
+}
+
+static inline int pack_image(int ix, int iy, int iz) {
+  return ((ix + 512) & 1023) | (((iy + 512) & 1023) << 10) | (((iz + 512) & 1023) << 20);
+}
+static inline void unpack_image(int im, int *ix, int *iy, int *iz) {
+  *ix = (im & 1023) - 512; *iy = ((im >> 10) & 1023) - 512; *iz = ((im >> 20) & 1023) - 512;
+}
+
+extern "C" int le_upload_atoms(le_ctx *c, int n, const int *tag, const int *type, const double *x, const double *v, const int *image) {
+  if (!c) return LE_EINVAL;
+  if (n < 1 || !type || !x) return fail(c, LE_EINVAL, "le_upload_atoms: bad arguments");
+  if (c->atoms_loaded) return fail(c, LE_ESTATE, "atoms already uploaded (create a new context)");
+  if (n >= (1 << 28)) return fail(c, LE_EINVAL, "at most 2^28-1 atoms per GPU");
+  cudaSetDevice(c->device);
+  c->N = n;
+  Dev &d = c->d;
+  d.N = n; d.bpa = c->bpa; d.maxspecial = c->maxspecial; d.maxneigh = c->maxneigh;
+  int r;
+  if ((r = dalloc(c, &d.pos[0], n))) return r;
+  if ((r = dalloc(c, &d.pos[1], n))) return r;
+  if ((r = dalloc(c, &d.pos_hold, n))) return r;
+  if ((r = dalloc(c, &d.vel, n))) return r;
+  if ((r = dalloc(c, &d.vel_tmp, n))) return r;
+  if ((r = dalloc(c, &d.img, n))) return r;
+  if ((r = dalloc(c, &d.img_hold, n))) return r;
+  if ((r = dalloc(c, &d.counts, n))) return r;
+  if ((r = dalloc(c, &d.neigh, (size_t)n * c->maxneigh))) return r;
+  if ((r = dalloc(c, &d.bondrow, (size_t)n * c->bpa))) return r;
+  if ((r = dalloc(c, &d.num_bond, n))) return r;
+  if ((r = dalloc(c, &d.bond_type, (size_t)n * c->bpa))) return r;
+  if ((r = dalloc(c, &d.bond_atom, (size_t)n * c->bpa))) return r;
+  if ((r = dalloc(c, &d.nspecial, (size_t)n * 3))) return r;
+  if ((r = dalloc(c, &d.special, (size_t)n * c->maxspecial))) return r;
+  if ((r = dalloc(c, &d.map, n))) return r;
+  if ((r = dalloc(c, &d.bond_cross, (size_t)n * c->bpa))) return r;
+  if ((r = dalloc(c, &d.ex13, n))) return r;
+  if ((r = dalloc(c, &d.cellid, n))) return r;
+  if ((r = dalloc(c, &d.slot, n))) return r;
+  if ((r = dalloc(c, &d.order, n))) return r;
+  if ((r = dalloc(c, &d.ctrl, 1))) return r;
+  if ((r = dalloc(c, &d.thermo, (size_t)LE_THERMO_W * THERMO_SLOTS))) return r;
+  if ((r = dalloc(c, &d.fout, (size_t)n * 3))) return r;
+  if ((r = le_fix_alloc(c->lf, n, c->maxspecial, c->allocs, c->stream))) return fail(c, LE_ENOMEM, "cudaMalloc failed for USER-LE scratch");
+  c->atoms_loaded = true;
+
+  std::vector<int4> hp(n);
+  std::vector<float4> hv(n);
+  std::vector<int> himg(n), hmap(n);
+  std::vector<char> seen(n, 0);
+  for (int k = 0; k < n; k++) {
+    const int t = tag ? tag[k] : k + 1;
+    if (t < 1 || t > n || seen[t - 1]) return fail(c, LE_EINVAL, "atom ids must be a permutation of 1..N");
+    seen[t - 1] = 1;
+    if (type[k] < 1 || type[k] > c->ntypes) return fail(c, LE_EINVAL, "Invalid atom type in Atoms section of data file");
+    int w[3];
+    unsigned u[3];
+    for (int q = 0; q < 3; q++) u[q] = quantize(x[3 * k + q], c->lo[q], c->hi[q] - c->lo[q], &w[q]);
+    int ix = 0, iy = 0, iz = 0;
+    if (image) unpack_image(image[k], &ix, &iy, &iz);
+    // entries are stored in tag order initially: sorted index == tag-1 until the first rebuild
+    hp[t - 1] = make_int4((int)u[0], (int)u[1], (int)u[2], type[k] - 1);
+    float4 vv;
+    vv.x = v ? (float)v[3 * k] : 0.f; vv.y = v ? (float)v[3 * k + 1] : 0.f; vv.z = v ? (float)v[3 * k + 2] : 0.f;
+    vv.w = h_int_as_float(t);
+    hv[t - 1] = vv;
+    himg[t - 1] = pack_image(ix + w[0], iy + w[1], iz + w[2]);
+    hmap[t - 1] = t - 1;
+  }
+  c->cur = 0;
+  CK(cudaMemcpyAsync(d.pos[0], hp.data(), sizeof(int4) * n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d.pos_hold, hp.data(), sizeof(int4) * n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d.vel, hv.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d.img, himg.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d.img_hold, himg.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d.map, hmap.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->lists_valid = false; c->params_dirty = true;
+  return LE_OK;
+}
+
+static int upload_topology_host(le_ctx *c, const std::vector<int> &nb, const std::vector<int> &bt, const std::vector<int> &ba,
+                                const std::vector<int> &ns, const std::vector<int> &sp) {
+  Dev &d = c->d;
+  const size_t n = c->N;
+  CK(cudaMemcpyAsync(d.num_bond, nb.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d.bond_type, bt.data(), sizeof(int) * n * c->bpa, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d.bond_atom, ba.data(), sizeof(int) * n * c->bpa, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d.nspecial, ns.data(), sizeof(int) * n * 3, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d.special, sp.data(), sizeof(int) * n * c->maxspecial, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  int64_t tot = 0;
+  for (size_t k = 0; k < n; k++) tot += nb[k];
+  c->nbonds = tot / 2;
+  long long nb64 = c->nbonds;
+  CK(cudaMemcpyAsync(&c->d.ctrl->nbonds, &nb64, sizeof nb64, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->topo_loaded = true; c->lists_valid = false;
+  return LE_OK;
+}
+
+extern "C" int le_upload_bonds(le_ctx *c, int nbonds, const int *btype, const int *atom1, const int *atom2) {
+  if (!c) return LE_EINVAL;
+  if (!c->atoms_loaded) return fail(c, LE_ESTATE, "upload atoms before bonds");
+  const int n = c->N, bpa = c->bpa, ms = c->maxspecial;
+  std::vector<int> nb(n, 0), bt((size_t)n * bpa, 0), ba((size_t)n * bpa, 0), ns((size_t)n * 3, 0), sp((size_t)n * ms, 0);
+  // Atom::data_bonds with newton_bond off (src/atom.cpp:1261-1278): each bond goes to both atoms, file order
+  for (int k = 0; k < nbonds; k++) {
+    const int a = atom1[k], b = atom2[k], t = btype[k];
+    if (a < 1 || a > n || b < 1 || b > n || a == b) return fail(c, LE_EINVAL, "Invalid atom ID in Bonds section of data file");
+    if (t < 1 || t > c->nbondtypes) return fail(c, LE_EINVAL, "Invalid bond type in Bonds section of data file");
+    if (nb[a - 1] >= bpa || nb[b - 1] >= bpa) return fail(c, LE_EINVAL, "bonds per atom exceed bond_per_atom=%d", bpa);
+    bt[(size_t)(a - 1) * bpa + nb[a - 1]] = t; ba[(size_t)(a - 1) * bpa + nb[a - 1]] = b; nb[a - 1]++;
+    bt[(size_t)(b - 1) * bpa + nb[b - 1]] = t; ba[(size_t)(b - 1) * bpa + nb[b - 1]] = a; nb[b - 1]++;
+  }
+  // special lists: 1-2 = bond partners; 1-3 = partners of partners; 1-4 = partners of 1-3; each tier without
+  // self and without anything already listed (Special::build + combine, src/special.cpp:55-154,611-762)
+  std::vector<int> tmp;
+  for (int i = 0; i < n; i++) {
+    tmp.clear();
+    auto have = [&](int t) { return t == i + 1 || std::find(tmp.begin(), tmp.end(), t) != tmp.end(); };
+    for (int m = 0; m < nb[i]; m++) { int t = ba[(size_t)i * bpa + m]; if (!have(t)) tmp.push_back(t); }
+    const int n1 = (int)tmp.size();
+    for (int a = 0; a < n1; a++) { int j = tmp[a] - 1; for (int m = 0; m < nb[j]; m++) { int t = ba[(size_t)j * bpa + m]; if (!have(t)) tmp.push_back(t); } }
+    const int n2 = (int)tmp.size();
+    for (int a = n1; a < n2; a++) { int j = tmp[a] - 1; for (int m = 0; m < nb[j]; m++) { int t = ba[(size_t)j * bpa + m]; if (!have(t)) tmp.push_back(t); } }
+    const int n3 = (int)tmp.size();
+    if (n3 > ms) return fail(c, LE_EINVAL, "special list of atom %d needs %d entries > maxspecial=%d", i + 1, n3, ms);
+    ns[(size_t)i * 3] = n1; ns[(size_t)i * 3 + 1] = n2; ns[(size_t)i * 3 + 2] = n3;
+    for (int a = 0; a < n3; a++) sp[(size_t)i * ms + a] = tmp[a];
+  }
+  return upload_topology_host(c, nb, bt, ba, ns, sp);
+}
+
+extern "C" int le_upload_topology(le_ctx *c, const int *num_bond, const int *bond_type, const int *bond_atom, const int *nspecial, const int *special) {
+  if (!c) return LE_EINVAL;
+  if (!c->atoms_loaded) return fail(c, LE_ESTATE, "upload atoms before topology");
+  const size_t n = c->N;
+  for (size_t k = 0; k < n; k++) {
+    if (num_bond[k] < 0 || num_bond[k] > c->bpa) return fail(c, LE_EINVAL, "num_bond out of range for atom %zu", k + 1);
+    if (nspecial[3 * k + 2] > c->maxspecial || nspecial[3 * k] > nspecial[3 * k + 1] || nspecial[3 * k + 1] > nspecial[3 * k + 2])
+      return fail(c, LE_EINVAL, "nspecial out of range for atom %zu", k + 1);
+  }
+  std::vector<int> nb(num_bond, num_bond + n), bt(bond_type, bond_type + n * c->bpa), ba(bond_atom, bond_atom + n * c->bpa);
+  std::vector<int> ns(nspecial, nspecial + n * 3), sp(special, special + n * c->maxspecial);
+  return upload_topology_host(c, nb, bt, ba, ns, sp);
+}
+
+// scatter host values given in tag order into the current sorted order
+static int fetch_map(le_ctx *c, std::vector<int> &hmap) {
+  hmap.resize(c->N);
+  CK(cudaMemcpyAsync(hmap.data(), c->d.map, sizeof(int) * c->N, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return LE_OK;
+}
+
+extern "C" int le_set_positions(le_ctx *c, const double *x, const int *image) {
+  if (!c || !x) return LE_EINVAL;
+  if (!c->atoms_loaded) return fail(c, LE_ESTATE, "no atoms");
+  cudaSetDevice(c->device);
+  const int n = c->N;
+  std::vector<int> hmap; int r = fetch_map(c, hmap); if (r) return r;
+  std::vector<int4> hp(n); std::vector<int> himg(n);
+  CK(cudaMemcpyAsync(hp.data(), c->d.pos[c->cur], sizeof(int4) * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(himg.data(), c->d.img, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int t = 0; t < n; t++) {
+    const int k = hmap[t];
+    int w[3]; unsigned u[3];
+    for (int q = 0; q < 3; q++) u[q] = quantize(x[3 * t + q], c->lo[q], c->hi[q] - c->lo[q], &w[q]);
+    int ix = 0, iy = 0, iz = 0;
+    if (image) unpack_image(image[t], &ix, &iy, &iz);
+    else {
+      // no image flags given: keep the unwrapped trajectory continuous (nearest-image move)
+      unpack_image(himg[k], &ix, &iy, &iz);
+      const unsigned old[3] = {(unsigned)hp[k].x, (unsigned)hp[k].y, (unsigned)hp[k].z};
+      int *im[3] = {&ix, &iy, &iz};
+      for (int q = 0; q < 3; q++) {
+        const long long raw = (long long)u[q] - (long long)old[q];
+        const int wrapped = (int)(u[q] - old[q]);
+        *im[q] += (int)(((long long)wrapped - raw) >> 32);   // +1: crossed the upper face
+      }
+    }
+    hp[k].x = (int)u[0]; hp[k].y = (int)u[1]; hp[k].z = (int)u[2];
+    himg[k] = image ? pack_image(ix + w[0], iy + w[1], iz + w[2]) : pack_image(ix, iy, iz);
+  }
+  CK(cudaMemcpyAsync(c->d.pos[c->cur], hp.data(), sizeof(int4) * n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d.img, himg.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return LE_OK;
+}
+
+extern "C" int le_set_velocities(le_ctx *c, const double *v) {
+  if (!c || !v) return LE_EINVAL;
+  if (!c->atoms_loaded) return fail(c, LE_ESTATE, "no atoms");
+  cudaSetDevice(c->device);
+  const int n = c->N;
+  std::vector<int> hmap; int r = fetch_map(c, hmap); if (r) return r;
+  std::vector<float4> hv(n);
+  for (int t = 0; t < n; t++) {
+    float4 vv; vv.x = (float)v[3 * t]; vv.y = (float)v[3 * t + 1]; vv.z = (float)v[3 * t + 2]; vv.w = h_int_as_float(t + 1);
+    hv[hmap[t]] = vv;
+  }
+  CK(cudaMemcpyAsync(c->d.vel, hv.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return LE_OK;
+}
+
+// ---- rebuild / step drivers -------------------------------------------------------------------------
+static void enqueue_rebuild(le_ctx *c, int gated) {
+  Dev &d = c->d;
+  const int n = c->N;
+  LAUNCH(c, k_cell_count, grid_for(n, 256), 256, d, c->cur, gated);
+  LAUNCH(c, k_scan_partial, d.nscanblocks, SCAN_BLOCK, d, gated);
+  LAUNCH(c, k_scan_blocks, 1, SCAN_BLOCK, d, gated);
+  LAUNCH(c, k_scan_apply, d.nscanblocks, SCAN_BLOCK, d, gated);
+  LAUNCH(c, k_cell_scatter, grid_for(n, 256), 256, d, gated);
+  LAUNCH(c, k_cell_sort, grid_for(d.ncells, 128), 128, d, gated);
+  LAUNCH(c, k_gather, grid_for(n, 256), 256, d, c->cur, gated);
+  LAUNCH(c, k_build, grid_for(n, 128), 128, d, c->cur, gated);
+  LAUNCH(c, k_after_build, 1, 1, d, gated);
+}
+
+static const char *derr_text(int code) {
+  switch (code) {
+    case LE_DERR_BAD_FENE: return "Bad FENE bond";
+    case LE_DERR_NEIGH_OVERFLOW: return "Neighbor list overflow, boost neigh_modify one";
+    case LE_DERR_BONDCOUNT: return "Fix extrusion, more than one bond type 2";
+    case LE_DERR_SPECIAL_OVERFLOW: return "Special list size exceeded in fix bond/create";
+    case LE_DERR_BOND_OVERFLOW: return "New bond exceeded bonds per atom";
+    case LE_DERR_COUNT_MISMATCH: return "Numbers of created and broken bonds are not equal";
+    case LE_DERR_MISSING_ATOM: return "Bond atoms missing";
+    case LE_DERR_RNG_OVERFLOW: return "USER-LE random draw buffer overflow";
+    default: return "device error";
+  }
+}
+
+// copy the control block back and turn a device-side abort into an error return
+static int sync_and_check(le_ctx *c) {
+  CK(cudaMemcpyAsync(c->h_ctrl, c->d.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaGetLastError());
+  const Ctrl &k = *c->h_ctrl;
+  c->stats.neigh_builds = k.nbuilds;
+  c->stats.dangerous_builds = k.ndanger;
+  c->stats.last_extrusion_shifts = k.le_count[0]; c->stats.last_unloads = k.le_count[1]; c->stats.last_loads = k.le_count[2];
+  c->stats.extrusion_shifts = k.le_count[4]; c->stats.unloads = k.le_count[5]; c->stats.loads = k.le_count[6];
+  if (c->topo_loaded) c->nbonds = k.nbonds;
+  if (k.err) {
+    int code = k.err;
+    int info[4] = {k.err_info[0], k.err_info[1], k.err_info[2], k.err_info[3]};
+    cudaMemsetAsync(&c->d.ctrl->err, 0, sizeof(int), c->stream);
+    cudaStreamSynchronize(c->stream);
+    return fail(c, LE_ERUN, "%s (%d %d %d %d)", derr_text(code), info[0], info[1], info[2], info[3]);
+  }
+  return LE_OK;
+}
+
+static int ensure_ready(le_ctx *c) {
+  if (!c->atoms_loaded) return fail(c, LE_ESTATE, "no atoms uploaded");
+  cudaSetDevice(c->device);
+  if (!c->topo_loaded) {
+    int r = le_upload_bonds(c, 0, nullptr, nullptr, nullptr);
+    if (r) return r;
+  }
+  return push_params(c);
+}
+
+extern "C" int le_force_rebuild(le_ctx *c) {
+  if (!c) return LE_EINVAL;
+  int r = ensure_ready(c); if (r) return r;
+  enqueue_rebuild(c, 0);
+  c->lists_valid = true;
+  return sync_and_check(c);
+}
+
+static void thermo_from_slot(le_ctx *c, const double *s, int64_t step, le_thermo *t) {
+  const double n = (double)c->N;
+  const double dof = 3.0 * n - 3.0;                          // compute temp, extra_dof = 3
+  double vol = 1.0;
+  for (int k = 0; k < 3; k++) vol *= c->hi[k] - c->lo[k];
+  memset(t, 0, sizeof *t);
+  t->step = step;
+  t->ke = 0.5 * s[0];
+  t->temp = dof > 0 ? s[0] / dof : 0.0;                      // ComputeTemp::compute_scalar, boltz = mvv2e = 1
+  t->epair = s[1] / n;
+  t->emol = s[2] / n;
+  t->etotal = (0.5 * s[0] + s[1] + s[2]) / n;
+  for (int k = 0; k < 6; k++) t->virial[k] = s[3 + k];
+  t->press = (s[0] + s[3] + s[4] + s[5]) / (3.0 * vol);     // ComputePressure::compute_scalar, nktv2p = 1
+  t->fene_warnings = (int64_t)llround(s[9]);
+  t->nbonds = c->nbonds;
+}
+
+static void launch_step(le_ctx *c, const StepArgs &a) {
+  const int grid = grid_for(c->N, 256);
+  if (a.ev) LAUNCH(c, k_step<1>, grid, 256, c->d, a);
+  else LAUNCH(c, k_step<0>, grid, 256, c->d, a);
+}
+
+static float tsqrt_at(le_ctx *c, int64_t step, int64_t begin, int64_t end) {
+  double delta = (double)(step - begin);
+  if (delta != 0.0) delta /= (double)(end - begin);
+  const double t = c->t_start + delta * (c->t_stop - c->t_start);
+  return (float)sqrt(t);
+}
+
+extern "C" int le_compute_forces(le_ctx *c, double *f, le_thermo *out) {
+  if (!c) return LE_EINVAL;
+  int r = ensure_ready(c); if (r) return r;
+  enqueue_rebuild(c, 0);
+  c->lists_valid = true;
+  CK(cudaMemsetAsync(c->d.thermo, 0, sizeof(double) * LE_THERMO_W, c->stream));
+  StepArgs a; memset(&a, 0, sizeof a);
+  a.rd = c->cur; a.ev = 1; a.slot = 0; a.write_force = 1;
+  launch_step(c, a);
+  CK(cudaMemcpyAsync(c->h_thermo, c->d.thermo, sizeof(double) * LE_THERMO_W, cudaMemcpyDeviceToHost, c->stream));
+  r = sync_and_check(c); if (r) return r;
+  if (out) thermo_from_slot(c, c->h_thermo, c->ntimestep, out);
+  if (f) {
+    CK(cudaMemcpyAsync(f, c->d.fout, sizeof(double) * 3 * c->N, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return LE_OK;
+}
+
+#include "le_fix_host.inl"
+
+extern "C" int le_run(le_ctx *c, int64_t nsteps) {
+  if (!c || nsteps < 0) return LE_EINVAL;
+  int r = ensure_ready(c); if (r) return r;
+  if (!c->nve_on && nsteps > 0) return fail(c, LE_ESTATE, "no integrator: define fix nve before run");
+  Dev &d = c->d;
+  const int64_t begin = c->ntimestep, end = begin + nsteps;
+  // Verlet::setup: full rebuild, then forces at the current positions
+  enqueue_rebuild(c, 0);
+  c->lists_valid = true;
+  int used_slots = 0;
+  std::vector<int64_t> slot_step;
+  auto want_thermo = [&](int64_t s) { return s == begin || s == end || (c->thermo_every > 0 && s % c->thermo_every == 0); };
+  auto flush_thermo = [&]() -> int {
+    if (!used_slots) return LE_OK;
+    CK(cudaMemcpyAsync(c->h_thermo, d.thermo, sizeof(double) * LE_THERMO_W * used_slots, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < used_slots; k++) {
+      le_thermo t; thermo_from_slot(c, c->h_thermo + (size_t)k * LE_THERMO_W, slot_step[k], &t);
+      c->thermo.push_back(t);
+    }
+    used_slots = 0; slot_step.clear();
+    return LE_OK;
+  };
+  CK(cudaMemsetAsync(d.thermo, 0, sizeof(double) * LE_THERMO_W * THERMO_SLOTS, c->stream));
+  CK(cudaEventRecord(c->ev0, c->stream));
+  for (int64_t s = begin; s <= end; s++) {
+    StepArgs a; memset(&a, 0, sizeof a);
+    a.rd = c->cur;
+    a.do_final = (s > begin);
+    a.do_initial = (s < end);
+    a.langevin = c->langevin_on;
+    a.step_lo = (unsigned)(s & 0xffffffffu); a.step_hi = (unsigned)((uint64_t)s >> 32);
+    a.tsqrt = tsqrt_at(c, s, begin, end > begin ? end : begin + 1);
+    if (want_thermo(s)) {
+      if (used_slots == THERMO_SLOTS) {
+        r = flush_thermo(); if (r) return r;
+        CK(cudaMemsetAsync(d.thermo, 0, sizeof(double) * LE_THERMO_W * THERMO_SLOTS, c->stream));
+      }
+      a.ev = 1; a.slot = used_slots++; slot_step.push_back(s);
+    }
+    launch_step(c, a);
+    if (s < end) {
+      c->cur ^= 1;
+      const int64_t next = s + 1;
+      // Modify::post_integrate: the USER-LE fixes, in definition order extrusion / unload / load
+      r = enqueue_le_events(c, next); if (r) return r;
+      LAUNCH(c, k_decide, 1, 1, d);
+      enqueue_rebuild(c, 1);
+    }
+  }
+  CK(cudaEventRecord(c->ev1, c->stream));
+  c->ntimestep = end;
+  c->stats.steps += nsteps;
+  r = flush_thermo(); if (r) return r;
+  r = sync_and_check(c); if (r) return r;
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+  c->stats.last_run_gpu_ms = ms;
+  return LE_OK;
+}
+
+// ---- results ----------------------------------------------------------------------------------------
+extern "C" int le_natoms(const le_ctx *c) { return c ? c->N : 0; }
+extern "C" int64_t le_timestep(const le_ctx *c) { return c ? c->ntimestep : 0; }
+
+extern "C" int le_download_x(le_ctx *c, double *x, int *image) {
+  if (!c) return LE_EINVAL;
+  if (!c->atoms_loaded) return fail(c, LE_ESTATE, "no atoms");
+  cudaSetDevice(c->device);
+  const int n = c->N;
+  std::vector<int4> hp(n); std::vector<float4> hv(n); std::vector<int> himg(n);
+  CK(cudaMemcpyAsync(hp.data(), c->d.pos[c->cur], sizeof(int4) * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(hv.data(), c->d.vel, sizeof(float4) * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(himg.data(), c->d.img, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  const double two32 = 4294967296.0;
+  for (int k = 0; k < n; k++) {
+    const int t = h_float_as_int(hv[k].w) - 1;
+    const unsigned u[3] = {(unsigned)hp[k].x, (unsigned)hp[k].y, (unsigned)hp[k].z};
+    if (x) for (int q = 0; q < 3; q++) {
+      const double scale = (c->hi[q] - c->lo[q]) / two32;
+      x[3 * t + q] = c->lo[q] + (double)u[q] * scale;
+    }
+    if (image) image[t] = himg[k];
+  }
+  return LE_OK;
+}
+
+extern "C" int le_download_v(le_ctx *c, double *v) {
+  if (!c || !v) return LE_EINVAL;
+  if (!c->atoms_loaded) return fail(c, LE_ESTATE, "no atoms");
+  cudaSetDevice(c->device);
+  const int n = c->N;
+  std::vector<float4> hv(n);
+  CK(cudaMemcpyAsync(hv.data(), c->d.vel, sizeof(float4) * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < n; k++) {
+    const int t = h_float_as_int(hv[k].w) - 1;
+    v[3 * t] = hv[k].x; v[3 * t + 1] = hv[k].y; v[3 * t + 2] = hv[k].z;
+  }
+  return LE_OK;
+}
+
+extern "C" int le_download_types(le_ctx *c, int *type) {
+  if (!c || !type) return LE_EINVAL;
+  if (!c->atoms_loaded) return fail(c, LE_ESTATE, "no atoms");
+  cudaSetDevice(c->device);
+  const int n = c->N;
+  std::vector<int4> hp(n); std::vector<float4> hv(n);
+  CK(cudaMemcpyAsync(hp.data(), c->d.pos[c->cur], sizeof(int4) * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(hv.data(), c->d.vel, sizeof(float4) * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int k = 0; k < n; k++) type[h_float_as_int(hv[k].w) - 1] = (hp[k].w & 0xff) + 1;
+  return LE_OK;
+}
+
+extern "C" int le_download_topology(le_ctx *c, int *num_bond, int *bond_type, int *bond_atom, int *nspecial, int *special) {
+  if (!c) return LE_EINVAL;
+  if (!c->atoms_loaded) return fail(c, LE_ESTATE, "no atoms");
+  cudaSetDevice(c->device);
+  const size_t n = c->N;
+  if (num_bond) CK(cudaMemcpyAsync(num_bond, c->d.num_bond, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+  if (bond_type) CK(cudaMemcpyAsync(bond_type, c->d.bond_type, sizeof(int) * n * c->bpa, cudaMemcpyDeviceToHost, c->stream));
+  if (bond_atom) CK(cudaMemcpyAsync(bond_atom, c->d.bond_atom, sizeof(int) * n * c->bpa, cudaMemcpyDeviceToHost, c->stream));
+  if (nspecial) CK(cudaMemcpyAsync(nspecial, c->d.nspecial, sizeof(int) * n * 3, cudaMemcpyDeviceToHost, c->stream));
+  if (special) CK(cudaMemcpyAsync(special, c->d.special, sizeof(int) * n * c->maxspecial, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return LE_OK;
+}
+
+extern "C" int le_download_neighlist(le_ctx *c, int half, int64_t *offsets, int *entries, int64_t *nentries) {
+  if (!c) return LE_EINVAL;
+  if (!c->lists_valid) return fail(c, LE_ESTATE, "no neighbor list has been built yet");
+  cudaSetDevice(c->device);
+  const int n = c->N;
+  std::vector<unsigned> cnt(n); std::vector<float4> hv(n); std::vector<int> hmap;
+  int r = fetch_map(c, hmap); if (r) return r;
+  CK(cudaMemcpyAsync(cnt.data(), c->d.counts, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(hv.data(), c->d.vel, sizeof(float4) * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  int maxc = 0; int64_t tot = 0;
+  for (int k = 0; k < n; k++) {
+    const int cc = half ? (cnt[k] >> 8) & 0xff : cnt[k] & 0xff;
+    maxc = std::max(maxc, (int)(cnt[k] & 0xff)); tot += cc;
+  }
+  if (nentries) *nentries = tot;
+  if (!entries || !offsets) return LE_OK;
+  std::vector<unsigned> rows((size_t)std::max(maxc, 1) * n);
+  CK(cudaMemcpyAsync(rows.data(), c->d.neigh, sizeof(unsigned) * (size_t)maxc * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  int64_t o = 0;
+  for (int t = 0; t < n; t++) {
+    const int k = hmap[t];
+    offsets[t] = o;
+    const int cc = half ? (cnt[k] >> 8) & 0xff : cnt[k] & 0xff;
+    for (int q = 0; q < cc; q++) {
+      const unsigned e = rows[(size_t)q * n + k];
+      const int tj = h_float_as_int(hv[e & NEIGH_IDX_MASK].w);
+      entries[o++] = tj | (int)((e >> 30) << 30);
+    }
+  }
+  offsets[n] = o;
+  return LE_OK;
+}
+
+extern "C" int le_download_bondlist(le_ctx *c, int *rows, int64_t *nrows) {
+  if (!c) return LE_EINVAL;
+  if (!c->lists_valid) return fail(c, LE_ESTATE, "no bond list has been built yet");
+  cudaSetDevice(c->device);
+  const size_t n = c->N; const int bpa = c->bpa;
+  std::vector<int> nb(n), bt(n * bpa), ba(n * bpa); std::vector<unsigned char> cross(n * bpa);
+  CK(cudaMemcpyAsync(nb.data(), c->d.num_bond, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(bt.data(), c->d.bond_type, sizeof(int) * n * bpa, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(ba.data(), c->d.bond_atom, sizeof(int) * n * bpa, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(cross.data(), c->d.bond_cross, n * bpa, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  int64_t o = 0;
+  for (size_t i = 0; i < n; i++)
+    for (int m = 0; m < nb[i]; m++) {
+      const int p = ba[i * bpa + m];
+      // NTopoBondAll::build with newton_bond off: kept iff i < closest_image(partner); a ghost image always is
+      if (cross[i * bpa + m] != 21 || (int)(i + 1) < p) {
+        if (rows) { rows[3 * o] = (int)i + 1; rows[3 * o + 1] = p; rows[3 * o + 2] = bt[i * bpa + m]; }
+        o++;
+      }
+    }
+  if (nrows) *nrows = o;
+  return LE_OK;
+}
+
+extern "C" int le_thermo_count(const le_ctx *c) { return c ? (int)c->thermo.size() : 0; }
+
+extern "C" int le_get_thermo(const le_ctx *c, int index, le_thermo *out) {
+  if (!c || !out) return LE_EINVAL;
+  const int n = (int)c->thermo.size();
+  if (index < 0) index += n;
+  if (index < 0 || index >= n) return LE_EINVAL;
+  *out = c->thermo[index];
+  return LE_OK;
+}
+
+extern "C" int le_get_stats(le_ctx *c, le_stats *out) {
+  if (!c || !out) return LE_EINVAL;
+  if (c->lists_valid) {
+    cudaSetDevice(c->device);
+    unsigned long long *dcount = (unsigned long long *)c->lf.scratch64;
+    CK(cudaMemsetAsync(dcount, 0, 2 * sizeof(unsigned long long), c->stream));
+    LAUNCH(c, k_count_pairs, grid_for(c->N, 256), 256, c->d, dcount);
+    unsigned long long h[2];
+    CK(cudaMemcpyAsync(h, dcount, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->stats.half_pairs = (int64_t)h[0]; c->stats.full_entries = (int64_t)h[1];
+  }
+  *out = c->stats;
+  return LE_OK;
+}
+
+extern "C" int le_compute_rg(le_ctx *c, double *rg) {
+  if (!c || !rg) return LE_EINVAL;
+  const int n = c->N;
+  std::vector<double> x((size_t)n * 3); std::vector<int> im(n);
+  int r = le_download_x(c, x.data(), im.data()); if (r) return r;
+  // ComputeGyration (src/compute_gyration.cpp): mass-weighted, unwrapped coordinates; equal masses assumed per type
+  std::vector<int> ty(n); r = le_download_types(c, ty.data()); if (r) return r;
+  double cm[3] = {0, 0, 0}, mt = 0;
+  std::vector<double> ux((size_t)n * 3);
+  for (int k = 0; k < n; k++) {
+    int ix, iy, iz; unpack_image(im[k], &ix, &iy, &iz);
+    const int ii[3] = {ix, iy, iz};
+    const double m = c->mass[ty[k] - 1];
+    for (int q = 0; q < 3; q++) { ux[3 * k + q] = x[3 * k + q] + ii[q] * (c->hi[q] - c->lo[q]); cm[q] += m * ux[3 * k + q]; }
+    mt += m;
+  }
+  for (int q = 0; q < 3; q++) cm[q] /= mt;
+  double s = 0;
+  for (int k = 0; k < n; k++) {
+    const double m = c->mass[ty[k] - 1];
+    for (int q = 0; q < 3; q++) { const double dd = ux[3 * k + q] - cm[q]; s += m * dd * dd; }
+  }
+  *rg = sqrt(s / mt);
+  return LE_OK;
+}

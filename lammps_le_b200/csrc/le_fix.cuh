@@ -1,0 +1,792 @@
+// le_fix.cuh -- the three USER-LE fixes as device kernels.
+//
+// The reference code (src/USER-LE/fix_extrusion.cpp:256-872, fix_ex_load.cpp:329-655,
+// fix_ex_unload.cpp:172-372) is a set of SEQUENTIAL loops over the bond list / the half neighbor
+// list / the local atoms whose iterations communicate through per-atom scratch (to_add, to_remove,
+// distsq, partner) and which consume one sequential Marsaglia stream.  To stay bit-exact yet
+// parallel we use three facts:
+//   1. the number of draws an iteration consumes depends only on the state BEFORE the loop, so an
+//      exclusive scan gives every iteration its offset into the stream, which is generated in bulk
+//      (k_ranmars_fill: the lag-97/33 recurrence advances 32 values per warp step);
+//   2. every iteration reads and writes scratch only at a few beads around its extruder (its "touch
+//      set"); two iterations whose touch sets are disjoint commute;
+//   3. so the loop is run by an ORDERED EXECUTOR: in rounds, every pending iteration claims its
+//      beads with atomicMin(priority = position in the sequential order); an iteration that holds
+//      all its beads has no earlier pending conflicting iteration and executes.  Extruders are thus
+//      resolved in chain-position order with a neighbor-exclusion pass, deterministically.
+// Everything here is indexed by tag (t-1); positions are reached through the tag map.
+#pragma once
+#include "le_common.cuh"
+#include <vector>
+
+#define LE_EXEC_THREADS 1024
+#define LE_COPYMAX 192
+
+struct RngDev {
+  int s[97];          // ring of the last 97 raw values, 24-bit integers (RanMars::u, src/random_mars.cpp)
+  int head;           // index of the oldest value (the one written 97 draws ago)
+  int c;              // RanMars::c * 2^24
+  long long consumed; // draws handed out so far
+};
+
+struct RngHost { int seeded; int seed; };
+
+struct LeFixDev {
+  int N;
+  int *bondcount, *to_add, *to_remove, *final_add, *final_remove, *partner;
+  double *distsq, *prob;
+  unsigned *claim;
+  int *flag, *scan, *scan2, *ndraw, *tasks, *blocksum;
+  unsigned char *done;
+  int *counters;        // [16] device counters
+  double *draws;
+  int draws_cap;
+  RngDev *rngdev;       // [3]
+  RngHost rng[3];
+  void *scratch64;
+};
+
+struct ExtrusionArgs { int btype, neutral, left, right, lr; double p; };
+struct LoadArgs { int btype, itype, jtype, imax, inew, jmax, jnew; double cutsq, fraction; };
+struct UnloadArgs { int btype; double cutsq, fraction; };
+
+enum { CNT_NTASK = 0, CNT_NDRAW = 1, CNT_NBREAK = 2, CNT_NCREATE = 3, CNT_TOTAL = 4 };
+
+static int le_fix_alloc(LeFixDev &f, int n, int maxspecial, std::vector<void *> &allocs, cudaStream_t st) {
+  f.N = n;
+  auto A = [&](void **p, size_t bytes) -> int {
+    if (cudaMalloc(p, bytes) != cudaSuccess) return -1;
+    cudaMemsetAsync(*p, 0, bytes, st);
+    allocs.push_back(*p);
+    return 0;
+  };
+  const size_t n1 = (size_t)n + 2;
+  int r = 0;
+  r |= A((void **)&f.bondcount, n1 * 4); r |= A((void **)&f.to_add, n1 * 4); r |= A((void **)&f.to_remove, n1 * 4);
+  r |= A((void **)&f.final_add, n1 * 4); r |= A((void **)&f.final_remove, n1 * 4); r |= A((void **)&f.partner, n1 * 4);
+  r |= A((void **)&f.distsq, n1 * 8); r |= A((void **)&f.prob, n1 * 8);
+  r |= A((void **)&f.claim, n1 * 4); r |= A((void **)&f.flag, n1 * 4); r |= A((void **)&f.scan, n1 * 4);
+  r |= A((void **)&f.scan2, n1 * 4); r |= A((void **)&f.ndraw, n1 * 4);
+  r |= A((void **)&f.tasks, n1 * 4); r |= A((void **)&f.blocksum, (n1 / 1024 + 2) * 4);
+  r |= A((void **)&f.done, n1);
+  r |= A((void **)&f.counters, 16 * 4);
+  f.draws_cap = 2 * n + 64;
+  r |= A((void **)&f.draws, (size_t)f.draws_cap * 8);
+  r |= A((void **)&f.rngdev, 3 * sizeof(RngDev));
+  r |= A(&f.scratch64, 64);
+  (void)maxspecial;
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RanMars (src/random_mars.cpp:29-95) in exact 24-bit integer arithmetic.
+//   raw_n = (raw_{n-97} - raw_{n-33}) mod 1;  c_n = c_{n-1} - cd (+cm if negative);  out = (raw_n - c_n) mod 1
+//   every value is a multiple of 2^-24, so the reference's doubles are reproduced exactly.
+// One warp produces 32 consecutive draws per iteration (the shortest lag is 33).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_ranmars_fill(RngDev *st, double *out, const int *n_ptr, int cap, Ctrl *ctrl) {
+  __shared__ int ring[256];   // power-of-two ring holding at least 97+32 values
+  const int lane = threadIdx.x;
+  int n = n_ptr ? *n_ptr : 0;
+  if (n <= 0) return;
+  if (out && n > cap) { if (lane == 0) le_raise(ctrl, LE_DERR_RNG_OVERFLOW, n, cap); return; }
+  // unroll the circular state into chronological order: ring[k] = raw_{base+k}, k = 0..96
+  for (int k = lane; k < 97; k += 32) ring[k] = st->s[(st->head + k) % 97];
+  long long c = st->c;
+  __syncwarp();
+  const long long CD = 7654321, CM = 16777213;
+  int w = 97;                 // next write position (monotone, masked on access)
+  for (int base = 0; base < n; base += 32) {
+    const int a = ring[(w + lane - 97) & 255];
+    const int b = ring[(w + lane - 33) & 255];
+    int raw = a - b;
+    if (raw < 0) raw += 16777216;
+    // c after (base+lane+1) further decrements
+    long long cc = (c - ((long long)(lane + 1) * CD) % CM) % CM;
+    if (cc < 0) cc += CM;
+    int v = raw - (int)cc;
+    if (v < 0) v += 16777216;
+    __syncwarp();
+    ring[(w + lane) & 255] = raw;
+    if (out && base + lane < n) out[base + lane] = (double)v * (1.0 / 16777216.0);
+    __syncwarp();
+    // advance by min(32, remaining): only whole batches except possibly the last
+    const int adv = min(32, n - base);
+    c = (c - ((long long)adv * CD) % CM) % CM;
+    if (c < 0) c += CM;
+    w += adv;
+    if (adv < 32) break;
+  }
+  __syncwarp();
+  // store the last 97 raw values back, oldest first
+  for (int k = lane; k < 97; k += 32) st->s[k] = ring[(w - 97 + k) & 255];
+  if (lane == 0) { st->head = 0; st->c = (int)c; st->consumed += n; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic exclusive scan over n ints (three launches) and flag compaction
+// ------------------------------------------------------------------------------------------------
+__global__ void k_iscan_partial(const int *in, int n, int *blocksum) {
+  __shared__ int sh[32];
+  const int idx = blockIdx.x * 1024 + threadIdx.x;
+  int s = (idx < n) ? in[idx] : 0;
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int t = sh[threadIdx.x];
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) blocksum[blockIdx.x] = t;
+  }
+}
+__global__ void k_iscan_blocks(int *blocksum, int nblocks, int *total) {
+  __shared__ int sh[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += 1024) {
+    const int idx = base + threadIdx.x;
+    const int v = (idx < nblocks) ? blocksum[idx] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      int t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (idx < nblocks) blocksum[idx] = carry + sh[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += sh[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total) *total = carry;
+}
+__global__ void k_iscan_apply(const int *in, int *out, int n, const int *blocksum) {
+  __shared__ int sh[1024];
+  const int idx = blockIdx.x * 1024 + threadIdx.x;
+  const int v = (idx < n) ? in[idx] : 0;
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    int t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
+    __syncthreads();
+    sh[threadIdx.x] += t;
+    __syncthreads();
+  }
+  if (idx < n) out[idx] = blocksum[blockIdx.x] + sh[threadIdx.x] - v;
+}
+// tasks[scan[i]] = i for flagged i (flag value > 0)
+__global__ void k_compact(const int *flag, const int *scan, int n, int *tasks) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (flag[i] > 0) tasks[scan[i]] = i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// helpers: tag-indexed access to the live state
+// ------------------------------------------------------------------------------------------------
+struct LeView {
+  Dev d; LeFixDev f; int cur;
+};
+
+// the coordinate the reference holds for an OWNED atom between reneighborings: wrapped at the last
+// rebuild (Domain::pbc runs only then, src/verlet.cpp:272), drifting freely since
+__device__ __forceinline__ void raw_xyz(const LeView &V, int tag, double x[3]) {
+  const int k = V.d.map[tag - 1];
+  const int4 p = V.d.pos[V.cur][k];
+  const int im = V.d.img[k], ih = V.d.img_hold[k];
+  const unsigned u[3] = {(unsigned)p.x, (unsigned)p.y, (unsigned)p.z};
+  const int di[3] = {(im & 1023) - (ih & 1023), ((im >> 10) & 1023) - ((ih >> 10) & 1023), ((im >> 20) & 1023) - ((ih >> 20) & 1023)};
+#pragma unroll
+  for (int q = 0; q < 3; q++) {
+    double v = le_deq(u[q], q);
+    if (di[q]) v = __dadd_rn(v, (double)di[q] * c_P.L[q]);
+    x[q] = v;
+  }
+}
+__device__ __forceinline__ double dist2(const double a[3], const double b[3]) {
+  const double dx = __dsub_rn(a[0], b[0]), dy = __dsub_rn(a[1], b[1]), dz = __dsub_rn(a[2], b[2]);
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+__device__ __forceinline__ int type_of(const LeView &V, int tag) {
+  return (V.d.pos[V.cur][V.d.map[tag - 1]].w & 0xff) + 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ordered executor (one block).  Task must provide:
+//   int  ntasks;  unsigned prio(int k);  int beads(int k, int b[4]) (tag-1 indices, may repeat);
+//   void exec(int k)
+// ------------------------------------------------------------------------------------------------
+template <class Task>
+__device__ void ordered_execute(Task &T, unsigned *claim, unsigned char *done) {
+  __shared__ int remaining;
+  const int n = T.ntasks();
+  for (int k = threadIdx.x; k < n; k += blockDim.x) done[k] = 0;
+  __syncthreads();
+  for (int round = 0; round <= n; round++) {
+    if (threadIdx.x == 0) remaining = 0;
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+      if (done[k]) continue;
+      int b[4];
+      const int nb = T.beads(k, b);
+      const unsigned pr = T.prio(k);
+      for (int q = 0; q < nb; q++) atomicMin(&claim[b[q]], pr);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+      if (done[k]) continue;
+      int b[4];
+      const int nb = T.beads(k, b);
+      const unsigned pr = T.prio(k);
+      bool mine = true;
+      for (int q = 0; q < nb; q++) mine = mine && (claim[b[q]] == pr);
+      if (mine) { T.exec(k); done[k] = 1; }
+      else remaining = 1;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+      if (done[k] == 2) continue;
+      int b[4];
+      const int nb = T.beads(k, b);
+      for (int q = 0; q < nb; q++) claim[b[q]] = 0xffffffffu;
+      if (done[k] == 1) done[k] = 2;
+    }
+    __syncthreads();
+    if (!remaining) break;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared pieces: bond count, slot deletion, special-list edits (identical in the three fixes)
+// ------------------------------------------------------------------------------------------------
+// delete the first slot of atom t whose partner is p (fix_extrusion.cpp:656-668, fix_ex_unload.cpp:293-302)
+__device__ __forceinline__ void delete_bond_slot(const Dev &d, int t, int p) {
+  int *ba = d.bond_atom + (size_t)(t - 1) * d.bpa, *bt = d.bond_type + (size_t)(t - 1) * d.bpa;
+  const int nb = d.num_bond[t - 1];
+  for (int m = 0; m < nb; m++) {
+    if (ba[m] == p) {
+      for (int k = m; k < nb - 1; k++) { ba[k] = ba[k + 1]; bt[k] = bt[k + 1]; }
+      d.num_bond[t - 1] = nb - 1;
+      break;
+    }
+  }
+}
+// remove p from the 1-2 part of t's special list (fix_extrusion.cpp:673-683)
+__device__ __forceinline__ void special_remove12(const Dev &d, int t, int p) {
+  int *sl = d.special + (size_t)(t - 1) * d.maxspecial;
+  int *ns = d.nspecial + (size_t)(t - 1) * 3;
+  const int n1 = ns[0], n3 = ns[2];
+  int m;
+  for (m = 0; m < n1; m++) if (sl[m] == p) break;
+  for (; m < n3 - 1; m++) sl[m] = sl[m + 1];
+  ns[0]--; ns[1]--; ns[2]--;
+}
+// make p a 1-2 neighbor of t (fix_extrusion.cpp:748-771, fix_ex_load.cpp:570-588)
+__device__ __forceinline__ void special_insert12(const Dev &d, int t, int p) {
+  int *sl = d.special + (size_t)(t - 1) * d.maxspecial;
+  int *ns = d.nspecial + (size_t)(t - 1) * 3;
+  int n1 = ns[0], n2 = ns[1], n3 = ns[2];
+  int m;
+  for (m = n1; m < n3; m++) if (sl[m] == p) break;
+  if (m < n3) {
+    for (int n = m; n < n3 - 1; n++) sl[n] = sl[n + 1];
+    n3--;
+    if (m < n2) n2--;
+  }
+  if (n3 == d.maxspecial) { le_raise(d.ctrl, LE_DERR_SPECIAL_OVERFLOW, t, p); return; }
+  for (m = n3; m > n1; m--) sl[m] = sl[m - 1];
+  sl[n1] = p;
+  ns[0] = n1 + 1; ns[1] = n2 + 1; ns[2] = n3 + 1;
+}
+
+// FixExtrusion::dedup (fix_extrusion.cpp:1116-1135)
+__device__ __forceinline__ int le_dedup(int nstart, int nstop, int *copy) {
+  int m = nstart;
+  while (m < nstop) {
+    int i;
+    for (i = 0; i < m; i++)
+      if (copy[i] == copy[m]) { copy[m] = copy[nstop - 1]; nstop--; break; }
+    if (i == m) m++;
+  }
+  return nstop;
+}
+
+// rebuild_special_one (fix_extrusion.cpp:1045-1108): 1-3 = 1-2 of 1-2, 1-4 = 1-2 of 1-3
+__device__ void rebuild_special_one(const Dev &d, int t) {
+  int copy[LE_COPYMAX];
+  int *sl = d.special + (size_t)(t - 1) * d.maxspecial;
+  int *ns = d.nspecial + (size_t)(t - 1) * 3;
+  const int cn1 = ns[0];
+  for (int i = 0; i < cn1; i++) copy[i] = sl[i];
+  int cn2 = cn1;
+  for (int i = 0; i < cn1; i++) {
+    const int n = copy[i];
+    const int *s2 = d.special + (size_t)(n - 1) * d.maxspecial;
+    const int m1 = d.nspecial[(size_t)(n - 1) * 3];
+    for (int j = 0; j < m1; j++)
+      if (s2[j] != t) { if (cn2 >= LE_COPYMAX) { le_raise(d.ctrl, LE_DERR_SPECIAL_OVERFLOW, t, cn2); return; } copy[cn2++] = s2[j]; }
+  }
+  cn2 = le_dedup(cn1, cn2, copy);
+  if (cn2 > d.maxspecial) { le_raise(d.ctrl, LE_DERR_SPECIAL_OVERFLOW, t, cn2); return; }
+  int cn3 = cn2;
+  for (int i = cn1; i < cn2; i++) {
+    const int n = copy[i];
+    const int *s2 = d.special + (size_t)(n - 1) * d.maxspecial;
+    const int m1 = d.nspecial[(size_t)(n - 1) * 3];
+    for (int j = 0; j < m1; j++)
+      if (s2[j] != t) { if (cn3 >= LE_COPYMAX) { le_raise(d.ctrl, LE_DERR_SPECIAL_OVERFLOW, t, cn3); return; } copy[cn3++] = s2[j]; }
+  }
+  cn3 = le_dedup(cn2, cn3, copy);
+  if (cn3 > d.maxspecial) { le_raise(d.ctrl, LE_DERR_SPECIAL_OVERFLOW, t, cn3); return; }
+  // the 1-2 part is unchanged (and is being read by other threads): write only tiers 2 and 3
+  ns[1] = cn2; ns[2] = cn3;
+  for (int i = cn1; i < cn3; i++) sl[i] = copy[i];
+}
+
+// update_topology sweeps (fix_extrusion.cpp:924-1002, fix_ex_load.cpp:700-751, fix_ex_unload.cpp:417-463).
+// mode 0: broken bonds, marks = final_remove: influenced if endpoint, or BOTH ends of one broken bond are in
+//         the full special list;  mode 1: created bonds, marks = final_add: endpoint, or EITHER end among 1-2/1-3.
+__global__ void k_le_topo_sweep(Dev d, const int *marks, int mode, const int *gate) {
+  if (gate && *gate == 0) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) {
+    const int t = i + 1;
+    bool infl = marks[i] != 0;
+    if (!infl) {
+      const int *sl = d.special + (size_t)i * d.maxspecial;
+      if (mode == 0) {
+        const int n = d.nspecial[(size_t)i * 3 + 2];
+        for (int k = 0; k < n && !infl; k++) {
+          const int s = sl[k];
+          const int p = marks[s - 1];
+          if (p == 0) continue;
+          int found = 0;
+          for (int q = 0; q < n; q++) if (sl[q] == s || sl[q] == p) found++;
+          if (found == 2) infl = true;
+        }
+      } else {
+        const int n = d.nspecial[(size_t)i * 3 + 1];
+        for (int k = 0; k < n; k++) if (marks[sl[k] - 1] != 0) { infl = true; break; }
+      }
+    }
+    if (infl) rebuild_special_one(d, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fix extrusion
+// ------------------------------------------------------------------------------------------------
+// E0a: recount bondcount, clear scratch (fix_extrusion.cpp:281-295,339-348)
+__global__ void k_ext_init(LeView V, int btype) {
+  const Dev &d = V.d; const LeFixDev &f = V.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) {
+    int bc = 0;
+    const int nb = d.num_bond[i];
+    for (int m = 0; m < nb; m++) if (d.bond_type[(size_t)i * d.bpa + m] == btype) bc++;
+    if (bc > 1) le_raise(d.ctrl, LE_DERR_BONDCOUNT, i + 1, bc);
+    f.bondcount[i] = bc;
+    f.to_add[i] = 0; f.to_remove[i] = 0; f.final_add[i] = 0; f.final_remove[i] = 0;
+    f.distsq[i] = LE_BIG; f.claim[i] = 0xffffffffu; f.partner[i] = 0;
+    if (i < 16) f.counters[i] = 0;
+  }
+}
+
+// side test of the candidate pass; returns whether the clauses before the random draws hold and how many
+// draws the reference's short-circuit chain consumes (fix_extrusion.cpp:406-416 / :420-429)
+__device__ __forceinline__ bool ext_side_base(const LeView &V, const ExtrusionArgs &A, int bead, int barrier, int &ndraw) {
+  ndraw = 0;
+  if (bead < 1 || bead > V.d.N) return false;
+  const int nb = V.d.num_bond[bead - 1], bc = V.f.bondcount[bead - 1];
+  if (!(nb - bc == 2 && bc == 0)) return false;
+  const int ty = type_of(V, bead);
+  if (!(ty == A.left || ty == A.right || ty == A.lr || ty == A.neutral)) return false;
+  if (ty == barrier || ty == A.lr) ndraw = 1;
+  return true;
+}
+
+// E0b: which atoms own a bondlist visit of an extruder, and how many draws that visit consumes
+__global__ void k_ext_visits(LeView V, ExtrusionArgs A) {
+  const Dev &d = V.d; const LeFixDev &f = V.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) {
+    int visit = 0, nd = 0;
+    const int nb = d.num_bond[i];
+    for (int m = 0; m < nb; m++) {
+      if (d.bond_type[(size_t)i * d.bpa + m] != A.btype) continue;
+      const int p = d.bond_atom[(size_t)i * d.bpa + m];
+      // NTopoBondAll::build, newton_bond off: listed from atom i iff i < closest image of p
+      if (!(d.bond_cross[(size_t)i * d.bpa + m] != 21 || (i + 1) < p)) continue;
+      const int a = min(i + 1, p), b = max(i + 1, p);
+      const int nba = d.num_bond[a - 1], nbb = d.num_bond[b - 1];
+      if (nba == 1 || nbb == 1 || nba == 0 || nbb == 0 || f.bondcount[a - 1] != 1 || f.bondcount[b - 1] != 1) continue;
+      visit = 1;
+      int n1, n2;
+      ext_side_base(V, A, a - 1, A.left, n1);
+      ext_side_base(V, A, b + 1, A.right, n2);
+      nd = n1 + n2;
+      f.partner[i] = p;   // remembered for the executor
+      break;              // bondcount <= 1: at most one extruder slot
+    }
+    f.flag[i] = visit;
+    f.ndraw[i] = nd;
+  }
+}
+
+struct VisitTask {
+  LeView V; ExtrusionArgs A; const int *ntask_ptr;
+  __device__ int ntasks() const { return *ntask_ptr; }
+  __device__ unsigned prio(int k) const { return (unsigned)V.f.tasks[k]; }
+  __device__ int beads(int k, int b[4]) const {
+    const int i = V.f.tasks[k];
+    const int p = V.f.partner[i];
+    const int lo = min(i + 1, p), hi = max(i + 1, p);
+    int n = 0;
+    if (lo - 1 >= 1) b[n++] = lo - 2;
+    b[n++] = lo - 1; b[n++] = hi - 1;
+    if (hi + 1 <= V.d.N) b[n++] = hi;
+    return n;
+  }
+  __device__ void exec(int k) {
+    const Dev &d = V.d; const LeFixDev &f = V.f;
+    const int i = f.tasks[k];
+    const int p = f.partner[i];
+    const int a = min(i + 1, p), b = max(i + 1, p);       // tags of i1 < i2
+    const int L = a - 1, R = b + 1;
+    int off = f.scan2[i];   // exclusive scan of the per-visit draw counts = position in the stream
+    int n1, n2;
+    bool okL = ext_side_base(V, A, L, A.left, n1);
+    if (okL && n1) okL = A.p > f.draws[off++];
+    bool okR = ext_side_base(V, A, R, A.right, n2);
+    if (okR && n2) okR = A.p > f.draws[off++];
+    double xa[3], xb[3];
+    if (okL && okR) {
+      raw_xyz(V, L, xa); raw_xyz(V, R, xb);
+      const double rsq = dist2(xa, xb);
+      if (rsq >= f.distsq[L - 1] && rsq >= f.distsq[R - 1]) return;
+      if (rsq < f.distsq[L - 1]) { f.distsq[L - 1] = rsq; f.to_add[L - 1] = R; }
+      if (rsq < f.distsq[R - 1]) { f.distsq[R - 1] = rsq; f.to_add[R - 1] = L; }
+      f.to_remove[a - 1] = b; f.to_remove[b - 1] = a;
+    } else if (okL) {
+      raw_xyz(V, L, xa); raw_xyz(V, b, xb);
+      const double rsq = dist2(xa, xb);
+      if (rsq >= f.distsq[L - 1]) return;
+      f.distsq[L - 1] = rsq; f.to_add[L - 1] = b;
+      if (f.distsq[b - 1] == LE_BIG) { f.distsq[b - 1] = rsq; f.to_add[b - 1] = L; }
+      f.to_remove[a - 1] = b; f.to_remove[b - 1] = a;
+    } else if (okR) {
+      raw_xyz(V, a, xa); raw_xyz(V, R, xb);
+      const double rsq = dist2(xa, xb);
+      if (rsq >= f.distsq[R - 1]) return;
+      if (f.distsq[a - 1] == LE_BIG) { f.distsq[a - 1] = rsq; f.to_add[a - 1] = R; }
+      f.distsq[R - 1] = rsq; f.to_add[R - 1] = a;
+      f.to_remove[a - 1] = b; f.to_remove[b - 1] = a;
+    }
+  }
+};
+
+__global__ void __launch_bounds__(LE_EXEC_THREADS) k_ext_candidates(LeView V, ExtrusionArgs A, const int *ntask) {
+  VisitTask T{V, A, ntask};
+  ordered_execute(T, V.f.claim, V.f.done);
+}
+
+// flag the atoms the next sequential pass iterates over
+__global__ void k_ext_flag(LeView V, int which) {   // which 0: to_add != 0, 1: to_remove != 0
+  const Dev &d = V.d; const LeFixDev &f = V.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x)
+    f.flag[i] = (which == 0 ? f.to_add[i] : f.to_remove[i]) != 0;
+}
+
+// reconciliation of proposals that lost a contest (fix_extrusion.cpp:517-599)
+struct ReconcileTask {
+  LeView V; const int *ntask_ptr;
+  __device__ int ntasks() const { return *ntask_ptr; }
+  __device__ unsigned prio(int k) const { return (unsigned)V.f.tasks[k]; }
+  __device__ void bounds(int k, int &ti, int &tj, int &lb, int &rb, bool &left) const {
+    ti = V.f.tasks[k] + 1; tj = V.f.to_add[ti - 1];
+    if (ti < tj) { lb = ti + 1; rb = tj - 1; left = true; } else { lb = tj + 1; rb = ti - 1; left = false; }
+  }
+  __device__ int beads(int k, int b[4]) const {
+    int ti, tj, lb, rb; bool left; bounds(k, ti, tj, lb, rb, left);
+    b[0] = ti - 1; b[1] = tj - 1; b[2] = lb - 1; b[3] = rb - 1;
+    return 4;
+  }
+  __device__ void exec(int k) {
+    const LeFixDev &f = V.f;
+    int ti, tj, lb, rb; bool left; bounds(k, ti, tj, lb, rb, left);
+    if (f.to_add[tj - 1] == ti) return;   // reciprocated: nothing to undo
+    int *tr = f.to_remove;
+    if (left) {
+      if (lb == tr[rb - 1] && tr[lb - 1] == rb) { tr[lb - 1] = 0; tr[rb - 1] = 0; }
+      else if (ti == tr[rb - 1] && tr[ti - 1] == rb) { tr[ti - 1] = 0; tr[rb - 1] = 0; }
+      else if (lb == tr[tj - 1] && tr[lb - 1] == tj) { tr[lb - 1] = 0; tr[tj - 1] = 0; }
+      else if (ti == tr[tj - 1] && tj == tr[ti - 1]) { tr[ti - 1] = 0; tr[tj - 1] = 0; }
+    } else {
+      if (lb == tr[rb - 1] && tr[lb - 1] == rb) { tr[lb - 1] = 0; tr[rb - 1] = 0; }
+      else if (ti == tr[lb - 1] && tr[ti - 1] == lb) { tr[ti - 1] = 0; tr[lb - 1] = 0; }
+      else if (rb == tr[tj - 1] && tr[rb - 1] == tj) { tr[rb - 1] = 0; tr[tj - 1] = 0; }
+      else if (ti == tr[tj - 1] && tj == tr[ti - 1]) { tr[ti - 1] = 0; tr[tj - 1] = 0; }
+    }
+  }
+};
+__global__ void __launch_bounds__(LE_EXEC_THREADS) k_ext_reconcile(LeView V, const int *ntask) {
+  ReconcileTask T{V, ntask};
+  ordered_execute(T, V.f.claim, V.f.done);
+}
+
+// break loop (fix_extrusion.cpp:618-692)
+struct BreakTask {
+  LeView V; const int *ntask_ptr;
+  __device__ int ntasks() const { return *ntask_ptr; }
+  __device__ unsigned prio(int k) const { return (unsigned)V.f.tasks[k]; }
+  __device__ int beads(int k, int b[4]) const {
+    const int ti = V.f.tasks[k] + 1, r = V.f.to_remove[ti - 1];
+    const int lb = min(ti, r), rb = max(ti, r);
+    int n = 0;
+    if (lb - 1 >= 1) b[n++] = lb - 2;
+    b[n++] = lb - 1; b[n++] = rb - 1;
+    if (rb + 1 <= V.d.N) b[n++] = rb;
+    return n;
+  }
+  __device__ int ta(int tag) const { return (tag >= 1 && tag <= V.d.N) ? V.f.to_add[tag - 1] : 0; }
+  __device__ void exec(int k) {
+    const Dev &d = V.d; const LeFixDev &f = V.f;
+    const int ti = f.tasks[k] + 1, r = f.to_remove[ti - 1];
+    if (f.to_remove[r - 1] != ti) return;
+    const int lb = min(ti, r), rb = max(ti, r);
+    if (ta(lb - 1) == rb && ta(rb) == lb - 1 && ta(lb) == rb + 1 && ta(rb + 1) == lb) {
+      f.to_add[lb - 2] = rb + 1; f.to_add[rb] = lb - 1; f.to_add[lb - 1] = 0; f.to_add[rb - 1] = 0;
+    }
+    if ((ta(lb - 1) == rb && ta(rb) == lb - 1) || (ta(lb - 1) == rb + 1 && ta(rb + 1) == lb - 1) ||
+        (ta(lb) == rb + 1 && ta(rb + 1) == lb)) {
+      delete_bond_slot(d, ti, r);
+      special_remove12(d, ti, r);
+      f.final_remove[ti - 1] = r; f.final_remove[r - 1] = ti;
+      if (ti < r) atomicAdd(&f.counters[CNT_NBREAK], 1);
+    }
+  }
+};
+__global__ void __launch_bounds__(LE_EXEC_THREADS) k_ext_break(LeView V, const int *ntask) {
+  BreakTask T{V, ntask};
+  ordered_execute(T, V.f.claim, V.f.done);
+}
+
+// create loop (fix_extrusion.cpp:699-786); iterations are independent
+__global__ void k_ext_create(LeView V, int btype) {
+  const Dev &d = V.d; const LeFixDev &f = V.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) {
+    const int ti = i + 1, tj = f.to_add[i];
+    if (tj == 0) continue;
+    if (f.to_add[tj - 1] != ti) continue;
+    if (d.num_bond[i] == d.bpa) continue;
+    const int lb = min(ti, tj), rb = max(ti, tj);
+    auto tr = [&](int tag) { return (tag >= 1 && tag <= d.N) ? f.to_remove[tag - 1] : 0; };
+    if ((tr(lb + 1) == rb && tr(rb) == lb + 1) || (tr(lb + 1) == rb - 1 && tr(rb - 1) == lb + 1) ||
+        (tr(lb) == rb - 1 && tr(rb - 1) == lb)) {
+      const int nb = d.num_bond[i];
+      d.bond_type[(size_t)i * d.bpa + nb] = btype;
+      d.bond_atom[(size_t)i * d.bpa + nb] = tj;
+      d.num_bond[i] = nb + 1;
+      special_insert12(d, ti, tj);
+      f.final_add[i] = tj; f.final_add[tj - 1] = ti;
+      if (ti < tj) atomicAdd(&f.counters[CNT_NCREATE], 1);
+    }
+  }
+}
+
+// bookkeeping after an event: counters, forced rebuild, sanity (fix_extrusion.cpp:788-809)
+__global__ void k_le_finish(Dev d, LeFixDev f, int which) {
+  const int nbreak = f.counters[CNT_NBREAK], ncreate = f.counters[CNT_NCREATE];
+  Ctrl *c = d.ctrl;
+  if (which == 1) {          // extrusion
+    c->le_count[0] = nbreak;
+    c->le_count[4] += nbreak;
+    if (nbreak != ncreate) le_raise(c, LE_DERR_COUNT_MISMATCH, ncreate, nbreak);
+    if (nbreak || ncreate) c->forced = 1;
+  } else if (which == 2) {   // unload
+    c->le_count[1] = nbreak;
+    c->le_count[5] += nbreak;
+    c->nbonds -= nbreak;
+    if (nbreak) c->forced = 1;
+  } else {                   // load
+    c->le_count[2] = ncreate;
+    c->le_count[6] += ncreate;
+    c->nbonds += ncreate;
+    if (ncreate) c->forced = 1;
+  }
+  f.counters[CNT_TOTAL] = nbreak + ncreate;   // gate of the topology sweeps
+}
+
+// ------------------------------------------------------------------------------------------------
+// fix ex_unload (fix_ex_unload.cpp:172-372)
+// ------------------------------------------------------------------------------------------------
+// candidate pass: every extruder bond longer than the cutoff makes its two atoms each other's partner.
+// The distance is the one the bondlist visit computes: owned-owned for a bond inside the box, owned-ghost
+// (partner shifted by the image found at the last rebuild) for one straddling the boundary.
+__global__ void k_unl_candidates(LeView V, UnloadArgs A) {
+  const Dev &d = V.d; const LeFixDev &f = V.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) {
+    int partner = 0; double best = 0.0;
+    const int nb = d.num_bond[i];
+    for (int m = 0; m < nb; m++) {
+      if (d.bond_type[(size_t)i * d.bpa + m] != A.btype) continue;
+      const int p = d.bond_atom[(size_t)i * d.bpa + m];
+      const int code = d.bond_cross[(size_t)i * d.bpa + m];
+      double xi[3], xp[3];
+      double rsq;
+      if (code == 21) {           // one visit, from the lower tag: (x[lo] - x[hi])
+        const int a = min(i + 1, p), b = max(i + 1, p);
+        raw_xyz(V, a, xi); raw_xyz(V, b, xp);
+        rsq = dist2(xi, xp);
+      } else {                    // visited from this atom with the partner's ghost image
+        raw_xyz(V, i + 1, xi); raw_xyz(V, p, xp);
+        const int sh[3] = {(code & 3) - 1, ((code >> 2) & 3) - 1, ((code >> 4) & 3) - 1};
+        for (int q = 0; q < 3; q++) if (sh[q]) xp[q] = __dadd_rn(xp[q], (double)sh[q] * c_P.L[q]);
+        rsq = dist2(xi, xp);
+      }
+      if (rsq <= A.cutsq) continue;
+      if (rsq > best) { best = rsq; partner = p; }
+    }
+    f.partner[i] = partner;
+    f.final_remove[i] = 0; f.final_add[i] = 0;
+    f.flag[i] = partner != 0;
+    if (i < 16) f.counters[i] = 0;
+  }
+}
+
+// probability[i] = uniform() for atoms with a partner, ascending (fix_ex_unload.cpp:256-259)
+__global__ void k_le_assign_draws(LeFixDev f, int n, const int *scan, double fraction) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (f.flag[i] > 0 && fraction < 1.0) f.prob[i] = f.draws[scan[i]];
+}
+
+__global__ void k_unl_break(LeView V, UnloadArgs A) {
+  const Dev &d = V.d; const LeFixDev &f = V.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) {
+    const int ti = i + 1, p = f.partner[i];
+    if (p == 0) continue;
+    if (f.partner[p - 1] != ti) continue;
+    if (A.fraction < 1.0) {
+      const double pr = (ti < p) ? f.prob[i] : f.prob[p - 1];
+      if (pr >= A.fraction) continue;
+    }
+    delete_bond_slot(d, ti, p);
+    special_remove12(d, ti, p);
+    f.final_remove[i] = p; f.final_remove[p - 1] = ti;
+    if (ti < p) atomicAdd(&f.counters[CNT_NBREAK], 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fix ex_load (fix_ex_load.cpp:329-655)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_load_init(LeView V, int btype) {
+  const Dev &d = V.d; const LeFixDev &f = V.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) {
+    int bc = 0;
+    const int nb = d.num_bond[i];
+    for (int m = 0; m < nb; m++) if (d.bond_type[(size_t)i * d.bpa + m] == btype) bc++;
+    f.bondcount[i] = bc;
+    f.partner[i] = 0; f.final_add[i] = 0; f.final_remove[i] = 0;
+    f.distsq[i] = LE_BIG; f.claim[i] = 0xffffffffu;
+    if (i < 16) f.counters[i] = 0;
+  }
+}
+
+// static part of the half-list scan for the pair (t, t+2), t = i+1 (fix_ex_load.cpp:447-494).
+// ex13 bit0: pair is in the half list of the last rebuild; bit1: stored on the lower tag; bit2: the
+// stored neighbor is a periodic ghost, whose num_bond the reference never communicates
+// (src/MOLECULE/atom_vec_bond.cpp:41) -- it reads 0 there, so such a pair is never eligible.
+__global__ void k_load_eligible(LeView V, LoadArgs A) {
+  const Dev &d = V.d; const LeFixDev &f = V.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) {
+    int ok = 0;
+    const int e = d.ex13[i];
+    if ((e & 1) && !(e & 4) && i + 2 < d.N) {
+      const int lo = i + 1, hi = i + 3, mid = i + 2;
+      const int ti = (e & 2) ? lo : hi, tj = (e & 2) ? hi : lo;     // list owner / stored neighbor
+      const int itype = type_of(V, ti), jtype = type_of(V, tj);
+      int possible = 0;
+      if (itype == A.itype && jtype == A.jtype) {
+        if ((A.imax == 0 || f.bondcount[ti - 1] < A.imax) && (A.jmax == 0 || f.bondcount[tj - 1] < A.jmax)) possible = 1;
+      } else if (itype == A.jtype && jtype == A.itype) {
+        if ((A.jmax == 0 || f.bondcount[ti - 1] < A.jmax) && (A.imax == 0 || f.bondcount[tj - 1] < A.imax)) possible = 1;
+      }
+      if (possible && d.num_bond[ti - 1] == 2 && d.num_bond[tj - 1] == 2 && d.num_bond[mid - 1] == 2) {
+        const int *sl = d.special + (size_t)(ti - 1) * d.maxspecial;
+        const int n1 = d.nspecial[(size_t)(ti - 1) * 3];
+        for (int k = 0; k < n1; k++) if (sl[k] == tj) possible = 0;
+        if (possible) {
+          double xi[3], xj[3];
+          raw_xyz(V, ti, xi); raw_xyz(V, tj, xj);
+          const double rsq = dist2(xi, xj);
+          if (rsq < A.cutsq) { ok = 1; f.prob[i] = rsq; }
+        }
+      }
+    }
+    f.flag[i] = ok;
+  }
+}
+
+struct LoadTask {
+  LeView V; const int *ntask_ptr;
+  __device__ int ntasks() const { return *ntask_ptr; }
+  // position in the half-list traversal: owner atom first (ilist is ascending), lower pair first
+  __device__ unsigned prio(int k) const {
+    const int i = V.f.tasks[k];
+    const int owner = (V.d.ex13[i] & 2) ? i + 1 : i + 3;
+    return (unsigned)owner * 2u + ((V.d.ex13[i] & 2) ? 1u : 0u);
+  }
+  __device__ int beads(int k, int b[4]) const {
+    const int i = V.f.tasks[k];
+    b[0] = i; b[1] = i + 1; b[2] = i + 2;
+    return 3;
+  }
+  __device__ void exec(int k) {
+    const LeFixDev &f = V.f;
+    const int i = f.tasks[k];
+    if (f.partner[i + 1] != 0) return;     // middle bead already claimed (fix_ex_load.cpp:471-476,484)
+    const double rsq = f.prob[i];
+    const int lo = i + 1, hi = i + 3;
+    if (rsq < f.distsq[lo - 1]) { f.partner[lo - 1] = hi; f.distsq[lo - 1] = rsq; }
+    if (rsq < f.distsq[hi - 1]) { f.partner[hi - 1] = lo; f.distsq[hi - 1] = rsq; }
+  }
+};
+__global__ void __launch_bounds__(LE_EXEC_THREADS) k_load_scan(LeView V, const int *ntask) {
+  LoadTask T{V, ntask};
+  ordered_execute(T, V.f.claim, V.f.done);
+}
+
+__global__ void k_load_flag_partners(LeFixDev f, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    f.flag[i] = f.partner[i] != 0;
+    f.prob[i] = LE_BIG;      // `probability` overlays distsq in the reference; only drawn entries are read
+  }
+}
+
+__global__ void k_load_create(LeView V, LoadArgs A) {
+  const Dev &d = V.d; const LeFixDev &f = V.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) {
+    const int ti = i + 1, p = f.partner[i];
+    if (p == 0) continue;
+    if (f.partner[p - 1] != ti) continue;
+    if (A.fraction < 1.0) {
+      const double pr = (ti < p) ? f.prob[i] : f.prob[p - 1];
+      if (pr >= A.fraction) continue;
+    }
+    const int nb = d.num_bond[i];
+    if (nb == d.bpa) { le_raise(d.ctrl, LE_DERR_BOND_OVERFLOW, ti, nb); continue; }
+    d.bond_type[(size_t)i * d.bpa + nb] = A.btype;
+    d.bond_atom[(size_t)i * d.bpa + nb] = p;
+    d.num_bond[i] = nb + 1;
+    special_insert12(d, ti, p);
+    const int bc = f.bondcount[i] + 1;
+    f.bondcount[i] = bc;
+    const int k = d.map[i];
+    int4 *pp = &d.pos[V.cur][k];
+    const int ty = (pp->w & 0xff) + 1;
+    if (ty == A.itype) { if (bc == A.imax) pp->w = (pp->w & ~0xff) | (A.inew - 1); }
+    else { if (bc == A.jmax) pp->w = (pp->w & ~0xff) | (A.jnew - 1); }
+    f.final_add[i] = p; f.final_add[p - 1] = ti;
+    if (ti < p) atomicAdd(&f.counters[CNT_NCREATE], 1);
+  }
+}

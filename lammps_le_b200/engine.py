@@ -1,0 +1,368 @@
+"""ctypes binding of include/le_b200.h -- the Python mirror of the C ABI.
+
+Every method maps one-to-one onto an `le_*` entry point (same names, argument meaning and error
+behaviour); errors are raised as `LeError` carrying `le_last_error()`, the way the reference raises
+`LAMMPSException` (src/library.h:236-237).  There is no fallback: if the CUDA library is missing or
+no GPU is present the constructor raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libleb200.so")
+
+LE_FIX_EXTRUSION, LE_FIX_EX_UNLOAD, LE_FIX_EX_LOAD = 1, 2, 3
+LE_BOND_NONE, LE_BOND_FENE, LE_BOND_HARMONIC = 0, 1, 2
+SBBITS = 30
+NEIGHMASK = 0x3FFFFFFF
+
+
+class LeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("le_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Thermo(C.Structure):
+    _fields_ = [("step", C.c_int64), ("temp", C.c_double), ("epair", C.c_double), ("emol", C.c_double),
+                ("etotal", C.c_double), ("press", C.c_double), ("ke", C.c_double), ("virial", C.c_double * 6),
+                ("nbonds", C.c_int64), ("fene_warnings", C.c_int64)]
+
+    def as_dict(self):
+        return {"step": self.step, "temp": self.temp, "epair": self.epair, "emol": self.emol,
+                "etotal": self.etotal, "press": self.press, "ke": self.ke, "virial": list(self.virial),
+                "nbonds": self.nbonds, "fene_warnings": self.fene_warnings}
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in
+                ("steps", "neigh_builds", "dangerous_builds", "half_pairs", "full_entries", "kernel_launches",
+                 "extrusion_shifts", "loads", "unloads", "last_extrusion_shifts", "last_loads", "last_unloads")] + \
+               [("last_run_gpu_ms", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen the CUDA library; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("lammps_le_b200: %s is missing -- the CUDA extension is not built; "
+                          "run `make -C lammps_le_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    P, I, D, I64 = C.c_void_p, C.c_int, C.c_double, C.c_int64
+    pd, pi = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    sig = {
+        "le_create": [C.POINTER(P), I, pd, pd, pi], "le_set_types": [P, I, pd, I],
+        "le_set_pair_lj": [P, I, pd, pd, pd, I], "le_set_bond": [P, I, I, pd], "le_set_special": [P, pd],
+        "le_set_neighbor": [P, D, I, I, I], "le_set_neighbor_capacity": [P, I], "le_set_newton": [P, I, I],
+        "le_set_capacity": [P, I, I], "le_set_timestep": [P, D], "le_reset_timestep": [P, I64],
+        "le_thermo_every": [P, I], "le_fix_nve": [P, I], "le_fix_nve_limit": [P, D],
+        "le_fix_langevin": [P, D, D, D, I], "le_fix_extrusion": [P, I, I, I, I, D, I, I, I],
+        "le_fix_ex_load": [P, I, I, I, D, I, D, I, I, I, I, I], "le_fix_ex_unload": [P, I, I, D, D, I],
+        "le_unfix": [P, I], "le_upload_atoms": [P, I, pi, pi, pd, pd, pi], "le_upload_bonds": [P, I, pi, pi, pi],
+        "le_upload_topology": [P, pi, pi, pi, pi, pi], "le_set_positions": [P, pd, pi], "le_set_velocities": [P, pd],
+        "le_run": [P, I64], "le_force_rebuild": [P], "le_run_le_event": [P, I],
+        "le_fix_rng_reset": [P, I, I, I64], "le_fix_rng_consumed": [P, I, C.POINTER(I64)],
+        "le_compute_forces": [P, pd, C.POINTER(Thermo)], "le_natoms": [P], "le_download_x": [P, pd, pi],
+        "le_download_v": [P, pd], "le_download_types": [P, pi], "le_download_topology": [P, pi, pi, pi, pi, pi],
+        "le_download_neighlist": [P, I, C.POINTER(I64), pi, C.POINTER(I64)],
+        "le_download_bondlist": [P, pi, C.POINTER(I64)], "le_thermo_count": [P],
+        "le_get_thermo": [P, I, C.POINTER(Thermo)], "le_get_stats": [P, C.POINTER(Stats)], "le_compute_rg": [P, pd],
+        "le_gen_saw_chains": [I, I, D, D, D, C.c_uint64, pd, pi], "le_gen_lattice_melt": [I, I, D, pd, pd, pi],
+    }
+    for name, args in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = I
+    lib.le_destroy.argtypes = [P]
+    lib.le_destroy.restype = None
+    lib.le_last_error.argtypes = [P]
+    lib.le_last_error.restype = C.c_char_p
+    lib.le_version.restype = C.c_char_p
+    lib.le_timestep.argtypes = [P]
+    lib.le_timestep.restype = I64
+    _lib = lib
+    return lib
+
+
+def _pd(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _pi(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Engine:
+    """One simulation context on one GPU (the reference's `LAMMPS` object for this path)."""
+
+    def __init__(self, boxlo, boxhi, periodic=(1, 1, 1), device=0):
+        self.lib = load_library()
+        self._h = C.c_void_p()
+        lo, hi, per = _f64(boxlo), _f64(boxhi), _i32(periodic)
+        rc = self.lib.le_create(C.byref(self._h), device, _pd(lo), _pd(hi), _pi(per))
+        if rc != 0:
+            msg = self.lib.le_last_error(self._h).decode() if self._h else "no CUDA device (there is no CPU fallback)"
+            if self._h:
+                self.lib.le_destroy(self._h)
+                self._h = C.c_void_p()
+            raise LeError(rc, msg)
+        self.boxlo, self.boxhi = np.array(lo), np.array(hi)
+        self.bpa, self.maxspecial, self.ntypes = 4, 16, 1
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.le_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise LeError(rc, self.lib.le_last_error(self._h).decode())
+
+    # ---- settings ----
+    def set_types(self, masses, nbondtypes):
+        m = _f64(masses)
+        self.ntypes = len(m)
+        self._ck(self.lib.le_set_types(self._h, len(m), _pd(m), nbondtypes))
+
+    def set_pair_lj(self, epsilon, sigma, cut, shift=True):
+        """epsilon/sigma/cut: scalars (all pairs) or ntypes x ntypes matrices."""
+        nt = self.ntypes
+        e, s, c = [np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (nt, nt)))
+                   for a in (epsilon, sigma, cut)]
+        self._ck(self.lib.le_set_pair_lj(self._h, nt, _pd(e), _pd(s), _pd(c), 1 if shift else 0))
+
+    def set_bond(self, btype, style, params):
+        style = {"fene": LE_BOND_FENE, "harmonic": LE_BOND_HARMONIC, "none": LE_BOND_NONE}.get(style, style)
+        p = np.zeros(4)
+        p[:len(params)] = params
+        self._ck(self.lib.le_set_bond(self._h, btype, style, _pd(p)))
+
+    def set_special(self, lj):
+        a = _f64(lj)
+        self._ck(self.lib.le_set_special(self._h, _pd(a)))
+
+    def set_neighbor(self, skin, every=1, delay=10, check=1):
+        self._ck(self.lib.le_set_neighbor(self._h, skin, every, delay, check))
+
+    def set_neighbor_capacity(self, n):
+        self._ck(self.lib.le_set_neighbor_capacity(self._h, n))
+
+    def set_newton(self, pair=1, bond=0):
+        self._ck(self.lib.le_set_newton(self._h, pair, bond))
+
+    def set_capacity(self, bond_per_atom, maxspecial):
+        self._ck(self.lib.le_set_capacity(self._h, bond_per_atom, maxspecial))
+        self.bpa, self.maxspecial = bond_per_atom, maxspecial
+
+    def set_timestep(self, dt):
+        self._ck(self.lib.le_set_timestep(self._h, dt))
+
+    def reset_timestep(self, step):
+        self._ck(self.lib.le_reset_timestep(self._h, step))
+
+    def thermo_every(self, n):
+        self._ck(self.lib.le_thermo_every(self._h, n))
+
+    # ---- fixes ----
+    def fix_nve(self, enable=True):
+        self._ck(self.lib.le_fix_nve(self._h, 1 if enable else 0))
+
+    def fix_nve_limit(self, xmax):
+        self._ck(self.lib.le_fix_nve_limit(self._h, xmax))
+
+    def fix_langevin(self, t_start, t_stop, damp, seed):
+        self._ck(self.lib.le_fix_langevin(self._h, t_start, t_stop, damp, seed))
+
+    def fix_extrusion(self, nevery, neutral, left, right, p_through, btype, roadblock=-1, seed=12345):
+        self._ck(self.lib.le_fix_extrusion(self._h, nevery, neutral, left, right, p_through, btype, roadblock, seed))
+
+    def fix_ex_load(self, nevery, itype, jtype, rc, btype, prob=1.0, seed=12345, iparam=(0, 0), jparam=(0, 0)):
+        self._ck(self.lib.le_fix_ex_load(self._h, nevery, itype, jtype, rc, btype, prob, seed,
+                                         iparam[0], iparam[1], jparam[0], jparam[1]))
+
+    def fix_ex_unload(self, nevery, btype, rc, prob=1.0, seed=12345):
+        self._ck(self.lib.le_fix_ex_unload(self._h, nevery, btype, rc, prob, seed))
+
+    def unfix(self, which):
+        self._ck(self.lib.le_unfix(self._h, which))
+
+    # ---- atoms ----
+    def upload_atoms(self, types, x, v=None, image=None, tags=None):
+        t, xx, vv, im, tg = _i32(types), _f64(x), _f64(v), _i32(image), _i32(tags)
+        self._ck(self.lib.le_upload_atoms(self._h, len(t), _pi(tg), _pi(t), _pd(xx), _pd(vv), _pi(im)))
+
+    def upload_bonds(self, btype, atom1, atom2):
+        b, a1, a2 = _i32(btype), _i32(atom1), _i32(atom2)
+        self._ck(self.lib.le_upload_bonds(self._h, len(b), _pi(b), _pi(a1), _pi(a2)))
+
+    def upload_topology(self, num_bond, bond_type, bond_atom, nspecial, special):
+        a = [_i32(q) for q in (num_bond, bond_type, bond_atom, nspecial, special)]
+        self._ck(self.lib.le_upload_topology(self._h, *[_pi(q) for q in a]))
+
+    def set_positions(self, x, image=None):
+        xx, im = _f64(x), _i32(image)
+        self._ck(self.lib.le_set_positions(self._h, _pd(xx), _pi(im)))
+
+    def set_velocities(self, v):
+        vv = _f64(v)
+        self._ck(self.lib.le_set_velocities(self._h, _pd(vv)))
+
+    # ---- run ----
+    def run(self, nsteps):
+        self._ck(self.lib.le_run(self._h, nsteps))
+
+    def force_rebuild(self):
+        self._ck(self.lib.le_force_rebuild(self._h))
+
+    def run_le_event(self, which):
+        self._ck(self.lib.le_run_le_event(self._h, which))
+
+    def fix_rng_reset(self, which, seed, consumed=0):
+        self._ck(self.lib.le_fix_rng_reset(self._h, which, seed, consumed))
+
+    def fix_rng_consumed(self, which):
+        n = C.c_int64()
+        self._ck(self.lib.le_fix_rng_consumed(self._h, which, C.byref(n)))
+        return n.value
+
+    def compute_forces(self):
+        n = self.natoms
+        f = np.zeros((n, 3))
+        t = Thermo()
+        self._ck(self.lib.le_compute_forces(self._h, _pd(f), C.byref(t)))
+        return f, t.as_dict()
+
+    # ---- results ----
+    @property
+    def natoms(self):
+        return self.lib.le_natoms(self._h)
+
+    @property
+    def timestep(self):
+        return self.lib.le_timestep(self._h)
+
+    def positions(self, unwrap=False):
+        n = self.natoms
+        x = np.zeros((n, 3))
+        im = np.zeros(n, dtype=np.int32)
+        self._ck(self.lib.le_download_x(self._h, _pd(x), _pi(im)))
+        if unwrap:
+            x = x + unpack_image(im) * (self.boxhi - self.boxlo)
+        return x, im
+
+    def velocities(self):
+        v = np.zeros((self.natoms, 3))
+        self._ck(self.lib.le_download_v(self._h, _pd(v)))
+        return v
+
+    def types(self):
+        t = np.zeros(self.natoms, dtype=np.int32)
+        self._ck(self.lib.le_download_types(self._h, _pi(t)))
+        return t
+
+    def topology(self):
+        n = self.natoms
+        nb = np.zeros(n, dtype=np.int32)
+        bt = np.zeros((n, self.bpa), dtype=np.int32)
+        ba = np.zeros((n, self.bpa), dtype=np.int32)
+        ns = np.zeros((n, 3), dtype=np.int32)
+        sp = np.zeros((n, self.maxspecial), dtype=np.int32)
+        self._ck(self.lib.le_download_topology(self._h, _pi(nb), _pi(bt), _pi(ba), _pi(ns), _pi(sp)))
+        return {"num_bond": nb, "bond_type": bt, "bond_atom": ba, "nspecial": ns, "special": sp}
+
+    def neighlist(self, half=True):
+        """CSR over tags: (offsets[N+1], entries) with entries = partner tag | which << 30."""
+        n = self.natoms
+        tot = C.c_int64()
+        self._ck(self.lib.le_download_neighlist(self._h, 1 if half else 0, None, None, C.byref(tot)))
+        off = np.zeros(n + 1, dtype=np.int64)
+        ent = np.zeros(max(tot.value, 1), dtype=np.int32)
+        self._ck(self.lib.le_download_neighlist(self._h, 1 if half else 0,
+                                                off.ctypes.data_as(C.POINTER(C.c_int64)), _pi(ent), C.byref(tot)))
+        return off, ent[:tot.value]
+
+    def bondlist(self):
+        n = C.c_int64()
+        self._ck(self.lib.le_download_bondlist(self._h, None, C.byref(n)))
+        rows = np.zeros((max(n.value, 1), 3), dtype=np.int32)
+        self._ck(self.lib.le_download_bondlist(self._h, _pi(rows), C.byref(n)))
+        return rows[:n.value]
+
+    def thermo(self, index=None):
+        if index is None:
+            out = []
+            for k in range(self.lib.le_thermo_count(self._h)):
+                t = Thermo()
+                self._ck(self.lib.le_get_thermo(self._h, k, C.byref(t)))
+                out.append(t.as_dict())
+            return out
+        t = Thermo()
+        self._ck(self.lib.le_get_thermo(self._h, index, C.byref(t)))
+        return t.as_dict()
+
+    def stats(self):
+        s = Stats()
+        self._ck(self.lib.le_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def rg(self):
+        r = C.c_double()
+        self._ck(self.lib.le_compute_rg(self._h, C.byref(r)))
+        return r.value
+
+
+def unpack_image(im):
+    im = np.asarray(im)
+    return np.stack([(im & 1023) - 512, ((im >> 10) & 1023) - 512, ((im >> 20) & 1023) - 512], axis=-1)
+
+
+def pack_image(ixyz):
+    a = np.asarray(ixyz, dtype=np.int64)
+    return (((a[..., 0] + 512) & 1023) | (((a[..., 1] + 512) & 1023) << 10) | (((a[..., 2] + 512) & 1023) << 20)).astype(np.int32)
+
+
+def gen_saw_chains(n, nchains, L, step=0.97, rmin=0.9, seed=12345):
+    """Self-avoiding walk(s) wrapped into [0,L)^3: returns x[n,3], image[n]."""
+    lib = load_library()
+    x = np.zeros((n, 3))
+    im = np.zeros(n, dtype=np.int32)
+    rc = lib.le_gen_saw_chains(n, nchains, L, step, rmin, seed, _pd(x), _pi(im))
+    if rc:
+        raise LeError(rc, "le_gen_saw_chains: bad arguments")
+    return x, im
+
+
+def gen_lattice_melt(nchains, length, rho=0.8442):
+    lib = load_library()
+    n = nchains * length
+    x = np.zeros((n, 3))
+    im = np.zeros(n, dtype=np.int32)
+    L = C.c_double()
+    rc = lib.le_gen_lattice_melt(nchains, length, rho, C.byref(L), _pd(x), _pi(im))
+    if rc:
+        raise LeError(rc, "le_gen_lattice_melt: bad arguments")
+    return x, im, L.value

@@ -1,0 +1,109 @@
+"""GPU tests of the timestep itself: integration, thermostat, reneighboring, determinism, error paths."""
+import numpy as np
+import pytest
+
+from lammps_le_b200 import systems
+from lammps_le_b200.engine import LeError
+
+pytestmark = pytest.mark.gpu
+
+
+def relaxed_chain(n=5000, next_=50, seed=9, steps=1500):
+    s = systems.chromatin_chain(n, next_, rho=0.2, seed=seed)
+    e = systems.make_engine(s, velocities=systems.maxwell_velocities(n, 1.0, np.ones(n), seed))
+    systems.relax(e, steps=steps)
+    return s, e
+
+
+def test_nve_conserves_energy():
+    s, e = relaxed_chain()
+    e.fix_langevin(1.0, 1.0, 1.0, 1)          # define then switch the thermostat off by unfixing: plain NVE
+    x, im = e.positions()
+    v = e.velocities()
+    topo = e.topology()
+    e.close()
+    e = systems.make_engine(s, velocities=v, dt=0.005)
+    e.set_positions(x, im)
+    e.upload_topology(topo["num_bond"], topo["bond_type"], topo["bond_atom"], topo["nspecial"], topo["special"])
+    e.fix_nve(True)
+    e.thermo_every(100)
+    e.run(2000)
+    th = e.thermo()
+    et = np.array([t["etotal"] for t in th])
+    ke = np.array([t["ke"] for t in th]) / e.natoms
+    assert len(th) == 21
+    drift = np.abs(et - et[0]).max()
+    assert drift < 2e-3 * ke.mean(), "NVE energy drift %.3g per atom (KE/atom %.3g)" % (drift, ke.mean())
+    st = e.stats()
+    assert st["neigh_builds"] > 5 and st["dangerous_builds"] == 0
+    e.close()
+
+
+def test_langevin_holds_temperature():
+    s, e = relaxed_chain(n=20000, next_=200, steps=1000)
+    e.fix_langevin(1.0, 1.0, 1.0, 904297)
+    e.thermo_every(50)
+    e.run(3000)
+    t = np.array([r["temp"] for r in e.thermo()][-40:])
+    assert abs(t.mean() - 1.0) < 0.03, "mean T %.4f" % t.mean()
+    e.close()
+
+
+def test_run_is_deterministic():
+    out = []
+    for _ in range(2):
+        s, e = relaxed_chain(n=3000, next_=30, steps=300)
+        e.fix_langevin(1.0, 1.0, 1.0, 77)
+        e.run(400)
+        out.append((e.positions()[0], e.velocities()))
+        e.close()
+    assert (out[0][0] == out[1][0]).all() and (out[0][1] == out[1][1]).all()
+
+
+def test_bad_fene_bond_aborts_the_run():
+    s = systems.chromatin_chain(500, 0, rho=0.2, seed=1)
+    s["x"] = s["x"].copy()
+    s["x"][250] += 2.9          # bond 250-251 and 251-252 now > 2 R0
+    e = systems.make_engine(s)
+    e.fix_nve(True)
+    with pytest.raises(LeError) as ei:
+        e.run(1)
+    assert "Bad FENE bond" in str(ei.value)
+    e.close()
+
+
+def test_short_nve_trajectory_matches_reference():
+    from oracle import refio
+    if not refio.have_reference():
+        pytest.skip("oracle/_ref not present on this box")
+    import os
+    import tempfile
+    from oracle.make_golden import force_case
+    s = systems.chromatin_chain(3000, 30, rho=0.2, seed=17)
+    rec0 = force_case(s, velocities=True)
+    # reference: 20 NVE steps from the snapped state
+    wd = tempfile.mkdtemp(prefix="le_traj_")
+    s2 = dict(s)
+    s2["x"], s2["image"], s2["v"] = rec0["x"], rec0["image"], rec0["v"]
+    refio.write_data_file(os.path.join(wd, "data.le"), s2)
+    deck = refio.deck_header(s2, "data.le") + ["fix 1 all nve", "thermo_style custom step temp epair emol etotal press",
+                                                 "thermo 20", "timestep 0.005", "run 20"]
+    final = os.path.join(wd, "final.bin")
+    out, _ = refio.run_reference(deck, workdir=wd, final=final)
+    ref = refio.read_records(final)[0]
+    rows = refio.parse_thermo(out)
+    from tests import lehelpers as H
+    e = H.engine_from_record(rec0, s["bond_coeffs"], positions="x")
+    e.set_timestep(0.005)
+    e.fix_nve(True)
+    e.run(20)
+    x, im = e.positions()
+    L = rec0["boxhi"] - rec0["boxlo"]
+    d = x - ref["x"]
+    d -= L * np.rint(d / L)
+    assert np.abs(d).max() < 2e-5, "max position deviation after 20 steps %.3g" % np.abs(d).max()
+    assert np.abs(e.velocities() - ref["v"]).max() < 2e-4
+    th = e.thermo(-1)
+    assert abs(th["etotal"] - rows[-1]["TotEng"]) < 2e-5 * abs(rows[-1]["TotEng"])
+    assert abs(th["temp"] - rows[-1]["Temp"]) < 1e-4
+    e.close()

@@ -1,0 +1,146 @@
+"""GPU parity tests against the reference: golden fixtures made by oracle/make_golden.py from the compiled
+reference, and -- when oracle/_ref travelled to this box -- fresh reference runs on larger inputs.
+
+Bars (BASELINE.json north_star): neighbor lists and USER-LE bond topology bit-exact; forces and energies
+within 1e-5 relative per atom.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from tests import lehelpers as H
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CHROMATIN_BONDS = {1: ("fene", (30.0, 1.5, 1.0, 1.0)), 2: ("harmonic", (20.0, 1.3))}
+FORCE_RTOL = 1e-5   # per atom, relative to max(|f_i|, rms |f|)
+
+
+def _force_record_from_npz(z):
+    rec = {k: z[k] for k in z.files}
+    rec["bpa"], rec["maxspecial"] = int(z["bpa"]), int(z["maxspecial"])
+    return rec
+
+
+def check_lists(e, rec):
+    off, ent = e.neighlist(half=True)
+    bad = H.compare_neighlists(off, ent, rec["neigh_offsets"], rec["neigh_entries"])
+    assert len(ent) == len(rec["neigh_entries"]), "half list size %d vs reference %d" % (len(ent), len(rec["neigh_entries"]))
+    assert not bad, "half neighbor sets differ for %d atoms, first tags %s" % (len(bad), bad[:10])
+    bl = e.bondlist()
+    assert bl.shape == rec["bondlist"].shape, "bondlist length %d vs %d" % (len(bl), len(rec["bondlist"]))
+    assert (bl == rec["bondlist"]).all(), "bondlist rows differ (order matters: it is the USER-LE visit order)"
+
+
+def check_forces(e, rec, thermo_ref=None):
+    f, th = e.compute_forces()
+    fr = rec["f"]
+    n = len(fr)
+    mag = np.sqrt((fr ** 2).sum(1))
+    rms = np.sqrt((mag ** 2).mean())
+    err = np.sqrt(((f - fr) ** 2).sum(1)) / np.maximum(mag, rms)
+    assert err.max() <= FORCE_RTOL, "max per-atom relative force error %.3g (atom %d)" % (err.max(), err.argmax() + 1)
+    epair_ref, emol_ref = rec["energy"][0] / n, rec["energy"][1] / n
+    assert abs(th["epair"] - epair_ref) <= 1e-5 * max(abs(epair_ref), 1e-3)
+    assert abs(th["emol"] - emol_ref) <= 1e-5 * abs(emol_ref)
+    w_ref = rec["virial_pair"] + rec["virial_bond"]
+    w = np.array(th["virial"])
+    assert np.abs(w - w_ref).max() <= 1e-5 * np.abs(w_ref[:3]).max()
+    if thermo_ref is not None:
+        assert abs(th["press"] - thermo_ref["Press"]) <= 2e-5 * max(abs(thermo_ref["Press"]), 1e-2)
+        assert abs(th["temp"] - thermo_ref["Temp"]) <= 1e-6 + 1e-6 * thermo_ref["Temp"]
+    return err.max()
+
+
+def test_lists_and_forces_golden():
+    rec = _force_record_from_npz(np.load(os.path.join(GOLD, "forces_chain.npz")))
+    e = H.engine_from_record(rec, CHROMATIN_BONDS, positions="x")
+    e.force_rebuild()
+    check_lists(e, rec)
+    t = rec["thermo"]
+    check_forces(e, rec, {"Temp": t[0], "Press": t[4]})
+    e.close()
+
+
+def replay_events(pre, post, cfg=H.LE_DECK):
+    """Replay every recorded USER-LE event from the reference's pre-state; compare the post-state."""
+    problems = []
+    nchecked = {1: 0, 2: 0, 3: 0}
+    from oracle import refio
+    for a, b in zip(pre, post):
+        e = H.engine_from_record(a, CHROMATIN_BONDS, positions="xhold")
+        H.define_le_fixes(e, cfg)
+        e.force_rebuild()
+        # lists of the last rebuild: the stale pair list ex_load scans and the bondlist the other two visit
+        off, ent = e.neighlist(half=True)
+        bad = H.compare_neighlists(off, ent, a["neigh_offsets"], a["neigh_entries"])
+        bl = e.bondlist()
+        if bad or bl.shape != a["bondlist"].shape or (bl != a["bondlist"]).any():
+            problems.append(("lists", a["step"], len(bad)))
+        e.set_positions(a["x"], a["image"])
+        w = a["which"]
+        slot = H.RNG_SLOT[w]
+        e.fix_rng_reset(H.WHICH[w], cfg[H.SEED_KEY[w]]["seed"], refio.draws_consumed(a["rngc"][slot]))
+        e.run_le_event(H.WHICH[w])
+        got = e.topology()
+        res = H.compare_topology(got, b)
+        res["type"] = int((e.types() != b["type"]).sum())
+        res["draws"] = int(e.fix_rng_consumed(H.WHICH[w]) != refio.draws_consumed(b["rngc"][slot]))
+        st = e.stats()
+        cnt = {1: st["last_extrusion_shifts"], 2: st["last_unloads"], 3: st["last_loads"]}[w]
+        res["counter"] = int(cnt != b["counters"][w - 1])
+        # special lists compare as tier SETS (dedup's swap-with-last order is not physical); exact order is reported
+        hard = {k: v for k, v in res.items() if k != "special_exact" and v}
+        if hard:
+            problems.append((a["step"], w, hard))
+        nchecked[w] += 1
+        e.close()
+    return problems, nchecked
+
+
+def test_le_replay_golden():
+    from oracle.make_golden import unpack_trace
+    pre, post = unpack_trace(np.load(os.path.join(GOLD, "le_trace_small.npz")))
+    problems, n = replay_events(pre, post)
+    assert n[1] >= 3 and n[2] >= 1 and n[3] >= 1
+    assert not problems, "USER-LE replay mismatches: %s" % problems[:5]
+
+
+def _need_ref():
+    from oracle import refio
+    if not refio.have_reference():
+        pytest.skip("oracle/_ref not present on this box")
+
+
+def test_le_replay_live_reference():
+    """a longer fresh trace: 4000 beads, 3000 steps (6 slide events, 30 loads, 30 unloads)"""
+    _need_ref()
+    from lammps_le_b200 import systems
+    from oracle.make_golden import le_trace
+    s = systems.chromatin_chain(4000, 60, rho=0.2, seed=21)
+    pre, post, _ = le_trace(s, 3010, H.le_deck_lines())
+    problems, n = replay_events(pre, post)
+    assert n[1] >= 6
+    assert not problems, "USER-LE replay mismatches: %s" % problems[:5]
+
+
+def test_forces_live_reference_chain_and_melt():
+    _need_ref()
+    from lammps_le_b200 import systems
+    from oracle.make_golden import force_case
+    s = systems.chromatin_chain(20000, 200, rho=0.2, seed=3)      # BASELINE config C2 size
+    rec = force_case(s)
+    e = H.engine_from_record(rec, CHROMATIN_BONDS, positions="x")
+    e.force_rebuild()
+    check_lists(e, rec)
+    check_forces(e, rec, rec["thermo"])
+    e.close()
+    m = systems.fene_melt(40, 100, rho=0.8442)                    # dense melt, lattice start + minimise
+    rec = force_case(m, velocities=True)
+    e = H.engine_from_record(rec, {1: ("fene", (30.0, 1.5, 1.0, 1.0))}, positions="x")
+    e.force_rebuild()
+    check_lists(e, rec)
+    check_forces(e, rec, rec["thermo"])
+    e.close()
