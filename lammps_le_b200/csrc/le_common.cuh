@@ -41,6 +41,9 @@ struct Params {
   float cutneighmaxsq_f;
   float cutsq[LE_MAXT * LE_MAXT], lj1[LE_MAXT * LE_MAXT], lj2[LE_MAXT * LE_MAXT];
   float lj3[LE_MAXT * LE_MAXT], lj4[LE_MAXT * LE_MAXT], offset[LE_MAXT * LE_MAXT];
+  float cutsq_screen[LE_MAXT * LE_MAXT];   // fp32 screen, slightly above cutsq
+  double cutsq_d[LE_MAXT * LE_MAXT], lj1_d[LE_MAXT * LE_MAXT], lj2_d[LE_MAXT * LE_MAXT];
+  double lj3_d[LE_MAXT * LE_MAXT], lj4_d[LE_MAXT * LE_MAXT], offset_d[LE_MAXT * LE_MAXT];
   float special_lj[4];
   int special_flag[4];
   int nscan_tier;       // how many special tiers find_special must scan (0..3)
@@ -48,6 +51,7 @@ struct Params {
   // bonds
   int bstyle[LE_MAXB];
   float bk[LE_MAXB], br0[LE_MAXB], beps[LE_MAXB], bsig[LE_MAXB];
+  double bk_d[LE_MAXB], br0_d[LE_MAXB], beps_d[LE_MAXB], bsig_d[LE_MAXB];
   // integration / thermostat
   float dt, dtf;
   float triggersq;

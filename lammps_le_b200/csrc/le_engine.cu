@@ -383,6 +383,8 @@ static int build_params(le_ctx *c) {
       const double cutsq = rc * rc;                       // Pair::init, src/pair.cpp:251
       P.cutsq[k] = (float)cutsq; P.lj1[k] = (float)lj1; P.lj2[k] = (float)lj2;
       P.lj3[k] = (float)lj3; P.lj4[k] = (float)lj4; P.offset[k] = (float)off;
+      P.cutsq_d[k] = cutsq; P.lj1_d[k] = lj1; P.lj2_d[k] = lj2; P.lj3_d[k] = lj3; P.lj4_d[k] = lj4; P.offset_d[k] = off;
+      P.cutsq_screen[k] = (float)(cutsq * 1.00001 + 1e-12);
       // Neighbor::init (src/neighbor.cpp:293-310)
       const double cutoff = sqrt(cutsq);
       const double cn = cutoff + (cutoff > 0.0 ? c->skin : 0.0);
@@ -420,6 +422,7 @@ static int build_params(le_ctx *c) {
     P.bstyle[k] = c->bstyle[k];
     P.bk[k] = (float)c->bparam[k][0]; P.br0[k] = (float)c->bparam[k][1];
     P.beps[k] = (float)c->bparam[k][2]; P.bsig[k] = (float)c->bparam[k][3];
+    P.bk_d[k] = c->bparam[k][0]; P.br0_d[k] = c->bparam[k][1]; P.beps_d[k] = c->bparam[k][2]; P.bsig_d[k] = c->bparam[k][3];
   }
   P.dt = (float)c->dt; P.dtf = (float)(0.5 * c->dt);       // FixNVE::init, ftm2v = 1
   P.triggersq = (float)(0.25 * c->skin * c->skin);

@@ -55,37 +55,42 @@ __device__ __forceinline__ void step_phase(const Dev &d, const StepArgs &a) {
     double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0, v4 = 0.0, v5 = 0.0;
 
     // ---- pair ----
+    // fp32 distance screen on the exact fixed-point differences; the (few) pairs inside the force cutoff are
+    // evaluated in fp64: r^-14 amplifies a 1e-7 error of r^2 sevenfold and the WCA/FENE terms of bonded
+    // neighbours cancel to ~10% of their size, so fp32 pair math cannot meet the 1e-5 per-atom bar
     const int nn = cnt & 0xff;
 #pragma unroll 4
     for (int k = 0; k < nn; k++) {
       const unsigned e = __ldg(&neigh[(size_t)k * N + i]);
       const int j = e & NEIGH_IDX_MASK;
       const int4 pj = __ldg(&posr[j]);
-      const float dx = (float)(int)((unsigned)pi.x - (unsigned)pj.x) * sx;
-      const float dy = (float)(int)((unsigned)pi.y - (unsigned)pj.y) * sy;
-      const float dz = (float)(int)((unsigned)pi.z - (unsigned)pj.z) * sz;
-      const float rsq = dx * dx + dy * dy + dz * dz;
+      const int idx = (int)((unsigned)pi.x - (unsigned)pj.x);
+      const int idy = (int)((unsigned)pi.y - (unsigned)pj.y);
+      const int idz = (int)((unsigned)pi.z - (unsigned)pj.z);
+      const float dxf = (float)idx * sx, dyf = (float)idy * sy, dzf = (float)idz * sz;
+      const float rsqf = dxf * dxf + dyf * dyf + dzf * dzf;
       const int tp = c_P.pair_uniform ? 0 : ti * nt + (pj.w & 0xff);
-      if (rsq < c_P.cutsq[tp]) {
-        const float r2inv = 1.0f / rsq;
-        const float r6inv = r2inv * r2inv * r2inv;
-        const float factor = c_P.special_lj[e >> 30];
-        const float fpair = factor * r6inv * (c_P.lj1[tp] * r6inv - c_P.lj2[tp]) * r2inv;
-        fx += (double)(dx * fpair);
-        fy += (double)(dy * fpair);
-        fz += (double)(dz * fpair);
-        if (EV) {
-          const double r6 = (double)r6inv;
-          evdwl += (double)factor * (r6 * ((double)c_P.lj3[tp] * r6 - (double)c_P.lj4[tp]) - (double)c_P.offset[tp]);
-          const double fp = (double)fpair;
-          v0 += (double)dx * dx * fp; v1 += (double)dy * dy * fp; v2 += (double)dz * dz * fp;
-          v3 += (double)dx * dy * fp; v4 += (double)dx * dz * fp; v5 += (double)dy * dz * fp;
+      if (rsqf < c_P.cutsq_screen[tp]) {
+        const double dx = (double)idx * c_P.scale[0], dy = (double)idy * c_P.scale[1], dz = (double)idz * c_P.scale[2];
+        const double rsq = dx * dx + dy * dy + dz * dz;
+        if (rsq < c_P.cutsq_d[tp]) {
+          double r2inv = (double)(1.0f / (float)rsq);
+          r2inv = r2inv * (2.0 - rsq * r2inv);            // one Newton step: full double accuracy
+          const double r6inv = r2inv * r2inv * r2inv;
+          const double factor = (double)c_P.special_lj[e >> 30];
+          const double fpair = factor * r6inv * (c_P.lj1_d[tp] * r6inv - c_P.lj2_d[tp]) * r2inv;
+          fx += dx * fpair; fy += dy * fpair; fz += dz * fpair;
+          if (EV) {
+            evdwl += factor * (r6inv * (c_P.lj3_d[tp] * r6inv - c_P.lj4_d[tp]) - c_P.offset_d[tp]);
+            v0 += dx * dx * fpair; v1 += dy * dy * fpair; v2 += dz * dz * fpair;
+            v3 += dx * dy * fpair; v4 += dx * dz * fpair; v5 += dy * dz * fpair;
+          }
         }
       }
     }
     double pv0 = v0, pv1 = v1, pv2 = v2, pv3 = v3, pv4 = v4, pv5 = v5;  // pair part (counted twice)
 
-    // ---- bonds ----
+    // ---- bonds (fp64: see above) ----
     const int nb = (cnt >> 16) & 0xff;
     double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0, b4 = 0.0, b5 = 0.0;
     for (int m = 0; m < nb; m++) {
@@ -93,49 +98,46 @@ __device__ __forceinline__ void step_phase(const Dev &d, const StepArgs &a) {
       const int j = e & BOND_IDX_MASK;
       const int bt = e >> 28;
       const int4 pj = __ldg(&posr[j]);
-      const float dx = (float)(int)((unsigned)pi.x - (unsigned)pj.x) * sx;
-      const float dy = (float)(int)((unsigned)pi.y - (unsigned)pj.y) * sy;
-      const float dz = (float)(int)((unsigned)pi.z - (unsigned)pj.z) * sz;
-      const float rsq = dx * dx + dy * dy + dz * dz;
-      float fbond;
+      const double dx = (double)(int)((unsigned)pi.x - (unsigned)pj.x) * c_P.scale[0];
+      const double dy = (double)(int)((unsigned)pi.y - (unsigned)pj.y) * c_P.scale[1];
+      const double dz = (double)(int)((unsigned)pi.z - (unsigned)pj.z) * c_P.scale[2];
+      const double rsq = dx * dx + dy * dy + dz * dz;
+      double fbond;
       if (c_P.bstyle[bt] == 1) {  // FENE
-        const float r0sq = c_P.br0[bt] * c_P.br0[bt];
-        float rlogarg = 1.0f - rsq / r0sq;
-        if (rlogarg < 0.1f) {
+        const double r0sq = c_P.br0_d[bt] * c_P.br0_d[bt];
+        double rlogarg = 1.0 - rsq / r0sq;
+        if (rlogarg < 0.1) {
           if (EV) acc[9] += 0.5;  // each long bond is seen from both ends
-          if (rlogarg <= -3.0f) le_raise(d.ctrl, LE_DERR_BAD_FENE, __float_as_int(vi.w), j);
-          rlogarg = 0.1f;
+          if (rlogarg <= -3.0) le_raise(d.ctrl, LE_DERR_BAD_FENE, __float_as_int(vi.w), j);
+          rlogarg = 0.1;
         }
-        fbond = -c_P.bk[bt] / rlogarg;
-        const float sig2 = c_P.bsig[bt] * c_P.bsig[bt];
-        float sr6 = 0.0f;
-        const bool core = rsq < 1.2599210498948732f * sig2;
+        fbond = -c_P.bk_d[bt] / rlogarg;
+        const double sig2 = c_P.bsig_d[bt] * c_P.bsig_d[bt];
+        double sr6 = 0.0;
+        const bool core = rsq < 1.2599210498948732 * sig2;   // TWO_1_3
         if (core) {
-          const float sr2 = sig2 / rsq;
+          const double sr2 = sig2 / rsq;
           sr6 = sr2 * sr2 * sr2;
-          fbond += 48.0f * c_P.beps[bt] * sr6 * (sr6 - 0.5f) / rsq;
+          fbond += 48.0 * c_P.beps_d[bt] * sr6 * (sr6 - 0.5) / rsq;
         }
         if (EV) {
-          double eb = -0.5 * (double)c_P.bk[bt] * (double)r0sq * log((double)rlogarg);
-          if (core) eb += 4.0 * (double)c_P.beps[bt] * (double)sr6 * ((double)sr6 - 1.0) + (double)c_P.beps[bt];
+          double eb = -0.5 * c_P.bk_d[bt] * r0sq * log(rlogarg);
+          if (core) eb += 4.0 * c_P.beps_d[bt] * sr6 * (sr6 - 1.0) + c_P.beps_d[bt];
           ebond += eb;
         }
       } else if (c_P.bstyle[bt] == 2) {  // harmonic
-        const float r = sqrtf(rsq);
-        const float dr = r - c_P.br0[bt];
-        const float rk = c_P.bk[bt] * dr;
-        fbond = (r > 0.0f) ? -2.0f * rk / r : 0.0f;
-        if (EV) ebond += (double)rk * (double)dr;
+        const double r = sqrt(rsq);
+        const double dr = r - c_P.br0_d[bt];
+        const double rk = c_P.bk_d[bt] * dr;
+        fbond = (r > 0.0) ? -2.0 * rk / r : 0.0;
+        if (EV) ebond += rk * dr;
       } else {
-        fbond = 0.0f;
+        fbond = 0.0;
       }
-      fx += (double)(dx * fbond);
-      fy += (double)(dy * fbond);
-      fz += (double)(dz * fbond);
+      fx += dx * fbond; fy += dy * fbond; fz += dz * fbond;
       if (EV) {
-        const double fb = (double)fbond;
-        b0 += (double)dx * dx * fb; b1 += (double)dy * dy * fb; b2 += (double)dz * dz * fb;
-        b3 += (double)dx * dy * fb; b4 += (double)dx * dz * fb; b5 += (double)dy * dz * fb;
+        b0 += dx * dx * fbond; b1 += dy * dy * fbond; b2 += dz * dz * fbond;
+        b3 += dx * dy * fbond; b4 += dx * dz * fbond; b5 += dy * dz * fbond;
       }
     }
 
