@@ -14,8 +14,13 @@ WCA_CUT = 1.12246
 NEUTRAL, LEFT, RIGHT, ROADBLOCK = 1, 2, 3, 4
 
 
+EXTRUDER_HARMONIC = ("harmonic", (20.0, 1.3))        # the deck of SURVEY.md Appendix B (parity fixtures)
+EXTRUDER_FENE = ("fene", (10.0, 4.0, 1.0, 1.0))        # same WCA core as the pair potential: no overlap while
+                                                       # bonded, so unloading never switches WCA on at small r
+
+
 def chromatin_chain(n, n_extruders, rho=0.2, seed=12345, barriers="periodic", nchains=1,
-                    p_left=0.005, p_right=0.005, p_block=0.001):
+                    p_left=0.005, p_right=0.005, p_block=0.001, extruder_bond=EXTRUDER_HARMONIC):
     """One (or nchains) self-avoiding chain(s) of n beads at number density rho with pre-placed extruders.
 
     barriers="periodic": CTCF every 100 beads, left at i%100==50, right at i%100==75 (config C2);
@@ -54,7 +59,7 @@ def chromatin_chain(n, n_extruders, rho=0.2, seed=12345, barriers="periodic", nc
         "name": "chromatin_%d" % n, "box": (np.zeros(3), np.full(3, L)), "types": types, "x": x, "image": image,
         "bonds": (np.concatenate(btype), np.concatenate(at1), np.concatenate(at2)),
         "masses": np.ones(4), "nbondtypes": 2, "ntypes": 4,
-        "bond_coeffs": {1: ("fene", (30.0, 1.5, 1.0, 1.0)), 2: ("harmonic", (20.0, 1.3))},
+        "bond_coeffs": {1: ("fene", (30.0, 1.5, 1.0, 1.0)), 2: extruder_bond},
         "bond_per_atom": 4, "maxspecial": 46,
     }
 

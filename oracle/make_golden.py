@@ -104,12 +104,14 @@ def main():
     s = systems.chromatin_chain(1200, 24, rho=0.2, seed=11)
     pre, post, _ = le_trace(s, 1510, le_deck_lines())
     # keep: the 4 extrusion events and a subset of load/unload events (all those that changed something + a few idle)
-    keep = []
+    ext, other = [], []
     for k, (a, b) in enumerate(zip(pre, post)):
         changed = (a["num_bond"] != b["num_bond"]).any() or (a["bond_atom"] != b["bond_atom"]).any()
-        if a["which"] == 1 or changed:
-            keep.append(k)
-    keep = keep[:14]
+        if a["which"] == 1:
+            ext.append(k)
+        elif changed:
+            other.append(k)
+    keep = sorted(ext + other[:10])
     np.savez_compressed(os.path.join(gold, "le_trace_small.npz"), **pack_trace([pre[k] for k in keep], [post[k] for k in keep]))
     print("le_trace_small: %d of %d events kept" % (len(keep), len(pre)))
     s2 = systems.chromatin_chain(3000, 40, rho=0.2, seed=5)
