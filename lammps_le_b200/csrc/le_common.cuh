@@ -2,19 +2,16 @@
 //
 // Layout in HBM (N atoms, all arrays device-resident for the life of the context):
 //   sorted order (index k = position after the last cell sort; rewritten at every rebuild)
-//     pos[2][N]   int4   {ux,uy,uz: 32-bit fixed-point box fractions, w: type-1}   double-buffered
-//     vel[N]      float4 {vx,vy,vz, w: tag bits}
+//     pos[2][N]   int4   {ux,uy,uz: 32-bit fixed-point box fractions, w: tag<<3 | type-1}   double-buffered
+//     vel[N]      float4 {vx,vy,vz, w: tag bits (host convenience)}
 //     pos_hold[N] int4   positions at the last rebuild (Neighbor::xhold, src/neighbor.cpp:2048-2052)
 //     img[N], img_hold[N]  LAMMPS-packed image flags now / at the last rebuild
-//     counts[N]   nfull | nhalf<<8 | nbond<<16
-//     neigh[maxneigh][N]  ELL full neighbor rows, half-list entries first; entry = k_j | which<<30
+//     counts[N]   nfull | nbond<<16
+//     neigh[maxneigh][N]  ELL full neighbor rows; entry = k_j | which<<30
 //     bondrow[bpa][N]     ELL bond partner rows; entry = k_j | (bondtype-1)<<28
 //   tag order (index t-1; what the reference's Atom class holds, src/atom.h)
 //     num_bond, bond_type[N][bpa], bond_atom[N][bpa], nspecial[N][3], special[N][maxspecial]
 //     map[N]      tag-1 -> sorted index (Atom::map, src/atom.h:354-358)
-//     bond_cross[N][bpa]  bond straddled the periodic boundary at the last rebuild (=> the reference's
-//                         bondlist holds it twice, src/ntopo_bond_all.cpp:65-66)
-//     ex13[N]     bit0: pair (t,t+2) is in the half list of the last rebuild, bit1: stored on t
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -52,6 +49,11 @@ struct Params {
   int bstyle[LE_MAXB];
   float bk[LE_MAXB], br0[LE_MAXB], beps[LE_MAXB], bsig[LE_MAXB];
   double bk_d[LE_MAXB], br0_d[LE_MAXB], beps_d[LE_MAXB], bsig_d[LE_MAXB];
+  double br0sq_d[LE_MAXB], binvr0sq_d[LE_MAXB], bsig2_d[LE_MAXB], bcore_d[LE_MAXB];  // R0^2, 1/R0^2, sigma^2, 2^(1/3) sigma^2
+  // fp32 brackets around cutneighsq: below lo a pair is certainly listed, above hi certainly not; only the
+  // sliver in between needs the reference's fp64 arithmetic (k_build)
+  float cutneigh_lo[LE_MAXT * LE_MAXT], cutneigh_hi[LE_MAXT * LE_MAXT];
+  float t_start, t_stop;
   // integration / thermostat
   float dt, dtf;
   float triggersq;
@@ -75,6 +77,11 @@ struct Ctrl {
   // USER-LE counters
   int le_count[8];
   long long nbonds;
+  // device-side run state, so that captured graphs are identical from step to step
+  int cur;                    // which of pos[0]/pos[1] holds the current coordinates
+  int pad0;
+  long long step;             // timestep of the next force evaluation (Update::ntimestep)
+  long long run_begin, run_end;  // Update::beginstep / endstep of the current run (Langevin ramp)
 };
 
 enum {
@@ -99,7 +106,6 @@ struct Dev {
   unsigned *counts, *neigh, *bondrow;
   // tag order
   int *num_bond, *bond_type, *bond_atom, *nspecial, *special, *map;
-  unsigned char *bond_cross, *ex13;
   // cell sort scratch
   int *cell_count, *cell_start, *cellid, *slot, *order, *blocksum;
   int ncell[3], ncells, nscanblocks;
@@ -139,6 +145,78 @@ __device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned
     k0 += W0; k1 += W1;
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// ---- reference arithmetic shared by the device list build and the host-side list download ----
+#ifdef __CUDA_ARCH__
+#define LE_DADD(a, b) __dadd_rn(a, b)
+#define LE_DSUB(a, b) __dsub_rn(a, b)
+#define LE_DMUL(a, b) __dmul_rn(a, b)
+#else
+#define LE_DADD(a, b) ((a) + (b))
+#define LE_DSUB(a, b) ((a) - (b))
+#define LE_DMUL(a, b) ((a) * (b))
+#endif
+
+// periodic shift of j's closest image relative to i in one dimension: (uj - ui)_wrapped - (uj - ui)_raw = s * 2^32
+__host__ __device__ __forceinline__ int le_image_shift(unsigned ui, unsigned uj) {
+  const int w = (int)(uj - ui);
+  return (int)(((long long)w - ((long long)uj - (long long)ui)) >> 32);
+}
+
+// dequantised coordinate with explicit Params (one multiply, one add, no fma contraction)
+__host__ __device__ __forceinline__ double le_deq_p(const Params &P, unsigned u, int d) {
+  return LE_DADD(P.lo[d], LE_DMUL((double)u, P.scale[d]));
+}
+
+// NBin::coord2bin for one dimension (src/nbin.cpp:120-150)
+__host__ __device__ __forceinline__ int le_ref_bin(const Params &P, double x, int dim) {
+  const double lo = P.lo[dim], hi = P.hi[dim], inv = P.bininv[dim];
+  const int nb = P.nbin[dim];
+  int ix;
+  if (x >= hi) ix = (int)LE_DMUL(LE_DSUB(x, hi), inv) + nb;
+  else if (x >= lo) { ix = (int)LE_DMUL(LE_DSUB(x, lo), inv); if (ix > nb - 1) ix = nb - 1; }
+  else ix = (int)LE_DMUL(LE_DSUB(x, lo), inv) - 1;
+  return ix;
+}
+
+// coordinates of i and of the image of j closest to i, as the reference holds them (owned atom / ghost made by
+// AtomVec::pack_border, x + pbc*prd)
+__host__ __device__ __forceinline__ void le_pair_coords(const Params &P, const unsigned ui[3], const unsigned uj[3],
+                                                        double xi[3], double xj[3], int sh[3]) {
+  for (int q = 0; q < 3; q++) {
+    xi[q] = le_deq_p(P, ui[q], q);
+    sh[q] = le_image_shift(ui[q], uj[q]);
+    double v = le_deq_p(P, uj[q], q);
+    if (sh[q]) v = LE_DADD(v, (double)sh[q] * P.L[q]);
+    xj[q] = v;
+  }
+}
+
+// squared distance with the reference's operation order (npair_half_bin_newton.cpp:98-102)
+__host__ __device__ __forceinline__ double le_pair_rsq_ref(const Params &P, const unsigned ui[3], const unsigned uj[3]) {
+  double xi[3], xj[3]; int sh[3];
+  le_pair_coords(P, ui, uj, xi, xj, sh);
+  const double dx = LE_DSUB(xi[0], xj[0]), dy = LE_DSUB(xi[1], xj[1]), dz = LE_DSUB(xi[2], xj[2]);
+  return LE_DADD(LE_DADD(LE_DMUL(dx, dx), LE_DMUL(dy, dy)), LE_DMUL(dz, dz));
+}
+
+// would NPairHalfBinNewton::build store the pair (i, j) in the list of atom i?  (same-bin rule
+// npair_half_bin_newton.cpp:84-91, upper-half stencil nstencil_half_bin_3d_newton.cpp:26-38)
+__host__ __device__ __forceinline__ bool le_pair_stored_on_i(const Params &P, const unsigned ui[3], const unsigned uj[3],
+                                                             int tagi, int tagj, int *ghost) {
+  double xi[3], xj[3]; int sh[3];
+  le_pair_coords(P, ui, uj, xi, xj, sh);
+  const int dbx = le_ref_bin(P, xj[0], 0) - le_ref_bin(P, xi[0], 0);
+  const int dby = le_ref_bin(P, xj[1], 1) - le_ref_bin(P, xi[1], 1);
+  const int dbz = le_ref_bin(P, xj[2], 2) - le_ref_bin(P, xi[2], 2);
+  const int gh = sh[0] | sh[1] | sh[2];
+  *ghost = gh != 0;
+  if ((dbx | dby | dbz) == 0) {
+    if (gh == 0) return tagj > tagi;       // owned j later in the bin's list (ascending local index == tag)
+    return !(xj[2] < xi[2] || (xj[2] == xi[2] && (xj[1] < xi[1] || (xj[1] == xi[1] && xj[0] < xi[0]))));  // ghost j
+  }
+  return dbz > 0 || (dbz == 0 && (dby > 0 || (dby == 0 && dbx > 0)));
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -27,6 +27,11 @@ struct FixExtrusionCfg { int on, nevery, neutral, left, right, btype, roadblock,
 struct FixExLoadCfg { int on, nevery, itype, jtype, btype, seed, imax, inew, jmax, jnew; double rc, prob; };
 struct FixExUnloadCfg { int on, nevery, btype, seed; double rc, prob; };
 
+#define PLAIN_UNROLL 8      // timesteps per launch of the steady-state graph
+#define REBUILD_KERNELS 8   // kernels in the conditional rebuild body
+
+struct GraphKey { Dev d; int langevin; };
+
 struct le_ctx {
   int device;
   cudaStream_t stream;
@@ -71,6 +76,13 @@ struct le_ctx {
   cudaEvent_t ev0, ev1;
   double *h_thermo;     // pinned
   Ctrl *h_ctrl;         // pinned
+  // captured step graphs (built lazily, rebuilt when anything baked into them changes)
+  GraphKey gkey;
+  bool graphs_ok;
+  cudaGraph_t g_plain, g_tail[2];
+  cudaGraphExec_t x_plain, x_tail[2];
+  int64_t direct_launches, graph_node_launches, direct_builds;
+  bool capturing;
 };
 
 static int fail(le_ctx *c, int code, const char *fmt, ...) {
@@ -93,7 +105,7 @@ static int fail(le_ctx *c, int code, const char *fmt, ...) {
 #define LAUNCH(c, kern, grid, block, ...)                      \
   do {                                                         \
     kern<<<(grid), (block), 0, (c)->stream>>>(__VA_ARGS__);    \
-    (c)->stats.kernel_launches++;                              \
+    if (!(c)->capturing) (c)->direct_launches++;               \
   } while (0)
 
 template <typename T>
@@ -152,6 +164,11 @@ extern "C" int le_create(le_ctx **out, int device, const double boxlo[3], const 
   memset(&c->lf, 0, sizeof c->lf);
   memset(&c->stats, 0, sizeof c->stats);
   c->nbonds = 0;
+  c->graphs_ok = false; c->capturing = false;
+  c->g_plain = nullptr; c->g_tail[0] = c->g_tail[1] = nullptr;
+  c->x_plain = nullptr; c->x_tail[0] = c->x_tail[1] = nullptr;
+  c->direct_launches = c->graph_node_launches = c->direct_builds = 0;
+  memset(&c->gkey, 0, sizeof c->gkey);
   cudaMallocHost(&c->h_thermo, sizeof(double) * LE_THERMO_W * THERMO_SLOTS);
   cudaMallocHost(&c->h_ctrl, sizeof(Ctrl));
   for (int k = 0; k < 3; k++)
@@ -162,10 +179,23 @@ extern "C" int le_create(le_ctx **out, int device, const double boxlo[3], const 
   return LE_OK;
 }
 
+static void destroy_graphs(le_ctx *c) {
+  if (c->x_plain) cudaGraphExecDestroy(c->x_plain);
+  if (c->g_plain) cudaGraphDestroy(c->g_plain);
+  for (int k = 0; k < 2; k++) {
+    if (c->x_tail[k]) cudaGraphExecDestroy(c->x_tail[k]);
+    if (c->g_tail[k]) cudaGraphDestroy(c->g_tail[k]);
+  }
+  c->x_plain = nullptr; c->g_plain = nullptr;
+  c->x_tail[0] = c->x_tail[1] = nullptr; c->g_tail[0] = c->g_tail[1] = nullptr;
+  c->graphs_ok = false;
+}
+
 extern "C" void le_destroy(le_ctx *c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  destroy_graphs(c);
   for (void *p : c->allocs) cudaFree(p);
   cudaFreeHost(c->h_thermo);
   cudaFreeHost(c->h_ctrl);
@@ -389,12 +419,14 @@ static int build_params(le_ctx *c) {
       const double cutoff = sqrt(cutsq);
       const double cn = cutoff + (cutoff > 0.0 ? c->skin : 0.0);
       P.cutneighsq[k] = cn * cn;
+      P.cutneigh_lo[k] = (float)(cn * cn * (1.0 - 1e-5));
+      P.cutneigh_hi[k] = (float)(cn * cn * (1.0 + 1e-5));
       cutneighmax = std::max(cutneighmax, cn);
       if (k > 0 && (c->eps[k] != c->eps[0] || c->sigma[k] != c->sigma[0] || c->cut[k] != c->cut[0])) uniform = false;
     }
   P.pair_uniform = uniform ? 1 : 0;
   if (!(cutneighmax > 0.0)) return fail(c, LE_ESTATE, "pair cutoff is zero: set pair_style lj/cut first");
-  P.cutneighmaxsq_f = (float)(cutneighmax * cutneighmax * 1.001 + 1e-6);
+  P.cutneighmaxsq_f = (float)(cutneighmax * cutneighmax * (1.0 + 2e-5));
   for (int k = 0; k < 3; k++)
     if (P.L[k] < 2.0 * cutneighmax) return fail(c, LE_EINVAL, "box length %g < 2 x neighbor cutoff %g: minimum image needs a larger box", P.L[k], cutneighmax);
   // reference bins: binsize = 1/2 cutneighmax snapped to the box (nbin_standard.cpp:95-131)
@@ -423,7 +455,12 @@ static int build_params(le_ctx *c) {
     P.bk[k] = (float)c->bparam[k][0]; P.br0[k] = (float)c->bparam[k][1];
     P.beps[k] = (float)c->bparam[k][2]; P.bsig[k] = (float)c->bparam[k][3];
     P.bk_d[k] = c->bparam[k][0]; P.br0_d[k] = c->bparam[k][1]; P.beps_d[k] = c->bparam[k][2]; P.bsig_d[k] = c->bparam[k][3];
+    P.br0sq_d[k] = P.br0_d[k] * P.br0_d[k];
+    P.binvr0sq_d[k] = P.br0sq_d[k] > 0.0 ? 1.0 / P.br0sq_d[k] : 0.0;
+    P.bsig2_d[k] = P.bsig_d[k] * P.bsig_d[k];
+    P.bcore_d[k] = 1.2599210498948732 * P.bsig2_d[k];        // TWO_1_3 (bond_fene.cpp:22)
   }
+  P.t_start = (float)c->t_start; P.t_stop = (float)c->t_stop;
   P.dt = (float)c->dt; P.dtf = (float)(0.5 * c->dt);       // FixNVE::init, ftm2v = 1
   P.triggersq = (float)(0.25 * c->skin * c->skin);
   P.vlimitsq = c->xlimit > 0.0 ? (float)((c->xlimit / c->dt) * (c->xlimit / c->dt)) : 0.0f;
@@ -519,8 +556,6 @@ extern "C" int le_upload_atoms(le_ctx *c, int n, const int *tag, const int *type
   if ((r = dalloc(c, &d.nspecial, (size_t)n * 3))) return r;
   if ((r = dalloc(c, &d.special, (size_t)n * c->maxspecial))) return r;
   if ((r = dalloc(c, &d.map, n))) return r;
-  if ((r = dalloc(c, &d.bond_cross, (size_t)n * c->bpa))) return r;
-  if ((r = dalloc(c, &d.ex13, n))) return r;
   if ((r = dalloc(c, &d.cellid, n))) return r;
   if ((r = dalloc(c, &d.slot, n))) return r;
   if ((r = dalloc(c, &d.order, n))) return r;
@@ -528,6 +563,7 @@ extern "C" int le_upload_atoms(le_ctx *c, int n, const int *tag, const int *type
   if ((r = dalloc(c, &d.thermo, (size_t)LE_THERMO_W * THERMO_SLOTS))) return r;
   if ((r = dalloc(c, &d.fout, (size_t)n * 3))) return r;
   if ((r = le_fix_alloc(c->lf, n, c->maxspecial, c->allocs, c->stream))) return fail(c, LE_ENOMEM, "cudaMalloc failed for USER-LE scratch");
+  if ((r = le_fix_alloc_rng(c->lf, c->allocs, c->stream))) return fail(c, LE_ENOMEM, "cudaMalloc failed for USER-LE scratch");
   c->atoms_loaded = true;
 
   std::vector<int4> hp(n);
@@ -545,7 +581,7 @@ extern "C" int le_upload_atoms(le_ctx *c, int n, const int *tag, const int *type
     int ix = 0, iy = 0, iz = 0;
     if (image) unpack_image(image[k], &ix, &iy, &iz);
     // entries are stored in tag order initially: sorted index == tag-1 until the first rebuild
-    hp[t - 1] = make_int4((int)u[0], (int)u[1], (int)u[2], type[k] - 1);
+    hp[t - 1] = make_int4((int)u[0], (int)u[1], (int)u[2], (t << 3) | (type[k] - 1));
     float4 vv;
     vv.x = v ? (float)v[3 * k] : 0.f; vv.y = v ? (float)v[3 * k + 1] : 0.f; vv.z = v ? (float)v[3 * k + 2] : 0.f;
     vv.w = h_int_as_float(t);
@@ -693,18 +729,89 @@ extern "C" int le_set_velocities(le_ctx *c, const double *v) {
 }
 
 // ---- rebuild / step drivers -------------------------------------------------------------------------
-static void enqueue_rebuild(le_ctx *c, int gated) {
+// the rebuild kernels; `direct` adds the bookkeeping k_decide does when the rebuild is a conditional graph node
+static void enqueue_rebuild(le_ctx *c, bool direct) {
   Dev &d = c->d;
   const int n = c->N;
-  LAUNCH(c, k_cell_count, grid_for(n, 256), 256, d, c->cur, gated);
-  LAUNCH(c, k_scan_partial, d.nscanblocks, SCAN_BLOCK, d, gated);
-  LAUNCH(c, k_scan_blocks, 1, SCAN_BLOCK, d, gated);
-  LAUNCH(c, k_scan_apply, d.nscanblocks, SCAN_BLOCK, d, gated);
-  LAUNCH(c, k_cell_scatter, grid_for(n, 256), 256, d, gated);
-  LAUNCH(c, k_cell_sort, grid_for(d.ncells, 128), 128, d, gated);
-  LAUNCH(c, k_gather, grid_for(n, 256), 256, d, c->cur, gated);
-  LAUNCH(c, k_build, grid_for(n, 128), 128, d, c->cur, gated);
-  LAUNCH(c, k_after_build, 1, 1, d, gated);
+  LAUNCH(c, k_cell_count, grid_for(n, 256), 256, d);
+  LAUNCH(c, k_scan_partial, d.nscanblocks, SCAN_BLOCK, d);
+  LAUNCH(c, k_scan_blocks, 1, SCAN_BLOCK, d);
+  LAUNCH(c, k_scan_apply, d.nscanblocks, SCAN_BLOCK, d);
+  LAUNCH(c, k_cell_scatter, grid_for(n, 256), 256, d);
+  LAUNCH(c, k_cell_sort, grid_for(d.ncells, 128), 128, d);
+  LAUNCH(c, k_gather, grid_for(n, 256), 256, d);
+  LAUNCH(c, k_build, grid_for(n, BUILD_THREADS), BUILD_THREADS, d);
+  if (direct) { LAUNCH(c, k_after_build, 1, 1, d); c->direct_builds++; }
+}
+
+#define CKG(call)                                                                             \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      c->capturing = false;                                                                   \
+      return fail(c, LE_ENOGPU, "CUDA graph error %s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); \
+    }                                                                                         \
+  } while (0)
+
+// append [k_decide(advance) -> IF(rebuild)] (and optionally a plain k_step after it) to graph g after node *tail
+static int graph_add_unit(le_ctx *c, cudaGraph_t g, cudaGraphNode_t *tail, int advance, bool with_step) {
+  cudaGraphConditionalHandle handle;
+  CKG(cudaGraphConditionalHandleCreate(&handle, g, 0, cudaGraphCondAssignDefault));
+  Dev d = c->d;
+  int adv = advance, use = 1;
+  void *dargs[] = {&d, &handle, &adv, &use};
+  cudaKernelNodeParams kp;
+  memset(&kp, 0, sizeof kp);
+  kp.func = (void *)k_decide; kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.kernelParams = dargs;
+  cudaGraphNode_t nd;
+  CKG(cudaGraphAddKernelNode(&nd, g, *tail ? tail : nullptr, *tail ? 1 : 0, &kp));
+  cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+  cp.conditional.handle = handle;
+  cp.conditional.type = cudaGraphCondTypeIf;
+  cp.conditional.size = 1;
+  cudaGraphNode_t nc;
+  CKG(cudaGraphAddNode(&nc, g, &nd, 1, &cp));
+  cudaGraph_t body = cp.conditional.phGraph_out[0];
+  c->capturing = true;
+  CKG(cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+  enqueue_rebuild(c, false);
+  cudaGraph_t got = nullptr;
+  CKG(cudaStreamEndCapture(c->stream, &got));
+  c->capturing = false;
+  *tail = nc;
+  if (with_step) {
+    StepArgs a; memset(&a, 0, sizeof a);
+    a.do_final = 1; a.do_initial = 1; a.langevin = c->langevin_on;
+    void *sargs[] = {&d, &a};
+    memset(&kp, 0, sizeof kp);
+    kp.func = (void *)k_step<0>; kp.gridDim = dim3(grid_for(c->N, STEP_THREADS)); kp.blockDim = dim3(STEP_THREADS); kp.kernelParams = sargs;
+    cudaGraphNode_t ns;
+    CKG(cudaGraphAddKernelNode(&ns, g, &nc, 1, &kp));
+    *tail = ns;
+  }
+  return LE_OK;
+}
+
+static int ensure_graphs(le_ctx *c) {
+  GraphKey key; memset(&key, 0, sizeof key);
+  key.d = c->d; key.langevin = c->langevin_on;
+  if (c->graphs_ok && memcmp(&key, &c->gkey, sizeof key) == 0) return LE_OK;
+  destroy_graphs(c);
+  int r;
+  for (int adv = 0; adv < 2; adv++) {
+    CKG(cudaGraphCreate(&c->g_tail[adv], 0));
+    cudaGraphNode_t tail = nullptr;
+    if ((r = graph_add_unit(c, c->g_tail[adv], &tail, adv, false))) return r;
+    CKG(cudaGraphInstantiate(&c->x_tail[adv], c->g_tail[adv], 0));
+  }
+  CKG(cudaGraphCreate(&c->g_plain, 0));
+  cudaGraphNode_t tail = nullptr;
+  for (int u = 0; u < PLAIN_UNROLL; u++)
+    if ((r = graph_add_unit(c, c->g_plain, &tail, 1, true))) return r;
+  CKG(cudaGraphInstantiate(&c->x_plain, c->g_plain, 0));
+  c->gkey = key;
+  c->graphs_ok = true;
+  return LE_OK;
 }
 
 static const char *derr_text(int code) {
@@ -728,6 +835,8 @@ static int sync_and_check(le_ctx *c) {
   CK(cudaGetLastError());
   const Ctrl &k = *c->h_ctrl;
   c->stats.neigh_builds = k.nbuilds;
+  c->stats.kernel_launches = c->direct_launches + c->graph_node_launches + REBUILD_KERNELS * (k.nbuilds - c->direct_builds);
+  if (k.cur != c->cur) return fail(c, LE_ERUN, "internal: host/device position buffer parity out of step");
   c->stats.dangerous_builds = k.ndanger;
   c->stats.last_extrusion_shifts = k.le_count[0]; c->stats.last_unloads = k.le_count[1]; c->stats.last_loads = k.le_count[2];
   c->stats.extrusion_shifts = k.le_count[4]; c->stats.unloads = k.le_count[5]; c->stats.loads = k.le_count[6];
@@ -755,7 +864,7 @@ static int ensure_ready(le_ctx *c) {
 extern "C" int le_force_rebuild(le_ctx *c) {
   if (!c) return LE_EINVAL;
   int r = ensure_ready(c); if (r) return r;
-  enqueue_rebuild(c, 0);
+  enqueue_rebuild(c, true);
   c->lists_valid = true;
   return sync_and_check(c);
 }
@@ -778,28 +887,29 @@ static void thermo_from_slot(le_ctx *c, const double *s, int64_t step, le_thermo
   t->nbonds = c->nbonds;
 }
 
-static void launch_step(le_ctx *c, const StepArgs &a) {
-  const int grid = grid_for(c->N, 256);
-  if (a.ev) LAUNCH(c, k_step<1>, grid, 256, c->d, a);
-  else LAUNCH(c, k_step<0>, grid, 256, c->d, a);
+static void launch_step(le_ctx *c, const StepArgs &a, bool ev) {
+  const int grid = grid_for(c->N, STEP_THREADS);
+  if (ev) LAUNCH(c, k_step<1>, grid, STEP_THREADS, c->d, a);
+  else LAUNCH(c, k_step<0>, grid, STEP_THREADS, c->d, a);
 }
 
-static float tsqrt_at(le_ctx *c, int64_t step, int64_t begin, int64_t end) {
-  double delta = (double)(step - begin);
-  if (delta != 0.0) delta /= (double)(end - begin);
-  const double t = c->t_start + delta * (c->t_stop - c->t_start);
-  return (float)sqrt(t);
+// Update::ntimestep / beginstep / endstep of the run that starts now -> device control block
+static int push_run_state(le_ctx *c, int64_t begin, int64_t end) {
+  long long v[3] = {begin, begin, end > begin ? end : begin + 1};
+  CK(cudaMemcpyAsync(&c->d.ctrl->step, v, sizeof v, cudaMemcpyHostToDevice, c->stream));
+  return LE_OK;
 }
 
 extern "C" int le_compute_forces(le_ctx *c, double *f, le_thermo *out) {
   if (!c) return LE_EINVAL;
   int r = ensure_ready(c); if (r) return r;
-  enqueue_rebuild(c, 0);
+  enqueue_rebuild(c, true);
   c->lists_valid = true;
   CK(cudaMemsetAsync(c->d.thermo, 0, sizeof(double) * LE_THERMO_W, c->stream));
+  r = push_run_state(c, c->ntimestep, c->ntimestep); if (r) return r;
   StepArgs a; memset(&a, 0, sizeof a);
-  a.rd = c->cur; a.ev = 1; a.slot = 0; a.write_force = 1;
-  launch_step(c, a);
+  a.slot = 0; a.write_force = 1;
+  launch_step(c, a, true);
   CK(cudaMemcpyAsync(c->h_thermo, c->d.thermo, sizeof(double) * LE_THERMO_W, cudaMemcpyDeviceToHost, c->stream));
   r = sync_and_check(c); if (r) return r;
   if (out) thermo_from_slot(c, c->h_thermo, c->ntimestep, out);
@@ -812,15 +922,21 @@ extern "C" int le_compute_forces(le_ctx *c, double *f, le_thermo *out) {
 
 #include "le_fix_host.inl"
 
+// does any USER-LE fix fire in Modify::post_integrate of timestep `step`?
+static bool le_event_at(const le_ctx *c, int64_t step) {
+  if (c->fx.on && (step % c->fx.nevery - 1) == 0) return true;
+  if (c->fu.on && (step % c->fu.nevery - 2) == 0) return true;
+  if (c->fl.on && (step % c->fl.nevery - 3) == 0) return true;
+  return false;
+}
+
 extern "C" int le_run(le_ctx *c, int64_t nsteps) {
   if (!c || nsteps < 0) return LE_EINVAL;
   int r = ensure_ready(c); if (r) return r;
   if (!c->nve_on && nsteps > 0) return fail(c, LE_ESTATE, "no integrator: define fix nve before run");
+  if ((r = ensure_graphs(c))) return r;
   Dev &d = c->d;
   const int64_t begin = c->ntimestep, end = begin + nsteps;
-  // Verlet::setup: full rebuild, then forces at the current positions
-  enqueue_rebuild(c, 0);
-  c->lists_valid = true;
   int used_slots = 0;
   std::vector<int64_t> slot_step;
   auto want_thermo = [&](int64_t s) { return s == begin || s == end || (c->thermo_every > 0 && s % c->thermo_every == 0); };
@@ -835,32 +951,73 @@ extern "C" int le_run(le_ctx *c, int64_t nsteps) {
     used_slots = 0; slot_step.clear();
     return LE_OK;
   };
-  CK(cudaMemsetAsync(d.thermo, 0, sizeof(double) * LE_THERMO_W * THERMO_SLOTS, c->stream));
-  CK(cudaEventRecord(c->ev0, c->stream));
-  for (int64_t s = begin; s <= end; s++) {
+  // one force evaluation at timestep s: finishes step s (unless it is the first of the run) and starts s+1
+  auto force_eval = [&](int64_t s) -> int {
     StepArgs a; memset(&a, 0, sizeof a);
-    a.rd = c->cur;
     a.do_final = (s > begin);
     a.do_initial = (s < end);
     a.langevin = c->langevin_on;
-    a.step_lo = (unsigned)(s & 0xffffffffu); a.step_hi = (unsigned)((uint64_t)s >> 32);
-    a.tsqrt = tsqrt_at(c, s, begin, end > begin ? end : begin + 1);
+    bool ev = false;
     if (want_thermo(s)) {
       if (used_slots == THERMO_SLOTS) {
-        r = flush_thermo(); if (r) return r;
+        int rr = flush_thermo(); if (rr) return rr;
         CK(cudaMemsetAsync(d.thermo, 0, sizeof(double) * LE_THERMO_W * THERMO_SLOTS, c->stream));
       }
-      a.ev = 1; a.slot = used_slots++; slot_step.push_back(s);
+      ev = true; a.slot = used_slots++; slot_step.push_back(s);
     }
-    launch_step(c, a);
-    if (s < end) {
-      c->cur ^= 1;
+    launch_step(c, a, ev);
+    return LE_OK;
+  };
+  CK(cudaMemsetAsync(d.thermo, 0, sizeof(double) * LE_THERMO_W * THERMO_SLOTS, c->stream));
+  if ((r = push_run_state(c, begin, end))) return r;
+  // Verlet::setup: full rebuild, then forces at the current positions
+  enqueue_rebuild(c, true);
+  c->lists_valid = true;
+  CK(cudaEventRecord(c->ev0, c->stream));
+  if ((r = force_eval(begin))) return r;
+  int64_t s = begin;
+  const char *dm = getenv("LE_B200_DIRECT");
+  const bool direct_mode = dm && dm[0] == '1';
+  while (s < end) {
+    if (direct_mode) {
+      // profiling path (LE_B200_DIRECT=1): ncu cannot see kernel nodes of graphs that hold conditional nodes, so
+      // launch every kernel directly and read the reneighbor decision back on the host
       const int64_t next = s + 1;
-      // Modify::post_integrate: the USER-LE fixes, in definition order extrusion / unload / load
-      r = enqueue_le_events(c, next); if (r) return r;
-      LAUNCH(c, k_decide, 1, 1, d);
-      enqueue_rebuild(c, 1);
+      c->cur ^= 1;
+      LAUNCH(c, k_advance, 1, 1, d);
+      if (le_event_at(c, next)) { r = enqueue_le_events(c, next); if (r) return r; }
+      LAUNCH(c, k_decide, 1, 1, d, (cudaGraphConditionalHandle)0, 0, 0);
+      CK(cudaMemcpyAsync(c->h_ctrl, d.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      if (c->h_ctrl->rebuild_now) { enqueue_rebuild(c, false); c->direct_builds++; }
+      if ((r = force_eval(next))) return r;
+      s = next;
+      continue;
     }
+    // steady state: PLAIN_UNROLL timesteps without USER-LE event, thermo output or end of run -> one graph launch
+    bool plain = (s + PLAIN_UNROLL < end);
+    for (int64_t n = s + 1; plain && n <= s + PLAIN_UNROLL; n++)
+      if (le_event_at(c, n) || want_thermo(n)) plain = false;
+    if (plain) {
+      CK(cudaGraphLaunch(c->x_plain, c->stream));
+      c->graph_node_launches += 2 * PLAIN_UNROLL;
+      if (PLAIN_UNROLL & 1) c->cur ^= 1;
+      s += PLAIN_UNROLL;
+      continue;
+    }
+    const int64_t next = s + 1;
+    c->cur ^= 1;
+    if (le_event_at(c, next)) {
+      // Modify::post_integrate of the new step: the USER-LE fixes, in definition order, before Neighbor::decide
+      LAUNCH(c, k_advance, 1, 1, d);
+      r = enqueue_le_events(c, next); if (r) return r;
+      CK(cudaGraphLaunch(c->x_tail[0], c->stream));
+    } else {
+      CK(cudaGraphLaunch(c->x_tail[1], c->stream));
+    }
+    c->graph_node_launches += 1;
+    if ((r = force_eval(next))) return r;
+    s = next;
   }
   CK(cudaEventRecord(c->ev1, c->stream));
   c->ntimestep = end;
@@ -924,7 +1081,7 @@ extern "C" int le_download_types(le_ctx *c, int *type) {
   CK(cudaMemcpyAsync(hp.data(), c->d.pos[c->cur], sizeof(int4) * n, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaMemcpyAsync(hv.data(), c->d.vel, sizeof(float4) * n, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  for (int k = 0; k < n; k++) type[h_float_as_int(hv[k].w) - 1] = (hp[k].w & 0xff) + 1;
+  for (int k = 0; k < n; k++) type[(hp[k].w >> 3) - 1] = (hp[k].w & 7) + 1;
   return LE_OK;
 }
 
@@ -947,33 +1104,40 @@ extern "C" int le_download_neighlist(le_ctx *c, int half, int64_t *offsets, int 
   if (!c->lists_valid) return fail(c, LE_ESTATE, "no neighbor list has been built yet");
   cudaSetDevice(c->device);
   const int n = c->N;
-  std::vector<unsigned> cnt(n); std::vector<float4> hv(n); std::vector<int> hmap;
+  std::vector<unsigned> cnt(n); std::vector<int4> hp(n); std::vector<int> hmap;
   int r = fetch_map(c, hmap); if (r) return r;
   CK(cudaMemcpyAsync(cnt.data(), c->d.counts, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(hv.data(), c->d.vel, sizeof(float4) * n, cudaMemcpyDeviceToHost, c->stream));
+  // positions at the last rebuild: the coordinates the list was built on
+  CK(cudaMemcpyAsync(hp.data(), c->d.pos_hold, sizeof(int4) * n, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  int maxc = 0; int64_t tot = 0;
-  for (int k = 0; k < n; k++) {
-    const int cc = half ? (cnt[k] >> 8) & 0xff : cnt[k] & 0xff;
-    maxc = std::max(maxc, (int)(cnt[k] & 0xff)); tot += cc;
-  }
-  if (nentries) *nentries = tot;
-  if (!entries || !offsets) return LE_OK;
+  int maxc = 0;
+  for (int k = 0; k < n; k++) maxc = std::max(maxc, (int)(cnt[k] & 0xff));
   std::vector<unsigned> rows((size_t)std::max(maxc, 1) * n);
   CK(cudaMemcpyAsync(rows.data(), c->d.neigh, sizeof(unsigned) * (size_t)maxc * n, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  // the device keeps full rows; which atom of a pair the reference's half list stores it on is derived here with
+  // the same arithmetic the device uses for the (t,t+2) pairs (le_pair_stored_on_i)
   int64_t o = 0;
   for (int t = 0; t < n; t++) {
     const int k = hmap[t];
-    offsets[t] = o;
-    const int cc = half ? (cnt[k] >> 8) & 0xff : cnt[k] & 0xff;
+    if (offsets) offsets[t] = o;
+    const int cc = cnt[k] & 0xff;
+    const unsigned ui[3] = {(unsigned)hp[k].x, (unsigned)hp[k].y, (unsigned)hp[k].z};
     for (int q = 0; q < cc; q++) {
       const unsigned e = rows[(size_t)q * n + k];
-      const int tj = h_float_as_int(hv[e & NEIGH_IDX_MASK].w);
-      entries[o++] = tj | (int)((e >> 30) << 30);
+      const int4 pj = hp[e & NEIGH_IDX_MASK];
+      const int tj = pj.w >> 3;
+      if (half) {
+        const unsigned uj[3] = {(unsigned)pj.x, (unsigned)pj.y, (unsigned)pj.z};
+        int ghost;
+        if (!le_pair_stored_on_i(c->P, ui, uj, t + 1, tj, &ghost)) continue;
+      }
+      if (entries && offsets) entries[o] = tj | (int)((e >> 30) << 30);
+      o++;
     }
   }
-  offsets[n] = o;
+  if (offsets) offsets[n] = o;
+  if (nentries) *nentries = o;
   return LE_OK;
 }
 
@@ -982,18 +1146,23 @@ extern "C" int le_download_bondlist(le_ctx *c, int *rows, int64_t *nrows) {
   if (!c->lists_valid) return fail(c, LE_ESTATE, "no bond list has been built yet");
   cudaSetDevice(c->device);
   const size_t n = c->N; const int bpa = c->bpa;
-  std::vector<int> nb(n), bt(n * bpa), ba(n * bpa); std::vector<unsigned char> cross(n * bpa);
+  std::vector<int> nb(n), bt(n * bpa), ba(n * bpa), hmap; std::vector<int4> hp(n);
+  int r = fetch_map(c, hmap); if (r) return r;
   CK(cudaMemcpyAsync(nb.data(), c->d.num_bond, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaMemcpyAsync(bt.data(), c->d.bond_type, sizeof(int) * n * bpa, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaMemcpyAsync(ba.data(), c->d.bond_atom, sizeof(int) * n * bpa, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(cross.data(), c->d.bond_cross, n * bpa, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(hp.data(), c->d.pos_hold, sizeof(int4) * n, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   int64_t o = 0;
   for (size_t i = 0; i < n; i++)
     for (int m = 0; m < nb[i]; m++) {
       const int p = ba[i * bpa + m];
-      // NTopoBondAll::build with newton_bond off: kept iff i < closest_image(partner); a ghost image always is
-      if (cross[i * bpa + m] != 21 || (int)(i + 1) < p) {
+      // NTopoBondAll::build with newton_bond off: kept iff i < closest_image(partner); a ghost image (the bond
+      // straddled the periodic boundary at the last rebuild) always is
+      const int4 pi = hp[hmap[i]], pj = hp[hmap[p - 1]];
+      const bool cross = le_image_shift((unsigned)pi.x, (unsigned)pj.x) || le_image_shift((unsigned)pi.y, (unsigned)pj.y) ||
+                         le_image_shift((unsigned)pi.z, (unsigned)pj.z);
+      if (cross || (int)(i + 1) < p) {
         if (rows) { rows[3 * o] = (int)i + 1; rows[3 * o + 1] = p; rows[3 * o + 2] = bt[i * bpa + m]; }
         o++;
       }
@@ -1023,7 +1192,8 @@ extern "C" int le_get_stats(le_ctx *c, le_stats *out) {
     unsigned long long h[2];
     CK(cudaMemcpyAsync(h, dcount, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    c->stats.half_pairs = (int64_t)h[0]; c->stats.full_entries = (int64_t)h[1];
+    // every pair sits in the full rows of both atoms and once in the reference's half list
+    c->stats.half_pairs = (int64_t)h[1] / 2; c->stats.full_entries = (int64_t)h[1];
   }
   *out = c->stats;
   return LE_OK;

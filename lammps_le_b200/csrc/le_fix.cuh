@@ -7,7 +7,7 @@
 // parallel we use three facts:
 //   1. the number of draws an iteration consumes depends only on the state BEFORE the loop, so an
 //      exclusive scan gives every iteration its offset into the stream, which is generated in bulk
-//      (k_ranmars_fill: the lag-97/33 recurrence advances 32 values per warp step);
+//      (k_ranmars_chunks: the linear lag-97/33 recurrence is jumped ahead chunk by chunk);
 //   2. every iteration reads and writes scratch only at a few beads around its extruder (its "touch
 //      set"); two iterations whose touch sets are disjoint commute;
 //   3. so the loop is run by an ORDERED EXECUTOR: in rounds, every pending iteration claims its
@@ -17,6 +17,7 @@
 // Everything here is indexed by tag (t-1); positions are reached through the tag map.
 #pragma once
 #include "le_common.cuh"
+#include <algorithm>
 #include <vector>
 
 #define LE_EXEC_THREADS 1024
@@ -41,6 +42,8 @@ struct LeFixDev {
   int *counters;        // [16] device counters
   double *draws;
   int draws_cap;
+  int *rm_base;         // [193] raw values ahead of the current state (k_ranmars_base)
+  unsigned *rm_jump;    // [(nchunks-1)][97] jump polynomials
   RngDev *rngdev;       // [3]
   RngHost rng[3];
   void *scratch64;
@@ -73,54 +76,145 @@ static int le_fix_alloc(LeFixDev &f, int n, int maxspecial, std::vector<void *> 
   f.draws_cap = 2 * n + 64;
   r |= A((void **)&f.draws, (size_t)f.draws_cap * 8);
   r |= A((void **)&f.rngdev, 3 * sizeof(RngDev));
+
   r |= A(&f.scratch64, 64);
   (void)maxspecial;
   return r;
 }
 
 // ------------------------------------------------------------------------------------------------
-// RanMars (src/random_mars.cpp:29-95) in exact 24-bit integer arithmetic.
-//   raw_n = (raw_{n-97} - raw_{n-33}) mod 1;  c_n = c_{n-1} - cd (+cm if negative);  out = (raw_n - c_n) mod 1
+// RanMars (src/random_mars.cpp:29-95) in exact 24-bit integer arithmetic, generated in parallel.
+//   raw_n = (raw_{n-97} - raw_{n-33}) mod 2^24;  c_n = c_{n-1} - cd (+cm if negative);  out = (raw_n - c_n) mod 2^24
 //   every value is a multiple of 2^-24, so the reference's doubles are reproduced exactly.
-// One warp produces 32 consecutive draws per iteration (the shortest lag is 33).
+// The raw recurrence is linear over Z/2^24 with characteristic polynomial x^97 + x^64 - 1, so the state K
+// draws ahead is a fixed linear map of the current one: x^(wK) mod p(x) (97 coefficients, precomputed on the host
+// for every chunk w) applied to 193 consecutive raw values.  Warp w jumps to draw w*K and produces K draws, 32
+// per step (the shortest lag is 33); c_n is an arithmetic progression mod cm and needs no jump table.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_ranmars_fill(RngDev *st, double *out, const int *n_ptr, int cap, Ctrl *ctrl) {
-  __shared__ int ring[256];   // power-of-two ring holding at least 97+32 values
+#define RM_CHUNK 1024
+#define RM_CD 7654321LL
+#define RM_CM 16777213LL
+
+// x^k mod (x^97 + x^64 - 1) over Z/2^24 for k = K, 2K, ..., (nchunks-1)K; row w-1 holds chunk w
+static void ranmars_jump_table(int nchunks, std::vector<unsigned> &table) {
+  const unsigned M = 0xffffffu;
+  auto mulmod = [&](const std::vector<unsigned> &a, const std::vector<unsigned> &b) {
+    std::vector<unsigned long long> t(193, 0);
+    for (int i = 0; i < 97; i++) {
+      if (!a[i]) continue;
+      for (int j = 0; j < 97; j++) t[i + j] = (t[i + j] + (unsigned long long)a[i] * b[j]) & M;
+    }
+    for (int dgr = 192; dgr >= 97; dgr--) {          // x^d = x^(d-97) * (1 - x^64)
+      const unsigned long long cf = t[dgr];
+      if (!cf) continue;
+      t[dgr - 97] = (t[dgr - 97] + cf) & M;
+      t[dgr - 33] = (t[dgr - 33] + (16777216ULL - cf)) & M;
+      t[dgr] = 0;
+    }
+    std::vector<unsigned> r(97);
+    for (int i = 0; i < 97; i++) r[i] = (unsigned)t[i];
+    return r;
+  };
+  std::vector<unsigned> xk(97, 0), base(97, 0);
+  base[1] = 1;                                        // x
+  xk[0] = 1;
+  for (int bit = 0, k = RM_CHUNK; k; k >>= 1, bit++) { if (k & 1) xk = mulmod(xk, base); base = mulmod(base, base); }
+  table.assign((size_t)std::max(nchunks - 1, 1) * 97, 0);
+  std::vector<unsigned> cur = xk;
+  for (int w = 1; w < nchunks; w++) {
+    for (int i = 0; i < 97; i++) table[(size_t)(w - 1) * 97 + i] = cur[i];
+    cur = mulmod(cur, xk);
+  }
+}
+
+static int le_fix_alloc_rng(LeFixDev &f, std::vector<void *> &allocs, cudaStream_t st) {
+  const int nchunks = (f.draws_cap + RM_CHUNK - 1) / RM_CHUNK;
+  std::vector<unsigned> table;
+  ranmars_jump_table(nchunks, table);
+  if (cudaMalloc((void **)&f.rm_base, 256 * 4) != cudaSuccess) return -1;
+  allocs.push_back(f.rm_base);
+  if (cudaMalloc((void **)&f.rm_jump, table.size() * 4) != cudaSuccess) return -1;
+  allocs.push_back(f.rm_jump);
+  cudaMemcpyAsync(f.rm_jump, table.data(), table.size() * 4, cudaMemcpyHostToDevice, st);
+  cudaStreamSynchronize(st);
+  return 0;
+}
+
+// raw values 0..192 relative to the current state (the state is raw 0..96), into `base`
+__global__ void k_ranmars_base(const RngDev *st, int *base, const int *n_ptr, int cap, Ctrl *ctrl) {
   const int lane = threadIdx.x;
-  int n = n_ptr ? *n_ptr : 0;
+  const int n = n_ptr ? *n_ptr : 0;
   if (n <= 0) return;
-  if (out && n > cap) { if (lane == 0) le_raise(ctrl, LE_DERR_RNG_OVERFLOW, n, cap); return; }
-  // unroll the circular state into chronological order: ring[k] = raw_{base+k}, k = 0..96
+  if (n > cap) { if (lane == 0) le_raise(ctrl, LE_DERR_RNG_OVERFLOW, n, cap); return; }
+  __shared__ int ring[224];
   for (int k = lane; k < 97; k += 32) ring[k] = st->s[(st->head + k) % 97];
-  long long c = st->c;
   __syncwarp();
-  const long long CD = 7654321, CM = 16777213;
-  int w = 97;                 // next write position (monotone, masked on access)
-  for (int base = 0; base < n; base += 32) {
-    const int a = ring[(w + lane - 97) & 255];
-    const int b = ring[(w + lane - 33) & 255];
-    int raw = a - b;
+  for (int w = 97; w < 193; w += 32) {
+    int raw = ring[w + lane - 97] - ring[w + lane - 33];
     if (raw < 0) raw += 16777216;
-    // c after (base+lane+1) further decrements
-    long long cc = (c - ((long long)(lane + 1) * CD) % CM) % CM;
-    if (cc < 0) cc += CM;
+    __syncwarp();
+    ring[w + lane] = raw;
+    __syncwarp();
+  }
+  for (int k = lane; k < 193; k += 32) base[k] = ring[k];
+  if (lane == 0) base[200] = st->c;   // the chunk warps must not read st: the last chunk rewrites it
+}
+
+// one warp per chunk of RM_CHUNK draws
+__global__ void __launch_bounds__(128) k_ranmars_chunks(RngDev *st, const int *__restrict__ base, const unsigned *__restrict__ jump,
+                                                        double *out, const int *n_ptr, int cap) {
+  __shared__ int rings[4][256];
+  __shared__ int sbase[193];
+  const int n = n_ptr ? *n_ptr : 0;
+  if (n <= 0 || n > cap) return;
+  const int nchunks = (n + RM_CHUNK - 1) / RM_CHUNK;
+  if ((int)blockIdx.x * 4 >= nchunks) return;
+  for (int k = threadIdx.x; k < 193; k += blockDim.x) sbase[k] = base[k];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  const int w = blockIdx.x * 4 + wl;
+  if (w >= nchunks) return;
+  int *ring = rings[wl];
+  // start state of this chunk: raw_{wK+i} = sum_j a_j raw_{i+j}
+  if (w == 0) {
+    for (int i = lane; i < 97; i += 32) ring[i] = sbase[i];
+  } else {
+    const unsigned *a = jump + (size_t)(w - 1) * 97;
+    for (int i = lane; i < 97; i += 32) {
+      unsigned long long acc = 0;
+      for (int j = 0; j < 97; j++) acc += (unsigned long long)__ldg(&a[j]) * (unsigned)sbase[i + j];
+      ring[i] = (int)(acc & 0xffffffu);
+    }
+  }
+  __syncwarp();
+  const long long first = (long long)w * RM_CHUNK;          // draws before this chunk
+  const long long cst = base[200];
+  long long c0 = (cst - (first % RM_CM) * RM_CD % RM_CM) % RM_CM;
+  if (c0 < 0) c0 += RM_CM;
+  const int count = min(RM_CHUNK, n - (int)first);
+  int wp = 97;
+  for (int b = 0; b < count; b += 32) {
+    int raw = ring[(wp + lane - 97) & 255] - ring[(wp + lane - 33) & 255];
+    if (raw < 0) raw += 16777216;
+    long long cc = (c0 - ((long long)(b + lane + 1) * RM_CD) % RM_CM) % RM_CM;
+    if (cc < 0) cc += RM_CM;
     int v = raw - (int)cc;
     if (v < 0) v += 16777216;
     __syncwarp();
-    ring[(w + lane) & 255] = raw;
-    if (out && base + lane < n) out[base + lane] = (double)v * (1.0 / 16777216.0);
+    ring[(wp + lane) & 255] = raw;
+    if (b + lane < count) out[first + b + lane] = (double)v * (1.0 / 16777216.0);
     __syncwarp();
-    // advance by min(32, remaining): only whole batches except possibly the last
-    const int adv = min(32, n - base);
-    c = (c - ((long long)adv * CD) % CM) % CM;
-    if (c < 0) c += CM;
-    w += adv;
-    if (adv < 32) break;
+    wp += min(32, count - b);
   }
-  __syncwarp();
-  // store the last 97 raw values back, oldest first
-  for (int k = lane; k < 97; k += 32) st->s[k] = ring[(w - 97 + k) & 255];
-  if (lane == 0) { st->head = 0; st->c = (int)c; st->consumed += n; }
+  // the chunk that holds the last draw leaves the new generator state: raw_n .. raw_{n+96}
+  if (w == nchunks - 1) {
+    __syncwarp();
+    long long cn = (cst - ((long long)n % RM_CM) * RM_CD % RM_CM) % RM_CM;
+    if (cn < 0) cn += RM_CM;
+    __syncwarp();
+    for (int k = lane; k < 97; k += 32) st->s[k] = ring[(wp - 97 + k) & 255];
+    if (lane == 0) { st->head = 0; st->c = (int)cn; st->consumed += n; }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -186,14 +280,15 @@ __global__ void k_compact(const int *flag, const int *scan, int n, int *tasks) {
 // helpers: tag-indexed access to the live state
 // ------------------------------------------------------------------------------------------------
 struct LeView {
-  Dev d; LeFixDev f; int cur;
+  Dev d; LeFixDev f;
+  __device__ __forceinline__ int cur() const { return d.ctrl->cur; }   // position buffer holding the current coordinates
 };
 
 // the coordinate the reference holds for an OWNED atom between reneighborings: wrapped at the last
 // rebuild (Domain::pbc runs only then, src/verlet.cpp:272), drifting freely since
 __device__ __forceinline__ void raw_xyz(const LeView &V, int tag, double x[3]) {
   const int k = V.d.map[tag - 1];
-  const int4 p = V.d.pos[V.cur][k];
+  const int4 p = V.d.pos[V.cur()][k];
   const int im = V.d.img[k], ih = V.d.img_hold[k];
   const unsigned u[3] = {(unsigned)p.x, (unsigned)p.y, (unsigned)p.z};
   const int di[3] = {(im & 1023) - (ih & 1023), ((im >> 10) & 1023) - ((ih >> 10) & 1023), ((im >> 20) & 1023) - ((ih >> 20) & 1023)};
@@ -204,12 +299,22 @@ __device__ __forceinline__ void raw_xyz(const LeView &V, int tag, double x[3]) {
     x[q] = v;
   }
 }
+// image of bond partner p closest to atom t at the last rebuild, as shifts -1/0/+1 per dimension packed 2 bits
+// each (+1 bias; 21 = same image): Domain::closest_image picks a ghost exactly when a shift is non-zero, and then
+// the reference's bondlist holds the bond twice (src/ntopo_bond_all.cpp:65-66)
+__device__ __forceinline__ int bond_cross_code(const Dev &d, int t, int p) {
+  const int4 a = d.pos_hold[d.map[t - 1]], b = d.pos_hold[d.map[p - 1]];
+  const int h0 = le_image_shift((unsigned)a.x, (unsigned)b.x);
+  const int h1 = le_image_shift((unsigned)a.y, (unsigned)b.y);
+  const int h2 = le_image_shift((unsigned)a.z, (unsigned)b.z);
+  return (h0 + 1) | ((h1 + 1) << 2) | ((h2 + 1) << 4);
+}
 __device__ __forceinline__ double dist2(const double a[3], const double b[3]) {
   const double dx = __dsub_rn(a[0], b[0]), dy = __dsub_rn(a[1], b[1]), dz = __dsub_rn(a[2], b[2]);
   return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 __device__ __forceinline__ int type_of(const LeView &V, int tag) {
-  return (V.d.pos[V.cur][V.d.map[tag - 1]].w & 0xff) + 1;
+  return (V.d.pos[V.cur()][V.d.map[tag - 1]].w & 7) + 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -415,7 +520,7 @@ __global__ void k_ext_visits(LeView V, ExtrusionArgs A) {
       if (d.bond_type[(size_t)i * d.bpa + m] != A.btype) continue;
       const int p = d.bond_atom[(size_t)i * d.bpa + m];
       // NTopoBondAll::build, newton_bond off: listed from atom i iff i < closest image of p
-      if (!(d.bond_cross[(size_t)i * d.bpa + m] != 21 || (i + 1) < p)) continue;
+      if (!((i + 1) < p || bond_cross_code(d, i + 1, p) != 21)) continue;
       const int a = min(i + 1, p), b = max(i + 1, p);
       const int nba = d.num_bond[a - 1], nbb = d.num_bond[b - 1];
       if (nba == 1 || nbb == 1 || nba == 0 || nbb == 0 || f.bondcount[a - 1] != 1 || f.bondcount[b - 1] != 1) continue;
@@ -630,7 +735,7 @@ __global__ void k_unl_candidates(LeView V, UnloadArgs A) {
     for (int m = 0; m < nb; m++) {
       if (d.bond_type[(size_t)i * d.bpa + m] != A.btype) continue;
       const int p = d.bond_atom[(size_t)i * d.bpa + m];
-      const int code = d.bond_cross[(size_t)i * d.bpa + m];
+      const int code = bond_cross_code(d, i + 1, p);
       double xi[3], xp[3];
       double rsq;
       if (code == 21) {           // one visit, from the lower tag: (x[lo] - x[hi])
@@ -693,67 +798,89 @@ __global__ void k_load_init(LeView V, int btype) {
 }
 
 // static part of the half-list scan for the pair (t, t+2), t = i+1 (fix_ex_load.cpp:447-494).
-// ex13 bit0: pair is in the half list of the last rebuild; bit1: stored on the lower tag; bit2: the
-// stored neighbor is a periodic ghost, whose num_bond the reference never communicates
-// (src/MOLECULE/atom_vec_bond.cpp:41) -- it reads 0 there, so such a pair is never eligible.
+// The list fix ex_load walks is the pair list of the LAST rebuild, so membership and
+// the atom the pair is stored on come from pos_hold: in the list iff rsq(pos_hold) <= cutneighsq (and not a 1-2
+// special, which is re-checked below exactly as the reference does); stored on the lower tag iff
+// le_pair_stored_on_i says so.  If the stored neighbor is a periodic ghost the reference reads the ghost's
+// num_bond, which is never communicated (src/MOLECULE/atom_vec_bond.cpp:41) and is 0: never eligible.
+// flag[i] = 0 not eligible, 1 eligible and stored on the upper tag, 2 eligible and stored on the lower tag.
 __global__ void k_load_eligible(LeView V, LoadArgs A) {
   const Dev &d = V.d; const LeFixDev &f = V.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) {
     int ok = 0;
-    const int e = d.ex13[i];
-    if ((e & 1) && !(e & 4) && i + 2 < d.N) {
+    if (i + 2 < d.N) {
       const int lo = i + 1, hi = i + 3, mid = i + 2;
-      const int ti = (e & 2) ? lo : hi, tj = (e & 2) ? hi : lo;     // list owner / stored neighbor
-      const int itype = type_of(V, ti), jtype = type_of(V, tj);
-      int possible = 0;
-      if (itype == A.itype && jtype == A.jtype) {
-        if ((A.imax == 0 || f.bondcount[ti - 1] < A.imax) && (A.jmax == 0 || f.bondcount[tj - 1] < A.jmax)) possible = 1;
-      } else if (itype == A.jtype && jtype == A.itype) {
-        if ((A.jmax == 0 || f.bondcount[ti - 1] < A.jmax) && (A.imax == 0 || f.bondcount[tj - 1] < A.imax)) possible = 1;
-      }
-      if (possible && d.num_bond[ti - 1] == 2 && d.num_bond[tj - 1] == 2 && d.num_bond[mid - 1] == 2) {
-        const int *sl = d.special + (size_t)(ti - 1) * d.maxspecial;
-        const int n1 = d.nspecial[(size_t)(ti - 1) * 3];
-        for (int k = 0; k < n1; k++) if (sl[k] == tj) possible = 0;
-        if (possible) {
-          double xi[3], xj[3];
-          raw_xyz(V, ti, xi); raw_xyz(V, tj, xj);
-          const double rsq = dist2(xi, xj);
-          if (rsq < A.cutsq) { ok = 1; f.prob[i] = rsq; }
+      if (d.num_bond[lo - 1] == 2 && d.num_bond[hi - 1] == 2 && d.num_bond[mid - 1] == 2) {
+        const int4 plo = d.pos_hold[d.map[lo - 1]], phi = d.pos_hold[d.map[hi - 1]];
+        const unsigned ulo[3] = {(unsigned)plo.x, (unsigned)plo.y, (unsigned)plo.z};
+        const unsigned uhi[3] = {(unsigned)phi.x, (unsigned)phi.y, (unsigned)phi.z};
+        const int tlo = plo.w & 7, thi = phi.w & 7;
+        if (le_pair_rsq_ref(c_P, ulo, uhi) <= c_P.cutneighsq[tlo * c_P.ntypes + thi]) {
+          int ghost;
+          const bool on_lo = le_pair_stored_on_i(c_P, ulo, uhi, lo, hi, &ghost);
+          if (!ghost) {
+            const int ti = on_lo ? lo : hi, tj = on_lo ? hi : lo;     // list owner / stored neighbor
+            const int itype = type_of(V, ti), jtype = type_of(V, tj);
+            int possible = 0;
+            if (itype == A.itype && jtype == A.jtype) {
+              if ((A.imax == 0 || f.bondcount[ti - 1] < A.imax) && (A.jmax == 0 || f.bondcount[tj - 1] < A.jmax)) possible = 1;
+            } else if (itype == A.jtype && jtype == A.itype) {
+              if ((A.jmax == 0 || f.bondcount[ti - 1] < A.jmax) && (A.imax == 0 || f.bondcount[tj - 1] < A.imax)) possible = 1;
+            }
+            if (possible) {
+              const int *sl = d.special + (size_t)(ti - 1) * d.maxspecial;
+              const int n1 = d.nspecial[(size_t)(ti - 1) * 3];
+              for (int k = 0; k < n1; k++) if (sl[k] == tj) possible = 0;
+            }
+            if (possible) {
+              double xi[3], xj[3];
+              raw_xyz(V, ti, xi); raw_xyz(V, tj, xj);
+              const double rsq = dist2(xi, xj);
+              if (rsq < A.cutsq) { ok = on_lo ? 2 : 1; f.prob[i] = rsq; }
+            }
+          }
         }
       }
     }
     f.flag[i] = ok;
+    f.done[i] = 0;
   }
 }
 
-struct LoadTask {
-  LeView V; const int *ntask_ptr;
-  __device__ int ntasks() const { return *ntask_ptr; }
-  // position in the half-list traversal: owner atom first (ilist is ascending), lower pair first
-  __device__ unsigned prio(int k) const {
-    const int i = V.f.tasks[k];
-    const int owner = (V.d.ex13[i] & 2) ? i + 1 : i + 3;
-    return (unsigned)owner * 2u + ((V.d.ex13[i] & 2) ? 1u : 0u);
+// The half-list scan itself (fix_ex_load.cpp:433-505) is sequential: a pair is skipped when its middle bead has
+// already been claimed as somebody's partner.  Pair i touches beads i, i+1, i+2 only, so two eligible pairs
+// interact only if they are at most 2 apart: maximal chains of eligible pairs with gaps <= 2 ("runs") are
+// independent of each other.  One thread replays one run in the reference's traversal order -- owner atom
+// ascending (ilist), the pair stored on the upper tag before the one stored on the lower tag.
+__device__ __forceinline__ unsigned load_prio(int i, int flag) {
+  const int owner = (flag == 2) ? i + 1 : i + 3;
+  return (unsigned)owner * 2u + ((flag == 2) ? 1u : 0u);
+}
+__global__ void k_load_scan_runs(LeView V) {
+  const Dev &d = V.d; const LeFixDev &f = V.f;
+  const int N = d.N;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    if (f.flag[i] <= 0) continue;
+    if ((i >= 1 && f.flag[i - 1] > 0) || (i >= 2 && f.flag[i - 2] > 0)) continue;   // not the head of its run
+    for (;;) {
+      // the pending pair of this run that the sequential scan reaches first
+      int best = -1; unsigned bp = 0xffffffffu;
+      int p = i;
+      while (p >= 0) {
+        if (!f.done[p]) { const unsigned pr = load_prio(p, f.flag[p]); if (pr < bp) { bp = pr; best = p; } }
+        if (p + 1 < N && f.flag[p + 1] > 0) p = p + 1;
+        else if (p + 2 < N && f.flag[p + 2] > 0) p = p + 2;
+        else p = -1;
+      }
+      if (best < 0) break;
+      f.done[best] = 1;
+      if (f.partner[best + 1] != 0) continue;     // middle bead already claimed (fix_ex_load.cpp:471-476,484)
+      const double rsq = f.prob[best];
+      const int lo = best + 1, hi = best + 3;
+      if (rsq < f.distsq[lo - 1]) { f.partner[lo - 1] = hi; f.distsq[lo - 1] = rsq; }
+      if (rsq < f.distsq[hi - 1]) { f.partner[hi - 1] = lo; f.distsq[hi - 1] = rsq; }
+    }
   }
-  __device__ int beads(int k, int b[4]) const {
-    const int i = V.f.tasks[k];
-    b[0] = i; b[1] = i + 1; b[2] = i + 2;
-    return 3;
-  }
-  __device__ void exec(int k) {
-    const LeFixDev &f = V.f;
-    const int i = f.tasks[k];
-    if (f.partner[i + 1] != 0) return;     // middle bead already claimed (fix_ex_load.cpp:471-476,484)
-    const double rsq = f.prob[i];
-    const int lo = i + 1, hi = i + 3;
-    if (rsq < f.distsq[lo - 1]) { f.partner[lo - 1] = hi; f.distsq[lo - 1] = rsq; }
-    if (rsq < f.distsq[hi - 1]) { f.partner[hi - 1] = lo; f.distsq[hi - 1] = rsq; }
-  }
-};
-__global__ void __launch_bounds__(LE_EXEC_THREADS) k_load_scan(LeView V, const int *ntask) {
-  LoadTask T{V, ntask};
-  ordered_execute(T, V.f.claim, V.f.done);
 }
 
 __global__ void k_load_flag_partners(LeFixDev f, int n) {
@@ -782,10 +909,10 @@ __global__ void k_load_create(LeView V, LoadArgs A) {
     const int bc = f.bondcount[i] + 1;
     f.bondcount[i] = bc;
     const int k = d.map[i];
-    int4 *pp = &d.pos[V.cur][k];
-    const int ty = (pp->w & 0xff) + 1;
-    if (ty == A.itype) { if (bc == A.imax) pp->w = (pp->w & ~0xff) | (A.inew - 1); }
-    else { if (bc == A.jmax) pp->w = (pp->w & ~0xff) | (A.jnew - 1); }
+    int4 *pp = &d.pos[V.cur()][k];
+    const int ty = (pp->w & 7) + 1;
+    if (ty == A.itype) { if (bc == A.imax) pp->w = (pp->w & ~7) | (A.inew - 1); }
+    else { if (bc == A.jmax) pp->w = (pp->w & ~7) | (A.jnew - 1); }
     f.final_add[i] = p; f.final_add[p - 1] = ti;
     if (ti < p) atomicAdd(&f.counters[CNT_NCREATE], 1);
   }

@@ -82,6 +82,14 @@ extern "C" int le_fix_rng_consumed(le_ctx *c, int which, int64_t *ndraws) {
   return LE_OK;
 }
 
+// n (device-side count) draws of fix `idx`'s Marsaglia stream into lf.draws
+static void ranmars_fill(le_ctx *c, int idx, const int *n_ptr) {
+  LeFixDev &f = c->lf;
+  const int nchunks = (f.draws_cap + RM_CHUNK - 1) / RM_CHUNK;
+  LAUNCH(c, k_ranmars_base, 1, 32, (const RngDev *)(f.rngdev + idx), f.rm_base, n_ptr, f.draws_cap, c->d.ctrl);
+  LAUNCH(c, k_ranmars_chunks, (nchunks + 3) / 4, 128, f.rngdev + idx, (const int *)f.rm_base, (const unsigned *)f.rm_jump, f.draws, n_ptr, f.draws_cap);
+}
+
 static void iscan(le_ctx *c, const int *in, int *out, int n, int *total) {
   const int nb = (n + 1023) / 1024;
   LAUNCH(c, k_iscan_partial, nb, 1024, in, n, c->lf.blocksum);
@@ -98,21 +106,21 @@ static void compact_tasks(le_ctx *c) {
 static void draw_for_flagged(le_ctx *c, int idx, double fraction) {
   LeFixDev &f = c->lf;
   iscan(c, f.flag, f.scan, c->N, f.counters + CNT_NDRAW);
-  LAUNCH(c, k_ranmars_fill, 1, 32, f.rngdev + idx, f.draws, (const int *)(f.counters + CNT_NDRAW), f.draws_cap, c->d.ctrl);
+  ranmars_fill(c, idx, (const int *)(f.counters + CNT_NDRAW));
   LAUNCH(c, k_le_assign_draws, grid_for(c->N, 256), 256, f, c->N, (const int *)f.scan, fraction);
 }
 
 static int enqueue_extrusion(le_ctx *c) {
   int r = ensure_rng(c, 0, c->fx.seed); if (r) return r;
   LeFixDev &f = c->lf;
-  LeView V{c->d, f, c->cur};
+  LeView V{c->d, f};
   ExtrusionArgs A{c->fx.btype, c->fx.neutral, c->fx.left, c->fx.right, c->fx.roadblock, c->fx.p};
   const int g = grid_for(c->N, 256);
   LAUNCH(c, k_ext_init, g, 256, V, A.btype);
   LAUNCH(c, k_ext_visits, g, 256, V, A);
   compact_tasks(c);
   iscan(c, f.ndraw, f.scan2, c->N, f.counters + CNT_NDRAW);
-  LAUNCH(c, k_ranmars_fill, 1, 32, f.rngdev + 0, f.draws, (const int *)(f.counters + CNT_NDRAW), f.draws_cap, c->d.ctrl);
+  ranmars_fill(c, 0, (const int *)(f.counters + CNT_NDRAW));
   LAUNCH(c, k_ext_candidates, 1, LE_EXEC_THREADS, V, A, (const int *)(f.counters + CNT_NTASK));
   LAUNCH(c, k_ext_flag, g, 256, V, 0);
   compact_tasks(c);
@@ -131,7 +139,7 @@ static int enqueue_extrusion(le_ctx *c) {
 static int enqueue_unload(le_ctx *c) {
   int r = ensure_rng(c, 1, c->fu.seed); if (r) return r;
   LeFixDev &f = c->lf;
-  LeView V{c->d, f, c->cur};
+  LeView V{c->d, f};
   UnloadArgs A{c->fu.btype, c->fu.rc * c->fu.rc, c->fu.prob};
   const int g = grid_for(c->N, 256);
   LAUNCH(c, k_unl_candidates, g, 256, V, A);
@@ -151,13 +159,12 @@ static int enqueue_load(le_ctx *c) {
       return fail(c, LE_EINVAL, "Fix ex_load cutoff is longer than pairwise cutoff");
   }
   LeFixDev &f = c->lf;
-  LeView V{c->d, f, c->cur};
+  LeView V{c->d, f};
   LoadArgs A{c->fl.btype, c->fl.itype, c->fl.jtype, c->fl.imax, c->fl.inew, c->fl.jmax, c->fl.jnew, c->fl.rc * c->fl.rc, c->fl.prob};
   const int g = grid_for(c->N, 256);
   LAUNCH(c, k_load_init, g, 256, V, A.btype);
   LAUNCH(c, k_load_eligible, g, 256, V, A);
-  compact_tasks(c);
-  LAUNCH(c, k_load_scan, 1, LE_EXEC_THREADS, V, (const int *)(f.counters + CNT_NTASK));
+  LAUNCH(c, k_load_scan_runs, g, 256, V);
   LAUNCH(c, k_load_flag_partners, g, 256, f, c->N);
   if (A.fraction < 1.0) draw_for_flagged(c, 2, A.fraction);
   LAUNCH(c, k_load_create, g, 256, V, A);
