@@ -53,7 +53,8 @@ struct Params {
   // fp32 brackets around cutneighsq: below lo a pair is certainly listed, above hi certainly not; only the
   // sliver in between needs the reference's fp64 arithmetic (k_build)
   float cutneigh_lo[LE_MAXT * LE_MAXT], cutneigh_hi[LE_MAXT * LE_MAXT];
-  float t_start, t_stop;
+  float t_start, t_stop, tsqrt_const;
+  float dtfm[LE_MAXT];   // dtf / mass
   // integration / thermostat
   float dt, dtf;
   float triggersq;
@@ -132,12 +133,13 @@ __device__ __forceinline__ double le_deq(unsigned u, int d) {
   return __dadd_rn(c_P.lo[d], __dmul_rn((double)u, c_P.scale[d]));
 }
 
-// Philox4x32-10 (Salmon et al. 2011) -- counter-based generator for the Langevin noise
-__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3,
+// Philox4x32-7 (Salmon et al. 2011: seven rounds already pass BigCrush) -- counter-based generator for the
+// Langevin noise, keyed by (seed), counted by (tag, timestep)
+__device__ __forceinline__ void philox4x32_7(unsigned c0, unsigned c1, unsigned c2, unsigned c3,
                                               unsigned k0, unsigned k1, unsigned out[4]) {
   const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-  for (int r = 0; r < 10; r++) {
+  for (int r = 0; r < 7; r++) {
     unsigned hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
     unsigned hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
     unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;

@@ -449,7 +449,7 @@ static int build_params(le_ctx *c) {
     P.special_flag[k] = c->special_lj[k] == 0.0 ? 0 : c->special_lj[k] == 1.0 ? 1 : 2;
     if (P.special_flag[k] != 1) P.nscan_tier = k;
   }
-  for (int k = 0; k < nt; k++) P.mass[k] = (float)c->mass[k];
+  for (int k = 0; k < nt; k++) { P.mass[k] = (float)c->mass[k]; P.dtfm[k] = (float)(0.5 * c->dt / c->mass[k]); }
   for (int k = 0; k < c->nbondtypes; k++) {
     P.bstyle[k] = c->bstyle[k];
     P.bk[k] = (float)c->bparam[k][0]; P.br0[k] = (float)c->bparam[k][1];
@@ -460,7 +460,7 @@ static int build_params(le_ctx *c) {
     P.bsig2_d[k] = P.bsig_d[k] * P.bsig_d[k];
     P.bcore_d[k] = 1.2599210498948732 * P.bsig2_d[k];        // TWO_1_3 (bond_fene.cpp:22)
   }
-  P.t_start = (float)c->t_start; P.t_stop = (float)c->t_stop;
+  P.t_start = (float)c->t_start; P.t_stop = (float)c->t_stop; P.tsqrt_const = (float)sqrt(c->t_start);
   P.dt = (float)c->dt; P.dtf = (float)(0.5 * c->dt);       // FixNVE::init, ftm2v = 1
   P.triggersq = (float)(0.25 * c->skin * c->skin);
   P.vlimitsq = c->xlimit > 0.0 ? (float)((c->xlimit / c->dt) * (c->xlimit / c->dt)) : 0.0f;

@@ -54,32 +54,38 @@ __device__ __noinline__ double harmonic_fbond(double rsq, double k, double r0, d
   return (r > 0.0) ? -2.0 * rk / r : 0.0;
 }
 
-template <int EV>
-__device__ __forceinline__ void pair_term(ForceAcc &A, const int4 pi, const int4 pj, unsigned e, int ti, int nt,
-                                          float sx, float sy, float sz) {
+// fp32 screen of one listed pair on the exact fixed-point differences: inside (a hair more than) the force cutoff?
+__device__ __forceinline__ bool pair_screen(const int4 pi, const int4 pj, int ti, int nt, float sx, float sy, float sz) {
   const int idx = (int)((unsigned)pi.x - (unsigned)pj.x);
   const int idy = (int)((unsigned)pi.y - (unsigned)pj.y);
   const int idz = (int)((unsigned)pi.z - (unsigned)pj.z);
   const float dxf = (float)idx * sx, dyf = (float)idy * sy, dzf = (float)idz * sz;
   const float rsqf = dxf * dxf + dyf * dyf + dzf * dzf;
   const int tp = c_P.pair_uniform ? 0 : ti * nt + (pj.w & 7);
-  // fp32 screen; the (few) pairs inside the force cutoff are evaluated in fp64: r^-14 amplifies a 1e-7 error of
-  // r^2 sevenfold and the WCA/FENE terms of bonded neighbours cancel to ~10% of their size, so fp32 pair math
-  // cannot meet the 1e-5 per-atom bar
-  if (rsqf < c_P.cutsq_screen[tp]) {
-    const double dx = (double)idx * c_P.scale[0], dy = (double)idy * c_P.scale[1], dz = (double)idz * c_P.scale[2];
-    const double rsq = dx * dx + dy * dy + dz * dz;
-    if (rsq < c_P.cutsq_d[tp]) {
-      const double r2inv = le_rcp(rsq);
-      const double r6inv = r2inv * r2inv * r2inv;
-      const double factor = (double)c_P.special_lj[e >> 30];
-      const double fpair = factor * r6inv * (c_P.lj1_d[tp] * r6inv - c_P.lj2_d[tp]) * r2inv;
-      A.fx += dx * fpair; A.fy += dy * fpair; A.fz += dz * fpair;
-      if (EV) {
-        A.evdwl += factor * (r6inv * (c_P.lj3_d[tp] * r6inv - c_P.lj4_d[tp]) - c_P.offset_d[tp]);
-        A.pv[0] += dx * dx * fpair; A.pv[1] += dy * dy * fpair; A.pv[2] += dz * dz * fpair;
-        A.pv[3] += dx * dy * fpair; A.pv[4] += dx * dz * fpair; A.pv[5] += dy * dz * fpair;
-      }
+  return rsqf < c_P.cutsq_screen[tp];
+}
+
+// the (few) pairs inside the force cutoff are evaluated in fp64: r^-14 amplifies a 1e-7 error of r^2 sevenfold and
+// the WCA/FENE terms of bonded neighbours cancel to ~10% of their size, so fp32 pair math cannot meet the 1e-5
+// per-atom bar
+template <int EV>
+__device__ __forceinline__ void pair_term(ForceAcc &A, const int4 pi, const int4 pj, unsigned e, int ti, int nt) {
+  const int idx = (int)((unsigned)pi.x - (unsigned)pj.x);
+  const int idy = (int)((unsigned)pi.y - (unsigned)pj.y);
+  const int idz = (int)((unsigned)pi.z - (unsigned)pj.z);
+  const int tp = c_P.pair_uniform ? 0 : ti * nt + (pj.w & 7);
+  const double dx = (double)idx * c_P.scale[0], dy = (double)idy * c_P.scale[1], dz = (double)idz * c_P.scale[2];
+  const double rsq = dx * dx + dy * dy + dz * dz;
+  if (rsq < c_P.cutsq_d[tp]) {
+    const double r2inv = le_rcp(rsq);
+    const double r6inv = r2inv * r2inv * r2inv;
+    const double factor = (double)c_P.special_lj[e >> 30];
+    const double fpair = factor * r6inv * (c_P.lj1_d[tp] * r6inv - c_P.lj2_d[tp]) * r2inv;
+    A.fx += dx * fpair; A.fy += dy * fpair; A.fz += dz * fpair;
+    if (EV) {
+      A.evdwl += factor * (r6inv * (c_P.lj3_d[tp] * r6inv - c_P.lj4_d[tp]) - c_P.offset_d[tp]);
+      A.pv[0] += dx * dx * fpair; A.pv[1] += dy * dy * fpair; A.pv[2] += dz * dz * fpair;
+      A.pv[3] += dx * dy * fpair; A.pv[4] += dx * dz * fpair; A.pv[5] += dy * dz * fpair;
     }
   }
 }
@@ -172,9 +178,9 @@ __global__ void __launch_bounds__(STEP_THREADS, EV ? 2 : 4) k_step(Dev d, StepAr
     // ---- batch 2: the gathers ----
     int4 pn[STEP_NB], pb[STEP_BB];
 #pragma unroll
-    for (int k = 0; k < STEP_NB; k++) pn[k] = (k < nn) ? __ldg(&posr[en[k] & NEIGH_IDX_MASK]) : pi;
+    for (int k = 0; k < STEP_NB; k++) pn[k] = __ldg(&posr[(k < nn) ? (int)(en[k] & NEIGH_IDX_MASK) : i]);
 #pragma unroll
-    for (int m = 0; m < STEP_BB; m++) pb[m] = (m < nb) ? __ldg(&posr[eb[m] & BOND_IDX_MASK]) : pi;
+    for (int m = 0; m < STEP_BB; m++) pb[m] = __ldg(&posr[(m < nb) ? (int)(eb[m] & BOND_IDX_MASK) : i]);
 
     ForceAcc A;
     A.fx = A.fy = A.fz = 0.0;
@@ -183,13 +189,25 @@ __global__ void __launch_bounds__(STEP_THREADS, EV ? 2 : 4) k_step(Dev d, StepAr
 #pragma unroll
       for (int q = 0; q < 6; q++) { A.pv[q] = 0.0; A.bv[q] = 0.0; }
     }
+    // screen every listed pair in fp32; the survivors (about one pair in five) are queued as a bit mask and
+    // evaluated by one fp64 loop, so a warp runs the fp64 code max-over-lanes(#survivors) times, not once per slot
+    unsigned hit = 0;
 #pragma unroll
     for (int k = 0; k < STEP_NB; k++)
-      if (k < nn) pair_term<EV>(A, pi, pn[k], en[k], ti, nt, sx, sy, sz);
-    for (int k = STEP_NB; k < nn; k++) {
-      const unsigned e = __ldg(&neigh[(size_t)k * N + i]);
-      const int4 pj = __ldg(&posr[e & NEIGH_IDX_MASK]);
-      pair_term<EV>(A, pi, pj, e, ti, nt, sx, sy, sz);
+      if (k < nn && pair_screen(pi, pn[k], ti, nt, sx, sy, sz)) hit |= 1u << k;
+    for (int k = STEP_NB; k < nn; k += 2) {          // rows beyond the first batch, two at a time
+      const int k1 = min(k + 1, nn - 1);
+      const unsigned e0 = __ldg(&neigh[(size_t)k * N + i]), e1 = __ldg(&neigh[(size_t)k1 * N + i]);
+      const int4 p0 = __ldg(&posr[e0 & NEIGH_IDX_MASK]), p1 = __ldg(&posr[e1 & NEIGH_IDX_MASK]);
+      if (pair_screen(pi, p0, ti, nt, sx, sy, sz)) pair_term<EV>(A, pi, p0, e0, ti, nt);
+      if (k1 > k && pair_screen(pi, p1, ti, nt, sx, sy, sz)) pair_term<EV>(A, pi, p1, e1, ti, nt);
+    }
+    while (hit) {
+      const int k = __ffs(hit) - 1;
+      hit &= hit - 1;
+      const unsigned e = k == 0 ? en[0] : k == 1 ? en[1] : k == 2 ? en[2] : en[3];
+      const int4 pj = __ldg(&posr[e & NEIGH_IDX_MASK]);     // second touch: an L1 hit
+      pair_term<EV>(A, pi, pj, e, ti, nt);
     }
 #pragma unroll
     for (int m = 0; m < STEP_BB; m++)
@@ -210,12 +228,11 @@ __global__ void __launch_bounds__(STEP_THREADS, EV ? 2 : 4) k_step(Dev d, StepAr
     float lx = 0.f, ly = 0.f, lz = 0.f;
     if (a.langevin) {
       unsigned r[4];
-      philox4x32_10((unsigned)tag, (unsigned)(step & 0xffffffffll), (unsigned)((unsigned long long)step >> 32), 0x4c45u,
+      philox4x32_7((unsigned)tag, (unsigned)(step & 0xffffffffll), (unsigned)((unsigned long long)step >> 32), 0x4c45u,
                     c_P.seed_lo, c_P.seed_hi, r);
       // FixLangevin::compute_target (src/fix_langevin.cpp:784-820): linear ramp over the run
-      float tsq;
-      if (c_P.t_start == c_P.t_stop) tsq = sqrtf(c_P.t_start);
-      else {
+      float tsq = c_P.tsqrt_const;
+      if (c_P.t_start != c_P.t_stop) {
         float delta = (float)(step - ctrl->run_begin);
         if (delta != 0.0f) delta /= (float)(ctrl->run_end - ctrl->run_begin);
         tsq = sqrtf(c_P.t_start + delta * (c_P.t_stop - c_P.t_start));
@@ -231,7 +248,7 @@ __global__ void __launch_bounds__(STEP_THREADS, EV ? 2 : 4) k_step(Dev d, StepAr
 
     // ---- velocity Verlet ----
     const float m = c_P.mass[ti];
-    const float dtfm = c_P.dtf / m;
+    const float dtfm = c_P.dtfm[ti];
     const float ffx = (float)fx + lx, ffy = (float)fy + ly, ffz = (float)fz + lz;
     if (a.do_final) {
       vi.x += dtfm * ffx; vi.y += dtfm * ffy; vi.z += dtfm * ffz;
