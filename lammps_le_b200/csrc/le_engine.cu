@@ -637,15 +637,17 @@ extern "C" int le_upload_bonds(le_ctx *c, int nbonds, const int *btype, const in
   }
   // special lists: 1-2 = bond partners; 1-3 = partners of partners; 1-4 = partners of 1-3; each tier without
   // self and without anything already listed (Special::build + combine, src/special.cpp:55-154,611-762)
+  // tiers whose weight (and every later one) is 1.0 are not built at all (special.cpp:92-101,111-121)
+  const int ntier = (c->special_lj[2] == 1.0 && c->special_lj[3] == 1.0) ? 1 : (c->special_lj[3] == 1.0 ? 2 : 3);
   std::vector<int> tmp;
   for (int i = 0; i < n; i++) {
     tmp.clear();
     auto have = [&](int t) { return t == i + 1 || std::find(tmp.begin(), tmp.end(), t) != tmp.end(); };
     for (int m = 0; m < nb[i]; m++) { int t = ba[(size_t)i * bpa + m]; if (!have(t)) tmp.push_back(t); }
     const int n1 = (int)tmp.size();
-    for (int a = 0; a < n1; a++) { int j = tmp[a] - 1; for (int m = 0; m < nb[j]; m++) { int t = ba[(size_t)j * bpa + m]; if (!have(t)) tmp.push_back(t); } }
+    for (int a = 0; a < n1 && ntier >= 2; a++) { int j = tmp[a] - 1; for (int m = 0; m < nb[j]; m++) { int t = ba[(size_t)j * bpa + m]; if (!have(t)) tmp.push_back(t); } }
     const int n2 = (int)tmp.size();
-    for (int a = n1; a < n2; a++) { int j = tmp[a] - 1; for (int m = 0; m < nb[j]; m++) { int t = ba[(size_t)j * bpa + m]; if (!have(t)) tmp.push_back(t); } }
+    for (int a = n1; a < n2 && ntier >= 3; a++) { int j = tmp[a] - 1; for (int m = 0; m < nb[j]; m++) { int t = ba[(size_t)j * bpa + m]; if (!have(t)) tmp.push_back(t); } }
     const int n3 = (int)tmp.size();
     if (n3 > ms) return fail(c, LE_EINVAL, "special list of atom %d needs %d entries > maxspecial=%d", i + 1, n3, ms);
     ns[(size_t)i * 3] = n1; ns[(size_t)i * 3 + 1] = n2; ns[(size_t)i * 3 + 2] = n3;

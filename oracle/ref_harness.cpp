@@ -15,6 +15,7 @@
 // Private members are reached with a test-only `#define private public`; nothing in the reference is edited.
 //
 // usage:  ref_harness -in deck [-final out.bin] [other lmp options]
+//         ref_harness -ranmars SEED N -log none        (prints N draws of RanMars(SEED))
 //         deck line:  fix ID all le/snap <file> <pre|post> [grid]
 #include <cmath>
 #include <cstdint>
@@ -218,8 +219,10 @@ int main(int argc, char **argv) {
   MPI_Init(&argc, &argv);
   const char *final_file = nullptr;
   int grid_final = 0;
+  int mars_seed = 0, mars_n = 0;
   std::vector<char *> args;
   for (int k = 0; k < argc; k++) {
+    if (strcmp(argv[k], "-ranmars") == 0 && k + 2 < argc) { mars_seed = atoi(argv[++k]); mars_n = atoi(argv[++k]); continue; }
     if (strcmp(argv[k], "-final") == 0 && k + 1 < argc) { final_file = argv[++k]; continue; }
     if (strcmp(argv[k], "-gridfinal") == 0) { grid_final = 1; continue; }
     args.push_back(argv[k]);
@@ -228,6 +231,14 @@ int main(int argc, char **argv) {
   try {
     LAMMPS *lammps = new LAMMPS((int)args.size(), args.data(), MPI_COMM_WORLD);
     (*lammps->modify->fix_map)["le/snap"] = &make_snap;
+    if (mars_seed > 0) {
+      // known-answer vectors of the reference's own RanMars (src/random_mars.cpp): exact doubles as hex floats
+      RanMars rm(lammps, mars_seed);
+      for (int k = 0; k < mars_n; k++) printf("RANMARS %a\n", rm.uniform());
+      delete lammps;
+      MPI_Finalize();
+      return 0;
+    }
     lammps->input->file();
     if (final_file) {
       (void)grid_final;

@@ -1,0 +1,173 @@
+"""CPU tests: the oracle restatement (oracle/restate.py) against the golden vectors.
+
+Pins the oracle on (1) the reference's own unit-test vectors (tests/golden/ref_yaml_*.npz, extracted from
+unittest/force-styles/tests/*.yaml by oracle/extract_ref_yaml.py) and (2) outputs of the compiled reference
+(tests/golden/forces_chain.npz, le_trace_small.npz; oracle/make_golden.py).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import restate as R
+from oracle.make_golden import unpack_trace
+from oracle import refio
+from tests import lehelpers as H
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CHROMATIN_BONDS = {1: ("fene", (30.0, 1.5, 1.0, 1.0)), 2: ("harmonic", (20.0, 1.3))}
+
+
+def test_ranmars_counter_and_range():
+    r = R.RanMars(12345)
+    vals = [r.uniform() for _ in range(1000)]
+    assert all(0.0 <= v < 1.0 for v in vals)
+    assert all(v * 16777216.0 == int(v * 16777216.0) for v in vals)      # 24-bit values: the GPU integer restatement is exact
+    assert refio.draws_consumed(r.c24()) == 1000 == r.ncalls
+    # known answers: first draws of the seeds the decks use, as the compiled reference produced them
+    z = np.load(os.path.join(GOLD, "ranmars_ref.npz"))
+    for seed, ref in zip(z["seeds"], z["draws"]):
+        rr = R.RanMars(int(seed))
+        got = np.array([rr.uniform() for _ in range(ref.shape[0])])
+        assert (got == ref).all(), "RanMars(%d) differs from the reference" % seed
+
+
+@pytest.fixture(scope="module")
+def force_rec():
+    z = np.load(os.path.join(GOLD, "forces_chain.npz"))
+    rec = {k: z[k] for k in z.files}
+    return rec
+
+
+def test_special_build_matches_reference(force_rec):
+    got = R.special_build(force_rec["num_bond"], force_rec["bond_atom"], special_lj=(0.0, 1.0, 1.0))   # special_bonds fene
+    ref = R.special_tiers(force_rec["nspecial"], force_rec["special"])
+    assert got == ref
+
+
+def test_bond_list_matches_reference(force_rec):
+    L = force_rec["boxhi"] - force_rec["boxlo"]
+    bl = R.bond_list(force_rec["x"], L, force_rec["num_bond"], force_rec["bond_type"], force_rec["bond_atom"])
+    assert bl.shape == force_rec["bondlist"].shape and (bl == force_rec["bondlist"]).all()
+
+
+def test_half_neighbor_list_matches_reference(force_rec):
+    rows = R.half_neighbor_list(force_rec["x"], force_rec["boxlo"], force_rec["boxhi"], 1.12246 + 0.4,
+                                force_rec["nspecial"], force_rec["special"])
+    ref = H.neigh_sets(force_rec["neigh_offsets"], force_rec["neigh_entries"])
+    bad = [t + 1 for t in range(len(rows)) if frozenset(rows[t]) != ref[t]]
+    assert not bad, "half-list sets differ for tags %s" % bad[:10]
+
+
+def test_forces_energy_virial_match_reference(force_rec):
+    x = force_rec["x"]
+    n = len(x)
+    L = force_rec["boxhi"] - force_rec["boxlo"]
+    off, ent = force_rec["neigh_offsets"], force_rec["neigh_entries"]
+    pi = np.repeat(np.arange(n), np.diff(off))
+    pj = (ent & R.NEIGHMASK) - 1
+    which = (ent >> R.SBBITS) & 3
+    co = R.lj_coeffs(1.0, 1.0, 1.12246, True)
+    fp, evdwl, vp = R.pair_lj_cut(x, L, pi, pj, which, co)
+    b1, b2, bt = R.unique_bonds(force_rec["num_bond"], force_rec["bond_type"], force_rec["bond_atom"])
+    fb, eb, vb, _ = R.bond_forces(x, L, b1, b2, bt, CHROMATIN_BONDS)
+    f = fp + fb
+    fr = force_rec["f"]
+    mag = np.sqrt((fr ** 2).sum(1))
+    err = np.sqrt(((f - fr) ** 2).sum(1)) / np.maximum(mag, np.sqrt((mag ** 2).mean()))
+    assert err.max() < 1e-11
+    assert abs(evdwl - force_rec["energy"][0]) <= 1e-10 * abs(force_rec["energy"][0])
+    assert abs(eb - force_rec["energy"][1]) <= 1e-10 * abs(force_rec["energy"][1])
+    assert np.abs(vp - force_rec["virial_pair"]).max() <= 1e-9 * np.abs(force_rec["virial_pair"]).max()
+    assert np.abs(vb - force_rec["virial_bond"]).max() <= 1e-9 * np.abs(force_rec["virial_bond"]).max()
+
+
+def _yaml_case(name):
+    p = os.path.join(GOLD, "ref_yaml_%s.npz" % name)
+    z = np.load(p, allow_pickle=False)
+    return {k: z[k] for k in z.files}
+
+
+def test_reference_unit_vectors_lj_cut():
+    """unittest/force-styles/tests/mol-pair-lj_cut.yaml: init_forces / init_vdwl / init_stress of the 29-atom molecule"""
+    c = _yaml_case("mol-pair-lj_cut")
+    x, typ = c["x"], c["type"]
+    n = len(x)
+    L = c["boxhi"] - c["boxlo"]
+    # all pairs within the pair cutoff; special weights from special_tiers (special_bonds lj 0 0 0 of the yaml's prerequisites)
+    tiers = R.special_build(c["num_bond"], c["bond_atom"])
+    # the 8.0 cutoff exceeds half the 15.0 box: a pair can see more than one periodic image, each is a ghost of its own.
+    # Special weights apply to every image of a special partner (the list stores them per local/ghost index by tag).
+    import itertools
+    pi, pj, which, sh = [], [], [], []
+    for i in range(n - 1):
+        for j in range(i + 1, n):
+            w = 0
+            for k in range(3):
+                if (j + 1) in tiers[i][k]:
+                    w = k + 1
+            for s in itertools.product((-1, 0, 1), repeat=3):
+                pi.append(i); pj.append(j); which.append(w); sh.append(s)
+    pi, pj, which, sh = np.array(pi), np.array(pj), np.array(which), np.array(sh, float)
+    eps, sig, cut = c["epsilon"], c["sigma"], c["cut"]     # [ntypes, ntypes] after mixing, as the yaml's pair_coeff lines give them
+    ti, tj = typ[pi] - 1, typ[pj] - 1
+    co = {k: np.empty(len(pi)) for k in ("lj1", "lj2", "lj3", "lj4", "offset", "cutsq")}
+    for a in range(eps.shape[0]):
+        for b in range(eps.shape[0]):
+            m = (ti == a) & (tj == b)
+            cc = R.lj_coeffs(eps[a, b], sig[a, b], cut[a, b], False)
+            for k in co:
+                co[k][m] = cc[k]
+    f, evdwl, vir = R.pair_lj_cut(x, L, pi, pj, which, co, special_lj=tuple(c["special_lj"]), shift=sh)
+    assert np.abs(f - c["init_forces"]).max() <= 5e-13 * max(1.0, np.abs(c["init_forces"]).max())
+    assert abs(evdwl - c["init_vdwl"]) <= 5e-13 * abs(c["init_vdwl"])
+    assert np.abs(vir - c["init_stress"]).max() <= 5e-13 * np.abs(c["init_stress"]).max()
+
+
+@pytest.mark.parametrize("name", ["bond-fene", "bond-harmonic"])
+def test_reference_unit_vectors_bonds(name):
+    """unittest/force-styles/tests/bond-fene.yaml / bond-harmonic.yaml: init_forces / init_energy / init_stress"""
+    c = _yaml_case(name)
+    x = c["x"]
+    L = c["boxhi"] - c["boxlo"]
+    style = "fene" if name == "bond-fene" else "harmonic"
+    coeffs = {k + 1: (style, tuple(c["bond_coeff"][k])) for k in range(len(c["bond_coeff"]))}
+    b1, b2, bt = R.unique_bonds(c["num_bond"], c["bond_type"], c["bond_atom"])
+    f, e, vir, _ = R.bond_forces(x, L, b1, b2, bt, coeffs)
+    assert np.abs(f - c["init_forces"]).max() <= 5e-13 * np.abs(c["init_forces"]).max()
+    assert abs(e - c["init_energy"]) <= 5e-13 * abs(c["init_energy"])
+    assert np.abs(vir - c["init_stress"]).max() <= 5e-13 * np.abs(c["init_stress"]).max()
+
+
+def test_le_events_replay_golden_trace():
+    """every recorded USER-LE event of the compiled reference: oracle post-state == reference post-state, bit-exact
+    bond rows, special lists in exact order, types, counters and number of Marsaglia draws"""
+    pre, post = unpack_trace(np.load(os.path.join(GOLD, "le_trace_small.npz")))
+    cfg = H.LE_DECK
+    seen = {1: 0, 2: 0, 3: 0}
+    for a, b in zip(pre, post):
+        w = a["which"]
+        S = R.copy_state(a)
+        slot = H.RNG_SLOT[w]
+        rng = R.RanMars(cfg[H.SEED_KEY[w]]["seed"]).skip(refio.draws_consumed(a["rngc"][slot]))
+        L = S["L"]
+        # the lists of the last rebuild are part of the recorded pre-state; the restated bond list must equal it
+        bl = R.bond_list(a["xhold"], L, a["num_bond"], a["bond_type"], a["bond_atom"])
+        assert bl.shape == a["bondlist"].shape and (bl == a["bondlist"]).all()
+        if w == 1:
+            c = cfg["extrusion"]
+            cnt, _ = R.fix_extrusion(S, rng, c["neutral"], c["left"], c["right"], c["p_through"], c["btype"], c["roadblock"])
+        elif w == 2:
+            c = cfg["ex_unload"]
+            cnt = R.fix_ex_unload(S, rng, c["btype"], c["rc"], c["prob"])
+        else:
+            c = cfg["ex_load"]
+            cnt = R.fix_ex_load(S, rng, c["itype"], c["jtype"], c["rc"], c["btype"], c["prob"], c["iparam"][0], c["iparam"][1],
+                                c["jparam"][0], c["jparam"][1], a["neigh_offsets"], a["neigh_entries"])
+        res = H.compare_topology(S, b)
+        assert not any(res.values()), "event step %d fix %d: %s" % (a["step"], w, res)
+        assert (S["type"] == b["type"]).all()
+        assert cnt == b["counters"][w - 1]
+        assert rng.c24() == b["rngc"][slot], "draw count differs at step %d fix %d" % (a["step"], w)
+        seen[w] += 1
+    assert seen[1] >= 3 and seen[2] >= 1 and seen[3] >= 1
