@@ -164,6 +164,25 @@ int le_get_stats(le_ctx *c, le_stats *out);
 /* radius of gyration of the whole system from unwrapped coordinates (compute gyration) */
 int le_compute_rg(le_ctx *c, double *rg);
 
+/* ---- several GPUs of one box: spatial domain decomposition (Comm/CommBrick, src/comm_brick.cpp:452-876) -----------
+ * One process (and one le_ctx) per GPU.  The box is cut into x-slabs of neighbor cells; each GPU owns one slab plus
+ * `halo_distance` (>= the neighbor cutoff; pass the longest bond + 2 backbone bonds when USER-LE fixes are used) of
+ * ghost cells on either side.  Ghost positions are stored by the owning GPU's integrator straight into the
+ * neighbor's memory over NVLink (CUDA IPC peer mappings), atoms migrate at every reneighboring, bond / special
+ * tables are replicated by tag so an extruder's bonds arrive with its beads.  Every rank makes the SAME sequence of
+ * calls with the SAME (global) arguments; uploads take the whole system, downloads fill only the entries of the atoms
+ * the GPU owns (the caller zero-fills and sums over ranks).
+ *   le_dd_init        after le_create, before le_upload_atoms
+ *   le_dd_get_handle  after le_upload_atoms: 64-byte CUDA IPC handle of this GPU's peer-visible arena
+ *   le_dd_connect     handles of all ranks (all-gathered by the caller, e.g. torch.distributed), rank-major */
+int le_dd_init(le_ctx *c, int rank, int nranks, double halo_distance);
+int le_dd_get_handle(le_ctx *c, void *handle64);
+int le_dd_connect(le_ctx *c, const void *handles);
+/* raw per-GPU tallies behind a thermo record / the last le_compute_forces: [16] = sum m v^2, evdwl, ebond,
+ * virial[6], FENE warnings, ... (multi-GPU callers sum over ranks before normalising) */
+int le_get_thermo_sums(const le_ctx *c, int index, double *out16);
+int le_get_force_sums(const le_ctx *c, double *out16);
+
 /* ---- synthetic inputs (host only; bench and tests) -------------------------------------------- */
 /* self-avoiding walk(s) of n beads in a periodic cube [0,L)^3: bond length `step`, no two beads closer
  * than rmin; x[n*3] wrapped coordinates, image[n] LAMMPS-packed image flags (may be NULL) */

@@ -1,17 +1,22 @@
 // le_common.cuh -- device data layout and small helpers shared by every kernel.
 //
-// Layout in HBM (N atoms, all arrays device-resident for the life of the context):
-//   sorted order (index k = position after the last cell sort; rewritten at every rebuild)
-//     pos[2][N]   int4   {ux,uy,uz: 32-bit fixed-point box fractions, w: tag<<3 | type-1}   double-buffered
-//     vel[N]      float4 {vx,vy,vz, w: tag bits (host convenience)}
-//     pos_hold[N] int4   positions at the last rebuild (Neighbor::xhold, src/neighbor.cpp:2048-2052)
-//     img[N], img_hold[N]  LAMMPS-packed image flags now / at the last rebuild
-//     counts[N]   nfull | nbond<<16
-//     neigh[maxneigh][N]  ELL full neighbor rows; entry = k_j | which<<30
-//     bondrow[bpa][N]     ELL bond partner rows; entry = k_j | (bondtype-1)<<28
-//   tag order (index t-1; what the reference's Atom class holds, src/atom.h)
+// Layout in HBM (N atoms in the whole system, `cap` local slots on this GPU; all arrays device-resident):
+//   local order (index k = slot after the last cell sort; rewritten at every rebuild).  One GPU owns the x-slab of
+//   cells [X0, X1) and keeps `halo` layers of ghost cells on either side; slots are laid out by region
+//     [0, own0)            ghosts of the left neighbor's last `halo` layers   (written by that GPU over NVLink)
+//     [own0, own0 + nown)  owned atoms, sorted by cell (x slowest, z fastest), by tag inside a cell
+//     [gr0, cap)           ghosts of the right neighbor's first `halo` layers
+//   (one GPU: own0 = 0, nown = N, no ghosts: the periodic wrap comes from the fixed-point differences)
+//     pos[2][cap]   int4   {ux,uy,uz: 32-bit fixed-point box fractions, w: tag<<3 | type-1}   double-buffered
+//     vel[cap]      float4 {vx,vy,vz, w: tag bits (host convenience)}
+//     pos_hold[cap] int4   positions at the last rebuild (Neighbor::xhold, src/neighbor.cpp:2048-2052)
+//     img[cap], img_hold[cap]  LAMMPS-packed image flags now / at the last rebuild (owned atoms)
+//     counts[cap]   nfull | nbond<<16
+//     neigh[maxneigh][cap]  ELL full neighbor rows; entry = k_j | which<<30
+//     bondrow[bpa][cap]     ELL bond partner rows; entry = k_j | (bondtype-1)<<28
+//   tag order (index t-1; what the reference's Atom class holds, src/atom.h) -- replicated on every GPU
 //     num_bond, bond_type[N][bpa], bond_atom[N][bpa], nspecial[N][3], special[N][maxspecial]
-//     map[N]      tag-1 -> sorted index (Atom::map, src/atom.h:354-358)
+//     map[N]      tag-1 -> local slot, -1 if the atom is neither owned nor a ghost here (Atom::map, src/atom.h:354-358)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -83,6 +88,17 @@ struct Ctrl {
   int pad0;
   long long step;             // timestep of the next force evaluation (Update::ntimestep)
   long long run_begin, run_end;  // Update::beginstep / endstep of the current run (Langevin ramp)
+  // local population (changes at every rebuild when atoms migrate between GPUs)
+  int nown;                   // owned atoms: slots [own0, own0 + nown)
+  int nghl, nghr;             // ghosts in [0, nghl) and [gr0, gr0 + nghr)
+  int send_l_end;             // owned slots [own0, send_l_end) are the left neighbor's right ghosts
+  int send_r_beg;             // owned slots [send_r_beg, own0 + nown) are the right neighbor's left ghosts
+  int nown_unsorted;          // owned + arrived atoms before the sort of a rebuild
+  unsigned blocks_done;       // k_step blocks that have finished their stores (last one signals the peers)
+  int pad1;
+  long long epoch;            // force evaluations so far: the value the per-step peer flags carry
+  long long rebuild_epoch;    // rebuilds so far (all GPUs rebuild on the same steps)
+  long long le_epoch;         // USER-LE exchange rounds so far
 };
 
 enum {
@@ -95,11 +111,44 @@ enum {
   LE_DERR_COUNT_MISMATCH = 6,
   LE_DERR_MISSING_ATOM = 7,
   LE_DERR_CELL_OVERFLOW = 8,
-  LE_DERR_RNG_OVERFLOW = 9
+  LE_DERR_RNG_OVERFLOW = 9,
+  LE_DERR_PEER_TIMEOUT = 10,
+  LE_DERR_LOCAL_OVERFLOW = 11
 };
 
+#define LE_MAXRANKS 8
+#define LE_GEO_D 3    // USER-LE geometry record, doubles per tag (see le_fix.cuh)
+#define LE_GEO_I 2    // ... ints per tag
+// what one GPU sees of another GPU's arena (CUDA IPC mapping); all offsets are identical on every rank
+struct PeerView {
+  int4 *pos[2];
+  int4 *pos_hold;
+  int *cell_start;
+  int4 *in_pos; float4 *in_vel; int *in_img;       // migration inbox [2][inbox_cap]: side 0 = from its left neighbor
+  unsigned long long *flags;                        // see FLAG_* below
+  double *geo;                                      // USER-LE geometry records, tag order
+  int *geo_i;
+};
+// flag words in every arena, written by peers with system-scope stores:
+//   [FLAG_STEP + src]      (epoch << 1) | moved          after src's k_step of that epoch has stored its halo
+//   [FLAG_INBOX + side]    (rebuild_epoch << 24) | count  migrants written into inbox `side`
+//   [FLAG_GHOST + side]    (rebuild_epoch << 24) | count  ghost slice `side` (0 = left ghosts) written
+//   [FLAG_LE + src]        le_epoch                        src's USER-LE geometry records stored
+enum { FLAG_STEP = 0, FLAG_INBOX = 16, FLAG_GHOST = 24, FLAG_LE = 32, FLAG_WORDS = 64 };
+
 struct Dev {
-  int N, bpa, maxspecial, maxneigh;
+  int N;              // atoms in the whole system = length of the tag-indexed arrays
+  int cap;            // local slots (owned + ghosts) = stride of the ELL rows
+  int own0, gr0;      // first owned slot / first right-ghost slot
+  int bpa, maxspecial, maxneigh;
+  // domain decomposition: x-slabs of cells
+  int nranks, rank, halo;
+  int X0, X1, nlx;    // owned global x-cells [X0, X1); local layers nlx = X1 - X0 + 2 halo
+  int nlx_left, nlx_right;   // the neighbors' layer counts (slab widths may differ by one)
+  int inbox_cap;
+  PeerView peer[LE_MAXRANKS];   // peer[rank] is this GPU's own arena
+  unsigned long long *flags;    // this GPU's flag words
+  int4 *in_pos; float4 *in_vel; int *in_img;
   int4 *pos[2];
   int4 *pos_hold;
   float4 *vel, *vel_tmp;
@@ -107,10 +156,14 @@ struct Dev {
   unsigned *counts, *neigh, *bondrow;
   // tag order
   int *num_bond, *bond_type, *bond_atom, *nspecial, *special, *map;
+  int *type_tag;      // atom type by tag (the USER-LE fixes read and change types of atoms that may live on another GPU)
   // cell sort scratch
   int *cell_count, *cell_start, *cellid, *slot, *order, *blocksum;
-  int ncell[3], ncells, nscanblocks;
-  int cell_rad[3], cell_span[3], cell_abs[3];  // per-dim stencil radius / span / "visit all cells" (k_build)
+  int *ghost_tag;     // [2 own0] tags of the current ghosts (left, then right)
+  int ncell[3];       // global cell grid
+  int ncells;         // local cell slots incl. region sentinels: nlx*ncy*ncz + 3
+  int nscanblocks;
+  int cell_span[3], cell_abs[3];  // per-dim stencil span / "visit all cells" (k_build)
   Ctrl *ctrl;
   double *thermo;   // [slots][LE_THERMO_W]
   double *fout;     // [N][3] optional force output (tag order)
@@ -121,6 +174,22 @@ struct Dev {
 
 // one translation unit (le_engine.cu) includes this header; the block is refreshed before every use
 __constant__ Params c_P;
+
+// slot of local cell (lx, cy, cz) in cell_start / cell_count.  x is the slowest index so that a slab's boundary
+// layers are contiguous slices of the local order; one sentinel slot follows each region (left ghosts / owned /
+// right ghosts) so that cell_start[c + 1] is always the end of cell c.
+__host__ __device__ __forceinline__ int cell_slot(const Dev &d, int lx, int cy, int cz) {
+  return (lx * d.ncell[1] + cy) * d.ncell[2] + cz + (lx >= d.halo) + (lx >= d.nlx - d.halo);
+}
+// local layer of a global x-cell: [halo, nlx - halo) owned, [0, halo) left halo, [nlx - halo, nlx) right halo,
+// -1 if the cell is neither in this GPU's slab nor in its halo
+__host__ __device__ __forceinline__ int local_layer(const Dev &d, int cx) {
+  int dd = cx - d.X0;
+  if (dd < 0) dd += d.ncell[0];
+  if (dd < d.X1 - d.X0 + d.halo) return dd + d.halo;
+  if (dd >= d.ncell[0] - d.halo) return dd - d.ncell[0] + d.halo;
+  return -1;
+}
 
 __device__ __forceinline__ void le_raise(Ctrl *c, int code, int a = 0, int b = 0, int e = 0, int f = 0) {
   if (atomicCAS(&c->err, 0, code) == 0) {

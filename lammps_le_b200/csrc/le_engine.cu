@@ -83,6 +83,15 @@ struct le_ctx {
   cudaGraphExec_t x_plain, x_tail[2];
   int64_t direct_launches, graph_node_launches, direct_builds;
   bool capturing;
+  // domain decomposition (x-slabs, one GPU per rank); nranks == 1: the whole box on this GPU
+  int nranks, rank;
+  double halo_dist;
+  void *arena; size_t arena_bytes;      // peer-visible allocation (CUDA IPC): pos, pos_hold, cell_start, inbox, flags, geo
+  void *peer_base[LE_MAXRANKS];
+  bool peers_open;
+  RbScratch *rb;
+  std::vector<double> force_sums;                 // ... of the last le_compute_forces
+  std::vector<std::vector<double>> thermo_sums;   // raw per-GPU tallies behind c->thermo (summed over ranks by the caller)
 };
 
 static int fail(le_ctx *c, int code, const char *fmt, ...) {
@@ -169,6 +178,8 @@ extern "C" int le_create(le_ctx **out, int device, const double boxlo[3], const 
   c->x_plain = nullptr; c->x_tail[0] = c->x_tail[1] = nullptr;
   c->direct_launches = c->graph_node_launches = c->direct_builds = 0;
   memset(&c->gkey, 0, sizeof c->gkey);
+  c->nranks = 1; c->rank = 0; c->halo_dist = 0.0; c->arena = nullptr; c->arena_bytes = 0; c->peers_open = false; c->rb = nullptr;
+  memset(c->peer_base, 0, sizeof c->peer_base);
   cudaMallocHost(&c->h_thermo, sizeof(double) * LE_THERMO_W * THERMO_SLOTS);
   cudaMallocHost(&c->h_ctrl, sizeof(Ctrl));
   for (int k = 0; k < 3; k++)
@@ -196,6 +207,9 @@ extern "C" void le_destroy(le_ctx *c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   destroy_graphs(c);
+  if (c->peers_open)
+    for (int p = 0; p < c->nranks; p++)
+      if (p != c->rank && c->peer_base[p]) cudaIpcCloseMemHandle(c->peer_base[p]);
   for (void *p : c->allocs) cudaFree(p);
   cudaFreeHost(c->h_thermo);
   cudaFreeHost(c->h_ctrl);
@@ -383,6 +397,53 @@ extern "C" int le_unfix(le_ctx *c, int which) {
   return LE_OK;
 }
 
+// cell grid (identical on every rank) and this rank's x-slab of it
+static int setup_cells(le_ctx *c, double cutneighmax) {
+  Params &P = c->P;
+  Dev &d = c->d;
+  int nc[3];
+  for (int k = 0; k < 3; k++) {
+    nc[k] = (int)floor(P.L[k] / cutneighmax);
+    if (nc[k] < 1) nc[k] = 1;
+    if (nc[k] > 1024) nc[k] = 1024;
+  }
+  while ((long long)nc[0] * nc[1] * nc[2] > std::max<long long>(4LL * c->N, 64)) {
+    int k = (nc[0] >= nc[1] && nc[0] >= nc[2]) ? 0 : (nc[1] >= nc[2] ? 1 : 2);
+    nc[k] = std::max(1, nc[k] - std::max(1, nc[k] / 16));
+  }
+  if (c->nranks > 1 && c->atoms_loaded && (nc[0] != d.ncell[0] || nc[1] != d.ncell[1] || nc[2] != d.ncell[2]))
+    return fail(c, LE_ESTATE, "multi-GPU: the cell grid (pair cutoff + skin) cannot change after the atoms were distributed");
+  for (int k = 0; k < 3; k++) d.ncell[k] = nc[k];
+  d.nranks = c->nranks; d.rank = c->rank;
+  if (c->nranks > 1) {
+    const int ncx = nc[0], Pn = c->nranks;
+    const double cw = P.L[0] / ncx;
+    const double hd = c->halo_dist > cutneighmax ? c->halo_dist : cutneighmax;
+    d.halo = (int)ceil(hd / cw - 1e-9);
+    if (d.halo < 1) d.halo = 1;
+    int wmin = ncx;
+    for (int r = 0; r < Pn; r++) wmin = std::min(wmin, (int)((long long)(r + 1) * ncx / Pn - (long long)r * ncx / Pn));
+    if (wmin < 2 * d.halo + 1)
+      return fail(c, LE_EINVAL, "multi-GPU: a slab of %d cell layers is too thin for a halo of %d layers (box too small for %d GPUs)", wmin, d.halo, Pn);
+    auto X = [&](int r) { return (int)((long long)r * ncx / Pn); };
+    d.X0 = X(c->rank); d.X1 = X(c->rank + 1);
+    d.nlx = d.X1 - d.X0 + 2 * d.halo;
+    const int rl = (c->rank + Pn - 1) % Pn, rr = (c->rank + 1) % Pn;
+    d.nlx_left = X(rl + 1) - X(rl) + 2 * d.halo;
+    d.nlx_right = X(rr + 1) - X(rr) + 2 * d.halo;
+    if (nc[1] < 3 || nc[2] < 3) return fail(c, LE_EINVAL, "multi-GPU: box too small");
+  } else {
+    d.halo = 0; d.X0 = 0; d.X1 = nc[0]; d.nlx = nc[0]; d.nlx_left = d.nlx_right = nc[0];
+  }
+  for (int k = 0; k < 3; k++) {
+    if (nc[k] >= 3 || (k == 0 && c->nranks > 1)) { d.cell_abs[k] = 0; d.cell_span[k] = 3; }
+    else { d.cell_abs[k] = 1; d.cell_span[k] = nc[k]; }
+  }
+  d.ncells = d.nlx * nc[1] * nc[2] + 3;
+  d.nscanblocks = ((d.nlx - 2 * d.halo) * nc[1] * nc[2] + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  return LE_OK;
+}
+
 // ---- parameter block ------------------------------------------------------------------------------
 static int build_params(le_ctx *c) {
   Params &P = c->P;
@@ -472,26 +533,7 @@ static int build_params(le_ctx *c) {
   P.seed_lo = (unsigned)c->lang_seed; P.seed_hi = 0x4c414e47u;
   P.every = c->every; P.delay = c->delay; P.check = c->check;
 
-  // cell grid: cells at least one neighbor cutoff wide
-  Dev &d = c->d;
-  for (int k = 0; k < 3; k++) {
-    int nc = (int)floor(P.L[k] / cutneighmax);
-    if (nc < 1) nc = 1;
-    if (nc > 1024) nc = 1024;
-    d.ncell[k] = nc;
-  }
-  while ((long long)d.ncell[0] * d.ncell[1] * d.ncell[2] > std::max<long long>(4LL * c->N, 64)) {
-    int k = (d.ncell[0] >= d.ncell[1] && d.ncell[0] >= d.ncell[2]) ? 0 : (d.ncell[1] >= d.ncell[2] ? 1 : 2);
-    d.ncell[k] = std::max(1, d.ncell[k] - std::max(1, d.ncell[k] / 16));
-  }
-  for (int k = 0; k < 3; k++) {
-    d.cell_rad[k] = 1;
-    if (d.ncell[k] >= 3) { d.cell_abs[k] = 0; d.cell_span[k] = 3; }
-    else { d.cell_abs[k] = 1; d.cell_span[k] = d.ncell[k]; }
-  }
-  d.ncells = d.ncell[0] * d.ncell[1] * d.ncell[2];
-  d.nscanblocks = (d.ncells + SCAN_BLOCK - 1) / SCAN_BLOCK;
-  return LE_OK;
+  return setup_cells(c, cutneighmax);
 }
 
 static int push_params(le_ctx *c) {
@@ -500,6 +542,7 @@ static int push_params(le_ctx *c) {
     int r = build_params(c);
     if (r) return r;
     if (c->atoms_loaded && (c->d.ncells != old_cells || !c->d.cell_count)) {
+      if (c->nranks > 1) return fail(c, LE_ESTATE, "multi-GPU: cell arrays are sized when the atoms are distributed");
       r = dalloc(c, &c->d.cell_count, (size_t)c->d.ncells + 1); if (r) return r;
       r = dalloc(c, &c->d.cell_start, (size_t)c->d.ncells + 1); if (r) return r;
       r = dalloc(c, &c->d.blocksum, (size_t)c->d.nscanblocks + 1); if (r) return r;
@@ -530,45 +573,49 @@ static inline void unpack_image(int im, int *ix, int *iy, int *iz) {
   *ix = (im & 1023) - 512; *iy = ((im >> 10) & 1023) - 512; *iz = ((im >> 20) & 1023) - 512;
 }
 
+// carve the peer-visible buffers out of one allocation so that one CUDA IPC handle per GPU is enough and every
+// rank can compute the addresses inside a peer's arena itself (same sizes on all ranks)
+struct ArenaLayout { size_t pos0, pos1, pos_hold, cell_start, in_pos, in_vel, in_img, flags, geo, geo_i, total; };
+static ArenaLayout arena_layout(int cap, int ncells_max, int inbox_cap, int nglobal) {
+  ArenaLayout a; size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+  a.pos0 = take((size_t)cap * 16); a.pos1 = take((size_t)cap * 16); a.pos_hold = take((size_t)cap * 16);
+  a.cell_start = take((size_t)ncells_max * 4);
+  a.in_pos = take((size_t)2 * inbox_cap * 16); a.in_vel = take((size_t)2 * inbox_cap * 16); a.in_img = take((size_t)2 * inbox_cap * 4);
+  a.flags = take(FLAG_WORDS * 8);
+  a.geo = take((size_t)nglobal * LE_GEO_D * 8); a.geo_i = take((size_t)nglobal * LE_GEO_I * 4);
+  a.total = o;
+  return a;
+}
+static void peer_view(PeerView *v, void *base, const ArenaLayout &a) {
+  char *b = (char *)base;
+  v->pos[0] = (int4 *)(b + a.pos0); v->pos[1] = (int4 *)(b + a.pos1); v->pos_hold = (int4 *)(b + a.pos_hold);
+  v->cell_start = (int *)(b + a.cell_start);
+  v->in_pos = (int4 *)(b + a.in_pos); v->in_vel = (float4 *)(b + a.in_vel); v->in_img = (int *)(b + a.in_img);
+  v->flags = (unsigned long long *)(b + a.flags);
+  v->geo = (double *)(b + a.geo); v->geo_i = (int *)(b + a.geo_i);
+}
+static ArenaLayout ctx_layout(const le_ctx *c) {
+  const Dev &d = c->d;
+  const int ncx = d.ncell[0], Pn = c->nranks;
+  const int nlx_max = (ncx + Pn - 1) / Pn + 2 * d.halo;
+  return arena_layout(d.cap, nlx_max * d.ncell[1] * d.ncell[2] + 3, d.inbox_cap, d.N);
+}
+
 extern "C" int le_upload_atoms(le_ctx *c, int n, const int *tag, const int *type, const double *x, const double *v, const int *image) {
   if (!c) return LE_EINVAL;
   if (n < 1 || !type || !x) return fail(c, LE_EINVAL, "le_upload_atoms: bad arguments");
   if (c->atoms_loaded) return fail(c, LE_ESTATE, "atoms already uploaded (create a new context)");
-  if (n >= (1 << 28)) return fail(c, LE_EINVAL, "at most 2^28-1 atoms per GPU");
+  if (n >= (1 << 28)) return fail(c, LE_EINVAL, "at most 2^28-1 atoms");
   cudaSetDevice(c->device);
   c->N = n;
   Dev &d = c->d;
   d.N = n; d.bpa = c->bpa; d.maxspecial = c->maxspecial; d.maxneigh = c->maxneigh;
   int r;
-  if ((r = dalloc(c, &d.pos[0], n))) return r;
-  if ((r = dalloc(c, &d.pos[1], n))) return r;
-  if ((r = dalloc(c, &d.pos_hold, n))) return r;
-  if ((r = dalloc(c, &d.vel, n))) return r;
-  if ((r = dalloc(c, &d.vel_tmp, n))) return r;
-  if ((r = dalloc(c, &d.img, n))) return r;
-  if ((r = dalloc(c, &d.img_hold, n))) return r;
-  if ((r = dalloc(c, &d.counts, n))) return r;
-  if ((r = dalloc(c, &d.neigh, (size_t)n * c->maxneigh))) return r;
-  if ((r = dalloc(c, &d.bondrow, (size_t)n * c->bpa))) return r;
-  if ((r = dalloc(c, &d.num_bond, n))) return r;
-  if ((r = dalloc(c, &d.bond_type, (size_t)n * c->bpa))) return r;
-  if ((r = dalloc(c, &d.bond_atom, (size_t)n * c->bpa))) return r;
-  if ((r = dalloc(c, &d.nspecial, (size_t)n * 3))) return r;
-  if ((r = dalloc(c, &d.special, (size_t)n * c->maxspecial))) return r;
-  if ((r = dalloc(c, &d.map, n))) return r;
-  if ((r = dalloc(c, &d.cellid, n))) return r;
-  if ((r = dalloc(c, &d.slot, n))) return r;
-  if ((r = dalloc(c, &d.order, n))) return r;
-  if ((r = dalloc(c, &d.ctrl, 1))) return r;
-  if ((r = dalloc(c, &d.thermo, (size_t)LE_THERMO_W * THERMO_SLOTS))) return r;
-  if ((r = dalloc(c, &d.fout, (size_t)n * 3))) return r;
-  if ((r = le_fix_alloc(c->lf, n, c->maxspecial, c->allocs, c->stream))) return fail(c, LE_ENOMEM, "cudaMalloc failed for USER-LE scratch");
-  if ((r = le_fix_alloc_rng(c->lf, c->allocs, c->stream))) return fail(c, LE_ENOMEM, "cudaMalloc failed for USER-LE scratch");
-  c->atoms_loaded = true;
-
+  // quantise; in tag order
   std::vector<int4> hp(n);
   std::vector<float4> hv(n);
-  std::vector<int> himg(n), hmap(n);
+  std::vector<int> himg(n);
   std::vector<char> seen(n, 0);
   for (int k = 0; k < n; k++) {
     const int t = tag ? tag[k] : k + 1;
@@ -580,24 +627,162 @@ extern "C" int le_upload_atoms(le_ctx *c, int n, const int *tag, const int *type
     for (int q = 0; q < 3; q++) u[q] = quantize(x[3 * k + q], c->lo[q], c->hi[q] - c->lo[q], &w[q]);
     int ix = 0, iy = 0, iz = 0;
     if (image) unpack_image(image[k], &ix, &iy, &iz);
-    // entries are stored in tag order initially: sorted index == tag-1 until the first rebuild
     hp[t - 1] = make_int4((int)u[0], (int)u[1], (int)u[2], (t << 3) | (type[k] - 1));
     float4 vv;
     vv.x = v ? (float)v[3 * k] : 0.f; vv.y = v ? (float)v[3 * k + 1] : 0.f; vv.z = v ? (float)v[3 * k + 2] : 0.f;
     vv.w = h_int_as_float(t);
     hv[t - 1] = vv;
     himg[t - 1] = pack_image(ix + w[0], iy + w[1], iz + w[2]);
-    hmap[t - 1] = t - 1;
+  }
+  // local capacity: one GPU holds everything; a slab holds its share (+25 %) and two ghost regions
+  std::vector<int> mine;        // tags-1 of the atoms this rank owns, ascending
+  if (c->nranks == 1) {
+    d.cap = n; d.own0 = 0; d.gr0 = n; d.inbox_cap = 1;
+    d.nranks = 1; d.rank = 0; d.halo = 0;
+  } else {
+    if (!c->pair_set) return fail(c, LE_ESTATE, "multi-GPU: set pair_style / neighbor before uploading atoms (the slabs are cut from the cell grid)");
+    if ((r = build_params(c))) return r;
+    const int ncx = d.ncell[0], Pn = c->nranks, H = d.halo;
+    std::vector<long long> per_layer(ncx, 0);
+    for (int t = 0; t < n; t++) per_layer[(int)(((unsigned long long)(unsigned)hp[t].x * (unsigned)ncx) >> 32)]++;
+    long long maxown = 0, maxghost = 0;
+    for (int rk = 0; rk < Pn; rk++) {
+      const int x0 = (int)((long long)rk * ncx / Pn), x1 = (int)((long long)(rk + 1) * ncx / Pn);
+      long long own = 0, gl = 0, gr = 0;
+      for (int q = x0; q < x1; q++) own += per_layer[q];
+      for (int q = 0; q < H; q++) { gl += per_layer[x0 + q]; gr += per_layer[x1 - 1 - q]; }
+      maxown = std::max(maxown, own); maxghost = std::max(maxghost, std::max(gl, gr));
+    }
+    const long long owncap = maxown + maxown / 4 + 4096, ghostcap = maxghost + maxghost / 2 + 4096;
+    d.own0 = (int)ghostcap; d.gr0 = (int)(ghostcap + owncap); d.cap = (int)(2 * ghostcap + owncap);
+    d.inbox_cap = (int)std::max<long long>(4096, owncap / 16);
+    for (int t = 0; t < n; t++) {
+      const int cx = (int)(((unsigned long long)(unsigned)hp[t].x * (unsigned)ncx) >> 32);
+      if (cx >= d.X0 && cx < d.X1) mine.push_back(t);
+    }
+  }
+  const int cap = d.cap;
+  if (c->nranks == 1) {
+    if ((r = dalloc(c, &d.pos[0], cap))) return r;
+    if ((r = dalloc(c, &d.pos[1], cap))) return r;
+    if ((r = dalloc(c, &d.pos_hold, cap))) return r;
+  } else {
+    const ArenaLayout a = ctx_layout(c);
+    if (cudaMalloc(&c->arena, a.total) != cudaSuccess) return fail(c, LE_ENOMEM, "cudaMalloc of the %zu-byte peer arena failed", a.total);
+    c->allocs.push_back(c->arena);
+    c->arena_bytes = a.total;
+    CK(cudaMemsetAsync(c->arena, 0, a.total, c->stream));
+    c->peer_base[c->rank] = c->arena;
+    peer_view(&d.peer[c->rank], c->arena, a);
+    const PeerView &me = d.peer[c->rank];
+    d.pos[0] = me.pos[0]; d.pos[1] = me.pos[1]; d.pos_hold = me.pos_hold; d.cell_start = me.cell_start;
+    d.in_pos = me.in_pos; d.in_vel = me.in_vel; d.in_img = me.in_img; d.flags = me.flags;
+    if ((r = dalloc(c, &d.cell_count, (size_t)d.ncells + 1))) return r;
+    if ((r = dalloc(c, &d.blocksum, (size_t)d.nscanblocks + 1))) return r;
+    if ((r = dalloc(c, &d.ghost_tag, (size_t)2 * d.own0 + 1))) return r;
+  }
+  if ((r = dalloc(c, &c->rb, 1))) return r;
+  if ((r = dalloc(c, &d.vel, cap))) return r;
+  if ((r = dalloc(c, &d.vel_tmp, cap))) return r;
+  if ((r = dalloc(c, &d.img, cap))) return r;
+  if ((r = dalloc(c, &d.img_hold, cap))) return r;
+  if ((r = dalloc(c, &d.counts, cap))) return r;
+  if ((r = dalloc(c, &d.neigh, (size_t)cap * c->maxneigh))) return r;
+  if ((r = dalloc(c, &d.bondrow, (size_t)cap * c->bpa))) return r;
+  if ((r = dalloc(c, &d.num_bond, n))) return r;
+  if ((r = dalloc(c, &d.bond_type, (size_t)n * c->bpa))) return r;
+  if ((r = dalloc(c, &d.bond_atom, (size_t)n * c->bpa))) return r;
+  if ((r = dalloc(c, &d.nspecial, (size_t)n * 3))) return r;
+  if ((r = dalloc(c, &d.special, (size_t)n * c->maxspecial))) return r;
+  if ((r = dalloc(c, &d.map, n))) return r;
+  if ((r = dalloc(c, &d.type_tag, n))) return r;
+  if ((r = dalloc(c, &d.cellid, cap))) return r;
+  if ((r = dalloc(c, &d.slot, cap))) return r;
+  if ((r = dalloc(c, &d.order, cap))) return r;
+  if ((r = dalloc(c, &d.ctrl, 1))) return r;
+  if ((r = dalloc(c, &d.thermo, (size_t)LE_THERMO_W * THERMO_SLOTS))) return r;
+  if ((r = dalloc(c, &d.fout, (size_t)n * 3))) return r;
+  if ((r = le_fix_alloc(c->lf, n, c->maxspecial, c->allocs, c->stream))) return fail(c, LE_ENOMEM, "cudaMalloc failed for USER-LE scratch");
+  if ((r = le_fix_alloc_rng(c->lf, c->allocs, c->stream))) return fail(c, LE_ENOMEM, "cudaMalloc failed for USER-LE scratch");
+  if (c->nranks == 1) {
+    if ((r = dalloc(c, &c->lf.geo, (size_t)n * LE_GEO_D))) return r;
+    if ((r = dalloc(c, &c->lf.geo_i, (size_t)n * LE_GEO_I))) return r;
+  } else {
+    c->lf.geo = d.peer[c->rank].geo; c->lf.geo_i = d.peer[c->rank].geo_i;
+  }
+  c->atoms_loaded = true;
+
+  // owned atoms go to slots own0.. in tag order (local order == tag order until the first rebuild)
+  std::vector<int> hmap(n, -1), htype(n);
+  for (int t = 0; t < n; t++) htype[t] = (hp[t].w & 7) + 1;
+  int nown = n;
+  if (c->nranks == 1) {
+    for (int t = 0; t < n; t++) hmap[t] = t;
+    CK(cudaMemcpyAsync(d.pos[0], hp.data(), sizeof(int4) * n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d.pos_hold, hp.data(), sizeof(int4) * n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d.vel, hv.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d.img, himg.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d.img_hold, himg.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    nown = (int)mine.size();
+    if (nown > d.gr0 - d.own0) return fail(c, LE_ENOMEM, "internal: slab capacity");
+    std::vector<int4> lp(nown); std::vector<float4> lv(nown); std::vector<int> li(nown);
+    for (int k = 0; k < nown; k++) { const int t = mine[k]; lp[k] = hp[t]; lv[k] = hv[t]; li[k] = himg[t]; hmap[t] = d.own0 + k; }
+    CK(cudaMemcpyAsync(d.pos[0] + d.own0, lp.data(), sizeof(int4) * nown, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d.pos_hold + d.own0, lp.data(), sizeof(int4) * nown, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d.vel + d.own0, lv.data(), sizeof(float4) * nown, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d.img + d.own0, li.data(), sizeof(int) * nown, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d.img_hold + d.own0, li.data(), sizeof(int) * nown, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
   }
   c->cur = 0;
-  CK(cudaMemcpyAsync(d.pos[0], hp.data(), sizeof(int4) * n, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(d.pos_hold, hp.data(), sizeof(int4) * n, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(d.vel, hv.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(d.img, himg.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(d.img_hold, himg.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(d.map, hmap.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d.type_tag, htype.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(&d.ctrl->nown, &nown, sizeof(int), cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   c->lists_valid = false; c->params_dirty = true;
+  return LE_OK;
+}
+
+// ---- multi-GPU set-up ---------------------------------------------------------------------------------
+extern "C" int le_dd_init(le_ctx *c, int rank, int nranks, double halo_distance) {
+  if (!c) return LE_EINVAL;
+  if (nranks < 1 || nranks > LE_MAXRANKS || rank < 0 || rank >= nranks) return fail(c, LE_EINVAL, "le_dd_init: rank %d of %d (at most %d GPUs)", rank, nranks, LE_MAXRANKS);
+  if (c->atoms_loaded) return fail(c, LE_ESTATE, "le_dd_init must precede le_upload_atoms");
+  c->rank = rank; c->nranks = nranks; c->halo_dist = halo_distance > 0.0 ? halo_distance : 0.0;
+  c->params_dirty = true;
+  return LE_OK;
+}
+
+extern "C" int le_dd_get_handle(le_ctx *c, void *handle64) {
+  if (!c || !handle64) return LE_EINVAL;
+  if (c->nranks < 2) { memset(handle64, 0, 64); return LE_OK; }
+  if (!c->arena) return fail(c, LE_ESTATE, "upload atoms first");
+  cudaSetDevice(c->device);
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, c->arena));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(handle64, &h, 64);
+  return LE_OK;
+}
+
+extern "C" int le_dd_connect(le_ctx *c, const void *handles /* [nranks][64] */) {
+  if (!c) return LE_EINVAL;
+  if (c->nranks < 2) return LE_OK;
+  if (!c->arena || !handles) return fail(c, LE_ESTATE, "upload atoms first");
+  cudaSetDevice(c->device);
+  const ArenaLayout a = ctx_layout(c);
+  for (int p = 0; p < c->nranks; p++) {
+    if (p == c->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char *)handles + (size_t)p * 64, 64);
+    void *base = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(c, LE_ENOGPU, "cudaIpcOpenMemHandle for rank %d failed: %s", p, cudaGetErrorString(e));
+    c->peer_base[p] = base;
+    peer_view(&c->d.peer[p], base, a);
+  }
+  c->peers_open = true;
   return LE_OK;
 }
 
@@ -682,14 +867,15 @@ extern "C" int le_set_positions(le_ctx *c, const double *x, const int *image) {
   if (!c || !x) return LE_EINVAL;
   if (!c->atoms_loaded) return fail(c, LE_ESTATE, "no atoms");
   cudaSetDevice(c->device);
-  const int n = c->N;
+  const int n = c->N, cap = c->d.cap;
   std::vector<int> hmap; int r = fetch_map(c, hmap); if (r) return r;
-  std::vector<int4> hp(n); std::vector<int> himg(n);
-  CK(cudaMemcpyAsync(hp.data(), c->d.pos[c->cur], sizeof(int4) * n, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(himg.data(), c->d.img, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+  std::vector<int4> hp(cap); std::vector<int> himg(cap);
+  CK(cudaMemcpyAsync(hp.data(), c->d.pos[c->cur], sizeof(int4) * cap, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(himg.data(), c->d.img, sizeof(int) * cap, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   for (int t = 0; t < n; t++) {
     const int k = hmap[t];
+    if (k < 0) continue;                       // neither owned nor a ghost on this GPU
     int w[3]; unsigned u[3];
     for (int q = 0; q < 3; q++) u[q] = quantize(x[3 * t + q], c->lo[q], c->hi[q] - c->lo[q], &w[q]);
     int ix = 0, iy = 0, iz = 0;
@@ -708,8 +894,8 @@ extern "C" int le_set_positions(le_ctx *c, const double *x, const int *image) {
     hp[k].x = (int)u[0]; hp[k].y = (int)u[1]; hp[k].z = (int)u[2];
     himg[k] = image ? pack_image(ix + w[0], iy + w[1], iz + w[2]) : pack_image(ix, iy, iz);
   }
-  CK(cudaMemcpyAsync(c->d.pos[c->cur], hp.data(), sizeof(int4) * n, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(c->d.img, himg.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d.pos[c->cur], hp.data(), sizeof(int4) * cap, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d.img, himg.data(), sizeof(int) * cap, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return LE_OK;
 }
@@ -718,14 +904,18 @@ extern "C" int le_set_velocities(le_ctx *c, const double *v) {
   if (!c || !v) return LE_EINVAL;
   if (!c->atoms_loaded) return fail(c, LE_ESTATE, "no atoms");
   cudaSetDevice(c->device);
-  const int n = c->N;
+  const int n = c->N, cap = c->d.cap;
   std::vector<int> hmap; int r = fetch_map(c, hmap); if (r) return r;
-  std::vector<float4> hv(n);
+  std::vector<float4> hv(cap);
+  CK(cudaMemcpyAsync(hv.data(), c->d.vel, sizeof(float4) * cap, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   for (int t = 0; t < n; t++) {
+    const int k = hmap[t];
+    if (k < c->d.own0 || k >= c->d.gr0) continue;
     float4 vv; vv.x = (float)v[3 * t]; vv.y = (float)v[3 * t + 1]; vv.z = (float)v[3 * t + 2]; vv.w = h_int_as_float(t + 1);
-    hv[hmap[t]] = vv;
+    hv[k] = vv;
   }
-  CK(cudaMemcpyAsync(c->d.vel, hv.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d.vel, hv.data(), sizeof(float4) * cap, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return LE_OK;
 }
@@ -734,17 +924,32 @@ extern "C" int le_set_velocities(le_ctx *c, const double *v) {
 // the rebuild kernels; `direct` adds the bookkeeping k_decide does when the rebuild is a conditional graph node
 static void enqueue_rebuild(le_ctx *c, bool direct) {
   Dev &d = c->d;
-  const int n = c->N;
-  LAUNCH(c, k_cell_count, grid_for(n, 256), 256, d);
+  const int nslots = d.gr0 - d.own0;                       // capacity of the owned region
+  const int ncell_own = (d.nlx - 2 * d.halo) * d.ncell[1] * d.ncell[2];
+  const bool dd = c->nranks > 1;
+  LAUNCH(c, k_rb_begin, 1, 1, d, c->rb);
+  if (dd) LAUNCH(c, k_clear_ghost_map, grid_for(2 * d.own0, 256), 256, d);
+  LAUNCH(c, k_cell_count, grid_for(nslots, 256), 256, d, c->rb);
+  if (dd) {
+    LAUNCH(c, k_rb_post_inbox, 1, 1, d, c->rb);
+    LAUNCH(c, k_inbox, grid_for(2 * d.inbox_cap, 256), 256, d, c->rb);
+  }
   LAUNCH(c, k_scan_partial, d.nscanblocks, SCAN_BLOCK, d);
   LAUNCH(c, k_scan_blocks, 1, SCAN_BLOCK, d);
   LAUNCH(c, k_scan_apply, d.nscanblocks, SCAN_BLOCK, d);
-  LAUNCH(c, k_cell_scatter, grid_for(n, 256), 256, d);
-  LAUNCH(c, k_cell_sort, grid_for(d.ncells, 128), 128, d);
-  LAUNCH(c, k_gather, grid_for(n, 256), 256, d);
-  LAUNCH(c, k_build, grid_for(n, BUILD_THREADS), BUILD_THREADS, d);
+  LAUNCH(c, k_cell_scatter, grid_for(nslots, 256), 256, d);
+  LAUNCH(c, k_cell_sort, grid_for(ncell_own, 128), 128, d);
+  LAUNCH(c, k_gather, grid_for(nslots, 256), 256, d);
+  if (dd) {
+    LAUNCH(c, k_push_ghosts, grid_for(std::max(d.own0, d.halo * d.ncell[1] * d.ncell[2] + 1), 256), 256, d);
+    LAUNCH(c, k_rb_post_ghosts, 1, 1, d);
+    LAUNCH(c, k_ghost_map, grid_for(2 * d.own0, 256), 256, d);
+  }
+  LAUNCH(c, k_build, grid_for(nslots, BUILD_THREADS), BUILD_THREADS, d);
   if (direct) { LAUNCH(c, k_after_build, 1, 1, d); c->direct_builds++; }
 }
+
+static int rebuild_kernel_count(const le_ctx *c) { return c->nranks > 1 ? 15 : 9; }
 
 #define CKG(call)                                                                             \
   do {                                                                                        \
@@ -786,7 +991,7 @@ static int graph_add_unit(le_ctx *c, cudaGraph_t g, cudaGraphNode_t *tail, int a
     a.do_final = 1; a.do_initial = 1; a.langevin = c->langevin_on;
     void *sargs[] = {&d, &a};
     memset(&kp, 0, sizeof kp);
-    kp.func = (void *)k_step<0>; kp.gridDim = dim3(grid_for(c->N, STEP_THREADS)); kp.blockDim = dim3(STEP_THREADS); kp.kernelParams = sargs;
+    kp.func = c->nranks > 1 ? (void *)k_step<0, 1> : (void *)k_step<0, 0>; kp.gridDim = dim3(grid_for(c->d.gr0 - c->d.own0, STEP_THREADS)); kp.blockDim = dim3(STEP_THREADS); kp.kernelParams = sargs;
     cudaGraphNode_t ns;
     CKG(cudaGraphAddKernelNode(&ns, g, &nc, 1, &kp));
     *tail = ns;
@@ -826,6 +1031,8 @@ static const char *derr_text(int code) {
     case LE_DERR_COUNT_MISMATCH: return "Numbers of created and broken bonds are not equal";
     case LE_DERR_MISSING_ATOM: return "Bond atoms missing";
     case LE_DERR_RNG_OVERFLOW: return "USER-LE random draw buffer overflow";
+    case LE_DERR_PEER_TIMEOUT: return "multi-GPU: a peer GPU did not answer (halo / migration hand-shake timed out)";
+    case LE_DERR_LOCAL_OVERFLOW: return "multi-GPU: local atom / ghost / inbox capacity exceeded or an atom left the halo";
     default: return "device error";
   }
 }
@@ -837,7 +1044,7 @@ static int sync_and_check(le_ctx *c) {
   CK(cudaGetLastError());
   const Ctrl &k = *c->h_ctrl;
   c->stats.neigh_builds = k.nbuilds;
-  c->stats.kernel_launches = c->direct_launches + c->graph_node_launches + REBUILD_KERNELS * (k.nbuilds - c->direct_builds);
+  c->stats.kernel_launches = c->direct_launches + c->graph_node_launches + rebuild_kernel_count(c) * (k.nbuilds - c->direct_builds);
   if (k.cur != c->cur) return fail(c, LE_ERUN, "internal: host/device position buffer parity out of step");
   c->stats.dangerous_builds = k.ndanger;
   c->stats.last_extrusion_shifts = k.le_count[0]; c->stats.last_unloads = k.le_count[1]; c->stats.last_loads = k.le_count[2];
@@ -890,9 +1097,14 @@ static void thermo_from_slot(le_ctx *c, const double *s, int64_t step, le_thermo
 }
 
 static void launch_step(le_ctx *c, const StepArgs &a, bool ev) {
-  const int grid = grid_for(c->N, STEP_THREADS);
-  if (ev) LAUNCH(c, k_step<1>, grid, STEP_THREADS, c->d, a);
-  else LAUNCH(c, k_step<0>, grid, STEP_THREADS, c->d, a);
+  const int grid = grid_for(c->d.gr0 - c->d.own0, STEP_THREADS);
+  if (c->nranks > 1) {
+    if (ev) LAUNCH(c, (k_step<1, 1>), grid, STEP_THREADS, c->d, a);
+    else LAUNCH(c, (k_step<0, 1>), grid, STEP_THREADS, c->d, a);
+  } else {
+    if (ev) LAUNCH(c, (k_step<1, 0>), grid, STEP_THREADS, c->d, a);
+    else LAUNCH(c, (k_step<0, 0>), grid, STEP_THREADS, c->d, a);
+  }
 }
 
 // Update::ntimestep / beginstep / endstep of the run that starts now -> device control block
@@ -911,10 +1123,12 @@ extern "C" int le_compute_forces(le_ctx *c, double *f, le_thermo *out) {
   r = push_run_state(c, c->ntimestep, c->ntimestep); if (r) return r;
   StepArgs a; memset(&a, 0, sizeof a);
   a.slot = 0; a.write_force = 1;
+  if (c->nranks > 1) CK(cudaMemsetAsync(c->d.fout, 0, sizeof(double) * 3 * c->N, c->stream));   // owned rows only are written
   launch_step(c, a, true);
   CK(cudaMemcpyAsync(c->h_thermo, c->d.thermo, sizeof(double) * LE_THERMO_W, cudaMemcpyDeviceToHost, c->stream));
   r = sync_and_check(c); if (r) return r;
   if (out) thermo_from_slot(c, c->h_thermo, c->ntimestep, out);
+  c->force_sums.assign(c->h_thermo, c->h_thermo + LE_THERMO_W);
   if (f) {
     CK(cudaMemcpyAsync(f, c->d.fout, sizeof(double) * 3 * c->N, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -949,6 +1163,7 @@ extern "C" int le_run(le_ctx *c, int64_t nsteps) {
     for (int k = 0; k < used_slots; k++) {
       le_thermo t; thermo_from_slot(c, c->h_thermo + (size_t)k * LE_THERMO_W, slot_step[k], &t);
       c->thermo.push_back(t);
+      c->thermo_sums.emplace_back(c->h_thermo + (size_t)k * LE_THERMO_W, c->h_thermo + (size_t)(k + 1) * LE_THERMO_W);
     }
     used_slots = 0; slot_step.clear();
     return LE_OK;
@@ -1036,19 +1251,28 @@ extern "C" int le_run(le_ctx *c, int64_t nsteps) {
 extern "C" int le_natoms(const le_ctx *c) { return c ? c->N : 0; }
 extern "C" int64_t le_timestep(const le_ctx *c) { return c ? c->ntimestep : 0; }
 
+// owned population right now
+static int fetch_nown(le_ctx *c, int *nown) {
+  CK(cudaMemcpyAsync(nown, &c->d.ctrl->nown, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return LE_OK;
+}
+
+// Multi-GPU: every download fills the entries of the atoms THIS GPU owns and leaves the others untouched; the
+// caller zero-fills and sums over ranks (lammps_le_b200/engine_dd.py).
 extern "C" int le_download_x(le_ctx *c, double *x, int *image) {
   if (!c) return LE_EINVAL;
   if (!c->atoms_loaded) return fail(c, LE_ESTATE, "no atoms");
   cudaSetDevice(c->device);
-  const int n = c->N;
-  std::vector<int4> hp(n); std::vector<float4> hv(n); std::vector<int> himg(n);
-  CK(cudaMemcpyAsync(hp.data(), c->d.pos[c->cur], sizeof(int4) * n, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(hv.data(), c->d.vel, sizeof(float4) * n, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(himg.data(), c->d.img, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+  int n; int r = fetch_nown(c, &n); if (r) return r;
+  const int o = c->d.own0;
+  std::vector<int4> hp(n); std::vector<int> himg(n);
+  CK(cudaMemcpyAsync(hp.data(), c->d.pos[c->cur] + o, sizeof(int4) * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(himg.data(), c->d.img + o, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   const double two32 = 4294967296.0;
   for (int k = 0; k < n; k++) {
-    const int t = h_float_as_int(hv[k].w) - 1;
+    const int t = (hp[k].w >> 3) - 1;
     const unsigned u[3] = {(unsigned)hp[k].x, (unsigned)hp[k].y, (unsigned)hp[k].z};
     if (x) for (int q = 0; q < 3; q++) {
       const double scale = (c->hi[q] - c->lo[q]) / two32;
@@ -1063,9 +1287,9 @@ extern "C" int le_download_v(le_ctx *c, double *v) {
   if (!c || !v) return LE_EINVAL;
   if (!c->atoms_loaded) return fail(c, LE_ESTATE, "no atoms");
   cudaSetDevice(c->device);
-  const int n = c->N;
+  int n; int r = fetch_nown(c, &n); if (r) return r;
   std::vector<float4> hv(n);
-  CK(cudaMemcpyAsync(hv.data(), c->d.vel, sizeof(float4) * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(hv.data(), c->d.vel + c->d.own0, sizeof(float4) * n, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   for (int k = 0; k < n; k++) {
     const int t = h_float_as_int(hv[k].w) - 1;
@@ -1078,10 +1302,9 @@ extern "C" int le_download_types(le_ctx *c, int *type) {
   if (!c || !type) return LE_EINVAL;
   if (!c->atoms_loaded) return fail(c, LE_ESTATE, "no atoms");
   cudaSetDevice(c->device);
-  const int n = c->N;
-  std::vector<int4> hp(n); std::vector<float4> hv(n);
-  CK(cudaMemcpyAsync(hp.data(), c->d.pos[c->cur], sizeof(int4) * n, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(hv.data(), c->d.vel, sizeof(float4) * n, cudaMemcpyDeviceToHost, c->stream));
+  int n; int r = fetch_nown(c, &n); if (r) return r;
+  std::vector<int4> hp(n);
+  CK(cudaMemcpyAsync(hp.data(), c->d.pos[c->cur] + c->d.own0, sizeof(int4) * n, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   for (int k = 0; k < n; k++) type[(hp[k].w >> 3) - 1] = (hp[k].w & 7) + 1;
   return LE_OK;
@@ -1105,28 +1328,30 @@ extern "C" int le_download_neighlist(le_ctx *c, int half, int64_t *offsets, int 
   if (!c) return LE_EINVAL;
   if (!c->lists_valid) return fail(c, LE_ESTATE, "no neighbor list has been built yet");
   cudaSetDevice(c->device);
-  const int n = c->N;
-  std::vector<unsigned> cnt(n); std::vector<int4> hp(n); std::vector<int> hmap;
+  const int n = c->N, cap = c->d.cap;
+  std::vector<unsigned> cnt(cap); std::vector<int4> hp(cap); std::vector<int> hmap;
   int r = fetch_map(c, hmap); if (r) return r;
-  CK(cudaMemcpyAsync(cnt.data(), c->d.counts, sizeof(unsigned) * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(cnt.data(), c->d.counts, sizeof(unsigned) * cap, cudaMemcpyDeviceToHost, c->stream));
   // positions at the last rebuild: the coordinates the list was built on
-  CK(cudaMemcpyAsync(hp.data(), c->d.pos_hold, sizeof(int4) * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(hp.data(), c->d.pos_hold, sizeof(int4) * cap, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   int maxc = 0;
-  for (int k = 0; k < n; k++) maxc = std::max(maxc, (int)(cnt[k] & 0xff));
-  std::vector<unsigned> rows((size_t)std::max(maxc, 1) * n);
-  CK(cudaMemcpyAsync(rows.data(), c->d.neigh, sizeof(unsigned) * (size_t)maxc * n, cudaMemcpyDeviceToHost, c->stream));
+  for (int t = 0; t < n; t++) { const int k = hmap[t]; if (k >= c->d.own0 && k < c->d.gr0) maxc = std::max(maxc, (int)(cnt[k] & 0xff)); }
+  std::vector<unsigned> rows((size_t)std::max(maxc, 1) * cap);
+  CK(cudaMemcpyAsync(rows.data(), c->d.neigh, sizeof(unsigned) * (size_t)maxc * cap, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   // the device keeps full rows; which atom of a pair the reference's half list stores it on is derived here with
-  // the same arithmetic the device uses for the (t,t+2) pairs (le_pair_stored_on_i)
+  // the same arithmetic the device uses for the (t,t+2) pairs (le_pair_stored_on_i).  Rows of atoms owned by
+  // another GPU stay empty.
   int64_t o = 0;
   for (int t = 0; t < n; t++) {
     const int k = hmap[t];
     if (offsets) offsets[t] = o;
+    if (k < c->d.own0 || k >= c->d.gr0) continue;
     const int cc = cnt[k] & 0xff;
     const unsigned ui[3] = {(unsigned)hp[k].x, (unsigned)hp[k].y, (unsigned)hp[k].z};
     for (int q = 0; q < cc; q++) {
-      const unsigned e = rows[(size_t)q * n + k];
+      const unsigned e = rows[(size_t)q * cap + k];
       const int4 pj = hp[e & NEIGH_IDX_MASK];
       const int tj = pj.w >> 3;
       if (half) {
@@ -1147,21 +1372,24 @@ extern "C" int le_download_bondlist(le_ctx *c, int *rows, int64_t *nrows) {
   if (!c) return LE_EINVAL;
   if (!c->lists_valid) return fail(c, LE_ESTATE, "no bond list has been built yet");
   cudaSetDevice(c->device);
-  const size_t n = c->N; const int bpa = c->bpa;
-  std::vector<int> nb(n), bt(n * bpa), ba(n * bpa), hmap; std::vector<int4> hp(n);
+  const size_t n = c->N; const int bpa = c->bpa, cap = c->d.cap;
+  std::vector<int> nb(n), bt(n * bpa), ba(n * bpa), hmap; std::vector<int4> hp(cap);
   int r = fetch_map(c, hmap); if (r) return r;
   CK(cudaMemcpyAsync(nb.data(), c->d.num_bond, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaMemcpyAsync(bt.data(), c->d.bond_type, sizeof(int) * n * bpa, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaMemcpyAsync(ba.data(), c->d.bond_atom, sizeof(int) * n * bpa, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(hp.data(), c->d.pos_hold, sizeof(int4) * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(hp.data(), c->d.pos_hold, sizeof(int4) * cap, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   int64_t o = 0;
-  for (size_t i = 0; i < n; i++)
+  for (size_t i = 0; i < n; i++) {
+    const int ki = hmap[i];
+    if (ki < c->d.own0 || ki >= c->d.gr0) continue;         // rows of the atoms this GPU owns
     for (int m = 0; m < nb[i]; m++) {
       const int p = ba[i * bpa + m];
       // NTopoBondAll::build with newton_bond off: kept iff i < closest_image(partner); a ghost image (the bond
       // straddled the periodic boundary at the last rebuild) always is
-      const int4 pi = hp[hmap[i]], pj = hp[hmap[p - 1]];
+      if (hmap[p - 1] < 0) return fail(c, LE_ERUN, "Bond atoms %d %d missing", (int)i + 1, p);
+      const int4 pi = hp[ki], pj = hp[hmap[p - 1]];
       const bool cross = le_image_shift((unsigned)pi.x, (unsigned)pj.x) || le_image_shift((unsigned)pi.y, (unsigned)pj.y) ||
                          le_image_shift((unsigned)pi.z, (unsigned)pj.z);
       if (cross || (int)(i + 1) < p) {
@@ -1169,6 +1397,7 @@ extern "C" int le_download_bondlist(le_ctx *c, int *rows, int64_t *nrows) {
         o++;
       }
     }
+  }
   if (nrows) *nrows = o;
   return LE_OK;
 }
@@ -1184,13 +1413,30 @@ extern "C" int le_get_thermo(const le_ctx *c, int index, le_thermo *out) {
   return LE_OK;
 }
 
+/* raw tallies behind thermo record `index` on THIS GPU: 0 sum m v^2, 1 evdwl, 2 ebond, 3..8 virial, 9 FENE warnings.
+ * Multi-GPU callers sum them over ranks and normalise as thermo_from_slot does. */
+extern "C" int le_get_thermo_sums(const le_ctx *c, int index, double *out16) {
+  if (!c || !out16) return LE_EINVAL;
+  const int n = (int)c->thermo_sums.size();
+  if (index < 0) index += n;
+  if (index < 0 || index >= n) return LE_EINVAL;
+  for (int k = 0; k < LE_THERMO_W; k++) out16[k] = c->thermo_sums[index][k];
+  return LE_OK;
+}
+
+extern "C" int le_get_force_sums(const le_ctx *c, double *out16) {
+  if (!c || !out16 || c->force_sums.size() != LE_THERMO_W) return LE_EINVAL;
+  for (int k = 0; k < LE_THERMO_W; k++) out16[k] = c->force_sums[k];
+  return LE_OK;
+}
+
 extern "C" int le_get_stats(le_ctx *c, le_stats *out) {
   if (!c || !out) return LE_EINVAL;
   if (c->lists_valid) {
     cudaSetDevice(c->device);
     unsigned long long *dcount = (unsigned long long *)c->lf.scratch64;
     CK(cudaMemsetAsync(dcount, 0, 2 * sizeof(unsigned long long), c->stream));
-    LAUNCH(c, k_count_pairs, grid_for(c->N, 256), 256, c->d, dcount);
+    LAUNCH(c, k_count_pairs, grid_for(c->d.gr0 - c->d.own0, 256), 256, c->d, dcount);
     unsigned long long h[2];
     CK(cudaMemcpyAsync(h, dcount, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));

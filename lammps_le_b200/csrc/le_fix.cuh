@@ -47,6 +47,8 @@ struct LeFixDev {
   RngDev *rngdev;       // [3]
   RngHost rng[3];
   void *scratch64;
+  double *geo;          // [N][LE_GEO_D] position-dependent inputs of the current event, by tag (in the peer arena)
+  int *geo_i;           // [N][LE_GEO_I]
 };
 
 struct ExtrusionArgs { int btype, neutral, left, right, lr; double p; };
@@ -911,8 +913,8 @@ __global__ void k_load_create(LeView V, LoadArgs A) {
     const int k = d.map[i];
     int4 *pp = &d.pos[V.cur()][k];
     const int ty = (pp->w & 7) + 1;
-    if (ty == A.itype) { if (bc == A.imax) pp->w = (pp->w & ~7) | (A.inew - 1); }
-    else { if (bc == A.jmax) pp->w = (pp->w & ~7) | (A.jnew - 1); }
+    if (ty == A.itype) { if (bc == A.imax) { pp->w = (pp->w & ~7) | (A.inew - 1); d.type_tag[i] = A.inew; } }
+    else { if (bc == A.jmax) { pp->w = (pp->w & ~7) | (A.jnew - 1); d.type_tag[i] = A.jnew; } }
     f.final_add[i] = p; f.final_add[p - 1] = ti;
     if (ti < p) atomicAdd(&f.counters[CNT_NCREATE], 1);
   }

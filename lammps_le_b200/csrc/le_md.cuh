@@ -137,23 +137,50 @@ __device__ __forceinline__ void bond_term(ForceAcc &A, const Dev &d, const int4 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// peer flags (multi-GPU): system-scope release stores / acquire loads on words in a peer's arena
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+#define LE_PEER_TIMEOUT_CYCLES 40000000000LL   // ~20 s: a peer that is this late is gone
+// spin until (word >> shift) >= want; gives up (and makes every later wait return at once) on timeout / error
+__device__ __noinline__ unsigned long long le_wait_flag(Ctrl *c, const unsigned long long *p, unsigned long long want, int shift) {
+  const long long t0 = clock64();
+  for (;;) {
+    const unsigned long long v = ld_sys(p);
+    if ((v >> shift) >= want) return v;
+    if (*(volatile int *)&c->err) return 0;
+    if (clock64() - t0 > LE_PEER_TIMEOUT_CYCLES) { le_raise(c, LE_DERR_PEER_TIMEOUT, (int)want, (int)(v >> shift), shift); return 0; }
+    __nanosleep(64);
+  }
+}
+__device__ __forceinline__ int left_rank(const Dev &d) { return (d.rank + d.nranks - 1) % d.nranks; }
+__device__ __forceinline__ int right_rank(const Dev &d) { return (d.rank + 1) % d.nranks; }
+
 #define STEP_THREADS 256
 #define STEP_NB 4     // neighbor slots fetched in the first batch
 #define STEP_BB 3     // bond slots fetched in the first batch
 
-template <int EV>
+template <int EV, int DD>
 __global__ void __launch_bounds__(STEP_THREADS, EV ? 2 : 4) k_step(Dev d, StepArgs a) {
-  const int N = d.N;
-  const Ctrl *__restrict__ ctrl = d.ctrl;
+  const int cap = d.cap;
+  Ctrl *__restrict__ ctrl = d.ctrl;
   const int rd = ctrl->cur;
   const long long step = ctrl->step;
+  const int own_end = d.own0 + ctrl->nown;
   const int4 *__restrict__ posr = d.pos[rd];
   int4 *__restrict__ posw = d.pos[rd ^ 1];
   const unsigned *__restrict__ neigh = d.neigh;
   const unsigned *__restrict__ bondrow = d.bondrow;
   const float sx = c_P.fscale[0], sy = c_P.fscale[1], sz = c_P.fscale[2];
   const int nt = c_P.ntypes;
-  const int i = blockIdx.x * STEP_THREADS + threadIdx.x;
+  const int i = d.own0 + blockIdx.x * STEP_THREADS + threadIdx.x;
 
   double acc[10];
   if (EV) {
@@ -161,16 +188,16 @@ __global__ void __launch_bounds__(STEP_THREADS, EV ? 2 : 4) k_step(Dev d, StepAr
     for (int q = 0; q < 10; q++) acc[q] = 0.0;
   }
 
-  if (i < N) {
+  if (i < own_end) {
     // ---- batch 1: everything addressed by i ----
     const int4 pi = posr[i];
     float4 vi = d.vel[i];
     const unsigned cnt = d.counts[i];
     unsigned en[STEP_NB], eb[STEP_BB];
 #pragma unroll
-    for (int k = 0; k < STEP_NB; k++) en[k] = __ldg(&neigh[(size_t)k * N + i]);       // rows exist up to maxneigh >= 4
+    for (int k = 0; k < STEP_NB; k++) en[k] = __ldg(&neigh[(size_t)k * cap + i]);       // rows exist up to maxneigh >= 4
 #pragma unroll
-    for (int m = 0; m < STEP_BB; m++) eb[m] = (m < d.bpa) ? __ldg(&bondrow[(size_t)m * N + i]) : 0u;
+    for (int m = 0; m < STEP_BB; m++) eb[m] = (m < d.bpa) ? __ldg(&bondrow[(size_t)m * cap + i]) : 0u;
     const int4 ph = d.pos_hold[i];
     const int nn = cnt & 0xff, nb = (cnt >> 16) & 0xff;
     const int ti = pi.w & 7;
@@ -197,7 +224,7 @@ __global__ void __launch_bounds__(STEP_THREADS, EV ? 2 : 4) k_step(Dev d, StepAr
       if (k < nn && pair_screen(pi, pn[k], ti, nt, sx, sy, sz)) hit |= 1u << k;
     for (int k = STEP_NB; k < nn; k += 2) {          // rows beyond the first batch, two at a time
       const int k1 = min(k + 1, nn - 1);
-      const unsigned e0 = __ldg(&neigh[(size_t)k * N + i]), e1 = __ldg(&neigh[(size_t)k1 * N + i]);
+      const unsigned e0 = __ldg(&neigh[(size_t)k * cap + i]), e1 = __ldg(&neigh[(size_t)k1 * cap + i]);
       const int4 p0 = __ldg(&posr[e0 & NEIGH_IDX_MASK]), p1 = __ldg(&posr[e1 & NEIGH_IDX_MASK]);
       if (pair_screen(pi, p0, ti, nt, sx, sy, sz)) pair_term<EV>(A, pi, p0, e0, ti, nt);
       if (k1 > k && pair_screen(pi, p1, ti, nt, sx, sy, sz)) pair_term<EV>(A, pi, p1, e1, ti, nt);
@@ -213,7 +240,7 @@ __global__ void __launch_bounds__(STEP_THREADS, EV ? 2 : 4) k_step(Dev d, StepAr
     for (int m = 0; m < STEP_BB; m++)
       if (m < nb) bond_term<EV>(A, d, pi, pb[m], eb[m], tag);
     for (int m = STEP_BB; m < nb; m++) {
-      const unsigned e = __ldg(&bondrow[(size_t)m * N + i]);
+      const unsigned e = __ldg(&bondrow[(size_t)m * cap + i]);
       const int4 pj = __ldg(&posr[e & BOND_IDX_MASK]);
       bond_term<EV>(A, d, pi, pj, e, tag);
     }
@@ -289,12 +316,20 @@ __global__ void __launch_bounds__(STEP_THREADS, EV ? 2 : 4) k_step(Dev d, StepAr
         int iz = ((im >> 20) & 1023) - 512 + wz;  // 10+10+10 packing of LAMMPS_SMALLBIG (src/lmptype.h)
         d.img[i] = ((ix + 512) & 1023) | (((iy + 512) & 1023) << 10) | (((iz + 512) & 1023) << 20);
       }
-      posw[i] = make_int4((int)nx, (int)ny, (int)nz, pi.w);
+      const int4 pnew = make_int4((int)nx, (int)ny, (int)nz, pi.w);
+      posw[i] = pnew;
+      // halo update fused into the integrator: atoms of the slab's boundary layers are also stored straight into
+      // the neighbor GPU's ghost slots over NVLink (the receiving slot was fixed at the last rebuild)
+      if (DD) {
+        if (i < ctrl->send_l_end) d.peer[left_rank(d)].pos[rd ^ 1][d.gr0 + (i - d.own0)] = pnew;
+        const int srb = ctrl->send_r_beg;
+        if (i >= srb) d.peer[right_rank(d)].pos[rd ^ 1][i - srb] = pnew;
+      }
       // displacement since the last rebuild
       const float hx = (float)(int)(nx - (unsigned)ph.x) * sx;
       const float hy = (float)(int)(ny - (unsigned)ph.y) * sy;
       const float hz = (float)(int)(nz - (unsigned)ph.z) * sz;
-      if (hx * hx + hy * hy + hz * hz > c_P.triggersq) d.ctrl->moved = 1;
+      if (hx * hx + hy * hy + hz * hz > c_P.triggersq) ctrl->moved = 1;
     }
     d.vel[i] = vi;
   }
@@ -317,17 +352,44 @@ __global__ void __launch_bounds__(STEP_THREADS, EV ? 2 : 4) k_step(Dev d, StepAr
       }
     }
   }
+
+}
+
+// close a force-evaluation epoch (one thread, in the kernel that follows k_step in stream order): tell every peer
+// that this GPU's k_step -- and with it the halo stores into the peer's ghost slots -- is complete, together with
+// this GPU's "an atom moved half the skin" bit; then wait for the same word from every peer and fold the bits, so
+// that the reneighbor decision is identical everywhere (the MPI_Allreduce of Neighbor::decide,
+// src/neighbor.cpp:1944).  Words of consecutive epochs alternate between two slots: a peer can run at most one
+// epoch ahead.
+__device__ __forceinline__ void close_epoch(const Dev &d) {
+  Ctrl *c = d.ctrl;
+  const unsigned long long e = (unsigned long long)c->epoch;
+  if (d.nranks > 1) {
+    __threadfence_system();
+    int moved = c->moved;
+    const unsigned long long word = (e << 1) | (unsigned long long)(moved != 0);
+    const int slot = FLAG_STEP + (int)(e & 1) * LE_MAXRANKS;
+    for (int p = 0; p < d.nranks; p++)
+      if (p != d.rank) st_sys(&d.peer[p].flags[slot + d.rank], word);
+    for (int p = 0; p < d.nranks; p++) {
+      if (p == d.rank) continue;
+      const unsigned long long v = le_wait_flag(c, &d.flags[slot + p], e, 1);
+      moved |= (int)(v & 1);
+    }
+    c->moved = moved;
+  }
+  c->epoch = (long long)e + 1;
 }
 
 // ------------------------------------------------------------------------------------------------
 // Neighbor::decide (src/neighbor.cpp:1933-1948): one thread.  With advance != 0 it first closes the
-// timestep (ntimestep++, swap the position buffers).  When it decides to rebuild it also does the
-// bookkeeping of Neighbor::build (ago = 0, ncalls++) because the rebuild kernels that follow are a
-// conditional graph node switched by cudaGraphSetConditional.
+// timestep (ntimestep++, swap the position buffers, wait for the peers' halos).  When it decides to
+// rebuild it also does the bookkeeping of Neighbor::build (ago = 0, ncalls++) because the rebuild
+// kernels that follow are a conditional graph node switched by cudaGraphSetConditional.
 // ------------------------------------------------------------------------------------------------
 __global__ void k_decide(Dev d, cudaGraphConditionalHandle handle, int advance, int use_handle) {
   Ctrl *c = d.ctrl;
-  if (advance) { c->step++; c->cur ^= 1; }
+  if (advance) { c->step++; c->cur ^= 1; close_epoch(d); }
   int r = 0;
   if (c->forced) r = 1;
   else {
@@ -348,7 +410,7 @@ __global__ void k_decide(Dev d, cudaGraphConditionalHandle handle, int advance, 
 }
 
 // close a timestep without deciding (the USER-LE fixes of the new step run before Neighbor::decide)
-__global__ void k_advance(Dev d) { d.ctrl->step++; d.ctrl->cur ^= 1; }
+__global__ void k_advance(Dev d) { d.ctrl->step++; d.ctrl->cur ^= 1; close_epoch(d); }
 
 // bookkeeping of an unconditional rebuild (Verlet::setup, le_force_rebuild)
 __global__ void k_after_build(Dev d) {
@@ -359,33 +421,106 @@ __global__ void k_after_build(Dev d) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// cell sort.  Cells are at least one neighbor cutoff wide; the fixed-point coordinate gives the
-// cell by one multiply-high.  Within a cell atoms are ordered by tag so that the sorted order --
-// and with it every floating-point sum downstream -- is reproducible from run to run.
+// rebuild, part 1: migration + cell sort of the owned atoms.
+//   Cells are at least one neighbor cutoff wide; the fixed-point coordinate gives the cell by one
+//   multiply-high.  Within a cell atoms are ordered by tag so that the local order -- and with it every
+//   floating-point sum downstream -- is reproducible from run to run.  An atom whose cell has left
+//   this GPU's slab is written straight into the inbox of the neighbor GPU (CommBrick::exchange,
+//   src/comm_brick.cpp:601-722); bond and special rows are replicated by tag, so the extruder bonds
+//   of a migrating bead arrive with it.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int cell_of(const Dev &d, int4 p) {
-  const int cx = __umulhi((unsigned)p.x, (unsigned)d.ncell[0]);
-  const int cy = __umulhi((unsigned)p.y, (unsigned)d.ncell[1]);
-  const int cz = __umulhi((unsigned)p.z, (unsigned)d.ncell[2]);
-  return (cz * d.ncell[1] + cy) * d.ncell[0] + cx;
+struct RbScratch { int out_count[2]; int in_count[2]; };
+
+__global__ void k_rb_begin(Dev d, RbScratch *rb) {
+  d.ctrl->rebuild_epoch++;
+  d.ctrl->nown_unsorted = d.ctrl->nown;
+  rb->out_count[0] = rb->out_count[1] = 0;
+  rb->in_count[0] = rb->in_count[1] = 0;
 }
 
-__global__ void k_cell_count(Dev d) {
+// forget the ghosts of the previous list (their tags may be anywhere after this rebuild)
+__global__ void k_clear_ghost_map(Dev d) {
+  const int nl = d.ctrl->nghl, nr = d.ctrl->nghr;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < nl + nr; g += gridDim.x * blockDim.x) {
+    // ghost_tag is this GPU's private record of its ghosts: the peers may already be overwriting pos_hold's ghost slots
+    d.map[d.ghost_tag[g] - 1] = -1;
+  }
+}
+
+__global__ void k_cell_count(Dev d, RbScratch *rb) {
   const int4 *__restrict__ pos = d.pos[d.ctrl->cur];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) {
-    const int c = cell_of(d, pos[i]);
+  const int lo = d.own0, hi = d.own0 + d.ctrl->nown;
+  for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
+    const int4 p = pos[i];
+    const int cx = __umulhi((unsigned)p.x, (unsigned)d.ncell[0]);
+    const int cy = __umulhi((unsigned)p.y, (unsigned)d.ncell[1]);
+    const int cz = __umulhi((unsigned)p.z, (unsigned)d.ncell[2]);
+    const int lx = local_layer(d, cx);
+    if (lx >= d.halo && lx < d.nlx - d.halo) {
+      const int c = cell_slot(d, lx, cy, cz);
+      d.cellid[i] = c;
+      d.slot[i] = atomicAdd(&d.cell_count[c], 1);
+    } else {
+      d.cellid[i] = -1;
+      d.map[(p.w >> 3) - 1] = -1;
+      if (lx < 0) { le_raise(d.ctrl, LE_DERR_LOCAL_OVERFLOW, p.w >> 3, cx, 1); continue; }
+      const int side = lx < d.halo ? 0 : 1;                 // 0: to the left neighbor
+      const int k = atomicAdd(&rb->out_count[side], 1);
+      if (k >= d.inbox_cap) { le_raise(d.ctrl, LE_DERR_LOCAL_OVERFLOW, k, d.inbox_cap, 2); continue; }
+      const PeerView &pv = d.peer[side == 0 ? left_rank(d) : right_rank(d)];
+      const size_t o = (size_t)(side == 0 ? 1 : 0) * d.inbox_cap + k;   // it arrives "from the right" at the left neighbor
+      pv.in_pos[o] = p; pv.in_vel[o] = d.vel[i]; pv.in_img[o] = d.img[i];
+    }
+  }
+}
+
+// tell the neighbors how many migrants were written into their inboxes, wait for ours
+__global__ void k_rb_post_inbox(Dev d, RbScratch *rb) {
+  Ctrl *c = d.ctrl;
+  __threadfence_system();
+  const unsigned long long e = (unsigned long long)c->rebuild_epoch;
+  const int par = (int)(e & 1) * 2;
+  st_sys(&d.peer[left_rank(d)].flags[FLAG_INBOX + par + 1], (e << 24) | (unsigned)rb->out_count[0]);
+  st_sys(&d.peer[right_rank(d)].flags[FLAG_INBOX + par + 0], (e << 24) | (unsigned)rb->out_count[1]);
+  for (int side = 0; side < 2; side++) {
+    const unsigned long long v = le_wait_flag(c, &d.flags[FLAG_INBOX + par + side], e, 24);
+    rb->in_count[side] = (int)(v & 0xffffffu);
+  }
+  c->nown_unsorted = c->nown + rb->in_count[0] + rb->in_count[1];
+  if (d.own0 + c->nown_unsorted > d.gr0) le_raise(c, LE_DERR_LOCAL_OVERFLOW, c->nown_unsorted, d.gr0 - d.own0, 3);
+}
+
+// append the arrived atoms behind the owned ones and count them into their cells
+__global__ void k_inbox(Dev d, RbScratch *rb) {
+  const int n0 = rb->in_count[0], n1 = rb->in_count[1];
+  const int cur = d.ctrl->cur;
+  const int base = d.own0 + d.ctrl->nown;
+  if (base + n0 + n1 > d.gr0) return;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n0 + n1; k += gridDim.x * blockDim.x) {
+    const size_t o = k < n0 ? (size_t)k : (size_t)d.inbox_cap + (k - n0);
+    const int4 p = d.in_pos[o];
+    const int i = base + k;
+    d.pos[cur][i] = p; d.vel[i] = d.in_vel[o]; d.img[i] = d.in_img[o];
+    const int cx = __umulhi((unsigned)p.x, (unsigned)d.ncell[0]);
+    const int cy = __umulhi((unsigned)p.y, (unsigned)d.ncell[1]);
+    const int cz = __umulhi((unsigned)p.z, (unsigned)d.ncell[2]);
+    const int lx = local_layer(d, cx);
+    if (lx < d.halo || lx >= d.nlx - d.halo) { le_raise(d.ctrl, LE_DERR_LOCAL_OVERFLOW, p.w >> 3, cx, 4); d.cellid[i] = -1; continue; }
+    const int c = cell_slot(d, lx, cy, cz);
     d.cellid[i] = c;
     d.slot[i] = atomicAdd(&d.cell_count[c], 1);
   }
 }
 
 #define SCAN_BLOCK 1024
-// exclusive scan of cell_count -> cell_start in three launches; also re-zeroes cell_count
+// exclusive scan of cell_count over the owned region's cell slots -> cell_start (three launches); re-zeroes cell_count
+__device__ __forceinline__ int own_cell_first(const Dev &d) { return cell_slot(d, d.halo, 0, 0); }
+__device__ __forceinline__ int own_cell_count(const Dev &d) { return (d.nlx - 2 * d.halo) * d.ncell[1] * d.ncell[2]; }
+
 __global__ void k_scan_partial(Dev d) {
   __shared__ int sh[32];
-  const int base = blockIdx.x * SCAN_BLOCK;
-  const int idx = base + threadIdx.x;
-  int v = (idx < d.ncells) ? d.cell_count[idx] : 0;
+  const int idx = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+  int v = (idx < own_cell_count(d)) ? d.cell_count[own_cell_first(d) + idx] : 0;
   int s = v;
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
@@ -429,39 +564,49 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_blocks(Dev d) {  // one blo
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
-  for (int base = 0; base < d.nscanblocks; base += SCAN_BLOCK) {
+  const int nblocks = (own_cell_count(d) + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  for (int base = 0; base < nblocks; base += SCAN_BLOCK) {
     const int idx = base + threadIdx.x;
-    const int v = (idx < d.nscanblocks) ? d.blocksum[idx] : 0;
+    const int v = (idx < nblocks) ? d.blocksum[idx] : 0;
     int tot;
     const int ex = block_excl_scan(v, &tot);
-    if (idx < d.nscanblocks) d.blocksum[idx] = carry + ex;
+    if (idx < nblocks) d.blocksum[idx] = carry + ex;
     __syncthreads();
     if (threadIdx.x == 0) carry += tot;
     __syncthreads();
+  }
+  // the owned population after migration; the sentinel slot behind the owned region closes its last cell
+  if (threadIdx.x == 0) {
+    d.ctrl->nown = carry;
+    d.cell_start[own_cell_first(d) + own_cell_count(d)] = d.own0 + carry;
   }
 }
 
 __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_apply(Dev d) {
   const int idx = blockIdx.x * SCAN_BLOCK + threadIdx.x;
-  const int v = (idx < d.ncells) ? d.cell_count[idx] : 0;
+  const int n = own_cell_count(d), first = own_cell_first(d);
+  const int v = (idx < n) ? d.cell_count[first + idx] : 0;
   const int ex = block_excl_scan(v, nullptr);
-  if (idx < d.ncells) {
-    d.cell_start[idx] = d.blocksum[blockIdx.x] + ex;
-    d.cell_count[idx] = 0;
+  if (idx < n) {
+    d.cell_start[first + idx] = d.own0 + d.blocksum[blockIdx.x] + ex;
+    d.cell_count[first + idx] = 0;
   }
-  if (idx == d.ncells - 1) d.cell_start[d.ncells] = d.N;
 }
 
 __global__ void k_cell_scatter(Dev d) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x)
-    d.order[d.cell_start[d.cellid[i]] + d.slot[i]] = i;
+  const int lo = d.own0, hi = d.own0 + d.ctrl->nown_unsorted;
+  for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
+    const int c = d.cellid[i];
+    if (c >= 0) d.order[d.cell_start[c] + d.slot[i]] = i;
+  }
 }
 
-// order each cell's members by tag (insertion sort; cells hold a handful of atoms)
+// order each owned cell's members by tag (insertion sort; cells hold a handful of atoms)
 __global__ void k_cell_sort(Dev d) {
   const int4 *__restrict__ pos = d.pos[d.ctrl->cur];
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < d.ncells; c += gridDim.x * blockDim.x) {
-    const int s = d.cell_start[c], e = d.cell_start[c + 1];
+  const int n = own_cell_count(d), first = own_cell_first(d);
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+    const int s = d.cell_start[first + q], e = d.cell_start[first + q + 1];
     for (int a = s + 1; a < e; a++) {
       const int ia = d.order[a];
       const int ta = pos[ia].w >> 3;
@@ -477,16 +622,90 @@ __global__ void k_cell_sort(Dev d) {
   }
 }
 
-// gather into sorted order: pos_hold (= new xhold), vel_tmp, img_hold; refresh the tag map
+// gather into the new local order: pos_hold (= new xhold), vel_tmp, img_hold; refresh the tag map
 __global__ void k_gather(Dev d) {
   const int4 *__restrict__ pos = d.pos[d.ctrl->cur];
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < d.N; k += gridDim.x * blockDim.x) {
+  const int lo = d.own0, hi = d.own0 + d.ctrl->nown;
+  for (int k = lo + blockIdx.x * blockDim.x + threadIdx.x; k < hi; k += gridDim.x * blockDim.x) {
     const int i = d.order[k];
     const int4 p = pos[i];
     d.pos_hold[k] = p;
     d.vel_tmp[k] = d.vel[i];
     d.img_hold[k] = d.img[i];
     d.map[(p.w >> 3) - 1] = k;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// rebuild, part 2 (multi-GPU): ghost creation (CommBrick::borders, src/comm_brick.cpp:727-876).
+//   Because x is the slowest index of the local order, the atoms of the slab's first / last `halo`
+//   layers are one contiguous slice each; it is stored verbatim into the neighbor's ghost slots
+//   together with the matching cell_start entries, so the neighbor needs neither a sort nor a scan
+//   for its ghosts and the per-step halo update of k_step is slot-for-slot.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int peer_cell_slot(const Dev &d, int nlx_peer, int lx, int cy, int cz) {
+  return (lx * d.ncell[1] + cy) * d.ncell[2] + cz + (lx >= d.halo) + (lx >= nlx_peer - d.halo);
+}
+
+__global__ void k_push_ghosts(Dev d) {
+  Ctrl *c = d.ctrl;
+  const int H = d.halo, ncy = d.ncell[1], ncz = d.ncell[2];
+  const int layer = ncy * ncz;
+  const int cur = c->cur;
+  const int own_lo = d.own0, own_hi = d.own0 + c->nown;
+  const int sl_end = d.cell_start[cell_slot(d, 2 * H - 1, ncy - 1, ncz - 1) + 1];   // end of my first H layers
+  const int sr_beg = d.cell_start[cell_slot(d, d.nlx - 2 * H, 0, 0)];               // start of my last H layers
+  const PeerView &L = d.peer[left_rank(d)], &R = d.peer[right_rank(d)];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  if (tid == 0) {
+    c->send_l_end = sl_end; c->send_r_beg = sr_beg;
+    if (sl_end - own_lo > d.own0 || own_hi - sr_beg > d.own0) le_raise(c, LE_DERR_LOCAL_OVERFLOW, sl_end - own_lo, own_hi - sr_beg, 5);
+  }
+  if (sl_end - own_lo > d.own0 || own_hi - sr_beg > d.own0) return;
+  for (int k = own_lo + tid; k < sl_end; k += nth) {          // -> right ghosts of the left neighbor
+    const int4 p = d.pos_hold[k];
+    L.pos_hold[d.gr0 + (k - own_lo)] = p;
+    L.pos[cur][d.gr0 + (k - own_lo)] = p;
+  }
+  for (int k = sr_beg + tid; k < own_hi; k += nth) {          // -> left ghosts of the right neighbor
+    const int4 p = d.pos_hold[k];
+    R.pos_hold[k - sr_beg] = p;
+    R.pos[cur][k - sr_beg] = p;
+  }
+  for (int q = tid; q <= H * layer; q += nth) {               // cell_start of those layers (+ the closing sentinel)
+    const int lx = q / layer, rem = q - lx * layer;
+    const int cy = rem / ncz, cz = rem - cy * ncz;
+    if (q < H * layer) {
+      L.cell_start[peer_cell_slot(d, d.nlx_left, d.nlx_left - H + lx, cy, cz)] = d.gr0 + (d.cell_start[cell_slot(d, H + lx, cy, cz)] - own_lo);
+      R.cell_start[peer_cell_slot(d, d.nlx_right, lx, cy, cz)] = d.cell_start[cell_slot(d, d.nlx - 2 * H + lx, cy, cz)] - sr_beg;
+    } else {
+      L.cell_start[d.nlx_left * layer + 2] = d.gr0 + (sl_end - own_lo);
+      R.cell_start[H * layer] = own_hi - sr_beg;
+    }
+  }
+}
+
+__global__ void k_rb_post_ghosts(Dev d) {
+  Ctrl *c = d.ctrl;
+  __threadfence_system();
+  const unsigned long long e = (unsigned long long)c->rebuild_epoch;
+  const int par = (int)(e & 1) * 2;
+  // my first layers are the left neighbor's RIGHT ghosts (side 1 there); my last layers the right neighbor's LEFT ghosts
+  st_sys(&d.peer[left_rank(d)].flags[FLAG_GHOST + par + 1], (e << 24) | (unsigned)(c->send_l_end - d.own0));
+  st_sys(&d.peer[right_rank(d)].flags[FLAG_GHOST + par + 0], (e << 24) | (unsigned)(d.own0 + c->nown - c->send_r_beg));
+  const unsigned long long v0 = le_wait_flag(c, &d.flags[FLAG_GHOST + par + 0], e, 24);
+  const unsigned long long v1 = le_wait_flag(c, &d.flags[FLAG_GHOST + par + 1], e, 24);
+  c->nghl = (int)(v0 & 0xffffffu);
+  c->nghr = (int)(v1 & 0xffffffu);
+}
+
+__global__ void k_ghost_map(Dev d) {
+  const int nl = d.ctrl->nghl, nr = d.ctrl->nghr;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < nl + nr; g += gridDim.x * blockDim.x) {
+    const int k = g < nl ? g : d.gr0 + (g - nl);
+    const int tag = d.pos_hold[k].w >> 3;
+    d.ghost_tag[g] = tag;
+    d.map[tag - 1] = k;
   }
 }
 
@@ -518,21 +737,22 @@ __device__ __noinline__ int build_border(int4 pi, int4 pj, int tp) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// neighbor + bond list build, one thread per atom of the sorted order.
-//   The atom's 3x3 rows of cells are walked as ONE flattened candidate stream (the three x-cells of
-//   a row are contiguous in the sorted order); positions carry tag and type, so a candidate costs
-//   one 16-byte load.  The distance is taken in fp32 on the exact fixed-point differences; only the
-//   1e-5 sliver around cutneighsq is re-evaluated in fp64 on the dequantised coordinates with the
-//   reference's operation order (delx = xi - xj', rsq = dx*dx+dy*dy+dz*dz, rsq <= cutneighsq;
-//   npair_half_bin_newton.cpp:98-103), so the pair set is bit-identical to NPairHalfBinNewton::build
-//   on the same coordinates.  Every accepted pair goes into the full row of BOTH atoms with the
-//   special-bond bits of find_special; which of the two the reference's half list stores it on
-//   (same-bin rule :84-91, upper-half stencil nstencil_half_bin_3d_newton.cpp:26-38) is only needed
-//   for the (t,t+2) pairs fix ex_load scans (derived there from pos_hold) and for le_download_neighlist.
+// rebuild, part 3: neighbor + bond list build, one thread per owned atom.
+//   The atom's 3x3 columns of cells are walked one after the other (the three z-cells of a column are
+//   contiguous in the local order, so a column is one slot range); positions carry tag and type, so a
+//   candidate costs one 16-byte load.  The distance is taken in
+//   fp32 on the exact fixed-point differences; only the 1e-5 sliver around cutneighsq is re-evaluated
+//   in fp64 on the dequantised coordinates with the reference's operation order (delx = xi - xj',
+//   rsq = dx*dx+dy*dy+dz*dz, rsq <= cutneighsq; npair_half_bin_newton.cpp:98-103), so the pair set is
+//   bit-identical to NPairHalfBinNewton::build on the same coordinates.  Every accepted pair goes into
+//   the full row of BOTH atoms with the special-bond bits of find_special; which of the two the
+//   reference's half list stores it on (same-bin rule :84-91, upper-half stencil
+//   nstencil_half_bin_3d_newton.cpp:26-38) is only needed for the (t,t+2) pairs fix ex_load scans
+//   (derived there from pos_hold) and for le_download_neighlist.
 //   Domain::minimum_image_check (npair_half_bin_newton.cpp:111) cannot fire here: the difference is
 //   the minimum image by construction and the box is at least two neighbor cutoffs wide.
-//   Also: bond partner rows (NTopoBondAll::build, src/ntopo_bond_all.cpp:39-86) and the copy of the sorted
-//   state back into the live arrays.
+//   Also: bond partner rows (NTopoBondAll::build, src/ntopo_bond_all.cpp:39-86) and the copy of the
+//   sorted state back into the live arrays.
 // ------------------------------------------------------------------------------------------------
 #define BUILD_THREADS 128
 #define BUILD_QUEUE 12
@@ -541,7 +761,7 @@ struct BuildCtx {
   unsigned *row;
   const int *srow;
   int s0, s1, s2, s3, n1, n2, nscan;
-  int tagi, ti, nt, maxn, N, n;
+  int tagi, ti, nt, maxn, cap, n;
 };
 
 // decide one screened candidate and append it to the row
@@ -553,26 +773,36 @@ __device__ __forceinline__ void build_accept(const Dev &d, BuildCtx &B, const in
   if (which < 0) return;
   if (rsqf >= c_P.cutneigh_lo[tp] && !build_border(pi, pj, tp)) return;
   if (B.n >= B.maxn) { le_raise(d.ctrl, LE_DERR_NEIGH_OVERFLOW, B.tagi, B.maxn); return; }
-  B.row[(size_t)B.n * B.N] = (unsigned)j | ((unsigned)which << 30);
+  B.row[(size_t)B.n * B.cap] = (unsigned)j | ((unsigned)which << 30);
   B.n++;
 }
 
 __global__ void __launch_bounds__(BUILD_THREADS) k_build(Dev d) {
   __shared__ int s_q[BUILD_QUEUE][BUILD_THREADS];
-  const int N = d.N;
+  const int cap = d.cap;
   const int cur = d.ctrl->cur;
   const int4 *__restrict__ ph = d.pos_hold;
   const int t = threadIdx.x;
-  const int i = blockIdx.x * BUILD_THREADS + t;
-  if (i >= N) return;
+  const int i = d.own0 + blockIdx.x * BUILD_THREADS + t;
+  if (i >= d.own0 + d.ctrl->nown) return;
   const int4 pi = ph[i];
+  BuildCtx B;
+  B.tagi = pi.w >> 3; B.ti = pi.w & 7; B.nt = c_P.ntypes; B.maxn = d.maxneigh; B.cap = cap; B.n = 0;
+  B.row = d.neigh + i;
+  B.srow = d.special + (size_t)(B.tagi - 1) * d.maxspecial;
+  // bond table of this atom: issue the tag-order loads now, they are consumed after the candidate scan
+  const int tagi = B.tagi;
+  const int nb = d.num_bond[tagi - 1];
+  int bpart[4] = {0, 0, 0, 0}, btyp[4] = {0, 0, 0, 0};
+  if (d.bpa == 4) {
+    const int4 a4 = *(const int4 *)(d.bond_atom + (size_t)(tagi - 1) * 4);
+    const int4 t4 = *(const int4 *)(d.bond_type + (size_t)(tagi - 1) * 4);
+    bpart[0] = a4.x; bpart[1] = a4.y; bpart[2] = a4.z; bpart[3] = a4.w;
+    btyp[0] = t4.x; btyp[1] = t4.y; btyp[2] = t4.z; btyp[3] = t4.w;
+  }
   d.pos[cur][i] = pi;
   d.vel[i] = d.vel_tmp[i];
   d.img[i] = d.img_hold[i];
-  BuildCtx B;
-  B.tagi = pi.w >> 3; B.ti = pi.w & 7; B.nt = c_P.ntypes; B.maxn = d.maxneigh; B.N = N; B.n = 0;
-  B.row = d.neigh + i;
-  B.srow = d.special + (size_t)(B.tagi - 1) * d.maxspecial;
   {
     const int *ns = d.nspecial + (size_t)(B.tagi - 1) * 3;
     const int n1 = ns[0], n2 = ns[1], n3 = ns[2];
@@ -586,25 +816,32 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_build(Dev d) {
   const int cx = __umulhi((unsigned)pi.x, (unsigned)ncx);
   const int cy = __umulhi((unsigned)pi.y, (unsigned)ncy);
   const int cz = __umulhi((unsigned)pi.z, (unsigned)ncz);
-  // per row (cy', cz') the three x-cells are one contiguous range of the sorted order; a row that wraps in x
+  const int lx = local_layer(d, cx);
+  // per column (lx', cy') the three z-cells are one contiguous range of the local order; a column that wraps in z
   // gets its far cell as a second, single-cell range (pass 1)
-  const int xlo = d.cell_abs[0] ? 0 : max(cx - 1, 0), xhi = d.cell_abs[0] ? ncx - 1 : min(cx + 1, ncx - 1);
-  const int xwrap = d.cell_abs[0] ? -1 : (cx == 0 ? ncx - 1 : (cx == ncx - 1 ? 0 : -1));
+  const int zlo = d.cell_abs[2] ? 0 : max(cz - 1, 0), zhi = d.cell_abs[2] ? ncz - 1 : min(cz + 1, ncz - 1);
+  const int zwrap = d.cell_abs[2] ? -1 : (cz == 0 ? ncz - 1 : (cz == ncz - 1 ? 0 : -1));
   const float screen = c_P.cutneighmaxsq_f;
   const float fsx = c_P.fscale[0], fsy = c_P.fscale[1], fsz = c_P.fscale[2];
   int nq = 0;
+  // the partners' slots: the map entries were written by k_gather / k_ghost_map before this kernel
+  int bslot[4] = {0, 0, 0, 0};
+  if (d.bpa == 4) {
+#pragma unroll
+    for (int m = 0; m < 4; m++) bslot[m] = (m < nb) ? __ldg(&d.map[bpart[m] - 1]) : 0;
+  }
 
   // ---- phase 1: fp32 screen of every candidate, four independent loads at a time ----
-  for (int pass = 0; pass < (xwrap >= 0 ? 2 : 1); pass++) {
-    const int xa = pass ? xwrap : xlo, xb = pass ? xwrap : xhi;
-    for (int oz = 0; oz < d.cell_span[2]; oz++) {
-      int zc = d.cell_abs[2] ? oz : cz - 1 + oz;
-      if (zc < 0) zc += ncz; else if (zc >= ncz) zc -= ncz;
+  for (int pass = 0; pass < (zwrap >= 0 ? 2 : 1); pass++) {
+    const int za = pass ? zwrap : zlo, zb = pass ? zwrap : zhi;
+    for (int ox = 0; ox < d.cell_span[0]; ox++) {
+      int xc = d.cell_abs[0] ? ox : lx - 1 + ox;
+      if (d.nranks == 1) { if (xc < 0) xc += ncx; else if (xc >= ncx) xc -= ncx; }   // one GPU: the slab is the whole box
       for (int oy = 0; oy < d.cell_span[1]; oy++) {
         int yc = d.cell_abs[1] ? oy : cy - 1 + oy;
         if (yc < 0) yc += ncy; else if (yc >= ncy) yc -= ncy;
-        const int base = (zc * ncy + yc) * ncx;
-        const int lo = __ldg(&d.cell_start[base + xa]), hi = __ldg(&d.cell_start[base + xb + 1]);
+        const int base = cell_slot(d, xc, yc, 0);
+        const int lo = __ldg(&d.cell_start[base + za]), hi = __ldg(&d.cell_start[base + zb + 1]);
         for (int j = lo; j < hi; j += 4) {
           int4 p[4];
 #pragma unroll
@@ -629,31 +866,42 @@ __global__ void __launch_bounds__(BUILD_THREADS) k_build(Dev d) {
   // ---- phase 2: decide the queued candidates ----
   const int nqq = min(nq, BUILD_QUEUE);
   for (int q = 0; q < nqq; q++) {
-    const int j = s_q[q][t];
-    const int4 pj = __ldg(&ph[j]);
+    const int jq = s_q[q][t];
+    const int4 pj = __ldg(&ph[jq]);
     const int idx = (int)((unsigned)pj.x - (unsigned)pi.x);
     const int idy = (int)((unsigned)pj.y - (unsigned)pi.y);
     const int idz = (int)((unsigned)pj.z - (unsigned)pi.z);
     const float fx = (float)idx * fsx, fy = (float)idy * fsy, fz = (float)idz * fsz;
-    build_accept(d, B, pi, pj, j, fx * fx + fy * fy + fz * fz);
+    build_accept(d, B, pi, pj, jq, fx * fx + fy * fy + fz * fz);
   }
 
   // bond partner rows
-  const int tagi = B.tagi;
-  const int nb = d.num_bond[tagi - 1];
-  for (int m = 0; m < nb; m++) {
-    const int pt = d.bond_atom[(size_t)(tagi - 1) * d.bpa + m];
-    const int bt = d.bond_type[(size_t)(tagi - 1) * d.bpa + m];
-    const int jb = d.map[pt - 1];
-    d.bondrow[(size_t)m * N + i] = (unsigned)jb | ((unsigned)(bt - 1) << 28);
+  bool missing = false;
+  if (d.bpa == 4) {
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+      if (m < nb) {
+        if (bslot[m] < 0) missing = true;
+        else d.bondrow[(size_t)m * cap + i] = (unsigned)bslot[m] | ((unsigned)(btyp[m] - 1) << 28);
+      }
+  } else {
+    for (int m = 0; m < nb; m++) {
+      const int pt = d.bond_atom[(size_t)(tagi - 1) * d.bpa + m];
+      const int bt = d.bond_type[(size_t)(tagi - 1) * d.bpa + m];
+      const int jb = d.map[pt - 1];
+      if (jb < 0) { missing = true; continue; }
+      d.bondrow[(size_t)m * cap + i] = (unsigned)jb | ((unsigned)(bt - 1) << 28);
+    }
   }
+  if (missing) le_raise(d.ctrl, LE_DERR_MISSING_ATOM, tagi, nb);
   d.counts[i] = (unsigned)B.n | ((unsigned)nb << 16);
 }
 
 // list statistics on demand
 __global__ void k_count_pairs(Dev d, unsigned long long *out) {
   unsigned long long h = 0, f = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) {
+  const int lo = d.own0, hi = d.own0 + d.ctrl->nown;
+  for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
     const unsigned c = d.counts[i];
     f += c & 0xff;
   }

@@ -78,6 +78,8 @@ def load_library():
         "le_download_bondlist": [P, pi, C.POINTER(I64)], "le_thermo_count": [P],
         "le_get_thermo": [P, I, C.POINTER(Thermo)], "le_get_stats": [P, C.POINTER(Stats)], "le_compute_rg": [P, pd],
         "le_gen_saw_chains": [I, I, D, D, D, C.c_uint64, pd, pi], "le_gen_lattice_melt": [I, I, D, pd, pd, pi],
+        "le_dd_init": [P, I, I, D], "le_dd_get_handle": [P, C.c_void_p], "le_dd_connect": [P, C.c_void_p],
+        "le_get_thermo_sums": [P, I, pd], "le_get_force_sums": [P, pd],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
