@@ -739,6 +739,8 @@ extern "C" int le_upload_atoms(le_ctx *c, int n, const int *tag, const int *type
   CK(cudaMemcpyAsync(d.map, hmap.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(d.type_tag, htype.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
   CK(cudaMemcpyAsync(&d.ctrl->nown, &nown, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  const long long one = 1;       // epoch 0 is what an untouched peer flag reads as
+  CK(cudaMemcpyAsync(&d.ctrl->epoch, &one, sizeof one, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   c->lists_valid = false; c->params_dirty = true;
   return LE_OK;

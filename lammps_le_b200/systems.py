@@ -86,10 +86,15 @@ def maxwell_velocities(n, temp, masses_per_atom, seed):
     return v
 
 
-def make_engine(system, device=0, skin=0.4, every=1, delay=1, check=1, dt=0.005, maxneigh=None, velocities=None):
-    """Engine configured like the reference deck of SURVEY.md Appendix B for `system`."""
+def make_engine(system, device=0, skin=0.4, every=1, delay=1, check=1, dt=0.005, maxneigh=None, velocities=None, dd=None):
+    """Engine configured like the reference deck of SURVEY.md Appendix B for `system`.
+    dd = dict(rank=, world=, halo=, group=): one slab of a multi-GPU run (engine_dd.DDEngine)."""
     lo, hi = system["box"]
-    e = Engine(lo, hi, (1, 1, 1), device)
+    if dd:
+        from .engine_dd import DDEngine
+        e = DDEngine(lo, hi, (1, 1, 1), device, **dd)
+    else:
+        e = Engine(lo, hi, (1, 1, 1), device)
     e.set_types(system["masses"], system["nbondtypes"])
     e.set_pair_lj(1.0, 1.0, WCA_CUT, shift=True)
     for bt, (style, params) in system["bond_coeffs"].items():
