@@ -707,6 +707,7 @@ extern "C" int le_upload_atoms(le_ctx *c, int n, const int *tag, const int *type
   if (c->nranks == 1) {
     if ((r = dalloc(c, &c->lf.geo, (size_t)n * LE_GEO_D))) return r;
     if ((r = dalloc(c, &c->lf.geo_i, (size_t)n * LE_GEO_I))) return r;
+    d.peer[0].geo = c->lf.geo; d.peer[0].geo_i = c->lf.geo_i;
   } else {
     c->lf.geo = d.peer[c->rank].geo; c->lf.geo_i = d.peer[c->rank].geo_i;
   }

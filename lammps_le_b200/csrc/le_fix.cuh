@@ -287,25 +287,31 @@ struct LeView {
 };
 
 // the coordinate the reference holds for an OWNED atom between reneighborings: wrapped at the last
-// rebuild (Domain::pbc runs only then, src/verlet.cpp:272), drifting freely since
-__device__ __forceinline__ void raw_xyz(const LeView &V, int tag, double x[3]) {
+// rebuild (Domain::pbc runs only then, src/verlet.cpp:272), drifting freely since.  The number of box
+// crossings since the rebuild is the wrap of the 32-bit coordinate relative to pos_hold, which is also
+// available for ghosts.  Returns false if the atom is not on this GPU (halo too thin).
+__device__ __forceinline__ bool raw_xyz(const LeView &V, int tag, double x[3]) {
   const int k = V.d.map[tag - 1];
-  const int4 p = V.d.pos[V.cur()][k];
-  const int im = V.d.img[k], ih = V.d.img_hold[k];
+  if (k < 0) { le_raise(V.d.ctrl, LE_DERR_MISSING_ATOM, tag, 0, 1); x[0] = x[1] = x[2] = 0.0; return false; }
+  const int4 p = V.d.pos[V.cur()][k], h = V.d.pos_hold[k];
   const unsigned u[3] = {(unsigned)p.x, (unsigned)p.y, (unsigned)p.z};
-  const int di[3] = {(im & 1023) - (ih & 1023), ((im >> 10) & 1023) - ((ih >> 10) & 1023), ((im >> 20) & 1023) - ((ih >> 20) & 1023)};
+  const unsigned uh[3] = {(unsigned)h.x, (unsigned)h.y, (unsigned)h.z};
 #pragma unroll
   for (int q = 0; q < 3; q++) {
     double v = le_deq(u[q], q);
-    if (di[q]) v = __dadd_rn(v, (double)di[q] * c_P.L[q]);
+    const int di = le_image_shift(uh[q], u[q]);
+    if (di) v = __dadd_rn(v, (double)di * c_P.L[q]);
     x[q] = v;
   }
+  return true;
 }
 // image of bond partner p closest to atom t at the last rebuild, as shifts -1/0/+1 per dimension packed 2 bits
 // each (+1 bias; 21 = same image): Domain::closest_image picks a ghost exactly when a shift is non-zero, and then
-// the reference's bondlist holds the bond twice (src/ntopo_bond_all.cpp:65-66)
+// the reference's bondlist holds the bond twice (src/ntopo_bond_all.cpp:65-66).  0 = partner not on this GPU.
 __device__ __forceinline__ int bond_cross_code(const Dev &d, int t, int p) {
-  const int4 a = d.pos_hold[d.map[t - 1]], b = d.pos_hold[d.map[p - 1]];
+  const int kt = d.map[t - 1], kp = d.map[p - 1];
+  if (kt < 0 || kp < 0) { le_raise(d.ctrl, LE_DERR_MISSING_ATOM, t, p, 2); return 0; }
+  const int4 a = d.pos_hold[kt], b = d.pos_hold[kp];
   const int h0 = le_image_shift((unsigned)a.x, (unsigned)b.x);
   const int h1 = le_image_shift((unsigned)a.y, (unsigned)b.y);
   const int h2 = le_image_shift((unsigned)a.z, (unsigned)b.z);
@@ -315,8 +321,45 @@ __device__ __forceinline__ double dist2(const double a[3], const double b[3]) {
   const double dx = __dsub_rn(a[0], b[0]), dy = __dsub_rn(a[1], b[1]), dz = __dsub_rn(a[2], b[2]);
   return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
-__device__ __forceinline__ int type_of(const LeView &V, int tag) {
-  return (V.d.pos[V.cur()][V.d.map[tag - 1]].w & 7) + 1;
+__device__ __forceinline__ int type_of(const LeView &V, int tag) { return V.d.type_tag[tag - 1]; }
+
+// ------------------------------------------------------------------------------------------------
+// position-dependent inputs of an event ("geometry records").  The decision logic of the three fixes is
+// replicated: every GPU runs it on the whole (small) set of extruders with identical inputs, so the
+// result is independent of the decomposition and bit-identical to the 1-rank reference.  What a GPU
+// cannot do alone is measure distances between beads it does not hold; so the owner of a bead computes
+// the few distances / image codes its extruder needs and stores them, by tag, into EVERY GPU's record
+// arrays (peer stores over NVLink), stamped with the event number.  One flag round (k_le_exchange)
+// later all GPUs hold all records.
+//   geo_i[t][0]  extrusion: bond_cross_code of t's extruder bond | unload: partner tag | load: eligibility flag
+//   geo_i[t][1]  stamp (Ctrl::le_epoch of the event that wrote the record; anything else = no record)
+//   geo[t][0..2] extrusion (t = lower end a): |L-R|^2, |L-b|^2, |a-R|^2 | load: |lo-hi|^2 in [0]
+// ------------------------------------------------------------------------------------------------
+__global__ void k_le_begin(Dev d) { d.ctrl->le_epoch++; }
+
+__device__ __forceinline__ void geo_store(const Dev &d, int i, int v0, int stamp, int nd, const double *r) {
+  for (int p = 0; p < d.nranks; p++) {
+    const PeerView &pv = d.peer[p];
+    for (int q = 0; q < nd; q++) pv.geo[(size_t)i * LE_GEO_D + q] = r[q];
+    pv.geo_i[(size_t)i * LE_GEO_I] = v0;
+    pv.geo_i[(size_t)i * LE_GEO_I + 1] = stamp;
+  }
+}
+__device__ __forceinline__ bool geo_fresh(const LeView &V, int i) {
+  return V.f.geo_i[(size_t)i * LE_GEO_I + 1] == (int)V.d.ctrl->le_epoch;
+}
+
+// all records of this event are out: tell every peer, wait for every peer (one thread)
+__global__ void k_le_exchange(Dev d) {
+  if (d.nranks <= 1) return;
+  Ctrl *c = d.ctrl;
+  __threadfence_system();
+  const unsigned long long e = (unsigned long long)c->le_epoch;
+  const int slot = FLAG_LE + (int)(e & 1) * LE_MAXRANKS;
+  for (int p = 0; p < d.nranks; p++)
+    if (p != d.rank) st_sys(&d.peer[p].flags[slot + d.rank], e);
+  for (int p = 0; p < d.nranks; p++)
+    if (p != d.rank) le_wait_flag(c, &d.flags[slot + p], e, 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -512,6 +555,38 @@ __device__ __forceinline__ bool ext_side_base(const LeView &V, const ExtrusionAr
   return true;
 }
 
+// E0g: geometry records of the extruders anchored on atoms this GPU owns
+__global__ void k_ext_geo(LeView V, ExtrusionArgs A) {
+  const Dev &d = V.d;
+  const int lo = d.own0, hi = d.own0 + d.ctrl->nown, stamp = (int)d.ctrl->le_epoch;
+  const int4 *__restrict__ pos = d.pos[V.cur()];
+  for (int k = lo + blockIdx.x * blockDim.x + threadIdx.x; k < hi; k += gridDim.x * blockDim.x) {
+    const int i = (pos[k].w >> 3) - 1;
+    const int nb = d.num_bond[i];
+    for (int m = 0; m < nb; m++) {
+      if (d.bond_type[(size_t)i * d.bpa + m] != A.btype) continue;
+      const int p = d.bond_atom[(size_t)i * d.bpa + m];
+      const int code = bond_cross_code(d, i + 1, p);
+      double r[3] = {0.0, 0.0, 0.0};
+      int nd = 0;
+      if (i + 1 < p) {                 // the lower end measures the three candidate bonds (fix_extrusion.cpp:431-434,451-454,492-495)
+        const int a = i + 1, b = p, L = a - 1, R = b + 1;
+        double xa[3], xb[3], xl[3], xr[3];
+        const bool hl = L >= 1, hr = R <= d.N;
+        raw_xyz(V, a, xa); raw_xyz(V, b, xb);
+        if (hl) raw_xyz(V, L, xl);
+        if (hr) raw_xyz(V, R, xr);
+        if (hl && hr) r[0] = dist2(xl, xr);
+        if (hl) r[1] = dist2(xl, xb);
+        if (hr) r[2] = dist2(xa, xr);
+        nd = 3;
+      }
+      geo_store(d, i, code, stamp, nd, r);
+      break;                           // bondcount <= 1 (checked by k_ext_init)
+    }
+  }
+}
+
 // E0b: which atoms own a bondlist visit of an extruder, and how many draws that visit consumes
 __global__ void k_ext_visits(LeView V, ExtrusionArgs A) {
   const Dev &d = V.d; const LeFixDev &f = V.f;
@@ -522,7 +597,8 @@ __global__ void k_ext_visits(LeView V, ExtrusionArgs A) {
       if (d.bond_type[(size_t)i * d.bpa + m] != A.btype) continue;
       const int p = d.bond_atom[(size_t)i * d.bpa + m];
       // NTopoBondAll::build, newton_bond off: listed from atom i iff i < closest image of p
-      if (!((i + 1) < p || bond_cross_code(d, i + 1, p) != 21)) continue;
+      if (!geo_fresh(V, i)) { le_raise(d.ctrl, LE_DERR_MISSING_ATOM, i + 1, p, 3); continue; }
+      if (!((i + 1) < p || f.geo_i[(size_t)i * LE_GEO_I] != 21)) continue;
       const int a = min(i + 1, p), b = max(i + 1, p);
       const int nba = d.num_bond[a - 1], nbb = d.num_bond[b - 1];
       if (nba == 1 || nbb == 1 || nba == 0 || nbb == 0 || f.bondcount[a - 1] != 1 || f.bondcount[b - 1] != 1) continue;
@@ -565,24 +641,21 @@ struct VisitTask {
     if (okL && n1) okL = A.p > f.draws[off++];
     bool okR = ext_side_base(V, A, R, A.right, n2);
     if (okR && n2) okR = A.p > f.draws[off++];
-    double xa[3], xb[3];
+    const double *g = f.geo + (size_t)(a - 1) * LE_GEO_D;     // measured by the owner of a (k_ext_geo)
     if (okL && okR) {
-      raw_xyz(V, L, xa); raw_xyz(V, R, xb);
-      const double rsq = dist2(xa, xb);
+      const double rsq = g[0];
       if (rsq >= f.distsq[L - 1] && rsq >= f.distsq[R - 1]) return;
       if (rsq < f.distsq[L - 1]) { f.distsq[L - 1] = rsq; f.to_add[L - 1] = R; }
       if (rsq < f.distsq[R - 1]) { f.distsq[R - 1] = rsq; f.to_add[R - 1] = L; }
       f.to_remove[a - 1] = b; f.to_remove[b - 1] = a;
     } else if (okL) {
-      raw_xyz(V, L, xa); raw_xyz(V, b, xb);
-      const double rsq = dist2(xa, xb);
+      const double rsq = g[1];
       if (rsq >= f.distsq[L - 1]) return;
       f.distsq[L - 1] = rsq; f.to_add[L - 1] = b;
       if (f.distsq[b - 1] == LE_BIG) { f.distsq[b - 1] = rsq; f.to_add[b - 1] = L; }
       f.to_remove[a - 1] = b; f.to_remove[b - 1] = a;
     } else if (okR) {
-      raw_xyz(V, a, xa); raw_xyz(V, R, xb);
-      const double rsq = dist2(xa, xb);
+      const double rsq = g[2];
       if (rsq >= f.distsq[R - 1]) return;
       if (f.distsq[a - 1] == LE_BIG) { f.distsq[a - 1] = rsq; f.to_add[a - 1] = R; }
       f.distsq[R - 1] = rsq; f.to_add[R - 1] = a;
@@ -728,10 +801,14 @@ __global__ void k_le_finish(Dev d, LeFixDev f, int which) {
 // ------------------------------------------------------------------------------------------------
 // candidate pass: every extruder bond longer than the cutoff makes its two atoms each other's partner.
 // The distance is the one the bondlist visit computes: owned-owned for a bond inside the box, owned-ghost
-// (partner shifted by the image found at the last rebuild) for one straddling the boundary.
-__global__ void k_unl_candidates(LeView V, UnloadArgs A) {
-  const Dev &d = V.d; const LeFixDev &f = V.f;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) {
+// (partner shifted by the image found at the last rebuild) for one straddling the boundary.  Measured by the
+// owner of each atom (k_unl_geo), collected by tag on every GPU (k_unl_candidates).
+__global__ void k_unl_geo(LeView V, UnloadArgs A) {
+  const Dev &d = V.d;
+  const int lo = d.own0, hi = d.own0 + d.ctrl->nown, stamp = (int)d.ctrl->le_epoch;
+  const int4 *__restrict__ pos = d.pos[V.cur()];
+  for (int k = lo + blockIdx.x * blockDim.x + threadIdx.x; k < hi; k += gridDim.x * blockDim.x) {
+    const int i = (pos[k].w >> 3) - 1;
     int partner = 0; double best = 0.0;
     const int nb = d.num_bond[i];
     for (int m = 0; m < nb; m++) {
@@ -753,6 +830,14 @@ __global__ void k_unl_candidates(LeView V, UnloadArgs A) {
       if (rsq <= A.cutsq) continue;
       if (rsq > best) { best = rsq; partner = p; }
     }
+    if (partner) geo_store(d, i, partner, stamp, 0, nullptr);
+  }
+}
+
+__global__ void k_unl_candidates(LeView V, UnloadArgs A) {
+  const Dev &d = V.d; const LeFixDev &f = V.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) {
+    const int partner = geo_fresh(V, i) ? f.geo_i[(size_t)i * LE_GEO_I] : 0;
     f.partner[i] = partner;
     f.final_remove[i] = 0; f.final_add[i] = 0;
     f.flag[i] = partner != 0;
@@ -806,11 +891,17 @@ __global__ void k_load_init(LeView V, int btype) {
 // le_pair_stored_on_i says so.  If the stored neighbor is a periodic ghost the reference reads the ghost's
 // num_bond, which is never communicated (src/MOLECULE/atom_vec_bond.cpp:41) and is 0: never eligible.
 // flag[i] = 0 not eligible, 1 eligible and stored on the upper tag, 2 eligible and stored on the lower tag.
-__global__ void k_load_eligible(LeView V, LoadArgs A) {
+// Measured for the pair (lo, lo+2) by the GPU that owns lo (k_load_geo); a partner outside its halo is farther
+// away than any list cutoff.  Collected by tag on every GPU (k_load_eligible).
+__global__ void k_load_geo(LeView V, LoadArgs A) {
   const Dev &d = V.d; const LeFixDev &f = V.f;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) {
+  const int own_lo = d.own0, own_hi = d.own0 + d.ctrl->nown, stamp = (int)d.ctrl->le_epoch;
+  const int4 *__restrict__ pos = d.pos[V.cur()];
+  for (int k = own_lo + blockIdx.x * blockDim.x + threadIdx.x; k < own_hi; k += gridDim.x * blockDim.x) {
+    const int i = (pos[k].w >> 3) - 1;
     int ok = 0;
-    if (i + 2 < d.N) {
+    double rsq_out = 0.0;
+    if (i + 2 < d.N && d.map[i + 2] >= 0) {
       const int lo = i + 1, hi = i + 3, mid = i + 2;
       if (d.num_bond[lo - 1] == 2 && d.num_bond[hi - 1] == 2 && d.num_bond[mid - 1] == 2) {
         const int4 plo = d.pos_hold[d.map[lo - 1]], phi = d.pos_hold[d.map[hi - 1]];
@@ -838,13 +929,22 @@ __global__ void k_load_eligible(LeView V, LoadArgs A) {
               double xi[3], xj[3];
               raw_xyz(V, ti, xi); raw_xyz(V, tj, xj);
               const double rsq = dist2(xi, xj);
-              if (rsq < A.cutsq) { ok = on_lo ? 2 : 1; f.prob[i] = rsq; }
+              if (rsq < A.cutsq) { ok = on_lo ? 2 : 1; rsq_out = rsq; }
             }
           }
         }
       }
     }
-    f.flag[i] = ok;
+    if (ok) geo_store(d, i, ok, stamp, 1, &rsq_out);
+  }
+}
+
+__global__ void k_load_eligible(LeView V) {
+  const Dev &d = V.d; const LeFixDev &f = V.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) {
+    const bool fresh = geo_fresh(V, i);
+    f.flag[i] = fresh ? f.geo_i[(size_t)i * LE_GEO_I] : 0;
+    if (fresh) f.prob[i] = f.geo[(size_t)i * LE_GEO_D];
     f.done[i] = 0;
   }
 }
@@ -910,11 +1010,17 @@ __global__ void k_load_create(LeView V, LoadArgs A) {
     special_insert12(d, ti, p);
     const int bc = f.bondcount[i] + 1;
     f.bondcount[i] = bc;
-    const int k = d.map[i];
-    int4 *pp = &d.pos[V.cur()][k];
-    const int ty = (pp->w & 7) + 1;
-    if (ty == A.itype) { if (bc == A.imax) { pp->w = (pp->w & ~7) | (A.inew - 1); d.type_tag[i] = A.inew; } }
-    else { if (bc == A.jmax) { pp->w = (pp->w & ~7) | (A.jnew - 1); d.type_tag[i] = A.jnew; } }
+    // type[i] = inewtype / jnewtype (fix_ex_load.cpp:594-598): the replicated table, and the copy of the atom this
+    // GPU holds (owned or ghost); the forced rebuild that follows refreshes pos_hold from it
+    const int ty = d.type_tag[i];
+    int nty = ty;
+    if (ty == A.itype) { if (bc == A.imax) nty = A.inew; }
+    else { if (bc == A.jmax) nty = A.jnew; }
+    if (nty != ty) {
+      d.type_tag[i] = nty;
+      const int k = d.map[i];
+      if (k >= 0) { int4 *pp = &d.pos[V.cur()][k]; pp->w = (pp->w & ~7) | (nty - 1); }
+    }
     f.final_add[i] = p; f.final_add[p - 1] = ti;
     if (ti < p) atomicAdd(&f.counters[CNT_NCREATE], 1);
   }

@@ -116,7 +116,11 @@ static int enqueue_extrusion(le_ctx *c) {
   LeView V{c->d, f};
   ExtrusionArgs A{c->fx.btype, c->fx.neutral, c->fx.left, c->fx.right, c->fx.roadblock, c->fx.p};
   const int g = grid_for(c->N, 256);
+  const int go = grid_for(c->d.gr0 - c->d.own0, 256);
+  LAUNCH(c, k_le_begin, 1, 1, c->d);
   LAUNCH(c, k_ext_init, g, 256, V, A.btype);
+  LAUNCH(c, k_ext_geo, go, 256, V, A);
+  LAUNCH(c, k_le_exchange, 1, 1, c->d);
   LAUNCH(c, k_ext_visits, g, 256, V, A);
   compact_tasks(c);
   iscan(c, f.ndraw, f.scan2, c->N, f.counters + CNT_NDRAW);
@@ -142,6 +146,9 @@ static int enqueue_unload(le_ctx *c) {
   LeView V{c->d, f};
   UnloadArgs A{c->fu.btype, c->fu.rc * c->fu.rc, c->fu.prob};
   const int g = grid_for(c->N, 256);
+  LAUNCH(c, k_le_begin, 1, 1, c->d);
+  LAUNCH(c, k_unl_geo, grid_for(c->d.gr0 - c->d.own0, 256), 256, V, A);
+  LAUNCH(c, k_le_exchange, 1, 1, c->d);
   LAUNCH(c, k_unl_candidates, g, 256, V, A);
   if (A.fraction < 1.0) draw_for_flagged(c, 1, A.fraction);
   LAUNCH(c, k_unl_break, g, 256, V, A);
@@ -162,8 +169,11 @@ static int enqueue_load(le_ctx *c) {
   LeView V{c->d, f};
   LoadArgs A{c->fl.btype, c->fl.itype, c->fl.jtype, c->fl.imax, c->fl.inew, c->fl.jmax, c->fl.jnew, c->fl.rc * c->fl.rc, c->fl.prob};
   const int g = grid_for(c->N, 256);
+  LAUNCH(c, k_le_begin, 1, 1, c->d);
   LAUNCH(c, k_load_init, g, 256, V, A.btype);
-  LAUNCH(c, k_load_eligible, g, 256, V, A);
+  LAUNCH(c, k_load_geo, grid_for(c->d.gr0 - c->d.own0, 256), 256, V, A);
+  LAUNCH(c, k_le_exchange, 1, 1, c->d);
+  LAUNCH(c, k_load_eligible, g, 256, V);
   LAUNCH(c, k_load_scan_runs, g, 256, V);
   LAUNCH(c, k_load_flag_partners, g, 256, f, c->N);
   if (A.fraction < 1.0) draw_for_flagged(c, 2, A.fraction);

@@ -69,6 +69,27 @@ if rank == 0:
     report("thermo after %d steps" % steps, abs(th["temp"] - th2["temp"]) < 0.02 and abs(th["emol"] - th2["emol"]) < 0.05 and abs(th["epair"] - th2["epair"]) < 0.01,
            "T %.4f/%.4f epair %.4f/%.4f emol %.4f/%.4f builds %d/%d" % (th["temp"], th2["temp"], th["epair"], th2["epair"], th["emol"], th2["emol"], st["neigh_builds"], st2["neigh_builds"]))
     print("dd: %.4f ms/step (GPU events, rank 0) over %d ranks; single GPU %.4f ms/step" % (st["last_run_gpu_ms"] / steps, world, st2["last_run_gpu_ms"] / steps), flush=True)
+# USER-LE events on the decomposed system: the decision logic is replicated, the geometry comes from the owners
+for e in (dd, ref):
+    if e is None: continue
+    e.fix_extrusion(200, 1, 2, 3, 0.5, 2, 4, 12345)
+    e.fix_ex_load(100, 1, 1, 1.12, 2, 0.02, 684474, (1, 1), (1, 1))
+    e.fix_ex_unload(100, 2, 0.5, 0.05, 456456)
+    e.reset_timestep(0)
+le_steps = 650
+dd.run(le_steps)
+st = dd.stats(); topo = dd.topology(); ty = dd.types(); x, im = dd.positions()
+if rank == 0:
+    ref.run(le_steps)
+    st2 = ref.stats(); topo2 = ref.topology(); ty2 = ref.types(); x2, im2 = ref.positions()
+    res = H.compare_topology(topo, topo2)
+    report("USER-LE topology after %d steps" % le_steps, not any(res.values()) and (ty == ty2).all(),
+           "shifts %d/%d loads %d/%d unloads %d/%d %s" % (st["extrusion_shifts"], st2["extrusion_shifts"], st["loads"], st2["loads"],
+                                                        st["unloads"], st2["unloads"], {k: v for k, v in res.items() if v}))
+    L = s["box"][1][0]
+    dx = np.abs(((x - x2) + L / 2) % L - L / 2).max()
+    report("positions after the LE run", dx < 1e-3, "max |dx| %.2e" % dx)
+    print("dd with LE: %.4f ms/step; single GPU %.4f ms/step" % (st["last_run_gpu_ms"] / le_steps, st2["last_run_gpu_ms"] / le_steps), flush=True)
 dd.barrier()
 if rank == 0:
     print("DD CHECK", "PASSED" if ok else "FAILED", flush=True)
