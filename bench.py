@@ -101,11 +101,14 @@ REF_LE_LINES = ["fix loop all extrusion 500 1 2 3 0.5 2 4",
                 "fix unloading all ex_unload 100 2 0.5 prob 0.05 456456"]
 
 
-def prepared_engine(n_beads, n_ext, seed, device, relax_steps):
+LE_HALO = 6.2   # ghost shell for USER-LE on several GPUs: longest extruder bond (FENE R0 = 4) + one backbone bond + skin
+
+
+def prepared_engine(n_beads, n_ext, seed, device, relax_steps, dd=None):
     from lammps_le_b200 import systems
     s = build_system(n_beads, n_ext, seed)
     v = systems.maxwell_velocities(n_beads, 1.0, np.ones(n_beads), seed)
-    e = systems.make_engine(s, device=device, velocities=v, dt=0.005)
+    e = systems.make_engine(s, device=device, velocities=v, dt=0.005, dd=dd)
     systems.relax(e, steps=relax_steps)
     e.fix_langevin(1.0, 1.0, 1.0, 904297)
     le_fixes(e)
@@ -149,12 +152,9 @@ def reference_rate(s, x, image, v, topo, md_steps_per_seg, nseg_warm, nseg_timed
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from lammps_le_b200.engine import Engine
+    from lammps_le_b200.engine_dd import init_process_group
+    rank, world, local, group = init_process_group()
     torch.cuda.set_device(local)
 
     def barrier():
@@ -163,8 +163,10 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     n_beads, n_ext, md = args.beads, args.extruders, args.md_steps
-    # independent objects: every rank owns its own chain(s) (weak scaling, no data-path collective)
-    s, e = prepared_engine(n_beads, n_ext, 12345 + rank, local, args.relax)
+    # weak scaling: ONE system of world x n_beads beads (world x n_ext extruders), cut into x-slabs, one per GPU;
+    # halo positions travel as peer stores from the integrator, atoms migrate at every reneighboring
+    dd = dict(rank=rank, world=world, halo=LE_HALO, group=group) if world > 1 else None
+    s, e = prepared_engine(n_beads * world, n_ext * world, 12345, local, args.relax, dd)
     for _ in range(args.warmup):
         e.run(md)
     st0 = e.stats()
@@ -173,10 +175,12 @@ def run_ours(args):
         sampler.start()
     barrier()
     t0 = time.perf_counter()
-    gpu_ms = 0.0
+    gpu_ms = le_ms = 0.0
     for _ in range(args.steps):
         e.run(md)
-        gpu_ms += e.stats()["last_run_gpu_ms"]
+        sk = Engine.stats(e)
+        gpu_ms += sk["last_run_gpu_ms"]
+        le_ms += sk["last_run_le_ms"]
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
@@ -188,9 +192,9 @@ def run_ours(args):
     total_atom_steps = world * n_beads * md * args.steps
     value = total_atom_steps / t_gpu
 
-    # ---- end to end through the C ABI with host buffers ----
-    x, im = e.positions()
-    v = e.velocities()
+    # ---- end to end through the C ABI with host buffers (several GPUs: every rank moves the atoms it owns) ----
+    x, im = Engine.positions(e)
+    v = Engine.velocities(e)
     xp = torch.from_numpy(x).pin_memory().numpy()
     vp = torch.from_numpy(v).pin_memory().numpy()
     barrier()
@@ -199,9 +203,9 @@ def run_ours(args):
         e.set_positions(xp, im)
         e.set_velocities(vp)
         e.run(md)
-        xo, im = e.positions()
+        xo, im = Engine.positions(e)
         xp[:] = xo
-        vp[:] = e.velocities()
+        vp[:] = Engine.velocities(e)
     barrier()
     t_e2e = time.perf_counter() - t0
     te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
@@ -212,20 +216,22 @@ def run_ours(args):
     d2h = n_beads * (24 + 24 + 4)
 
     if rank != 0:
+        if world > 1:
+            dist.barrier()
         e.close()
         if world > 1:
             dist.destroy_process_group()
         return
     # ---- roofline of the dominant kernel ----
-    nbar_full = st1["full_entries"] / n_beads
-    nbar_half = st1["half_pairs"] / n_beads
+    nbar_full = st1["full_entries"] / (n_beads * world)
+    nbar_half = st1["half_pairs"] / (n_beads * world)
     builds = st1["neigh_builds"] - st0["neigh_builds"]
     steps_timed = md * args.steps
     kint = steps_timed / max(builds, 1)
     bytes_step = 72.1 + 4.0 * nbar_half                      # SURVEY.md 8(d) algorithmic bytes per atom-step
     bytes_amort = bytes_step + (40.0 + 4.0 * nbar_half) / kint
     peak, how = measured_peak_gbs()
-    achieved = bytes_amort * n_beads * steps_timed / t_gpu / 1e9
+    achieved = bytes_amort * n_beads * steps_timed / t_gpu / 1e9          # per GPU
     line = {
         "metric": "atom-steps/s", "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_gpu / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -234,14 +240,16 @@ def run_ours(args):
                    "beads_per_gpu": n_beads, "md_steps_per_step": md, "nbar_half": nbar_half, "nbar_full": nbar_full,
                    "steps_per_rebuild": kint, "l2_note": "working set (%.0f MB per GPU) vs 126 MB L2: inputs %s L2" % (
                        n_beads * (32 + 16 + 16 + 4 * nbar_full + 12 + 4) / 1e6, "exceed" if n_beads >= 1000000 else "fit in"),
-                   "parallelism": "independent chains per GPU" if world > 1 else "single GPU"},
+                   "parallelism": ("one %d-bead system in %d x-slabs (one per GPU): halo stores over NVLink peer memory fused into "
+                                   "the integrator, flag hand-shakes, migration at every rebuild, replicated USER-LE logic" % (n_beads * world, world))
+                   if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": "atom-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": how, "bytes_per_atom_step": bytes_amort,
                      "kernel": "k_step<0> (+ amortised rebuild kernels)"},
-        "wall_s": t_wall,
+        "wall_s": t_wall, "user_le_ms_per_md_step": le_ms / steps_timed,
         "le_events": {"shifts": st1["extrusion_shifts"] - st0["extrusion_shifts"], "loads": st1["loads"] - st0["loads"],
                       "unloads": st1["unloads"] - st0["unloads"]},
     }
@@ -262,8 +270,10 @@ def run_ours(args):
                                         "sample": "oracle/_ref missing on this box"}
         except Exception as ex:  # the baseline must never take the bench line down
             line["cpu_baseline"] = {"value": None, "unit": "atom-steps/s", "cores": 0, "kind": "reference", "sample": "failed: %s" % str(ex)[:200]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
     e.close()
-    print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

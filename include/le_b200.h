@@ -73,6 +73,7 @@ typedef struct le_stats {
   int64_t extrusion_shifts, loads, unloads;         /* cumulative event counters */
   int64_t last_extrusion_shifts, last_loads, last_unloads; /* f_ID[1] of the three fixes */
   double last_run_gpu_ms;   /* CUDA-event time of the last le_run's step loop */
+  double last_run_le_ms;    /* ... of which inside the USER-LE fixes (post_integrate) */
 } le_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------- */

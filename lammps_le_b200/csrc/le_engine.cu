@@ -74,6 +74,9 @@ struct le_ctx {
   int64_t nbonds;
   le_stats stats;
   cudaEvent_t ev0, ev1;
+  bool timing; std::vector<cudaEvent_t> tm_ev; std::vector<const char *> tm_name; size_t tm_used;
+  std::vector<cudaEvent_t> le_ev;       // pairs of events around the USER-LE kernels of the current run
+  size_t le_ev_used;
   double *h_thermo;     // pinned
   Ctrl *h_ctrl;         // pinned
   // captured step graphs (built lazily, rebuilt when anything baked into them changes)
@@ -94,6 +97,36 @@ struct le_ctx {
   std::vector<std::vector<double>> thermo_sums;   // raw per-GPU tallies behind c->thermo (summed over ranks by the caller)
 };
 
+// LE_B200_TIMING=1 (with LE_B200_DIRECT=1): an event before every direct launch; le_run prints the time between
+// consecutive marks summed by kernel name (development aid for multi-GPU runs, where ncu cannot be used)
+static void time_mark(le_ctx *c, const char *name) {
+  cudaEvent_t e;
+  if (c->tm_used < c->tm_ev.size()) e = c->tm_ev[c->tm_used];
+  else { cudaEventCreate(&e); c->tm_ev.push_back(e); }
+  c->tm_used++;
+  c->tm_name.push_back(name);
+  cudaEventRecord(e, c->stream);
+}
+static void time_report(le_ctx *c) {
+  if (!c->timing || c->tm_used < 2) { c->tm_used = 0; c->tm_name.clear(); return; }
+  time_mark(c, "(end)");
+  cudaStreamSynchronize(c->stream);
+  std::vector<std::pair<std::string, std::pair<double, int>>> acc;
+  for (size_t k = 0; k + 1 < c->tm_used; k++) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->tm_ev[k], c->tm_ev[k + 1]);
+    size_t q = 0;
+    for (; q < acc.size(); q++) if (acc[q].first == c->tm_name[k]) break;
+    if (q == acc.size()) acc.push_back({c->tm_name[k], {0.0, 0}});
+    acc[q].second.first += ms; acc[q].second.second++;
+  }
+  std::sort(acc.begin(), acc.end(), [](const auto &a, const auto &b) { return a.second.first > b.second.first; });
+  double tot = 0; for (auto &a : acc) tot += a.second.first;
+  fprintf(stderr, "[le_b200 timing rank %d] %.3f ms between marks\n", c->rank, tot);
+  for (auto &a : acc) fprintf(stderr, "  %-28s n=%6d  %9.3f ms  %5.1f%%  %8.2f us each\n", a.first.c_str(), a.second.second, a.second.first, 100.0 * a.second.first / tot, 1e3 * a.second.first / a.second.second);
+  c->tm_used = 0; c->tm_name.clear();
+}
+
 static int fail(le_ctx *c, int code, const char *fmt, ...) {
   char buf[512];
   va_list ap;
@@ -113,6 +146,7 @@ static int fail(le_ctx *c, int code, const char *fmt, ...) {
 
 #define LAUNCH(c, kern, grid, block, ...)                      \
   do {                                                         \
+    if ((c)->timing && !(c)->capturing) time_mark(c, #kern);   \
     kern<<<(grid), (block), 0, (c)->stream>>>(__VA_ARGS__);    \
     if (!(c)->capturing) (c)->direct_launches++;               \
   } while (0)
@@ -150,6 +184,8 @@ extern "C" int le_create(le_ctx **out, int device, const double boxlo[3], const 
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return LE_ENOGPU; }
   cudaEventCreate(&c->ev0);
   cudaEventCreate(&c->ev1);
+  c->le_ev_used = 0;
+  { const char *tm = getenv("LE_B200_TIMING"); c->timing = tm && tm[0] == '1'; c->tm_used = 0; }
   for (int k = 0; k < 3; k++) {
     c->lo[k] = boxlo[k]; c->hi[k] = boxhi[k]; c->periodic[k] = periodic[k];
   }
@@ -213,6 +249,7 @@ extern "C" void le_destroy(le_ctx *c) {
   for (void *p : c->allocs) cudaFree(p);
   cudaFreeHost(c->h_thermo);
   cudaFreeHost(c->h_ctrl);
+  for (cudaEvent_t e : c->le_ev) cudaEventDestroy(e);
   cudaEventDestroy(c->ev0);
   cudaEventDestroy(c->ev1);
   cudaStreamDestroy(c->stream);
@@ -930,8 +967,6 @@ static void enqueue_rebuild(le_ctx *c, bool direct) {
   const int nslots = d.gr0 - d.own0;                       // capacity of the owned region
   const int ncell_own = (d.nlx - 2 * d.halo) * d.ncell[1] * d.ncell[2];
   const bool dd = c->nranks > 1;
-  LAUNCH(c, k_rb_begin, 1, 1, d, c->rb);
-  if (dd) LAUNCH(c, k_clear_ghost_map, grid_for(2 * d.own0, 256), 256, d);
   LAUNCH(c, k_cell_count, grid_for(nslots, 256), 256, d, c->rb);
   if (dd) {
     LAUNCH(c, k_rb_post_inbox, 1, 1, d, c->rb);
@@ -952,7 +987,7 @@ static void enqueue_rebuild(le_ctx *c, bool direct) {
   if (direct) { LAUNCH(c, k_after_build, 1, 1, d); c->direct_builds++; }
 }
 
-static int rebuild_kernel_count(const le_ctx *c) { return c->nranks > 1 ? 15 : 9; }
+static int rebuild_kernel_count(const le_ctx *c) { return c->nranks > 1 ? 13 : 8; }
 
 #define CKG(call)                                                                             \
   do {                                                                                        \
@@ -1141,6 +1176,12 @@ extern "C" int le_compute_forces(le_ctx *c, double *f, le_thermo *out) {
 
 #include "le_fix_host.inl"
 
+// event pair around the USER-LE kernels of one timestep (resolved at the end of le_run into stats.last_run_le_ms)
+static void le_mark(le_ctx *c) {
+  if (c->le_ev_used == c->le_ev.size()) { cudaEvent_t e; cudaEventCreate(&e); c->le_ev.push_back(e); }
+  cudaEventRecord(c->le_ev[c->le_ev_used++], c->stream);
+}
+
 // does any USER-LE fix fire in Modify::post_integrate of timestep `step`?
 static bool le_event_at(const le_ctx *c, int64_t step) {
   if (c->fx.on && (step % c->fx.nevery - 1) == 0) return true;
@@ -1193,6 +1234,7 @@ extern "C" int le_run(le_ctx *c, int64_t nsteps) {
   // Verlet::setup: full rebuild, then forces at the current positions
   enqueue_rebuild(c, true);
   c->lists_valid = true;
+  c->le_ev_used = 0;
   CK(cudaEventRecord(c->ev0, c->stream));
   if ((r = force_eval(begin))) return r;
   int64_t s = begin;
@@ -1205,7 +1247,7 @@ extern "C" int le_run(le_ctx *c, int64_t nsteps) {
       const int64_t next = s + 1;
       c->cur ^= 1;
       LAUNCH(c, k_advance, 1, 1, d);
-      if (le_event_at(c, next)) { r = enqueue_le_events(c, next); if (r) return r; }
+      if (le_event_at(c, next)) { le_mark(c); r = enqueue_le_events(c, next); if (r) return r; le_mark(c); }
       LAUNCH(c, k_decide, 1, 1, d, (cudaGraphConditionalHandle)0, 0, 0);
       CK(cudaMemcpyAsync(c->h_ctrl, d.ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
@@ -1230,7 +1272,9 @@ extern "C" int le_run(le_ctx *c, int64_t nsteps) {
     if (le_event_at(c, next)) {
       // Modify::post_integrate of the new step: the USER-LE fixes, in definition order, before Neighbor::decide
       LAUNCH(c, k_advance, 1, 1, d);
+      le_mark(c);
       r = enqueue_le_events(c, next); if (r) return r;
+      le_mark(c);
       CK(cudaGraphLaunch(c->x_tail[0], c->stream));
     } else {
       CK(cudaGraphLaunch(c->x_tail[1], c->stream));
@@ -1247,6 +1291,11 @@ extern "C" int le_run(le_ctx *c, int64_t nsteps) {
   float ms = 0.f;
   cudaEventElapsedTime(&ms, c->ev0, c->ev1);
   c->stats.last_run_gpu_ms = ms;
+  double le_ms = 0.0;
+  for (size_t k = 0; k + 1 < c->le_ev_used; k += 2) { float t = 0.f; cudaEventElapsedTime(&t, c->le_ev[k], c->le_ev[k + 1]); le_ms += t; }
+  c->stats.last_run_le_ms = le_ms;
+  c->le_ev_used = 0;
+  time_report(c);
   return LE_OK;
 }
 

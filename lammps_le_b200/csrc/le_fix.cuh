@@ -36,7 +36,8 @@ struct LeFixDev {
   int N;
   int *bondcount, *to_add, *to_remove, *final_add, *final_remove, *partner;
   double *distsq, *prob;
-  unsigned *claim;
+  unsigned long long *claim;   // ordered executor: (~round << 32) | priority of the best claimant of a bead
+  int *exec_rem;               // [LE_EXEC_ROUNDS + 1] "tasks were left over after round r"
   int *flag, *scan, *scan2, *ndraw, *tasks, *blocksum;
   unsigned char *done;
   int *counters;        // [16] device counters
@@ -70,7 +71,7 @@ static int le_fix_alloc(LeFixDev &f, int n, int maxspecial, std::vector<void *> 
   r |= A((void **)&f.bondcount, n1 * 4); r |= A((void **)&f.to_add, n1 * 4); r |= A((void **)&f.to_remove, n1 * 4);
   r |= A((void **)&f.final_add, n1 * 4); r |= A((void **)&f.final_remove, n1 * 4); r |= A((void **)&f.partner, n1 * 4);
   r |= A((void **)&f.distsq, n1 * 8); r |= A((void **)&f.prob, n1 * 8);
-  r |= A((void **)&f.claim, n1 * 4); r |= A((void **)&f.flag, n1 * 4); r |= A((void **)&f.scan, n1 * 4);
+  r |= A((void **)&f.claim, n1 * 8); r |= A((void **)&f.exec_rem, 64 * 4); r |= A((void **)&f.flag, n1 * 4); r |= A((void **)&f.scan, n1 * 4);
   r |= A((void **)&f.scan2, n1 * 4); r |= A((void **)&f.ndraw, n1 * 4);
   r |= A((void **)&f.tasks, n1 * 4); r |= A((void **)&f.blocksum, (n1 / 1024 + 2) * 4);
   r |= A((void **)&f.done, n1);
@@ -360,6 +361,7 @@ __global__ void k_le_exchange(Dev d) {
     if (p != d.rank) st_sys(&d.peer[p].flags[slot + d.rank], e);
   for (int p = 0; p < d.nranks; p++)
     if (p != d.rank) le_wait_flag(c, &d.flags[slot + p], e, 0);
+  __threadfence_system();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -367,40 +369,72 @@ __global__ void k_le_exchange(Dev d) {
 //   int  ntasks;  unsigned prio(int k);  int beads(int k, int b[4]) (tag-1 indices, may repeat);
 //   void exec(int k)
 // ------------------------------------------------------------------------------------------------
+// Rounds 0..LE_EXEC_ROUNDS-1 run as two grid-wide kernels each (claim, run); a claim is the 64-bit word
+// (~round << 32) | priority, so a later round's claim beats every stale one and nothing has to be reset between
+// rounds.  Whatever is still pending after the last grid round (a conflict chain longer than LE_EXEC_ROUNDS
+// extruders) is finished by one block that loops to completion.
+#define LE_EXEC_ROUNDS 6
+#define LE_EXEC_BASE_STRIDE (1u << 20)
+
+__device__ __forceinline__ unsigned long long exec_key(unsigned round, unsigned prio) {
+  return ((unsigned long long)(0xffffffffu - round) << 32) | prio;
+}
+
 template <class Task>
-__device__ void ordered_execute(Task &T, unsigned *claim, unsigned char *done) {
+__global__ void k_exec_claim(Task T, unsigned long long *claim, unsigned char *done, const int *rem, int round, unsigned base) {
+  if (round > 0 && rem[round - 1] == 0) return;
+  const int n = T.ntasks();
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    if (round == 0) done[k] = 0;
+    else if (done[k]) continue;
+    int b[4];
+    const int nb = T.beads(k, b);
+    const unsigned long long key = exec_key(base + round, T.prio(k));
+    for (int q = 0; q < nb; q++) atomicMin(&claim[b[q]], key);
+  }
+}
+
+template <class Task>
+__global__ void k_exec_run(Task T, unsigned long long *claim, unsigned char *done, int *rem, int round, unsigned base) {
+  if (round > 0 && rem[round - 1] == 0) return;
+  const int n = T.ntasks();
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    if (done[k]) continue;
+    int b[4];
+    const int nb = T.beads(k, b);
+    const unsigned long long key = exec_key(base + round, T.prio(k));
+    bool mine = true;
+    for (int q = 0; q < nb; q++) mine = mine && (claim[b[q]] == key);
+    if (mine) { T.exec(k); done[k] = 1; }
+    else rem[round] = 1;
+  }
+}
+
+template <class Task>
+__global__ void __launch_bounds__(LE_EXEC_THREADS) k_exec_finish(Task T, unsigned long long *claim, unsigned char *done, const int *rem, unsigned base) {
+  if (rem[LE_EXEC_ROUNDS - 1] == 0) return;
   __shared__ int remaining;
   const int n = T.ntasks();
-  for (int k = threadIdx.x; k < n; k += blockDim.x) done[k] = 0;
-  __syncthreads();
-  for (int round = 0; round <= n; round++) {
+  for (unsigned round = LE_EXEC_ROUNDS; round < LE_EXEC_BASE_STRIDE; round++) {
     if (threadIdx.x == 0) remaining = 0;
     __syncthreads();
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
       if (done[k]) continue;
       int b[4];
       const int nb = T.beads(k, b);
-      const unsigned pr = T.prio(k);
-      for (int q = 0; q < nb; q++) atomicMin(&claim[b[q]], pr);
+      const unsigned long long key = exec_key(base + round, T.prio(k));
+      for (int q = 0; q < nb; q++) atomicMin(&claim[b[q]], key);
     }
     __syncthreads();
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
       if (done[k]) continue;
       int b[4];
       const int nb = T.beads(k, b);
-      const unsigned pr = T.prio(k);
+      const unsigned long long key = exec_key(base + round, T.prio(k));
       bool mine = true;
-      for (int q = 0; q < nb; q++) mine = mine && (claim[b[q]] == pr);
+      for (int q = 0; q < nb; q++) mine = mine && (claim[b[q]] == key);
       if (mine) { T.exec(k); done[k] = 1; }
       else remaining = 1;
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
-      if (done[k] == 2) continue;
-      int b[4];
-      const int nb = T.beads(k, b);
-      for (int q = 0; q < nb; q++) claim[b[q]] = 0xffffffffu;
-      if (done[k] == 1) done[k] = 2;
     }
     __syncthreads();
     if (!remaining) break;
@@ -537,7 +571,7 @@ __global__ void k_ext_init(LeView V, int btype) {
     if (bc > 1) le_raise(d.ctrl, LE_DERR_BONDCOUNT, i + 1, bc);
     f.bondcount[i] = bc;
     f.to_add[i] = 0; f.to_remove[i] = 0; f.final_add[i] = 0; f.final_remove[i] = 0;
-    f.distsq[i] = LE_BIG; f.claim[i] = 0xffffffffu; f.partner[i] = 0;
+    f.distsq[i] = LE_BIG; f.claim[i] = ~0ull; f.partner[i] = 0;
     if (i < 16) f.counters[i] = 0;
   }
 }
@@ -664,10 +698,6 @@ struct VisitTask {
   }
 };
 
-__global__ void __launch_bounds__(LE_EXEC_THREADS) k_ext_candidates(LeView V, ExtrusionArgs A, const int *ntask) {
-  VisitTask T{V, A, ntask};
-  ordered_execute(T, V.f.claim, V.f.done);
-}
 
 // flag the atoms the next sequential pass iterates over
 __global__ void k_ext_flag(LeView V, int which) {   // which 0: to_add != 0, 1: to_remove != 0
@@ -708,10 +738,6 @@ struct ReconcileTask {
     }
   }
 };
-__global__ void __launch_bounds__(LE_EXEC_THREADS) k_ext_reconcile(LeView V, const int *ntask) {
-  ReconcileTask T{V, ntask};
-  ordered_execute(T, V.f.claim, V.f.done);
-}
 
 // break loop (fix_extrusion.cpp:618-692)
 struct BreakTask {
@@ -745,10 +771,6 @@ struct BreakTask {
     }
   }
 };
-__global__ void __launch_bounds__(LE_EXEC_THREADS) k_ext_break(LeView V, const int *ntask) {
-  BreakTask T{V, ntask};
-  ordered_execute(T, V.f.claim, V.f.done);
-}
 
 // create loop (fix_extrusion.cpp:699-786); iterations are independent
 __global__ void k_ext_create(LeView V, int btype) {
@@ -879,7 +901,7 @@ __global__ void k_load_init(LeView V, int btype) {
     for (int m = 0; m < nb; m++) if (d.bond_type[(size_t)i * d.bpa + m] == btype) bc++;
     f.bondcount[i] = bc;
     f.partner[i] = 0; f.final_add[i] = 0; f.final_remove[i] = 0;
-    f.distsq[i] = LE_BIG; f.claim[i] = 0xffffffffu;
+    f.distsq[i] = LE_BIG; f.claim[i] = ~0ull;
     if (i < 16) f.counters[i] = 0;
   }
 }

@@ -110,6 +110,19 @@ static void draw_for_flagged(le_ctx *c, int idx, double fraction) {
   LAUNCH(c, k_le_assign_draws, grid_for(c->N, 256), 256, f, c->N, (const int *)f.scan, fraction);
 }
 
+// ordered executor (le_fix.cuh): LE_EXEC_ROUNDS grid-wide rounds, then one block for whatever is left
+template <class Task>
+static void run_executor(le_ctx *c, const Task &T, unsigned base) {
+  LeFixDev &f = c->lf;
+  cudaMemsetAsync(f.exec_rem, 0, 64 * sizeof(int), c->stream);
+  const int grid = std::min(grid_for(c->N, 256), 592);
+  for (int round = 0; round < LE_EXEC_ROUNDS; round++) {
+    LAUNCH(c, k_exec_claim<Task>, grid, 256, T, f.claim, f.done, (const int *)f.exec_rem, round, base);
+    LAUNCH(c, k_exec_run<Task>, grid, 256, T, f.claim, f.done, f.exec_rem, round, base);
+  }
+  LAUNCH(c, k_exec_finish<Task>, 1, LE_EXEC_THREADS, T, f.claim, f.done, (const int *)f.exec_rem, base);
+}
+
 static int enqueue_extrusion(le_ctx *c) {
   int r = ensure_rng(c, 0, c->fx.seed); if (r) return r;
   LeFixDev &f = c->lf;
@@ -125,13 +138,13 @@ static int enqueue_extrusion(le_ctx *c) {
   compact_tasks(c);
   iscan(c, f.ndraw, f.scan2, c->N, f.counters + CNT_NDRAW);
   ranmars_fill(c, 0, (const int *)(f.counters + CNT_NDRAW));
-  LAUNCH(c, k_ext_candidates, 1, LE_EXEC_THREADS, V, A, (const int *)(f.counters + CNT_NTASK));
+  run_executor(c, VisitTask{V, A, (const int *)(f.counters + CNT_NTASK)}, 0u);
   LAUNCH(c, k_ext_flag, g, 256, V, 0);
   compact_tasks(c);
-  LAUNCH(c, k_ext_reconcile, 1, LE_EXEC_THREADS, V, (const int *)(f.counters + CNT_NTASK));
+  run_executor(c, ReconcileTask{V, (const int *)(f.counters + CNT_NTASK)}, LE_EXEC_BASE_STRIDE);
   LAUNCH(c, k_ext_flag, g, 256, V, 1);
   compact_tasks(c);
-  LAUNCH(c, k_ext_break, 1, LE_EXEC_THREADS, V, (const int *)(f.counters + CNT_NTASK));
+  run_executor(c, BreakTask{V, (const int *)(f.counters + CNT_NTASK)}, 2u * LE_EXEC_BASE_STRIDE);
   LAUNCH(c, k_ext_create, g, 256, V, A.btype);
   LAUNCH(c, k_le_finish, 1, 1, c->d, f, 1);
   const int gs = grid_for(c->N, 128);

@@ -140,12 +140,16 @@ __device__ __forceinline__ void bond_term(ForceAcc &A, const Dev &d, const int4 
 // ------------------------------------------------------------------------------------------------
 // peer flags (multi-GPU): system-scope release stores / acquire loads on words in a peer's arena
 // ------------------------------------------------------------------------------------------------
+// The poster issues ONE __threadfence_system() (all its earlier stores, and -- by stream order -- those of the
+// kernels before it, are then visible system-wide) followed by relaxed flag stores to each peer; the waiter polls
+// with relaxed loads and fences once after the last flag arrived.  (A release store / acquire load per flag costs
+// a full system fence each.)
 __device__ __forceinline__ void st_sys(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long ld_sys(const unsigned long long *p) {
   unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 #define LE_PEER_TIMEOUT_CYCLES 40000000000LL   // ~20 s: a peer that is this late is gone
@@ -180,7 +184,14 @@ __global__ void __launch_bounds__(STEP_THREADS, EV ? 2 : 4) k_step(Dev d, StepAr
   const unsigned *__restrict__ bondrow = d.bondrow;
   const float sx = c_P.fscale[0], sy = c_P.fscale[1], sz = c_P.fscale[2];
   const int nt = c_P.ntypes;
-  const int i = d.own0 + blockIdx.x * STEP_THREADS + threadIdx.x;
+  int i = d.own0 + blockIdx.x * STEP_THREADS + threadIdx.x;
+  if (DD) {
+    // the two boundary slices first, the interior last: their halo stores are in flight while the interior computes
+    const int g = blockIdx.x * STEP_THREADS + threadIdx.x;
+    const int nl = ctrl->send_l_end - d.own0, nr = own_end - ctrl->send_r_beg;
+    i = g < nl ? d.own0 + g : (g < nl + nr ? ctrl->send_r_beg + (g - nl) : ctrl->send_l_end + (g - nl - nr));
+    if (g >= ctrl->nown) i = own_end;
+  }
 
   double acc[10];
   if (EV) {
@@ -376,6 +387,7 @@ __device__ __forceinline__ void close_epoch(const Dev &d) {
       const unsigned long long v = le_wait_flag(c, &d.flags[slot + p], e, 1);
       moved |= (int)(v & 1);
     }
+    __threadfence_system();
     c->moved = moved;
   }
   c->epoch = (long long)e + 1;
@@ -431,25 +443,15 @@ __global__ void k_after_build(Dev d) {
 // ------------------------------------------------------------------------------------------------
 struct RbScratch { int out_count[2]; int in_count[2]; };
 
-__global__ void k_rb_begin(Dev d, RbScratch *rb) {
-  d.ctrl->rebuild_epoch++;
-  d.ctrl->nown_unsorted = d.ctrl->nown;
-  rb->out_count[0] = rb->out_count[1] = 0;
-  rb->in_count[0] = rb->in_count[1] = 0;
-}
-
-// forget the ghosts of the previous list (their tags may be anywhere after this rebuild)
-__global__ void k_clear_ghost_map(Dev d) {
-  const int nl = d.ctrl->nghl, nr = d.ctrl->nghr;
-  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < nl + nr; g += gridDim.x * blockDim.x) {
-    // ghost_tag is this GPU's private record of its ghosts: the peers may already be overwriting pos_hold's ghost slots
-    d.map[d.ghost_tag[g] - 1] = -1;
-  }
-}
-
 __global__ void k_cell_count(Dev d, RbScratch *rb) {
   const int4 *__restrict__ pos = d.pos[d.ctrl->cur];
   const int lo = d.own0, hi = d.own0 + d.ctrl->nown;
+  if (d.nranks > 1) {
+    // forget the ghosts of the previous list (their tags may be anywhere after this rebuild).  ghost_tag is this
+    // GPU's private record of its ghosts: the peers may already be overwriting pos_hold's ghost slots
+    const int nl = d.ctrl->nghl, nr = d.ctrl->nghr;
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < nl + nr; g += gridDim.x * blockDim.x) d.map[d.ghost_tag[g] - 1] = -1;
+  }
   for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
     const int4 p = pos[i];
     const int cx = __umulhi((unsigned)p.x, (unsigned)d.ncell[0]);
@@ -478,14 +480,16 @@ __global__ void k_cell_count(Dev d, RbScratch *rb) {
 __global__ void k_rb_post_inbox(Dev d, RbScratch *rb) {
   Ctrl *c = d.ctrl;
   __threadfence_system();
-  const unsigned long long e = (unsigned long long)c->rebuild_epoch;
+  const unsigned long long e = (unsigned long long)(++c->rebuild_epoch);
   const int par = (int)(e & 1) * 2;
   st_sys(&d.peer[left_rank(d)].flags[FLAG_INBOX + par + 1], (e << 24) | (unsigned)rb->out_count[0]);
   st_sys(&d.peer[right_rank(d)].flags[FLAG_INBOX + par + 0], (e << 24) | (unsigned)rb->out_count[1]);
+  rb->out_count[0] = rb->out_count[1] = 0;        // for the next rebuild
   for (int side = 0; side < 2; side++) {
     const unsigned long long v = le_wait_flag(c, &d.flags[FLAG_INBOX + par + side], e, 24);
     rb->in_count[side] = (int)(v & 0xffffffu);
   }
+  __threadfence_system();
   c->nown_unsorted = c->nown + rb->in_count[0] + rb->in_count[1];
   if (d.own0 + c->nown_unsorted > d.gr0) le_raise(c, LE_DERR_LOCAL_OVERFLOW, c->nown_unsorted, d.gr0 - d.own0, 3);
 }
@@ -594,7 +598,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_apply(Dev d) {
 }
 
 __global__ void k_cell_scatter(Dev d) {
-  const int lo = d.own0, hi = d.own0 + d.ctrl->nown_unsorted;
+  const int lo = d.own0, hi = d.own0 + (d.nranks > 1 ? d.ctrl->nown_unsorted : d.N);
   for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
     const int c = d.cellid[i];
     if (c >= 0) d.order[d.cell_start[c] + d.slot[i]] = i;
@@ -695,6 +699,7 @@ __global__ void k_rb_post_ghosts(Dev d) {
   st_sys(&d.peer[right_rank(d)].flags[FLAG_GHOST + par + 0], (e << 24) | (unsigned)(d.own0 + c->nown - c->send_r_beg));
   const unsigned long long v0 = le_wait_flag(c, &d.flags[FLAG_GHOST + par + 0], e, 24);
   const unsigned long long v1 = le_wait_flag(c, &d.flags[FLAG_GHOST + par + 1], e, 24);
+  __threadfence_system();
   c->nghl = (int)(v0 & 0xffffffu);
   c->nghr = (int)(v1 & 0xffffffu);
 }

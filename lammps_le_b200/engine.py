@@ -40,7 +40,7 @@ class Stats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in
                 ("steps", "neigh_builds", "dangerous_builds", "half_pairs", "full_entries", "kernel_launches",
                  "extrusion_shifts", "loads", "unloads", "last_extrusion_shifts", "last_loads", "last_unloads")] + \
-               [("last_run_gpu_ms", C.c_double)]
+               [("last_run_gpu_ms", C.c_double), ("last_run_le_ms", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
