@@ -1,0 +1,433 @@
+// le_deck.cpp -- C++ host front end: runs a LAMMPS input script (the subset of commands on the hot path)
+// unchanged on the B200 engine through the C ABI of include/le_b200.h.
+//
+//   le_deck -in in.chain [-echo]          (also: le_deck < in.chain)
+//
+// It plays the role of the reference's Input::file / Input::execute_command loop (src/input.cpp:161-300,
+// :680-820) and ReadData (src/read_data.cpp) for atom_style bond, and prints thermo output and the
+// "Loop time" line in the reference's format (src/thermo.cpp, src/finish.cpp:61-100) so that existing
+// post-processing keeps working.  Commands it knows:
+//   units lj | atom_style bond | newton P B | special_bonds fene|lj a b c | atom_modify ... | comm_modify ...
+//   read_data F [extra/bond/per/atom N] [extra/special/per/atom N] | mass T M
+//   neighbor S bin | neigh_modify every|delay|check ... | pair_style lj/cut RC | pair_modify shift yes|no
+//   pair_coeff I J eps sigma [rc] | bond_style fene|harmonic|hybrid ... | bond_coeff N [style] ...
+//   fix ID all nve | nve/limit X | langevin T0 T1 damp seed | extrusion ... | ex_load ... | ex_unload ...
+//   unfix ID | timestep dt | reset_timestep N | thermo N | thermo_style ... | thermo_modify ... | run N
+//   write_data F | log/echo/print (ignored or echoed)
+// Anything else stops with the reference's "Unknown command" error.  No compute happens here: every
+// number comes from libleb200.so (there is no CPU fallback).
+#include "../../include/le_b200.h"
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+namespace {
+
+typedef std::vector<std::string> Words;
+
+struct Deck {
+  le_ctx *ctx = nullptr;
+  // data file
+  int natoms = 0, nbonds = 0, ntypes = 0, nbondtypes = 0, extra_bond = 0, extra_special = 0;
+  double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+  std::vector<int> tag, mol, type, image, btype, b1, b2;
+  std::vector<double> x, v, mass;
+  bool have_v = false, uploaded = false;
+  int bpa = 1;                                         // bond_per_atom the context was sized with
+  // settings
+  double special[3] = {0.0, 0.0, 0.0};
+  int newton_pair = 1, newton_bond = 1;
+  double skin = 0.3; int every = 1, delay = 10, check = 1;
+  double pair_cut = 0.0; int shift = 0; bool pair_set = false;
+  std::vector<double> eps, sigma, cut; std::vector<char> coeff_set;
+  std::vector<std::string> bond_styles;                // bond_style arguments
+  std::map<int, std::pair<int, std::vector<double>>> bond_coeff;
+  double dt = 0.005;
+  int thermo_every = 0;
+  std::map<std::string, std::string> fix_style;        // fix ID -> style
+  bool echo = false;
+};
+
+[[noreturn]] void die(const std::string &msg) {
+  std::fprintf(stderr, "ERROR: %s\n", msg.c_str());
+  std::exit(1);
+}
+void ck(Deck &d, int rc) { if (rc) die(le_last_error(d.ctx)); }
+double num(const std::string &s) {
+  char *e; const double v = std::strtod(s.c_str(), &e);
+  if (*e) die("Expected floating point parameter instead of '" + s + "' in input script or data file");
+  return v;
+}
+int inum(const std::string &s) {
+  char *e; const long v = std::strtol(s.c_str(), &e, 10);
+  if (*e) die("Expected integer parameter instead of '" + s + "' in input script or data file");
+  return (int)v;
+}
+Words split(const std::string &line) {
+  std::string s = line.substr(0, line.find('#'));
+  std::istringstream is(s); Words w; std::string t;
+  while (is >> t) w.push_back(t);
+  return w;
+}
+
+// ---- read_data (src/read_data.cpp: header keywords :900-1100, Atoms/Velocities/Bonds sections) ----------------
+void read_data(Deck &d, const Words &w) {
+  if (w.size() < 2) die("Illegal read_data command");
+  for (size_t k = 2; k + 1 < w.size(); k += 2) {
+    if (w[k] == "extra/bond/per/atom") d.extra_bond = inum(w[k + 1]);
+    else if (w[k] == "extra/special/per/atom") d.extra_special = inum(w[k + 1]);
+    else die("Illegal read_data command");
+  }
+  std::ifstream f(w[1]);
+  if (!f) die("Cannot open file " + w[1]);
+  std::string line, section;
+  std::getline(f, line);                                 // title
+  std::vector<Words> rows;
+  auto header = [&](const Words &t) {
+    if (t.size() == 2 && t[1] == "atoms") d.natoms = inum(t[0]);
+    else if (t.size() == 2 && t[1] == "bonds") d.nbonds = inum(t[0]);
+    else if (t.size() == 3 && t[1] == "atom" && t[2] == "types") d.ntypes = inum(t[0]);
+    else if (t.size() == 3 && t[1] == "bond" && t[2] == "types") d.nbondtypes = inum(t[0]);
+    else if (t.size() == 5 && t[1] == "extra" && t[2] == "bond") d.extra_bond = inum(t[0]);
+    else if (t.size() == 5 && t[1] == "extra" && t[2] == "special") d.extra_special = inum(t[0]);
+    else if (t.size() == 4 && t[2] == "xlo") { d.lo[0] = num(t[0]); d.hi[0] = num(t[1]); }
+    else if (t.size() == 4 && t[2] == "ylo") { d.lo[1] = num(t[0]); d.hi[1] = num(t[1]); }
+    else if (t.size() == 4 && t[2] == "zlo") { d.lo[2] = num(t[0]); d.hi[2] = num(t[1]); }
+    else if (t.size() >= 2 && (t[1] == "angles" || t[1] == "dihedrals" || t[1] == "impropers")) { if (inum(t[0])) die("only atom_style bond data files are supported"); }
+    else if (t.size() >= 3 && (t[1] == "angle" || t[1] == "dihedral" || t[1] == "improper")) {}
+    else die("Unknown identifier in data file: " + t[0]);
+  };
+  auto finish_section = [&]() {
+    if (section == "Masses") {
+      d.mass.assign(d.ntypes, 1.0);
+      for (auto &r : rows) { const int t = inum(r[0]); if (t < 1 || t > d.ntypes) die("Invalid type for mass set"); d.mass[t - 1] = num(r[1]); }
+    } else if (section == "Atoms") {
+      if ((int)rows.size() != d.natoms) die("Did not assign all atoms correctly");
+      d.tag.resize(d.natoms); d.mol.resize(d.natoms); d.type.resize(d.natoms); d.image.assign(d.natoms, (512) | (512 << 10) | (512 << 20));
+      d.x.resize((size_t)3 * d.natoms);
+      for (int k = 0; k < d.natoms; k++) {
+        const Words &r = rows[k];
+        if (r.size() != 6 && r.size() != 9) die("Incorrect atom format in data file");
+        d.tag[k] = inum(r[0]); d.mol[k] = inum(r[1]); d.type[k] = inum(r[2]);
+        for (int q = 0; q < 3; q++) d.x[3 * k + q] = num(r[3 + q]);
+        if (r.size() == 9) {
+          const int ix = inum(r[6]), iy = inum(r[7]), iz = inum(r[8]);
+          d.image[k] = ((ix + 512) & 1023) | (((iy + 512) & 1023) << 10) | (((iz + 512) & 1023) << 20);
+        }
+      }
+    } else if (section == "Velocities") {
+      if (d.tag.empty()) die("Must read Atoms before Velocities");
+      std::map<int, int> where;
+      for (int k = 0; k < d.natoms; k++) where[d.tag[k]] = k;
+      d.v.assign((size_t)3 * d.natoms, 0.0);
+      for (auto &r : rows) { const int k = where.at(inum(r[0])); for (int q = 0; q < 3; q++) d.v[3 * k + q] = num(r[1 + q]); }
+      d.have_v = true;
+    } else if (section == "Bonds") {
+      if ((int)rows.size() != d.nbonds) die("Bonds assigned incorrectly");
+      for (auto &r : rows) { d.btype.push_back(inum(r[1])); d.b1.push_back(inum(r[2])); d.b2.push_back(inum(r[3])); }
+    } else if (section == "Bond Coeffs" || section == "Pair Coeffs" || section == "PairIJ Coeffs") {
+      // coefficients in the data file need the styles to be defined first; the decks on this path set them in the script
+    } else if (!section.empty()) die("Unknown section in data file: " + section);
+    rows.clear();
+  };
+  while (std::getline(f, line)) {
+    Words t = split(line);
+    if (t.empty()) continue;
+    const bool is_section = std::isalpha((unsigned char)t[0][0]);
+    if (is_section) {
+      finish_section();
+      section = t[0];
+      if (t.size() > 1 && t[1] == "Coeffs") section += " Coeffs";
+      continue;
+    }
+    if (section.empty()) header(t);
+    else rows.push_back(t);
+  }
+  finish_section();
+  if (d.natoms < 1) die("No atoms in data file");
+  if (d.mass.empty()) d.mass.assign(d.ntypes, 1.0);
+  const int per[3] = {1, 1, 1};
+  int rc = le_create(&d.ctx, 0, d.lo, d.hi, per);
+  if (rc) die(d.ctx ? le_last_error(d.ctx) : "no CUDA device (there is no CPU fallback)");
+  d.eps.assign((size_t)d.ntypes * d.ntypes, 0.0); d.sigma = d.eps; d.cut = d.eps; d.coeff_set.assign(d.eps.size(), 0);
+  std::printf("  %d atoms\n  %d bonds\n", d.natoms, d.nbonds);
+}
+
+int bond_style_id(const std::string &s) {
+  if (s == "fene") return LE_BOND_FENE;
+  if (s == "harmonic") return LE_BOND_HARMONIC;
+  if (s == "none" || s == "zero") return LE_BOND_NONE;
+  die("Unknown bond style " + s);
+}
+
+// push every setting into the context and upload the system on the first run
+void init(Deck &d) {
+  if (!d.ctx) die("Run command before simulation box is defined");
+  ck(d, le_set_types(d.ctx, d.ntypes, d.mass.data(), d.nbondtypes));
+  if (!d.pair_set) die("Pair style is not defined");
+  // Pair::mix_* geometric for lj units default (src/pair.cpp:577-607) for pairs without an explicit pair_coeff
+  std::vector<double> e = d.eps, s = d.sigma, c = d.cut;
+  const int nt = d.ntypes;
+  for (int i = 0; i < nt; i++) if (!d.coeff_set[i * nt + i]) die("All pair coeffs are not set");
+  for (int i = 0; i < nt; i++)
+    for (int j = 0; j < nt; j++)
+      if (!d.coeff_set[i * nt + j]) {
+        e[i * nt + j] = std::sqrt(e[i * nt + i] * e[j * nt + j]);
+        s[i * nt + j] = std::sqrt(s[i * nt + i] * s[j * nt + j]);
+        c[i * nt + j] = std::sqrt(c[i * nt + i] * c[j * nt + j]);     // mix_distance, geometric
+      }
+  ck(d, le_set_pair_lj(d.ctx, nt, e.data(), s.data(), c.data(), d.shift));
+  for (auto &kv : d.bond_coeff) {
+    double p[4] = {0, 0, 0, 0};
+    for (size_t k = 0; k < kv.second.second.size() && k < 4; k++) p[k] = kv.second.second[k];
+    ck(d, le_set_bond(d.ctx, kv.first, kv.second.first, p));
+  }
+  if ((int)d.bond_coeff.size() < d.nbondtypes) die("All bond coeffs are not set");
+  ck(d, le_set_special(d.ctx, d.special));
+  ck(d, le_set_newton(d.ctx, d.newton_pair, d.newton_bond));
+  ck(d, le_set_neighbor(d.ctx, d.skin, d.every, d.delay, d.check));
+  ck(d, le_set_timestep(d.ctx, d.dt));
+  ck(d, le_thermo_every(d.ctx, d.thermo_every));
+  if (!d.uploaded) {
+    // bond_per_atom / maxspecial as ReadData sizes them: the largest count in the file plus the "extra" head room
+    std::vector<int> nb(d.natoms + 1, 0);
+    for (int k = 0; k < d.nbonds; k++) { nb[d.b1[k]]++; if (!d.newton_bond) nb[d.b2[k]]++; else nb[d.b2[k]]++; }
+    int bpa = 1;
+    for (int t = 1; t <= d.natoms; t++) bpa = std::max(bpa, nb[t]);
+    bpa += d.extra_bond;
+    int maxspecial = bpa * (1 + bpa + bpa * bpa) / 1;      // generous bound on 1-2 + 1-3 + 1-4 partners
+    maxspecial = std::min(std::max(maxspecial, 4), 64) + d.extra_special;
+    if (maxspecial > 255) maxspecial = 255;
+    d.bpa = std::min(bpa, 15);
+    ck(d, le_set_capacity(d.ctx, d.bpa, maxspecial));
+    ck(d, le_upload_atoms(d.ctx, d.natoms, d.tag.data(), d.type.data(), d.x.data(), d.have_v ? d.v.data() : nullptr, d.image.data()));
+    ck(d, le_upload_bonds(d.ctx, d.nbonds, d.btype.data(), d.b1.data(), d.b2.data()));
+    d.uploaded = true;
+  }
+}
+
+void print_thermo(Deck &d, int first) {
+  const int n = le_thermo_count(d.ctx);
+  std::printf("Step Temp E_pair E_mol TotEng Press \n");
+  for (int k = first; k < n; k++) {
+    le_thermo t; le_get_thermo(d.ctx, k, &t);
+    std::printf("%8lld %12.8g %12.8g %12.8g %12.8g %12.8g \n", (long long)t.step, t.temp, t.epair, t.emol, t.etotal, t.press);
+  }
+}
+
+void run(Deck &d, const Words &w) {
+  if (w.size() < 2) die("Illegal run command");
+  const long long n = std::strtoll(w[1].c_str(), nullptr, 10);
+  init(d);
+  const int first = le_thermo_count(d.ctx);
+  const auto t0 = std::chrono::steady_clock::now();
+  ck(d, le_run(d.ctx, n));
+  const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  print_thermo(d, first);
+  le_stats st; ck(d, le_get_stats(d.ctx, &st));
+  std::printf("Loop time of %g on 1 procs for %lld steps with %d atoms\n\n", sec, n, d.natoms);
+  std::printf("Total # of neighbors = %lld\nAve neighs/atom = %g\nNeighbor list builds = %lld\nDangerous builds = %lld\n",
+              (long long)st.half_pairs, (double)st.half_pairs / d.natoms, (long long)st.neigh_builds, (long long)st.dangerous_builds);
+  std::printf("GPU time of the step loop = %g ms\n", st.last_run_gpu_ms);
+}
+
+void write_data(Deck &d, const Words &w) {
+  if (w.size() < 2) die("Illegal write_data command");
+  if (!d.uploaded) init(d);
+  const int n = d.natoms;
+  std::vector<double> x((size_t)3 * n), v((size_t)3 * n);
+  std::vector<int> im(n), ty(n), nb(n), bt, ba;
+  ck(d, le_download_x(d.ctx, x.data(), im.data()));
+  ck(d, le_download_v(d.ctx, v.data()));
+  ck(d, le_download_types(d.ctx, ty.data()));
+  const int bpa = d.bpa;
+  bt.resize((size_t)n * bpa); ba.resize((size_t)n * bpa);
+  ck(d, le_download_topology(d.ctx, nb.data(), bt.data(), ba.data(), nullptr, nullptr));
+  std::vector<int> mol_by_tag(n + 1, 0);
+  for (int k = 0; k < n; k++) mol_by_tag[d.tag[k]] = d.mol[k];
+  long long nbonds = 0;
+  for (int t = 0; t < n; t++) for (int m = 0; m < nb[t]; m++) if (t + 1 < ba[(size_t)t * bpa + m]) nbonds++;
+  FILE *f = std::fopen(w[1].c_str(), "w");
+  if (!f) die("Cannot open data file " + w[1]);
+  std::fprintf(f, "LAMMPS data file via write_data, le_b200, timestep = %lld\n\n%d atoms\n%d atom types\n%lld bonds\n%d bond types\n\n",
+               (long long)le_timestep(d.ctx), n, d.ntypes, nbonds, d.nbondtypes);
+  std::fprintf(f, "%.16e %.16e xlo xhi\n%.16e %.16e ylo yhi\n%.16e %.16e zlo zhi\n\nMasses\n\n", d.lo[0], d.hi[0], d.lo[1], d.hi[1], d.lo[2], d.hi[2]);
+  for (int t = 0; t < d.ntypes; t++) std::fprintf(f, "%d %.10g\n", t + 1, d.mass[t]);
+  std::fprintf(f, "\nAtoms # bond\n\n");
+  for (int t = 0; t < n; t++)
+    std::fprintf(f, "%d %d %d %.16e %.16e %.16e %d %d %d\n", t + 1, mol_by_tag[t + 1], ty[t], x[3 * t], x[3 * t + 1], x[3 * t + 2],
+                 (im[t] & 1023) - 512, ((im[t] >> 10) & 1023) - 512, ((im[t] >> 20) & 1023) - 512);
+  std::fprintf(f, "\nVelocities\n\n");
+  for (int t = 0; t < n; t++) std::fprintf(f, "%d %.16e %.16e %.16e\n", t + 1, v[3 * t], v[3 * t + 1], v[3 * t + 2]);
+  std::fprintf(f, "\nBonds\n\n");
+  long long id = 0;
+  for (int t = 0; t < n; t++)
+    for (int m = 0; m < nb[t]; m++)
+      if (t + 1 < ba[(size_t)t * bpa + m]) std::fprintf(f, "%lld %d %d %d\n", ++id, bt[(size_t)t * bpa + m], t + 1, ba[(size_t)t * bpa + m]);
+  std::fclose(f);
+}
+
+void expand_types(const std::string &s, int n, int &a, int &b) {     // utils::bounds: "*", "N", "N*", "*M", "N*M"
+  const size_t star = s.find('*');
+  if (star == std::string::npos) { a = b = inum(s); }
+  else { a = star == 0 ? 1 : inum(s.substr(0, star)); b = star + 1 == s.size() ? n : inum(s.substr(star + 1)); }
+  if (a < 1 || b > n || a > b) die("Invalid type range " + s);
+}
+
+void fix(Deck &d, const Words &w) {
+  if (w.size() < 4) die("Illegal fix command");
+  if (!d.ctx) die("Fix command before simulation box is defined");
+  if (w[2] != "all") die("only group all is supported");
+  const std::string &st = w[3];
+  auto need = [&](size_t n) { if (w.size() < n) die("Illegal fix " + st + " command"); };
+  // the fixes validate atom / bond types against the system: make the counts known first
+  ck(d, le_set_types(d.ctx, d.ntypes, d.mass.data(), d.nbondtypes));
+  if (st == "nve") ck(d, le_fix_nve(d.ctx, 1));
+  else if (st == "nve/limit") { need(5); ck(d, le_fix_nve_limit(d.ctx, num(w[4]))); }
+  else if (st == "langevin") { need(8); ck(d, le_fix_langevin(d.ctx, num(w[4]), num(w[5]), num(w[6]), inum(w[7]))); }
+  else if (st == "extrusion") {          // fix ID all extrusion N neutral left right p btype [roadblock]   (fix_extrusion.cpp:60-110)
+    need(10);
+    ck(d, le_fix_extrusion(d.ctx, inum(w[4]), inum(w[5]), inum(w[6]), inum(w[7]), num(w[8]), inum(w[9]), w.size() > 10 ? inum(w[10]) : -1, 0));
+  } else if (st == "ex_load") {          // fix ID all ex_load N itype jtype Rmin btype [prob f seed] [iparam M T] [jparam M T]   (fix_ex_load.cpp:60-150)
+    need(9);
+    double prob = 1.0; int seed = 12345, imax = 0, inew = inum(w[5]), jmax = 0, jnew = inum(w[6]);
+    for (size_t k = 9; k < w.size();) {
+      if (w[k] == "prob" && k + 2 < w.size()) { prob = num(w[k + 1]); seed = inum(w[k + 2]); k += 3; }
+      else if (w[k] == "iparam" && k + 2 < w.size()) { imax = inum(w[k + 1]); inew = inum(w[k + 2]); k += 3; }
+      else if (w[k] == "jparam" && k + 2 < w.size()) { jmax = inum(w[k + 1]); jnew = inum(w[k + 2]); k += 3; }
+      else die("Illegal fix ex_load command");
+    }
+    ck(d, le_fix_ex_load(d.ctx, inum(w[4]), inum(w[5]), inum(w[6]), num(w[7]), inum(w[8]), prob, seed, imax, inew, jmax, jnew));
+  } else if (st == "ex_unload") {        // fix ID all ex_unload N btype Rmax [prob f seed]   (fix_ex_unload.cpp:50-100)
+    need(7);
+    double prob = 1.0; int seed = 12345;
+    for (size_t k = 7; k < w.size();) {
+      if (w[k] == "prob" && k + 2 < w.size()) { prob = num(w[k + 1]); seed = inum(w[k + 2]); k += 3; }
+      else die("Illegal fix ex_unload command");
+    }
+    ck(d, le_fix_ex_unload(d.ctx, inum(w[4]), inum(w[5]), num(w[6]), prob, seed));
+  } else die("Unknown fix style " + st);
+  d.fix_style[w[1]] = st;
+}
+
+void unfix(Deck &d, const Words &w) {
+  if (w.size() < 2 || !d.fix_style.count(w[1])) die("Could not find fix ID to delete");
+  const std::string st = d.fix_style[w[1]];
+  if (st == "nve" || st == "nve/limit") ck(d, le_fix_nve(d.ctx, 0));
+  else if (st == "extrusion") ck(d, le_unfix(d.ctx, LE_FIX_EXTRUSION));
+  else if (st == "ex_load") ck(d, le_unfix(d.ctx, LE_FIX_EX_LOAD));
+  else if (st == "ex_unload") ck(d, le_unfix(d.ctx, LE_FIX_EX_UNLOAD));
+  else if (st == "langevin") die("unfix of fix langevin is not supported");
+  d.fix_style.erase(w[1]);
+}
+
+void execute_cmd(Deck &d, const Words &w);
+void execute(Deck &d, const Words &w) {
+  static const bool verbose = std::getenv("LE_DECK_TIMING") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  execute_cmd(d, w);
+  if (verbose) std::fprintf(stderr, "[le_deck] %-16s %.3f s\n", w[0].c_str(), std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+}
+void execute_cmd(Deck &d, const Words &w) {
+  const std::string &c = w[0];
+  if (c == "units") { if (w.size() < 2 || w[1] != "lj") die("only units lj is supported"); }
+  else if (c == "atom_style") { if (w.size() < 2 || w[1] != "bond") die("only atom_style bond is supported"); }
+  else if (c == "atom_modify" || c == "comm_modify" || c == "log" || c == "echo" || c == "thermo_style" || c == "thermo_modify" || c == "processors") {}
+  else if (c == "print") { for (size_t k = 1; k < w.size(); k++) std::printf("%s%s", w[k].c_str(), k + 1 < w.size() ? " " : "\n"); }
+  else if (c == "newton") {
+    if (w.size() == 2) d.newton_pair = d.newton_bond = (w[1] == "on");
+    else if (w.size() == 3) { d.newton_pair = (w[1] == "on"); d.newton_bond = (w[2] == "on"); }
+    else die("Illegal newton command");
+  } else if (c == "special_bonds") {
+    if (w.size() == 2 && w[1] == "fene") { d.special[0] = 0.0; d.special[1] = 1.0; d.special[2] = 1.0; }
+    else if (w.size() == 5 && w[1] == "lj") { for (int k = 0; k < 3; k++) d.special[k] = num(w[2 + k]); }
+    else if (w.size() == 5 && w[1] == "lj/coul") { for (int k = 0; k < 3; k++) d.special[k] = num(w[2 + k]); }
+    else die("Illegal special_bonds command");
+  } else if (c == "read_data") read_data(d, w);
+  else if (c == "mass") { if (w.size() != 3 || d.mass.empty()) die("Illegal mass command"); int a, b; expand_types(w[1], d.ntypes, a, b); for (int t = a; t <= b; t++) d.mass[t - 1] = num(w[2]); }
+  else if (c == "neighbor") { if (w.size() != 3 || w[2] != "bin") die("Illegal neighbor command (only bin)"); d.skin = num(w[1]); }
+  else if (c == "neigh_modify") {
+    for (size_t k = 1; k + 1 < w.size(); k += 2) {
+      if (w[k] == "every") d.every = inum(w[k + 1]);
+      else if (w[k] == "delay") d.delay = inum(w[k + 1]);
+      else if (w[k] == "check") d.check = (w[k + 1] == "yes");
+      else if (w[k] == "one" || w[k] == "page") {}
+      else die("Illegal neigh_modify command");
+    }
+  } else if (c == "pair_style") {
+    if (w.size() != 3 || w[1] != "lj/cut") die("only pair_style lj/cut is supported");
+    d.pair_cut = num(w[2]); d.pair_set = true;
+  } else if (c == "pair_modify") {
+    for (size_t k = 1; k + 1 < w.size(); k += 2) {
+      if (w[k] == "shift") d.shift = (w[k + 1] == "yes");
+      else if (w[k] == "mix") { if (w[k + 1] != "geometric") die("only pair_modify mix geometric is supported"); }
+      else die("Illegal pair_modify command");
+    }
+  } else if (c == "pair_coeff") {
+    if (!d.ctx) die("Pair_coeff command before simulation box is defined");
+    if (!d.pair_set || w.size() < 5) die("Incorrect args for pair coefficients");
+    int a0, a1, b0, b1; expand_types(w[1], d.ntypes, a0, a1); expand_types(w[2], d.ntypes, b0, b1);
+    for (int i = a0; i <= a1; i++)
+      for (int j = std::max(b0, i); j <= b1; j++)
+        for (int q = 0; q < 2; q++) {
+          const int k = q ? (j - 1) * d.ntypes + (i - 1) : (i - 1) * d.ntypes + (j - 1);
+          d.eps[k] = num(w[3]); d.sigma[k] = num(w[4]); d.cut[k] = w.size() > 5 ? num(w[5]) : d.pair_cut; d.coeff_set[k] = 1;
+        }
+  } else if (c == "bond_style") { d.bond_styles.assign(w.begin() + 1, w.end()); if (d.bond_styles.empty()) die("Illegal bond_style command"); }
+  else if (c == "bond_coeff") {
+    if (!d.ctx) die("Bond_coeff command before simulation box is defined");
+    if (d.bond_styles.empty() || w.size() < 3) die("Incorrect args for bond coefficients");
+    int a, b; expand_types(w[1], d.nbondtypes, a, b);
+    size_t p = 2; std::string style = d.bond_styles[0];
+    if (style == "hybrid") { style = w[2]; p = 3; }
+    std::vector<double> par;
+    for (; p < w.size(); p++) par.push_back(num(w[p]));
+    for (int t = a; t <= b; t++) d.bond_coeff[t] = {bond_style_id(style), par};
+  } else if (c == "fix") fix(d, w);
+  else if (c == "unfix") unfix(d, w);
+  else if (c == "timestep") { if (w.size() != 2) die("Illegal timestep command"); d.dt = num(w[1]); }
+  else if (c == "reset_timestep") { if (w.size() != 2 || !d.ctx) die("Illegal reset_timestep command"); ck(d, le_reset_timestep(d.ctx, std::strtoll(w[1].c_str(), nullptr, 10))); }
+  else if (c == "thermo") { if (w.size() != 2) die("Illegal thermo command"); d.thermo_every = inum(w[1]); }
+  else if (c == "run") run(d, w);
+  else if (c == "write_data") write_data(d, w);
+  else die("Unknown command: " + c);
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  Deck d;
+  const char *infile = nullptr;
+  for (int k = 1; k < argc; k++) {
+    if (!std::strcmp(argv[k], "-in") && k + 1 < argc) infile = argv[++k];
+    else if (!std::strcmp(argv[k], "-echo")) d.echo = true;
+    else if (!std::strcmp(argv[k], "-log") || !std::strcmp(argv[k], "-screen")) k++;
+  }
+  std::ifstream fin;
+  if (infile) { fin.open(infile); if (!fin) die(std::string("Cannot open input script ") + infile); }
+  std::istream &in = infile ? (std::istream &)fin : std::cin;
+  std::printf("%s -- LAMMPS input front end\n", le_version());
+  std::string line, acc;
+  while (std::getline(in, line)) {
+    // '&' continuation (Input::file, src/input.cpp:195-215)
+    size_t e = line.find_last_not_of(" \t\r");
+    if (e != std::string::npos && line[e] == '&') { acc += line.substr(0, e) + " "; continue; }
+    acc += line;
+    Words w = split(acc);
+    if (d.echo && !w.empty()) std::printf("%s\n", acc.c_str());
+    acc.clear();
+    if (w.empty()) continue;
+    execute(d, w);
+  }
+  if (d.ctx) le_destroy(d.ctx);
+  return 0;
+}

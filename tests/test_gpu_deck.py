@@ -1,0 +1,104 @@
+"""BASELINE.json configs[0] through the C++ host front end: the reference's bench/in.chain input script runs UNCHANGED
+on le_deck (lammps_le_b200/csrc/le_deck.cpp -> C ABI -> CUDA engine) and reproduces the thermo output of the
+reference's own published log (bench/log.6Oct16.chain.fixed.icc.1; fixture tests/golden/bench_chain.npz)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+# bench/in.chain of the reference, verbatim (20 input lines)
+IN_CHAIN = """# FENE beadspring benchmark
+
+units		lj
+atom_style	bond
+special_bonds   fene
+
+read_data	data.chain
+
+neighbor	0.4 bin
+neigh_modify	every 1 delay 1
+
+bond_style      fene
+bond_coeff	1 30.0 1.5 1.0 1.0
+
+pair_style	lj/cut 1.12
+pair_modify	shift yes
+pair_coeff	1 1 1.0 1.0 1.12
+
+fix		1 all nve
+fix		2 all langevin 1.0 1.0 10.0 904297
+
+thermo          100
+timestep	0.012
+
+run		100
+"""
+
+
+def write_data_chain(path, z):
+    z = {k: z[k] for k in z.files} if hasattr(z, "files") else z      # an NpzFile decompresses on every access
+    n = len(z["x"])
+    with open(path, "w") as f:
+        f.write("LAMMPS data file (tests/golden/bench_chain.npz)\n\n%d atoms\n%d bonds\n\n1 atom types\n1 bond types\n\n" % (n, len(z["bonds"])))
+        for k, ax in enumerate("xyz"):
+            f.write("%.17g %.17g %slo %shi\n" % (z["boxlo"][k], z["boxhi"][k], ax, ax))
+        f.write("\nMasses\n\n1 1\n\nAtoms\n\n")
+        for t in range(n):
+            f.write("%d %d %d %.17g %.17g %.17g %d %d %d\n" % (t + 1, z["mol"][t], z["type"][t], *z["x"][t], *z["image"][t]))
+        f.write("\nVelocities\n\n")
+        for t in range(n):
+            f.write("%d %.17g %.17g %.17g\n" % (t + 1, *z["v"][t]))
+        f.write("\nBonds\n\n")
+        for k, (bt, a, b) in enumerate(z["bonds"]):
+            f.write("%d %d %d %d\n" % (k + 1, bt, a, b))
+
+
+def parse_thermo(out):
+    m = re.search(r"Step Temp E_pair E_mol TotEng Press \n(.*?)\nLoop time", out, re.S)
+    return np.array([[float(v) for v in row.split()] for row in m.group(1).splitlines()])
+
+
+@pytest.mark.gpu
+def test_bench_in_chain_runs_unchanged_and_matches_the_reference_log(tmp_path):
+    z = np.load(os.path.join(GOLD, "bench_chain.npz"))
+    write_data_chain(tmp_path / "data.chain", z)
+    (tmp_path / "in.chain").write_text(IN_CHAIN)
+    exe = os.path.join(ROOT, "lammps_le_b200", "le_deck")
+    assert os.path.exists(exe), "le_deck is not built (make -C lammps_le_b200/csrc)"
+    r = subprocess.run([exe, "-in", "in.chain"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    th = parse_thermo(r.stdout)
+    ref = z["ref_thermo"]
+    assert th.shape == ref.shape and (th[:, 0] == ref[:, 0]).all()
+    # step 0 is deterministic: Temp, E_pair, E_mol, TotEng, Press as the reference prints them (8 significant digits);
+    # positions are snapped to a 2^-32 box-fraction grid (8e-9 sigma here), which moves the energies by < 1e-6 relative
+    rel = np.abs(th[0, 1:] - ref[0, 1:]) / np.abs(ref[0, 1:])
+    assert rel.max() < 2e-6, (th[0], ref[0])
+    # step 100: a different (counter-based) noise stream -> agreement within thermal fluctuations of a 32,000-bead melt
+    assert abs(th[1, 1] - ref[1, 1]) < 0.02           # Temp
+    assert abs(th[1, 2] - ref[1, 2]) < 0.02           # E_pair
+    assert abs(th[1, 3] - ref[1, 3]) < 0.08           # E_mol
+    assert abs(th[1, 5] - ref[1, 5]) < 0.15           # Press
+    builds = int(re.search(r"Neighbor list builds = (\d+)", r.stdout).group(1))
+    assert abs(builds - int(z["ref_builds"])) <= 6
+
+
+@pytest.mark.gpu
+def test_deck_write_data_roundtrip(tmp_path):
+    """write_data -> read_data through the front end: same step-0 thermo from the written file"""
+    z = np.load(os.path.join(GOLD, "bench_chain.npz"))
+    write_data_chain(tmp_path / "data.chain", z)
+    deck = IN_CHAIN.replace("run\t\t100", "run 0\nwrite_data out.data")
+    (tmp_path / "in.a").write_text(deck)
+    (tmp_path / "in.b").write_text(deck.replace("data.chain", "out.data").replace("write_data out.data", ""))
+    exe = os.path.join(ROOT, "lammps_le_b200", "le_deck")
+    a = subprocess.run([exe, "-in", "in.a"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    b = subprocess.run([exe, "-in", "in.b"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert a.returncode == 0 and b.returncode == 0, a.stderr[-1500:] + b.stderr[-1500:]
+    ta, tb = parse_thermo(a.stdout), parse_thermo(b.stdout)
+    assert np.abs(ta[0] - tb[0]).max() < 1e-9
