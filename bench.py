@@ -192,28 +192,30 @@ def run_ours(args):
     total_atom_steps = world * n_beads * md * args.steps
     value = total_atom_steps / t_gpu
 
-    # ---- end to end through the C ABI with host buffers (several GPUs: every rank moves the atoms it owns) ----
-    x, im = Engine.positions(e)
-    v = Engine.velocities(e)
-    xp = torch.from_numpy(x).pin_memory().numpy()
-    vp = torch.from_numpy(v).pin_memory().numpy()
+    # ---- end to end through the C ABI with HOST buffers: every step uploads positions + velocities of the atoms the GPU
+    # owns from pinned host memory (le_upload_owned), runs, and downloads them again (le_download_owned) ----
+    bufs = e.owned_buffers(pinned=True)
+    nloc = e.download_owned(bufs)
     barrier()
     t0 = time.perf_counter()
+    moved = 0
     for _ in range(max(1, args.steps // 2)):
-        e.set_positions(xp, im)
-        e.set_velocities(vp)
+        e.upload_owned(nloc, bufs)
         e.run(md)
-        xo, im = Engine.positions(e)
-        xp[:] = xo
-        vp[:] = Engine.velocities(e)
+        nloc = e.download_owned(bufs)
+        moved += nloc
     barrier()
     t_e2e = time.perf_counter() - t0
-    te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+    te = torch.tensor([t_e2e, float(moved)], dtype=torch.float64, device="cuda")
     if world > 1:
+        tsum = te.clone()
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        moved = float(tsum[1])
     e2e_value = world * n_beads * md * max(1, args.steps // 2) / float(te[0])
-    h2d = n_beads * (24 + 24 + 4)
-    d2h = n_beads * (24 + 24 + 4)
+    per_step_atoms = moved / max(1, args.steps // 2)
+    h2d = int(per_step_atoms * (4 + 24 + 4 + 24))
+    d2h = int(per_step_atoms * (4 + 24 + 4 + 24))
 
     if rank != 0:
         if world > 1:
@@ -260,6 +262,7 @@ def run_ours(args):
             if refio.have_reference():
                 topo = e.topology()
                 seg = max(4, int(2.0e6 / n_beads * 8))          # ~16 MD steps per segment at 1M beads
+                xo, im = e.positions()
                 rate, _, wall_ref, nst = reference_rate(s, xo, im, e.velocities(), topo, seg, 1, 5)
                 line["cpu_baseline"] = {"value": rate, "unit": "atom-steps/s", "cores": 1, "kind": "reference",
                                         "sample": "%d MD steps of the same relaxed state in oracle/_ref/lmp_ref (1 rank: USER-LE is only "

@@ -153,6 +153,13 @@ int le_download_v(le_ctx *c, double *v);
 int le_download_types(le_ctx *c, int *type);
 int le_download_topology(le_ctx *c, int *num_bond, int *bond_type, int *bond_atom, int *nspecial,
                          int *special);
+/* bulk exchange of the atoms THIS GPU owns, in device order, with the double <-> fixed-point conversion done on
+ * the GPU (the host only moves flat buffers; use pinned memory for full PCIe speed).  Arrays hold at least
+ * le_local_capacity() entries; any output pointer may be NULL.  le_upload_owned addresses atoms by tag (they must
+ * be owned by this GPU) and, like le_set_positions, does not rebuild lists. */
+int le_local_capacity(const le_ctx *c);
+int le_download_owned(le_ctx *c, int *n_out, int *tag, double *x, int *image, double *v);
+int le_upload_owned(le_ctx *c, int n, const int *tag, const double *x, const int *image, const double *v);
 /* half neighbor list of the last build, CSR over tags: offsets[N+1]; entries = partner tag | which<<30
  * (the reference's j ^ (which << SBBITS), src/npair_half_bin_newton.cpp:113, with j replaced by tag).
  * Call with entries == NULL to get the total count in *nentries. */

@@ -93,6 +93,8 @@ struct le_ctx {
   void *peer_base[LE_MAXRANKS];
   bool peers_open;
   RbScratch *rb;
+  // device staging of le_download_owned / le_upload_owned (allocated on first use, [cap])
+  int *st_tag, *st_img; double *st_x, *st_v;
   std::vector<double> force_sums;                 // ... of the last le_compute_forces
   std::vector<std::vector<double>> thermo_sums;   // raw per-GPU tallies behind c->thermo (summed over ranks by the caller)
 };
@@ -216,6 +218,7 @@ extern "C" int le_create(le_ctx **out, int device, const double boxlo[3], const 
   memset(&c->gkey, 0, sizeof c->gkey);
   c->nranks = 1; c->rank = 0; c->halo_dist = 0.0; c->arena = nullptr; c->arena_bytes = 0; c->peers_open = false; c->rb = nullptr;
   memset(c->peer_base, 0, sizeof c->peer_base);
+  c->st_tag = c->st_img = nullptr; c->st_x = c->st_v = nullptr;
   cudaMallocHost(&c->h_thermo, sizeof(double) * LE_THERMO_W * THERMO_SLOTS);
   cudaMallocHost(&c->h_ctrl, sizeof(Ctrl));
   for (int k = 0; k < 3; k++)
@@ -983,7 +986,15 @@ static void enqueue_rebuild(le_ctx *c, bool direct) {
     LAUNCH(c, k_rb_post_ghosts, 1, 1, d);
     LAUNCH(c, k_ghost_map, grid_for(2 * d.own0, 256), 256, d);
   }
-  LAUNCH(c, k_build, grid_for(nslots, BUILD_THREADS), BUILD_THREADS, d);
+  {
+    static const int minb = getenv("LE_BUILD_MINB") ? atoi(getenv("LE_BUILD_MINB")) : 8;
+    const int g = grid_for(nslots, BUILD_THREADS);
+    if (minb == 10) LAUNCH(c, k_build<10>, g, BUILD_THREADS, d);
+    else if (minb == 12) LAUNCH(c, k_build<12>, g, BUILD_THREADS, d);
+    else if (minb == 16) LAUNCH(c, k_build<16>, g, BUILD_THREADS, d);
+    else if (minb == 6) LAUNCH(c, k_build<6>, g, BUILD_THREADS, d);
+    else LAUNCH(c, k_build<8>, g, BUILD_THREADS, d);
+  }
   if (direct) { LAUNCH(c, k_after_build, 1, 1, d); c->direct_builds++; }
 }
 
@@ -1029,7 +1040,8 @@ static int graph_add_unit(le_ctx *c, cudaGraph_t g, cudaGraphNode_t *tail, int a
     a.do_final = 1; a.do_initial = 1; a.langevin = c->langevin_on;
     void *sargs[] = {&d, &a};
     memset(&kp, 0, sizeof kp);
-    kp.func = c->nranks > 1 ? (void *)k_step<0, 1> : (void *)k_step<0, 0>; kp.gridDim = dim3(grid_for(c->d.gr0 - c->d.own0, STEP_THREADS)); kp.blockDim = dim3(STEP_THREADS); kp.kernelParams = sargs;
+    static const int minb = getenv("LE_STEP_MINB") ? atoi(getenv("LE_STEP_MINB")) : 4;
+    kp.func = c->nranks > 1 ? (void *)k_step<0, 1> : (minb == 5 ? (void *)k_step<0, 0, 5> : minb == 6 ? (void *)k_step<0, 0, 6> : minb == 3 ? (void *)k_step<0, 0, 3> : (void *)k_step<0, 0>); kp.gridDim = dim3(grid_for(c->d.gr0 - c->d.own0, STEP_THREADS)); kp.blockDim = dim3(STEP_THREADS); kp.kernelParams = sargs;
     cudaGraphNode_t ns;
     CKG(cudaGraphAddKernelNode(&ns, g, &nc, 1, &kp));
     *tail = ns;
@@ -1140,7 +1152,11 @@ static void launch_step(le_ctx *c, const StepArgs &a, bool ev) {
     if (ev) LAUNCH(c, (k_step<1, 1>), grid, STEP_THREADS, c->d, a);
     else LAUNCH(c, (k_step<0, 1>), grid, STEP_THREADS, c->d, a);
   } else {
+    static const int minb = getenv("LE_STEP_MINB") ? atoi(getenv("LE_STEP_MINB")) : 4;
     if (ev) LAUNCH(c, (k_step<1, 0>), grid, STEP_THREADS, c->d, a);
+    else if (minb == 5) LAUNCH(c, (k_step<0, 0, 5>), grid, STEP_THREADS, c->d, a);
+    else if (minb == 6) LAUNCH(c, (k_step<0, 0, 6>), grid, STEP_THREADS, c->d, a);
+    else if (minb == 3) LAUNCH(c, (k_step<0, 0, 3>), grid, STEP_THREADS, c->d, a);
     else LAUNCH(c, (k_step<0, 0>), grid, STEP_THREADS, c->d, a);
   }
 }
@@ -1360,6 +1376,51 @@ extern "C" int le_download_types(le_ctx *c, int *type) {
   CK(cudaStreamSynchronize(c->stream));
   for (int k = 0; k < n; k++) type[(hp[k].w >> 3) - 1] = (hp[k].w & 7) + 1;
   return LE_OK;
+}
+
+static int ensure_staging(le_ctx *c) {
+  if (c->st_tag) return LE_OK;
+  const size_t cap = c->d.cap;
+  int r;
+  if ((r = dalloc(c, &c->st_tag, cap))) return r;
+  if ((r = dalloc(c, &c->st_img, cap))) return r;
+  if ((r = dalloc(c, &c->st_x, cap * 3))) return r;
+  if ((r = dalloc(c, &c->st_v, cap * 3))) return r;
+  return LE_OK;
+}
+
+extern "C" int le_local_capacity(const le_ctx *c) { return c && c->atoms_loaded ? c->d.gr0 - c->d.own0 : 0; }
+
+extern "C" int le_download_owned(le_ctx *c, int *n_out, int *tag, double *x, int *image, double *v) {
+  if (!c || !n_out) return LE_EINVAL;
+  if (!c->atoms_loaded) return fail(c, LE_ESTATE, "no atoms");
+  cudaSetDevice(c->device);
+  int r = ensure_staging(c); if (r) return r;
+  int n; r = fetch_nown(c, &n); if (r) return r;
+  LAUNCH(c, k_pack_owned, grid_for(n, 256), 256, c->d, tag ? c->st_tag : nullptr, x ? c->st_x : nullptr, image ? c->st_img : nullptr, v ? c->st_v : nullptr);
+  if (tag) CK(cudaMemcpyAsync(tag, c->st_tag, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+  if (x) CK(cudaMemcpyAsync(x, c->st_x, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+  if (image) CK(cudaMemcpyAsync(image, c->st_img, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+  if (v) CK(cudaMemcpyAsync(v, c->st_v, sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  *n_out = n;
+  return LE_OK;
+}
+
+extern "C" int le_upload_owned(le_ctx *c, int n, const int *tag, const double *x, const int *image, const double *v) {
+  if (!c || !tag || n < 0) return LE_EINVAL;
+  if (!c->atoms_loaded) return fail(c, LE_ESTATE, "no atoms");
+  if (n > c->d.gr0 - c->d.own0) return fail(c, LE_EINVAL, "le_upload_owned: %d atoms exceed the local capacity %d", n, c->d.gr0 - c->d.own0);
+  cudaSetDevice(c->device);
+  int r = ensure_ready(c); if (r) return r;
+  if ((r = ensure_staging(c))) return r;
+  CK(cudaMemcpyAsync(c->st_tag, tag, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+  if (x) CK(cudaMemcpyAsync(c->st_x, x, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+  if (x && image) CK(cudaMemcpyAsync(c->st_img, image, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+  if (v) CK(cudaMemcpyAsync(c->st_v, v, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, c->stream));
+  LAUNCH(c, k_unpack_owned, grid_for(n, 256), 256, c->d, n, (const int *)c->st_tag, x ? (const double *)c->st_x : nullptr,
+         (x && image) ? (const int *)c->st_img : nullptr, v ? (const double *)c->st_v : nullptr);
+  return sync_and_check(c);
 }
 
 extern "C" int le_download_topology(le_ctx *c, int *num_bond, int *bond_type, int *bond_atom, int *nspecial, int *special) {

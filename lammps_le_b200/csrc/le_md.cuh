@@ -171,8 +171,8 @@ __device__ __forceinline__ int right_rank(const Dev &d) { return (d.rank + 1) % 
 #define STEP_NB 4     // neighbor slots fetched in the first batch
 #define STEP_BB 3     // bond slots fetched in the first batch
 
-template <int EV, int DD>
-__global__ void __launch_bounds__(STEP_THREADS, EV ? 2 : 4) k_step(Dev d, StepArgs a) {
+template <int EV, int DD, int MINB = 4>
+__global__ void __launch_bounds__(STEP_THREADS, EV ? 2 : MINB) k_step(Dev d, StepArgs a) {
   const int cap = d.cap;
   Ctrl *__restrict__ ctrl = d.ctrl;
   const int rd = ctrl->cur;
@@ -782,7 +782,8 @@ __device__ __forceinline__ void build_accept(const Dev &d, BuildCtx &B, const in
   B.n++;
 }
 
-__global__ void __launch_bounds__(BUILD_THREADS) k_build(Dev d) {
+template <int MINB>
+__global__ void __launch_bounds__(BUILD_THREADS, MINB) k_build(Dev d) {
   __shared__ int s_q[BUILD_QUEUE][BUILD_THREADS];
   const int cap = d.cap;
   const int cur = d.ctrl->cur;
@@ -915,4 +916,68 @@ __global__ void k_count_pairs(Dev d, unsigned long long *out) {
     f += __shfl_xor_sync(0xffffffffu, f, o);
   }
   if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], h); atomicAdd(&out[1], f); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host <-> device exchange of the atoms this GPU owns (le_download_owned / le_upload_owned): conversion between
+// the reference's doubles and the fixed-point / fp32 device state happens here, so the host only moves flat
+// buffers.  The quantisation is the one le_upload_atoms does on the host (nearest grid point; a coordinate
+// outside the box is wrapped and the wrap goes into the image flags, Domain::remap src/domain.cpp:1050-1110).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pack_owned(Dev d, int *tag, double *x, int *image, double *v) {
+  const int n = d.ctrl->nown;
+  const int4 *__restrict__ pos = d.pos[d.ctrl->cur];
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const int k = d.own0 + j;
+    const int4 p = pos[k];
+    if (tag) tag[j] = p.w >> 3;
+    if (x) {
+      x[3 * j] = le_deq((unsigned)p.x, 0); x[3 * j + 1] = le_deq((unsigned)p.y, 1); x[3 * j + 2] = le_deq((unsigned)p.z, 2);
+    }
+    if (image) image[j] = d.img[k];
+    if (v) { const float4 vv = d.vel[k]; v[3 * j] = vv.x; v[3 * j + 1] = vv.y; v[3 * j + 2] = vv.z; }
+  }
+}
+
+__global__ void k_unpack_owned(Dev d, int n, const int *tag, const double *x, const int *image, const double *v) {
+  int4 *__restrict__ pos = d.pos[d.ctrl->cur];
+  const int own_end = d.own0 + d.ctrl->nown;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const int t = tag[j];
+    const int k = (t >= 1 && t <= d.N) ? d.map[t - 1] : -1;
+    if (k < d.own0 || k >= own_end) { le_raise(d.ctrl, LE_DERR_MISSING_ATOM, t, k, 4); continue; }
+    if (x) {
+      int4 p = pos[k];
+      int w[3];
+      unsigned u[3];
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        const double f = __ddiv_rn(__dsub_rn(x[3 * j + q], c_P.lo[q]), c_P.L[q]);
+        const double fl = floor(f);
+        double uu = rint(__dmul_rn(__dsub_rn(f, fl), 4294967296.0));
+        int ww = (int)fl;
+        if (uu >= 4294967296.0) { uu -= 4294967296.0; ww += 1; }
+        u[q] = (unsigned)uu; w[q] = ww;
+      }
+      int ix, iy, iz;
+      if (image) {
+        const int im = image[j];
+        ix = (im & 1023) - 512 + w[0]; iy = ((im >> 10) & 1023) - 512 + w[1]; iz = ((im >> 20) & 1023) - 512 + w[2];
+      } else {
+        // no image flags given: keep the unwrapped trajectory continuous (nearest-image move)
+        const int im = d.img[k];
+        ix = (im & 1023) - 512 + le_image_shift((unsigned)p.x, u[0]);
+        iy = ((im >> 10) & 1023) - 512 + le_image_shift((unsigned)p.y, u[1]);
+        iz = ((im >> 20) & 1023) - 512 + le_image_shift((unsigned)p.z, u[2]);
+      }
+      d.img[k] = ((ix + 512) & 1023) | (((iy + 512) & 1023) << 10) | (((iz + 512) & 1023) << 20);
+      p.x = (int)u[0]; p.y = (int)u[1]; p.z = (int)u[2];
+      pos[k] = p;
+    }
+    if (v) {
+      float4 vv = d.vel[k];
+      vv.x = (float)v[3 * j]; vv.y = (float)v[3 * j + 1]; vv.z = (float)v[3 * j + 2];
+      d.vel[k] = vv;
+    }
+  }
 }

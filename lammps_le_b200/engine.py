@@ -78,6 +78,7 @@ def load_library():
         "le_download_bondlist": [P, pi, C.POINTER(I64)], "le_thermo_count": [P],
         "le_get_thermo": [P, I, C.POINTER(Thermo)], "le_get_stats": [P, C.POINTER(Stats)], "le_compute_rg": [P, pd],
         "le_gen_saw_chains": [I, I, D, D, D, C.c_uint64, pd, pi], "le_gen_lattice_melt": [I, I, D, pd, pd, pi],
+        "le_local_capacity": [P], "le_download_owned": [P, pi, pi, pd, pi, pd], "le_upload_owned": [P, I, pi, pd, pi, pd],
         "le_dd_init": [P, I, I, D], "le_dd_get_handle": [P, C.c_void_p], "le_dd_connect": [P, C.c_void_p],
         "le_get_thermo_sums": [P, I, pd], "le_get_force_sums": [P, pd],
     }
@@ -275,6 +276,26 @@ class Engine:
         if unwrap:
             x = x + unpack_image(im) * (self.boxhi - self.boxlo)
         return x, im
+
+    def owned_buffers(self, pinned=True):
+        """host buffers for download_owned / upload_owned: (tag[cap], x[cap,3], image[cap], v[cap,3])"""
+        cap = self.lib.le_local_capacity(self._h)
+        bufs = [np.zeros(cap, np.int32), np.zeros((cap, 3)), np.zeros(cap, np.int32), np.zeros((cap, 3))]
+        if pinned:
+            import torch
+            bufs = [torch.from_numpy(b).pin_memory().numpy() for b in bufs]
+        return tuple(bufs)
+
+    def download_owned(self, bufs):
+        """fill bufs (owned_buffers()) with the atoms this GPU owns; returns their number"""
+        tag, x, im, v = bufs
+        n = C.c_int()
+        self._ck(self.lib.le_download_owned(self._h, C.byref(n), _pi(tag), _pd(x), _pi(im), _pd(v)))
+        return n.value
+
+    def upload_owned(self, n, bufs):
+        tag, x, im, v = bufs
+        self._ck(self.lib.le_upload_owned(self._h, n, _pi(tag), _pd(x), _pi(im), _pd(v)))
 
     def velocities(self):
         v = np.zeros((self.natoms, 3))

@@ -107,3 +107,33 @@ def test_short_nve_trajectory_matches_reference():
     assert abs(th["etotal"] - rows[-1]["TotEng"]) < 2e-5 * abs(rows[-1]["TotEng"])
     assert abs(th["temp"] - rows[-1]["Temp"]) < 1e-4
     e.close()
+
+
+@pytest.mark.gpu
+def test_owned_bulk_exchange_roundtrip():
+    """le_download_owned / le_upload_owned (device-side double <-> fixed point) against the tag-order calls"""
+    from lammps_le_b200 import systems
+    s = systems.chromatin_chain(5000, 50, rho=0.2, seed=3)
+    v = systems.maxwell_velocities(5000, 1.0, np.ones(5000), 2)
+    e = systems.make_engine(s, velocities=v)
+    e.fix_nve(True); e.fix_langevin(1.0, 1.0, 1.0, 77)
+    e.run(50)
+    x, im = e.positions(); vv = e.velocities()
+    bufs = e.owned_buffers(pinned=False)
+    n = e.download_owned(bufs)
+    tag, xb, imb, vb = bufs
+    assert n == 5000 and sorted(tag[:n].tolist()) == list(range(1, 5001))
+    assert (xb[:n] == x[tag[:n] - 1]).all() and (imb[:n] == im[tag[:n] - 1]).all() and (vb[:n] == vv[tag[:n] - 1]).all()
+    # upload shifted coordinates (some leave the box) and compare with le_set_positions on a twin engine
+    L = s["box"][1][0]
+    xb[:n] += 0.37
+    e2 = systems.make_engine(s, velocities=v)
+    e2.fix_nve(True); e2.fix_langevin(1.0, 1.0, 1.0, 77)
+    e2.run(50)
+    xs = x + 0.37
+    e2.set_positions(xs, im)
+    e.upload_owned(n, bufs)
+    xa, ia = e.positions(); xc, ic = e2.positions()
+    assert (xa == xc).all() and (ia == ic).all()
+    assert (xa >= 0).all() and (xa < L).all()
+    e.close(); e2.close()
