@@ -101,6 +101,7 @@ REF_LE_LINES = ["fix loop all extrusion 500 1 2 3 0.5 2 4",
                 "fix unloading all ex_unload 100 2 0.5 prob 0.05 456456"]
 
 
+NCU_TRAFFIC_PER_LAUNCH = 99.3e6   # bytes: 87.8 MB read + 11.5 MB written per k_step<0> launch at 1M beads (ncu capture of round 1)
 LE_HALO = 6.2   # ghost shell for USER-LE on several GPUs: longest extruder bond (FENE R0 = 4) + one backbone bond + skin
 
 
@@ -192,6 +193,11 @@ def run_ours(args):
     total_atom_steps = world * n_beads * md * args.steps
     value = total_atom_steps / t_gpu
 
+    # ---- live duration of the dominant kernel: a short run with direct launches and CUDA events around k_step<0>
+    # on the engine's own stream (steps without USER-LE event) ----
+    kstep_us = e.run_timed(40)
+    e.run(md - 40)            # complete the cycle so that the next segment starts at the same USER-LE phase
+
     # ---- end to end through the C ABI with HOST buffers: every step uploads positions + velocities of the atoms the GPU
     # owns from pinned host memory (le_upload_owned), runs, and downloads them again (le_download_owned) ----
     bufs = e.owned_buffers(pinned=True)
@@ -233,7 +239,8 @@ def run_ours(args):
     bytes_step = 72.1 + 4.0 * nbar_half                      # SURVEY.md 8(d) algorithmic bytes per atom-step
     bytes_amort = bytes_step + (40.0 + 4.0 * nbar_half) / kint
     peak, how = measured_peak_gbs()
-    achieved = bytes_amort * n_beads * steps_timed / t_gpu / 1e9          # per GPU
+    whole_step = bytes_amort * n_beads * steps_timed / t_gpu / 1e9        # per GPU, everything amortised (rebuilds, USER-LE)
+    achieved = bytes_step * n_beads / (kstep_us * 1e-6) / 1e9             # the step kernel alone: algorithmic bytes / its duration
     line = {
         "metric": "atom-steps/s", "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_gpu / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -249,8 +256,11 @@ def run_ours(args):
         "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": how, "bytes_per_atom_step": bytes_amort,
-                     "kernel": "k_step<0> (+ amortised rebuild kernels)"},
+                     "traffic": NCU_TRAFFIC_PER_LAUNCH if n_beads == 1000000 else None, "peak_source": how,
+                     "kernel": "k_step<0>", "kernel_us": kstep_us, "bytes_per_atom_step": bytes_step,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_step<0> launch, ncu --set full, profiles/r01_ncu_full_kstep_kbuild.txt",
+                     "whole_step": {"achieved": whole_step, "frac": whole_step / peak, "bytes_per_atom_step": bytes_amort,
+                                    "note": "72.1 + 4 nbar + (40 + 4 nbar)/K bytes per atom-step over the whole timed loop (rebuilds and USER-LE included)"}},
         "wall_s": t_wall, "user_le_ms_per_md_step": le_ms / steps_timed,
         "le_events": {"shifts": st1["extrusion_shifts"] - st0["extrusion_shifts"], "loads": st1["loads"] - st0["loads"],
                       "unloads": st1["unloads"] - st0["unloads"]},

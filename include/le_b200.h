@@ -136,6 +136,9 @@ int le_set_velocities(le_ctx *c, const double *v);
 /* ---- run ------------------------------------------------------------------------------- */
 int le_run(le_ctx *c, int64_t nsteps);                      /* run N */
 int le_force_rebuild(le_ctx *c);                            /* Neighbor::build(1) now */
+/* le_run with direct launches and an event before every launch; *kstep_us = average duration of the plain step
+ * kernel (launch to next launch on the stream), for live roofline measurements */
+int le_run_timed(le_ctx *c, int64_t nsteps, double *kstep_us);
 /* run one USER-LE fix's post_integrate on the current state, regardless of the step gate */
 int le_run_le_event(le_ctx *c, int which);
 /* skip n draws of that fix's Marsaglia stream / re-seed it (state replay) */

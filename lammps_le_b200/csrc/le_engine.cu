@@ -74,6 +74,7 @@ struct le_ctx {
   int64_t nbonds;
   le_stats stats;
   cudaEvent_t ev0, ev1;
+  bool timing_quiet, force_direct; double kstep_avg_ms;
   bool timing; std::vector<cudaEvent_t> tm_ev; std::vector<const char *> tm_name; size_t tm_used;
   std::vector<cudaEvent_t> le_ev;       // pairs of events around the USER-LE kernels of the current run
   size_t le_ev_used;
@@ -113,6 +114,14 @@ static void time_report(le_ctx *c) {
   if (!c->timing || c->tm_used < 2) { c->tm_used = 0; c->tm_name.clear(); return; }
   time_mark(c, "(end)");
   cudaStreamSynchronize(c->stream);
+  {
+    // average launch-to-next-launch time of the plain step kernel (le_run_timed)
+    double sum = 0; int n = 0;
+    for (size_t k = 0; k + 1 < c->tm_used; k++)
+      if (!strncmp(c->tm_name[k], "(k_step<0", 9)) { float ms = 0.f; cudaEventElapsedTime(&ms, c->tm_ev[k], c->tm_ev[k + 1]); sum += ms; n++; }
+    c->kstep_avg_ms = n ? sum / n : 0.0;
+  }
+  if (c->timing_quiet) { c->tm_used = 0; c->tm_name.clear(); return; }
   std::vector<std::pair<std::string, std::pair<double, int>>> acc;
   for (size_t k = 0; k + 1 < c->tm_used; k++) {
     float ms = 0.f;
@@ -188,6 +197,7 @@ extern "C" int le_create(le_ctx **out, int device, const double boxlo[3], const 
   cudaEventCreate(&c->ev1);
   c->le_ev_used = 0;
   { const char *tm = getenv("LE_B200_TIMING"); c->timing = tm && tm[0] == '1'; c->tm_used = 0; }
+  c->timing_quiet = false; c->force_direct = false; c->kstep_avg_ms = 0.0;
   for (int k = 0; k < 3; k++) {
     c->lo[k] = boxlo[k]; c->hi[k] = boxhi[k]; c->periodic[k] = periodic[k];
   }
@@ -1255,7 +1265,7 @@ extern "C" int le_run(le_ctx *c, int64_t nsteps) {
   if ((r = force_eval(begin))) return r;
   int64_t s = begin;
   const char *dm = getenv("LE_B200_DIRECT");
-  const bool direct_mode = dm && dm[0] == '1';
+  const bool direct_mode = (dm && dm[0] == '1') || c->force_direct;
   while (s < end) {
     if (direct_mode) {
       // profiling path (LE_B200_DIRECT=1): ncu cannot see kernel nodes of graphs that hold conditional nodes, so
@@ -1535,6 +1545,19 @@ extern "C" int le_get_thermo_sums(const le_ctx *c, int index, double *out16) {
   if (index < 0 || index >= n) return LE_EINVAL;
   for (int k = 0; k < LE_THERMO_W; k++) out16[k] = c->thermo_sums[index][k];
   return LE_OK;
+}
+
+/* le_run with every kernel launched directly and an event in front of each launch; *kstep_us = average time from the
+ * launch of the plain step kernel k_step<0> to the next launch on the stream (= its duration; bench.py's live
+ * roofline measurement).  Same results as le_run. */
+extern "C" int le_run_timed(le_ctx *c, int64_t nsteps, double *kstep_us) {
+  if (!c || !kstep_us) return LE_EINVAL;
+  const bool t0 = c->timing, q0 = c->timing_quiet;
+  c->timing = true; c->timing_quiet = !t0; c->force_direct = true;
+  const int r = le_run(c, nsteps);
+  c->timing = t0; c->timing_quiet = q0; c->force_direct = false;
+  *kstep_us = 1e3 * c->kstep_avg_ms;
+  return r;
 }
 
 extern "C" int le_get_force_sums(const le_ctx *c, double *out16) {

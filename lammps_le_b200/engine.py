@@ -70,7 +70,7 @@ def load_library():
         "le_fix_ex_load": [P, I, I, I, D, I, D, I, I, I, I, I], "le_fix_ex_unload": [P, I, I, D, D, I],
         "le_unfix": [P, I], "le_upload_atoms": [P, I, pi, pi, pd, pd, pi], "le_upload_bonds": [P, I, pi, pi, pi],
         "le_upload_topology": [P, pi, pi, pi, pi, pi], "le_set_positions": [P, pd, pi], "le_set_velocities": [P, pd],
-        "le_run": [P, I64], "le_force_rebuild": [P], "le_run_le_event": [P, I],
+        "le_run": [P, I64], "le_run_timed": [P, I64, pd], "le_force_rebuild": [P], "le_run_le_event": [P, I],
         "le_fix_rng_reset": [P, I, I, I64], "le_fix_rng_consumed": [P, I, C.POINTER(I64)],
         "le_compute_forces": [P, pd, C.POINTER(Thermo)], "le_natoms": [P], "le_download_x": [P, pd, pi],
         "le_download_v": [P, pd], "le_download_types": [P, pi], "le_download_topology": [P, pi, pi, pi, pi, pi],
@@ -237,6 +237,12 @@ class Engine:
     # ---- run ----
     def run(self, nsteps):
         self._ck(self.lib.le_run(self._h, nsteps))
+
+    def run_timed(self, nsteps):
+        """run with direct launches; returns the average duration (us) of the plain step kernel"""
+        us = C.c_double()
+        self._ck(self.lib.le_run_timed(self._h, nsteps, C.byref(us)))
+        return us.value
 
     def force_rebuild(self):
         self._ck(self.lib.le_force_rebuild(self._h))

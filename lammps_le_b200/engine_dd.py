@@ -88,6 +88,10 @@ class DDEngine(Engine):
         self.barrier()
         super().run(nsteps)
 
+    def run_timed(self, nsteps):
+        self.barrier()
+        return super().run_timed(nsteps)
+
     def force_rebuild(self):
         self.barrier()
         super().force_rebuild()
