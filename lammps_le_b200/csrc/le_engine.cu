@@ -1051,7 +1051,10 @@ static int graph_add_unit(le_ctx *c, cudaGraph_t g, cudaGraphNode_t *tail, int a
     void *sargs[] = {&d, &a};
     memset(&kp, 0, sizeof kp);
     static const int minb = getenv("LE_STEP_MINB") ? atoi(getenv("LE_STEP_MINB")) : 4;
-    kp.func = c->nranks > 1 ? (void *)k_step<0, 1> : (minb == 5 ? (void *)k_step<0, 0, 5> : minb == 6 ? (void *)k_step<0, 0, 6> : minb == 3 ? (void *)k_step<0, 0, 3> : (void *)k_step<0, 0>); kp.gridDim = dim3(grid_for(c->d.gr0 - c->d.own0, STEP_THREADS)); kp.blockDim = dim3(STEP_THREADS); kp.kernelParams = sargs;
+    const bool uni = c->P.pair_uniform != 0;
+    kp.func = c->nranks > 1 ? (uni ? (void *)k_step<0, 1, 4, 1> : (void *)k_step<0, 1>)
+                            : (minb == 5 ? (void *)k_step<0, 0, 5> : minb == 6 ? (void *)k_step<0, 0, 6> : minb == 3 ? (void *)k_step<0, 0, 3>
+                               : uni ? (void *)k_step<0, 0, 4, 1> : (void *)k_step<0, 0>); kp.gridDim = dim3(grid_for(c->d.gr0 - c->d.own0, STEP_THREADS)); kp.blockDim = dim3(STEP_THREADS); kp.kernelParams = sargs;
     cudaGraphNode_t ns;
     CKG(cudaGraphAddKernelNode(&ns, g, &nc, 1, &kp));
     *tail = ns;
@@ -1158,8 +1161,10 @@ static void thermo_from_slot(le_ctx *c, const double *s, int64_t step, le_thermo
 
 static void launch_step(le_ctx *c, const StepArgs &a, bool ev) {
   const int grid = grid_for(c->d.gr0 - c->d.own0, STEP_THREADS);
+  const bool uni = c->P.pair_uniform != 0;
   if (c->nranks > 1) {
     if (ev) LAUNCH(c, (k_step<1, 1>), grid, STEP_THREADS, c->d, a);
+    else if (uni) LAUNCH(c, (k_step<0, 1, 4, 1>), grid, STEP_THREADS, c->d, a);
     else LAUNCH(c, (k_step<0, 1>), grid, STEP_THREADS, c->d, a);
   } else {
     static const int minb = getenv("LE_STEP_MINB") ? atoi(getenv("LE_STEP_MINB")) : 4;
@@ -1167,6 +1172,7 @@ static void launch_step(le_ctx *c, const StepArgs &a, bool ev) {
     else if (minb == 5) LAUNCH(c, (k_step<0, 0, 5>), grid, STEP_THREADS, c->d, a);
     else if (minb == 6) LAUNCH(c, (k_step<0, 0, 6>), grid, STEP_THREADS, c->d, a);
     else if (minb == 3) LAUNCH(c, (k_step<0, 0, 3>), grid, STEP_THREADS, c->d, a);
+    else if (uni) LAUNCH(c, (k_step<0, 0, 4, 1>), grid, STEP_THREADS, c->d, a);
     else LAUNCH(c, (k_step<0, 0>), grid, STEP_THREADS, c->d, a);
   }
 }

@@ -56,7 +56,7 @@ struct ExtrusionArgs { int btype, neutral, left, right, lr; double p; };
 struct LoadArgs { int btype, itype, jtype, imax, inew, jmax, jnew; double cutsq, fraction; };
 struct UnloadArgs { int btype; double cutsq, fraction; };
 
-enum { CNT_NTASK = 0, CNT_NDRAW = 1, CNT_NBREAK = 2, CNT_NCREATE = 3, CNT_TOTAL = 4 };
+enum { CNT_NTASK = 0, CNT_NDRAW = 1, CNT_NBREAK = 2, CNT_NCREATE = 3, CNT_TOTAL = 4, CNT_NLIST = 5 };
 
 static int le_fix_alloc(LeFixDev &f, int n, int maxspecial, std::vector<void *> &allocs, cudaStream_t st) {
   f.N = n;
@@ -236,42 +236,27 @@ __global__ void k_iscan_partial(const int *in, int n, int *blocksum) {
     if (threadIdx.x == 0) blocksum[blockIdx.x] = t;
   }
 }
-__global__ void k_iscan_blocks(int *blocksum, int nblocks, int *total) {
-  __shared__ int sh[1024];
+__global__ void __launch_bounds__(1024) k_iscan_blocks(int *blocksum, int nblocks, int *total) {
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   for (int base = 0; base < nblocks; base += 1024) {
     const int idx = base + threadIdx.x;
     const int v = (idx < nblocks) ? blocksum[idx] : 0;
-    sh[threadIdx.x] = v;
+    int tot;
+    const int ex = block_excl_scan(v, &tot);
+    if (idx < nblocks) blocksum[idx] = carry + ex;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-      int t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
-      __syncthreads();
-      sh[threadIdx.x] += t;
-      __syncthreads();
-    }
-    if (idx < nblocks) blocksum[idx] = carry + sh[threadIdx.x] - v;
-    __syncthreads();
-    if (threadIdx.x == 0) carry += sh[1023];
+    if (threadIdx.x == 0) carry += tot;
     __syncthreads();
   }
   if (threadIdx.x == 0 && total) *total = carry;
 }
-__global__ void k_iscan_apply(const int *in, int *out, int n, const int *blocksum) {
-  __shared__ int sh[1024];
+__global__ void __launch_bounds__(1024) k_iscan_apply(const int *in, int *out, int n, const int *blocksum) {
   const int idx = blockIdx.x * 1024 + threadIdx.x;
   const int v = (idx < n) ? in[idx] : 0;
-  sh[threadIdx.x] = v;
-  __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {
-    int t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
-    __syncthreads();
-    sh[threadIdx.x] += t;
-    __syncthreads();
-  }
-  if (idx < n) out[idx] = blocksum[blockIdx.x] + sh[threadIdx.x] - v;
+  const int ex = block_excl_scan(v, nullptr);
+  if (idx < n) out[idx] = blocksum[blockIdx.x] + ex;
 }
 // tasks[scan[i]] = i for flagged i (flag value > 0)
 __global__ void k_compact(const int *flag, const int *scan, int n, int *tasks) {
@@ -532,10 +517,13 @@ __device__ void rebuild_special_one(const Dev &d, int t) {
 // update_topology sweeps (fix_extrusion.cpp:924-1002, fix_ex_load.cpp:700-751, fix_ex_unload.cpp:417-463).
 // mode 0: broken bonds, marks = final_remove: influenced if endpoint, or BOTH ends of one broken bond are in
 //         the full special list;  mode 1: created bonds, marks = final_add: endpoint, or EITHER end among 1-2/1-3.
-__global__ void k_le_topo_sweep(Dev d, const int *marks, int mode, const int *gate) {
+// Two kernels: a light sweep over all tags that only DETECTS the influenced atoms and appends them to a list
+// (few registers, full occupancy, streams the tables once), then rebuild_special_one over that short list (the
+// rebuilds commute: each writes only its own atom's 1-3/1-4 tiers and reads only 1-2 tiers, which no rebuild
+// touches).
+__global__ void k_le_topo_detect(Dev d, const int *marks, int mode, const int *gate, int *list, int *nlist) {
   if (gate && *gate == 0) return;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) {
-    const int t = i + 1;
     bool infl = marks[i] != 0;
     if (!infl) {
       const int *sl = d.special + (size_t)i * d.maxspecial;
@@ -554,9 +542,14 @@ __global__ void k_le_topo_sweep(Dev d, const int *marks, int mode, const int *ga
         for (int k = 0; k < n; k++) if (marks[sl[k] - 1] != 0) { infl = true; break; }
       }
     }
-    if (infl) rebuild_special_one(d, t);
+    if (infl) list[atomicAdd(nlist, 1)] = i + 1;
   }
 }
+__global__ void k_le_topo_rebuild(Dev d, const int *list, int *nlist) {
+  const int n = *nlist;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) rebuild_special_one(d, list[k]);
+}
+__global__ void k_le_topo_reset(int *nlist) { *nlist = 0; }
 
 // ------------------------------------------------------------------------------------------------
 // fix extrusion

@@ -123,6 +123,16 @@ static void run_executor(le_ctx *c, const Task &T, unsigned base) {
   LAUNCH(c, k_exec_finish<Task>, 1, LE_EXEC_THREADS, T, f.claim, f.done, (const int *)f.exec_rem, base);
 }
 
+// update_topology sweep: detect the influenced atoms (light, all tags), rebuild their special lists (short list)
+static void topo_sweep(le_ctx *c, const int *marks, int mode) {
+  LeFixDev &f = c->lf;
+  int *nlist = f.counters + CNT_NLIST;
+  const int *gate = (const int *)(f.counters + CNT_TOTAL);
+  LAUNCH(c, k_le_topo_reset, 1, 1, nlist);
+  LAUNCH(c, k_le_topo_detect, std::min(grid_for(c->N, 256), 148 * 8), 256, c->d, marks, mode, gate, f.tasks, nlist);
+  LAUNCH(c, k_le_topo_rebuild, 296, 128, c->d, (const int *)f.tasks, nlist);
+}
+
 static int enqueue_extrusion(le_ctx *c) {
   int r = ensure_rng(c, 0, c->fx.seed); if (r) return r;
   LeFixDev &f = c->lf;
@@ -147,9 +157,8 @@ static int enqueue_extrusion(le_ctx *c) {
   run_executor(c, BreakTask{V, (const int *)(f.counters + CNT_NTASK)}, 2u * LE_EXEC_BASE_STRIDE);
   LAUNCH(c, k_ext_create, g, 256, V, A.btype);
   LAUNCH(c, k_le_finish, 1, 1, c->d, f, 1);
-  const int gs = grid_for(c->N, 128);
-  LAUNCH(c, k_le_topo_sweep, gs, 128, c->d, (const int *)f.final_remove, 0, (const int *)(f.counters + CNT_TOTAL));
-  LAUNCH(c, k_le_topo_sweep, gs, 128, c->d, (const int *)f.final_add, 1, (const int *)(f.counters + CNT_TOTAL));
+  topo_sweep(c, (const int *)f.final_remove, 0);
+  topo_sweep(c, (const int *)f.final_add, 1);
   return LE_OK;
 }
 
@@ -166,7 +175,7 @@ static int enqueue_unload(le_ctx *c) {
   if (A.fraction < 1.0) draw_for_flagged(c, 1, A.fraction);
   LAUNCH(c, k_unl_break, g, 256, V, A);
   LAUNCH(c, k_le_finish, 1, 1, c->d, f, 2);
-  LAUNCH(c, k_le_topo_sweep, grid_for(c->N, 128), 128, c->d, (const int *)f.final_remove, 0, (const int *)(f.counters + CNT_TOTAL));
+  topo_sweep(c, (const int *)f.final_remove, 0);
   return LE_OK;
 }
 
@@ -192,7 +201,7 @@ static int enqueue_load(le_ctx *c) {
   if (A.fraction < 1.0) draw_for_flagged(c, 2, A.fraction);
   LAUNCH(c, k_load_create, g, 256, V, A);
   LAUNCH(c, k_le_finish, 1, 1, c->d, f, 3);
-  LAUNCH(c, k_le_topo_sweep, grid_for(c->N, 128), 128, c->d, (const int *)f.final_add, 1, (const int *)(f.counters + CNT_TOTAL));
+  topo_sweep(c, (const int *)f.final_add, 1);
   return LE_OK;
 }
 

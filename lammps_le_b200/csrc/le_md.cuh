@@ -55,25 +55,26 @@ __device__ __noinline__ double harmonic_fbond(double rsq, double k, double r0, d
 }
 
 // fp32 screen of one listed pair on the exact fixed-point differences: inside (a hair more than) the force cutoff?
+template <int UNI>
 __device__ __forceinline__ bool pair_screen(const int4 pi, const int4 pj, int ti, int nt, float sx, float sy, float sz) {
   const int idx = (int)((unsigned)pi.x - (unsigned)pj.x);
   const int idy = (int)((unsigned)pi.y - (unsigned)pj.y);
   const int idz = (int)((unsigned)pi.z - (unsigned)pj.z);
   const float dxf = (float)idx * sx, dyf = (float)idy * sy, dzf = (float)idz * sz;
   const float rsqf = dxf * dxf + dyf * dyf + dzf * dzf;
-  const int tp = c_P.pair_uniform ? 0 : ti * nt + (pj.w & 7);
+  const int tp = UNI ? 0 : ti * nt + (pj.w & 7);      // UNI: one coefficient set for all type pairs -> immediate constant operands
   return rsqf < c_P.cutsq_screen[tp];
 }
 
 // the (few) pairs inside the force cutoff are evaluated in fp64: r^-14 amplifies a 1e-7 error of r^2 sevenfold and
 // the WCA/FENE terms of bonded neighbours cancel to ~10% of their size, so fp32 pair math cannot meet the 1e-5
 // per-atom bar
-template <int EV>
+template <int EV, int UNI>
 __device__ __forceinline__ void pair_term(ForceAcc &A, const int4 pi, const int4 pj, unsigned e, int ti, int nt) {
   const int idx = (int)((unsigned)pi.x - (unsigned)pj.x);
   const int idy = (int)((unsigned)pi.y - (unsigned)pj.y);
   const int idz = (int)((unsigned)pi.z - (unsigned)pj.z);
-  const int tp = c_P.pair_uniform ? 0 : ti * nt + (pj.w & 7);
+  const int tp = UNI ? 0 : ti * nt + (pj.w & 7);
   const double dx = (double)idx * c_P.scale[0], dy = (double)idy * c_P.scale[1], dz = (double)idz * c_P.scale[2];
   const double rsq = dx * dx + dy * dy + dz * dz;
   if (rsq < c_P.cutsq_d[tp]) {
@@ -171,7 +172,7 @@ __device__ __forceinline__ int right_rank(const Dev &d) { return (d.rank + 1) % 
 #define STEP_NB 4     // neighbor slots fetched in the first batch
 #define STEP_BB 3     // bond slots fetched in the first batch
 
-template <int EV, int DD, int MINB = 4>
+template <int EV, int DD, int MINB = 4, int UNI = 0>
 __global__ void __launch_bounds__(STEP_THREADS, EV ? 2 : MINB) k_step(Dev d, StepArgs a) {
   const int cap = d.cap;
   Ctrl *__restrict__ ctrl = d.ctrl;
@@ -232,20 +233,20 @@ __global__ void __launch_bounds__(STEP_THREADS, EV ? 2 : MINB) k_step(Dev d, Ste
     unsigned hit = 0;
 #pragma unroll
     for (int k = 0; k < STEP_NB; k++)
-      if (k < nn && pair_screen(pi, pn[k], ti, nt, sx, sy, sz)) hit |= 1u << k;
+      if (k < nn && pair_screen<UNI>(pi, pn[k], ti, nt, sx, sy, sz)) hit |= 1u << k;
     for (int k = STEP_NB; k < nn; k += 2) {          // rows beyond the first batch, two at a time
       const int k1 = min(k + 1, nn - 1);
       const unsigned e0 = __ldg(&neigh[(size_t)k * cap + i]), e1 = __ldg(&neigh[(size_t)k1 * cap + i]);
       const int4 p0 = __ldg(&posr[e0 & NEIGH_IDX_MASK]), p1 = __ldg(&posr[e1 & NEIGH_IDX_MASK]);
-      if (pair_screen(pi, p0, ti, nt, sx, sy, sz)) pair_term<EV>(A, pi, p0, e0, ti, nt);
-      if (k1 > k && pair_screen(pi, p1, ti, nt, sx, sy, sz)) pair_term<EV>(A, pi, p1, e1, ti, nt);
+      if (pair_screen<UNI>(pi, p0, ti, nt, sx, sy, sz)) pair_term<EV, UNI>(A, pi, p0, e0, ti, nt);
+      if (k1 > k && pair_screen<UNI>(pi, p1, ti, nt, sx, sy, sz)) pair_term<EV, UNI>(A, pi, p1, e1, ti, nt);
     }
     while (hit) {
       const int k = __ffs(hit) - 1;
       hit &= hit - 1;
       const unsigned e = k == 0 ? en[0] : k == 1 ? en[1] : k == 2 ? en[2] : en[3];
       const int4 pj = __ldg(&posr[e & NEIGH_IDX_MASK]);     // second touch: an L1 hit
-      pair_term<EV>(A, pi, pj, e, ti, nt);
+      pair_term<EV, UNI>(A, pi, pj, e, ti, nt);
     }
 #pragma unroll
     for (int m = 0; m < STEP_BB; m++)
