@@ -1250,6 +1250,7 @@ extern "C" int le_run(le_ctx *c, int64_t nsteps) {
     a.do_final = (s > begin);
     a.do_initial = (s < end);
     a.langevin = c->langevin_on;
+    { static const int skip = getenv("LE_STEP_SKIP") ? atoi(getenv("LE_STEP_SKIP")) : 0; a.skip = skip & 15; if (skip & 16) a.langevin = 0; }
     bool ev = false;
     if (want_thermo(s)) {
       if (used_slots == THERMO_SLOTS) {

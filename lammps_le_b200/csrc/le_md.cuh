@@ -13,6 +13,7 @@ struct StepArgs {
   int slot;           // thermo slot to tally energy / virial / kinetic energy into (EV kernels)
   int write_force;    // store the conservative force of every atom in fout (tag order)
   int langevin;       // add drag + noise
+  int skip;           // development only (LE_STEP_SKIP): 1 no gathers, 2 no pair evaluation, 4 no bonds, 8 no neighbor rows
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -211,15 +212,17 @@ __global__ void __launch_bounds__(STEP_THREADS, EV ? 2 : MINB) k_step(Dev d, Ste
 #pragma unroll
     for (int m = 0; m < STEP_BB; m++) eb[m] = (m < d.bpa) ? __ldg(&bondrow[(size_t)m * cap + i]) : 0u;
     const int4 ph = d.pos_hold[i];
-    const int nn = cnt & 0xff, nb = (cnt >> 16) & 0xff;
+    int nn = cnt & 0xff, nb = (cnt >> 16) & 0xff;
+    if (a.skip & 8) nn = 0;
+    if (a.skip & 4) nb = 0;
     const int ti = pi.w & 7;
     const int tag = pi.w >> 3;
     // ---- batch 2: the gathers ----
     int4 pn[STEP_NB], pb[STEP_BB];
 #pragma unroll
-    for (int k = 0; k < STEP_NB; k++) pn[k] = __ldg(&posr[(k < nn) ? (int)(en[k] & NEIGH_IDX_MASK) : i]);
+    for (int k = 0; k < STEP_NB; k++) pn[k] = __ldg(&posr[(k < nn && !(a.skip & 1)) ? (int)(en[k] & NEIGH_IDX_MASK) : i]);
 #pragma unroll
-    for (int m = 0; m < STEP_BB; m++) pb[m] = __ldg(&posr[(m < nb) ? (int)(eb[m] & BOND_IDX_MASK) : i]);
+    for (int m = 0; m < STEP_BB; m++) pb[m] = __ldg(&posr[(m < nb && !(a.skip & 1)) ? (int)(eb[m] & BOND_IDX_MASK) : i]);
 
     ForceAcc A;
     A.fx = A.fy = A.fz = 0.0;
@@ -241,6 +244,7 @@ __global__ void __launch_bounds__(STEP_THREADS, EV ? 2 : MINB) k_step(Dev d, Ste
       if (pair_screen<UNI>(pi, p0, ti, nt, sx, sy, sz)) pair_term<EV, UNI>(A, pi, p0, e0, ti, nt);
       if (k1 > k && pair_screen<UNI>(pi, p1, ti, nt, sx, sy, sz)) pair_term<EV, UNI>(A, pi, p1, e1, ti, nt);
     }
+    if (a.skip & 2) hit = 0;
     while (hit) {
       const int k = __ffs(hit) - 1;
       hit &= hit - 1;
