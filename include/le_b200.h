@@ -174,6 +174,14 @@ int le_get_thermo(const le_ctx *c, int index, le_thermo *out); /* index < 0 coun
 int le_get_stats(le_ctx *c, le_stats *out);
 /* radius of gyration of the whole system from unwrapped coordinates (compute gyration) */
 int le_compute_rg(le_ctx *c, double *rg);
+/* polymer observables tallied on the device over the atoms this GPU owns (multi-GPU: sum the outputs over ranks):
+ *   rg_sums[5]   = sum m, sum m x, sum m y, sum m z, sum m |x|^2 of the UNWRAPPED coordinates
+ *                  (compute gyration, src/compute_gyration.cpp:60-100: Rg^2 = S4/S0 - |S1..3/S0|^2)
+ *   contacts[ns] = number of bead pairs (t, t + s_list[k]) closer than rc (minimum image; tags are chain positions)
+ *   loop_hist[nbins] = histogram of b - a over the bonds (a < b) of type btype, bins of bin_width, last bin = overflow
+ *                  (the loops; compute property/local batom1 batom2 btype, src/compute_property_local.cpp:104-117) */
+int le_observables(le_ctx *c, int ns, const int *s_list, double rc, int btype, int nbins, int bin_width,
+                   double *rg_sums, int64_t *contacts, int64_t *loop_hist);
 
 /* ---- several GPUs of one box: spatial domain decomposition (Comm/CommBrick, src/comm_brick.cpp:452-876) -----------
  * One process (and one le_ctx) per GPU.  The box is cut into x-slabs of neighbor cells; each GPU owns one slab plus

@@ -90,6 +90,7 @@ struct le_ctx {
   // domain decomposition (x-slabs, one GPU per rank); nranks == 1: the whole box on this GPU
   int nranks, rank;
   double halo_dist;
+  std::vector<int> xcut;                // slab boundaries in x-cells, [nranks + 1]; empty = equal numbers of cell layers
   void *arena; size_t arena_bytes;      // peer-visible allocation (CUDA IPC): pos, pos_hold, cell_start, inbox, flags, geo
   void *peer_base[LE_MAXRANKS];
   bool peers_open;
@@ -471,11 +472,12 @@ static int setup_cells(le_ctx *c, double cutneighmax) {
     const double hd = c->halo_dist > cutneighmax ? c->halo_dist : cutneighmax;
     d.halo = (int)ceil(hd / cw - 1e-9);
     if (d.halo < 1) d.halo = 1;
+    const bool cuts = (int)c->xcut.size() == Pn + 1 && c->xcut[Pn] == ncx;
+    auto X = [&](int r) { return cuts ? c->xcut[r] : (int)((long long)r * ncx / Pn); };
     int wmin = ncx;
-    for (int r = 0; r < Pn; r++) wmin = std::min(wmin, (int)((long long)(r + 1) * ncx / Pn - (long long)r * ncx / Pn));
+    for (int r = 0; r < Pn; r++) wmin = std::min(wmin, X(r + 1) - X(r));
     if (wmin < 2 * d.halo + 1)
       return fail(c, LE_EINVAL, "multi-GPU: a slab of %d cell layers is too thin for a halo of %d layers (box too small for %d GPUs)", wmin, d.halo, Pn);
-    auto X = [&](int r) { return (int)((long long)r * ncx / Pn); };
     d.X0 = X(c->rank); d.X1 = X(c->rank + 1);
     d.nlx = d.X1 - d.X0 + 2 * d.halo;
     const int rl = (c->rank + Pn - 1) % Pn, rr = (c->rank + 1) % Pn;
@@ -648,7 +650,9 @@ static void peer_view(PeerView *v, void *base, const ArenaLayout &a) {
 static ArenaLayout ctx_layout(const le_ctx *c) {
   const Dev &d = c->d;
   const int ncx = d.ncell[0], Pn = c->nranks;
-  const int nlx_max = (ncx + Pn - 1) / Pn + 2 * d.halo;
+  int wmax = (ncx + Pn - 1) / Pn;
+  if ((int)c->xcut.size() == Pn + 1) for (int r = 0; r < Pn; r++) wmax = std::max(wmax, c->xcut[r + 1] - c->xcut[r]);
+  const int nlx_max = wmax + 2 * d.halo;
   return arena_layout(d.cap, nlx_max * d.ncell[1] * d.ncell[2] + 3, d.inbox_cap, d.N);
 }
 
@@ -695,9 +699,26 @@ extern "C" int le_upload_atoms(le_ctx *c, int n, const int *tag, const int *type
     const int ncx = d.ncell[0], Pn = c->nranks, H = d.halo;
     std::vector<long long> per_layer(ncx, 0);
     for (int t = 0; t < n; t++) per_layer[(int)(((unsigned long long)(unsigned)hp[t].x * (unsigned)ncx) >> 32)]++;
+    // static load balance (the job of `balance 1.0 shift x`, src/balance.cpp, done once on the initial distribution):
+    // cut where the cumulative atom count crosses r N / P, keeping every slab at least 2 halo + 1 layers wide
+    {
+      const int wmin = 2 * H + 1;
+      c->xcut.assign(Pn + 1, 0);
+      c->xcut[Pn] = ncx;
+      long long cum = 0; int xq = 0;
+      for (int rk = 1; rk < Pn; rk++) {
+        const long long target = (long long)n * rk / Pn;
+        while (xq < ncx && cum + per_layer[xq] <= target) cum += per_layer[xq++];
+        int cut = xq;
+        cut = std::max(cut, c->xcut[rk - 1] + wmin);
+        cut = std::min(cut, ncx - (Pn - rk) * wmin);
+        c->xcut[rk] = cut;
+      }
+      if ((r = build_params(c))) return r;       // slabs of this rank and its neighbors from the cuts
+    }
     long long maxown = 0, maxghost = 0;
     for (int rk = 0; rk < Pn; rk++) {
-      const int x0 = (int)((long long)rk * ncx / Pn), x1 = (int)((long long)(rk + 1) * ncx / Pn);
+      const int x0 = c->xcut[rk], x1 = c->xcut[rk + 1];
       long long own = 0, gl = 0, gr = 0;
       for (int q = x0; q < x1; q++) own += per_layer[q];
       for (int q = 0; q < H; q++) { gl += per_layer[x0 + q]; gr += per_layer[x1 - 1 - q]; }
@@ -1587,6 +1608,35 @@ extern "C" int le_get_stats(le_ctx *c, le_stats *out) {
     c->stats.half_pairs = (int64_t)h[1] / 2; c->stats.full_entries = (int64_t)h[1];
   }
   *out = c->stats;
+  return LE_OK;
+}
+
+extern "C" int le_observables(le_ctx *c, int ns, const int *s_list, double rc, int btype, int nbins, int bin_width,
+                              double *rg_sums, int64_t *contacts, int64_t *loop_hist) {
+  if (!c) return LE_EINVAL;
+  if (!c->atoms_loaded) return fail(c, LE_ESTATE, "no atoms");
+  if (ns < 0 || ns > OBS_MAXS || nbins < 0 || nbins > 4096 || (nbins > 0 && bin_width < 1)) return fail(c, LE_EINVAL, "le_observables: at most %d separations, 4096 bins", OBS_MAXS);
+  cudaSetDevice(c->device);
+  int r = ensure_ready(c); if (r) return r;
+  ObsArgs A; memset(&A, 0, sizeof A);
+  A.ns = ns; A.btype = btype; A.nbins = nbins; A.bin_width = bin_width; A.rcsq = (float)(rc * rc);
+  for (int k = 0; k < ns; k++) { if (s_list[k] < 1) return fail(c, LE_EINVAL, "le_observables: separations must be >= 1"); A.s[k] = s_list[k]; }
+  double *dd; unsigned long long *di;
+  const size_t ni = (size_t)ns + nbins + 1;
+  if (cudaMalloc(&dd, 8 * sizeof(double)) != cudaSuccess || cudaMalloc(&di, ni * sizeof(unsigned long long)) != cudaSuccess)
+    return fail(c, LE_ENOMEM, "cudaMalloc failed in le_observables");
+  CK(cudaMemsetAsync(dd, 0, 8 * sizeof(double), c->stream));
+  CK(cudaMemsetAsync(di, 0, ni * sizeof(unsigned long long), c->stream));
+  LAUNCH(c, k_observables, std::min(grid_for(c->d.gr0 - c->d.own0, 256), 148 * 8), 256, c->d, A, dd, di);
+  std::vector<unsigned long long> hi(ni);
+  double hd[8];
+  CK(cudaMemcpyAsync(hd, dd, sizeof hd, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(hi.data(), di, ni * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(dd); cudaFree(di);
+  if (rg_sums) for (int k = 0; k < 5; k++) rg_sums[k] = hd[k];
+  if (contacts) for (int k = 0; k < ns; k++) contacts[k] = (int64_t)hi[k];
+  if (loop_hist) for (int k = 0; k < nbins; k++) loop_hist[k] = (int64_t)hi[ns + k];
   return LE_OK;
 }
 

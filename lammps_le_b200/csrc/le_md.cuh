@@ -986,3 +986,55 @@ __global__ void k_unpack_owned(Dev d, int n, const int *tag, const double *x, co
     }
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// polymer observables on the device: radius of gyration from unwrapped coordinates
+// (ComputeGyration, src/compute_gyration.cpp:60-100), contact counts of bead pairs (t, t+s) for a list of chain
+// separations s (-> contact probability P(s)), and the histogram of extruder loop sizes |b - a| over the bonds of
+// one type (the loops; compute property/local batom1 batom2 btype, src/compute_property_local.cpp:104-117).
+// One pass over the owned atoms; every GPU tallies its own atoms, the caller sums over GPUs.
+//   out_d[0..4] = sum m, sum m x, sum m y, sum m z, sum m |x|^2      out_i[0..ns) contacts, then nbins histogram bins
+// ------------------------------------------------------------------------------------------------
+#define OBS_MAXS 32
+struct ObsArgs { int ns, btype, nbins, bin_width; float rcsq; int s[OBS_MAXS]; };
+
+__global__ void k_observables(Dev d, ObsArgs A, double *out_d, unsigned long long *out_i) {
+  const int n = d.ctrl->nown;
+  const int4 *__restrict__ pos = d.pos[d.ctrl->cur];
+  double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const int k = d.own0 + j;
+    const int4 p = pos[k];
+    const int t = p.w >> 3;
+    const int im = d.img[k];
+    const double m = (double)c_P.mass[p.w & 7];
+    const double x = le_deq((unsigned)p.x, 0) + (double)((im & 1023) - 512) * c_P.L[0];
+    const double y = le_deq((unsigned)p.y, 1) + (double)(((im >> 10) & 1023) - 512) * c_P.L[1];
+    const double z = le_deq((unsigned)p.z, 2) + (double)(((im >> 20) & 1023) - 512) * c_P.L[2];
+    acc[0] += m; acc[1] += m * x; acc[2] += m * y; acc[3] += m * z; acc[4] += m * (x * x + y * y + z * z);
+    for (int q = 0; q < A.ns; q++) {
+      const int t2 = t + A.s[q];
+      if (t2 > d.N) continue;
+      const int k2 = d.map[t2 - 1];
+      if (k2 < 0) continue;                    // not on this GPU: farther away than the halo, hence than rc
+      const int4 p2 = pos[k2];
+      const float dx = (float)(int)((unsigned)p2.x - (unsigned)p.x) * c_P.fscale[0];
+      const float dy = (float)(int)((unsigned)p2.y - (unsigned)p.y) * c_P.fscale[1];
+      const float dz = (float)(int)((unsigned)p2.z - (unsigned)p.z) * c_P.fscale[2];
+      if (dx * dx + dy * dy + dz * dz < A.rcsq) atomicAdd(&out_i[q], 1ull);
+    }
+    if (A.nbins > 0) {
+      const int nb = d.num_bond[t - 1];
+      for (int mth = 0; mth < nb; mth++) {
+        if (d.bond_type[(size_t)(t - 1) * d.bpa + mth] != A.btype) continue;
+        const int b = d.bond_atom[(size_t)(t - 1) * d.bpa + mth];
+        if (b > t) atomicAdd(&out_i[A.ns + min((b - t) / A.bin_width, A.nbins - 1)], 1ull);
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 5; q++) {
+    const double sres = warp_sum(acc[q]);
+    if ((threadIdx.x & 31) == 0 && sres != 0.0) atomicAdd(&out_d[q], sres);
+  }
+}

@@ -78,6 +78,7 @@ def load_library():
         "le_download_bondlist": [P, pi, C.POINTER(I64)], "le_thermo_count": [P],
         "le_get_thermo": [P, I, C.POINTER(Thermo)], "le_get_stats": [P, C.POINTER(Stats)], "le_compute_rg": [P, pd],
         "le_gen_saw_chains": [I, I, D, D, D, C.c_uint64, pd, pi], "le_gen_lattice_melt": [I, I, D, pd, pd, pi],
+        "le_observables": [P, I, pi, D, I, I, I, pd, C.POINTER(I64), C.POINTER(I64)],
         "le_local_capacity": [P], "le_download_owned": [P, pi, pi, pd, pi, pd], "le_upload_owned": [P, I, pi, pd, pi, pd],
         "le_dd_init": [P, I, I, D], "le_dd_get_handle": [P, C.c_void_p], "le_dd_connect": [P, C.c_void_p],
         "le_get_thermo_sums": [P, I, pd], "le_get_force_sums": [P, pd],
@@ -357,6 +358,28 @@ class Engine:
         s = Stats()
         self._ck(self.lib.le_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def observables_raw(self, s_list, rc=1.5, btype=2, nbins=64, bin_width=8):
+        """device tallies over the atoms this GPU owns: (rg_sums[5], contacts[len(s_list)], loop_hist[nbins])"""
+        sl = _i32(s_list)
+        sums = np.zeros(5)
+        cont = np.zeros(len(sl), dtype=np.int64)
+        hist = np.zeros(max(nbins, 1), dtype=np.int64)
+        self._ck(self.lib.le_observables(self._h, len(sl), _pi(sl), rc, btype, nbins, bin_width, _pd(sums),
+                                         cont.ctypes.data_as(C.POINTER(C.c_int64)), hist.ctypes.data_as(C.POINTER(C.c_int64))))
+        return sums, cont, hist[:nbins]
+
+    def observables(self, s_list, rc=1.5, btype=2, nbins=64, bin_width=8):
+        """Rg, contact probability P(s) and the loop-size histogram, computed on the GPU"""
+        sums, cont, hist = self._sum_over_ranks(*self.observables_raw(s_list, rc, btype, nbins, bin_width))
+        n = self.natoms
+        com = sums[1:4] / sums[0]
+        rg = float(np.sqrt(max(sums[4] / sums[0] - (com ** 2).sum(), 0.0)))
+        ps = cont / np.maximum(n - np.asarray(s_list), 1)
+        return {"rg": rg, "ps": ps, "loop_hist": hist, "nloops": int(hist.sum())}
+
+    def _sum_over_ranks(self, *arrays):
+        return arrays
 
     def rg(self):
         r = C.c_double()

@@ -167,6 +167,9 @@ class DDEngine(Engine):
             out.append(finalize_thermo(s, self.natoms, vol, t.step, t.nbonds))
         return out if index is None else out[0]
 
+    def _sum_over_ranks(self, *arrays):
+        return tuple(self._allreduce(np.ascontiguousarray(a)) for a in arrays)
+
     def stats(self):
         s = super().stats()
         if self.world > 1:

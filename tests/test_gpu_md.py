@@ -137,3 +137,37 @@ def test_owned_bulk_exchange_roundtrip():
     assert (xa == xc).all() and (ia == ic).all()
     assert (xa >= 0).all() and (xa < L).all()
     e.close(); e2.close()
+
+
+@pytest.mark.gpu
+def test_device_observables_match_host():
+    """le_observables (Rg, contact counts, loop-size histogram on the GPU) against numpy on downloaded state"""
+    s = systems.chromatin_chain(6000, 80, rho=0.2, seed=9, extruder_bond=systems.EXTRUDER_FENE)
+    v = systems.maxwell_velocities(6000, 1.0, np.ones(6000), 5)
+    e = systems.make_engine(s, velocities=v)
+    systems.relax(e, steps=1500)
+    e.fix_langevin(1.0, 1.0, 1.0, 99)
+    e.fix_extrusion(200, 1, 2, 3, 0.5, 2, 4, 12345)
+    e.run(1300)
+    s_list = [2, 3, 5, 8, 16, 50]
+    o = e.observables(s_list, rc=1.5, btype=2, nbins=16, bin_width=4)
+    xu, _ = e.positions(unwrap=True)
+    rg = np.sqrt(((xu - xu.mean(0)) ** 2).sum(1).mean())
+    assert abs(o["rg"] - rg) < 1e-9 * rg and abs(o["rg"] - e.rg()) < 1e-9 * rg
+    x, _ = e.positions()
+    L = s["box"][1][0]
+    for k, sp in enumerate(s_list):
+        dd = x[sp:] - x[:-sp]
+        dd -= L * np.rint(dd / L)
+        r2 = (dd ** 2).sum(1)
+        cnt = int((r2 < 1.5 ** 2).sum())
+        near_cut = int((np.abs(np.sqrt(r2) - 1.5) < 1e-5).sum())        # fp32 distance on the device
+        assert abs(int(round(o["ps"][k] * (6000 - sp))) - cnt) <= near_cut
+    topo = e.topology()
+    nb, bt, ba = topo["num_bond"], topo["bond_type"], topo["bond_atom"]
+    mask = (np.arange(bt.shape[1])[None, :] < nb[:, None]) & (bt == 2) & (ba > (np.arange(6000) + 1)[:, None])
+    ii, mm = np.nonzero(mask)
+    sizes = ba[ii, mm] - (ii + 1)
+    hist = np.bincount(np.minimum(sizes // 4, 15), minlength=16)
+    assert (o["loop_hist"] == hist).all() and o["nloops"] == len(sizes)
+    e.close()
