@@ -492,7 +492,7 @@ static int setup_cells(le_ctx *c, double cutneighmax) {
     else { d.cell_abs[k] = 1; d.cell_span[k] = nc[k]; }
   }
   d.ncells = d.nlx * nc[1] * nc[2] + 3;
-  d.nscanblocks = ((d.nlx - 2 * d.halo) * nc[1] * nc[2] + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  d.nscanblocks = ((d.nlx - 2 * d.halo) * nc[1] * nc[2] + SCAN_TILE - 1) / SCAN_TILE;
   return LE_OK;
 }
 
@@ -999,7 +999,6 @@ extern "C" int le_set_velocities(le_ctx *c, const double *v) {
 static void enqueue_rebuild(le_ctx *c, bool direct) {
   Dev &d = c->d;
   const int nslots = d.gr0 - d.own0;                       // capacity of the owned region
-  const int ncell_own = (d.nlx - 2 * d.halo) * d.ncell[1] * d.ncell[2];
   const bool dd = c->nranks > 1;
   LAUNCH(c, k_cell_count, grid_for(nslots, 256), 256, d, c->rb);
   if (dd) {
@@ -1010,7 +1009,6 @@ static void enqueue_rebuild(le_ctx *c, bool direct) {
   LAUNCH(c, k_scan_blocks, 1, SCAN_BLOCK, d);
   LAUNCH(c, k_scan_apply, d.nscanblocks, SCAN_BLOCK, d);
   LAUNCH(c, k_cell_scatter, grid_for(nslots, 256), 256, d);
-  LAUNCH(c, k_cell_sort, grid_for(ncell_own, 128), 128, d);
   LAUNCH(c, k_gather, grid_for(nslots, 256), 256, d);
   if (dd) {
     LAUNCH(c, k_push_ghosts, grid_for(std::max(d.own0, d.halo * d.ncell[1] * d.ncell[2] + 1), 256), 256, d);
@@ -1029,7 +1027,7 @@ static void enqueue_rebuild(le_ctx *c, bool direct) {
   if (direct) { LAUNCH(c, k_after_build, 1, 1, d); c->direct_builds++; }
 }
 
-static int rebuild_kernel_count(const le_ctx *c) { return c->nranks > 1 ? 13 : 8; }
+static int rebuild_kernel_count(const le_ctx *c) { return c->nranks > 1 ? 12 : 7; }
 
 #define CKG(call)                                                                             \
   do {                                                                                        \

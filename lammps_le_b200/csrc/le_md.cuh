@@ -522,15 +522,19 @@ __global__ void k_inbox(Dev d, RbScratch *rb) {
 }
 
 #define SCAN_BLOCK 1024
+#define SCAN_ITEMS 4                          // consecutive cells per thread
+#define SCAN_TILE (SCAN_BLOCK * SCAN_ITEMS)
 // exclusive scan of cell_count over the owned region's cell slots -> cell_start (three launches); re-zeroes cell_count
 __device__ __forceinline__ int own_cell_first(const Dev &d) { return cell_slot(d, d.halo, 0, 0); }
 __device__ __forceinline__ int own_cell_count(const Dev &d) { return (d.nlx - 2 * d.halo) * d.ncell[1] * d.ncell[2]; }
 
 __global__ void k_scan_partial(Dev d) {
   __shared__ int sh[32];
-  const int idx = blockIdx.x * SCAN_BLOCK + threadIdx.x;
-  int v = (idx < own_cell_count(d)) ? d.cell_count[own_cell_first(d) + idx] : 0;
-  int s = v;
+  const int idx = (blockIdx.x * SCAN_BLOCK + threadIdx.x) * SCAN_ITEMS;
+  const int n = own_cell_count(d), first = own_cell_first(d);
+  int s = 0;
+#pragma unroll
+  for (int q = 0; q < SCAN_ITEMS; q++) s += (idx + q < n) ? d.cell_count[first + idx + q] : 0;
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
   __syncthreads();
@@ -573,7 +577,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_blocks(Dev d) {  // one blo
   __shared__ int carry;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
-  const int nblocks = (own_cell_count(d) + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  const int nblocks = (own_cell_count(d) + SCAN_TILE - 1) / SCAN_TILE;
   for (int base = 0; base < nblocks; base += SCAN_BLOCK) {
     const int idx = base + threadIdx.x;
     const int v = (idx < nblocks) ? d.blocksum[idx] : 0;
@@ -592,14 +596,19 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_blocks(Dev d) {  // one blo
 }
 
 __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_apply(Dev d) {
-  const int idx = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+  const int idx = (blockIdx.x * SCAN_BLOCK + threadIdx.x) * SCAN_ITEMS;
   const int n = own_cell_count(d), first = own_cell_first(d);
-  const int v = (idx < n) ? d.cell_count[first + idx] : 0;
-  const int ex = block_excl_scan(v, nullptr);
-  if (idx < n) {
-    d.cell_start[first + idx] = d.own0 + d.blocksum[blockIdx.x] + ex;
-    d.cell_count[first + idx] = 0;
-  }
+  int v[SCAN_ITEMS], tsum = 0;
+#pragma unroll
+  for (int q = 0; q < SCAN_ITEMS; q++) { v[q] = (idx + q < n) ? d.cell_count[first + idx + q] : 0; tsum += v[q]; }
+  int run = d.own0 + d.blocksum[blockIdx.x] + block_excl_scan(tsum, nullptr);
+#pragma unroll
+  for (int q = 0; q < SCAN_ITEMS; q++)
+    if (idx + q < n) {
+      d.cell_start[first + idx + q] = run;
+      d.cell_count[first + idx + q] = 0;
+      run += v[q];
+    }
 }
 
 __global__ void k_cell_scatter(Dev d) {
@@ -610,33 +619,26 @@ __global__ void k_cell_scatter(Dev d) {
   }
 }
 
-// order each owned cell's members by tag (insertion sort; cells hold a handful of atoms)
-__global__ void k_cell_sort(Dev d) {
-  const int4 *__restrict__ pos = d.pos[d.ctrl->cur];
-  const int n = own_cell_count(d), first = own_cell_first(d);
-  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
-    const int s = d.cell_start[first + q], e = d.cell_start[first + q + 1];
-    for (int a = s + 1; a < e; a++) {
-      const int ia = d.order[a];
-      const int ta = pos[ia].w >> 3;
-      int b = a - 1;
-      while (b >= s) {
-        const int ib = d.order[b];
-        if ((pos[ib].w >> 3) <= ta) break;
-        d.order[b + 1] = ib;
-        b--;
-      }
-      d.order[b + 1] = ia;
-    }
-  }
-}
-
-// gather into the new local order: pos_hold (= new xhold), vel_tmp, img_hold; refresh the tag map
+// gather into the new local order: pos_hold (= new xhold), vel_tmp, img_hold; refresh the tag map.
+// Inside a cell atoms are ordered by tag: slot k of a cell takes the member whose tag has rank k - cell_start among
+// the cell's members (cells hold a handful of atoms, so every slot simply ranks them all -- no separate sort pass).
 __global__ void k_gather(Dev d) {
   const int4 *__restrict__ pos = d.pos[d.ctrl->cur];
   const int lo = d.own0, hi = d.own0 + d.ctrl->nown;
   for (int k = lo + blockIdx.x * blockDim.x + threadIdx.x; k < hi; k += gridDim.x * blockDim.x) {
-    const int i = d.order[k];
+    int i = d.order[k];
+    const int c = d.cellid[i];
+    const int s = d.cell_start[c], e = d.cell_start[c + 1];
+    if (e - s > 1) {
+      const int want = k - s;
+      for (int a = s; a < e; a++) {
+        const int ia = d.order[a];
+        const int ta = pos[ia].w >> 3;
+        int rank = 0;
+        for (int b = s; b < e; b++) rank += (pos[d.order[b]].w >> 3) < ta;
+        if (rank == want) { i = ia; break; }
+      }
+    }
     const int4 p = pos[i];
     d.pos_hold[k] = p;
     d.vel_tmp[k] = d.vel[i];
