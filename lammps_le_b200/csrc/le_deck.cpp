@@ -13,7 +13,7 @@
 //   pair_coeff I J eps sigma [rc] | bond_style fene|harmonic|hybrid ... | bond_coeff N [style] ...
 //   fix ID all nve | nve/limit X | langevin T0 T1 damp seed | extrusion ... | ex_load ... | ex_unload ...
 //   unfix ID | timestep dt | reset_timestep N | thermo N | thermo_style ... | thermo_modify ... | run N
-//   write_data F | log/echo/print (ignored or echoed)
+//   write_data F | dump ID all custom N F cols | undump ID | log/echo/print (ignored or echoed)
 // Anything else stops with the reference's "Unknown command" error.  No compute happens here: every
 // number comes from libleb200.so (there is no CPU fallback).
 #include "../../include/le_b200.h"
@@ -54,6 +54,8 @@ struct Deck {
   double dt = 0.005;
   int thermo_every = 0;
   std::map<std::string, std::string> fix_style;        // fix ID -> style
+  struct Dump { std::string id, file; int every; std::vector<std::string> cols; FILE *fp; };
+  std::vector<Dump> dumps;                             // dump ID all custom N file cols...
   bool echo = false;
 };
 
@@ -218,9 +220,53 @@ void init(Deck &d) {
 void print_thermo(Deck &d, int first) {
   const int n = le_thermo_count(d.ctx);
   std::printf("Step Temp E_pair E_mol TotEng Press \n");
+  long long last = -1;
   for (int k = first; k < n; k++) {
     le_thermo t; le_get_thermo(d.ctx, k, &t);
+    // segment boundaries of a run split by dumps are not thermo steps of the script
+    const bool edge = k == first || k == n - 1;
+    if (!edge && !(d.thermo_every > 0 && t.step % d.thermo_every == 0)) continue;
+    if (t.step == last) continue;
+    last = t.step;
     std::printf("%8lld %12.8g %12.8g %12.8g %12.8g %12.8g \n", (long long)t.step, t.temp, t.epair, t.emol, t.etotal, t.press);
+  }
+}
+
+// one frame of every dump that is due on this step, in the reference's text format (src/dump_custom.cpp:
+// "ITEM: TIMESTEP / NUMBER OF ATOMS / BOX BOUNDS pp pp pp / ATOMS cols", atoms in id order = dump_modify sort id)
+void write_dumps(Deck &d, long long step) {
+  bool due = false;
+  for (auto &dp : d.dumps) if (step % dp.every == 0) due = true;
+  if (!due) return;
+  const int n = d.natoms;
+  std::vector<double> x((size_t)3 * n), v((size_t)3 * n);
+  std::vector<int> im(n), ty(n);
+  ck(d, le_download_x(d.ctx, x.data(), im.data()));
+  ck(d, le_download_v(d.ctx, v.data()));
+  ck(d, le_download_types(d.ctx, ty.data()));
+  for (auto &dp : d.dumps) {
+    if (step % dp.every) continue;
+    if (!dp.fp) { dp.fp = std::fopen(dp.file.c_str(), "w"); if (!dp.fp) die("Cannot open dump file " + dp.file); }
+    std::fprintf(dp.fp, "ITEM: TIMESTEP\n%lld\nITEM: NUMBER OF ATOMS\n%d\nITEM: BOX BOUNDS pp pp pp\n", step, n);
+    for (int q = 0; q < 3; q++) std::fprintf(dp.fp, "%-1.16e %-1.16e\n", d.lo[q], d.hi[q]);
+    std::fprintf(dp.fp, "ITEM: ATOMS");
+    for (auto &c : dp.cols) std::fprintf(dp.fp, " %s", c.c_str());
+    std::fprintf(dp.fp, "\n");
+    for (int t = 0; t < n; t++) {
+      const int ii[3] = {(im[t] & 1023) - 512, ((im[t] >> 10) & 1023) - 512, ((im[t] >> 20) & 1023) - 512};
+      for (size_t k = 0; k < dp.cols.size(); k++) {
+        const std::string &c = dp.cols[k];
+        const char *sep = k + 1 < dp.cols.size() ? " " : "\n";
+        if (c == "id") std::fprintf(dp.fp, "%d%s", t + 1, sep);
+        else if (c == "type") std::fprintf(dp.fp, "%d%s", ty[t], sep);
+        else if (c == "mol") std::fprintf(dp.fp, "%d%s", d.mol.empty() ? 0 : d.mol[t], sep);
+        else if (c == "x" || c == "y" || c == "z") std::fprintf(dp.fp, "%g%s", x[3 * t + (c[0] - 'x')], sep);
+        else if (c == "xu" || c == "yu" || c == "zu") { const int q = c[0] - 'x'; std::fprintf(dp.fp, "%g%s", x[3 * t + q] + ii[q] * (d.hi[q] - d.lo[q]), sep); }
+        else if (c == "ix" || c == "iy" || c == "iz") std::fprintf(dp.fp, "%d%s", ii[c[1] - 'x'], sep);
+        else if (c == "vx" || c == "vy" || c == "vz") std::fprintf(dp.fp, "%g%s", v[3 * t + (c[1] - 'x')], sep);
+      }
+    }
+    std::fflush(dp.fp);
   }
 }
 
@@ -230,7 +276,19 @@ void run(Deck &d, const Words &w) {
   init(d);
   const int first = le_thermo_count(d.ctx);
   const auto t0 = std::chrono::steady_clock::now();
-  ck(d, le_run(d.ctx, n));
+  if (d.dumps.empty()) ck(d, le_run(d.ctx, n));
+  else {
+    // run in segments that end on the dump steps (every segment is a `run` of its own: Verlet::setup rebuilds the lists)
+    long long done = 0, step = le_timestep(d.ctx);
+    write_dumps(d, step);
+    while (done < n) {
+      long long seg = n - done;
+      for (auto &dp : d.dumps) seg = std::min(seg, dp.every - step % dp.every);
+      ck(d, le_run(d.ctx, seg));
+      done += seg; step += seg;
+      write_dumps(d, step);
+    }
+  }
   const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   print_thermo(d, first);
   le_stats st; ck(d, le_get_stats(d.ctx, &st));
@@ -397,6 +455,23 @@ void execute_cmd(Deck &d, const Words &w) {
   else if (c == "timestep") { if (w.size() != 2) die("Illegal timestep command"); d.dt = num(w[1]); }
   else if (c == "reset_timestep") { if (w.size() != 2 || !d.ctx) die("Illegal reset_timestep command"); ck(d, le_reset_timestep(d.ctx, std::strtoll(w[1].c_str(), nullptr, 10))); }
   else if (c == "thermo") { if (w.size() != 2) die("Illegal thermo command"); d.thermo_every = inum(w[1]); }
+  else if (c == "dump") {
+    if (w.size() < 7 || w[2] != "all" || w[3] != "custom") die("Illegal dump command (only: dump ID all custom N file columns...)");
+    Deck::Dump dp; dp.id = w[1]; dp.every = inum(w[4]); dp.file = w[5]; dp.fp = nullptr;
+    if (dp.every <= 0) die("Invalid dump frequency");
+    for (size_t k = 6; k < w.size(); k++) {
+      static const char *ok[] = {"id", "type", "mol", "x", "y", "z", "xu", "yu", "zu", "ix", "iy", "iz", "vx", "vy", "vz"};
+      bool known = false;
+      for (const char *o : ok) known = known || w[k] == o;
+      if (!known) die("Invalid attribute in dump custom command: " + w[k]);
+      dp.cols.push_back(w[k]);
+    }
+    d.dumps.push_back(dp);
+  } else if (c == "undump") {
+    for (size_t k = 0; k < d.dumps.size(); k++)
+      if (w.size() > 1 && d.dumps[k].id == w[1]) { if (d.dumps[k].fp) std::fclose(d.dumps[k].fp); d.dumps.erase(d.dumps.begin() + k); return; }
+    die("Could not find undump ID");
+  } else if (c == "dump_modify") {}
   else if (c == "run") run(d, w);
   else if (c == "write_data") write_data(d, w);
   else die("Unknown command: " + c);
@@ -428,6 +503,7 @@ int main(int argc, char **argv) {
     if (w.empty()) continue;
     execute(d, w);
   }
+  for (auto &dp : d.dumps) if (dp.fp) std::fclose(dp.fp);
   if (d.ctx) le_destroy(d.ctx);
   return 0;
 }

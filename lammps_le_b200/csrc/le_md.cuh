@@ -407,22 +407,25 @@ __device__ __forceinline__ void close_epoch(const Dev &d) {
 __global__ void k_decide(Dev d, cudaGraphConditionalHandle handle, int advance, int use_handle) {
   Ctrl *c = d.ctrl;
   if (advance) { c->step++; c->cur ^= 1; close_epoch(d); }
+  // moved / forced / rebuild_now / ago are the first 16 bytes of the control block: one load, one store
+  int4 w;
+  asm volatile("ld.volatile.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(c) : "memory");
+  int moved = w.x, forced = w.y, ago = w.w;
   int r = 0;
-  if (c->forced) r = 1;
+  if (forced) r = 1;
   else {
-    c->ago++;
-    if (c->ago >= c_P.delay && c->ago % c_P.every == 0) {
+    ago++;
+    if (ago >= c_P.delay && ago % c_P.every == 0) {
       if (!c_P.check) r = 1;
-      else if (c->moved) {
+      else if (moved) {
         r = 1;
         const int mx = c_P.every > c_P.delay ? c_P.every : c_P.delay;
-        if (c->ago == mx) c->ndanger++;
+        if (ago == mx) c->ndanger++;
       }
     }
   }
-  c->rebuild_now = r;
-  c->forced = 0;
-  if (r) { c->moved = 0; c->ago = 0; c->nbuilds++; }
+  if (r) { moved = 0; ago = 0; c->nbuilds++; }
+  *reinterpret_cast<int4 *>(c) = make_int4(moved, 0, r, ago);
   if (use_handle) cudaGraphSetConditional(handle, r ? 1u : 0u);
 }
 

@@ -102,3 +102,25 @@ def test_deck_write_data_roundtrip(tmp_path):
     assert a.returncode == 0 and b.returncode == 0, a.stderr[-1500:] + b.stderr[-1500:]
     ta, tb = parse_thermo(a.stdout), parse_thermo(b.stdout)
     assert np.abs(ta[0] - tb[0]).max() < 1e-9
+
+
+@pytest.mark.gpu
+def test_deck_dump_custom(tmp_path):
+    """dump ID all custom N file id type xu yu zu: frames in the reference's text format on the dump steps"""
+    z = np.load(os.path.join(GOLD, "bench_chain.npz"))
+    write_data_chain(tmp_path / "data.chain", z)
+    deck = IN_CHAIN.replace("run\t\t100", "dump 1 all custom 20 traj.lammpstrj id type xu yu zu\nrun 50")
+    (tmp_path / "in.d").write_text(deck)
+    exe = os.path.join(ROOT, "lammps_le_b200", "le_deck")
+    r = subprocess.run([exe, "-in", "in.d"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    lines = (tmp_path / "traj.lammpstrj").read_text().splitlines()
+    n = 32000
+    per = 9 + n
+    assert len(lines) == 3 * per                         # steps 0, 20, 40
+    assert [lines[k * per + 1] for k in range(3)] == ["0", "20", "40"]
+    assert lines[8] == "ITEM: ATOMS id type xu yu zu"
+    first = np.array(lines[9].split(), dtype=float)
+    assert first[0] == 1 and np.allclose(first[2:], z["x"][0], atol=1e-5)
+    th = parse_thermo(r.stdout)
+    assert th[0, 0] == 0 and th[-1, 0] == 50
