@@ -102,7 +102,7 @@ REF_LE_LINES = ["fix loop all extrusion 500 1 2 3 0.5 2 4",
 
 
 NCU_TRAFFIC_PER_LAUNCH = 99.3e6   # bytes: 87.8 MB read + 11.5 MB written per k_step<0> launch at 1M beads (ncu capture of round 1)
-LE_HALO = 6.2   # ghost shell for USER-LE on several GPUs: longest extruder bond (FENE R0 = 4) + one backbone bond + skin
+LE_HALO = 6.0   # ghost shell for USER-LE on several GPUs: longest extruder bond (FENE R0 = 4) + one backbone bond (1.5) + skin (4 cell layers here)
 
 
 def prepared_engine(n_beads, n_ext, seed, device, relax_steps, dd=None):

@@ -665,7 +665,6 @@ __global__ void k_push_ghosts(Dev d) {
   Ctrl *c = d.ctrl;
   const int H = d.halo, ncy = d.ncell[1], ncz = d.ncell[2];
   const int layer = ncy * ncz;
-  const int cur = c->cur;
   const int own_lo = d.own0, own_hi = d.own0 + c->nown;
   const int sl_end = d.cell_start[cell_slot(d, 2 * H - 1, ncy - 1, ncz - 1) + 1];   // end of my first H layers
   const int sr_beg = d.cell_start[cell_slot(d, d.nlx - 2 * H, 0, 0)];               // start of my last H layers
@@ -677,14 +676,10 @@ __global__ void k_push_ghosts(Dev d) {
   }
   if (sl_end - own_lo > d.own0 || own_hi - sr_beg > d.own0) return;
   for (int k = own_lo + tid; k < sl_end; k += nth) {          // -> right ghosts of the left neighbor
-    const int4 p = d.pos_hold[k];
-    L.pos_hold[d.gr0 + (k - own_lo)] = p;
-    L.pos[cur][d.gr0 + (k - own_lo)] = p;
+    L.pos_hold[d.gr0 + (k - own_lo)] = d.pos_hold[k];   // the receiver copies it into its live buffer (k_ghost_map)
   }
   for (int k = sr_beg + tid; k < own_hi; k += nth) {          // -> left ghosts of the right neighbor
-    const int4 p = d.pos_hold[k];
-    R.pos_hold[k - sr_beg] = p;
-    R.pos[cur][k - sr_beg] = p;
+    R.pos_hold[k - sr_beg] = d.pos_hold[k];
   }
   for (int q = tid; q <= H * layer; q += nth) {               // cell_start of those layers (+ the closing sentinel)
     const int lx = q / layer, rem = q - lx * layer;
@@ -718,7 +713,9 @@ __global__ void k_ghost_map(Dev d) {
   const int nl = d.ctrl->nghl, nr = d.ctrl->nghr;
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < nl + nr; g += gridDim.x * blockDim.x) {
     const int k = g < nl ? g : d.gr0 + (g - nl);
-    const int tag = d.pos_hold[k].w >> 3;
+    const int4 p = d.pos_hold[k];
+    const int tag = p.w >> 3;
+    d.pos[d.ctrl->cur][k] = p;
     d.ghost_tag[g] = tag;
     d.map[tag - 1] = k;
   }
