@@ -1067,6 +1067,7 @@ static int graph_add_unit(le_ctx *c, cudaGraph_t g, cudaGraphNode_t *tail, int a
   if (with_step) {
     StepArgs a; memset(&a, 0, sizeof a);
     a.do_final = 1; a.do_initial = 1; a.langevin = c->langevin_on;
+    { static const int skip = getenv("LE_STEP_SKIP") ? atoi(getenv("LE_STEP_SKIP")) : 0; a.skip = skip & (15 | 32); if (skip & 16) a.langevin = 0; }
     void *sargs[] = {&d, &a};
     memset(&kp, 0, sizeof kp);
     static const int minb = getenv("LE_STEP_MINB") ? atoi(getenv("LE_STEP_MINB")) : 4;
@@ -1269,7 +1270,7 @@ extern "C" int le_run(le_ctx *c, int64_t nsteps) {
     a.do_final = (s > begin);
     a.do_initial = (s < end);
     a.langevin = c->langevin_on;
-    { static const int skip = getenv("LE_STEP_SKIP") ? atoi(getenv("LE_STEP_SKIP")) : 0; a.skip = skip & 15; if (skip & 16) a.langevin = 0; }
+    { static const int skip = getenv("LE_STEP_SKIP") ? atoi(getenv("LE_STEP_SKIP")) : 0; a.skip = skip & (15 | 32); if (skip & 16) a.langevin = 0; }
     bool ev = false;
     if (want_thermo(s)) {
       if (used_slots == THERMO_SLOTS) {

@@ -13,7 +13,7 @@ struct StepArgs {
   int slot;           // thermo slot to tally energy / virial / kinetic energy into (EV kernels)
   int write_force;    // store the conservative force of every atom in fout (tag order)
   int langevin;       // add drag + noise
-  int skip;           // development only (LE_STEP_SKIP): 1 no gathers, 2 no pair evaluation, 4 no bonds, 8 no neighbor rows
+  int skip;           // development only (LE_STEP_SKIP): 1 no gathers, 2 no pair evaluation, 4 no bonds, 8 no neighbor rows, 32 no boundary-first block order
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(STEP_THREADS, EV ? 2 : MINB) k_step(Dev d, Ste
   const float sx = c_P.fscale[0], sy = c_P.fscale[1], sz = c_P.fscale[2];
   const int nt = c_P.ntypes;
   int i = d.own0 + blockIdx.x * STEP_THREADS + threadIdx.x;
-  if (DD) {
+  if (DD && !(a.skip & 32)) {
     // the two boundary slices first, the interior last: their halo stores are in flight while the interior computes
     const int g = blockIdx.x * STEP_THREADS + threadIdx.x;
     const int nl = ctrl->send_l_end - d.own0, nr = own_end - ctrl->send_r_beg;
