@@ -28,7 +28,6 @@ struct FixExLoadCfg { int on, nevery, itype, jtype, btype, seed, imax, inew, jma
 struct FixExUnloadCfg { int on, nevery, btype, seed; double rc, prob; };
 
 #define PLAIN_UNROLL 8      // timesteps per launch of the steady-state graph
-#define REBUILD_KERNELS 8   // kernels in the conditional rebuild body
 
 struct GraphKey { Dev d; int langevin; };
 

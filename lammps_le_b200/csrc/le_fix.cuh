@@ -657,7 +657,7 @@ struct VisitTask {
     return n;
   }
   __device__ void exec(int k) {
-    const Dev &d = V.d; const LeFixDev &f = V.f;
+    const LeFixDev &f = V.f;
     const int i = f.tasks[k];
     const int p = f.partner[i];
     const int a = min(i + 1, p), b = max(i + 1, p);       // tags of i1 < i2
