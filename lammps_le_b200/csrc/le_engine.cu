@@ -723,7 +723,8 @@ extern "C" int le_upload_atoms(le_ctx *c, int n, const int *tag, const int *type
       for (int q = 0; q < H; q++) { gl += per_layer[x0 + q]; gr += per_layer[x1 - 1 - q]; }
       maxown = std::max(maxown, own); maxghost = std::max(maxghost, std::max(gl, gr));
     }
-    const long long owncap = maxown + maxown / 4 + 4096, ghostcap = maxghost + maxghost / 2 + 4096;
+    // multiples of 64 slots: the owned region starts on a 128-byte line of every per-atom array
+    const long long owncap = (maxown + maxown / 4 + 4096 + 63) & ~63LL, ghostcap = (maxghost + maxghost / 2 + 4096 + 63) & ~63LL;
     d.own0 = (int)ghostcap; d.gr0 = (int)(ghostcap + owncap); d.cap = (int)(2 * ghostcap + owncap);
     d.inbox_cap = (int)std::max<long long>(4096, owncap / 16);
     for (int t = 0; t < n; t++) {
@@ -1073,7 +1074,7 @@ static int graph_add_unit(le_ctx *c, cudaGraph_t g, cudaGraphNode_t *tail, int a
     const bool uni = c->P.pair_uniform != 0;
     kp.func = c->nranks > 1 ? (uni ? (void *)k_step<0, 1, 4, 1> : (void *)k_step<0, 1>)
                             : (minb == 5 ? (void *)k_step<0, 0, 5> : minb == 6 ? (void *)k_step<0, 0, 6> : minb == 3 ? (void *)k_step<0, 0, 3>
-                               : uni ? (void *)k_step<0, 0, 4, 1> : (void *)k_step<0, 0>); kp.gridDim = dim3(grid_for(c->d.gr0 - c->d.own0, STEP_THREADS)); kp.blockDim = dim3(STEP_THREADS); kp.kernelParams = sargs;
+                               : uni ? (void *)k_step<0, 0, 4, 1> : (void *)k_step<0, 0>); kp.gridDim = dim3(grid_for(c->d.gr0 - c->d.own0, STEP_THREADS) + (c->nranks > 1 ? 1 : 0)); kp.blockDim = dim3(STEP_THREADS); kp.kernelParams = sargs;
     cudaGraphNode_t ns;
     CKG(cudaGraphAddKernelNode(&ns, g, &nc, 1, &kp));
     *tail = ns;
@@ -1179,7 +1180,7 @@ static void thermo_from_slot(le_ctx *c, const double *s, int64_t step, le_thermo
 }
 
 static void launch_step(le_ctx *c, const StepArgs &a, bool ev) {
-  const int grid = grid_for(c->d.gr0 - c->d.own0, STEP_THREADS);
+  const int grid = grid_for(c->d.gr0 - c->d.own0, STEP_THREADS) + (c->nranks > 1 ? 1 : 0);
   const bool uni = c->P.pair_uniform != 0;
   if (c->nranks > 1) {
     if (ev) LAUNCH(c, (k_step<1, 1>), grid, STEP_THREADS, c->d, a);

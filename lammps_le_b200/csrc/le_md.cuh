@@ -188,11 +188,16 @@ __global__ void __launch_bounds__(STEP_THREADS, EV ? 2 : MINB) k_step(Dev d, Ste
   const int nt = c_P.ntypes;
   int i = d.own0 + blockIdx.x * STEP_THREADS + threadIdx.x;
   if (DD && !(a.skip & 32)) {
-    // the two boundary slices first, the interior last: their halo stores are in flight while the interior computes
+    // the two boundary slices first, the interior last: their halo stores are in flight while the interior computes.
+    // Segment starts are kept multiples of 64 slots (own0 is one), so that every warp still reads whole 128-byte
+    // lines: the left slice is widened to the next multiple, the right one starts at the previous multiple.
     const int g = blockIdx.x * STEP_THREADS + threadIdx.x;
-    const int nl = ctrl->send_l_end - d.own0, nr = own_end - ctrl->send_r_beg;
-    i = g < nl ? d.own0 + g : (g < nl + nr ? ctrl->send_r_beg + (g - nl) : ctrl->send_l_end + (g - nl - nr));
-    if (g >= ctrl->nown) i = own_end;
+    const int a_end = min(own_end, d.own0 + ((ctrl->send_l_end - d.own0 + 63) & ~63));
+    const int b_beg = max(a_end, d.own0 + ((ctrl->send_r_beg - d.own0) & ~63));
+    const int nl = a_end - d.own0, nr = own_end - b_beg, nrp = (nr + 63) & ~63;
+    if (g < nl) i = d.own0 + g;
+    else if (g < nl + nrp) i = (g - nl < nr) ? b_beg + (g - nl) : own_end;
+    else { i = a_end + (g - nl - nrp); if (i >= b_beg) i = own_end; }
   }
 
   double acc[10];
