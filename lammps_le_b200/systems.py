@@ -118,3 +118,35 @@ def relax(e, steps=2000, xmax=0.05, temp=1.0, damp=1.0, seed=4711):
     e.fix_langevin(temp, temp, damp, seed)
     e.run(steps)
     e.fix_nve(True)
+
+
+def replicate(system, nx, ny, nz):
+    """`replicate nx ny nz` (src/replicate.cpp) of a bonded system: images of the box side by side, bonds copied with
+    the atom ids shifted; used for the weak-scaling melt of bench/in.chain.scaled"""
+    lo, hi = (np.asarray(a, dtype=np.float64) for a in system["box"])
+    L = hi - lo
+    n = len(system["types"])
+    bt, a1, a2 = system["bonds"]
+    xs, ts, ims, bts, b1s, b2s = [], [], [], [], [], []
+    from .engine import unpack_image, pack_image
+    img = unpack_image(system["image"])
+    k = 0
+    for ix in range(nx):
+        for iy in range(ny):
+            for iz in range(nz):
+                # a bond may cross the original box: unwrap, shift, wrap into the big box
+                xu = system["x"] + img * L + np.array([ix, iy, iz]) * L
+                big = L * np.array([nx, ny, nz])
+                w = np.floor((xu - lo) / big)
+                xs.append(xu - w * big)
+                ims.append(pack_image(w.astype(np.int64)))
+                ts.append(system["types"])
+                bts.append(bt); b1s.append(a1 + k * n); b2s.append(a2 + k * n)
+                k += 1
+    out = dict(system)
+    out.update(name="%s_x%d" % (system.get("name", "sys"), nx * ny * nz), box=(lo, lo + L * np.array([nx, ny, nz])),
+               types=np.concatenate(ts), x=np.concatenate(xs), image=np.concatenate(ims),
+               bonds=(np.concatenate(bts), np.concatenate(b1s).astype(np.int32), np.concatenate(b2s).astype(np.int32)))
+    if system.get("v") is not None:
+        out["v"] = np.tile(system["v"], (nx * ny * nz, 1))
+    return out

@@ -13,9 +13,24 @@ from tests import lehelpers as H
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 400
 rank, world, local, group = init_process_group()
-s = systems.chromatin_chain(n, n // 100, rho=0.2, seed=12345, barriers="random", extruder_bond=systems.EXTRUDER_FENE)
-v = systems.maxwell_velocities(n, 1.0, np.ones(n), 1)
-dd = systems.make_engine(s, device=local, velocities=v, dd=dict(rank=rank, world=world, halo=6.2, group=group))
+melt = len(sys.argv) > 3 and sys.argv[3] == "melt"
+if melt:
+    # BASELINE configs[2], bench/in.chain.scaled: the 32,000-bead FENE melt of bench/data.chain replicated `world` times along x
+    z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "bench_chain.npz"))
+    z = {k: z[k] for k in z.files}
+    from lammps_le_b200.engine import pack_image
+    base = {"name": "melt", "box": (z["boxlo"], z["boxhi"]), "types": z["type"], "x": z["x"], "image": pack_image(z["image"]),
+            "bonds": (z["bonds"][:, 0].copy(), z["bonds"][:, 1].copy(), z["bonds"][:, 2].copy()), "masses": np.ones(1), "nbondtypes": 1,
+            "ntypes": 1, "bond_coeffs": {1: ("fene", (30.0, 1.5, 1.0, 1.0))}, "bond_per_atom": 2, "maxspecial": 8, "v": z["v"]}
+    s = systems.replicate(base, world, 1, 1)
+    n = len(s["types"])
+    v = s["v"]
+    halo = 0.0
+else:
+    s = systems.chromatin_chain(n, n // 100, rho=0.2, seed=12345, barriers="random", extruder_bond=systems.EXTRUDER_FENE)
+    v = systems.maxwell_velocities(n, 1.0, np.ones(n), 1)
+    halo = 6.2
+dd = systems.make_engine(s, device=local, velocities=v, dd=dict(rank=rank, world=world, halo=halo, group=group))
 ref = systems.make_engine(s, device=local, velocities=v) if rank == 0 else None
 ok = True
 
@@ -69,6 +84,12 @@ if rank == 0:
     report("thermo after %d steps" % steps, abs(th["temp"] - th2["temp"]) < 0.02 and abs(th["emol"] - th2["emol"]) < 0.05 and abs(th["epair"] - th2["epair"]) < 0.01,
            "T %.4f/%.4f epair %.4f/%.4f emol %.4f/%.4f builds %d/%d" % (th["temp"], th2["temp"], th["epair"], th2["epair"], th["emol"], th2["emol"], st["neigh_builds"], st2["neigh_builds"]))
     print("dd: %.4f ms/step (GPU events, rank 0) over %d ranks; single GPU %.4f ms/step" % (st["last_run_gpu_ms"] / steps, world, st2["last_run_gpu_ms"] / steps), flush=True)
+if melt:
+    dd.barrier()
+    if rank == 0:
+        print("DD CHECK", "PASSED" if ok else "FAILED", flush=True)
+    dd.close()
+    sys.exit(0 if ok else 1)
 # USER-LE events on the decomposed system: the decision logic is replicated, the geometry comes from the owners
 for e in (dd, ref):
     if e is None: continue
