@@ -76,3 +76,17 @@ def test_lattice_melt_bonds_have_lattice_spacing():
     d -= L * np.rint(d / L)
     r = np.sqrt((d ** 2).sum(1))
     assert len(bt) == 40 * 99 and r.max() < 1.2 and r.min() > 0.9
+
+
+def test_le_deck_front_end_rejects_unknown_commands(tmp_path):
+    """the C++ host front end stops on a command outside the path with the reference's error text (no GPU needed:
+    nothing has touched the device yet)"""
+    import subprocess
+    exe = os.path.join(ROOT, "lammps_le_b200", "le_deck")
+    assert os.path.exists(exe), "le_deck is not built (make -C lammps_le_b200/csrc)"
+    (tmp_path / "in.bad").write_text("units lj\natom_style bond\nkspace_style pppm 1e-4\n")
+    r = subprocess.run([exe, "-in", "in.bad"], cwd=tmp_path, capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "Unknown command: kspace_style" in r.stderr
+    (tmp_path / "in.units").write_text("units real\n")
+    r = subprocess.run([exe, "-in", "in.units"], cwd=tmp_path, capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "only units lj" in r.stderr
