@@ -7,6 +7,7 @@
 #include "../../include/le_b200.h"
 #include "le_common.cuh"
 #include "le_md.cuh"
+#include "le_step2.cuh"
 #include "le_fix.cuh"
 
 #include <math.h>
@@ -29,10 +30,10 @@ struct FixExUnloadCfg { int on, nevery, btype, seed; double rc, prob; };
 
 #define PLAIN_UNROLL 8      // timesteps per launch of the steady-state graph
 
-struct GraphKey { Dev d; int langevin; };
+struct GraphKey { Dev d; int langevin; int variant; };
 
 struct le_ctx {
-  int device;
+  int device, sm_count;
   cudaStream_t stream;
   std::string err;
   // box
@@ -80,10 +81,10 @@ struct le_ctx {
   double *h_thermo;     // pinned
   Ctrl *h_ctrl;         // pinned
   // captured step graphs (built lazily, rebuilt when anything baked into them changes)
-  GraphKey gkey;
+  GraphKey gkey; int gkey_variant;
   bool graphs_ok;
-  cudaGraph_t g_plain, g_tail[2];
-  cudaGraphExec_t x_plain, x_tail[2];
+  cudaGraph_t g_plain[2], g_tail[2];          // g_plain[p]: steady-state graph launched when pos[p] holds the coordinates
+  cudaGraphExec_t x_plain[2], x_tail[2];
   int64_t direct_launches, graph_node_launches, direct_builds;
   bool capturing;
   // domain decomposition (x-slabs, one GPU per rank); nranks == 1: the whole box on this GPU
@@ -118,7 +119,7 @@ static void time_report(le_ctx *c) {
     // average launch-to-next-launch time of the plain step kernel (le_run_timed)
     double sum = 0; int n = 0;
     for (size_t k = 0; k + 1 < c->tm_used; k++)
-      if (!strncmp(c->tm_name[k], "(k_step<0", 9)) { float ms = 0.f; cudaEventElapsedTime(&ms, c->tm_ev[k], c->tm_ev[k + 1]); sum += ms; n++; }
+      if (!strncmp(c->tm_name[k], "(k_step<0", 9) || !strncmp(c->tm_name[k], "(k_step2", 8)) { float ms = 0.f; cudaEventElapsedTime(&ms, c->tm_ev[k], c->tm_ev[k + 1]); sum += ms; n++; }
     c->kstep_avg_ms = n ? sum / n : 0.0;
   }
   if (c->timing_quiet) { c->tm_used = 0; c->tm_name.clear(); return; }
@@ -195,6 +196,7 @@ extern "C" int le_create(le_ctx **out, int device, const double boxlo[3], const 
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return LE_ENOGPU; }
   cudaEventCreate(&c->ev0);
   cudaEventCreate(&c->ev1);
+  if (cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c->sm_count < 1) c->sm_count = 148;
   c->le_ev_used = 0;
   { const char *tm = getenv("LE_B200_TIMING"); c->timing = tm && tm[0] == '1'; c->tm_used = 0; }
   c->timing_quiet = false; c->force_direct = false; c->kstep_avg_ms = 0.0;
@@ -222,8 +224,8 @@ extern "C" int le_create(le_ctx **out, int device, const double boxlo[3], const 
   memset(&c->stats, 0, sizeof c->stats);
   c->nbonds = 0;
   c->graphs_ok = false; c->capturing = false;
-  c->g_plain = nullptr; c->g_tail[0] = c->g_tail[1] = nullptr;
-  c->x_plain = nullptr; c->x_tail[0] = c->x_tail[1] = nullptr;
+  c->g_plain[0] = c->g_plain[1] = nullptr; c->g_tail[0] = c->g_tail[1] = nullptr;
+  c->x_plain[0] = c->x_plain[1] = nullptr; c->x_tail[0] = c->x_tail[1] = nullptr;
   c->direct_launches = c->graph_node_launches = c->direct_builds = 0;
   memset(&c->gkey, 0, sizeof c->gkey);
   c->nranks = 1; c->rank = 0; c->halo_dist = 0.0; c->arena = nullptr; c->arena_bytes = 0; c->peers_open = false; c->rb = nullptr;
@@ -240,13 +242,15 @@ extern "C" int le_create(le_ctx **out, int device, const double boxlo[3], const 
 }
 
 static void destroy_graphs(le_ctx *c) {
-  if (c->x_plain) cudaGraphExecDestroy(c->x_plain);
-  if (c->g_plain) cudaGraphDestroy(c->g_plain);
+  for (int k = 0; k < 2; k++) {
+    if (c->x_plain[k]) cudaGraphExecDestroy(c->x_plain[k]);
+    if (c->g_plain[k]) cudaGraphDestroy(c->g_plain[k]);
+  }
   for (int k = 0; k < 2; k++) {
     if (c->x_tail[k]) cudaGraphExecDestroy(c->x_tail[k]);
     if (c->g_tail[k]) cudaGraphDestroy(c->g_tail[k]);
   }
-  c->x_plain = nullptr; c->g_plain = nullptr;
+  c->x_plain[0] = c->x_plain[1] = nullptr; c->g_plain[0] = c->g_plain[1] = nullptr;
   c->x_tail[0] = c->x_tail[1] = nullptr; c->g_tail[0] = c->g_tail[1] = nullptr;
   c->graphs_ok = false;
 }
@@ -571,6 +575,7 @@ static int build_params(le_ctx *c) {
     P.binvr0sq_d[k] = P.br0sq_d[k] > 0.0 ? 1.0 / P.br0sq_d[k] : 0.0;
     P.bsig2_d[k] = P.bsig_d[k] * P.bsig_d[k];
     P.bcore_d[k] = 1.2599210498948732 * P.bsig2_d[k];        // TWO_1_3 (bond_fene.cpp:22)
+    P.beps48_d[k] = 48.0 * P.beps_d[k];
   }
   P.t_start = (float)c->t_start; P.t_stop = (float)c->t_stop; P.tsqrt_const = (float)sqrt(c->t_start);
   P.dt = (float)c->dt; P.dtf = (float)(0.5 * c->dt);       // FixNVE::init, ftm2v = 1
@@ -994,6 +999,55 @@ extern "C" int le_set_velocities(le_ctx *c, const double *v) {
   return LE_OK;
 }
 
+// ---- which plain step kernel (no energy / virial tally) -----------------------------------------------
+// LE_STEP_VARIANT (read at every le_run, so one process can compare variants): 0 = k_step; bit 0 = k_step2 (le_step2.cuh),
+// bit 1 = 128 threads per block instead of 256, bit 2 = L2 prefetch one wave ahead, bit 3 = int -> double on the fp64
+// pipe, bit 4 = k_step2 also on several GPUs, bit 5 = persistent grid (with bit 2: prefetch into the L1).  k_step2 needs the uniform lj/cut case and special weights in {0, 1};
+// otherwise k_step runs whatever the switch says.
+#ifndef LE_STEP_VARIANT_DEFAULT
+#define LE_STEP_VARIANT_DEFAULT 0
+#endif
+typedef void (*step_fn_t)(Dev, StepArgs);
+struct StepKernel { step_fn_t fn; int threads; const char *name; bool persistent; };
+
+static int step_variant() { const char *v = getenv("LE_STEP_VARIANT"); return v ? atoi(v) : LE_STEP_VARIANT_DEFAULT; }
+
+static bool step2_eligible(const le_ctx *c) {
+  if (!c->P.pair_uniform) return false;
+  for (int k = 1; k <= 3; k++) if (c->P.special_flag[k] == 2) return false;
+  return true;
+}
+
+#define STEP2_CASE(dd, nt, pf, mg) { (step_fn_t)k_step2<dd, nt, pf, mg>, nt, "(k_step2<" #dd "," #nt "," #pf "," #mg ">)", false }
+#define STEP2P_CASE(nt, pf, mg) { (step_fn_t)k_step2p<nt, pf, mg>, nt, "(k_step2p<" #nt "," #pf "," #mg ">)", true }
+static StepKernel plain_step_kernel(const le_ctx *c, int variant) {
+  const bool dd = c->nranks > 1;
+  if ((variant & 1) && step2_eligible(c) && (!dd || (variant & 16))) {
+    const bool small = variant & 2, pf = variant & 4, mg = variant & 8, pers = variant & 32;
+    if (dd) return small ? StepKernel STEP2_CASE(1, 128, 0, 0) : StepKernel STEP2_CASE(1, 256, 0, 0);
+    static const StepKernel tab[16] = {
+        STEP2_CASE(0, 256, 0, 0), STEP2_CASE(0, 128, 0, 0), STEP2_CASE(0, 256, 1, 0), STEP2_CASE(0, 128, 1, 0),
+        STEP2_CASE(0, 256, 0, 1), STEP2_CASE(0, 128, 0, 1), STEP2_CASE(0, 256, 1, 1), STEP2_CASE(0, 128, 1, 1),
+        STEP2P_CASE(256, 0, 0), STEP2P_CASE(128, 0, 0), STEP2P_CASE(256, 1, 0), STEP2P_CASE(128, 1, 0),
+        STEP2P_CASE(256, 0, 1), STEP2P_CASE(128, 0, 1), STEP2P_CASE(256, 1, 1), STEP2P_CASE(128, 1, 1)};
+    return tab[(small ? 1 : 0) | (pf ? 2 : 0) | (mg ? 4 : 0) | (pers ? 8 : 0)];
+  }
+  const bool uni = c->P.pair_uniform != 0;
+  static const int minb = getenv("LE_STEP_MINB") ? atoi(getenv("LE_STEP_MINB")) : 4;
+  step_fn_t fn;
+  if (dd) fn = uni ? (step_fn_t)k_step<0, 1, 4, 1> : (step_fn_t)k_step<0, 1>;
+  else fn = minb == 5 ? (step_fn_t)k_step<0, 0, 5> : minb == 6 ? (step_fn_t)k_step<0, 0, 6> : minb == 3 ? (step_fn_t)k_step<0, 0, 3>
+            : uni ? (step_fn_t)k_step<0, 0, 4, 1> : (step_fn_t)k_step<0, 0>;
+  return StepKernel{fn, STEP_THREADS, "(k_step<0>)", false};
+}
+
+// blocks of a plain step launch: one per NT owned slots (+1 boundary bookkeeping block on a slab); a persistent kernel
+// gets one wave of resident blocks
+static int step_grid(const le_ctx *c, const StepKernel &sk) {
+  const int g = grid_for(c->d.gr0 - c->d.own0, sk.threads) + (c->nranks > 1 ? 1 : 0);
+  return sk.persistent ? std::min(g, c->sm_count * (1024 / sk.threads)) : g;
+}
+
 // ---- rebuild / step drivers -------------------------------------------------------------------------
 // the rebuild kernels; `direct` adds the bookkeeping k_decide does when the rebuild is a conditional graph node
 static void enqueue_rebuild(le_ctx *c, bool direct) {
@@ -1039,7 +1093,7 @@ static int rebuild_kernel_count(const le_ctx *c) { return c->nranks > 1 ? 12 : 7
   } while (0)
 
 // append [k_decide(advance) -> IF(rebuild)] (and optionally a plain k_step after it) to graph g after node *tail
-static int graph_add_unit(le_ctx *c, cudaGraph_t g, cudaGraphNode_t *tail, int advance, bool with_step) {
+static int graph_add_unit(le_ctx *c, cudaGraph_t g, cudaGraphNode_t *tail, int advance, bool with_step, int step_rd = 0) {
   cudaGraphConditionalHandle handle;
   CKG(cudaGraphConditionalHandleCreate(&handle, g, 0, cudaGraphCondAssignDefault));
   Dev d = c->d;
@@ -1068,13 +1122,12 @@ static int graph_add_unit(le_ctx *c, cudaGraph_t g, cudaGraphNode_t *tail, int a
     StepArgs a; memset(&a, 0, sizeof a);
     a.do_final = 1; a.do_initial = 1; a.langevin = c->langevin_on;
     { static const int skip = getenv("LE_STEP_SKIP") ? atoi(getenv("LE_STEP_SKIP")) : 0; a.skip = skip & (15 | 32); if (skip & 16) a.langevin = 0; }
+    a.rdp1 = step_rd + 1;
     void *sargs[] = {&d, &a};
     memset(&kp, 0, sizeof kp);
-    static const int minb = getenv("LE_STEP_MINB") ? atoi(getenv("LE_STEP_MINB")) : 4;
-    const bool uni = c->P.pair_uniform != 0;
-    kp.func = c->nranks > 1 ? (uni ? (void *)k_step<0, 1, 4, 1> : (void *)k_step<0, 1>)
-                            : (minb == 5 ? (void *)k_step<0, 0, 5> : minb == 6 ? (void *)k_step<0, 0, 6> : minb == 3 ? (void *)k_step<0, 0, 3>
-                               : uni ? (void *)k_step<0, 0, 4, 1> : (void *)k_step<0, 0>); kp.gridDim = dim3(grid_for(c->d.gr0 - c->d.own0, STEP_THREADS) + (c->nranks > 1 ? 1 : 0)); kp.blockDim = dim3(STEP_THREADS); kp.kernelParams = sargs;
+    const StepKernel sk = plain_step_kernel(c, c->gkey_variant);
+    kp.func = (void *)sk.fn; kp.gridDim = dim3(step_grid(c, sk));
+    kp.blockDim = dim3(sk.threads); kp.kernelParams = sargs;
     cudaGraphNode_t ns;
     CKG(cudaGraphAddKernelNode(&ns, g, &nc, 1, &kp));
     *tail = ns;
@@ -1084,9 +1137,10 @@ static int graph_add_unit(le_ctx *c, cudaGraph_t g, cudaGraphNode_t *tail, int a
 
 static int ensure_graphs(le_ctx *c) {
   GraphKey key; memset(&key, 0, sizeof key);
-  key.d = c->d; key.langevin = c->langevin_on;
+  key.d = c->d; key.langevin = c->langevin_on; key.variant = step_variant();
   if (c->graphs_ok && memcmp(&key, &c->gkey, sizeof key) == 0) return LE_OK;
   destroy_graphs(c);
+  c->gkey_variant = key.variant;
   int r;
   for (int adv = 0; adv < 2; adv++) {
     CKG(cudaGraphCreate(&c->g_tail[adv], 0));
@@ -1094,11 +1148,15 @@ static int ensure_graphs(le_ctx *c) {
     if ((r = graph_add_unit(c, c->g_tail[adv], &tail, adv, false))) return r;
     CKG(cudaGraphInstantiate(&c->x_tail[adv], c->g_tail[adv], 0));
   }
-  CKG(cudaGraphCreate(&c->g_plain, 0));
-  cudaGraphNode_t tail = nullptr;
-  for (int u = 0; u < PLAIN_UNROLL; u++)
-    if ((r = graph_add_unit(c, c->g_plain, &tail, 1, true))) return r;
-  CKG(cudaGraphInstantiate(&c->x_plain, c->g_plain, 0));
+  // the steady-state graph, once per buffer parity at its launch: every k_decide flips the buffers, so the step kernel
+  // of unit u reads pos[p ^ ((u + 1) & 1)] -- known here, passed as a kernel argument (StepArgs::rdp1)
+  for (int p = 0; p < 2; p++) {
+    CKG(cudaGraphCreate(&c->g_plain[p], 0));
+    cudaGraphNode_t tail = nullptr;
+    for (int u = 0; u < PLAIN_UNROLL; u++)
+      if ((r = graph_add_unit(c, c->g_plain[p], &tail, 1, true, p ^ ((u + 1) & 1)))) return r;
+    CKG(cudaGraphInstantiate(&c->x_plain[p], c->g_plain[p], 0));
+  }
   c->gkey = key;
   c->graphs_ok = true;
   return LE_OK;
@@ -1179,22 +1237,20 @@ static void thermo_from_slot(le_ctx *c, const double *s, int64_t step, le_thermo
   t->nbonds = c->nbonds;
 }
 
-static void launch_step(le_ctx *c, const StepArgs &a, bool ev) {
-  const int grid = grid_for(c->d.gr0 - c->d.own0, STEP_THREADS) + (c->nranks > 1 ? 1 : 0);
-  const bool uni = c->P.pair_uniform != 0;
-  if (c->nranks > 1) {
-    if (ev) LAUNCH(c, (k_step<1, 1>), grid, STEP_THREADS, c->d, a);
-    else if (uni) LAUNCH(c, (k_step<0, 1, 4, 1>), grid, STEP_THREADS, c->d, a);
-    else LAUNCH(c, (k_step<0, 1>), grid, STEP_THREADS, c->d, a);
-  } else {
-    static const int minb = getenv("LE_STEP_MINB") ? atoi(getenv("LE_STEP_MINB")) : 4;
-    if (ev) LAUNCH(c, (k_step<1, 0>), grid, STEP_THREADS, c->d, a);
-    else if (minb == 5) LAUNCH(c, (k_step<0, 0, 5>), grid, STEP_THREADS, c->d, a);
-    else if (minb == 6) LAUNCH(c, (k_step<0, 0, 6>), grid, STEP_THREADS, c->d, a);
-    else if (minb == 3) LAUNCH(c, (k_step<0, 0, 3>), grid, STEP_THREADS, c->d, a);
-    else if (uni) LAUNCH(c, (k_step<0, 0, 4, 1>), grid, STEP_THREADS, c->d, a);
-    else LAUNCH(c, (k_step<0, 0>), grid, STEP_THREADS, c->d, a);
+// one force evaluation + integration; the host's record of the buffer parity (c->cur) is what the kernel will find
+// in Ctrl::cur when it runs, so it travels as an argument
+static void launch_step(le_ctx *c, StepArgs a, bool ev) {
+  if (ev) {
+    const int grid = grid_for(c->d.gr0 - c->d.own0, STEP_THREADS) + (c->nranks > 1 ? 1 : 0);
+    if (c->nranks > 1) LAUNCH(c, (k_step<1, 1>), grid, STEP_THREADS, c->d, a);
+    else LAUNCH(c, (k_step<1, 0>), grid, STEP_THREADS, c->d, a);
+    return;
   }
+  const StepKernel sk = plain_step_kernel(c, step_variant());
+  a.rdp1 = c->cur + 1;
+  if (c->timing && !c->capturing) time_mark(c, sk.name);
+  sk.fn<<<step_grid(c, sk), sk.threads, 0, c->stream>>>(c->d, a);
+  if (!c->capturing) c->direct_launches++;
 }
 
 // Update::ntimestep / beginstep / endstep of the run that starts now -> device control block
@@ -1314,7 +1370,7 @@ extern "C" int le_run(le_ctx *c, int64_t nsteps) {
     for (int64_t n = s + 1; plain && n <= s + PLAIN_UNROLL; n++)
       if (le_event_at(c, n) || want_thermo(n)) plain = false;
     if (plain) {
-      CK(cudaGraphLaunch(c->x_plain, c->stream));
+      CK(cudaGraphLaunch(c->x_plain[c->cur], c->stream));
       c->graph_node_launches += 2 * PLAIN_UNROLL;
       if (PLAIN_UNROLL & 1) c->cur ^= 1;
       s += PLAIN_UNROLL;

@@ -13,6 +13,7 @@ struct StepArgs {
   int slot;           // thermo slot to tally energy / virial / kinetic energy into (EV kernels)
   int write_force;    // store the conservative force of every atom in fout (tag order)
   int langevin;       // add drag + noise
+  int rdp1;           // 1 + position buffer holding the current coordinates when the host knows it, 0 = read Ctrl::cur (k_step2)
   int skip;           // development only (LE_STEP_SKIP): 1 no gathers, 2 no pair evaluation, 4 no bonds, 8 no neighbor rows, 32 no boundary-first block order
 };
 
