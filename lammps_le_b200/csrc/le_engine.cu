@@ -30,7 +30,7 @@ struct FixExUnloadCfg { int on, nevery, btype, seed; double rc, prob; };
 
 #define PLAIN_UNROLL 8      // timesteps per launch of the steady-state graph
 
-struct GraphKey { Dev d; int langevin; int variant; };
+struct GraphKey { Dev d; int langevin; int variant; int rb_variant; };
 
 struct le_ctx {
   int device, sm_count;
@@ -1049,6 +1049,12 @@ static int step_grid(const le_ctx *c, const StepKernel &sk) {
 }
 
 // ---- rebuild / step drivers -------------------------------------------------------------------------
+// LE_REBUILD_VARIANT (read at every le_run): bit 0 = k_gather2 (scatter form of the in-cell ordering)
+#ifndef LE_REBUILD_VARIANT_DEFAULT
+#define LE_REBUILD_VARIANT_DEFAULT 0
+#endif
+static int rebuild_variant() { const char *v = getenv("LE_REBUILD_VARIANT"); return v ? atoi(v) : LE_REBUILD_VARIANT_DEFAULT; }
+
 // the rebuild kernels; `direct` adds the bookkeeping k_decide does when the rebuild is a conditional graph node
 static void enqueue_rebuild(le_ctx *c, bool direct) {
   Dev &d = c->d;
@@ -1063,7 +1069,8 @@ static void enqueue_rebuild(le_ctx *c, bool direct) {
   LAUNCH(c, k_scan_blocks, 1, SCAN_BLOCK, d);
   LAUNCH(c, k_scan_apply, d.nscanblocks, SCAN_BLOCK, d);
   LAUNCH(c, k_cell_scatter, grid_for(nslots, 256), 256, d);
-  LAUNCH(c, k_gather, grid_for(nslots, 256), 256, d);
+  if (rebuild_variant() & 1) LAUNCH(c, k_gather2, grid_for(nslots, 256), 256, d);
+  else LAUNCH(c, k_gather, grid_for(nslots, 256), 256, d);
   if (dd) {
     LAUNCH(c, k_push_ghosts, grid_for(std::max(d.own0, d.halo * d.ncell[1] * d.ncell[2] + 1), 256), 256, d);
     LAUNCH(c, k_rb_post_ghosts, 1, 1, d);
@@ -1137,7 +1144,7 @@ static int graph_add_unit(le_ctx *c, cudaGraph_t g, cudaGraphNode_t *tail, int a
 
 static int ensure_graphs(le_ctx *c) {
   GraphKey key; memset(&key, 0, sizeof key);
-  key.d = c->d; key.langevin = c->langevin_on; key.variant = step_variant();
+  key.d = c->d; key.langevin = c->langevin_on; key.variant = step_variant(); key.rb_variant = rebuild_variant();
   if (c->graphs_ok && memcmp(&key, &c->gkey, sizeof key) == 0) return LE_OK;
   destroy_graphs(c);
   c->gkey_variant = key.variant;

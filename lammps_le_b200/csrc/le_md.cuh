@@ -656,6 +656,31 @@ __global__ void k_gather(Dev d) {
   }
 }
 
+// k_gather as a scatter: the thread of unsorted member i counts the members of its cell with a smaller tag (one pass
+// over the cell instead of one pass per member) and writes i's state to slot cell_start + rank.  Same permutation,
+// same arrays as k_gather.
+__global__ void k_gather2(Dev d) {
+  const int4 *__restrict__ pos = d.pos[d.ctrl->cur];
+  const int lo = d.own0, hi = d.own0 + d.ctrl->nown;
+  for (int k = lo + blockIdx.x * blockDim.x + threadIdx.x; k < hi; k += gridDim.x * blockDim.x) {
+    const int i = d.order[k];
+    const int4 p = pos[i];
+    const int c = d.cellid[i];
+    const int s = d.cell_start[c], e = d.cell_start[c + 1];
+    const int tg = p.w >> 3;
+    int rank = 0;
+    if (e - s > 1) {
+#pragma unroll 4
+      for (int b = s; b < e; b++) rank += (pos[d.order[b]].w >> 3) < tg;
+    }
+    const int ks = s + rank;
+    d.pos_hold[ks] = p;
+    d.vel_tmp[ks] = d.vel[i];
+    d.img_hold[ks] = d.img[i];
+    d.map[tg - 1] = ks;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // rebuild, part 2 (multi-GPU): ghost creation (CommBrick::borders, src/comm_brick.cpp:727-876).
 //   Because x is the slowest index of the local order, the atoms of the slab's first / last `halo`
