@@ -1049,7 +1049,8 @@ static int step_grid(const le_ctx *c, const StepKernel &sk) {
 }
 
 // ---- rebuild / step drivers -------------------------------------------------------------------------
-// LE_REBUILD_VARIANT (read at every le_run): bit 0 = k_gather2 (scatter form of the in-cell ordering)
+// LE_REBUILD_VARIANT (read at every le_run): bit 0 = k_gather2 (scatter form of the in-cell ordering), bit 1 / bit 2 =
+// k_build screens 2 / 8 candidates per trip instead of 4
 #ifndef LE_REBUILD_VARIANT_DEFAULT
 #define LE_REBUILD_VARIANT_DEFAULT 0
 #endif
@@ -1079,7 +1080,10 @@ static void enqueue_rebuild(le_ctx *c, bool direct) {
   {
     static const int minb = getenv("LE_BUILD_MINB") ? atoi(getenv("LE_BUILD_MINB")) : 8;
     const int g = grid_for(nslots, BUILD_THREADS);
-    if (minb == 10) LAUNCH(c, k_build<10>, g, BUILD_THREADS, d);
+    const int rbv = rebuild_variant();
+    if (rbv & 2) LAUNCH(c, (k_build<8, 2>), g, BUILD_THREADS, d);
+    else if (rbv & 4) LAUNCH(c, (k_build<8, 8>), g, BUILD_THREADS, d);
+    else if (minb == 10) LAUNCH(c, k_build<10>, g, BUILD_THREADS, d);
     else if (minb == 12) LAUNCH(c, k_build<12>, g, BUILD_THREADS, d);
     else if (minb == 16) LAUNCH(c, k_build<16>, g, BUILD_THREADS, d);
     else if (minb == 6) LAUNCH(c, k_build<6>, g, BUILD_THREADS, d);

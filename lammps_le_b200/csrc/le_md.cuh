@@ -820,7 +820,8 @@ __device__ __forceinline__ void build_accept(const Dev &d, BuildCtx &B, const in
   B.n++;
 }
 
-template <int MINB>
+// W: candidates fetched and screened per trip of the inner loop (independent loads in flight vs padded slots)
+template <int MINB, int W = 4>
 __global__ void __launch_bounds__(BUILD_THREADS, MINB) k_build(Dev d) {
   __shared__ int s_q[BUILD_QUEUE][BUILD_THREADS];
   const int cap = d.cap;
@@ -886,12 +887,12 @@ __global__ void __launch_bounds__(BUILD_THREADS, MINB) k_build(Dev d) {
         if (yc < 0) yc += ncy; else if (yc >= ncy) yc -= ncy;
         const int base = cell_slot(d, xc, yc, 0);
         const int lo = __ldg(&d.cell_start[base + za]), hi = __ldg(&d.cell_start[base + zb + 1]);
-        for (int j = lo; j < hi; j += 4) {
-          int4 p[4];
+        for (int j = lo; j < hi; j += W) {
+          int4 p[W];
 #pragma unroll
-          for (int u = 0; u < 4; u++) p[u] = __ldg(&ph[min(j + u, hi - 1)]);
+          for (int u = 0; u < W; u++) p[u] = __ldg(&ph[min(j + u, hi - 1)]);
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
+          for (int u = 0; u < W; u++) {
             const int idx = (int)((unsigned)p[u].x - (unsigned)pi.x);
             const int idy = (int)((unsigned)p[u].y - (unsigned)pi.y);
             const int idz = (int)((unsigned)p[u].z - (unsigned)pi.z);
