@@ -1001,14 +1001,15 @@ extern "C" int le_set_velocities(le_ctx *c, const double *v) {
 
 // ---- which plain step kernel (no energy / virial tally) -----------------------------------------------
 // LE_STEP_VARIANT (read at every le_run, so one process can compare variants): 0 = k_step; bit 0 = k_step2 (le_step2.cuh),
-// bit 1 = 128 threads per block instead of 256, bit 2 = L2 prefetch one wave ahead, bit 3 = int -> double on the fp64
-// pipe, bit 4 = k_step2 also on several GPUs, bit 5 = persistent grid (with bit 2: prefetch into the L1).  k_step2 needs the uniform lj/cut case and special weights in {0, 1};
-// otherwise k_step runs whatever the switch says.
+// bit 1 = 128 threads per block instead of 256, bit 2 = L2 prefetch one wave ahead, bit 5 = persistent grid (k_step2p),
+// bits 5 + 3 = persistent and software-pipelined (k_step2q; bit 6: at full occupancy, with spills), bit 4 = k_step2 also
+// on several GPUs.  k_step2 needs the uniform lj/cut case and special weights in {0, 1}; otherwise k_step runs whatever
+// the switch says.
 #ifndef LE_STEP_VARIANT_DEFAULT
 #define LE_STEP_VARIANT_DEFAULT 0
 #endif
 typedef void (*step_fn_t)(Dev, StepArgs);
-struct StepKernel { step_fn_t fn; int threads; const char *name; bool persistent; };
+struct StepKernel { step_fn_t fn; int threads; const char *name; int wave_blocks; };   // wave_blocks: persistent grid, blocks per SM (0 = one block per NT atoms)
 
 static int step_variant() { const char *v = getenv("LE_STEP_VARIANT"); return v ? atoi(v) : LE_STEP_VARIANT_DEFAULT; }
 
@@ -1018,19 +1019,21 @@ static bool step2_eligible(const le_ctx *c) {
   return true;
 }
 
-#define STEP2_CASE(dd, nt, pf, mg) { (step_fn_t)k_step2<dd, nt, pf, mg>, nt, "(k_step2<" #dd "," #nt "," #pf "," #mg ">)", false }
-#define STEP2P_CASE(nt, pf, mg) { (step_fn_t)k_step2p<nt, pf, mg>, nt, "(k_step2p<" #nt "," #pf "," #mg ">)", true }
+#define STEP2_CASE(dd, nt, pf) { (step_fn_t)k_step2<dd, nt, pf, 0>, nt, "(k_step2<" #dd "," #nt "," #pf ">)", 0 }
+#define STEP2P_CASE(nt, pf) { (step_fn_t)k_step2p<nt, pf, 0>, nt, "(k_step2p<" #nt "," #pf ">)", 1024 / nt }
+#define STEP2Q_CASE(nt, bps) { (step_fn_t)k_step2q<nt, bps, 0>, nt, "(k_step2q<" #nt "," #bps ">)", bps }
 static StepKernel plain_step_kernel(const le_ctx *c, int variant) {
   const bool dd = c->nranks > 1;
   if ((variant & 1) && step2_eligible(c) && (!dd || (variant & 16))) {
-    const bool small = variant & 2, pf = variant & 4, mg = variant & 8, pers = variant & 32;
-    if (dd) return small ? StepKernel STEP2_CASE(1, 128, 0, 0) : StepKernel STEP2_CASE(1, 256, 0, 0);
-    static const StepKernel tab[16] = {
-        STEP2_CASE(0, 256, 0, 0), STEP2_CASE(0, 128, 0, 0), STEP2_CASE(0, 256, 1, 0), STEP2_CASE(0, 128, 1, 0),
-        STEP2_CASE(0, 256, 0, 1), STEP2_CASE(0, 128, 0, 1), STEP2_CASE(0, 256, 1, 1), STEP2_CASE(0, 128, 1, 1),
-        STEP2P_CASE(256, 0, 0), STEP2P_CASE(128, 0, 0), STEP2P_CASE(256, 1, 0), STEP2P_CASE(128, 1, 0),
-        STEP2P_CASE(256, 0, 1), STEP2P_CASE(128, 0, 1), STEP2P_CASE(256, 1, 1), STEP2P_CASE(128, 1, 1)};
-    return tab[(small ? 1 : 0) | (pf ? 2 : 0) | (mg ? 4 : 0) | (pers ? 8 : 0)];
+    const bool small = variant & 2, pf = variant & 4, pipe = variant & 8, pers = variant & 32, full = variant & 64;
+    if (dd) return small ? StepKernel STEP2_CASE(1, 128, 0) : StepKernel STEP2_CASE(1, 256, 0);
+    if (pers && pipe) {
+      if (small) return full ? StepKernel STEP2Q_CASE(128, 8) : StepKernel STEP2Q_CASE(128, 6);
+      return full ? StepKernel STEP2Q_CASE(256, 4) : StepKernel STEP2Q_CASE(256, 3);
+    }
+    static const StepKernel tab[8] = {STEP2_CASE(0, 256, 0), STEP2_CASE(0, 128, 0), STEP2_CASE(0, 256, 1), STEP2_CASE(0, 128, 1),
+                                      STEP2P_CASE(256, 0), STEP2P_CASE(128, 0), STEP2P_CASE(256, 1), STEP2P_CASE(128, 1)};
+    return tab[(small ? 1 : 0) | (pf ? 2 : 0) | (pers ? 4 : 0)];
   }
   const bool uni = c->P.pair_uniform != 0;
   static const int minb = getenv("LE_STEP_MINB") ? atoi(getenv("LE_STEP_MINB")) : 4;
@@ -1038,14 +1041,14 @@ static StepKernel plain_step_kernel(const le_ctx *c, int variant) {
   if (dd) fn = uni ? (step_fn_t)k_step<0, 1, 4, 1> : (step_fn_t)k_step<0, 1>;
   else fn = minb == 5 ? (step_fn_t)k_step<0, 0, 5> : minb == 6 ? (step_fn_t)k_step<0, 0, 6> : minb == 3 ? (step_fn_t)k_step<0, 0, 3>
             : uni ? (step_fn_t)k_step<0, 0, 4, 1> : (step_fn_t)k_step<0, 0>;
-  return StepKernel{fn, STEP_THREADS, "(k_step<0>)", false};
+  return StepKernel{fn, STEP_THREADS, "(k_step<0>)", 0};
 }
 
 // blocks of a plain step launch: one per NT owned slots (+1 boundary bookkeeping block on a slab); a persistent kernel
 // gets one wave of resident blocks
 static int step_grid(const le_ctx *c, const StepKernel &sk) {
   const int g = grid_for(c->d.gr0 - c->d.own0, sk.threads) + (c->nranks > 1 ? 1 : 0);
-  return sk.persistent ? std::min(g, c->sm_count * (1024 / sk.threads)) : g;
+  return sk.wave_blocks ? std::min(g, c->sm_count * sk.wave_blocks) : g;
 }
 
 // ---- rebuild / step drivers -------------------------------------------------------------------------

@@ -110,10 +110,30 @@ __device__ __forceinline__ void philox4x32_7w(unsigned c0, unsigned c1, unsigned
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-// one atom (slot i) of one timestep.  inext: the slot this thread's successor works on (the same thread in a persistent
-// grid, another block's thread otherwise), or -1; PF asks for its lines ahead of time (PF = 1: into the L2, 2: into the L1)
+// the loads of an atom that the gathers depend on: its own position, the list counts, the first four neighbor rows and
+// the first three bond rows.  No load depends on another.
+struct Step2Head { int4 pi; unsigned cnt, en0, en1, en2, en3, eb0, eb1, eb2; };
+
+__device__ __forceinline__ Step2Head step2_head(const Dev &d, const int4 *__restrict__ posr, const int i) {
+  const int cap = d.cap;
+  const unsigned *__restrict__ neigh = d.neigh;
+  const unsigned *__restrict__ bondrow = d.bondrow;
+  Step2Head h;
+  h.pi = posr[i];
+  h.cnt = d.counts[i];
+  h.en0 = __ldg(&neigh[i]); h.en1 = __ldg(&neigh[(size_t)cap + i]);
+  h.en2 = __ldg(&neigh[(size_t)2 * cap + i]); h.en3 = __ldg(&neigh[(size_t)3 * cap + i]);
+  h.eb0 = __ldg(&bondrow[i]);                 // bondrow holds d.bpa rows
+  h.eb1 = d.bpa > 1 ? __ldg(&bondrow[(size_t)cap + i]) : 0u;
+  h.eb2 = d.bpa > 2 ? __ldg(&bondrow[(size_t)2 * cap + i]) : 0u;
+  return h;
+}
+
+// one atom (slot i) of one timestep, its head already requested.  inext: the slot this thread's successor works on
+// (the same thread in a persistent grid, another block's thread otherwise), or -1; PF asks for its lines ahead of time
+// (PF = 1: into the L2, 2: into the L1)
 template <int DD, int PF, int MAGIC>
-__device__ __forceinline__ void step2_atom(const Dev &d, const StepArgs &a, const int i, const int inext, const int rd) {
+__device__ __forceinline__ void step2_atom(const Dev &d, const StepArgs &a, const int i, const int inext, const int rd, const Step2Head &h) {
   const int cap = d.cap;
   Ctrl *__restrict__ ctrl = d.ctrl;
   const unsigned *__restrict__ neigh = d.neigh;
@@ -121,14 +141,10 @@ __device__ __forceinline__ void step2_atom(const Dev &d, const StepArgs &a, cons
   const int4 *__restrict__ posr = d.pos[rd];
   int4 *__restrict__ posw = d.pos[rd ^ 1];
 
-  // ---- batch 1: everything addressed by i; no load depends on another ----
-  const int4 pi = posr[i];
+  // ---- batch 1 (with the head): everything addressed by i ----
+  const int4 pi = h.pi;
+  const unsigned cnt = h.cnt, en0 = h.en0, en1 = h.en1, en2 = h.en2, en3 = h.en3, eb0 = h.eb0, eb1 = h.eb1, eb2 = h.eb2;
   float4 vi = d.vel[i];
-  const unsigned cnt = d.counts[i];
-  const unsigned en0 = __ldg(&neigh[i]), en1 = __ldg(&neigh[(size_t)cap + i]);
-  const unsigned en2 = __ldg(&neigh[(size_t)2 * cap + i]), en3 = __ldg(&neigh[(size_t)3 * cap + i]);
-  const unsigned eb0 = __ldg(&bondrow[i]);                 // bondrow holds d.bpa rows
-  const unsigned eb1 = d.bpa > 1 ? __ldg(&bondrow[(size_t)cap + i]) : 0u, eb2 = d.bpa > 2 ? __ldg(&bondrow[(size_t)2 * cap + i]) : 0u;
   const int4 ph = d.pos_hold[i];
   const long long step = ctrl->step;
   if (PF && inext >= 0) {
@@ -319,16 +335,39 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_step2(Dev d, StepArgs a) {
   }
   const int rd = a.rdp1 ? a.rdp1 - 1 : d.ctrl->cur;
   const int inext = (!DD && i + STEP2_WAVE < d.own0 + d.N) ? i + STEP2_WAVE : -1;
-  step2_atom<DD, PF, MAGIC>(d, a, i, inext, rd);
+  step2_atom<DD, PF, MAGIC>(d, a, i, inext, rd, step2_head(d, d.pos[rd], i));
 }
 
-// persistent form (one GPU): one wave of blocks walks the atoms with a grid stride; the lines of a thread's next atom
-// are requested (into the L1 of the SM that will use them) before the current one is worked on
+// persistent form (one GPU): one wave of blocks walks the atoms with a grid stride (no block launches inside the
+// step, no partial last wave).  PF = 1 / 2: the lines of a thread's next atom are requested into the L2 / L1 ahead of time
 template <int NT, int PF, int MAGIC>
 __global__ void __launch_bounds__(NT, 1024 / NT) k_step2p(Dev d, StepArgs a) {
   const int rd = a.rdp1 ? a.rdp1 - 1 : d.ctrl->cur;
   const int end = d.own0 + d.N, stride = gridDim.x * NT;
 #pragma unroll 1
   for (int i = d.own0 + blockIdx.x * NT + threadIdx.x; i < end; i += stride)
-    step2_atom<0, PF ? 2 : 0, MAGIC>(d, a, i, i + stride < end ? i + stride : -1, rd);
+    step2_atom<0, PF, MAGIC>(d, a, i, i + stride < end ? i + stride : -1, rd, step2_head(d, d.pos[rd], i));
+}
+
+// persistent and software-pipelined: the head of a thread's NEXT atom is loaded into registers before the current atom
+// is worked on, so the gathers of every atom but the first start without waiting for memory.  Twelve more live
+// registers: NT x BPS threads per SM with BPS chosen so that nothing spills.
+template <int NT, int BPS, int MAGIC>
+__global__ void __launch_bounds__(NT, BPS) k_step2q(Dev d, StepArgs a) {
+  const int rd = a.rdp1 ? a.rdp1 - 1 : d.ctrl->cur;
+  const int4 *__restrict__ posr = d.pos[rd];
+  const int end = d.own0 + d.N, stride = gridDim.x * NT;
+  int i = d.own0 + blockIdx.x * NT + threadIdx.x;
+  if (i >= end) return;
+  Step2Head cur = step2_head(d, posr, i);
+#pragma unroll 1
+  for (;;) {
+    const int in = i + stride;
+    const bool more = in < end;
+    const Step2Head nxt = step2_head(d, posr, more ? in : i);     // the last trip re-reads its own head (cache hits)
+    step2_atom<0, 0, MAGIC>(d, a, i, -1, rd, cur);
+    if (!more) break;
+    cur = nxt;
+    i = in;
+  }
 }

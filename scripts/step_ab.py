@@ -16,7 +16,7 @@ import numpy as np
 from lammps_le_b200 import systems
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
-variants = [int(v) for v in sys.argv[2:]] or [0, 1, 3, 5, 9, 33, 35, 37, 39, 47, 1001, 1002, 1004]
+variants = [int(v) for v in sys.argv[2:]] or [0, 1, 3, 5, 33, 35, 37, 39, 41, 43, 105, 107, 1001]
 if variants[0] != 0:
     variants = [0] + variants
 # a variant >= 1000 is k_step with LE_REBUILD_VARIANT = variant - 1000 (rebuild-chain kernels, same identity check)
