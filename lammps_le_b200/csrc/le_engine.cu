@@ -577,6 +577,8 @@ static int build_params(le_ctx *c) {
     P.bcore_d[k] = 1.2599210498948732 * P.bsig2_d[k];        // TWO_1_3 (bond_fene.cpp:22)
     P.beps48_d[k] = 48.0 * P.beps_d[k];
   }
+  P.bond_all_fene = c->nbondtypes > 0;
+  for (int k = 0; k < c->nbondtypes; k++) if (c->bstyle[k] != 1) P.bond_all_fene = 0;
   P.t_start = (float)c->t_start; P.t_stop = (float)c->t_stop; P.tsqrt_const = (float)sqrt(c->t_start);
   P.dt = (float)c->dt; P.dtf = (float)(0.5 * c->dt);       // FixNVE::init, ftm2v = 1
   P.triggersq = (float)(0.25 * c->skin * c->skin);
@@ -1002,7 +1004,8 @@ extern "C" int le_set_velocities(le_ctx *c, const double *v) {
 // ---- which plain step kernel (no energy / virial tally) -----------------------------------------------
 // LE_STEP_VARIANT (read at every le_run, so one process can compare variants): 0 = k_step; bit 0 = k_step2 (le_step2.cuh),
 // bit 1 = 128 threads per block instead of 256, bit 2 = L2 prefetch one wave ahead, bit 5 = persistent grid (k_step2p),
-// bits 5 + 3 = persistent and software-pipelined (k_step2q; bit 6: at full occupancy, with spills), bit 4 = k_step2 also
+// bits 5 + 3 = persistent and software-pipelined (k_step2q; bit 6: at full occupancy, with spills), bit 7 = thermostat
+// force computed under the gathers + two FENE bonds side by side (with or without bit 5), bit 4 = k_step2 also
 // on several GPUs.  k_step2 needs the uniform lj/cut case and special weights in {0, 1}; otherwise k_step runs whatever
 // the switch says.
 #ifndef LE_STEP_VARIANT_DEFAULT
@@ -1030,6 +1033,12 @@ static StepKernel plain_step_kernel(const le_ctx *c, int variant) {
     if (pers && pipe) {
       if (small) return full ? StepKernel STEP2Q_CASE(128, 8) : StepKernel STEP2Q_CASE(128, 6);
       return full ? StepKernel STEP2Q_CASE(256, 4) : StepKernel STEP2Q_CASE(256, 3);
+    }
+    if (variant & 128) {
+      if (pers) return small ? StepKernel{(step_fn_t)k_step2p<128, 0, 0, 1>, 128, "(k_step2p<128,0,ilp>)", 8}
+                             : StepKernel{(step_fn_t)k_step2p<256, 0, 0, 1>, 256, "(k_step2p<256,0,ilp>)", 4};
+      return small ? StepKernel{(step_fn_t)k_step2<0, 128, 0, 0, 1>, 128, "(k_step2<0,128,0,ilp>)", 0}
+                   : StepKernel{(step_fn_t)k_step2<0, 256, 0, 0, 1>, 256, "(k_step2<0,256,0,ilp>)", 0};
     }
     static const StepKernel tab[8] = {STEP2_CASE(0, 256, 0), STEP2_CASE(0, 128, 0), STEP2_CASE(0, 256, 1), STEP2_CASE(0, 128, 1),
                                       STEP2P_CASE(256, 0), STEP2P_CASE(128, 0), STEP2P_CASE(256, 1), STEP2P_CASE(128, 1)};

@@ -95,6 +95,42 @@ __device__ __forceinline__ void bond_eval2(double &fx, double &fy, double &fz, C
   fx = __fma_rn(dx, fbond, fx); fy = __fma_rn(dy, fbond, fy); fz = __fma_rn(dz, fbond, fz);
 }
 
+// two FENE bonds side by side in one straight line of code (independent fp64 chains interleave; k_step's per-instruction
+// profile shows a dependent instruction every ~8 cycles, the bonds being the longest chains).  The WCA core term is
+// computed whether it applies or not and selected; values and order of the sums are those of two bond_eval2 calls.
+template <int MAGIC>
+__device__ __forceinline__ void fene_eval2x(double &fx, double &fy, double &fz, Ctrl *ctrl, const int4 pi, const int4 pa, const int4 pb,
+                                            unsigned ea, unsigned eb, int tagi) {
+  const int bta = ea >> 28, btb = eb >> 28;
+  const double dya = __dmul_rn(le_i2d<MAGIC>((int)((unsigned)pi.y - (unsigned)pa.y)), c_P.scale[1]);
+  const double dyb = __dmul_rn(le_i2d<MAGIC>((int)((unsigned)pi.y - (unsigned)pb.y)), c_P.scale[1]);
+  const double dxa = __dmul_rn(le_i2d<MAGIC>((int)((unsigned)pi.x - (unsigned)pa.x)), c_P.scale[0]);
+  const double dxb = __dmul_rn(le_i2d<MAGIC>((int)((unsigned)pi.x - (unsigned)pb.x)), c_P.scale[0]);
+  const double dza = __dmul_rn(le_i2d<MAGIC>((int)((unsigned)pi.z - (unsigned)pa.z)), c_P.scale[2]);
+  const double dzb = __dmul_rn(le_i2d<MAGIC>((int)((unsigned)pi.z - (unsigned)pb.z)), c_P.scale[2]);
+  const double rsqa = __fma_rn(dza, dza, __fma_rn(dxa, dxa, __dmul_rn(dya, dya)));
+  const double rsqb = __fma_rn(dzb, dzb, __fma_rn(dxb, dxb, __dmul_rn(dyb, dyb)));
+  double rla = __fma_rn(-rsqa, c_P.binvr0sq_d[bta], 1.0), rlb = __fma_rn(-rsqb, c_P.binvr0sq_d[btb], 1.0);
+  if (rla < 0.1 || rlb < 0.1) {          // rare: an overstretched bond
+    if (rla <= -3.0) le_raise(ctrl, LE_DERR_BAD_FENE, tagi, (int)(ea & BOND_IDX_MASK));
+    else if (rlb <= -3.0) le_raise(ctrl, LE_DERR_BAD_FENE, tagi, (int)(eb & BOND_IDX_MASK));
+    if (rla < 0.1) rla = 0.1;
+    if (rlb < 0.1) rlb = 0.1;
+  }
+  const double ta = le_rcp2(__dmul_rn(rla, rsqa)), tb = le_rcp2(__dmul_rn(rlb, rsqb));
+  const double inv_rla = __dmul_rn(ta, rsqa), inv_rsqa = __dmul_rn(ta, rla);
+  const double inv_rlb = __dmul_rn(tb, rsqb), inv_rsqb = __dmul_rn(tb, rlb);
+  double fa = __dmul_rn(-c_P.bk_d[bta], inv_rla), fb = __dmul_rn(-c_P.bk_d[btb], inv_rlb);
+  const double sr2a = __dmul_rn(c_P.bsig2_d[bta], inv_rsqa), sr2b = __dmul_rn(c_P.bsig2_d[btb], inv_rsqb);
+  const double sr6a = __dmul_rn(sr2a, __dmul_rn(sr2a, sr2a)), sr6b = __dmul_rn(sr2b, __dmul_rn(sr2b, sr2b));
+  const double fca = __fma_rn(__dmul_rn(__dmul_rn(c_P.beps48_d[bta], sr6a), __dadd_rn(sr6a, -0.5)), inv_rsqa, fa);
+  const double fcb = __fma_rn(__dmul_rn(__dmul_rn(c_P.beps48_d[btb], sr6b), __dadd_rn(sr6b, -0.5)), inv_rsqb, fb);
+  fa = rsqa < c_P.bcore_d[bta] ? fca : fa;
+  fb = rsqb < c_P.bcore_d[btb] ? fcb : fb;
+  fx = __fma_rn(dxa, fa, fx); fy = __fma_rn(dya, fa, fy); fz = __fma_rn(dza, fa, fz);
+  fx = __fma_rn(dxb, fb, fx); fy = __fma_rn(dyb, fb, fy); fz = __fma_rn(dzb, fb, fz);
+}
+
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -108,6 +144,26 @@ __device__ __forceinline__ void philox4x32_7w(unsigned c0, unsigned c1, unsigned
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// Langevin drag + uniform noise of one atom (FixLangevin::post_force_templated, src/fix_langevin.cpp:587-777)
+__device__ __forceinline__ void step2_langevin(float &lx, float &ly, float &lz, const Ctrl *ctrl, const float4 vi, int tag, int ti, long long step) {
+  unsigned r[4];
+  philox4x32_7w((unsigned)tag, (unsigned)(step & 0xffffffffll), (unsigned)((unsigned long long)step >> 32), 0x4c45u,
+                 c_P.seed_lo, c_P.seed_hi, r);
+  float tsq = c_P.tsqrt_const;
+  if (c_P.t_start != c_P.t_stop) {   // FixLangevin::compute_target (src/fix_langevin.cpp:784-820)
+    float delta = (float)(step - ctrl->run_begin);
+    if (delta != 0.0f) delta /= (float)(ctrl->run_end - ctrl->run_begin);
+    tsq = sqrtf(__fmaf_rn(delta, __fadd_rn(c_P.t_stop, -c_P.t_start), c_P.t_start));
+  }
+  const float g1 = c_P.gfac1[ti], g2 = __fmul_rn(c_P.gfac2[ti], tsq);
+  const float u0 = __fmaf_rn((float)(r[0] >> 8), 5.9604644775390625e-8f, -0.5f);
+  const float u1 = __fmaf_rn((float)(r[1] >> 8), 5.9604644775390625e-8f, -0.5f);
+  const float u2 = __fmaf_rn((float)(r[2] >> 8), 5.9604644775390625e-8f, -0.5f);
+  lx = __fmaf_rn(g1, vi.x, __fmul_rn(g2, u0));
+  ly = __fmaf_rn(g1, vi.y, __fmul_rn(g2, u1));
+  lz = __fmaf_rn(g1, vi.z, __fmul_rn(g2, u2));
 }
 
 // the loads of an atom that the gathers depend on: its own position, the list counts, the first four neighbor rows and
@@ -132,7 +188,7 @@ __device__ __forceinline__ Step2Head step2_head(const Dev &d, const int4 *__rest
 // one atom (slot i) of one timestep, its head already requested.  inext: the slot this thread's successor works on
 // (the same thread in a persistent grid, another block's thread otherwise), or -1; PF asks for its lines ahead of time
 // (PF = 1: into the L2, 2: into the L1)
-template <int DD, int PF, int MAGIC>
+template <int DD, int PF, int MAGIC, int ILP = 0>
 __device__ __forceinline__ void step2_atom(const Dev &d, const StepArgs &a, const int i, const int inext, const int rd, const Step2Head &h) {
   const int cap = d.cap;
   Ctrl *__restrict__ ctrl = d.ctrl;
@@ -178,6 +234,10 @@ __device__ __forceinline__ void step2_atom(const Dev &d, const StepArgs &a, cons
     et2 = nn > 6 ? __ldg(r4 + 2 * (size_t)cap) : 0u;
     et3 = nn > 7 ? __ldg(r4 + 3 * (size_t)cap) : 0u;
   }
+
+  // ILP: the thermostat's force is computed here, while the gathers are in flight (it needs nothing from them)
+  float lx = 0.f, ly = 0.f, lz = 0.f;
+  if (ILP && a.langevin) step2_langevin(lx, ly, lz, ctrl, vi, tag, ti, step);
 
   const float sx = c_P.fscale[0], sy = c_P.fscale[1], sz = c_P.fscale[2];
   const float cs = c_P.cutsq_screen[0];
@@ -232,9 +292,15 @@ __device__ __forceinline__ void step2_atom(const Dev &d, const StepArgs &a, cons
     const unsigned e = (b & 3u) ? ((b & 1u) ? en0 : en1) : ((b & 4u) ? en2 : en3);
     pair_eval2<MAGIC>(fx, fy, fz, pi, __ldg(&posr[e & NEIGH_IDX_MASK]));   // second touch of the position: an L1 hit
   }
-  if (0 < nb) bond_eval2<MAGIC>(fx, fy, fz, ctrl, pi, pb0, eb0, tag);
-  if (1 < nb) bond_eval2<MAGIC>(fx, fy, fz, ctrl, pi, pb1, eb1, tag);
-  if (2 < nb) bond_eval2<MAGIC>(fx, fy, fz, ctrl, pi, pb2, eb2, tag);
+  if (ILP && c_P.bond_all_fene) {
+    if (1 < nb) fene_eval2x<MAGIC>(fx, fy, fz, ctrl, pi, pb0, pb1, eb0, eb1, tag);
+    else if (0 < nb) bond_eval2<MAGIC>(fx, fy, fz, ctrl, pi, pb0, eb0, tag);
+    if (2 < nb) bond_eval2<MAGIC>(fx, fy, fz, ctrl, pi, pb2, eb2, tag);
+  } else {
+    if (0 < nb) bond_eval2<MAGIC>(fx, fy, fz, ctrl, pi, pb0, eb0, tag);
+    if (1 < nb) bond_eval2<MAGIC>(fx, fy, fz, ctrl, pi, pb1, eb1, tag);
+    if (2 < nb) bond_eval2<MAGIC>(fx, fy, fz, ctrl, pi, pb2, eb2, tag);
+  }
 #pragma unroll 1
   for (int mth = 3; mth < nb; mth++) {
     const unsigned e = __ldg(&bondrow[(size_t)mth * cap + i]);
@@ -242,25 +308,7 @@ __device__ __forceinline__ void step2_atom(const Dev &d, const StepArgs &a, cons
   }
 
   // ---- Langevin drag + uniform noise (post_force); fp32, added to the rounded conservative force ----
-  float lx = 0.f, ly = 0.f, lz = 0.f;
-  if (a.langevin) {
-    unsigned r[4];
-    philox4x32_7w((unsigned)tag, (unsigned)(step & 0xffffffffll), (unsigned)((unsigned long long)step >> 32), 0x4c45u,
-                   c_P.seed_lo, c_P.seed_hi, r);
-    float tsq = c_P.tsqrt_const;
-    if (c_P.t_start != c_P.t_stop) {   // FixLangevin::compute_target (src/fix_langevin.cpp:784-820)
-      float delta = (float)(step - ctrl->run_begin);
-      if (delta != 0.0f) delta /= (float)(ctrl->run_end - ctrl->run_begin);
-      tsq = sqrtf(__fmaf_rn(delta, __fadd_rn(c_P.t_stop, -c_P.t_start), c_P.t_start));
-    }
-    const float g1 = c_P.gfac1[ti], g2 = __fmul_rn(c_P.gfac2[ti], tsq);
-    const float u0 = __fmaf_rn((float)(r[0] >> 8), 5.9604644775390625e-8f, -0.5f);
-    const float u1 = __fmaf_rn((float)(r[1] >> 8), 5.9604644775390625e-8f, -0.5f);
-    const float u2 = __fmaf_rn((float)(r[2] >> 8), 5.9604644775390625e-8f, -0.5f);
-    lx = __fmaf_rn(g1, vi.x, __fmul_rn(g2, u0));
-    ly = __fmaf_rn(g1, vi.y, __fmul_rn(g2, u1));
-    lz = __fmaf_rn(g1, vi.z, __fmul_rn(g2, u2));
-  }
+  if (!ILP && a.langevin) step2_langevin(lx, ly, lz, ctrl, vi, tag, ti, step);
 
   // ---- velocity Verlet ----
   const float dtfm = c_P.dtfm[ti];
@@ -314,8 +362,9 @@ __device__ __forceinline__ void step2_atom(const Dev &d, const StepArgs &a, cons
 #define STEP2_WAVE (148 * 1024)   // atoms one wave of resident threads works on
 
 // DD: multi-GPU slab (halo stores fused in, boundary blocks first); NT: threads per block (1024 / NT blocks per SM);
-// PF: ask the L2 for the lines of the atom one wave ahead; MAGIC: see le_i2d
-template <int DD, int NT, int PF, int MAGIC>
+// PF: ask the L2 for the lines of the atom one wave ahead; MAGIC: see le_i2d; ILP: thermostat force computed while the
+// gathers are in flight, two FENE bonds evaluated side by side
+template <int DD, int NT, int PF, int MAGIC, int ILP = 0>
 __global__ void __launch_bounds__(NT, 1024 / NT) k_step2(Dev d, StepArgs a) {
   int i = d.own0 + blockIdx.x * NT + threadIdx.x;
   if (DD) {
@@ -335,18 +384,18 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_step2(Dev d, StepArgs a) {
   }
   const int rd = a.rdp1 ? a.rdp1 - 1 : d.ctrl->cur;
   const int inext = (!DD && i + STEP2_WAVE < d.own0 + d.N) ? i + STEP2_WAVE : -1;
-  step2_atom<DD, PF, MAGIC>(d, a, i, inext, rd, step2_head(d, d.pos[rd], i));
+  step2_atom<DD, PF, MAGIC, ILP>(d, a, i, inext, rd, step2_head(d, d.pos[rd], i));
 }
 
 // persistent form (one GPU): one wave of blocks walks the atoms with a grid stride (no block launches inside the
 // step, no partial last wave).  PF = 1 / 2: the lines of a thread's next atom are requested into the L2 / L1 ahead of time
-template <int NT, int PF, int MAGIC>
+template <int NT, int PF, int MAGIC, int ILP = 0>
 __global__ void __launch_bounds__(NT, 1024 / NT) k_step2p(Dev d, StepArgs a) {
   const int rd = a.rdp1 ? a.rdp1 - 1 : d.ctrl->cur;
   const int end = d.own0 + d.N, stride = gridDim.x * NT;
 #pragma unroll 1
   for (int i = d.own0 + blockIdx.x * NT + threadIdx.x; i < end; i += stride)
-    step2_atom<0, PF, MAGIC>(d, a, i, i + stride < end ? i + stride : -1, rd, step2_head(d, d.pos[rd], i));
+    step2_atom<0, PF, MAGIC, ILP>(d, a, i, i + stride < end ? i + stride : -1, rd, step2_head(d, d.pos[rd], i));
 }
 
 // persistent and software-pipelined: the head of a thread's NEXT atom is loaded into registers before the current atom
