@@ -1009,7 +1009,7 @@ extern "C" int le_set_velocities(le_ctx *c, const double *v) {
 // on several GPUs.  k_step2 needs the uniform lj/cut case and special weights in {0, 1}; otherwise k_step runs whatever
 // the switch says.
 #ifndef LE_STEP_VARIANT_DEFAULT
-#define LE_STEP_VARIANT_DEFAULT 0
+#define LE_STEP_VARIANT_DEFAULT 33   // k_step2p<256>: fastest of the variants measured at 1M beads (profiles/r01_step_variants.txt)
 #endif
 typedef void (*step_fn_t)(Dev, StepArgs);
 struct StepKernel { step_fn_t fn; int threads; const char *name; int wave_blocks; };   // wave_blocks: persistent grid, blocks per SM (0 = one block per NT atoms)
