@@ -14,8 +14,6 @@
 //     counts[cap]   nfull | nbond<<16
 //     neigh[maxneigh][cap]  ELL full neighbor rows; entry = k_j | which<<30
 //     bondrow[bpa][cap]     ELL bond partner rows; entry = k_j | (bondtype-1)<<28
-//     head[cap]     2 x uint4: counts + the first four neighbor entries + the first three bond entries of the atom again,
-//                   as one 32-byte record (one memory stream instead of eight for the loads every step starts with)
 //   tag order (index t-1; what the reference's Atom class holds, src/atom.h) -- replicated on every GPU
 //     num_bond, bond_type[N][bpa], bond_atom[N][bpa], nspecial[N][3], special[N][maxspecial]
 //     map[N]      tag-1 -> local slot, -1 if the atom is neither owned nor a ghost here (Atom::map, src/atom.h:354-358)
@@ -158,7 +156,6 @@ struct Dev {
   float4 *vel, *vel_tmp;
   int *img, *img_hold;
   unsigned *counts, *neigh, *bondrow;
-  uint4 *head;        // [2 cap] per atom {counts, neigh rows 0..2} {neigh row 3, bond rows 0..2}: one 32-byte record (k_step2 HR)
   // tag order
   int *num_bond, *bond_type, *bond_atom, *nspecial, *special, *map;
   int *type_tag;      // atom type by tag (the USER-LE fixes read and change types of atoms that may live on another GPU)

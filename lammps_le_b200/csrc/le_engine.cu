@@ -767,7 +767,6 @@ extern "C" int le_upload_atoms(le_ctx *c, int n, const int *tag, const int *type
   if ((r = dalloc(c, &d.counts, cap))) return r;
   if ((r = dalloc(c, &d.neigh, (size_t)cap * c->maxneigh))) return r;
   if ((r = dalloc(c, &d.bondrow, (size_t)cap * c->bpa))) return r;
-  if ((r = dalloc(c, &d.head, (size_t)cap * 2))) return r;
   if ((r = dalloc(c, &d.num_bond, n))) return r;
   if ((r = dalloc(c, &d.bond_type, (size_t)n * c->bpa))) return r;
   if ((r = dalloc(c, &d.bond_atom, (size_t)n * c->bpa))) return r;
@@ -1006,8 +1005,7 @@ extern "C" int le_set_velocities(le_ctx *c, const double *v) {
 // LE_STEP_VARIANT (read at every le_run, so one process can compare variants): 0 = k_step; bit 0 = k_step2 (le_step2.cuh),
 // bit 1 = 128 threads per block instead of 256, bit 2 = L2 prefetch one wave ahead, bit 5 = persistent grid (k_step2p),
 // bits 5 + 3 = persistent and software-pipelined (k_step2q; bit 6: at full occupancy, with spills), bit 7 = thermostat
-// force computed under the gathers + two FENE bonds side by side (with or without bit 5), bit 8 = counts and first rows
-// from the 32-byte head record (with or without bit 5), bit 4 = k_step2 also
+// force computed under the gathers + two FENE bonds side by side (with or without bit 5), bit 4 = k_step2 also
 // on several GPUs.  k_step2 needs the uniform lj/cut case and special weights in {0, 1}; otherwise k_step runs whatever
 // the switch says.
 #ifndef LE_STEP_VARIANT_DEFAULT
@@ -1035,10 +1033,6 @@ static StepKernel plain_step_kernel(const le_ctx *c, int variant) {
     if (pers && pipe) {
       if (small) return full ? StepKernel STEP2Q_CASE(128, 8) : StepKernel STEP2Q_CASE(128, 6);
       return full ? StepKernel STEP2Q_CASE(256, 4) : StepKernel STEP2Q_CASE(256, 3);
-    }
-    if (variant & 256) {
-      if (pers) return StepKernel{(step_fn_t)k_step2p<256, 0, 0, 0, 1>, 256, "(k_step2p<256,0,hr>)", 4};
-      return StepKernel{(step_fn_t)k_step2<0, 256, 0, 0, 0, 1>, 256, "(k_step2<0,256,0,hr>)", 0};
     }
     if (variant & 128) {
       if (pers) return small ? StepKernel{(step_fn_t)k_step2p<128, 0, 0, 1>, 128, "(k_step2p<128,0,ilp>)", 8}

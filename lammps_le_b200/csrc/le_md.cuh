@@ -940,18 +940,6 @@ __global__ void __launch_bounds__(BUILD_THREADS, MINB) k_build(Dev d) {
   }
   if (missing) le_raise(d.ctrl, LE_DERR_MISSING_ATOM, tagi, nb);
   d.counts[i] = (unsigned)B.n | ((unsigned)nb << 16);
-  // the head record: what a step reads first, gathered into 32 contiguous bytes (entries beyond the counts are zero)
-  uint4 h0, h1;
-  h0.x = (unsigned)B.n | ((unsigned)nb << 16);
-  h0.y = B.n > 0 ? B.row[0] : 0u;
-  h0.z = B.n > 1 ? B.row[(size_t)cap] : 0u;
-  h0.w = B.n > 2 ? B.row[(size_t)2 * cap] : 0u;
-  h1.x = B.n > 3 ? B.row[(size_t)3 * cap] : 0u;
-  h1.y = (nb > 0 && !missing) ? d.bondrow[i] : 0u;
-  h1.z = (nb > 1 && !missing) ? d.bondrow[(size_t)cap + i] : 0u;
-  h1.w = (nb > 2 && !missing) ? d.bondrow[(size_t)2 * cap + i] : 0u;
-  d.head[2 * (size_t)i] = h0;
-  d.head[2 * (size_t)i + 1] = h1;
 }
 
 // list statistics on demand

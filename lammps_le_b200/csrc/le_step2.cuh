@@ -170,19 +170,12 @@ __device__ __forceinline__ void step2_langevin(float &lx, float &ly, float &lz, 
 // the first three bond rows.  No load depends on another.
 struct Step2Head { int4 pi; unsigned cnt, en0, en1, en2, en3, eb0, eb1, eb2; };
 
-// HR: counts and rows from the atom's 32-byte head record (two 16-byte loads of one stream) instead of eight arrays
-template <int HR = 0>
 __device__ __forceinline__ Step2Head step2_head(const Dev &d, const int4 *__restrict__ posr, const int i) {
   const int cap = d.cap;
   const unsigned *__restrict__ neigh = d.neigh;
   const unsigned *__restrict__ bondrow = d.bondrow;
   Step2Head h;
   h.pi = posr[i];
-  if (HR) {
-    const uint4 a = __ldg(&d.head[2 * (size_t)i]), b = __ldg(&d.head[2 * (size_t)i + 1]);
-    h.cnt = a.x; h.en0 = a.y; h.en1 = a.z; h.en2 = a.w; h.en3 = b.x; h.eb0 = b.y; h.eb1 = b.z; h.eb2 = b.w;
-    return h;
-  }
   h.cnt = d.counts[i];
   h.en0 = __ldg(&neigh[i]); h.en1 = __ldg(&neigh[(size_t)cap + i]);
   h.en2 = __ldg(&neigh[(size_t)2 * cap + i]); h.en3 = __ldg(&neigh[(size_t)3 * cap + i]);
@@ -371,7 +364,7 @@ __device__ __forceinline__ void step2_atom(const Dev &d, const StepArgs &a, cons
 // DD: multi-GPU slab (halo stores fused in, boundary blocks first); NT: threads per block (1024 / NT blocks per SM);
 // PF: ask the L2 for the lines of the atom one wave ahead; MAGIC: see le_i2d; ILP: thermostat force computed while the
 // gathers are in flight, two FENE bonds evaluated side by side
-template <int DD, int NT, int PF, int MAGIC, int ILP = 0, int HR = 0>
+template <int DD, int NT, int PF, int MAGIC, int ILP = 0>
 __global__ void __launch_bounds__(NT, 1024 / NT) k_step2(Dev d, StepArgs a) {
   int i = d.own0 + blockIdx.x * NT + threadIdx.x;
   if (DD) {
@@ -391,18 +384,18 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_step2(Dev d, StepArgs a) {
   }
   const int rd = a.rdp1 ? a.rdp1 - 1 : d.ctrl->cur;
   const int inext = (!DD && i + STEP2_WAVE < d.own0 + d.N) ? i + STEP2_WAVE : -1;
-  step2_atom<DD, PF, MAGIC, ILP>(d, a, i, inext, rd, step2_head<HR>(d, d.pos[rd], i));
+  step2_atom<DD, PF, MAGIC, ILP>(d, a, i, inext, rd, step2_head(d, d.pos[rd], i));
 }
 
 // persistent form (one GPU): one wave of blocks walks the atoms with a grid stride (no block launches inside the
 // step, no partial last wave).  PF = 1 / 2: the lines of a thread's next atom are requested into the L2 / L1 ahead of time
-template <int NT, int PF, int MAGIC, int ILP = 0, int HR = 0>
+template <int NT, int PF, int MAGIC, int ILP = 0>
 __global__ void __launch_bounds__(NT, 1024 / NT) k_step2p(Dev d, StepArgs a) {
   const int rd = a.rdp1 ? a.rdp1 - 1 : d.ctrl->cur;
   const int end = d.own0 + d.N, stride = gridDim.x * NT;
 #pragma unroll 1
   for (int i = d.own0 + blockIdx.x * NT + threadIdx.x; i < end; i += stride)
-    step2_atom<0, PF, MAGIC, ILP>(d, a, i, i + stride < end ? i + stride : -1, rd, step2_head<HR>(d, d.pos[rd], i));
+    step2_atom<0, PF, MAGIC, ILP>(d, a, i, i + stride < end ? i + stride : -1, rd, step2_head(d, d.pos[rd], i));
 }
 
 // persistent and software-pipelined: the head of a thread's NEXT atom is loaded into registers before the current atom

@@ -11,7 +11,7 @@ from lammps_le_b200 import systems
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [1, 3, 5, 33, 35, 37, 41, 43, 105, 107, 129, 161, 163, 257, 289]   # bit 0 k_step2, 1: 128 threads, 2: L2 prefetch, 5: persistent, 5+3: pipelined, 6: full occupancy, 7: ILP, 8: head record
+VARIANTS = [1, 3, 5, 33, 35, 37, 41, 43, 105, 107, 129, 161, 163]   # bit 0 k_step2, 1: 128 threads, 2: L2 prefetch, 5: persistent, 5+3: pipelined, 6: full occupancy, 7: ILP
 
 
 def trajectory(monkeypatch, variant, system, v0, langevin, steps, dt):
