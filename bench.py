@@ -12,7 +12,7 @@ One bench "step" = `--md-steps` MD timesteps (default 500 = one full USER-LE cyc
 value      whole-job atom-steps/s with all state resident in HBM when the timed region starts
 e2e        same metric through the C ABI with HOST buffers: every step uploads positions+velocities from
            pinned host memory, runs, and downloads positions
-roofline   fused step kernel k_step<0>: algorithmic bytes (72.1 + 4 nbar per atom-step, nbar measured)
+roofline   fused step kernel (k_step2p, le_step2.cuh): algorithmic bytes (72.1 + 4 nbar per atom-step, nbar measured)
            / CUDA-event time of the step loop, against MEASURED_PEAKS.json hbm_gbs
 cpu_baseline  the compiled reference (oracle/_ref/lmp_ref) on a bounded sample of the same workload
 """
@@ -101,7 +101,7 @@ REF_LE_LINES = ["fix loop all extrusion 500 1 2 3 0.5 2 4",
                 "fix unloading all ex_unload 100 2 0.5 prob 0.05 456456"]
 
 
-NCU_TRAFFIC_PER_LAUNCH = 99.3e6   # bytes: 87.8 MB read + 11.5 MB written per k_step<0> launch at 1M beads (ncu capture of round 1)
+NCU_TRAFFIC_PER_LAUNCH = 99.2e6   # bytes: 87.8 MB read + 11.4 MB written per k_step2p launch at 1M beads (ncu --set full, profiles/r01_ncu_full_kstep2p.txt)
 LE_HALO = 6.0   # ghost shell for USER-LE on several GPUs: longest extruder bond (FENE R0 = 4) + one backbone bond (1.5) + skin (4 cell layers here)
 
 
@@ -257,8 +257,8 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_TRAFFIC_PER_LAUNCH if n_beads == 1000000 else None, "peak_source": how,
-                     "kernel": "k_step<0>", "kernel_us": kstep_us, "bytes_per_atom_step": bytes_step,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_step<0> launch, ncu --set full, profiles/r01_ncu_full_kstep_kbuild.txt",
+                     "kernel": Engine.step_kernel_name(e), "kernel_us": kstep_us, "bytes_per_atom_step": bytes_step,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_step2p<0,256,0,0> launch, ncu --set full, profiles/r01_ncu_full_kstep2p.txt",
                      "whole_step": {"achieved": whole_step, "frac": whole_step / peak, "bytes_per_atom_step": bytes_amort,
                                     "note": "72.1 + 4 nbar + (40 + 4 nbar)/K bytes per atom-step over the whole timed loop (rebuilds and USER-LE included)"}},
         "wall_s": t_wall, "user_le_ms_per_md_step": le_ms / steps_timed,

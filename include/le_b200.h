@@ -139,6 +139,8 @@ int le_force_rebuild(le_ctx *c);                            /* Neighbor::build(1
 /* le_run with direct launches and an event before every launch; *kstep_us = average duration of the plain step
  * kernel (launch to next launch on the stream), for live roofline measurements */
 int le_run_timed(le_ctx *c, int64_t nsteps, double *kstep_us);
+/* name of the plain step kernel le_run launches in the current configuration (for reports; e.g. "k_step2p<0,256,0,0>") */
+const char *le_step_kernel_name(le_ctx *c);
 /* run one USER-LE fix's post_integrate on the current state, regardless of the step gate */
 int le_run_le_event(le_ctx *c, int which);
 /* skip n draws of that fix's Marsaglia stream / re-seed it (state replay) */

@@ -1022,26 +1022,27 @@ static bool step2_eligible(const le_ctx *c) {
   return true;
 }
 
-#define STEP2_CASE(dd, nt, pf) { (step_fn_t)k_step2<dd, nt, pf, 0>, nt, "(k_step2<" #dd "," #nt "," #pf ">)", 0 }
-#define STEP2P_CASE(nt, pf) { (step_fn_t)k_step2p<nt, pf, 0>, nt, "(k_step2p<" #nt "," #pf ">)", 1024 / nt }
-#define STEP2Q_CASE(nt, bps) { (step_fn_t)k_step2q<nt, bps, 0>, nt, "(k_step2q<" #nt "," #bps ">)", bps }
+#define STEP2_CASE(dd, nt, pf, ilp) { (step_fn_t)k_step2<dd, nt, pf, ilp>, nt, "(k_step2<" #dd "," #nt "," #pf "," #ilp ">)", 0 }
+#define STEP2P_CASE(dd, nt, pf, ilp) { (step_fn_t)k_step2p<dd, nt, pf, ilp>, nt, "(k_step2p<" #dd "," #nt "," #pf "," #ilp ">)", 1024 / nt }
+#define STEP2Q_CASE(nt, bps) { (step_fn_t)k_step2q<nt, bps>, nt, "(k_step2q<" #nt "," #bps ">)", bps }
 static StepKernel plain_step_kernel(const le_ctx *c, int variant) {
   const bool dd = c->nranks > 1;
   if ((variant & 1) && step2_eligible(c) && (!dd || (variant & 16))) {
-    const bool small = variant & 2, pf = variant & 4, pipe = variant & 8, pers = variant & 32, full = variant & 64;
-    if (dd) return small ? StepKernel STEP2_CASE(1, 128, 0) : StepKernel STEP2_CASE(1, 256, 0);
+    const bool small = variant & 2, pf = variant & 4, pipe = variant & 8, pers = variant & 32, full = variant & 64, ilp = variant & 128;
+    if (dd) {
+      if (pers) return small ? StepKernel STEP2P_CASE(1, 128, 0, 0) : StepKernel STEP2P_CASE(1, 256, 0, 0);
+      return small ? StepKernel STEP2_CASE(1, 128, 0, 0) : StepKernel STEP2_CASE(1, 256, 0, 0);
+    }
     if (pers && pipe) {
       if (small) return full ? StepKernel STEP2Q_CASE(128, 8) : StepKernel STEP2Q_CASE(128, 6);
       return full ? StepKernel STEP2Q_CASE(256, 4) : StepKernel STEP2Q_CASE(256, 3);
     }
-    if (variant & 128) {
-      if (pers) return small ? StepKernel{(step_fn_t)k_step2p<128, 0, 0, 1>, 128, "(k_step2p<128,0,ilp>)", 8}
-                             : StepKernel{(step_fn_t)k_step2p<256, 0, 0, 1>, 256, "(k_step2p<256,0,ilp>)", 4};
-      return small ? StepKernel{(step_fn_t)k_step2<0, 128, 0, 0, 1>, 128, "(k_step2<0,128,0,ilp>)", 0}
-                   : StepKernel{(step_fn_t)k_step2<0, 256, 0, 0, 1>, 256, "(k_step2<0,256,0,ilp>)", 0};
+    if (ilp) {
+      if (pers) return small ? StepKernel STEP2P_CASE(0, 128, 0, 1) : StepKernel STEP2P_CASE(0, 256, 0, 1);
+      return small ? StepKernel STEP2_CASE(0, 128, 0, 1) : StepKernel STEP2_CASE(0, 256, 0, 1);
     }
-    static const StepKernel tab[8] = {STEP2_CASE(0, 256, 0), STEP2_CASE(0, 128, 0), STEP2_CASE(0, 256, 1), STEP2_CASE(0, 128, 1),
-                                      STEP2P_CASE(256, 0), STEP2P_CASE(128, 0), STEP2P_CASE(256, 1), STEP2P_CASE(128, 1)};
+    static const StepKernel tab[8] = {STEP2_CASE(0, 256, 0, 0), STEP2_CASE(0, 128, 0, 0), STEP2_CASE(0, 256, 1, 0), STEP2_CASE(0, 128, 1, 0),
+                                      STEP2P_CASE(0, 256, 0, 0), STEP2P_CASE(0, 128, 0, 0), STEP2P_CASE(0, 256, 1, 0), STEP2P_CASE(0, 128, 1, 0)};
     return tab[(small ? 1 : 0) | (pf ? 2 : 0) | (pers ? 4 : 0)];
   }
   const bool uni = c->P.pair_uniform != 0;
@@ -1664,6 +1665,14 @@ extern "C" int le_run_timed(le_ctx *c, int64_t nsteps, double *kstep_us) {
   c->timing = t0; c->timing_quiet = q0; c->force_direct = false;
   *kstep_us = 1e3 * c->kstep_avg_ms;
   return r;
+}
+
+extern "C" const char *le_step_kernel_name(le_ctx *c) {
+  if (!c) return "";
+  static thread_local std::string name;
+  name = plain_step_kernel(c, step_variant()).name;           // "(kernel<...>)" as the timing marks spell it
+  if (name.size() >= 2 && name.front() == '(' && name.back() == ')') name = name.substr(1, name.size() - 2);
+  return name.c_str();
 }
 
 extern "C" int le_get_force_sums(const le_ctx *c, double *out16) {

@@ -22,14 +22,6 @@
 #pragma once
 #include "le_md.cuh"
 
-// exact int32 -> double.  MAGIC: on the fp64 pipe (2^52 + 2^31 + v assembled from its bit pattern, minus the
-// constant) instead of the conversion unit (I2F.F64), which is the busiest pipe of k_step; the value is the same.
-template <int MAGIC>
-__device__ __forceinline__ double le_i2d(int v) {
-  if (MAGIC) return __dadd_rn(__hiloint2double(0x43300000, v ^ (int)0x80000000), -4503601774854144.0);
-  return (double)v;
-}
-
 __device__ __forceinline__ double le_rcp2(double x) {   // == le_rcp, with the contractions written out
   double t;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(t) : "d"(x));
@@ -47,11 +39,10 @@ __device__ __forceinline__ bool screen2(const int4 pi, const int4 pj, float sx, 
 }
 
 // WCA term of one listed pair in fp64 (pair_term<0,1> with factor_lj == 1)
-template <int MAGIC>
 __device__ __forceinline__ void pair_eval2(double &fx, double &fy, double &fz, const int4 pi, const int4 pj) {
-  const double dy = __dmul_rn(le_i2d<MAGIC>((int)((unsigned)pi.y - (unsigned)pj.y)), c_P.scale[1]);
-  const double dx = __dmul_rn(le_i2d<MAGIC>((int)((unsigned)pi.x - (unsigned)pj.x)), c_P.scale[0]);
-  const double dz = __dmul_rn(le_i2d<MAGIC>((int)((unsigned)pi.z - (unsigned)pj.z)), c_P.scale[2]);
+  const double dy = __dmul_rn((double)((int)((unsigned)pi.y - (unsigned)pj.y)), c_P.scale[1]);
+  const double dx = __dmul_rn((double)((int)((unsigned)pi.x - (unsigned)pj.x)), c_P.scale[0]);
+  const double dz = __dmul_rn((double)((int)((unsigned)pi.z - (unsigned)pj.z)), c_P.scale[2]);
   const double rsq = __fma_rn(dz, dz, __fma_rn(dx, dx, __dmul_rn(dy, dy)));
   if (rsq < c_P.cutsq_d[0]) {
     const double r2inv = le_rcp2(rsq);
@@ -62,13 +53,12 @@ __device__ __forceinline__ void pair_eval2(double &fx, double &fy, double &fz, c
 }
 
 // FENE / harmonic term of one bond partner (bond_term<0>)
-template <int MAGIC>
 __device__ __forceinline__ void bond_eval2(double &fx, double &fy, double &fz, Ctrl *ctrl, const int4 pi, const int4 pj,
                                            unsigned e, int tagi) {
   const int bt = e >> 28;
-  const double dy = __dmul_rn(le_i2d<MAGIC>((int)((unsigned)pi.y - (unsigned)pj.y)), c_P.scale[1]);
-  const double dx = __dmul_rn(le_i2d<MAGIC>((int)((unsigned)pi.x - (unsigned)pj.x)), c_P.scale[0]);
-  const double dz = __dmul_rn(le_i2d<MAGIC>((int)((unsigned)pi.z - (unsigned)pj.z)), c_P.scale[2]);
+  const double dy = __dmul_rn((double)((int)((unsigned)pi.y - (unsigned)pj.y)), c_P.scale[1]);
+  const double dx = __dmul_rn((double)((int)((unsigned)pi.x - (unsigned)pj.x)), c_P.scale[0]);
+  const double dz = __dmul_rn((double)((int)((unsigned)pi.z - (unsigned)pj.z)), c_P.scale[2]);
   const double rsq = __fma_rn(dz, dz, __fma_rn(dx, dx, __dmul_rn(dy, dy)));
   const int style = c_P.bstyle[bt];
   double fbond;
@@ -98,16 +88,15 @@ __device__ __forceinline__ void bond_eval2(double &fx, double &fy, double &fz, C
 // two FENE bonds side by side in one straight line of code (independent fp64 chains interleave; k_step's per-instruction
 // profile shows a dependent instruction every ~8 cycles, the bonds being the longest chains).  The WCA core term is
 // computed whether it applies or not and selected; values and order of the sums are those of two bond_eval2 calls.
-template <int MAGIC>
 __device__ __forceinline__ void fene_eval2x(double &fx, double &fy, double &fz, Ctrl *ctrl, const int4 pi, const int4 pa, const int4 pb,
                                             unsigned ea, unsigned eb, int tagi) {
   const int bta = ea >> 28, btb = eb >> 28;
-  const double dya = __dmul_rn(le_i2d<MAGIC>((int)((unsigned)pi.y - (unsigned)pa.y)), c_P.scale[1]);
-  const double dyb = __dmul_rn(le_i2d<MAGIC>((int)((unsigned)pi.y - (unsigned)pb.y)), c_P.scale[1]);
-  const double dxa = __dmul_rn(le_i2d<MAGIC>((int)((unsigned)pi.x - (unsigned)pa.x)), c_P.scale[0]);
-  const double dxb = __dmul_rn(le_i2d<MAGIC>((int)((unsigned)pi.x - (unsigned)pb.x)), c_P.scale[0]);
-  const double dza = __dmul_rn(le_i2d<MAGIC>((int)((unsigned)pi.z - (unsigned)pa.z)), c_P.scale[2]);
-  const double dzb = __dmul_rn(le_i2d<MAGIC>((int)((unsigned)pi.z - (unsigned)pb.z)), c_P.scale[2]);
+  const double dya = __dmul_rn((double)((int)((unsigned)pi.y - (unsigned)pa.y)), c_P.scale[1]);
+  const double dyb = __dmul_rn((double)((int)((unsigned)pi.y - (unsigned)pb.y)), c_P.scale[1]);
+  const double dxa = __dmul_rn((double)((int)((unsigned)pi.x - (unsigned)pa.x)), c_P.scale[0]);
+  const double dxb = __dmul_rn((double)((int)((unsigned)pi.x - (unsigned)pb.x)), c_P.scale[0]);
+  const double dza = __dmul_rn((double)((int)((unsigned)pi.z - (unsigned)pa.z)), c_P.scale[2]);
+  const double dzb = __dmul_rn((double)((int)((unsigned)pi.z - (unsigned)pb.z)), c_P.scale[2]);
   const double rsqa = __fma_rn(dza, dza, __fma_rn(dxa, dxa, __dmul_rn(dya, dya)));
   const double rsqb = __fma_rn(dzb, dzb, __fma_rn(dxb, dxb, __dmul_rn(dyb, dyb)));
   double rla = __fma_rn(-rsqa, c_P.binvr0sq_d[bta], 1.0), rlb = __fma_rn(-rsqb, c_P.binvr0sq_d[btb], 1.0);
@@ -132,7 +121,6 @@ __device__ __forceinline__ void fene_eval2x(double &fx, double &fy, double &fz, 
 }
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // same generator as philox4x32_7 (le_common.cuh) with each 32x32 -> 64-bit product taken as one wide multiply
 __device__ __forceinline__ void philox4x32_7w(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned out[4]) {
@@ -186,9 +174,9 @@ __device__ __forceinline__ Step2Head step2_head(const Dev &d, const int4 *__rest
 }
 
 // one atom (slot i) of one timestep, its head already requested.  inext: the slot this thread's successor works on
-// (the same thread in a persistent grid, another block's thread otherwise), or -1; PF asks for its lines ahead of time
-// (PF = 1: into the L2, 2: into the L1)
-template <int DD, int PF, int MAGIC, int ILP = 0>
+// (the same thread in a persistent grid, another block's thread otherwise), or -1; PF asks the L2 for its lines ahead
+// of time
+template <int DD, int PF, int ILP = 0>
 __device__ __forceinline__ void step2_atom(const Dev &d, const StepArgs &a, const int i, const int inext, const int rd, const Step2Head &h) {
   const int cap = d.cap;
   Ctrl *__restrict__ ctrl = d.ctrl;
@@ -205,17 +193,10 @@ __device__ __forceinline__ void step2_atom(const Dev &d, const StepArgs &a, cons
   const long long step = ctrl->step;
   if (PF && inext >= 0) {
     const int ip = inext;
-    if (PF == 1) {
-      prefetch_l2(&posr[ip]); prefetch_l2(&d.vel[ip]); prefetch_l2(&d.pos_hold[ip]); prefetch_l2(&d.counts[ip]);
-      prefetch_l2(&neigh[ip]); prefetch_l2(&neigh[(size_t)cap + ip]); prefetch_l2(&neigh[(size_t)2 * cap + ip]);
-      prefetch_l2(&neigh[(size_t)3 * cap + ip]);
-      prefetch_l2(&bondrow[ip]); prefetch_l2(&bondrow[(size_t)(d.bpa > 1) * cap + ip]); prefetch_l2(&bondrow[(size_t)(d.bpa > 2 ? 2 : 0) * cap + ip]);
-    } else {
-      prefetch_l1(&posr[ip]); prefetch_l1(&d.vel[ip]); prefetch_l1(&d.pos_hold[ip]); prefetch_l1(&d.counts[ip]);
-      prefetch_l1(&neigh[ip]); prefetch_l1(&neigh[(size_t)cap + ip]); prefetch_l1(&neigh[(size_t)2 * cap + ip]);
-      prefetch_l1(&neigh[(size_t)3 * cap + ip]);
-      prefetch_l1(&bondrow[ip]); prefetch_l1(&bondrow[(size_t)(d.bpa > 1) * cap + ip]); prefetch_l1(&bondrow[(size_t)(d.bpa > 2 ? 2 : 0) * cap + ip]);
-    }
+    prefetch_l2(&posr[ip]); prefetch_l2(&d.vel[ip]); prefetch_l2(&d.pos_hold[ip]); prefetch_l2(&d.counts[ip]);
+    prefetch_l2(&neigh[ip]); prefetch_l2(&neigh[(size_t)cap + ip]); prefetch_l2(&neigh[(size_t)2 * cap + ip]);
+    prefetch_l2(&neigh[(size_t)3 * cap + ip]);
+    prefetch_l2(&bondrow[ip]); prefetch_l2(&bondrow[(size_t)(d.bpa > 1) * cap + ip]); prefetch_l2(&bondrow[(size_t)(d.bpa > 2 ? 2 : 0) * cap + ip]);
   }
 
   const int nn = cnt & 0xff, nb = (cnt >> 16) & 0xff;
@@ -277,34 +258,34 @@ __device__ __forceinline__ void step2_atom(const Dev &d, const StepArgs &a, cons
 #pragma unroll 1
   for (int k = 32; k < nn; k++) {
     const unsigned e = __ldg(&neigh[(size_t)k * cap + i]);
-    pair_eval2<MAGIC>(fx, fy, fz, pi, __ldg(&posr[e & NEIGH_IDX_MASK]));
+    pair_eval2(fx, fy, fz, pi, __ldg(&posr[e & NEIGH_IDX_MASK]));
   }
   // the survivors, evaluated in fp64 in the order k_step adds them: rows 4, 5, ... first, then 0..3; a warp runs each
   // loop max-over-lanes(#survivors) times.  Rows 4.. are rare (their row entry is fetched again: an L1 hit)
 #pragma unroll 1
   for (unsigned m = hit >> 4; m; m &= m - 1) {
     const unsigned e = __ldg(&neigh[(size_t)(__ffs(m) + 3) * cap + i]);
-    pair_eval2<MAGIC>(fx, fy, fz, pi, __ldg(&posr[e & NEIGH_IDX_MASK]));
+    pair_eval2(fx, fy, fz, pi, __ldg(&posr[e & NEIGH_IDX_MASK]));
   }
 #pragma unroll 1
   for (unsigned m = hit & 15u; m; m &= m - 1) {
     const unsigned b = m & (0u - m);                         // lowest survivor: 1, 2, 4 or 8
     const unsigned e = (b & 3u) ? ((b & 1u) ? en0 : en1) : ((b & 4u) ? en2 : en3);
-    pair_eval2<MAGIC>(fx, fy, fz, pi, __ldg(&posr[e & NEIGH_IDX_MASK]));   // second touch of the position: an L1 hit
+    pair_eval2(fx, fy, fz, pi, __ldg(&posr[e & NEIGH_IDX_MASK]));   // second touch of the position: an L1 hit
   }
   if (ILP && c_P.bond_all_fene) {
-    if (1 < nb) fene_eval2x<MAGIC>(fx, fy, fz, ctrl, pi, pb0, pb1, eb0, eb1, tag);
-    else if (0 < nb) bond_eval2<MAGIC>(fx, fy, fz, ctrl, pi, pb0, eb0, tag);
-    if (2 < nb) bond_eval2<MAGIC>(fx, fy, fz, ctrl, pi, pb2, eb2, tag);
+    if (1 < nb) fene_eval2x(fx, fy, fz, ctrl, pi, pb0, pb1, eb0, eb1, tag);
+    else if (0 < nb) bond_eval2(fx, fy, fz, ctrl, pi, pb0, eb0, tag);
+    if (2 < nb) bond_eval2(fx, fy, fz, ctrl, pi, pb2, eb2, tag);
   } else {
-    if (0 < nb) bond_eval2<MAGIC>(fx, fy, fz, ctrl, pi, pb0, eb0, tag);
-    if (1 < nb) bond_eval2<MAGIC>(fx, fy, fz, ctrl, pi, pb1, eb1, tag);
-    if (2 < nb) bond_eval2<MAGIC>(fx, fy, fz, ctrl, pi, pb2, eb2, tag);
+    if (0 < nb) bond_eval2(fx, fy, fz, ctrl, pi, pb0, eb0, tag);
+    if (1 < nb) bond_eval2(fx, fy, fz, ctrl, pi, pb1, eb1, tag);
+    if (2 < nb) bond_eval2(fx, fy, fz, ctrl, pi, pb2, eb2, tag);
   }
 #pragma unroll 1
   for (int mth = 3; mth < nb; mth++) {
     const unsigned e = __ldg(&bondrow[(size_t)mth * cap + i]);
-    bond_eval2<MAGIC>(fx, fy, fz, ctrl, pi, __ldg(&posr[e & BOND_IDX_MASK]), e, tag);
+    bond_eval2(fx, fy, fz, ctrl, pi, __ldg(&posr[e & BOND_IDX_MASK]), e, tag);
   }
 
   // ---- Langevin drag + uniform noise (post_force); fp32, added to the rounded conservative force ----
@@ -361,47 +342,72 @@ __device__ __forceinline__ void step2_atom(const Dev &d, const StepArgs &a, cons
 
 #define STEP2_WAVE (148 * 1024)   // atoms one wave of resident threads works on
 
-// DD: multi-GPU slab (halo stores fused in, boundary blocks first); NT: threads per block (1024 / NT blocks per SM);
-// PF: ask the L2 for the lines of the atom one wave ahead; MAGIC: see le_i2d; ILP: thermostat force computed while the
-// gathers are in flight, two FENE bonds evaluated side by side
-template <int DD, int NT, int PF, int MAGIC, int ILP = 0>
+// Work order on a slab of a multi-GPU run: the two boundary slices first, the interior last, so that the halo stores
+// are in flight while the interior computes (see k_step).  Segment starts are multiples of 64 slots.  Maps position g
+// of that order to a slot; returns own_end for a padding position.
+struct Step2Order { int own0, own_end, a_end, b_beg, nl, nr, nrp; };
+__device__ __forceinline__ Step2Order step2_order(const Dev &d) {
+  const Ctrl *__restrict__ ctrl = d.ctrl;
+  Step2Order o;
+  o.own0 = d.own0;
+  o.own_end = d.own0 + ctrl->nown;
+  o.a_end = min(o.own_end, d.own0 + ((ctrl->send_l_end - d.own0 + 63) & ~63));
+  o.b_beg = max(o.a_end, d.own0 + ((ctrl->send_r_beg - d.own0) & ~63));
+  o.nl = o.a_end - d.own0; o.nr = o.own_end - o.b_beg; o.nrp = (o.nr + 63) & ~63;
+  return o;
+}
+__device__ __forceinline__ int step2_slot(const Step2Order &o, int g) {
+  if (g < o.nl) return o.own0 + g;
+  if (g < o.nl + o.nrp) return (g - o.nl < o.nr) ? o.b_beg + (g - o.nl) : o.own_end;
+  const int i = o.a_end + (g - o.nl - o.nrp);
+  return i >= o.b_beg ? o.own_end : i;
+}
+
+// DD: multi-GPU slab (halo stores fused in, boundary slices first); NT: threads per block (1024 / NT blocks per SM);
+// PF: ask the L2 for the lines of the atom one wave ahead; ILP: thermostat force computed while the gathers are in
+// flight, two FENE bonds evaluated side by side
+template <int DD, int NT, int PF, int ILP = 0>
 __global__ void __launch_bounds__(NT, 1024 / NT) k_step2(Dev d, StepArgs a) {
   int i = d.own0 + blockIdx.x * NT + threadIdx.x;
   if (DD) {
-    // the two boundary slices first, the interior last (see k_step)
-    Ctrl *__restrict__ ctrl = d.ctrl;
-    const int own_end = d.own0 + ctrl->nown;
-    const int g = blockIdx.x * NT + threadIdx.x;
-    const int a_end = min(own_end, d.own0 + ((ctrl->send_l_end - d.own0 + 63) & ~63));
-    const int b_beg = max(a_end, d.own0 + ((ctrl->send_r_beg - d.own0) & ~63));
-    const int nl = a_end - d.own0, nr = own_end - b_beg, nrp = (nr + 63) & ~63;
-    if (g < nl) i = d.own0 + g;
-    else if (g < nl + nrp) i = (g - nl < nr) ? b_beg + (g - nl) : own_end;
-    else { i = a_end + (g - nl - nrp); if (i >= b_beg) i = own_end; }
-    if (i >= own_end) return;
+    const Step2Order o = step2_order(d);
+    i = step2_slot(o, blockIdx.x * NT + threadIdx.x);
+    if (i >= o.own_end) return;
   } else {
     if (i >= d.own0 + d.N) return;   // one GPU owns every atom: no look at the control block before the loads
   }
   const int rd = a.rdp1 ? a.rdp1 - 1 : d.ctrl->cur;
   const int inext = (!DD && i + STEP2_WAVE < d.own0 + d.N) ? i + STEP2_WAVE : -1;
-  step2_atom<DD, PF, MAGIC, ILP>(d, a, i, inext, rd, step2_head(d, d.pos[rd], i));
+  step2_atom<DD, PF, ILP>(d, a, i, inext, rd, step2_head(d, d.pos[rd], i));
 }
 
-// persistent form (one GPU): one wave of blocks walks the atoms with a grid stride (no block launches inside the
-// step, no partial last wave).  PF = 1 / 2: the lines of a thread's next atom are requested into the L2 / L1 ahead of time
-template <int NT, int PF, int MAGIC, int ILP = 0>
+// persistent form: one wave of blocks walks the atoms with a grid stride (no block launches inside the step, no
+// partial last wave); on a slab the stride runs over the boundary-first order.  PF: the lines of a thread's next
+// atom are requested into the L2 ahead of time
+template <int DD, int NT, int PF, int ILP = 0>
 __global__ void __launch_bounds__(NT, 1024 / NT) k_step2p(Dev d, StepArgs a) {
   const int rd = a.rdp1 ? a.rdp1 - 1 : d.ctrl->cur;
-  const int end = d.own0 + d.N, stride = gridDim.x * NT;
+  const int stride = gridDim.x * NT;
+  if (DD) {
+    const Step2Order o = step2_order(d);
+    const int gend = o.nl + o.nrp + (o.b_beg - o.a_end);      // positions of the order: left slice, padded right slice, interior
 #pragma unroll 1
-  for (int i = d.own0 + blockIdx.x * NT + threadIdx.x; i < end; i += stride)
-    step2_atom<0, PF, MAGIC, ILP>(d, a, i, i + stride < end ? i + stride : -1, rd, step2_head(d, d.pos[rd], i));
+    for (int g = blockIdx.x * NT + threadIdx.x; g < gend; g += stride) {
+      const int i = step2_slot(o, g);
+      if (i < o.own_end) step2_atom<DD, 0, ILP>(d, a, i, -1, rd, step2_head(d, d.pos[rd], i));
+    }
+  } else {
+    const int end = d.own0 + d.N;
+#pragma unroll 1
+    for (int i = d.own0 + blockIdx.x * NT + threadIdx.x; i < end; i += stride)
+      step2_atom<DD, PF, ILP>(d, a, i, i + stride < end ? i + stride : -1, rd, step2_head(d, d.pos[rd], i));
+  }
 }
 
 // persistent and software-pipelined: the head of a thread's NEXT atom is loaded into registers before the current atom
 // is worked on, so the gathers of every atom but the first start without waiting for memory.  Twelve more live
 // registers: NT x BPS threads per SM with BPS chosen so that nothing spills.
-template <int NT, int BPS, int MAGIC>
+template <int NT, int BPS>
 __global__ void __launch_bounds__(NT, BPS) k_step2q(Dev d, StepArgs a) {
   const int rd = a.rdp1 ? a.rdp1 - 1 : d.ctrl->cur;
   const int4 *__restrict__ posr = d.pos[rd];
@@ -414,7 +420,7 @@ __global__ void __launch_bounds__(NT, BPS) k_step2q(Dev d, StepArgs a) {
     const int in = i + stride;
     const bool more = in < end;
     const Step2Head nxt = step2_head(d, posr, more ? in : i);     // the last trip re-reads its own head (cache hits)
-    step2_atom<0, 0, MAGIC>(d, a, i, -1, rd, cur);
+    step2_atom<0, 0>(d, a, i, -1, rd, cur);
     if (!more) break;
     cur = nxt;
     i = in;

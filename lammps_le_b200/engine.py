@@ -92,6 +92,8 @@ def load_library():
     lib.le_last_error.argtypes = [P]
     lib.le_last_error.restype = C.c_char_p
     lib.le_version.restype = C.c_char_p
+    lib.le_step_kernel_name.argtypes = [P]
+    lib.le_step_kernel_name.restype = C.c_char_p
     lib.le_timestep.argtypes = [P]
     lib.le_timestep.restype = I64
     _lib = lib
@@ -244,6 +246,10 @@ class Engine:
         us = C.c_double()
         self._ck(self.lib.le_run_timed(self._h, nsteps, C.byref(us)))
         return us.value
+
+    def step_kernel_name(self):
+        """the plain step kernel le_run launches in this configuration"""
+        return self.lib.le_step_kernel_name(self._h).decode()
 
     def force_rebuild(self):
         self._ck(self.lib.le_force_rebuild(self._h))
