@@ -81,7 +81,7 @@ struct le_ctx {
   double *h_thermo;     // pinned
   Ctrl *h_ctrl;         // pinned
   // captured step graphs (built lazily, rebuilt when anything baked into them changes)
-  GraphKey gkey; int gkey_variant;
+  GraphKey gkey; int gkey_variant, plain_graph_kernels;
   bool graphs_ok;
   cudaGraph_t g_plain[2], g_tail[2];          // g_plain[p]: steady-state graph launched when pos[p] holds the coordinates
   cudaGraphExec_t x_plain[2], x_tail[2];
@@ -1005,7 +1005,8 @@ extern "C" int le_set_velocities(le_ctx *c, const double *v) {
 // LE_STEP_VARIANT (read at every le_run, so one process can compare variants): 0 = k_step; bit 0 = k_step2 (le_step2.cuh),
 // bit 1 = 128 threads per block instead of 256, bit 2 = L2 prefetch one wave ahead, bit 5 = persistent grid (k_step2p),
 // bits 5 + 3 = persistent and software-pipelined (k_step2q; bit 6: at full occupancy, with spills), bit 7 = thermostat
-// force computed under the gathers + two FENE bonds side by side (with or without bit 5), bit 4 = k_step2 also
+// force computed under the gathers + two FENE bonds side by side (with or without bit 5), bit 9 (with bits 0 and 5) = the
+// step kernel's last block takes the reneighbor decision of the next timestep inside the steady-state graph, bit 4 = k_step2 also
 // on several GPUs.  k_step2 needs the uniform lj/cut case and special weights in {0, 1}; otherwise k_step runs whatever
 // the switch says.
 #ifndef LE_STEP_VARIANT_DEFAULT
@@ -1116,24 +1117,29 @@ static int rebuild_kernel_count(const le_ctx *c) { return c->nranks > 1 ? 12 : 7
     }                                                                                         \
   } while (0)
 
-// append [k_decide(advance) -> IF(rebuild)] (and optionally a plain k_step after it) to graph g after node *tail
-static int graph_add_unit(le_ctx *c, cudaGraph_t g, cudaGraphNode_t *tail, int advance, bool with_step, int step_rd = 0) {
-  cudaGraphConditionalHandle handle;
-  CKG(cudaGraphConditionalHandleCreate(&handle, g, 0, cudaGraphCondAssignDefault));
+// append [k_decide(advance) -> IF(rebuild)] (and optionally a plain k_step after it) to graph g after node *tail.
+// `handle` switches this unit's conditional node; with_decide = false: the step kernel of the previous unit has taken
+// the decision (StepArgs::fuse) and set the handle.  next_handle != 0: this unit's step kernel does the same for the
+// unit that follows.
+static int graph_add_unit(le_ctx *c, cudaGraph_t g, cudaGraphNode_t *tail, int advance, bool with_step, int step_rd,
+                          cudaGraphConditionalHandle handle, bool with_decide, cudaGraphConditionalHandle next_handle) {
   Dev d = c->d;
-  int adv = advance, use = 1;
-  void *dargs[] = {&d, &handle, &adv, &use};
   cudaKernelNodeParams kp;
-  memset(&kp, 0, sizeof kp);
-  kp.func = (void *)k_decide; kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.kernelParams = dargs;
-  cudaGraphNode_t nd;
-  CKG(cudaGraphAddKernelNode(&nd, g, *tail ? tail : nullptr, *tail ? 1 : 0, &kp));
+  if (with_decide) {
+    int adv = advance, use = 1;
+    void *dargs[] = {&d, &handle, &adv, &use};
+    memset(&kp, 0, sizeof kp);
+    kp.func = (void *)k_decide; kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.kernelParams = dargs;
+    cudaGraphNode_t nd;
+    CKG(cudaGraphAddKernelNode(&nd, g, *tail ? tail : nullptr, *tail ? 1 : 0, &kp));
+    *tail = nd;
+  }
   cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
   cp.conditional.handle = handle;
   cp.conditional.type = cudaGraphCondTypeIf;
   cp.conditional.size = 1;
   cudaGraphNode_t nc;
-  CKG(cudaGraphAddNode(&nc, g, &nd, 1, &cp));
+  CKG(cudaGraphAddNode(&nc, g, *tail ? tail : nullptr, *tail ? 1 : 0, &cp));
   cudaGraph_t body = cp.conditional.phGraph_out[0];
   c->capturing = true;
   CKG(cudaStreamBeginCaptureToGraph(c->stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
@@ -1147,6 +1153,7 @@ static int graph_add_unit(le_ctx *c, cudaGraph_t g, cudaGraphNode_t *tail, int a
     a.do_final = 1; a.do_initial = 1; a.langevin = c->langevin_on;
     { static const int skip = getenv("LE_STEP_SKIP") ? atoi(getenv("LE_STEP_SKIP")) : 0; a.skip = skip & (15 | 32); if (skip & 16) a.langevin = 0; }
     a.rdp1 = step_rd + 1;
+    if (next_handle) { a.fuse = 1; a.handle = next_handle; }
     void *sargs[] = {&d, &a};
     memset(&kp, 0, sizeof kp);
     const StepKernel sk = plain_step_kernel(c, c->gkey_variant);
@@ -1159,6 +1166,13 @@ static int graph_add_unit(le_ctx *c, cudaGraph_t g, cudaGraphNode_t *tail, int a
   return LE_OK;
 }
 
+// the reneighbor decision fused into the step kernel (LE_STEP_VARIANT bit 9): only the persistent single-GPU kernel has
+// the last-block epilogue
+static bool fused_decide(const le_ctx *c, int variant) {
+  return (variant & 512) && c->nranks == 1 && plain_step_kernel(c, variant).fn != nullptr && (variant & 1) && (variant & 32) && !(variant & 8) &&
+         step2_eligible(c);
+}
+
 static int ensure_graphs(le_ctx *c) {
   GraphKey key; memset(&key, 0, sizeof key);
   key.d = c->d; key.langevin = c->langevin_on; key.variant = step_variant(); key.rb_variant = rebuild_variant();
@@ -1169,16 +1183,25 @@ static int ensure_graphs(le_ctx *c) {
   for (int adv = 0; adv < 2; adv++) {
     CKG(cudaGraphCreate(&c->g_tail[adv], 0));
     cudaGraphNode_t tail = nullptr;
-    if ((r = graph_add_unit(c, c->g_tail[adv], &tail, adv, false))) return r;
+    cudaGraphConditionalHandle h;
+    CKG(cudaGraphConditionalHandleCreate(&h, c->g_tail[adv], 0, cudaGraphCondAssignDefault));
+    if ((r = graph_add_unit(c, c->g_tail[adv], &tail, adv, false, 0, h, true, 0))) return r;
     CKG(cudaGraphInstantiate(&c->x_tail[adv], c->g_tail[adv], 0));
   }
   // the steady-state graph, once per buffer parity at its launch: every k_decide flips the buffers, so the step kernel
-  // of unit u reads pos[p ^ ((u + 1) & 1)] -- known here, passed as a kernel argument (StepArgs::rdp1)
+  // of unit u reads pos[p ^ ((u + 1) & 1)] -- known here, passed as a kernel argument (StepArgs::rdp1).  With the
+  // fused decision only the first unit keeps its k_decide: the step kernel of unit u decides for unit u + 1.
+  const bool fused = fused_decide(c, key.variant);
+  c->plain_graph_kernels = fused ? PLAIN_UNROLL + 1 : 2 * PLAIN_UNROLL;
   for (int p = 0; p < 2; p++) {
     CKG(cudaGraphCreate(&c->g_plain[p], 0));
+    cudaGraphConditionalHandle h[PLAIN_UNROLL];
+    for (int u = 0; u < PLAIN_UNROLL; u++) CKG(cudaGraphConditionalHandleCreate(&h[u], c->g_plain[p], 0, cudaGraphCondAssignDefault));
     cudaGraphNode_t tail = nullptr;
     for (int u = 0; u < PLAIN_UNROLL; u++)
-      if ((r = graph_add_unit(c, c->g_plain[p], &tail, 1, true, p ^ ((u + 1) & 1)))) return r;
+      if ((r = graph_add_unit(c, c->g_plain[p], &tail, 1, true, p ^ ((u + 1) & 1), h[u], u == 0 || !fused,
+                              fused && u + 1 < PLAIN_UNROLL ? h[u + 1] : 0)))
+        return r;
     CKG(cudaGraphInstantiate(&c->x_plain[p], c->g_plain[p], 0));
   }
   c->gkey = key;
@@ -1395,7 +1418,7 @@ extern "C" int le_run(le_ctx *c, int64_t nsteps) {
       if (le_event_at(c, n) || want_thermo(n)) plain = false;
     if (plain) {
       CK(cudaGraphLaunch(c->x_plain[c->cur], c->stream));
-      c->graph_node_launches += 2 * PLAIN_UNROLL;
+      c->graph_node_launches += c->plain_graph_kernels;
       if (PLAIN_UNROLL & 1) c->cur ^= 1;
       s += PLAIN_UNROLL;
       continue;

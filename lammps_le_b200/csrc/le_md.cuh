@@ -14,6 +14,9 @@ struct StepArgs {
   int write_force;    // store the conservative force of every atom in fout (tag order)
   int langevin;       // add drag + noise
   int rdp1;           // 1 + position buffer holding the current coordinates when the host knows it, 0 = read Ctrl::cur (k_step2)
+  int fuse;           // k_step2p inside the steady-state graph: the last block to finish also closes the timestep and takes the
+                      // reneighbor decision of the next one (k_decide's work), switching the conditional node `handle`
+  unsigned long long handle;
   int skip;           // development only (LE_STEP_SKIP): 1 no gathers, 2 no pair evaluation, 4 no bonds, 8 no neighbor rows, 32 no boundary-first block order
 };
 
@@ -410,7 +413,7 @@ __device__ __forceinline__ void close_epoch(const Dev &d) {
 // rebuild it also does the bookkeeping of Neighbor::build (ago = 0, ncalls++) because the rebuild
 // kernels that follow are a conditional graph node switched by cudaGraphSetConditional.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_decide(Dev d, cudaGraphConditionalHandle handle, int advance, int use_handle) {
+__device__ __forceinline__ void decide_body(const Dev &d, cudaGraphConditionalHandle handle, int advance, int use_handle) {
   Ctrl *c = d.ctrl;
   if (advance) { c->step++; c->cur ^= 1; close_epoch(d); }
   // moved / forced / rebuild_now / ago are the first 16 bytes of the control block: one load, one store
@@ -434,6 +437,8 @@ __global__ void k_decide(Dev d, cudaGraphConditionalHandle handle, int advance, 
   *reinterpret_cast<int4 *>(c) = make_int4(moved, 0, r, ago);
   if (use_handle) cudaGraphSetConditional(handle, r ? 1u : 0u);
 }
+
+__global__ void k_decide(Dev d, cudaGraphConditionalHandle handle, int advance, int use_handle) { decide_body(d, handle, advance, use_handle); }
 
 // close a timestep without deciding (the USER-LE fixes of the new step run before Neighbor::decide)
 __global__ void k_advance(Dev d) { d.ctrl->step++; d.ctrl->cur ^= 1; close_epoch(d); }

@@ -401,6 +401,19 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_step2p(Dev d, StepArgs a) {
 #pragma unroll 1
     for (int i = d.own0 + blockIdx.x * NT + threadIdx.x; i < end; i += stride)
       step2_atom<DD, PF, ILP>(d, a, i, i + stride < end ? i + stride : -1, rd, step2_head(d, d.pos[rd], i));
+    if (a.fuse) {
+      // the block that finishes last has seen the `moved` stores of all the others (fence + counter): it does k_decide's
+      // work for the next timestep -- one kernel and one dependency bubble less per step inside the steady-state graph
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&d.ctrl->blocks_done, 1u) == gridDim.x - 1) {
+          d.ctrl->blocks_done = 0;
+          __threadfence();
+          decide_body(d, (cudaGraphConditionalHandle)a.handle, 1, 1);
+        }
+      }
+    }
   }
 }
 
