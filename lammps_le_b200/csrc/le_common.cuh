@@ -56,7 +56,6 @@ struct Params {
   double bk_d[LE_MAXB], br0_d[LE_MAXB], beps_d[LE_MAXB], bsig_d[LE_MAXB];
   double br0sq_d[LE_MAXB], binvr0sq_d[LE_MAXB], bsig2_d[LE_MAXB], bcore_d[LE_MAXB];  // R0^2, 1/R0^2, sigma^2, 2^(1/3) sigma^2
   double beps48_d[LE_MAXB];   // 48 epsilon (k_step2)
-  int bond_all_fene;          // every bond type is FENE (k_step2 evaluates two bonds side by side)
   // fp32 brackets around cutneighsq: below lo a pair is certainly listed, above hi certainly not; only the
   // sliver in between needs the reference's fp64 arithmetic (k_build)
   float cutneigh_lo[LE_MAXT * LE_MAXT], cutneigh_hi[LE_MAXT * LE_MAXT];

@@ -30,7 +30,7 @@ struct FixExUnloadCfg { int on, nevery, btype, seed; double rc, prob; };
 
 #define PLAIN_UNROLL 8      // timesteps per launch of the steady-state graph
 
-struct GraphKey { Dev d; int langevin; int variant; int rb_variant; };
+struct GraphKey { Dev d; int langevin; int variant; };
 
 struct le_ctx {
   int device, sm_count;
@@ -577,8 +577,6 @@ static int build_params(le_ctx *c) {
     P.bcore_d[k] = 1.2599210498948732 * P.bsig2_d[k];        // TWO_1_3 (bond_fene.cpp:22)
     P.beps48_d[k] = 48.0 * P.beps_d[k];
   }
-  P.bond_all_fene = c->nbondtypes > 0;
-  for (int k = 0; k < c->nbondtypes; k++) if (c->bstyle[k] != 1) P.bond_all_fene = 0;
   P.t_start = (float)c->t_start; P.t_stop = (float)c->t_stop; P.tsqrt_const = (float)sqrt(c->t_start);
   P.dt = (float)c->dt; P.dtf = (float)(0.5 * c->dt);       // FixNVE::init, ftm2v = 1
   P.triggersq = (float)(0.25 * c->skin * c->skin);
@@ -1003,14 +1001,12 @@ extern "C" int le_set_velocities(le_ctx *c, const double *v) {
 
 // ---- which plain step kernel (no energy / virial tally) -----------------------------------------------
 // LE_STEP_VARIANT (read at every le_run, so one process can compare variants): 0 = k_step; bit 0 = k_step2 (le_step2.cuh),
-// bit 1 = 128 threads per block instead of 256, bit 2 = L2 prefetch one wave ahead, bit 5 = persistent grid (k_step2p),
-// bits 5 + 3 = persistent and software-pipelined (k_step2q; bit 6: at full occupancy, with spills), bit 7 = thermostat
-// force computed under the gathers + two FENE bonds side by side (with or without bit 5), bit 9 (with bits 0 and 5) = the
-// step kernel's last block takes the reneighbor decision of the next timestep inside the steady-state graph, bit 4 = k_step2 also
-// on several GPUs.  k_step2 needs the uniform lj/cut case and special weights in {0, 1}; otherwise k_step runs whatever
-// the switch says.
+// bit 1 = 128 threads per block instead of 256, bit 5 = persistent grid (k_step2p), bit 9 (with bits 0 and 5) = the step
+// kernel's last block takes the reneighbor decision of the next timestep inside the steady-state graph, bit 4 = k_step2
+// also on several GPUs.  k_step2 needs the uniform lj/cut case and special weights in {0, 1}; otherwise k_step runs
+// whatever the switch says.
 #ifndef LE_STEP_VARIANT_DEFAULT
-#define LE_STEP_VARIANT_DEFAULT 33   // k_step2p<256>: fastest of the variants measured at 1M beads (profiles/r01_step_variants.txt)
+#define LE_STEP_VARIANT_DEFAULT 33   // k_step2p<0,256>: fastest of the variants measured at 1M beads (profiles/r01_step_variants.txt)
 #endif
 typedef void (*step_fn_t)(Dev, StepArgs);
 struct StepKernel { step_fn_t fn; int threads; const char *name; int wave_blocks; };   // wave_blocks: persistent grid, blocks per SM (0 = one block per NT atoms)
@@ -1023,28 +1019,20 @@ static bool step2_eligible(const le_ctx *c) {
   return true;
 }
 
-#define STEP2_CASE(dd, nt, pf, ilp) { (step_fn_t)k_step2<dd, nt, pf, ilp>, nt, "(k_step2<" #dd "," #nt "," #pf "," #ilp ">)", 0 }
-#define STEP2P_CASE(dd, nt, pf, ilp) { (step_fn_t)k_step2p<dd, nt, pf, ilp>, nt, "(k_step2p<" #dd "," #nt "," #pf "," #ilp ">)", 1024 / nt }
-#define STEP2Q_CASE(nt, bps) { (step_fn_t)k_step2q<nt, bps>, nt, "(k_step2q<" #nt "," #bps ">)", bps }
+#define STEP2_CASE(dd, nt) { (step_fn_t)k_step2<dd, nt>, nt, "(k_step2<" #dd "," #nt ">)", 0 }
+#define STEP2P_CASE(dd, nt) { (step_fn_t)k_step2p<dd, nt>, nt, "(k_step2p<" #dd "," #nt ">)", 1024 / nt }
 static StepKernel plain_step_kernel(const le_ctx *c, int variant) {
   const bool dd = c->nranks > 1;
   if ((variant & 1) && step2_eligible(c) && (!dd || (variant & 16))) {
-    const bool small = variant & 2, pf = variant & 4, pipe = variant & 8, pers = variant & 32, full = variant & 64, ilp = variant & 128;
+    const bool small = variant & 2, pers = variant & 32;
     if (dd) {
-      if (pers) return small ? StepKernel STEP2P_CASE(1, 128, 0, 0) : StepKernel STEP2P_CASE(1, 256, 0, 0);
-      return small ? StepKernel STEP2_CASE(1, 128, 0, 0) : StepKernel STEP2_CASE(1, 256, 0, 0);
+      if (pers) return small ? StepKernel STEP2P_CASE(1, 128) : StepKernel STEP2P_CASE(1, 256);
+      return small ? StepKernel STEP2_CASE(1, 128) : StepKernel STEP2_CASE(1, 256);
     }
-    if (pers && pipe) {
-      if (small) return full ? StepKernel STEP2Q_CASE(128, 8) : StepKernel STEP2Q_CASE(128, 6);
-      return full ? StepKernel STEP2Q_CASE(256, 4) : StepKernel STEP2Q_CASE(256, 3);
-    }
-    if (ilp) {
-      if (pers) return small ? StepKernel STEP2P_CASE(0, 128, 0, 1) : StepKernel STEP2P_CASE(0, 256, 0, 1);
-      return small ? StepKernel STEP2_CASE(0, 128, 0, 1) : StepKernel STEP2_CASE(0, 256, 0, 1);
-    }
-    static const StepKernel tab[8] = {STEP2_CASE(0, 256, 0, 0), STEP2_CASE(0, 128, 0, 0), STEP2_CASE(0, 256, 1, 0), STEP2_CASE(0, 128, 1, 0),
-                                      STEP2P_CASE(0, 256, 0, 0), STEP2P_CASE(0, 128, 0, 0), STEP2P_CASE(0, 256, 1, 0), STEP2P_CASE(0, 128, 1, 0)};
-    return tab[(small ? 1 : 0) | (pf ? 2 : 0) | (pers ? 4 : 0)];
+    if (pers && (variant & 512))   // with the epilogue of the fused reneighbor decision (same kernel name for the timing marks)
+      return small ? StepKernel{(step_fn_t)k_step2p<0, 128, 1>, 128, "(k_step2p<0,128,fuse>)", 8} : StepKernel{(step_fn_t)k_step2p<0, 256, 1>, 256, "(k_step2p<0,256,fuse>)", 4};
+    if (pers) return small ? StepKernel STEP2P_CASE(0, 128) : StepKernel STEP2P_CASE(0, 256);
+    return small ? StepKernel STEP2_CASE(0, 128) : StepKernel STEP2_CASE(0, 256);
   }
   const bool uni = c->P.pair_uniform != 0;
   static const int minb = getenv("LE_STEP_MINB") ? atoi(getenv("LE_STEP_MINB")) : 4;
@@ -1063,13 +1051,6 @@ static int step_grid(const le_ctx *c, const StepKernel &sk) {
 }
 
 // ---- rebuild / step drivers -------------------------------------------------------------------------
-// LE_REBUILD_VARIANT (read at every le_run): bit 0 = k_gather2 (scatter form of the in-cell ordering), bit 1 / bit 2 =
-// k_build screens 2 / 8 candidates per trip instead of 4
-#ifndef LE_REBUILD_VARIANT_DEFAULT
-#define LE_REBUILD_VARIANT_DEFAULT 0
-#endif
-static int rebuild_variant() { const char *v = getenv("LE_REBUILD_VARIANT"); return v ? atoi(v) : LE_REBUILD_VARIANT_DEFAULT; }
-
 // the rebuild kernels; `direct` adds the bookkeeping k_decide does when the rebuild is a conditional graph node
 static void enqueue_rebuild(le_ctx *c, bool direct) {
   Dev &d = c->d;
@@ -1084,8 +1065,7 @@ static void enqueue_rebuild(le_ctx *c, bool direct) {
   LAUNCH(c, k_scan_blocks, 1, SCAN_BLOCK, d);
   LAUNCH(c, k_scan_apply, d.nscanblocks, SCAN_BLOCK, d);
   LAUNCH(c, k_cell_scatter, grid_for(nslots, 256), 256, d);
-  if (rebuild_variant() & 1) LAUNCH(c, k_gather2, grid_for(nslots, 256), 256, d);
-  else LAUNCH(c, k_gather, grid_for(nslots, 256), 256, d);
+  LAUNCH(c, k_gather, grid_for(nslots, 256), 256, d);
   if (dd) {
     LAUNCH(c, k_push_ghosts, grid_for(std::max(d.own0, d.halo * d.ncell[1] * d.ncell[2] + 1), 256), 256, d);
     LAUNCH(c, k_rb_post_ghosts, 1, 1, d);
@@ -1094,10 +1074,7 @@ static void enqueue_rebuild(le_ctx *c, bool direct) {
   {
     static const int minb = getenv("LE_BUILD_MINB") ? atoi(getenv("LE_BUILD_MINB")) : 8;
     const int g = grid_for(nslots, BUILD_THREADS);
-    const int rbv = rebuild_variant();
-    if (rbv & 2) LAUNCH(c, (k_build<8, 2>), g, BUILD_THREADS, d);
-    else if (rbv & 4) LAUNCH(c, (k_build<8, 8>), g, BUILD_THREADS, d);
-    else if (minb == 10) LAUNCH(c, k_build<10>, g, BUILD_THREADS, d);
+    if (minb == 10) LAUNCH(c, k_build<10>, g, BUILD_THREADS, d);
     else if (minb == 12) LAUNCH(c, k_build<12>, g, BUILD_THREADS, d);
     else if (minb == 16) LAUNCH(c, k_build<16>, g, BUILD_THREADS, d);
     else if (minb == 6) LAUNCH(c, k_build<6>, g, BUILD_THREADS, d);
@@ -1169,13 +1146,12 @@ static int graph_add_unit(le_ctx *c, cudaGraph_t g, cudaGraphNode_t *tail, int a
 // the reneighbor decision fused into the step kernel (LE_STEP_VARIANT bit 9): only the persistent single-GPU kernel has
 // the last-block epilogue
 static bool fused_decide(const le_ctx *c, int variant) {
-  return (variant & 512) && c->nranks == 1 && plain_step_kernel(c, variant).fn != nullptr && (variant & 1) && (variant & 32) && !(variant & 8) &&
-         step2_eligible(c);
+  return (variant & 512) && (variant & 1) && (variant & 32) && c->nranks == 1 && step2_eligible(c);
 }
 
 static int ensure_graphs(le_ctx *c) {
   GraphKey key; memset(&key, 0, sizeof key);
-  key.d = c->d; key.langevin = c->langevin_on; key.variant = step_variant(); key.rb_variant = rebuild_variant();
+  key.d = c->d; key.langevin = c->langevin_on; key.variant = step_variant();
   if (c->graphs_ok && memcmp(&key, &c->gkey, sizeof key) == 0) return LE_OK;
   destroy_graphs(c);
   c->gkey_variant = key.variant;

@@ -661,31 +661,6 @@ __global__ void k_gather(Dev d) {
   }
 }
 
-// k_gather as a scatter: the thread of unsorted member i counts the members of its cell with a smaller tag (one pass
-// over the cell instead of one pass per member) and writes i's state to slot cell_start + rank.  Same permutation,
-// same arrays as k_gather.
-__global__ void k_gather2(Dev d) {
-  const int4 *__restrict__ pos = d.pos[d.ctrl->cur];
-  const int lo = d.own0, hi = d.own0 + d.ctrl->nown;
-  for (int k = lo + blockIdx.x * blockDim.x + threadIdx.x; k < hi; k += gridDim.x * blockDim.x) {
-    const int i = d.order[k];
-    const int4 p = pos[i];
-    const int c = d.cellid[i];
-    const int s = d.cell_start[c], e = d.cell_start[c + 1];
-    const int tg = p.w >> 3;
-    int rank = 0;
-    if (e - s > 1) {
-#pragma unroll 4
-      for (int b = s; b < e; b++) rank += (pos[d.order[b]].w >> 3) < tg;
-    }
-    const int ks = s + rank;
-    d.pos_hold[ks] = p;
-    d.vel_tmp[ks] = d.vel[i];
-    d.img_hold[ks] = d.img[i];
-    d.map[tg - 1] = ks;
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // rebuild, part 2 (multi-GPU): ghost creation (CommBrick::borders, src/comm_brick.cpp:727-876).
 //   Because x is the slowest index of the local order, the atoms of the slab's first / last `halo`
@@ -825,8 +800,8 @@ __device__ __forceinline__ void build_accept(const Dev &d, BuildCtx &B, const in
   B.n++;
 }
 
-// W: candidates fetched and screened per trip of the inner loop (independent loads in flight vs padded slots)
-template <int MINB, int W = 4>
+// (4 candidates per trip of the inner loop: 2 or 8 measured 30 % slower, profiles/r01_step_variants.txt)
+template <int MINB>
 __global__ void __launch_bounds__(BUILD_THREADS, MINB) k_build(Dev d) {
   __shared__ int s_q[BUILD_QUEUE][BUILD_THREADS];
   const int cap = d.cap;
@@ -892,12 +867,12 @@ __global__ void __launch_bounds__(BUILD_THREADS, MINB) k_build(Dev d) {
         if (yc < 0) yc += ncy; else if (yc >= ncy) yc -= ncy;
         const int base = cell_slot(d, xc, yc, 0);
         const int lo = __ldg(&d.cell_start[base + za]), hi = __ldg(&d.cell_start[base + zb + 1]);
-        for (int j = lo; j < hi; j += W) {
-          int4 p[W];
+        for (int j = lo; j < hi; j += 4) {
+          int4 p[4];
 #pragma unroll
-          for (int u = 0; u < W; u++) p[u] = __ldg(&ph[min(j + u, hi - 1)]);
+          for (int u = 0; u < 4; u++) p[u] = __ldg(&ph[min(j + u, hi - 1)]);
 #pragma unroll
-          for (int u = 0; u < W; u++) {
+          for (int u = 0; u < 4; u++) {
             const int idx = (int)((unsigned)p[u].x - (unsigned)pi.x);
             const int idy = (int)((unsigned)p[u].y - (unsigned)pi.y);
             const int idz = (int)((unsigned)p[u].z - (unsigned)pi.z);

@@ -1,9 +1,9 @@
-// le_step2.cuh -- k_step2: second generation of the fused step kernel (plain steps: no energy / virial tally).
+// le_step2.cuh -- k_step2 / k_step2p: second generation of the fused step kernel (plain steps: no energy / virial tally).
 //
 // Same physics and -- operation for operation, rounding for rounding -- the same arithmetic as k_step<0,*,*,1>
-// (le_md.cuh), so trajectories are bit-identical to it (scripts/step_ab.py checks exactly that); what changes is
-// how the work is issued.  The round-1 ncu capture of k_step (profiles/r01_ncu_full_kstep_kbuild.txt and the
-// per-instruction page) showed three things this kernel removes:
+// (le_md.cuh), so trajectories are bit-identical to it (tests/test_gpu_step2.py, scripts/step_ab.py check exactly
+// that); what changes is how the work is issued.  The round-1 ncu capture of k_step
+// (profiles/r01_kstep_sass_hotspots.txt) showed three things this kernel removes:
 //   * every warp began by waiting for Ctrl::cur (a dependent L2 round trip, 9 % of the stall samples) before it
 //     could address pos[cur]: the host knows the buffer parity of every launch -- also inside the captured graphs,
 //     which are instantiated once per starting parity -- and passes it as a kernel argument (StepArgs::rdp1);
@@ -13,7 +13,13 @@
 //     the first batch and their positions come back as one batch of four;
 //   * 842 warp instructions per 32 atoms, a third of them bookkeeping: branchy screens, development switches,
 //     per-type coefficient look-ups of the uniform case, 64-bit image-flag comparisons, spills.  Here: branch-free
-//     screens, one hit queue for all rows, carry-based image flags, no switches.
+//     screens, one survivor queue per row group, carry-based image flags, wide multiplies in Philox, no switches:
+//     758 instructions.
+// The persistent form k_step2p (one wave of blocks, grid stride) is the default: 44.5 us against k_step's 54.5 us at
+// 10^6 beads.  Measured and removed again (profiles/r01_step_variants.txt; git history has the code): L2 / L1 prefetch
+// of a thread's next atom, software pipelining with the next atom's head in registers, the thermostat force computed
+// under the gathers + two FENE bonds evaluated side by side, int -> double conversion on the fp64 pipe, a 32-byte
+// per-atom head record instead of eight arrays -- none of them faster than this form.
 // Specialisation (the host falls back to k_step otherwise): one lj/cut coefficient set for all type pairs, special
 // weights in {0, 1} only (every listed pair has factor 1).
 //   reference: PairLJCut::compute src/pair_lj_cut.cpp:68-140, BondFENE::compute src/MOLECULE/bond_fene.cpp:52-128,
@@ -85,42 +91,6 @@ __device__ __forceinline__ void bond_eval2(double &fx, double &fy, double &fz, C
   fx = __fma_rn(dx, fbond, fx); fy = __fma_rn(dy, fbond, fy); fz = __fma_rn(dz, fbond, fz);
 }
 
-// two FENE bonds side by side in one straight line of code (independent fp64 chains interleave; k_step's per-instruction
-// profile shows a dependent instruction every ~8 cycles, the bonds being the longest chains).  The WCA core term is
-// computed whether it applies or not and selected; values and order of the sums are those of two bond_eval2 calls.
-__device__ __forceinline__ void fene_eval2x(double &fx, double &fy, double &fz, Ctrl *ctrl, const int4 pi, const int4 pa, const int4 pb,
-                                            unsigned ea, unsigned eb, int tagi) {
-  const int bta = ea >> 28, btb = eb >> 28;
-  const double dya = __dmul_rn((double)((int)((unsigned)pi.y - (unsigned)pa.y)), c_P.scale[1]);
-  const double dyb = __dmul_rn((double)((int)((unsigned)pi.y - (unsigned)pb.y)), c_P.scale[1]);
-  const double dxa = __dmul_rn((double)((int)((unsigned)pi.x - (unsigned)pa.x)), c_P.scale[0]);
-  const double dxb = __dmul_rn((double)((int)((unsigned)pi.x - (unsigned)pb.x)), c_P.scale[0]);
-  const double dza = __dmul_rn((double)((int)((unsigned)pi.z - (unsigned)pa.z)), c_P.scale[2]);
-  const double dzb = __dmul_rn((double)((int)((unsigned)pi.z - (unsigned)pb.z)), c_P.scale[2]);
-  const double rsqa = __fma_rn(dza, dza, __fma_rn(dxa, dxa, __dmul_rn(dya, dya)));
-  const double rsqb = __fma_rn(dzb, dzb, __fma_rn(dxb, dxb, __dmul_rn(dyb, dyb)));
-  double rla = __fma_rn(-rsqa, c_P.binvr0sq_d[bta], 1.0), rlb = __fma_rn(-rsqb, c_P.binvr0sq_d[btb], 1.0);
-  if (rla < 0.1 || rlb < 0.1) {          // rare: an overstretched bond
-    if (rla <= -3.0) le_raise(ctrl, LE_DERR_BAD_FENE, tagi, (int)(ea & BOND_IDX_MASK));
-    else if (rlb <= -3.0) le_raise(ctrl, LE_DERR_BAD_FENE, tagi, (int)(eb & BOND_IDX_MASK));
-    if (rla < 0.1) rla = 0.1;
-    if (rlb < 0.1) rlb = 0.1;
-  }
-  const double ta = le_rcp2(__dmul_rn(rla, rsqa)), tb = le_rcp2(__dmul_rn(rlb, rsqb));
-  const double inv_rla = __dmul_rn(ta, rsqa), inv_rsqa = __dmul_rn(ta, rla);
-  const double inv_rlb = __dmul_rn(tb, rsqb), inv_rsqb = __dmul_rn(tb, rlb);
-  double fa = __dmul_rn(-c_P.bk_d[bta], inv_rla), fb = __dmul_rn(-c_P.bk_d[btb], inv_rlb);
-  const double sr2a = __dmul_rn(c_P.bsig2_d[bta], inv_rsqa), sr2b = __dmul_rn(c_P.bsig2_d[btb], inv_rsqb);
-  const double sr6a = __dmul_rn(sr2a, __dmul_rn(sr2a, sr2a)), sr6b = __dmul_rn(sr2b, __dmul_rn(sr2b, sr2b));
-  const double fca = __fma_rn(__dmul_rn(__dmul_rn(c_P.beps48_d[bta], sr6a), __dadd_rn(sr6a, -0.5)), inv_rsqa, fa);
-  const double fcb = __fma_rn(__dmul_rn(__dmul_rn(c_P.beps48_d[btb], sr6b), __dadd_rn(sr6b, -0.5)), inv_rsqb, fb);
-  fa = rsqa < c_P.bcore_d[bta] ? fca : fa;
-  fb = rsqb < c_P.bcore_d[btb] ? fcb : fb;
-  fx = __fma_rn(dxa, fa, fx); fy = __fma_rn(dya, fa, fy); fz = __fma_rn(dza, fa, fz);
-  fx = __fma_rn(dxb, fb, fx); fy = __fma_rn(dyb, fb, fy); fz = __fma_rn(dzb, fb, fz);
-}
-
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // same generator as philox4x32_7 (le_common.cuh) with each 32x32 -> 64-bit product taken as one wide multiply
 __device__ __forceinline__ void philox4x32_7w(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned out[4]) {
@@ -173,11 +143,9 @@ __device__ __forceinline__ Step2Head step2_head(const Dev &d, const int4 *__rest
   return h;
 }
 
-// one atom (slot i) of one timestep, its head already requested.  inext: the slot this thread's successor works on
-// (the same thread in a persistent grid, another block's thread otherwise), or -1; PF asks the L2 for its lines ahead
-// of time
-template <int DD, int PF, int ILP = 0>
-__device__ __forceinline__ void step2_atom(const Dev &d, const StepArgs &a, const int i, const int inext, const int rd, const Step2Head &h) {
+// one atom (slot i) of one timestep, its head already requested
+template <int DD>
+__device__ __forceinline__ void step2_atom(const Dev &d, const StepArgs &a, const int i, const int rd, const Step2Head &h) {
   const int cap = d.cap;
   Ctrl *__restrict__ ctrl = d.ctrl;
   const unsigned *__restrict__ neigh = d.neigh;
@@ -191,14 +159,6 @@ __device__ __forceinline__ void step2_atom(const Dev &d, const StepArgs &a, cons
   float4 vi = d.vel[i];
   const int4 ph = d.pos_hold[i];
   const long long step = ctrl->step;
-  if (PF && inext >= 0) {
-    const int ip = inext;
-    prefetch_l2(&posr[ip]); prefetch_l2(&d.vel[ip]); prefetch_l2(&d.pos_hold[ip]); prefetch_l2(&d.counts[ip]);
-    prefetch_l2(&neigh[ip]); prefetch_l2(&neigh[(size_t)cap + ip]); prefetch_l2(&neigh[(size_t)2 * cap + ip]);
-    prefetch_l2(&neigh[(size_t)3 * cap + ip]);
-    prefetch_l2(&bondrow[ip]); prefetch_l2(&bondrow[(size_t)(d.bpa > 1) * cap + ip]); prefetch_l2(&bondrow[(size_t)(d.bpa > 2 ? 2 : 0) * cap + ip]);
-  }
-
   const int nn = cnt & 0xff, nb = (cnt >> 16) & 0xff;
   const int ti = pi.w & 7;
   const int tag = pi.w >> 3;
@@ -215,10 +175,6 @@ __device__ __forceinline__ void step2_atom(const Dev &d, const StepArgs &a, cons
     et2 = nn > 6 ? __ldg(r4 + 2 * (size_t)cap) : 0u;
     et3 = nn > 7 ? __ldg(r4 + 3 * (size_t)cap) : 0u;
   }
-
-  // ILP: the thermostat's force is computed here, while the gathers are in flight (it needs nothing from them)
-  float lx = 0.f, ly = 0.f, lz = 0.f;
-  if (ILP && a.langevin) step2_langevin(lx, ly, lz, ctrl, vi, tag, ti, step);
 
   const float sx = c_P.fscale[0], sy = c_P.fscale[1], sz = c_P.fscale[2];
   const float cs = c_P.cutsq_screen[0];
@@ -273,15 +229,9 @@ __device__ __forceinline__ void step2_atom(const Dev &d, const StepArgs &a, cons
     const unsigned e = (b & 3u) ? ((b & 1u) ? en0 : en1) : ((b & 4u) ? en2 : en3);
     pair_eval2(fx, fy, fz, pi, __ldg(&posr[e & NEIGH_IDX_MASK]));   // second touch of the position: an L1 hit
   }
-  if (ILP && c_P.bond_all_fene) {
-    if (1 < nb) fene_eval2x(fx, fy, fz, ctrl, pi, pb0, pb1, eb0, eb1, tag);
-    else if (0 < nb) bond_eval2(fx, fy, fz, ctrl, pi, pb0, eb0, tag);
-    if (2 < nb) bond_eval2(fx, fy, fz, ctrl, pi, pb2, eb2, tag);
-  } else {
-    if (0 < nb) bond_eval2(fx, fy, fz, ctrl, pi, pb0, eb0, tag);
-    if (1 < nb) bond_eval2(fx, fy, fz, ctrl, pi, pb1, eb1, tag);
-    if (2 < nb) bond_eval2(fx, fy, fz, ctrl, pi, pb2, eb2, tag);
-  }
+  if (0 < nb) bond_eval2(fx, fy, fz, ctrl, pi, pb0, eb0, tag);
+  if (1 < nb) bond_eval2(fx, fy, fz, ctrl, pi, pb1, eb1, tag);
+  if (2 < nb) bond_eval2(fx, fy, fz, ctrl, pi, pb2, eb2, tag);
 #pragma unroll 1
   for (int mth = 3; mth < nb; mth++) {
     const unsigned e = __ldg(&bondrow[(size_t)mth * cap + i]);
@@ -289,7 +239,8 @@ __device__ __forceinline__ void step2_atom(const Dev &d, const StepArgs &a, cons
   }
 
   // ---- Langevin drag + uniform noise (post_force); fp32, added to the rounded conservative force ----
-  if (!ILP && a.langevin) step2_langevin(lx, ly, lz, ctrl, vi, tag, ti, step);
+  float lx = 0.f, ly = 0.f, lz = 0.f;
+  if (a.langevin) step2_langevin(lx, ly, lz, ctrl, vi, tag, ti, step);
 
   // ---- velocity Verlet ----
   const float dtfm = c_P.dtfm[ti];
@@ -340,8 +291,6 @@ __device__ __forceinline__ void step2_atom(const Dev &d, const StepArgs &a, cons
   d.vel[i] = vi;
 }
 
-#define STEP2_WAVE (148 * 1024)   // atoms one wave of resident threads works on
-
 // Work order on a slab of a multi-GPU run: the two boundary slices first, the interior last, so that the halo stores
 // are in flight while the interior computes (see k_step).  Segment starts are multiples of 64 slots.  Maps position g
 // of that order to a slot; returns own_end for a padding position.
@@ -363,10 +312,9 @@ __device__ __forceinline__ int step2_slot(const Step2Order &o, int g) {
   return i >= o.b_beg ? o.own_end : i;
 }
 
-// DD: multi-GPU slab (halo stores fused in, boundary slices first); NT: threads per block (1024 / NT blocks per SM);
-// PF: ask the L2 for the lines of the atom one wave ahead; ILP: thermostat force computed while the gathers are in
-// flight, two FENE bonds evaluated side by side
-template <int DD, int NT, int PF, int ILP = 0>
+// one block per NT atoms.  DD: multi-GPU slab (halo stores fused in, boundary slices first); NT: threads per block
+// (1024 / NT blocks per SM)
+template <int DD, int NT>
 __global__ void __launch_bounds__(NT, 1024 / NT) k_step2(Dev d, StepArgs a) {
   int i = d.own0 + blockIdx.x * NT + threadIdx.x;
   if (DD) {
@@ -377,14 +325,13 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_step2(Dev d, StepArgs a) {
     if (i >= d.own0 + d.N) return;   // one GPU owns every atom: no look at the control block before the loads
   }
   const int rd = a.rdp1 ? a.rdp1 - 1 : d.ctrl->cur;
-  const int inext = (!DD && i + STEP2_WAVE < d.own0 + d.N) ? i + STEP2_WAVE : -1;
-  step2_atom<DD, PF, ILP>(d, a, i, inext, rd, step2_head(d, d.pos[rd], i));
+  step2_atom<DD>(d, a, i, rd, step2_head(d, d.pos[rd], i));
 }
 
-// persistent form: one wave of blocks walks the atoms with a grid stride (no block launches inside the step, no
-// partial last wave); on a slab the stride runs over the boundary-first order.  PF: the lines of a thread's next
-// atom are requested into the L2 ahead of time
-template <int DD, int NT, int PF, int ILP = 0>
+// persistent form (the default): one wave of blocks walks the atoms with a grid stride -- no block launches inside
+// the step, no partial last wave; on a slab the stride runs over the boundary-first order.  FUSE: with the epilogue
+// that takes the reneighbor decision of the next timestep (StepArgs::fuse)
+template <int DD, int NT, int FUSE = 0>
 __global__ void __launch_bounds__(NT, 1024 / NT) k_step2p(Dev d, StepArgs a) {
   const int rd = a.rdp1 ? a.rdp1 - 1 : d.ctrl->cur;
   const int stride = gridDim.x * NT;
@@ -394,14 +341,14 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_step2p(Dev d, StepArgs a) {
 #pragma unroll 1
     for (int g = blockIdx.x * NT + threadIdx.x; g < gend; g += stride) {
       const int i = step2_slot(o, g);
-      if (i < o.own_end) step2_atom<DD, 0, ILP>(d, a, i, -1, rd, step2_head(d, d.pos[rd], i));
+      if (i < o.own_end) step2_atom<DD>(d, a, i, rd, step2_head(d, d.pos[rd], i));
     }
   } else {
     const int end = d.own0 + d.N;
 #pragma unroll 1
     for (int i = d.own0 + blockIdx.x * NT + threadIdx.x; i < end; i += stride)
-      step2_atom<DD, PF, ILP>(d, a, i, i + stride < end ? i + stride : -1, rd, step2_head(d, d.pos[rd], i));
-    if (a.fuse) {
+      step2_atom<DD>(d, a, i, rd, step2_head(d, d.pos[rd], i));
+    if (FUSE && a.fuse) {
       // the block that finishes last has seen the `moved` stores of all the others (fence + counter): it does k_decide's
       // work for the next timestep -- one kernel and one dependency bubble less per step inside the steady-state graph
       __syncthreads();
@@ -414,28 +361,5 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_step2p(Dev d, StepArgs a) {
         }
       }
     }
-  }
-}
-
-// persistent and software-pipelined: the head of a thread's NEXT atom is loaded into registers before the current atom
-// is worked on, so the gathers of every atom but the first start without waiting for memory.  Twelve more live
-// registers: NT x BPS threads per SM with BPS chosen so that nothing spills.
-template <int NT, int BPS>
-__global__ void __launch_bounds__(NT, BPS) k_step2q(Dev d, StepArgs a) {
-  const int rd = a.rdp1 ? a.rdp1 - 1 : d.ctrl->cur;
-  const int4 *__restrict__ posr = d.pos[rd];
-  const int end = d.own0 + d.N, stride = gridDim.x * NT;
-  int i = d.own0 + blockIdx.x * NT + threadIdx.x;
-  if (i >= end) return;
-  Step2Head cur = step2_head(d, posr, i);
-#pragma unroll 1
-  for (;;) {
-    const int in = i + stride;
-    const bool more = in < end;
-    const Step2Head nxt = step2_head(d, posr, more ? in : i);     // the last trip re-reads its own head (cache hits)
-    step2_atom<0, 0>(d, a, i, -1, rd, cur);
-    if (!more) break;
-    cur = nxt;
-    i = in;
   }
 }

@@ -1,7 +1,7 @@
 """GPU test: the second-generation step kernel (k_step2, csrc/le_step2.cuh) against the first (k_step).
 
-k_step2 issues the work differently (buffer parity as an argument, batched tail rows, one survivor queue, persistent /
-prefetching forms) but does the same arithmetic in the same order: trajectories must agree BIT FOR BIT, through the
+k_step2 issues the work differently (buffer parity as an argument, batched tail rows, one survivor queue, persistent
+grid) but does the same arithmetic in the same order: trajectories must agree BIT FOR BIT, through the
 captured-graph path and through direct launches, with and without the thermostat, for a dilute chain (short rows)
 and a dense melt (rows beyond the first batch)."""
 import numpy as np
@@ -11,7 +11,7 @@ from lammps_le_b200 import systems
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [1, 3, 5, 33, 35, 37, 41, 43, 105, 107, 129, 161, 163]   # bit 0 k_step2, 1: 128 threads, 2: L2 prefetch, 5: persistent, 5+3: pipelined, 6: full occupancy, 7: ILP
+VARIANTS = [1, 3, 33, 35]   # LE_STEP_VARIANT: bit 0 k_step2, bit 1 128-thread blocks, bit 5 persistent grid (33 = the default)
 
 
 def trajectory(monkeypatch, variant, system, v0, langevin, steps, dt):
