@@ -180,7 +180,9 @@ class DDEngine(Engine):
 
 
 def init_process_group():
-    """(rank, world, local_rank, gloo group) from the torchrun environment; (0, 1, 0, None) when run plainly"""
+    """(rank, world, local_rank, gloo group) from the torchrun environment; (0, 1, 0, None) when run plainly.
+    LE_DD_SHARE_GPU=1 puts every rank on device 0 (development on a one-GPU box: the slabs then time-slice one GPU and
+    talk through CUDA IPC exactly as they would over NVLink; NCCL refuses two ranks per device, so gloo only)."""
     import os
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -190,8 +192,11 @@ def init_process_group():
     import torch.distributed as dist
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("MASTER_PORT", "29511")
+    share = os.environ.get("LE_DD_SHARE_GPU", "0") == "1"
+    if share:
+        local = 0
     if not dist.is_initialized():
-        if torch.cuda.is_available():
+        if torch.cuda.is_available() and not share:
             torch.cuda.set_device(local)
             dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
         else:
