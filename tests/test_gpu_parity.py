@@ -126,6 +126,24 @@ def test_le_replay_live_reference():
     assert not problems, "USER-LE replay mismatches: %s" % problems[:5]
 
 
+@pytest.mark.xfail(reason="added after the last GPU call of round 1 (the oracle restatement passes these traces on the CPU, "
+                          "tests/test_oracle.py): first GPU run pending", strict=False)
+@pytest.mark.parametrize("name", ["closed", "open"])
+def test_le_replay_live_reference_barrier_variants(name):
+    """fully closed (p_through 0, CTCF every 100 beads) and fully transparent (p_through 1) barriers, dense event cadence"""
+    _need_ref()
+    from lammps_le_b200 import systems
+    from oracle.make_golden import le_trace
+    from tests.test_oracle import LE_VARIANTS
+    v = LE_VARIANTS[name]
+    s = systems.chromatin_chain(v["nbeads"], v["next_"], rho=0.2, seed=v["seed"], barriers=v["barriers"],
+                                p_left=0.03, p_right=0.03, p_block=0.01)
+    pre, post, _ = le_trace(s, v["steps"], H.le_deck_lines(v["deck"]))
+    problems, n = replay_events(pre, post, v["deck"])
+    assert n[1] >= 5 and n[2] >= 5 and n[3] >= 5
+    assert not problems, "USER-LE replay mismatches: %s" % problems[:5]
+
+
 def test_forces_live_reference_chain_and_melt():
     _need_ref()
     from lammps_le_b200 import systems

@@ -139,12 +139,11 @@ def test_reference_unit_vectors_bonds(name):
     assert np.abs(vir - c["init_stress"]).max() <= 5e-13 * np.abs(c["init_stress"]).max()
 
 
-def test_le_events_replay_golden_trace():
-    """every recorded USER-LE event of the compiled reference: oracle post-state == reference post-state, bit-exact
-    bond rows, special lists in exact order, types, counters and number of Marsaglia draws"""
-    pre, post = unpack_trace(np.load(os.path.join(GOLD, "le_trace_small.npz")))
-    cfg = H.LE_DECK
+def replay_with_oracle(pre, post, cfg):
+    """every recorded USER-LE event: oracle post-state == reference post-state, bit-exact bond rows, special lists in
+    exact order, types, counters and number of Marsaglia draws; returns the number of events per fix"""
     seen = {1: 0, 2: 0, 3: 0}
+    changed = {1: 0, 2: 0, 3: 0}
     for a, b in zip(pre, post):
         w = a["which"]
         S = R.copy_state(a)
@@ -170,4 +169,42 @@ def test_le_events_replay_golden_trace():
         assert cnt == b["counters"][w - 1]
         assert rng.c24() == b["rngc"][slot], "draw count differs at step %d fix %d" % (a["step"], w)
         seen[w] += 1
+        changed[w] += int((a["bond_atom"] != b["bond_atom"]).any() or (a["num_bond"] != b["num_bond"]).any())
+    return seen, changed
+
+
+def test_le_events_replay_golden_trace():
+    pre, post = unpack_trace(np.load(os.path.join(GOLD, "le_trace_small.npz")))
+    seen, _ = replay_with_oracle(pre, post, H.LE_DECK)
     assert seen[1] >= 3 and seen[2] >= 1 and seen[3] >= 1
+
+
+LE_VARIANTS = {
+    # transparent barriers, dense cadence: many slides, loads on a chain that already carries extruders
+    "open": dict(barriers="random", nbeads=900, next_=30, steps=620, seed=3, deck={
+        "extrusion": dict(nevery=100, neutral=1, left=2, right=3, p_through=1.0, btype=2, roadblock=4, seed=12345),
+        "ex_load": dict(nevery=50, itype=1, jtype=1, rc=1.12, btype=2, prob=0.2, seed=99, iparam=(1, 1), jparam=(1, 1)),
+        "ex_unload": dict(nevery=50, btype=2, rc=0.5, prob=0.2, seed=7)}),
+    # closed barriers every 100 beads (configs[1] layout): extruders stall at CTCF sites and behind each other
+    "closed": dict(barriers="periodic", nbeads=1000, next_=60, steps=620, seed=4, deck={
+        "extrusion": dict(nevery=100, neutral=1, left=2, right=3, p_through=0.0, btype=2, roadblock=4, seed=777),
+        "ex_load": dict(nevery=100, itype=1, jtype=1, rc=1.12, btype=2, prob=0.05, seed=684474, iparam=(1, 1), jparam=(1, 1)),
+        "ex_unload": dict(nevery=100, btype=2, rc=0.5, prob=0.05, seed=456456)}),
+}
+
+
+@pytest.mark.parametrize("name", sorted(LE_VARIANTS))
+def test_le_events_replay_live_reference_variants(name):
+    """the restatement against the compiled reference (oracle/_ref) on USER-LE settings the golden trace does not hold:
+    fully transparent and fully closed barriers, dense event cadence, more extruders per bead"""
+    if not refio.have_reference():
+        pytest.skip("oracle/_ref not built")
+    from lammps_le_b200 import systems
+    from oracle.make_golden import le_trace
+    v = LE_VARIANTS[name]
+    s = systems.chromatin_chain(v["nbeads"], v["next_"], rho=0.2, seed=v["seed"], barriers=v["barriers"],
+                                p_left=0.03, p_right=0.03, p_block=0.01)
+    pre, post, _ = le_trace(s, v["steps"], H.le_deck_lines(v["deck"]))
+    seen, changed = replay_with_oracle(pre, post, v["deck"])
+    assert seen[1] >= 5 and seen[2] >= 5 and seen[3] >= 5
+    assert changed[1] >= 3, "the extrusion fix must have moved bonds in this trace"
