@@ -30,7 +30,7 @@ struct FixExUnloadCfg { int on, nevery, btype, seed; double rc, prob; };
 
 #define PLAIN_UNROLL 8      // timesteps per launch of the steady-state graph
 
-struct GraphKey { Dev d; int langevin; int variant; };
+struct GraphKey { Dev d; int langevin; int variant; int pair32; };
 
 struct le_ctx {
   int device, sm_count;
@@ -541,6 +541,7 @@ static int build_params(le_ctx *c) {
       if (k > 0 && (c->eps[k] != c->eps[0] || c->sigma[k] != c->sigma[0] || c->cut[k] != c->cut[0])) uniform = false;
     }
   P.pair_uniform = uniform ? 1 : 0;
+  { const char *p32 = getenv("LE_PAIR_FP32"); P.pair32 = (p32 && p32[0] == '1') ? 1 : 0; }   // development switch, see pair_term32
   if (!(cutneighmax > 0.0)) return fail(c, LE_ESTATE, "pair cutoff is zero: set pair_style lj/cut first");
   P.cutneighmaxsq_f = (float)(cutneighmax * cutneighmax * (1.0 + 2e-5));
   for (int k = 0; k < 3; k++)
@@ -1025,6 +1026,11 @@ static StepKernel plain_step_kernel(const le_ctx *c, int variant) {
   const bool dd = c->nranks > 1;
   if ((variant & 1) && step2_eligible(c) && (!dd || (variant & 16))) {
     const bool small = variant & 2, pers = variant & 32;
+    if (c->P.pair32) {   // fp32 pair terms: 256-thread forms only
+      if (dd) return pers ? StepKernel{(step_fn_t)k_step2p<1, 256, 0, 1>, 256, "(k_step2p<1,256,p32>)", 4} : StepKernel{(step_fn_t)k_step2<1, 256, 1>, 256, "(k_step2<1,256,p32>)", 0};
+      if (pers && (variant & 512)) return StepKernel{(step_fn_t)k_step2p<0, 256, 1, 1>, 256, "(k_step2p<0,256,fuse,p32>)", 4};
+      return pers ? StepKernel{(step_fn_t)k_step2p<0, 256, 0, 1>, 256, "(k_step2p<0,256,p32>)", 4} : StepKernel{(step_fn_t)k_step2<0, 256, 1>, 256, "(k_step2<0,256,p32>)", 0};
+    }
     if (dd) {
       if (pers) return small ? StepKernel STEP2P_CASE(1, 128) : StepKernel STEP2P_CASE(1, 256);
       return small ? StepKernel STEP2_CASE(1, 128) : StepKernel STEP2_CASE(1, 256);
@@ -1034,6 +1040,7 @@ static StepKernel plain_step_kernel(const le_ctx *c, int variant) {
     if (pers) return small ? StepKernel STEP2P_CASE(0, 128) : StepKernel STEP2P_CASE(0, 256);
     return small ? StepKernel STEP2_CASE(0, 128) : StepKernel STEP2_CASE(0, 256);
   }
+  if (c->P.pair32) return StepKernel{dd ? (step_fn_t)k_step<0, 1, 4, 0, 1> : (step_fn_t)k_step<0, 0, 4, 0, 1>, STEP_THREADS, "(k_step<0,p32>)", 0};
   const bool uni = c->P.pair_uniform != 0;
   static const int minb = getenv("LE_STEP_MINB") ? atoi(getenv("LE_STEP_MINB")) : 4;
   step_fn_t fn;
@@ -1151,7 +1158,7 @@ static bool fused_decide(const le_ctx *c, int variant) {
 
 static int ensure_graphs(le_ctx *c) {
   GraphKey key; memset(&key, 0, sizeof key);
-  key.d = c->d; key.langevin = c->langevin_on; key.variant = step_variant();
+  key.d = c->d; key.langevin = c->langevin_on; key.variant = step_variant(); key.pair32 = c->P.pair32;
   if (c->graphs_ok && memcmp(&key, &c->gkey, sizeof key) == 0) return LE_OK;
   destroy_graphs(c);
   c->gkey_variant = key.variant;
@@ -1265,7 +1272,10 @@ static void thermo_from_slot(le_ctx *c, const double *s, int64_t step, le_thermo
 static void launch_step(le_ctx *c, StepArgs a, bool ev) {
   if (ev) {
     const int grid = grid_for(c->d.gr0 - c->d.own0, STEP_THREADS) + (c->nranks > 1 ? 1 : 0);
-    if (c->nranks > 1) LAUNCH(c, (k_step<1, 1>), grid, STEP_THREADS, c->d, a);
+    if (c->P.pair32) {
+      if (c->nranks > 1) LAUNCH(c, (k_step<1, 1, 4, 0, 1>), grid, STEP_THREADS, c->d, a);
+      else LAUNCH(c, (k_step<1, 0, 4, 0, 1>), grid, STEP_THREADS, c->d, a);
+    } else if (c->nranks > 1) LAUNCH(c, (k_step<1, 1>), grid, STEP_THREADS, c->d, a);
     else LAUNCH(c, (k_step<1, 0>), grid, STEP_THREADS, c->d, a);
     return;
   }

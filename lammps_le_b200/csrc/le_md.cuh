@@ -35,6 +35,7 @@ struct StepArgs {
 // ------------------------------------------------------------------------------------------------
 struct ForceAcc {
   double fx, fy, fz;
+  float px, py, pz;     // fp32 partial sum of the pair forces (Params::pair32)
   double evdwl, ebond;
   double pv[6], bv[6];
   double warn;
@@ -92,6 +93,31 @@ __device__ __forceinline__ void pair_term(ForceAcc &A, const int4 pi, const int4
       A.evdwl += factor * (r6inv * (c_P.lj3_d[tp] * r6inv - c_P.lj4_d[tp]) - c_P.offset_d[tp]);
       A.pv[0] += dx * dx * fpair; A.pv[1] += dy * dy * fpair; A.pv[2] += dz * dz * fpair;
       A.pv[3] += dx * dy * fpair; A.pv[4] += dx * dz * fpair; A.pv[5] += dy * dz * fpair;
+    }
+  }
+}
+
+// The same pair term in fp32 (Params::pair32; "fp32 pair math, fp64 accumulation"): listed pairs are never bonded
+// (special_bonds 0 x x drops the 1-2 pairs), so there is no FENE/WCA cancellation to protect and r^-14 turns the 1e-7 of an
+// fp32 r^2 into ~1e-6 of the pair force.  An atom's pair terms are summed in fp32 in row order (rows 0, 1, 2, ...), the
+// sum then joins the fp64 bond terms.  Shared by k_step and k_step2 so that both give the same bits.
+template <int EV, int UNI>
+__device__ __forceinline__ void pair_term32(ForceAcc &A, const int4 pi, const int4 pj, unsigned e, int ti, int nt, float sx, float sy, float sz) {
+  const float dxf = __fmul_rn((float)(int)((unsigned)pi.x - (unsigned)pj.x), sx);
+  const float dyf = __fmul_rn((float)(int)((unsigned)pi.y - (unsigned)pj.y), sy);
+  const float dzf = __fmul_rn((float)(int)((unsigned)pi.z - (unsigned)pj.z), sz);
+  const float rsqf = __fmaf_rn(dzf, dzf, __fmaf_rn(dxf, dxf, __fmul_rn(dyf, dyf)));
+  const int tp = UNI ? 0 : ti * nt + (pj.w & 7);
+  if (rsqf < c_P.cutsq[tp]) {
+    const float r2inv = __frcp_rn(rsqf);
+    const float r6inv = __fmul_rn(__fmul_rn(r2inv, r2inv), r2inv);
+    const float factor = c_P.special_lj[e >> 30];
+    const float fpair = __fmul_rn(__fmul_rn(__fmul_rn(factor, r6inv), __fmaf_rn(c_P.lj1[tp], r6inv, -c_P.lj2[tp])), r2inv);
+    A.px = __fmaf_rn(dxf, fpair, A.px); A.py = __fmaf_rn(dyf, fpair, A.py); A.pz = __fmaf_rn(dzf, fpair, A.pz);
+    if (EV) {
+      A.evdwl += (double)(factor * (r6inv * (c_P.lj3[tp] * r6inv - c_P.lj4[tp]) - c_P.offset[tp]));
+      A.pv[0] += (double)(dxf * dxf * fpair); A.pv[1] += (double)(dyf * dyf * fpair); A.pv[2] += (double)(dzf * dzf * fpair);
+      A.pv[3] += (double)(dxf * dyf * fpair); A.pv[4] += (double)(dxf * dzf * fpair); A.pv[5] += (double)(dyf * dzf * fpair);
     }
   }
 }
@@ -177,7 +203,8 @@ __device__ __forceinline__ int right_rank(const Dev &d) { return (d.rank + 1) % 
 #define STEP_NB 4     // neighbor slots fetched in the first batch
 #define STEP_BB 3     // bond slots fetched in the first batch
 
-template <int EV, int DD, int MINB = 4, int UNI = 0>
+// P32: pair terms in fp32 (Params::pair32; a separate instantiation so that the fp64 kernels stay as they were measured)
+template <int EV, int DD, int MINB = 4, int UNI = 0, int P32 = 0>
 __global__ void __launch_bounds__(STEP_THREADS, EV ? 2 : MINB) k_step(Dev d, StepArgs a) {
   const int cap = d.cap;
   Ctrl *__restrict__ ctrl = d.ctrl;
@@ -239,6 +266,20 @@ __global__ void __launch_bounds__(STEP_THREADS, EV ? 2 : MINB) k_step(Dev d, Ste
       A.evdwl = A.ebond = A.warn = 0.0;
 #pragma unroll
       for (int q = 0; q < 6; q++) { A.pv[q] = 0.0; A.bv[q] = 0.0; }
+    }
+    if (P32) {
+      A.px = A.py = A.pz = 0.f;
+      // pair terms in fp32, rows in ascending order (pair_term32)
+#pragma unroll
+      for (int k = 0; k < STEP_NB; k++)
+        if (k < nn && pair_screen<UNI>(pi, pn[k], ti, nt, sx, sy, sz)) pair_term32<EV, UNI>(A, pi, pn[k], en[k], ti, nt, sx, sy, sz);
+      for (int k = STEP_NB; k < nn; k++) {
+        const unsigned e0 = __ldg(&neigh[(size_t)k * cap + i]);
+        const int4 p0 = __ldg(&posr[e0 & NEIGH_IDX_MASK]);
+        if (pair_screen<UNI>(pi, p0, ti, nt, sx, sy, sz)) pair_term32<EV, UNI>(A, pi, p0, e0, ti, nt, sx, sy, sz);
+      }
+      A.fx = (double)A.px; A.fy = (double)A.py; A.fz = (double)A.pz;
+      nn = 0;                                   // nothing left for the fp64 pair code below
     }
     // screen every listed pair in fp32; the survivors (about one pair in five) are queued as a bit mask and
     // evaluated by one fp64 loop, so a warp runs the fp64 code max-over-lanes(#survivors) times, not once per slot

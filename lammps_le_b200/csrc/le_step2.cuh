@@ -58,6 +58,20 @@ __device__ __forceinline__ void pair_eval2(double &fx, double &fy, double &fz, c
   }
 }
 
+// one listed pair in fp32, added to the atom's fp32 pair sum (pair_term32<0,1> of le_md.cuh without the branch: a row
+// that is empty or outside the cutoff adds an exact zero, so the sums carry the same bits)
+__device__ __forceinline__ void pair_acc32(float &px, float &py, float &pz, const int4 pi, const int4 pj, bool live, float sx, float sy, float sz) {
+  const float dxf = __fmul_rn((float)(int)((unsigned)pi.x - (unsigned)pj.x), sx);
+  const float dyf = __fmul_rn((float)(int)((unsigned)pi.y - (unsigned)pj.y), sy);
+  const float dzf = __fmul_rn((float)(int)((unsigned)pi.z - (unsigned)pj.z), sz);
+  const float rsqf = __fmaf_rn(dzf, dzf, __fmaf_rn(dxf, dxf, __fmul_rn(dyf, dyf)));
+  const bool in = live && rsqf < c_P.cutsq[0];
+  const float r2inv = __frcp_rn(in ? rsqf : 1.0f);
+  const float r6inv = __fmul_rn(__fmul_rn(r2inv, r2inv), r2inv);
+  const float fpair = in ? __fmul_rn(__fmul_rn(r6inv, __fmaf_rn(c_P.lj1[0], r6inv, -c_P.lj2[0])), r2inv) : 0.f;
+  px = __fmaf_rn(dxf, fpair, px); py = __fmaf_rn(dyf, fpair, py); pz = __fmaf_rn(dzf, fpair, pz);
+}
+
 // FENE / harmonic term of one bond partner (bond_term<0>)
 __device__ __forceinline__ void bond_eval2(double &fx, double &fy, double &fz, Ctrl *ctrl, const int4 pi, const int4 pj,
                                            unsigned e, int tagi) {
@@ -143,8 +157,8 @@ __device__ __forceinline__ Step2Head step2_head(const Dev &d, const int4 *__rest
   return h;
 }
 
-// one atom (slot i) of one timestep, its head already requested
-template <int DD>
+// one atom (slot i) of one timestep, its head already requested.  P32: pair terms in fp32 (Params::pair32)
+template <int DD, int P32 = 0>
 __device__ __forceinline__ void step2_atom(const Dev &d, const StepArgs &a, const int i, const int rd, const Step2Head &h) {
   const int cap = d.cap;
   Ctrl *__restrict__ ctrl = d.ctrl;
@@ -177,57 +191,89 @@ __device__ __forceinline__ void step2_atom(const Dev &d, const StepArgs &a, cons
   }
 
   const float sx = c_P.fscale[0], sy = c_P.fscale[1], sz = c_P.fscale[2];
-  const float cs = c_P.cutsq_screen[0];
-  // screen every listed pair in fp32; bit k of `hit` = row k is (a hair more than) inside the force cutoff
-  // (the first four without a branch: an empty slot holds the atom itself, passes, and is masked off by the count)
-  unsigned hit = (screen2(pi, pn0, sx, sy, sz, cs) ? 1u : 0u) | (screen2(pi, pn1, sx, sy, sz, cs) ? 2u : 0u) |
-                 (screen2(pi, pn2, sx, sy, sz, cs) ? 4u : 0u) | (screen2(pi, pn3, sx, sy, sz, cs) ? 8u : 0u);
-  hit &= (1u << min(nn, 4)) - 1u;
-  // the bond partners' positions: requested now (the registers of the four screened positions are free again),
-  // they arrive while the survivors are evaluated
-  const int4 pb0 = __ldg(&posr[0 < nb ? (int)(eb0 & BOND_IDX_MASK) : i]);
-  const int4 pb1 = __ldg(&posr[1 < nb ? (int)(eb1 & BOND_IDX_MASK) : i]);
-  const int4 pb2 = __ldg(&posr[2 < nb ? (int)(eb2 & BOND_IDX_MASK) : i]);
-  // rows 4.. four at a time (the first group was requested with batch 2)
-#pragma unroll 1
-  for (int kb = 4; kb < nn && kb < 32; kb += 4) {
-    if (kb > 4) {
-      et0 = __ldg(&neigh[(size_t)kb * cap + i]);
-      et1 = kb + 1 < nn ? __ldg(&neigh[(size_t)(kb + 1) * cap + i]) : 0u;
-      et2 = kb + 2 < nn ? __ldg(&neigh[(size_t)(kb + 2) * cap + i]) : 0u;
-      et3 = kb + 3 < nn ? __ldg(&neigh[(size_t)(kb + 3) * cap + i]) : 0u;
-    }
-    const int4 q0 = __ldg(&posr[(int)(et0 & NEIGH_IDX_MASK)]);
-    const int4 q1 = __ldg(&posr[kb + 1 < nn ? (int)(et1 & NEIGH_IDX_MASK) : i]);
-    const int4 q2 = __ldg(&posr[kb + 2 < nn ? (int)(et2 & NEIGH_IDX_MASK) : i]);
-    const int4 q3 = __ldg(&posr[kb + 3 < nn ? (int)(et3 & NEIGH_IDX_MASK) : i]);
-    unsigned h = 0;
-    if (screen2(pi, q0, sx, sy, sz, cs)) h |= 1u;
-    if (kb + 1 < nn && screen2(pi, q1, sx, sy, sz, cs)) h |= 2u;
-    if (kb + 2 < nn && screen2(pi, q2, sx, sy, sz, cs)) h |= 4u;
-    if (kb + 3 < nn && screen2(pi, q3, sx, sy, sz, cs)) h |= 8u;
-    hit |= h << kb;
-  }
-
+  int4 pb0, pb1, pb2;      // the bond partners' positions
   double fx = 0.0, fy = 0.0, fz = 0.0;
-  // rows 32.. (dense systems only): no queue bit left, evaluate directly
+  if (P32) {
+    // pair terms in fp32, rows in ascending order, no branch for the first four; the bond partners' positions are
+    // requested in between and arrive while the tail rows are worked on
+    float px = 0.f, py = 0.f, pz = 0.f;
+    pair_acc32(px, py, pz, pi, pn0, 0 < nn, sx, sy, sz);
+    pair_acc32(px, py, pz, pi, pn1, 1 < nn, sx, sy, sz);
+    pair_acc32(px, py, pz, pi, pn2, 2 < nn, sx, sy, sz);
+    pair_acc32(px, py, pz, pi, pn3, 3 < nn, sx, sy, sz);
+    pb0 = __ldg(&posr[0 < nb ? (int)(eb0 & BOND_IDX_MASK) : i]);
+    pb1 = __ldg(&posr[1 < nb ? (int)(eb1 & BOND_IDX_MASK) : i]);
+    pb2 = __ldg(&posr[2 < nb ? (int)(eb2 & BOND_IDX_MASK) : i]);
 #pragma unroll 1
-  for (int k = 32; k < nn; k++) {
-    const unsigned e = __ldg(&neigh[(size_t)k * cap + i]);
-    pair_eval2(fx, fy, fz, pi, __ldg(&posr[e & NEIGH_IDX_MASK]));
-  }
-  // the survivors, evaluated in fp64 in the order k_step adds them: rows 4, 5, ... first, then 0..3; a warp runs each
-  // loop max-over-lanes(#survivors) times.  Rows 4.. are rare (their row entry is fetched again: an L1 hit)
+    for (int kb = 4; kb < nn; kb += 4) {
+      if (kb > 4) {
+        et0 = __ldg(&neigh[(size_t)kb * cap + i]);
+        et1 = kb + 1 < nn ? __ldg(&neigh[(size_t)(kb + 1) * cap + i]) : 0u;
+        et2 = kb + 2 < nn ? __ldg(&neigh[(size_t)(kb + 2) * cap + i]) : 0u;
+        et3 = kb + 3 < nn ? __ldg(&neigh[(size_t)(kb + 3) * cap + i]) : 0u;
+      }
+      const int4 q0 = __ldg(&posr[(int)(et0 & NEIGH_IDX_MASK)]);
+      const int4 q1 = __ldg(&posr[kb + 1 < nn ? (int)(et1 & NEIGH_IDX_MASK) : i]);
+      const int4 q2 = __ldg(&posr[kb + 2 < nn ? (int)(et2 & NEIGH_IDX_MASK) : i]);
+      const int4 q3 = __ldg(&posr[kb + 3 < nn ? (int)(et3 & NEIGH_IDX_MASK) : i]);
+      pair_acc32(px, py, pz, pi, q0, true, sx, sy, sz);
+      pair_acc32(px, py, pz, pi, q1, kb + 1 < nn, sx, sy, sz);
+      pair_acc32(px, py, pz, pi, q2, kb + 2 < nn, sx, sy, sz);
+      pair_acc32(px, py, pz, pi, q3, kb + 3 < nn, sx, sy, sz);
+    }
+    fx = (double)px; fy = (double)py; fz = (double)pz;
+  } else {
+    const float cs = c_P.cutsq_screen[0];
+    // screen every listed pair in fp32; bit k of `hit` = row k is (a hair more than) inside the force cutoff
+    // (the first four without a branch: an empty slot holds the atom itself, passes, and is masked off by the count)
+    unsigned hit = (screen2(pi, pn0, sx, sy, sz, cs) ? 1u : 0u) | (screen2(pi, pn1, sx, sy, sz, cs) ? 2u : 0u) |
+                   (screen2(pi, pn2, sx, sy, sz, cs) ? 4u : 0u) | (screen2(pi, pn3, sx, sy, sz, cs) ? 8u : 0u);
+    hit &= (1u << min(nn, 4)) - 1u;
+    // the bond partners' positions: requested now (the registers of the four screened positions are free again),
+    // they arrive while the survivors are evaluated
+    pb0 = __ldg(&posr[0 < nb ? (int)(eb0 & BOND_IDX_MASK) : i]);
+    pb1 = __ldg(&posr[1 < nb ? (int)(eb1 & BOND_IDX_MASK) : i]);
+    pb2 = __ldg(&posr[2 < nb ? (int)(eb2 & BOND_IDX_MASK) : i]);
+    // rows 4.. four at a time (the first group was requested with batch 2)
 #pragma unroll 1
-  for (unsigned m = hit >> 4; m; m &= m - 1) {
-    const unsigned e = __ldg(&neigh[(size_t)(__ffs(m) + 3) * cap + i]);
-    pair_eval2(fx, fy, fz, pi, __ldg(&posr[e & NEIGH_IDX_MASK]));
-  }
+    for (int kb = 4; kb < nn && kb < 32; kb += 4) {
+      if (kb > 4) {
+        et0 = __ldg(&neigh[(size_t)kb * cap + i]);
+        et1 = kb + 1 < nn ? __ldg(&neigh[(size_t)(kb + 1) * cap + i]) : 0u;
+        et2 = kb + 2 < nn ? __ldg(&neigh[(size_t)(kb + 2) * cap + i]) : 0u;
+        et3 = kb + 3 < nn ? __ldg(&neigh[(size_t)(kb + 3) * cap + i]) : 0u;
+      }
+      const int4 q0 = __ldg(&posr[(int)(et0 & NEIGH_IDX_MASK)]);
+      const int4 q1 = __ldg(&posr[kb + 1 < nn ? (int)(et1 & NEIGH_IDX_MASK) : i]);
+      const int4 q2 = __ldg(&posr[kb + 2 < nn ? (int)(et2 & NEIGH_IDX_MASK) : i]);
+      const int4 q3 = __ldg(&posr[kb + 3 < nn ? (int)(et3 & NEIGH_IDX_MASK) : i]);
+      unsigned h = 0;
+      if (screen2(pi, q0, sx, sy, sz, cs)) h |= 1u;
+      if (kb + 1 < nn && screen2(pi, q1, sx, sy, sz, cs)) h |= 2u;
+      if (kb + 2 < nn && screen2(pi, q2, sx, sy, sz, cs)) h |= 4u;
+      if (kb + 3 < nn && screen2(pi, q3, sx, sy, sz, cs)) h |= 8u;
+      hit |= h << kb;
+    }
+
+    // rows 32.. (dense systems only): no queue bit left, evaluate directly
 #pragma unroll 1
-  for (unsigned m = hit & 15u; m; m &= m - 1) {
-    const unsigned b = m & (0u - m);                         // lowest survivor: 1, 2, 4 or 8
-    const unsigned e = (b & 3u) ? ((b & 1u) ? en0 : en1) : ((b & 4u) ? en2 : en3);
-    pair_eval2(fx, fy, fz, pi, __ldg(&posr[e & NEIGH_IDX_MASK]));   // second touch of the position: an L1 hit
+    for (int k = 32; k < nn; k++) {
+      const unsigned e = __ldg(&neigh[(size_t)k * cap + i]);
+      pair_eval2(fx, fy, fz, pi, __ldg(&posr[e & NEIGH_IDX_MASK]));
+    }
+    // the survivors, evaluated in fp64 in the order k_step adds them: rows 4, 5, ... first, then 0..3; a warp runs each
+    // loop max-over-lanes(#survivors) times.  Rows 4.. are rare (their row entry is fetched again: an L1 hit)
+#pragma unroll 1
+    for (unsigned m = hit >> 4; m; m &= m - 1) {
+      const unsigned e = __ldg(&neigh[(size_t)(__ffs(m) + 3) * cap + i]);
+      pair_eval2(fx, fy, fz, pi, __ldg(&posr[e & NEIGH_IDX_MASK]));
+    }
+#pragma unroll 1
+    for (unsigned m = hit & 15u; m; m &= m - 1) {
+      const unsigned b = m & (0u - m);                         // lowest survivor: 1, 2, 4 or 8
+      const unsigned e = (b & 3u) ? ((b & 1u) ? en0 : en1) : ((b & 4u) ? en2 : en3);
+      pair_eval2(fx, fy, fz, pi, __ldg(&posr[e & NEIGH_IDX_MASK]));   // second touch of the position: an L1 hit
+    }
   }
   if (0 < nb) bond_eval2(fx, fy, fz, ctrl, pi, pb0, eb0, tag);
   if (1 < nb) bond_eval2(fx, fy, fz, ctrl, pi, pb1, eb1, tag);
@@ -314,7 +360,7 @@ __device__ __forceinline__ int step2_slot(const Step2Order &o, int g) {
 
 // one block per NT atoms.  DD: multi-GPU slab (halo stores fused in, boundary slices first); NT: threads per block
 // (1024 / NT blocks per SM)
-template <int DD, int NT>
+template <int DD, int NT, int P32 = 0>
 __global__ void __launch_bounds__(NT, 1024 / NT) k_step2(Dev d, StepArgs a) {
   int i = d.own0 + blockIdx.x * NT + threadIdx.x;
   if (DD) {
@@ -325,13 +371,13 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_step2(Dev d, StepArgs a) {
     if (i >= d.own0 + d.N) return;   // one GPU owns every atom: no look at the control block before the loads
   }
   const int rd = a.rdp1 ? a.rdp1 - 1 : d.ctrl->cur;
-  step2_atom<DD>(d, a, i, rd, step2_head(d, d.pos[rd], i));
+  step2_atom<DD, P32>(d, a, i, rd, step2_head(d, d.pos[rd], i));
 }
 
 // persistent form (the default): one wave of blocks walks the atoms with a grid stride -- no block launches inside
 // the step, no partial last wave; on a slab the stride runs over the boundary-first order.  FUSE: with the epilogue
-// that takes the reneighbor decision of the next timestep (StepArgs::fuse)
-template <int DD, int NT, int FUSE = 0>
+// that takes the reneighbor decision of the next timestep (StepArgs::fuse); P32: pair terms in fp32 (Params::pair32)
+template <int DD, int NT, int FUSE = 0, int P32 = 0>
 __global__ void __launch_bounds__(NT, 1024 / NT) k_step2p(Dev d, StepArgs a) {
   const int rd = a.rdp1 ? a.rdp1 - 1 : d.ctrl->cur;
   const int stride = gridDim.x * NT;
@@ -341,13 +387,13 @@ __global__ void __launch_bounds__(NT, 1024 / NT) k_step2p(Dev d, StepArgs a) {
 #pragma unroll 1
     for (int g = blockIdx.x * NT + threadIdx.x; g < gend; g += stride) {
       const int i = step2_slot(o, g);
-      if (i < o.own_end) step2_atom<DD>(d, a, i, rd, step2_head(d, d.pos[rd], i));
+      if (i < o.own_end) step2_atom<DD, P32>(d, a, i, rd, step2_head(d, d.pos[rd], i));
     }
   } else {
     const int end = d.own0 + d.N;
 #pragma unroll 1
     for (int i = d.own0 + blockIdx.x * NT + threadIdx.x; i < end; i += stride)
-      step2_atom<DD>(d, a, i, rd, step2_head(d, d.pos[rd], i));
+      step2_atom<DD, P32>(d, a, i, rd, step2_head(d, d.pos[rd], i));
     if (FUSE && a.fuse) {
       // the block that finishes last has seen the `moved` stores of all the others (fence + counter): it does k_decide's
       // work for the next timestep -- one kernel and one dependency bubble less per step inside the steady-state graph

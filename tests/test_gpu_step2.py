@@ -71,3 +71,38 @@ def test_fused_decide_matches_step(monkeypatch):
     ref = trajectory(monkeypatch, 0, s, v, True, 150, 0.005)
     got = trajectory(monkeypatch, 1 + 32 + 512, s, v, True, 150, 0.005)
     assert np.array_equal(got[0][0], ref[0][0]) and np.array_equal(got[1], ref[1]) and got[2] == ref[2]
+
+
+PENDING = "fp32 pair terms (LE_PAIR_FP32=1) were written after the last GPU call of round 1: first run pending"
+
+
+@pytest.mark.xfail(reason=PENDING, strict=False)
+def test_pair_fp32_forces_meet_the_per_atom_bar(monkeypatch):
+    """pair terms in fp32, bonds in fp64: step-0 forces of the golden chain within 1e-5 per atom of the reference"""
+    import os
+    from tests import lehelpers as H
+    from tests.test_gpu_parity import CHROMATIN_BONDS, GOLD, _force_record_from_npz, check_forces
+    monkeypatch.setenv("LE_PAIR_FP32", "1")
+    rec = _force_record_from_npz(np.load(os.path.join(GOLD, "forces_chain.npz")))
+    e = H.engine_from_record(rec, CHROMATIN_BONDS, positions="x")
+    e.force_rebuild()
+    err = check_forces(e, rec)          # asserts <= 1e-5 per atom, energies and virial to 1e-5
+    e.close()
+    assert err is None or err <= 1e-5
+
+
+@pytest.mark.xfail(reason=PENDING, strict=False)
+def test_pair_fp32_step2_matches_step(monkeypatch):
+    """k_step2p and k_step sum an atom's fp32 pair terms in the same order: same bits"""
+    monkeypatch.setenv("LE_PAIR_FP32", "1")
+    n = 6000
+    s, v = relaxed(systems.chromatin_chain(n, 60, rho=0.2, seed=5), n, 600)
+    ref = trajectory(monkeypatch, 0, s, v, True, 150, 0.005)
+    for var in (1, 33):
+        got = trajectory(monkeypatch, var, s, v, True, 150, 0.005)
+        assert np.array_equal(got[0][0], ref[0][0]) and np.array_equal(got[1], ref[1]), "variant %d" % var
+    m = systems.fene_melt(nchains=40, length=100)
+    m, vm = relaxed(m, len(m["types"]), 400)
+    ref = trajectory(monkeypatch, 0, m, vm, True, 100, 0.005)
+    got = trajectory(monkeypatch, 33, m, vm, True, 100, 0.005)
+    assert np.array_equal(got[0][0], ref[0][0]) and np.array_equal(got[1], ref[1]), "melt"

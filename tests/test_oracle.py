@@ -208,3 +208,39 @@ def test_le_events_replay_live_reference_variants(name):
     seen, changed = replay_with_oracle(pre, post, v["deck"])
     assert seen[1] >= 5 and seen[2] >= 5 and seen[3] >= 5
     assert changed[1] >= 3, "the extrusion fix must have moved bonds in this trace"
+
+
+def test_fp32_pair_math_error_budget(force_rec):
+    """Error budget of the optional fp32 pair path (LE_PAIR_FP32=1, pair_term32 in csrc/le_md.cuh), emulated operation for
+    operation in numpy float32 on the golden chain: WCA pair terms in fp32 on the fixed-point differences, bonds in
+    fp64.  The per-atom force error must stay below the 1e-5 bar (it sits near 6e-6: in a minimised state pair and
+    bond terms of order 10 cancel to a net force of order 1); the default fp64 pair path is at 1e-12."""
+    c = force_rec
+    x, lo, hi = c["x"], c["boxlo"], c["boxhi"]
+    L = hi - lo
+    n = len(x)
+    rows = R.half_neighbor_list(x, lo, hi, 1.12246 + 0.4, c["nspecial"], c["special"])
+    pi = np.array([t for t in range(n) for _ in rows[t]], dtype=int)
+    pj = np.array([(v & R.NEIGHMASK) - 1 for t in range(n) for v in rows[t]], dtype=int)
+    b1, b2, bt = R.unique_bonds(c["num_bond"], c["bond_type"], c["bond_atom"])
+    fb, _, _, _ = R.bond_forces(x, L, b1, b2, bt, {1: ("fene", (30.0, 1.5, 1.0, 1.0)), 2: ("harmonic", (20.0, 1.3))})
+    u = np.rint((x - lo) / L * 4294967296.0).astype(np.int64)
+    d = ((u[pi] - u[pj]) + 2 ** 31) % 2 ** 32 - 2 ** 31                  # signed 32-bit difference = minimum image
+    df = d.astype(np.float32) * (L / 4294967296.0).astype(np.float32)[None, :]
+
+    def fma(a, b, cc):
+        return (a.astype(np.float64) * b.astype(np.float64) + cc.astype(np.float64)).astype(np.float32)
+
+    rsq = fma(df[:, 2], df[:, 2], fma(df[:, 0], df[:, 0], df[:, 1] * df[:, 1]))
+    inn = rsq < np.float32(1.12246 ** 2)
+    r2 = np.float32(1.0) / np.where(inn, rsq, np.float32(1.0))
+    r6 = (r2 * r2) * r2
+    fp = np.where(inn, (r6 * fma(np.full_like(r6, 48.0), r6, np.full_like(r6, -24.0))) * r2, np.float32(0.0))
+    contrib = (df * fp[:, None]).astype(np.float64)
+    f = fb.copy()
+    np.add.at(f, pi, contrib)
+    np.add.at(f, pj, -contrib)
+    mag = np.sqrt((c["f"] ** 2).sum(1))
+    err = np.sqrt(((f - c["f"]) ** 2).sum(1)) / np.maximum(mag, np.sqrt((mag ** 2).mean()))
+    assert inn.sum() > 100
+    assert 1e-7 < err.max() <= 1e-5, "fp32 pair path: max per-atom relative force error %.3g" % err.max()
