@@ -14,7 +14,8 @@ e2e        same metric through the C ABI with HOST buffers: every step uploads p
            pinned host memory, runs, and downloads positions
 roofline   fused step kernel (k_step2p, le_step2.cuh): algorithmic bytes (72.1 + 4 nbar per atom-step, nbar measured)
            / CUDA-event time of the step loop, against MEASURED_PEAKS.json hbm_gbs
-cpu_baseline  the compiled reference (oracle/_ref/lmp_ref) on a bounded sample of the same workload
+cpu_baseline  the compiled reference (oracle/_ref, threaded USER-OMP build when present, up to 16 host threads) on a
+              bounded sample of the same workload
 """
 import argparse
 import json
@@ -117,9 +118,10 @@ def prepared_engine(n_beads, n_ext, seed, device, relax_steps, dd=None):
     return s, e
 
 
-def reference_rate(s, x, image, v, topo, md_steps_per_seg, nseg_warm, nseg_timed, workdir=None):
+def reference_rate(s, x, image, v, topo, md_steps_per_seg, nseg_warm, nseg_timed, workdir=None, threads=1):
     """atom-steps/s of oracle/_ref/lmp_ref on the same (relaxed) state; window placed so that one ex_unload
-    and one ex_load event fall inside the timed segments and no fix extrusion event does."""
+    and one ex_load event fall inside the timed segments and no fix extrusion event does.
+    threads > 1: the threaded build of the reference (oracle/_ref/omp, USER-OMP styles via `-sf omp`)."""
     from oracle import refio
     wd = workdir or tempfile.mkdtemp(prefix="le_bench_ref_")
     n = len(s["types"])
@@ -140,7 +142,7 @@ def reference_rate(s, x, image, v, topo, md_steps_per_seg, nseg_warm, nseg_timed
     deck += ["thermo_style custom step temp epair emol bonds", "thermo 1000000", "timestep 0.005"]
     deck += ["run %d" % md_steps_per_seg] * (nseg_warm + nseg_timed)
     t0 = time.time()
-    out, _ = refio.run_reference(deck, workdir=wd, harness=False, timeout=3000)
+    out, _ = refio.run_reference(deck, workdir=wd, harness=False, timeout=3000, threads=threads)
     wall = time.time() - t0
     import re
     loops = [(float(a), int(b)) for a, b in re.findall(r"Loop time of ([0-9.eE+-]+) on \d+ procs for (\d+) steps", out)]
@@ -148,6 +150,23 @@ def reference_rate(s, x, image, v, topo, md_steps_per_seg, nseg_warm, nseg_timed
     tsum = sum(t for t, _ in timed)
     steps = sum(k for _, k in timed)
     return n * steps / tsum, tsum / max(len(timed), 1), wall, steps
+
+
+def reference_threads():
+    """host threads for the reference: all the cores of the box when the threaded build is there (one MPI rank in any
+    case: the USER-LE fixes are only defined on one rank), else 1"""
+    from oracle import refio
+    if not refio.have_threaded_reference():
+        return 1
+    if os.environ.get("LE_REF_THREADS"):
+        return max(1, int(os.environ["LE_REF_THREADS"]))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    # beyond ~16 threads the threaded part (pair, bond, neighbor, nve) no longer shrinks the step: fix langevin and the
+    # USER-LE fixes are serial (measured here: 1.5x at 4 and at 8 threads)
+    return max(1, min(cores, 16))
 
 
 def run_ours(args):
@@ -273,11 +292,13 @@ def run_ours(args):
                 topo = e.topology()
                 seg = max(4, int(2.0e6 / n_beads * 8))          # ~16 MD steps per segment at 1M beads
                 xo, im = e.positions()
-                rate, _, wall_ref, nst = reference_rate(s, xo, im, e.velocities(), topo, seg, 1, 5)
-                line["cpu_baseline"] = {"value": rate, "unit": "atom-steps/s", "cores": 1, "kind": "reference",
-                                        "sample": "%d MD steps of the same relaxed state in oracle/_ref/lmp_ref (1 rank: USER-LE is only "
-                                                  "defined on one rank), window holds one ex_unload and one ex_load event, %.0f s wall incl. setup"
-                                                  % (nst, wall_ref)}
+                nthr = reference_threads()
+                rate, _, wall_ref, nst = reference_rate(s, xo, im, e.velocities(), topo, seg, 1, 5, threads=nthr)
+                line["cpu_baseline"] = {"value": rate, "unit": "atom-steps/s", "cores": nthr, "kind": "reference",
+                                        "sample": "%d MD steps of the same relaxed state in the compiled reference (oracle/_ref, 1 MPI rank: USER-LE "
+                                                  "is only defined on one rank; %s), window holds one ex_unload and one ex_load event, %.0f s wall "
+                                                  "incl. setup" % (nst, "%d OpenMP threads, USER-OMP pair/bond/neighbor/nve styles, fix langevin and "
+                                                  "the USER-LE fixes serial" % nthr if nthr > 1 else "serial build", wall_ref)}
             else:
                 line["cpu_baseline"] = {"value": None, "unit": "atom-steps/s", "cores": 0, "kind": "reference",
                                         "sample": "oracle/_ref missing on this box"}
@@ -327,13 +348,14 @@ def run_reference_arm(args):
                 nb[p - 1] += 1
         topo = {"num_bond": nb, "bond_type": btab, "bond_atom": atab}
     seg = max(4, int(2.0e6 / n_beads * 8))
-    rate, t_seg, wall, nst = reference_rate(s, x, im, v, topo, seg, args.warmup, args.steps)
+    nthr = reference_threads()
+    rate, t_seg, wall, nst = reference_rate(s, x, im, v, topo, seg, args.warmup, args.steps, threads=nthr)
     line = {"impl": "reference", "metric": "atom-steps/s", "value": rate, "unit": "atom-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_seg, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD if n_beads == 1000000 else "same model, %d beads, %d extruders" % (n_beads, n_ext),
-                       "md_steps_per_step": seg, "parallelism": "1 MPI rank (serial stubs)"},
-            "cpu_baseline": {"value": rate, "unit": "atom-steps/s", "cores": 1, "kind": "reference",
+                       "md_steps_per_step": seg, "parallelism": "1 MPI rank (serial stubs), %d OpenMP thread(s)" % nthr},
+            "cpu_baseline": {"value": rate, "unit": "atom-steps/s", "cores": nthr, "kind": "reference",
                              "sample": "%d MD steps in %d `run` segments, %s; window holds one ex_unload + one ex_load event; "
                                        "Loop time of each segment as LAMMPS prints it" % (nst, args.steps, prep)},
             "e2e": {"value": rate, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

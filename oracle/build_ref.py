@@ -34,6 +34,30 @@ OBJ = os.path.join(OUT, "obj")
 SRC_DIRS = ["src", "src/MOLECULE", "src/USER-LE"]
 CXXFLAGS = ["-O2", "-std=c++11", "-fPIC", "-DLAMMPS_SMALLBIG", "-DLAMMPS_EXCEPTIONS",
             "-ffp-contract=off", "-w"]
+OMP = False      # second build (oracle/_ref/omp/): the same sources + the USER-OMP styles whose base style is compiled, -fopenmp
+
+
+def set_variant(omp):
+    """switch the module-level paths / flags between the serial build and the threaded one (bench.py's reference arm)"""
+    global OUT, GEN, OBJ, SRC_DIRS, CXXFLAGS, OMP
+    OMP = omp
+    OUT = os.path.join(HERE, "_ref", "omp") if omp else os.path.join(HERE, "_ref")
+    GEN, OBJ = os.path.join(OUT, "gen"), os.path.join(OUT, "obj")
+    SRC_DIRS = ["src", "src/MOLECULE", "src/USER-LE"] + (["src/USER-OMP"] if omp else [])
+    CXXFLAGS = ["-O2", "-std=c++11", "-fPIC", "-DLAMMPS_SMALLBIG", "-DLAMMPS_EXCEPTIONS", "-ffp-contract=off", "-w"]
+    if omp:
+        CXXFLAGS += ["-fopenmp", "-DLMP_USER_OMP"]
+
+
+def omp_file_wanted(name):
+    """src/USER-OMP/Install.sh: x_omp.{cpp,h} is installed only if x.{cpp,h} exists among the compiled sources"""
+    if name in ("thr_omp.cpp", "thr_omp.h", "thr_data.cpp", "thr_data.h"):
+        return True
+    m = re.match(r"(.*)_omp\.(cpp|h)$", name)
+    if not m:
+        return False
+    base = "%s.%s" % (m.group(1), m.group(2))
+    return any(os.path.exists(os.path.join(REF, d, base)) for d in ("src", "src/MOLECULE", "src/USER-LE"))
 
 # (marker in header, filename prefix regex, style_<name>.h)
 STYLES = [
@@ -69,7 +93,7 @@ def gen_headers():
     headers = []
     for d in SRC_DIRS:
         p = os.path.join(REF, d)
-        headers += [os.path.join(p, h) for h in sorted(os.listdir(p)) if h.endswith(".h")]
+        headers += [os.path.join(p, h) for h in sorted(os.listdir(p)) if h.endswith(".h") and (d != "src/USER-OMP" or omp_file_wanted(h))]
     first_lines = {}
     for h in headers:
         with open(h, errors="replace") as f:
@@ -90,7 +114,7 @@ def gen_headers():
     write_if_changed(os.path.join(GEN, "lmpinstalledpkgs.h"),
                      "#ifndef LMP_INSTALLED_PKGS_H\n#define LMP_INSTALLED_PKGS_H\n"
                      "const char * LAMMPS_NS::LAMMPS::installed_packages[] = "
-                     '{"MOLECULE", "USER-LE", NULL};\n#endif\n')
+                     '{"MOLECULE", "USER-LE"%s, NULL};\n#endif\n' % (', "USER-OMP"' if OMP else ""))
     write_if_changed(os.path.join(GEN, "lmpgitversion.h"),
                      "#ifndef LMP_GIT_VERSION_H\n#define LMP_GIT_VERSION_H\n"
                      "const bool LAMMPS_NS::LAMMPS::has_git_info = false;\n"
@@ -114,9 +138,9 @@ def compile_one(job):
     return r.returncode, src, r.stderr
 
 
-def main():
+def build():
     if not os.path.isdir(os.path.join(REF, "src")):
-        if os.path.exists(os.path.join(OUT, "ref_harness")):
+        if os.path.exists(os.path.join(OUT, "lmp_ref" if OMP else "ref_harness")):
             print("oracle/_ref: reference tree absent, using prebuilt files")
             return 0
         print("oracle/_ref: reference tree absent and nothing prebuilt", file=sys.stderr)
@@ -127,7 +151,7 @@ def main():
     for d in SRC_DIRS:
         p = os.path.join(REF, d)
         for s in sorted(os.listdir(p)):
-            if s.endswith(".cpp") and s != "main.cpp":
+            if s.endswith(".cpp") and s != "main.cpp" and (d != "src/USER-OMP" or omp_file_wanted(s)):
                 jobs.append((os.path.join(p, s), os.path.join(OBJ, s[:-4] + ".o"), "g++"))
     jobs.append((os.path.join(REF, "src/STUBS/mpi.c"), os.path.join(OBJ, "mpi_stubs.o"), "gcc"))
     nthreads = int(os.environ.get("LE_BUILD_JOBS", str(os.cpu_count() or 4)))
@@ -143,7 +167,7 @@ def main():
     objs = [j[1] for j in jobs]
     lib = os.path.join(OUT, "liblammps_ref.so")
     if not up_to_date(lib, objs):
-        subprocess.check_call(["g++", "-shared", "-o", lib] + objs)
+        subprocess.check_call(["g++", "-shared", "-o", lib] + objs + (["-fopenmp"] if OMP else []))
     rpath = "-Wl,-rpath,$ORIGIN"
     lmp = os.path.join(OUT, "lmp_ref")
     main_cpp = os.path.join(REF, "src/main.cpp")
@@ -152,11 +176,26 @@ def main():
                                                                  "-llammps_ref", rpath])
     harness_src = os.path.join(HERE, "ref_harness.cpp")
     harness = os.path.join(OUT, "ref_harness")
-    if os.path.exists(harness_src) and not up_to_date(harness, [lib, harness_src]):
+    if not OMP and os.path.exists(harness_src) and not up_to_date(harness, [lib, harness_src]):
         subprocess.check_call(["g++"] + CXXFLAGS + includes() + [harness_src, "-o", harness, "-L" + OUT,
                                                                  "-llammps_ref", rpath])
     print("oracle/_ref built:", lib)
     return 0
+
+
+def main():
+    set_variant(False)
+    rc = build()
+    if rc == 0 and os.path.isdir(os.path.join(REF, "src/USER-OMP")) and os.environ.get("LE_REF_OMP", "1") == "1":
+        # the threaded build only feeds bench.py's reference arm; its failure must not take the oracle down
+        set_variant(True)
+        try:
+            if build():
+                print("oracle/_ref/omp: threaded reference build failed (bench.py falls back to the serial one)", file=sys.stderr)
+        except Exception as ex:
+            print("oracle/_ref/omp: %s" % ex, file=sys.stderr)
+        set_variant(False)
+    return rc
 
 
 if __name__ == "__main__":

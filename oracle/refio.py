@@ -133,21 +133,33 @@ def deck_header(system, datafile, skin=0.4, every=1, delay=1, check="yes", sort=
     return lines
 
 
-def run_reference(deck_lines, workdir=None, final=None, harness=True, timeout=3600, log=False):
-    """Run a deck through ref_harness (or lmp_ref); returns (stdout, path of the -final file or None)."""
+LMP_OMP = os.path.join(REF_DIR, "omp", "lmp_ref")     # the same sources + USER-OMP styles, built with -fopenmp
+
+
+def have_threaded_reference():
+    return os.path.exists(LMP_OMP) and os.path.exists(os.path.join(REF_DIR, "omp", "liblammps_ref.so"))
+
+
+def run_reference(deck_lines, workdir=None, final=None, harness=True, timeout=3600, log=False, threads=1):
+    """Run a deck through ref_harness (or lmp_ref); returns (stdout, path of the -final file or None).
+    threads > 1 (harness=False only): the threaded build with `-sf omp -pk omp threads` -- pair, bond, neighbor and
+    nve styles run in OpenMP threads, fix langevin and the USER-LE fixes stay serial (they have no /omp form)."""
     if not have_reference():
         raise RuntimeError("oracle/_ref is not built: run python oracle/build_ref.py")
     workdir = workdir or tempfile.mkdtemp(prefix="le_ref_")
     deck = os.path.join(workdir, "in.deck")
     with open(deck, "w") as f:
         f.write("\n".join(deck_lines) + "\n")
-    cmd = [HARNESS if harness else LMP, "-in", deck, "-log", "none" if not log else os.path.join(workdir, "log.lammps")]
+    omp = threads > 1 and not harness and have_threaded_reference()
+    cmd = [HARNESS if harness else (LMP_OMP if omp else LMP), "-in", deck, "-log", "none" if not log else os.path.join(workdir, "log.lammps")]
+    if omp:
+        cmd += ["-sf", "omp", "-pk", "omp", str(threads)]
     if not log:
         cmd += ["-screen", os.path.join(workdir, "screen.txt")]
     if final and harness:
         cmd += ["-final", final]
     env = dict(os.environ)
-    env["OMP_NUM_THREADS"] = "1"
+    env["OMP_NUM_THREADS"] = str(threads) if omp else "1"
     r = subprocess.run(cmd, cwd=workdir, capture_output=True, text=True, timeout=timeout, env=env)
     out = r.stdout
     scr = os.path.join(workdir, "screen.txt")
