@@ -212,6 +212,15 @@ int le_gen_saw_chains(int n, int nchains, double L, double step, double rmin, ui
 /* FENE-melt start: nchains*len beads on a snake path through a simple-cubic lattice at density rho */
 int le_gen_lattice_melt(int nchains, int len, double rho, double *L, double *x, int *image);
 
+/* ---- `velocity all create T seed ...` (host only) ------------------------------------------------ */
+/* Velocity::create (src/velocity.cpp:162-401) for all atoms of a 3-d system in tag order: Park-Miller draws
+ * (src/random_park.cpp) in the reference's order, 1/sqrt(mass) scaling, `mom yes` momentum zeroing, rescale to t_desired
+ * with 3N-3 degrees of freedom (compute temp).  loop: 0 = all, 1 = local (one rank), 2 = geom (x[n*3] needed: the generator
+ * is re-seeded from each atom's coordinates).  dist: 0 = uniform, 1 = gaussian.  `rot yes`, `sum yes`, `bias yes` and other
+ * temperature computes are not provided.  v[n*3] receives the result; feed it to le_set_velocities. */
+int le_host_velocity_create(int n, const int *type, const double *mass_per_type, const double *x, double t_desired, int seed,
+                            int dist, int mom, int loop, double *v);
+
 #ifdef __cplusplus
 }
 #endif

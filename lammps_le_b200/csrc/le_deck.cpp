@@ -13,6 +13,7 @@
 //   pair_coeff I J eps sigma [rc] | bond_style fene|harmonic|hybrid ... | bond_coeff N [style] ...
 //   fix ID all nve | nve/limit X | langevin T0 T1 damp seed | extrusion ... | ex_load ... | ex_unload ...
 //   unfix ID | timestep dt | reset_timestep N | thermo N | thermo_style ... | thermo_modify ... | run N
+//   velocity all create T seed [dist uniform|gaussian] [mom yes|no] [loop all|local|geom]
 //   write_data F | dump ID all custom N F cols | undump ID | log/echo/print (ignored or echoed)
 // Anything else stops with the reference's "Unknown command" error.  No compute happens here: every
 // number comes from libleb200.so (there is no CPU fallback).
@@ -395,6 +396,51 @@ void execute(Deck &d, const Words &w) {
   execute_cmd(d, w);
   if (verbose) std::fprintf(stderr, "[le_deck] %-16s %.3f s\n", w[0].c_str(), std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
 }
+// velocity all create T seed [dist uniform|gaussian] [mom yes|no] [rot no] [loop all|local|geom] [sum no] [units box]
+// (Velocity::create, src/velocity.cpp:162-401): computed on the host in the reference's draw order, then uploaded
+void velocity(Deck &d, const Words &w) {
+  if (w.size() < 5 || (w.size() - 5) % 2) die("Illegal velocity command");
+  if (d.natoms == 0 || !d.ctx) die("Velocity command before simulation box is defined");
+  if (w[1] != "all") die("Could not find velocity group ID (only group all is supported)");
+  if (w[2] != "create") die("Illegal velocity command (only velocity ... create is supported)");
+  const double t_desired = num(w[3]);
+  const int seed = inum(w[4]);
+  int dist = 0, mom = 1, loop = 0;
+  for (size_t k = 5; k + 1 < w.size(); k += 2) {
+    const std::string &key = w[k], &val = w[k + 1];
+    if (key == "dist") { if (val == "uniform") dist = 0; else if (val == "gaussian") dist = 1; else die("Illegal velocity command"); }
+    else if (key == "mom") { if (val == "yes") mom = 1; else if (val == "no") mom = 0; else die("Illegal velocity command"); }
+    else if (key == "rot") { if (val == "yes") die("velocity create rot yes is not supported"); else if (val != "no") die("Illegal velocity command"); }
+    else if (key == "loop") { if (val == "all") loop = 0; else if (val == "local") loop = 1; else if (val == "geom") loop = 2; else die("Illegal velocity command"); }
+    else if (key == "sum") { if (val == "yes") die("velocity create sum yes is not supported"); else if (val != "no") die("Illegal velocity command"); }
+    else if (key == "units") { if (val != "box" && val != "lattice") die("Illegal velocity command"); }
+    else die("Illegal velocity command");
+  }
+  if (seed <= 0) die("Illegal velocity create command");
+  const int n = d.natoms;
+  std::vector<int> type(n);
+  std::vector<double> x((size_t)n * 3), v((size_t)n * 3);
+  if (!d.uploaded) {
+    for (int k = 0; k < n; k++) {
+      const int t = d.tag[k] - 1;
+      if (t < 0 || t >= n) die("Atom IDs must be consecutive for velocity create loop all");
+      type[t] = d.type[k];
+      for (int q = 0; q < 3; q++) x[3 * (size_t)t + q] = d.x[3 * (size_t)k + q];
+    }
+  } else {
+    ck(d, le_download_x(d.ctx, x.data(), nullptr));
+    ck(d, le_download_types(d.ctx, type.data()));
+  }
+  if (le_host_velocity_create(n, type.data(), d.mass.data(), x.data(), t_desired, seed, dist, mom, loop, v.data())) die("Illegal velocity create command");
+  if (!d.uploaded) {
+    d.v.assign((size_t)n * 3, 0.0);
+    for (int k = 0; k < n; k++) for (int q = 0; q < 3; q++) d.v[3 * (size_t)k + q] = v[3 * (size_t)(d.tag[k] - 1) + q];
+    d.have_v = true;
+  } else {
+    ck(d, le_set_velocities(d.ctx, v.data()));
+  }
+}
+
 void execute_cmd(Deck &d, const Words &w) {
   const std::string &c = w[0];
   if (c == "units") { if (w.size() < 2 || w[1] != "lj") die("only units lj is supported"); }
@@ -472,6 +518,7 @@ void execute_cmd(Deck &d, const Words &w) {
       if (w.size() > 1 && d.dumps[k].id == w[1]) { if (d.dumps[k].fp) std::fclose(d.dumps[k].fp); d.dumps.erase(d.dumps.begin() + k); return; }
     die("Could not find undump ID");
   } else if (c == "dump_modify") {}
+  else if (c == "velocity") velocity(d, w);
   else if (c == "run") run(d, w);
   else if (c == "write_data") write_data(d, w);
   else die("Unknown command: " + c);

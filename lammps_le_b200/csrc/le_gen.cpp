@@ -124,3 +124,95 @@ extern "C" int le_gen_lattice_melt(int nchains, int len, double rho, double *L, 
     }
   return LE_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// `velocity all create T seed [dist uniform|gaussian] [mom yes|no] [loop all|local|geom]`
+//   reference: Velocity::create src/velocity.cpp:162-401, RanPark src/random_park.cpp:25-128,
+//   Velocity::zero_momentum src/velocity.cpp:741-767, ComputeTemp::compute_scalar src/compute_temp.cpp:83-110
+//   (dof = 3N - 3), Velocity::rescale src/velocity.cpp:716-735.  Host only: the deck front end and the Python
+//   mirror call it and upload the result.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct RanPark {                      // Park-Miller minimal standard generator, src/random_park.cpp:25-74
+  int seed, save;
+  double second;
+  explicit RanPark(int s) : seed(s), save(0), second(0.0) {}
+  double uniform() {
+    const int IA = 16807, IM = 2147483647, IQ = 127773, IR = 2836;
+    const int k = seed / IQ;
+    seed = IA * (seed - k * IQ) - IR * k;
+    if (seed < 0) seed += IM;
+    return (1.0 / IM) * seed;
+  }
+  double gaussian() {
+    double first;
+    if (!save) {
+      double v1, v2, rsq;
+      do {
+        v1 = 2.0 * uniform() - 1.0;
+        v2 = 2.0 * uniform() - 1.0;
+        rsq = v1 * v1 + v2 * v2;
+      } while (rsq >= 1.0 || rsq == 0.0);
+      const double fac = sqrt(-2.0 * log(rsq) / rsq);
+      second = v1 * fac;
+      first = v2 * fac;
+      save = 1;
+    } else {
+      first = second;
+      save = 0;
+    }
+    return first;
+  }
+  void reset(int ibase, const double *coord) {      // src/random_park.cpp:92-128: hash of the seed and the coordinates
+    unsigned int hash = 0;
+    const char *str = (const char *)&ibase;
+    for (size_t i = 0; i < sizeof(int); i++) { hash += str[i]; hash += (hash << 10); hash ^= (hash >> 6); }
+    str = (const char *)coord;
+    for (size_t i = 0; i < 3 * sizeof(double); i++) { hash += str[i]; hash += (hash << 10); hash ^= (hash >> 6); }
+    hash += (hash << 3); hash ^= (hash >> 11); hash += (hash << 15);
+    seed = hash & 0x7ffffff;
+    if (!seed) seed = 1;
+    for (int i = 0; i < 5; i++) uniform();
+    save = 0;
+  }
+};
+}  // namespace
+
+extern "C" int le_host_velocity_create(int n, const int *type, const double *mass_per_type, const double *x, double t_desired, int seed,
+                                       int dist, int mom, int loop, double *v) {
+  if (n < 1 || !type || !mass_per_type || !v || seed <= 0 || t_desired < 0.0 || dist < 0 || dist > 1 || loop < 0 || loop > 2) return LE_EINVAL;
+  if (loop == 2 && !x) return LE_EINVAL;
+  RanPark random(loop == 2 ? 1 : seed);
+  if (loop == 1) for (int i = 0; i < 100; i++) random.uniform();     // WARMUP of loop local (seed + me, me = 0)
+  for (int i = 0; i < n; i++) {
+    if (loop == 2) random.reset(seed, x + 3 * (size_t)i);
+    double vx, vy, vz;
+    if (dist == 0) { vx = random.uniform() - 0.5; vy = random.uniform() - 0.5; vz = random.uniform() - 0.5; }
+    else { vx = random.gaussian(); vy = random.gaussian(); vz = random.gaussian(); }
+    const double factor = 1.0 / sqrt(mass_per_type[type[i] - 1]);
+    v[3 * (size_t)i] = vx * factor; v[3 * (size_t)i + 1] = vy * factor; v[3 * (size_t)i + 2] = vz * factor;
+  }
+  if (mom) {   // Group::vcm: p[] summed in atom order, divided by the total mass; then subtracted from every atom
+    double p[3] = {0.0, 0.0, 0.0}, masstotal = 0.0;
+    for (int i = 0; i < n; i++) masstotal += mass_per_type[type[i] - 1];
+    for (int i = 0; i < n; i++) {
+      const double m = mass_per_type[type[i] - 1];
+      p[0] += v[3 * (size_t)i] * m; p[1] += v[3 * (size_t)i + 1] * m; p[2] += v[3 * (size_t)i + 2] * m;
+    }
+    double vcm[3] = {0.0, 0.0, 0.0};
+    if (masstotal > 0.0) for (int k = 0; k < 3; k++) vcm[k] = p[k] / masstotal;
+    for (int i = 0; i < n; i++) for (int k = 0; k < 3; k++) v[3 * (size_t)i + k] -= vcm[k];
+  }
+  // compute temp: t = sum m v^2 / dof, dof = 3N - 3 (extra_dof = dimension)
+  double t = 0.0;
+  for (int i = 0; i < n; i++)
+    t += (v[3 * (size_t)i] * v[3 * (size_t)i] + v[3 * (size_t)i + 1] * v[3 * (size_t)i + 1] + v[3 * (size_t)i + 2] * v[3 * (size_t)i + 2]) *
+         mass_per_type[type[i] - 1];
+  const double dof = 3.0 * n - 3.0;
+  if (dof <= 0.0) return LE_EINVAL;
+  t *= 1.0 / dof;
+  if (t == 0.0) return LE_EINVAL;                                  // "Attempting to rescale a 0.0 temperature"
+  const double factor = sqrt(t_desired / t);
+  for (size_t k = 0; k < 3 * (size_t)n; k++) v[k] *= factor;
+  return LE_OK;
+}

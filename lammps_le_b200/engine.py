@@ -82,6 +82,7 @@ def load_library():
         "le_local_capacity": [P], "le_download_owned": [P, pi, pi, pd, pi, pd], "le_upload_owned": [P, I, pi, pd, pi, pd],
         "le_dd_init": [P, I, I, D], "le_dd_get_handle": [P, C.c_void_p], "le_dd_connect": [P, C.c_void_p],
         "le_get_thermo_sums": [P, I, pd], "le_get_force_sums": [P, pd],
+        "le_host_velocity_create": [I, pi, pd, pd, D, I, I, I, I, pd],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
@@ -401,6 +402,22 @@ def unpack_image(im):
 def pack_image(ixyz):
     a = np.asarray(ixyz, dtype=np.int64)
     return (((a[..., 0] + 512) & 1023) | (((a[..., 1] + 512) & 1023) << 10) | (((a[..., 2] + 512) & 1023) << 20)).astype(np.int32)
+
+
+def velocity_create(types, masses, t_desired, seed, dist="uniform", mom=True, loop="all", x=None):
+    """`velocity all create T seed dist ... mom ... loop ...` (Velocity::create, src/velocity.cpp:162-401) on the host:
+    returns v[n,3] in tag order for Engine.set_velocities."""
+    lib = load_library()
+    types = np.ascontiguousarray(types, dtype=np.int32)
+    masses = np.ascontiguousarray(masses, dtype=np.float64)
+    n = len(types)
+    v = np.zeros((n, 3))
+    xx = np.ascontiguousarray(x, dtype=np.float64) if x is not None else None
+    rc = lib.le_host_velocity_create(n, _pi(types), _pd(masses), _pd(xx) if xx is not None else None, float(t_desired), int(seed),
+                                     {"uniform": 0, "gaussian": 1}[dist], 1 if mom else 0, {"all": 0, "local": 1, "geom": 2}[loop], _pd(v))
+    if rc:
+        raise LeError(rc, "velocity create: illegal arguments")
+    return v
 
 
 def gen_saw_chains(n, nchains, L, step=0.97, rmin=0.9, seed=12345):

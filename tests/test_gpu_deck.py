@@ -124,3 +124,19 @@ def test_deck_dump_custom(tmp_path):
     assert first[0] == 1 and np.allclose(first[2:], z["x"][0], atol=1e-5)
     th = parse_thermo(r.stdout)
     assert th[0, 0] == 0 and th[-1, 0] == 50
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(reason="`velocity all create` in le_deck was wired after the last GPU call of round 1 (the host function is checked "
+                          "against the reference on the CPU, tests/test_velocity_create.py): first GPU run pending", strict=False)
+def test_deck_velocity_create(tmp_path):
+    """velocity all create 1.0 seed before `run 0`: the temperature of step 0 is the requested one, as in the reference"""
+    z = np.load(os.path.join(GOLD, "bench_chain.npz"))
+    write_data_chain(tmp_path / "data.chain", z)
+    deck = IN_CHAIN.replace("run\t\t100", "velocity all create 1.25 4928459 dist gaussian\nrun 0")
+    (tmp_path / "in.v").write_text(deck)
+    exe = os.path.join(ROOT, "lammps_le_b200", "le_deck")
+    r = subprocess.run([exe, "-in", "in.v"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    th = parse_thermo(r.stdout)
+    assert abs(th[0, 1] - 1.25) < 1e-6        # velocities are stored in fp32
