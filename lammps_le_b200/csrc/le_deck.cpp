@@ -12,7 +12,8 @@
 //   neighbor S bin | neigh_modify every|delay|check ... | pair_style lj/cut RC | pair_modify shift yes|no
 //   pair_coeff I J eps sigma [rc] | bond_style fene|harmonic|hybrid ... | bond_coeff N [style] ...
 //   fix ID all nve | nve/limit X | langevin T0 T1 damp seed | extrusion ... | ex_load ... | ex_unload ...
-//   unfix ID | timestep dt | reset_timestep N | thermo N | thermo_style ... | thermo_modify ... | run N
+//   unfix ID | timestep dt | reset_timestep N | thermo N | thermo_modify ... | run N
+//   thermo_style one | custom step elapsed dt time atoms temp press pe ke etotal evdwl epair ebond emol vol density lx ly lz bonds
 //   velocity all create T seed [dist uniform|gaussian] [mom yes|no] [loop all|local|geom]
 //   write_data F | dump ID all custom N F cols | undump ID | log/echo/print (ignored or echoed)
 // Anything else stops with the reference's "Unknown command" error.  No compute happens here: every
@@ -57,6 +58,7 @@ struct Deck {
   std::map<std::string, std::string> fix_style;        // fix ID -> style
   struct Dump { std::string id, file; int every; std::vector<std::string> cols; FILE *fp; };
   std::vector<Dump> dumps;                             // dump ID all custom N file cols...
+  std::vector<int> thermo_cols;                        // thermo_style custom: indices into THERMO_FIELDS (empty = style one)
   bool echo = false;
 };
 
@@ -218,18 +220,72 @@ void init(Deck &d) {
   }
 }
 
+// thermo_style one | custom kw ...: the keywords of src/thermo.cpp:700-860 this path can fill, with the reference's
+// column titles; energies are per atom (units lj: thermo_modify norm yes)
+struct ThermoField { const char *key, *title; bool integer; };
+const ThermoField THERMO_FIELDS[] = {
+    {"step", "Step", true}, {"elapsed", "Elapsed", true}, {"dt", "Dt", false}, {"time", "Time", false}, {"atoms", "Atoms", true},
+    {"temp", "Temp", false}, {"press", "Press", false}, {"pe", "PotEng", false}, {"ke", "KinEng", false}, {"etotal", "TotEng", false},
+    {"evdwl", "E_vdwl", false}, {"epair", "E_pair", false}, {"ebond", "E_bond", false}, {"emol", "E_mol", false},
+    {"vol", "Volume", false}, {"density", "Density", false}, {"lx", "Lx", false}, {"ly", "Ly", false}, {"lz", "Lz", false},
+    {"bonds", "Bonds", true}};
+
+void thermo_style(Deck &d, const Words &w) {
+  if (w.size() < 2) die("Illegal thermo_style command");
+  d.thermo_cols.clear();
+  if (w[1] == "one") return;                                // the default line: step temp epair emol etotal press
+  if (w[1] != "custom") die("Illegal thermo_style command (only one | custom)");
+  if (w.size() < 3) die("Illegal thermo style custom command");
+  for (size_t k = 2; k < w.size(); k++) {
+    int found = -1;
+    for (size_t q = 0; q < sizeof(THERMO_FIELDS) / sizeof(THERMO_FIELDS[0]); q++) if (w[k] == THERMO_FIELDS[q].key) found = (int)q;
+    if (found < 0) die("Unknown keyword in thermo_style custom command: " + w[k]);
+    d.thermo_cols.push_back(found);
+  }
+}
+
 void print_thermo(Deck &d, int first) {
   const int n = le_thermo_count(d.ctx);
-  std::printf("Step Temp E_pair E_mol TotEng Press \n");
-  long long last = -1;
+  std::vector<int> cols = d.thermo_cols;
+  if (cols.empty()) cols = {0, 5, 11, 13, 9, 6};            // step temp epair emol etotal press
+  for (int q : cols) std::printf("%s ", THERMO_FIELDS[q].title);
+  std::printf("\n");
+  double vol = 1.0, mtot = 0.0;
+  for (int k = 0; k < 3; k++) vol *= d.hi[k] - d.lo[k];
+  for (int k = 0; k < d.natoms; k++) mtot += d.mass[d.type[k] - 1];
+  long long last = -1, step0 = -1;
   for (int k = first; k < n; k++) {
     le_thermo t; le_get_thermo(d.ctx, k, &t);
+    if (step0 < 0) step0 = t.step;
     // segment boundaries of a run split by dumps are not thermo steps of the script
     const bool edge = k == first || k == n - 1;
     if (!edge && !(d.thermo_every > 0 && t.step % d.thermo_every == 0)) continue;
     if (t.step == last) continue;
     last = t.step;
-    std::printf("%8lld %12.8g %12.8g %12.8g %12.8g %12.8g \n", (long long)t.step, t.temp, t.epair, t.emol, t.etotal, t.press);
+    for (int q : cols) {
+      long long iv = 0; double fv = 0.0;
+      switch (q) {
+        case 0: iv = t.step; break;
+        case 1: iv = t.step - step0; break;
+        case 2: fv = d.dt; break;
+        case 3: fv = (double)t.step * d.dt; break;
+        case 4: iv = d.natoms; break;
+        case 5: fv = t.temp; break;
+        case 6: fv = t.press; break;
+        case 7: fv = t.epair + t.emol; break;
+        case 8: fv = t.ke / d.natoms; break;
+        case 9: fv = t.etotal; break;
+        case 10: case 11: fv = t.epair; break;
+        case 12: case 13: fv = t.emol; break;
+        case 14: fv = vol; break;
+        case 15: fv = mtot / vol; break;
+        case 16: case 17: case 18: fv = d.hi[q - 16] - d.lo[q - 16]; break;
+        case 19: iv = t.nbonds; break;
+      }
+      if (THERMO_FIELDS[q].integer) std::printf("%8lld ", iv);
+      else std::printf("%12.8g ", fv);
+    }
+    std::printf("\n");
   }
 }
 
@@ -445,7 +501,8 @@ void execute_cmd(Deck &d, const Words &w) {
   const std::string &c = w[0];
   if (c == "units") { if (w.size() < 2 || w[1] != "lj") die("only units lj is supported"); }
   else if (c == "atom_style") { if (w.size() < 2 || w[1] != "bond") die("only atom_style bond is supported"); }
-  else if (c == "atom_modify" || c == "comm_modify" || c == "log" || c == "echo" || c == "thermo_style" || c == "thermo_modify" || c == "processors") {}
+  else if (c == "atom_modify" || c == "comm_modify" || c == "log" || c == "echo" || c == "thermo_modify" || c == "processors") {}
+  else if (c == "thermo_style") thermo_style(d, w);
   else if (c == "print") { for (size_t k = 1; k < w.size(); k++) std::printf("%s%s", w[k].c_str(), k + 1 < w.size() ? " " : "\n"); }
   else if (c == "newton") {
     if (w.size() == 2) d.newton_pair = d.newton_bond = (w[1] == "on");

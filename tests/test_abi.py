@@ -90,3 +90,20 @@ def test_le_deck_front_end_rejects_unknown_commands(tmp_path):
     (tmp_path / "in.units").write_text("units real\n")
     r = subprocess.run([exe, "-in", "in.units"], cwd=tmp_path, capture_output=True, text=True, timeout=60)
     assert r.returncode == 1 and "only units lj" in r.stderr
+
+
+def test_le_deck_front_end_checks_thermo_style_and_velocity_before_touching_the_device(tmp_path):
+    """thermo_style custom keywords and the velocity command are validated with the reference's error texts"""
+    import subprocess
+    exe = os.path.join(ROOT, "lammps_le_b200", "le_deck")
+    cases = {
+        "units lj\nthermo_style custom step temp nonsense\n": "Unknown keyword in thermo_style custom command: nonsense",
+        "units lj\nthermo_style multi\n": "Illegal thermo_style command",
+        "units lj\nthermo_style custom step temp pe ke etotal bonds vol\nvelocity all create 1.0 12345\n": "Velocity command before simulation box is defined",
+        "units lj\nvelocity all create 1.0\n": "Illegal velocity command",
+    }
+    for k, (deck, msg) in enumerate(cases.items()):
+        f = tmp_path / ("in.%d" % k)
+        f.write_text(deck)
+        r = subprocess.run([exe, "-in", f.name], cwd=tmp_path, capture_output=True, text=True, timeout=60)
+        assert r.returncode == 1 and msg in r.stderr, (deck, r.stderr)
