@@ -221,6 +221,14 @@ int le_gen_lattice_melt(int nchains, int len, double rho, double *L, double *x, 
 int le_host_velocity_create(int n, const int *type, const double *mass_per_type, const double *x, double t_desired, int seed,
                             int dist, int mom, int loop, double *v);
 
+/* ---- `compute property/local batom1 batom2 btype` (host only) ------------------------------------ */
+/* ComputePropertyLocal::count_bonds / pack (src/compute_property_local.cpp:463-493): the bonds in the order the
+ * reference lists them -- atoms in tag order, their bond slots in slot order, with newton_bond off only from the end with
+ * the smaller tag, deleted bonds (type 0) skipped.  rows[3*k..] = batom1, batom2, btype; returns the number of rows
+ * (rows may be NULL to count). */
+int64_t le_host_property_local_bonds(int n, int bpa, const int *num_bond, const int *bond_type, const int *bond_atom,
+                                     int newton_bond, int *rows);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,7 @@
 //   thermo_style one | custom step elapsed dt time atoms temp press pe ke etotal evdwl epair ebond emol vol density lx ly lz bonds
 //   velocity all create T seed [dist uniform|gaussian] [mom yes|no] [loop all|local|geom]
 //   write_data F | dump ID all custom N F cols | undump ID | log/echo/print (ignored or echoed)
+//   compute ID all property/local batom1 batom2 btype | dump ID all local N F [index] c_ID[k] ... (the loops)
 // Anything else stops with the reference's "Unknown command" error.  No compute happens here: every
 // number comes from libleb200.so (there is no CPU fallback).
 #include "../../include/le_b200.h"
@@ -56,7 +57,8 @@ struct Deck {
   double dt = 0.005;
   int thermo_every = 0;
   std::map<std::string, std::string> fix_style;        // fix ID -> style
-  struct Dump { std::string id, file; int every; std::vector<std::string> cols; FILE *fp; };
+  struct Dump { std::string id, file; int every; std::vector<std::string> cols; FILE *fp; bool local = false; std::vector<int> lcols; };   // lcols: 0 = index, k = k-th attribute of the compute
+  std::map<std::string, std::vector<std::string>> prop_local;   // compute ID all property/local batom1|batom2|btype ...
   std::vector<Dump> dumps;                             // dump ID all custom N file cols...
   std::vector<int> thermo_cols;                        // thermo_style custom: indices into THERMO_FIELDS (empty = style one)
   bool echo = false;
@@ -301,9 +303,34 @@ void write_dumps(Deck &d, long long step) {
   ck(d, le_download_x(d.ctx, x.data(), im.data()));
   ck(d, le_download_v(d.ctx, v.data()));
   ck(d, le_download_types(d.ctx, ty.data()));
+  std::vector<int> rows; long long nrows = -1;            // bonds as compute property/local lists them (fetched once per step)
   for (auto &dp : d.dumps) {
     if (step % dp.every) continue;
     if (!dp.fp) { dp.fp = std::fopen(dp.file.c_str(), "w"); if (!dp.fp) die("Cannot open dump file " + dp.file); }
+    if (dp.local) {
+      // dump local (src/dump_local.cpp:254-282, :380-395): one entry per bond, values with "%g " / the index with "%d "
+      if (nrows < 0) {
+        std::vector<int> nb(n), bt((size_t)n * d.bpa), ba((size_t)n * d.bpa);
+        ck(d, le_download_topology(d.ctx, nb.data(), bt.data(), ba.data(), nullptr, nullptr));
+        nrows = le_host_property_local_bonds(n, d.bpa, nb.data(), bt.data(), ba.data(), d.newton_bond, nullptr);
+        rows.resize((size_t)std::max(nrows, 1LL) * 3);
+        le_host_property_local_bonds(n, d.bpa, nb.data(), bt.data(), ba.data(), d.newton_bond, rows.data());
+      }
+      std::fprintf(dp.fp, "ITEM: TIMESTEP\n%lld\nITEM: NUMBER OF ENTRIES\n%lld\nITEM: BOX BOUNDS pp pp pp\n", step, nrows);
+      for (int q = 0; q < 3; q++) std::fprintf(dp.fp, "%-1.16e %-1.16e\n", d.lo[q], d.hi[q]);
+      std::fprintf(dp.fp, "ITEM: ENTRIES ");
+      for (auto &c : dp.cols) std::fprintf(dp.fp, "%s ", c.c_str());
+      std::fprintf(dp.fp, "\n");
+      for (long long k = 0; k < nrows; k++) {
+        for (int a : dp.lcols) {
+          if (a == 0) std::fprintf(dp.fp, "%lld ", k + 1);
+          else std::fprintf(dp.fp, "%g ", (double)rows[3 * k + (a - 1)]);
+        }
+        std::fprintf(dp.fp, "\n");
+      }
+      std::fflush(dp.fp);
+      continue;
+    }
     std::fprintf(dp.fp, "ITEM: TIMESTEP\n%lld\nITEM: NUMBER OF ATOMS\n%d\nITEM: BOX BOUNDS pp pp pp\n", step, n);
     for (int q = 0; q < 3; q++) std::fprintf(dp.fp, "%-1.16e %-1.16e\n", d.lo[q], d.hi[q]);
     std::fprintf(dp.fp, "ITEM: ATOMS");
@@ -559,9 +586,31 @@ void execute_cmd(Deck &d, const Words &w) {
   else if (c == "reset_timestep") { if (w.size() != 2 || !d.ctx) die("Illegal reset_timestep command"); ck(d, le_reset_timestep(d.ctx, std::strtoll(w[1].c_str(), nullptr, 10))); }
   else if (c == "thermo") { if (w.size() != 2) die("Illegal thermo command"); d.thermo_every = inum(w[1]); }
   else if (c == "dump") {
-    if (w.size() < 7 || w[2] != "all" || w[3] != "custom") die("Illegal dump command (only: dump ID all custom N file columns...)");
+    if (w.size() < 7 || w[2] != "all" || (w[3] != "custom" && w[3] != "local")) die("Illegal dump command (only: dump ID all custom|local N file columns...)");
     Deck::Dump dp; dp.id = w[1]; dp.every = inum(w[4]); dp.file = w[5]; dp.fp = nullptr;
     if (dp.every <= 0) die("Invalid dump frequency");
+    if (w[3] == "local") {
+      // dump ID all local N file index c_ID[k] ...: columns of ONE compute property/local (the bonds: batom1 batom2 btype)
+      dp.local = true;
+      std::string cid;
+      for (size_t k = 6; k < w.size(); k++) {
+        if (w[k] == "index") { dp.lcols.push_back(0); dp.cols.push_back(w[k]); continue; }
+        const size_t lb = w[k].find('['), rb = w[k].find(']');
+        if (w[k].compare(0, 2, "c_") || lb == std::string::npos || rb == std::string::npos || rb < lb) die("Invalid attribute in dump local command");
+        const std::string id = w[k].substr(2, lb - 2);
+        if (!d.prop_local.count(id)) die("Could not find dump local compute ID");
+        if (!cid.empty() && cid != id) die("Dump local attributes contain no compute or fix");   // one compute per dump here
+        cid = id;
+        const int col = inum(w[k].substr(lb + 1, rb - lb - 1));
+        if (col < 1 || col > (int)d.prop_local[id].size()) die("Dump local compute vector is accessed out-of-range");
+        const std::string &attr = d.prop_local[id][col - 1];
+        dp.lcols.push_back(attr == "batom1" ? 1 : attr == "batom2" ? 2 : 3);
+        dp.cols.push_back(w[k]);
+      }
+      if (cid.empty()) die("Dump local attributes contain no compute or fix");
+      d.dumps.push_back(dp);
+      return;
+    }
     for (size_t k = 6; k < w.size(); k++) {
       static const char *ok[] = {"id", "type", "mol", "x", "y", "z", "xu", "yu", "zu", "ix", "iy", "iz", "vx", "vy", "vz"};
       bool known = false;
@@ -575,6 +624,12 @@ void execute_cmd(Deck &d, const Words &w) {
       if (w.size() > 1 && d.dumps[k].id == w[1]) { if (d.dumps[k].fp) std::fclose(d.dumps[k].fp); d.dumps.erase(d.dumps.begin() + k); return; }
     die("Could not find undump ID");
   } else if (c == "dump_modify") {}
+  else if (c == "compute") {
+    if (w.size() < 5 || w[2] != "all" || w[3] != "property/local") die("Illegal compute command (only: compute ID all property/local batom1 batom2 btype)");
+    std::vector<std::string> attrs(w.begin() + 4, w.end());
+    for (auto &a : attrs) if (a != "batom1" && a != "batom2" && a != "btype") die("Invalid keyword in compute property/local command");
+    d.prop_local[w[1]] = attrs;
+  } else if (c == "uncompute") { if (w.size() != 2 || !d.prop_local.erase(w[1])) die("Could not find compute ID to delete"); }
   else if (c == "velocity") velocity(d, w);
   else if (c == "run") run(d, w);
   else if (c == "write_data") write_data(d, w);

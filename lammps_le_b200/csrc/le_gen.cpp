@@ -216,3 +216,20 @@ extern "C" int le_host_velocity_create(int n, const int *type, const double *mas
   for (size_t k = 0; k < 3 * (size_t)n; k++) v[k] *= factor;
   return LE_OK;
 }
+
+// compute property/local batom1 batom2 btype (src/compute_property_local.cpp:463-493, pack_batom1/2, pack_btype)
+extern "C" int64_t le_host_property_local_bonds(int n, int bpa, const int *num_bond, const int *bond_type, const int *bond_atom,
+                                                int newton_bond, int *rows) {
+  if (n < 0 || bpa < 1 || !num_bond || !bond_type || !bond_atom) return -1;
+  int64_t m = 0;
+  for (int a1 = 0; a1 < n; a1++)
+    for (int i = 0; i < num_bond[a1]; i++) {
+      const int t2 = bond_atom[(size_t)a1 * bpa + i];
+      if (t2 < 1 || t2 > n) continue;                       // partner unknown to this proc
+      if (newton_bond == 0 && a1 + 1 > t2) continue;
+      if (bond_type[(size_t)a1 * bpa + i] == 0) continue;
+      if (rows) { rows[3 * m] = a1 + 1; rows[3 * m + 1] = t2; rows[3 * m + 2] = bond_type[(size_t)a1 * bpa + i]; }
+      m++;
+    }
+  return m;
+}

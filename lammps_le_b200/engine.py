@@ -93,6 +93,8 @@ def load_library():
     lib.le_last_error.argtypes = [P]
     lib.le_last_error.restype = C.c_char_p
     lib.le_version.restype = C.c_char_p
+    lib.le_host_property_local_bonds.argtypes = [I, I, pi, pi, pi, I, pi]
+    lib.le_host_property_local_bonds.restype = I64
     lib.le_step_kernel_name.argtypes = [P]
     lib.le_step_kernel_name.restype = C.c_char_p
     lib.le_timestep.argtypes = [P]
@@ -402,6 +404,19 @@ def unpack_image(im):
 def pack_image(ixyz):
     a = np.asarray(ixyz, dtype=np.int64)
     return (((a[..., 0] + 512) & 1023) | (((a[..., 1] + 512) & 1023) << 10) | (((a[..., 2] + 512) & 1023) << 20)).astype(np.int32)
+
+
+def property_local_bonds(num_bond, bond_type, bond_atom, newton_bond=0):
+    """rows (batom1, batom2, btype) of `compute property/local batom1 batom2 btype` in the reference's order"""
+    lib = load_library()
+    nb = np.ascontiguousarray(num_bond, dtype=np.int32)
+    bt = np.ascontiguousarray(bond_type, dtype=np.int32)
+    ba = np.ascontiguousarray(bond_atom, dtype=np.int32)
+    n, bpa = bt.shape
+    m = lib.le_host_property_local_bonds(n, bpa, _pi(nb), _pi(bt), _pi(ba), int(newton_bond), None)
+    rows = np.zeros((max(m, 1), 3), dtype=np.int32)
+    lib.le_host_property_local_bonds(n, bpa, _pi(nb), _pi(bt), _pi(ba), int(newton_bond), _pi(rows))
+    return rows[:m]
 
 
 def velocity_create(types, masses, t_desired, seed, dist="uniform", mom=True, loop="all", x=None):

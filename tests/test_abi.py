@@ -101,6 +101,8 @@ def test_le_deck_front_end_checks_thermo_style_and_velocity_before_touching_the_
         "units lj\nthermo_style multi\n": "Illegal thermo_style command",
         "units lj\nthermo_style custom step temp pe ke etotal bonds vol\nvelocity all create 1.0 12345\n": "Velocity command before simulation box is defined",
         "units lj\nvelocity all create 1.0\n": "Illegal velocity command",
+        "units lj\ncompute b all property/local batom1 foo\n": "Invalid keyword in compute property/local command",
+        "units lj\ndump d all local 10 f.dump c_b[1]\n": "Could not find dump local compute ID",
     }
     for k, (deck, msg) in enumerate(cases.items()):
         f = tmp_path / ("in.%d" % k)
