@@ -101,6 +101,8 @@ struct Ctrl {
   long long epoch;            // force evaluations so far: the value the per-step peer flags carry
   long long rebuild_epoch;    // rebuilds so far (all GPUs rebuild on the same steps)
   long long le_epoch;         // USER-LE exchange rounds so far
+  unsigned tile_next;         // k_step2d: tiles handed out beyond the first wave (reset by the block that finishes last)
+  unsigned pad2;
 };
 
 enum {

@@ -1003,7 +1003,8 @@ extern "C" int le_set_velocities(le_ctx *c, const double *v) {
 // ---- which plain step kernel (no energy / virial tally) -----------------------------------------------
 // LE_STEP_VARIANT (read at every le_run, so one process can compare variants): 0 = k_step; bit 0 = k_step2 (le_step2.cuh),
 // bit 1 = 128 threads per block instead of 256, bit 5 = persistent grid (k_step2p), bit 9 (with bits 0 and 5) = the step
-// kernel's last block takes the reneighbor decision of the next timestep inside the steady-state graph, bit 4 = k_step2
+// kernel's last block takes the reneighbor decision of the next timestep inside the steady-state graph, bit 10 (with bits
+// 0 and 5) = dynamic tile fetch (k_step2d), bit 4 = k_step2
 // also on several GPUs.  k_step2 needs the uniform lj/cut case and special weights in {0, 1}; otherwise k_step runs
 // whatever the switch says.
 #ifndef LE_STEP_VARIANT_DEFAULT
@@ -1026,6 +1027,8 @@ static StepKernel plain_step_kernel(const le_ctx *c, int variant) {
   const bool dd = c->nranks > 1;
   if ((variant & 1) && step2_eligible(c) && (!dd || (variant & 16))) {
     const bool small = variant & 2, pers = variant & 32;
+    if (!dd && pers && (variant & 1024))   // dynamic tile fetch (256-thread form)
+      return c->P.pair32 ? StepKernel{(step_fn_t)k_step2d<256, 1>, 256, "(k_step2d<256,p32>)", 4} : StepKernel{(step_fn_t)k_step2d<256>, 256, "(k_step2d<256>)", 4};
     if (c->P.pair32) {   // fp32 pair terms: 256-thread forms only
       if (dd) return pers ? StepKernel{(step_fn_t)k_step2p<1, 256, 0, 1>, 256, "(k_step2p<1,256,p32>)", 4} : StepKernel{(step_fn_t)k_step2<1, 256, 1>, 256, "(k_step2<1,256,p32>)", 0};
       if (pers && (variant & 512)) return StepKernel{(step_fn_t)k_step2p<0, 256, 1, 1>, 256, "(k_step2p<0,256,fuse,p32>)", 4};
@@ -1153,7 +1156,7 @@ static int graph_add_unit(le_ctx *c, cudaGraph_t g, cudaGraphNode_t *tail, int a
 // the reneighbor decision fused into the step kernel (LE_STEP_VARIANT bit 9): only the persistent single-GPU kernel has
 // the last-block epilogue
 static bool fused_decide(const le_ctx *c, int variant) {
-  return (variant & 512) && (variant & 1) && (variant & 32) && c->nranks == 1 && step2_eligible(c);
+  return (variant & 512) && !(variant & 1024) && (variant & 1) && (variant & 32) && c->nranks == 1 && step2_eligible(c);
 }
 
 static int ensure_graphs(le_ctx *c) {

@@ -16,7 +16,7 @@ import numpy as np
 from lammps_le_b200 import systems
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
-variants = [int(v) for v in sys.argv[2:]] or [0, 1, 3, 33, 35, 545]
+variants = [int(v) for v in sys.argv[2:]] or [0, 1, 3, 33, 35, 545, 1057]
 if variants[0] != 0:
     variants = [0] + variants
 os.makedirs("gpurun_out", exist_ok=True)
