@@ -16,7 +16,8 @@
 //     screens, one survivor queue per row group, carry-based image flags, wide multiplies in Philox, no switches:
 //     758 instructions.
 // The persistent form k_step2p (one wave of blocks, grid stride) is the default: 44.5 us against k_step's 54.5 us at
-// 10^6 beads.  Measured and removed again (profiles/r01_step_variants.txt; git history has the code): L2 / L1 prefetch
+// 10^6 beads.  Written after the last GPU minute of round 1 and still off: the fused reneighbor decision (FUSE), fp32
+// pair terms (P32), dynamic tile fetch (k_step2d).  Measured and removed again (profiles/r01_step_variants.txt; git history has the code): L2 / L1 prefetch
 // of a thread's next atom, software pipelining with the next atom's head in registers, the thermostat force computed
 // under the gathers + two FENE bonds evaluated side by side, int -> double conversion on the fp64 pipe, a 32-byte
 // per-atom head record instead of eight arrays -- none of them faster than this form.
