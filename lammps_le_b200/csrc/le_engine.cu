@@ -1115,7 +1115,7 @@ static int graph_add_unit(le_ctx *c, cudaGraph_t g, cudaGraphNode_t *tail, int a
   if (with_decide) {
     int adv = advance, use = 1;
     void *dargs[] = {&d, &handle, &adv, &use};
-    memset(&kp, 0, sizeof kp);
+    kp = cudaKernelNodeParams{};
     kp.func = (void *)k_decide; kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.kernelParams = dargs;
     cudaGraphNode_t nd;
     CKG(cudaGraphAddKernelNode(&nd, g, *tail ? tail : nullptr, *tail ? 1 : 0, &kp));
@@ -1142,7 +1142,7 @@ static int graph_add_unit(le_ctx *c, cudaGraph_t g, cudaGraphNode_t *tail, int a
     a.rdp1 = step_rd + 1;
     if (next_handle) { a.fuse = 1; a.handle = next_handle; }
     void *sargs[] = {&d, &a};
-    memset(&kp, 0, sizeof kp);
+    kp = cudaKernelNodeParams{};
     const StepKernel sk = plain_step_kernel(c, c->gkey_variant);
     kp.func = (void *)sk.fn; kp.gridDim = dim3(step_grid(c, sk));
     kp.blockDim = dim3(sk.threads); kp.kernelParams = sargs;
