@@ -244,3 +244,36 @@ def test_fp32_pair_math_error_budget(force_rec):
     err = np.sqrt(((f - c["f"]) ** 2).sum(1)) / np.maximum(mag, np.sqrt((mag ** 2).mean()))
     assert inn.sum() > 100
     assert 1e-7 < err.max() <= 1e-5, "fp32 pair path: max per-atom relative force error %.3g" % err.max()
+
+
+def test_lists_and_forces_match_live_reference_on_a_dense_melt():
+    """the restatement against the compiled reference on a dense FENE melt (rho* = 0.8442, ten half neighbors per atom,
+    many pairs stored through periodic ghosts): special lists, bond list, half list sets, forces, energies, virials"""
+    if not refio.have_reference():
+        pytest.skip("oracle/_ref not built")
+    from lammps_le_b200 import systems
+    from oracle.make_golden import force_case
+    m = systems.fene_melt(8, 60, rho=0.8442)
+    rec = force_case(m, velocities=True)
+    n = len(rec["x"])
+    L = rec["boxhi"] - rec["boxlo"]
+    assert R.special_build(rec["num_bond"], rec["bond_atom"], special_lj=(0.0, 1.0, 1.0)) == R.special_tiers(rec["nspecial"], rec["special"])
+    bl = R.bond_list(rec["x"], L, rec["num_bond"], rec["bond_type"], rec["bond_atom"])
+    assert bl.shape == rec["bondlist"].shape and (bl == rec["bondlist"]).all()
+    rows = R.half_neighbor_list(rec["x"], rec["boxlo"], rec["boxhi"], 1.12246 + 0.4, rec["nspecial"], rec["special"])
+    ref = H.neigh_sets(rec["neigh_offsets"], rec["neigh_entries"])
+    assert sum(len(r) for r in rows) > 4 * n
+    bad = [t + 1 for t in range(n) if frozenset(rows[t]) != ref[t]]
+    assert not bad, "half-list sets differ for tags %s" % bad[:10]
+    pi = np.array([t for t in range(n) for _ in rows[t]], dtype=int)
+    pj = np.array([(v & R.NEIGHMASK) - 1 for t in range(n) for v in rows[t]], dtype=int)
+    fp, evdwl, vp = R.pair_lj_cut(rec["x"], L, pi, pj, np.zeros(len(pi), int), R.lj_coeffs(1.0, 1.0, 1.12246, True))
+    b1, b2, bt = R.unique_bonds(rec["num_bond"], rec["bond_type"], rec["bond_atom"])
+    fb, eb, vb, _ = R.bond_forces(rec["x"], L, b1, b2, bt, {1: ("fene", (30.0, 1.5, 1.0, 1.0))})
+    fr = rec["f"]
+    mag = np.sqrt((fr ** 2).sum(1))
+    err = np.sqrt(((fp + fb - fr) ** 2).sum(1)) / np.maximum(mag, np.sqrt((mag ** 2).mean()))
+    assert err.max() < 1e-11
+    assert abs(evdwl - rec["energy"][0]) <= 1e-10 * abs(rec["energy"][0]) and abs(eb - rec["energy"][1]) <= 1e-10 * abs(rec["energy"][1])
+    assert np.abs(vp - rec["virial_pair"]).max() <= 1e-9 * np.abs(rec["virial_pair"]).max()
+    assert np.abs(vb - rec["virial_bond"]).max() <= 1e-9 * np.abs(rec["virial_bond"]).max()
