@@ -164,9 +164,10 @@ def reference_threads():
         cores = len(os.sched_getaffinity(0))
     except Exception:
         cores = os.cpu_count() or 1
-    # beyond ~16 threads the threaded part (pair, bond, neighbor, nve) no longer shrinks the step: fix langevin and the
-    # USER-LE fixes are serial (measured here: 1.5x at 4 and at 8 threads)
-    return max(1, min(cores, 16))
+    # one thread per physical core (logical CPUs / 2), at most 16: beyond that the threaded part (pair, bond, neighbor,
+    # nve) no longer shrinks the step -- fix langevin and the USER-LE fixes are serial.  Measured in the build container
+    # (8 logical CPUs) at 1M beads: 2.2 M atom-steps/s with 1 thread, 3.5 M with 4, 2.9 M with 8.
+    return max(1, min(cores // 2, 16))
 
 
 def run_ours(args):
