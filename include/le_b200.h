@@ -139,7 +139,7 @@ int le_force_rebuild(le_ctx *c);                            /* Neighbor::build(1
 /* le_run with direct launches and an event before every launch; *kstep_us = average duration of the plain step
  * kernel (launch to next launch on the stream), for live roofline measurements */
 int le_run_timed(le_ctx *c, int64_t nsteps, double *kstep_us);
-/* name of the plain step kernel le_run launches in the current configuration (for reports; e.g. "k_step2p<0,256,0,0>") */
+/* name of the plain step kernel le_run launches in the current configuration (for reports; e.g. "k_step3<0,0,1>") */
 const char *le_step_kernel_name(le_ctx *c);
 /* run one USER-LE fix's post_integrate on the current state, regardless of the step gate */
 int le_run_le_event(le_ctx *c, int which);
@@ -149,6 +149,9 @@ int le_fix_rng_consumed(le_ctx *c, int which, int64_t *ndraws);
 /* compute forces/energies at the current positions without integrating (run 0 without fixes):
  * f[N*3] conservative pair+bond force in tag order (may be NULL) */
 int le_compute_forces(le_ctx *c, double *f, le_thermo *out);
+/* the same forces from the plain (no energy / virial tally) instantiation of the step kernel, the one production
+ * timesteps run; f[N*3] */
+int le_compute_forces_plain(le_ctx *c, double *f);
 
 /* ---- results --------------------------------------------------------------------------- */
 int le_natoms(const le_ctx *c);

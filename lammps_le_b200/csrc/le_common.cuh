@@ -8,14 +8,19 @@
 //     [gr0, cap)           ghosts of the right neighbor's first `halo` layers
 //   (one GPU: own0 = 0, nown = N, no ghosts: the periodic wrap comes from the fixed-point differences)
 //     pos[2][cap]   int4   {ux,uy,uz: 32-bit fixed-point box fractions, w: tag<<3 | type-1}   double-buffered
-//     vel[cap]      float4 {vx,vy,vz, w: tag bits (host convenience)}
+//     vel[cap]      float4 {vx,vy,vz, w: aux word -- list counts and the displacement bound, see AUX_* below}
 //     pos_hold[cap] int4   positions at the last rebuild (Neighbor::xhold, src/neighbor.cpp:2048-2052)
 //     img[cap], img_hold[cap]  LAMMPS-packed image flags now / at the last rebuild (owned atoms)
-//     counts[cap]   nfull | nbond<<16
-//     neigh[maxneigh][cap]  ELL full neighbor rows; entry = k_j | which<<30
 //     bondrow[bpa][cap]     ELL bond partner rows; entry = k_j | (bondtype-1)<<28
+//   neighbor list: the owned slots are cut into TILES of 32 consecutive slots (one warp of the step kernel).  The full
+//   list of a tile is ONE flat run of entries, grouped by owner (slot order), each pair (i,j) present in the run of
+//   i's tile and in the run of j's tile:
+//     tile_cnt[ntiles]            entries of the tile
+//     nbr[ntiles][32 * maxneigh]  entry = k_j | owner_lane<<25 | which<<30   (k_j < 2^25 local slots per GPU)
+//     nbr_ell[maxneigh][cap]      scratch of the list build (per-atom rows before they are packed into the tile run)
 //   tag order (index t-1; what the reference's Atom class holds, src/atom.h) -- replicated on every GPU
 //     num_bond, bond_type[N][bpa], bond_atom[N][bpa], nspecial[N][3], special[N][maxspecial]
+//     topo[N]     64-byte digest of the five tables above for the list build (TopoRec), refreshed when they change
 //     map[N]      tag-1 -> local slot, -1 if the atom is neither owned nor a ghost here (Atom::map, src/atom.h:354-358)
 #pragma once
 #include <cuda_runtime.h>
@@ -24,8 +29,31 @@
 #define LE_MAXT 8    // atom types
 #define LE_MAXB 8    // bond types
 #define LE_BIG 1.0e20
-#define NEIGH_IDX_MASK 0x3fffffffu
+#define NEIGH_IDX_BITS 25
+#define NEIGH_IDX_MASK 0x01ffffffu
 #define BOND_IDX_MASK 0x0fffffffu
+#define TILE 32
+
+// aux word of an owned atom (vel[k].w, as bits): neighbor count, bond count, and an upper bound of the distance the atom
+// has moved since the last rebuild in units of (skin/2)/65536 (saturating).  The step kernel adds each step's path
+// length to the bound (rounded up) and looks at pos_hold -- the exact test of Neighbor::check_distance -- only for the
+// few atoms whose bound has reached skin/2: the 16-byte pos_hold read leaves the per-step working set.
+#define AUX_NN(a) ((a) & 0xffu)
+#define AUX_NB(a) (((a) >> 8) & 0xfu)
+#define AUX_BOUND(a) ((a) >> 12)
+#define AUX_BOUND_ONE 65536u         // bound value that means "skin/2"
+#define AUX_BOUND_MAX 0xfffffu
+#define AUX_PACK(nn, nb, bound) ((unsigned)(nn) | ((unsigned)(nb) << 8) | ((unsigned)(bound) << 12))
+
+// digest of one atom's topology for the list build, tag order.  bond slots beyond 4 / specials beyond 10 are read from
+// the full tables (rare)
+struct __align__(16) TopoRec {
+  unsigned hdr;        // num_bond | nscan<<8 | n1<<16 | n2<<24   (nscan: special entries find_special must scan)
+  unsigned btypes;     // bond type - 1 of slots 0..7, 4 bits each
+  int batom[4];        // bond partner tags of slots 0..3
+  int spec[10];        // special[0..9]
+};
+#define TOPO_NSPEC 10
 
 struct Params {
   // box and fixed-point mapping: x = lo + u*scale, scale = L/2^32
@@ -61,6 +89,7 @@ struct Params {
   // sliver in between needs the reference's fp64 arithmetic (k_build)
   float cutneigh_lo[LE_MAXT * LE_MAXT], cutneigh_hi[LE_MAXT * LE_MAXT];
   float t_start, t_stop, tsqrt_const;
+  float inv_bound_unit;  // 65536 / (skin/2) (aux displacement bound)
   float dtfm[LE_MAXT];   // dtf / mass
   // integration / thermostat
   float dt, dtf;
@@ -101,8 +130,10 @@ struct Ctrl {
   long long epoch;            // force evaluations so far: the value the per-step peer flags carry
   long long rebuild_epoch;    // rebuilds so far (all GPUs rebuild on the same steps)
   long long le_epoch;         // USER-LE exchange rounds so far
-  unsigned tile_next;         // k_step2d: tiles handed out beyond the first wave (reset by the block that finishes last)
-  unsigned pad2;
+  unsigned scan_ticket;       // k_scan_cells: tile tickets (reset by the block that finishes last)
+  unsigned scan_done;
+  unsigned nbuilds_scan;      // launches of k_scan_cells so far (the epoch of its state words)
+  unsigned pad3;
 };
 
 enum {
@@ -157,12 +188,17 @@ struct Dev {
   int4 *pos_hold;
   float4 *vel, *vel_tmp;
   int *img, *img_hold;
-  unsigned *counts, *neigh, *bondrow;
+  unsigned *bondrow;
+  unsigned *tile_cnt, *nbr, *nbr_ell;
+  int tcap;           // entries per tile run = 32 * maxneigh
+  TopoRec *topo;
+  int4 *order2;       // cell sort: {old slot, tag, cell start, cell end} in cell order
+  unsigned long long *scan_state;   // single-pass scan of the cell counts (decoupled look-back)
   // tag order
   int *num_bond, *bond_type, *bond_atom, *nspecial, *special, *map;
   int *type_tag;      // atom type by tag (the USER-LE fixes read and change types of atoms that may live on another GPU)
   // cell sort scratch
-  int *cell_count, *cell_start, *cellid, *slot, *order, *blocksum;
+  int *cell_count, *cell_start, *cellid, *slot;
   int *ghost_tag;     // [2 own0] tags of the current ghosts (left, then right)
   int ncell[3];       // global cell grid
   int ncells;         // local cell slots incl. region sentinels: nlx*ncy*ncz + 3

@@ -7,7 +7,9 @@
 #include "../../include/le_b200.h"
 #include "le_common.cuh"
 #include "le_md.cuh"
-#include "le_step2.cuh"
+#include "le_sort.cuh"
+#include "le_build3.cuh"
+#include "le_step3.cuh"
 #include "le_fix.cuh"
 
 #include <math.h>
@@ -19,7 +21,6 @@
 #include <string>
 #include <vector>
 
-static inline float h_int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 static inline int h_float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 
 #define THERMO_SLOTS 4096
@@ -30,7 +31,7 @@ struct FixExUnloadCfg { int on, nevery, btype, seed; double rc, prob; };
 
 #define PLAIN_UNROLL 8      // timesteps per launch of the steady-state graph
 
-struct GraphKey { Dev d; int langevin; int variant; int pair32; };
+struct GraphKey { Dev d; int langevin; int uni; };
 
 struct le_ctx {
   int device, sm_count;
@@ -66,6 +67,7 @@ struct le_ctx {
   int64_t ntimestep;
   int cur;              // position buffer holding the current coordinates
   bool atoms_loaded, topo_loaded, lists_valid, params_dirty;
+  bool topo_dirty;      // the tag-ordered topology tables changed since the last k_topo_pack
   Dev d;
   Params P;
   std::vector<void *> allocs;
@@ -81,7 +83,7 @@ struct le_ctx {
   double *h_thermo;     // pinned
   Ctrl *h_ctrl;         // pinned
   // captured step graphs (built lazily, rebuilt when anything baked into them changes)
-  GraphKey gkey; int gkey_variant, plain_graph_kernels;
+  GraphKey gkey; int plain_graph_kernels;
   bool graphs_ok;
   cudaGraph_t g_plain[2], g_tail[2];          // g_plain[p]: steady-state graph launched when pos[p] holds the coordinates
   cudaGraphExec_t x_plain[2], x_tail[2];
@@ -119,7 +121,7 @@ static void time_report(le_ctx *c) {
     // average launch-to-next-launch time of the plain step kernel (le_run_timed)
     double sum = 0; int n = 0;
     for (size_t k = 0; k + 1 < c->tm_used; k++)
-      if (!strncmp(c->tm_name[k], "(k_step<0", 9) || !strncmp(c->tm_name[k], "(k_step2", 8)) { float ms = 0.f; cudaEventElapsedTime(&ms, c->tm_ev[k], c->tm_ev[k + 1]); sum += ms; n++; }
+      if (!strncmp(c->tm_name[k], "(k_step3<0", 10)) { float ms = 0.f; cudaEventElapsedTime(&ms, c->tm_ev[k], c->tm_ev[k + 1]); sum += ms; n++; }
     c->kstep_avg_ms = n ? sum / n : 0.0;
   }
   if (c->timing_quiet) { c->tm_used = 0; c->tm_name.clear(); return; }
@@ -218,7 +220,7 @@ extern "C" int le_create(le_ctx **out, int device, const double boxlo[3], const 
   c->thermo_every = 0;
   c->N = 0; c->ntimestep = 0; c->cur = 0;
   c->atoms_loaded = c->topo_loaded = c->lists_valid = false;
-  c->params_dirty = true;
+  c->params_dirty = true; c->topo_dirty = true;
   memset(&c->d, 0, sizeof c->d);
   memset(&c->lf, 0, sizeof c->lf);
   memset(&c->stats, 0, sizeof c->stats);
@@ -315,7 +317,7 @@ extern "C" int le_set_special(le_ctx *c, const double lj[3]) {
     if (lj[k] < 0.0 || lj[k] > 1.0) return fail(c, LE_EINVAL, "Illegal special_bonds command");
     c->special_lj[k + 1] = lj[k];
   }
-  c->params_dirty = true; c->lists_valid = false;
+  c->params_dirty = true; c->lists_valid = false; c->topo_dirty = true;
   return LE_OK;
 }
 
@@ -541,7 +543,6 @@ static int build_params(le_ctx *c) {
       if (k > 0 && (c->eps[k] != c->eps[0] || c->sigma[k] != c->sigma[0] || c->cut[k] != c->cut[0])) uniform = false;
     }
   P.pair_uniform = uniform ? 1 : 0;
-  { const char *p32 = getenv("LE_PAIR_FP32"); P.pair32 = (p32 && p32[0] == '1') ? 1 : 0; }   // development switch, see pair_term32
   if (!(cutneighmax > 0.0)) return fail(c, LE_ESTATE, "pair cutoff is zero: set pair_style lj/cut first");
   P.cutneighmaxsq_f = (float)(cutneighmax * cutneighmax * (1.0 + 2e-5));
   for (int k = 0; k < 3; k++)
@@ -581,6 +582,7 @@ static int build_params(le_ctx *c) {
   P.t_start = (float)c->t_start; P.t_stop = (float)c->t_stop; P.tsqrt_const = (float)sqrt(c->t_start);
   P.dt = (float)c->dt; P.dtf = (float)(0.5 * c->dt);       // FixNVE::init, ftm2v = 1
   P.triggersq = (float)(0.25 * c->skin * c->skin);
+  P.inv_bound_unit = c->skin > 0.0 ? (float)(65536.0 / (0.5 * c->skin)) : 3.0e38f;   // aux displacement bound, units of (skin/2)/65536
   P.vlimitsq = c->xlimit > 0.0 ? (float)((c->xlimit / c->dt) * (c->xlimit / c->dt)) : 0.0f;
   P.nve_on = c->nve_on; P.langevin_on = c->langevin_on;
   for (int k = 0; k < nt; k++) {                             // FixLangevin::init (src/fix_langevin.cpp:296-309)
@@ -602,7 +604,7 @@ static int push_params(le_ctx *c) {
       if (c->nranks > 1) return fail(c, LE_ESTATE, "multi-GPU: cell arrays are sized when the atoms are distributed");
       r = dalloc(c, &c->d.cell_count, (size_t)c->d.ncells + 1); if (r) return r;
       r = dalloc(c, &c->d.cell_start, (size_t)c->d.ncells + 1); if (r) return r;
-      r = dalloc(c, &c->d.blocksum, (size_t)c->d.nscanblocks + 1); if (r) return r;
+      r = dalloc(c, &c->d.scan_state, (size_t)c->d.nscanblocks + 1); if (r) return r;
     }
     c->params_dirty = false;
   }
@@ -666,6 +668,7 @@ extern "C" int le_upload_atoms(le_ctx *c, int n, const int *tag, const int *type
   if (n < 1 || !type || !x) return fail(c, LE_EINVAL, "le_upload_atoms: bad arguments");
   if (c->atoms_loaded) return fail(c, LE_ESTATE, "atoms already uploaded (create a new context)");
   if (n >= (1 << 28)) return fail(c, LE_EINVAL, "at most 2^28-1 atoms");
+  if (c->nranks == 1 && n >= (1 << NEIGH_IDX_BITS)) return fail(c, LE_EINVAL, "at most 2^%d-1 atoms per GPU (neighbor entries hold a %d-bit slot): use more GPUs", NEIGH_IDX_BITS, NEIGH_IDX_BITS);
   cudaSetDevice(c->device);
   c->N = n;
   Dev &d = c->d;
@@ -689,7 +692,7 @@ extern "C" int le_upload_atoms(le_ctx *c, int n, const int *tag, const int *type
     hp[t - 1] = make_int4((int)u[0], (int)u[1], (int)u[2], (t << 3) | (type[k] - 1));
     float4 vv;
     vv.x = v ? (float)v[3 * k] : 0.f; vv.y = v ? (float)v[3 * k + 1] : 0.f; vv.z = v ? (float)v[3 * k + 2] : 0.f;
-    vv.w = h_int_as_float(t);
+    vv.w = 0.f;                                   // aux word: no lists yet
     hv[t - 1] = vv;
     himg[t - 1] = pack_image(ix + w[0], iy + w[1], iz + w[2]);
   }
@@ -732,6 +735,7 @@ extern "C" int le_upload_atoms(le_ctx *c, int n, const int *tag, const int *type
     // multiples of 64 slots: the owned region starts on a 128-byte line of every per-atom array
     const long long owncap = (maxown + maxown / 4 + 4096 + 63) & ~63LL, ghostcap = (maxghost + maxghost / 2 + 4096 + 63) & ~63LL;
     d.own0 = (int)ghostcap; d.gr0 = (int)(ghostcap + owncap); d.cap = (int)(2 * ghostcap + owncap);
+    if (d.cap >= (1 << NEIGH_IDX_BITS)) return fail(c, LE_EINVAL, "at most 2^%d-1 local atoms per GPU (neighbor entries hold a %d-bit slot): use more GPUs", NEIGH_IDX_BITS, NEIGH_IDX_BITS);
     d.inbox_cap = (int)std::max<long long>(4096, owncap / 16);
     for (int t = 0; t < n; t++) {
       const int cx = (int)(((unsigned long long)(unsigned)hp[t].x * (unsigned)ncx) >> 32);
@@ -755,7 +759,7 @@ extern "C" int le_upload_atoms(le_ctx *c, int n, const int *tag, const int *type
     d.pos[0] = me.pos[0]; d.pos[1] = me.pos[1]; d.pos_hold = me.pos_hold; d.cell_start = me.cell_start;
     d.in_pos = me.in_pos; d.in_vel = me.in_vel; d.in_img = me.in_img; d.flags = me.flags;
     if ((r = dalloc(c, &d.cell_count, (size_t)d.ncells + 1))) return r;
-    if ((r = dalloc(c, &d.blocksum, (size_t)d.nscanblocks + 1))) return r;
+    if ((r = dalloc(c, &d.scan_state, (size_t)d.nscanblocks + 1))) return r;
     if ((r = dalloc(c, &d.ghost_tag, (size_t)2 * d.own0 + 1))) return r;
   }
   if ((r = dalloc(c, &c->rb, 1))) return r;
@@ -763,9 +767,13 @@ extern "C" int le_upload_atoms(le_ctx *c, int n, const int *tag, const int *type
   if ((r = dalloc(c, &d.vel_tmp, cap))) return r;
   if ((r = dalloc(c, &d.img, cap))) return r;
   if ((r = dalloc(c, &d.img_hold, cap))) return r;
-  if ((r = dalloc(c, &d.counts, cap))) return r;
-  if ((r = dalloc(c, &d.neigh, (size_t)cap * c->maxneigh))) return r;
+  d.tcap = TILE * c->maxneigh;
+  if ((r = dalloc(c, &d.tile_cnt, (size_t)(cap / TILE) + 2))) return r;
+  if ((r = dalloc(c, &d.nbr, ((size_t)(d.gr0 - d.own0) / TILE + 2) * d.tcap))) return r;
+  if ((r = dalloc(c, &d.nbr_ell, (size_t)cap * std::max(c->maxneigh - 15, 1)))) return r;   // rows beyond the smallest shared-memory queue
   if ((r = dalloc(c, &d.bondrow, (size_t)cap * c->bpa))) return r;
+  if ((r = dalloc(c, &d.topo, (size_t)n))) return r;
+  if ((r = dalloc(c, &d.order2, (size_t)cap))) return r;
   if ((r = dalloc(c, &d.num_bond, n))) return r;
   if ((r = dalloc(c, &d.bond_type, (size_t)n * c->bpa))) return r;
   if ((r = dalloc(c, &d.bond_atom, (size_t)n * c->bpa))) return r;
@@ -775,7 +783,6 @@ extern "C" int le_upload_atoms(le_ctx *c, int n, const int *tag, const int *type
   if ((r = dalloc(c, &d.type_tag, n))) return r;
   if ((r = dalloc(c, &d.cellid, cap))) return r;
   if ((r = dalloc(c, &d.slot, cap))) return r;
-  if ((r = dalloc(c, &d.order, cap))) return r;
   if ((r = dalloc(c, &d.ctrl, 1))) return r;
   if ((r = dalloc(c, &d.thermo, (size_t)LE_THERMO_W * THERMO_SLOTS))) return r;
   if ((r = dalloc(c, &d.fout, (size_t)n * 3))) return r;
@@ -882,7 +889,7 @@ static int upload_topology_host(le_ctx *c, const std::vector<int> &nb, const std
   long long nb64 = c->nbonds;
   CK(cudaMemcpyAsync(&c->d.ctrl->nbonds, &nb64, sizeof nb64, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  c->topo_loaded = true; c->lists_valid = false;
+  c->topo_loaded = true; c->lists_valid = false; c->topo_dirty = true;
   return LE_OK;
 }
 
@@ -992,108 +999,88 @@ extern "C" int le_set_velocities(le_ctx *c, const double *v) {
   for (int t = 0; t < n; t++) {
     const int k = hmap[t];
     if (k < c->d.own0 || k >= c->d.gr0) continue;
-    float4 vv; vv.x = (float)v[3 * t]; vv.y = (float)v[3 * t + 1]; vv.z = (float)v[3 * t + 2]; vv.w = h_int_as_float(t + 1);
-    hv[k] = vv;
+    hv[k].x = (float)v[3 * t]; hv[k].y = (float)v[3 * t + 1]; hv[k].z = (float)v[3 * t + 2];   // .w (aux word) stays
   }
   CK(cudaMemcpyAsync(c->d.vel, hv.data(), sizeof(float4) * cap, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return LE_OK;
 }
 
-// ---- which plain step kernel (no energy / virial tally) -----------------------------------------------
-// LE_STEP_VARIANT (read at every le_run, so one process can compare variants): 0 = k_step; bit 0 = k_step2 (le_step2.cuh),
-// bit 1 = 128 threads per block instead of 256, bit 5 = persistent grid (k_step2p), bit 9 (with bits 0 and 5) = the step
-// kernel's last block takes the reneighbor decision of the next timestep inside the steady-state graph, bit 10 (with bits
-// 0 and 5) = dynamic tile fetch (k_step2d), bit 4 = k_step2
-// also on several GPUs.  k_step2 needs the uniform lj/cut case and special weights in {0, 1}; otherwise k_step runs
-// whatever the switch says.
-#ifndef LE_STEP_VARIANT_DEFAULT
-#define LE_STEP_VARIANT_DEFAULT 33   // k_step2p<0,256>: fastest of the variants measured at 1M beads (profiles/r01_step_variants.txt)
-#endif
+// ---- which step kernel ----------------------------------------------------------------------------------
+// k_step3<EV, DD, UNI> (le_step3.cuh).  UNI: one lj/cut coefficient set for all type pairs and special weights in {0, 1}
+// only (every listed pair has factor 1) -- coefficients become immediate operands.
 typedef void (*step_fn_t)(Dev, StepArgs);
-struct StepKernel { step_fn_t fn; int threads; const char *name; int wave_blocks; };   // wave_blocks: persistent grid, blocks per SM (0 = one block per NT atoms)
+struct StepKernel { step_fn_t fn; int threads; const char *name; int wave_blocks; };   // wave_blocks: persistent grid, blocks per SM
 
-static int step_variant() { const char *v = getenv("LE_STEP_VARIANT"); return v ? atoi(v) : LE_STEP_VARIANT_DEFAULT; }
-
-static bool step2_eligible(const le_ctx *c) {
+static bool step_uniform(const le_ctx *c) {
   if (!c->P.pair_uniform) return false;
   for (int k = 1; k <= 3; k++) if (c->P.special_flag[k] == 2) return false;
   return true;
 }
 
-#define STEP2_CASE(dd, nt) { (step_fn_t)k_step2<dd, nt>, nt, "(k_step2<" #dd "," #nt ">)", 0 }
-#define STEP2P_CASE(dd, nt) { (step_fn_t)k_step2p<dd, nt>, nt, "(k_step2p<" #dd "," #nt ">)", 1024 / nt }
-static StepKernel plain_step_kernel(const le_ctx *c, int variant) {
-  const bool dd = c->nranks > 1;
-  if ((variant & 1) && step2_eligible(c) && (!dd || (variant & 16))) {
-    const bool small = variant & 2, pers = variant & 32;
-    if (!dd && pers && (variant & 1024))   // dynamic tile fetch (256-thread form)
-      return c->P.pair32 ? StepKernel{(step_fn_t)k_step2d<256, 1>, 256, "(k_step2d<256,p32>)", 4} : StepKernel{(step_fn_t)k_step2d<256>, 256, "(k_step2d<256>)", 4};
-    if (c->P.pair32) {   // fp32 pair terms: 256-thread forms only
-      if (dd) return pers ? StepKernel{(step_fn_t)k_step2p<1, 256, 0, 1>, 256, "(k_step2p<1,256,p32>)", 4} : StepKernel{(step_fn_t)k_step2<1, 256, 1>, 256, "(k_step2<1,256,p32>)", 0};
-      if (pers && (variant & 512)) return StepKernel{(step_fn_t)k_step2p<0, 256, 1, 1>, 256, "(k_step2p<0,256,fuse,p32>)", 4};
-      return pers ? StepKernel{(step_fn_t)k_step2p<0, 256, 0, 1>, 256, "(k_step2p<0,256,p32>)", 4} : StepKernel{(step_fn_t)k_step2<0, 256, 1>, 256, "(k_step2<0,256,p32>)", 0};
-    }
-    if (dd) {
-      if (pers) return small ? StepKernel STEP2P_CASE(1, 128) : StepKernel STEP2P_CASE(1, 256);
-      return small ? StepKernel STEP2_CASE(1, 128) : StepKernel STEP2_CASE(1, 256);
-    }
-    if (pers && (variant & 512))   // with the epilogue of the fused reneighbor decision (same kernel name for the timing marks)
-      return small ? StepKernel{(step_fn_t)k_step2p<0, 128, 1>, 128, "(k_step2p<0,128,fuse>)", 8} : StepKernel{(step_fn_t)k_step2p<0, 256, 1>, 256, "(k_step2p<0,256,fuse>)", 4};
-    if (pers) return small ? StepKernel STEP2P_CASE(0, 128) : StepKernel STEP2P_CASE(0, 256);
-    return small ? StepKernel STEP2_CASE(0, 128) : StepKernel STEP2_CASE(0, 256);
+static StepKernel step_kernel(const le_ctx *c, bool ev) {
+  const bool dd = c->nranks > 1, uni = step_uniform(c);
+  if (ev) {
+    if (dd) return uni ? StepKernel{(step_fn_t)k_step3<1, 1, 1>, STEP3_THREADS, "(k_step3<1,1,1>)", 2} : StepKernel{(step_fn_t)k_step3<1, 1, 0>, STEP3_THREADS, "(k_step3<1,1,0>)", 2};
+    return uni ? StepKernel{(step_fn_t)k_step3<1, 0, 1>, STEP3_THREADS, "(k_step3<1,0,1>)", 2} : StepKernel{(step_fn_t)k_step3<1, 0, 0>, STEP3_THREADS, "(k_step3<1,0,0>)", 2};
   }
-  if (c->P.pair32) return StepKernel{dd ? (step_fn_t)k_step<0, 1, 4, 0, 1> : (step_fn_t)k_step<0, 0, 4, 0, 1>, STEP_THREADS, "(k_step<0,p32>)", 0};
-  const bool uni = c->P.pair_uniform != 0;
-  static const int minb = getenv("LE_STEP_MINB") ? atoi(getenv("LE_STEP_MINB")) : 4;
-  step_fn_t fn;
-  if (dd) fn = uni ? (step_fn_t)k_step<0, 1, 4, 1> : (step_fn_t)k_step<0, 1>;
-  else fn = minb == 5 ? (step_fn_t)k_step<0, 0, 5> : minb == 6 ? (step_fn_t)k_step<0, 0, 6> : minb == 3 ? (step_fn_t)k_step<0, 0, 3>
-            : uni ? (step_fn_t)k_step<0, 0, 4, 1> : (step_fn_t)k_step<0, 0>;
-  return StepKernel{fn, STEP_THREADS, "(k_step<0>)", 0};
+  if (dd) return uni ? StepKernel{(step_fn_t)k_step3<0, 1, 1>, STEP3_THREADS, "(k_step3<0,1,1>)", 4} : StepKernel{(step_fn_t)k_step3<0, 1, 0>, STEP3_THREADS, "(k_step3<0,1,0>)", 4};
+  return uni ? StepKernel{(step_fn_t)k_step3<0, 0, 1>, STEP3_THREADS, "(k_step3<0,0,1>)", 4} : StepKernel{(step_fn_t)k_step3<0, 0, 0>, STEP3_THREADS, "(k_step3<0,0,0>)", 4};
 }
 
-// blocks of a plain step launch: one per NT owned slots (+1 boundary bookkeeping block on a slab); a persistent kernel
-// gets one wave of resident blocks
+// one wave of resident blocks (persistent grid over the tiles), fewer when there are fewer tiles
 static int step_grid(const le_ctx *c, const StepKernel &sk) {
-  const int g = grid_for(c->d.gr0 - c->d.own0, sk.threads) + (c->nranks > 1 ? 1 : 0);
-  return sk.wave_blocks ? std::min(g, c->sm_count * sk.wave_blocks) : g;
+  const int tiles = (c->d.gr0 - c->d.own0 + TILE - 1) / TILE + 2;
+  const int g = (tiles + STEP3_WARPS - 1) / STEP3_WARPS;
+  return std::max(1, std::min(g, c->sm_count * sk.wave_blocks));
 }
 
 // ---- rebuild / step drivers -------------------------------------------------------------------------
+// expected number of candidates that pass the distance screen of the list build (listed + excluded bonded neighbors):
+// picks the shared-memory queue depth of k_build3
+static int build_queue_depth(const le_ctx *c) {
+  double vol = 1.0;
+  for (int k = 0; k < 3; k++) vol *= c->hi[k] - c->lo[k];
+  double cn = 0.0;
+  for (int k = 0; k < c->ntypes * c->ntypes; k++) cn = std::max(cn, sqrt(c->P.cutneighsq[k]));
+  const double expect = (double)c->N / vol * 4.18879 * cn * cn * cn + 3.0;
+  return expect > 9.0 ? 28 : 16;
+}
+
+// the tag-ordered topology tables -> the 64-byte digests the list build reads
+static void enqueue_topo_pack(le_ctx *c) {
+  LAUNCH(c, k_topo_pack, std::min(grid_for(c->N, 256), c->sm_count * 8), 256, c->d);
+  c->topo_dirty = false;
+}
+
 // the rebuild kernels; `direct` adds the bookkeeping k_decide does when the rebuild is a conditional graph node
 static void enqueue_rebuild(le_ctx *c, bool direct) {
   Dev &d = c->d;
   const int nslots = d.gr0 - d.own0;                       // capacity of the owned region
   const bool dd = c->nranks > 1;
+  if (c->topo_dirty && !c->capturing) enqueue_topo_pack(c);
   LAUNCH(c, k_cell_count, grid_for(nslots, 256), 256, d, c->rb);
   if (dd) {
     LAUNCH(c, k_rb_post_inbox, 1, 1, d, c->rb);
     LAUNCH(c, k_inbox, grid_for(2 * d.inbox_cap, 256), 256, d, c->rb);
   }
-  LAUNCH(c, k_scan_partial, d.nscanblocks, SCAN_BLOCK, d);
-  LAUNCH(c, k_scan_blocks, 1, SCAN_BLOCK, d);
-  LAUNCH(c, k_scan_apply, d.nscanblocks, SCAN_BLOCK, d);
+  LAUNCH(c, k_scan_cells, d.nscanblocks, SCAN_BLOCK, d);
   LAUNCH(c, k_cell_scatter, grid_for(nslots, 256), 256, d);
-  LAUNCH(c, k_gather, grid_for(nslots, 256), 256, d);
+  LAUNCH(c, k_permute, grid_for(nslots, 256), 256, d);
   if (dd) {
     LAUNCH(c, k_push_ghosts, grid_for(std::max(d.own0, d.halo * d.ncell[1] * d.ncell[2] + 1), 256), 256, d);
     LAUNCH(c, k_rb_post_ghosts, 1, 1, d);
     LAUNCH(c, k_ghost_map, grid_for(2 * d.own0, 256), 256, d);
   }
   {
-    static const int minb = getenv("LE_BUILD_MINB") ? atoi(getenv("LE_BUILD_MINB")) : 8;
     const int g = grid_for(nslots, BUILD_THREADS);
-    if (minb == 10) LAUNCH(c, k_build<10>, g, BUILD_THREADS, d);
-    else if (minb == 12) LAUNCH(c, k_build<12>, g, BUILD_THREADS, d);
-    else if (minb == 16) LAUNCH(c, k_build<16>, g, BUILD_THREADS, d);
-    else if (minb == 6) LAUNCH(c, k_build<6>, g, BUILD_THREADS, d);
-    else LAUNCH(c, k_build<8>, g, BUILD_THREADS, d);
+    if (build_queue_depth(c) > 16) LAUNCH(c, (k_build3<28, 4>), g, BUILD_THREADS, d);
+    else LAUNCH(c, (k_build3<16, 8>), g, BUILD_THREADS, d);
   }
   if (direct) { LAUNCH(c, k_after_build, 1, 1, d); c->direct_builds++; }
 }
 
-static int rebuild_kernel_count(const le_ctx *c) { return c->nranks > 1 ? 12 : 7; }
+static int rebuild_kernel_count(const le_ctx *c) { return c->nranks > 1 ? 10 : 5; }
 
 #define CKG(call)                                                                             \
   do {                                                                                        \
@@ -1104,15 +1091,13 @@ static int rebuild_kernel_count(const le_ctx *c) { return c->nranks > 1 ? 12 : 7
     }                                                                                         \
   } while (0)
 
-// append [k_decide(advance) -> IF(rebuild)] (and optionally a plain k_step after it) to graph g after node *tail.
-// `handle` switches this unit's conditional node; with_decide = false: the step kernel of the previous unit has taken
-// the decision (StepArgs::fuse) and set the handle.  next_handle != 0: this unit's step kernel does the same for the
-// unit that follows.
+// append [k_decide(advance) -> IF(rebuild)] (and optionally a plain step kernel after it) to graph g after node *tail.
+// `handle` switches this unit's conditional node.
 static int graph_add_unit(le_ctx *c, cudaGraph_t g, cudaGraphNode_t *tail, int advance, bool with_step, int step_rd,
-                          cudaGraphConditionalHandle handle, bool with_decide, cudaGraphConditionalHandle next_handle) {
+                          cudaGraphConditionalHandle handle) {
   Dev d = c->d;
   cudaKernelNodeParams kp;
-  if (with_decide) {
+  {
     int adv = advance, use = 1;
     void *dargs[] = {&d, &handle, &adv, &use};
     kp = cudaKernelNodeParams{};
@@ -1138,12 +1123,10 @@ static int graph_add_unit(le_ctx *c, cudaGraph_t g, cudaGraphNode_t *tail, int a
   if (with_step) {
     StepArgs a; memset(&a, 0, sizeof a);
     a.do_final = 1; a.do_initial = 1; a.langevin = c->langevin_on;
-    { static const int skip = getenv("LE_STEP_SKIP") ? atoi(getenv("LE_STEP_SKIP")) : 0; a.skip = skip & (15 | 32); if (skip & 16) a.langevin = 0; }
     a.rdp1 = step_rd + 1;
-    if (next_handle) { a.fuse = 1; a.handle = next_handle; }
     void *sargs[] = {&d, &a};
     kp = cudaKernelNodeParams{};
-    const StepKernel sk = plain_step_kernel(c, c->gkey_variant);
+    const StepKernel sk = step_kernel(c, false);
     kp.func = (void *)sk.fn; kp.gridDim = dim3(step_grid(c, sk));
     kp.blockDim = dim3(sk.threads); kp.kernelParams = sargs;
     cudaGraphNode_t ns;
@@ -1153,41 +1136,30 @@ static int graph_add_unit(le_ctx *c, cudaGraph_t g, cudaGraphNode_t *tail, int a
   return LE_OK;
 }
 
-// the reneighbor decision fused into the step kernel (LE_STEP_VARIANT bit 9): only the persistent single-GPU kernel has
-// the last-block epilogue
-static bool fused_decide(const le_ctx *c, int variant) {
-  return (variant & 512) && !(variant & 1024) && (variant & 1) && (variant & 32) && c->nranks == 1 && step2_eligible(c);
-}
-
 static int ensure_graphs(le_ctx *c) {
   GraphKey key; memset(&key, 0, sizeof key);
-  key.d = c->d; key.langevin = c->langevin_on; key.variant = step_variant(); key.pair32 = c->P.pair32;
+  key.d = c->d; key.langevin = c->langevin_on; key.uni = step_uniform(c) ? 1 : 0;
   if (c->graphs_ok && memcmp(&key, &c->gkey, sizeof key) == 0) return LE_OK;
   destroy_graphs(c);
-  c->gkey_variant = key.variant;
   int r;
   for (int adv = 0; adv < 2; adv++) {
     CKG(cudaGraphCreate(&c->g_tail[adv], 0));
     cudaGraphNode_t tail = nullptr;
     cudaGraphConditionalHandle h;
     CKG(cudaGraphConditionalHandleCreate(&h, c->g_tail[adv], 0, cudaGraphCondAssignDefault));
-    if ((r = graph_add_unit(c, c->g_tail[adv], &tail, adv, false, 0, h, true, 0))) return r;
+    if ((r = graph_add_unit(c, c->g_tail[adv], &tail, adv, false, 0, h))) return r;
     CKG(cudaGraphInstantiate(&c->x_tail[adv], c->g_tail[adv], 0));
   }
   // the steady-state graph, once per buffer parity at its launch: every k_decide flips the buffers, so the step kernel
-  // of unit u reads pos[p ^ ((u + 1) & 1)] -- known here, passed as a kernel argument (StepArgs::rdp1).  With the
-  // fused decision only the first unit keeps its k_decide: the step kernel of unit u decides for unit u + 1.
-  const bool fused = fused_decide(c, key.variant);
-  c->plain_graph_kernels = fused ? PLAIN_UNROLL + 1 : 2 * PLAIN_UNROLL;
+  // of unit u reads pos[p ^ ((u + 1) & 1)] -- known here, passed as a kernel argument (StepArgs::rdp1)
+  c->plain_graph_kernels = 2 * PLAIN_UNROLL;
   for (int p = 0; p < 2; p++) {
     CKG(cudaGraphCreate(&c->g_plain[p], 0));
     cudaGraphConditionalHandle h[PLAIN_UNROLL];
     for (int u = 0; u < PLAIN_UNROLL; u++) CKG(cudaGraphConditionalHandleCreate(&h[u], c->g_plain[p], 0, cudaGraphCondAssignDefault));
     cudaGraphNode_t tail = nullptr;
     for (int u = 0; u < PLAIN_UNROLL; u++)
-      if ((r = graph_add_unit(c, c->g_plain[p], &tail, 1, true, p ^ ((u + 1) & 1), h[u], u == 0 || !fused,
-                              fused && u + 1 < PLAIN_UNROLL ? h[u + 1] : 0)))
-        return r;
+      if ((r = graph_add_unit(c, c->g_plain[p], &tail, 1, true, p ^ ((u + 1) & 1), h[u]))) return r;
     CKG(cudaGraphInstantiate(&c->x_plain[p], c->g_plain[p], 0));
   }
   c->gkey = key;
@@ -1273,16 +1245,7 @@ static void thermo_from_slot(le_ctx *c, const double *s, int64_t step, le_thermo
 // one force evaluation + integration; the host's record of the buffer parity (c->cur) is what the kernel will find
 // in Ctrl::cur when it runs, so it travels as an argument
 static void launch_step(le_ctx *c, StepArgs a, bool ev) {
-  if (ev) {
-    const int grid = grid_for(c->d.gr0 - c->d.own0, STEP_THREADS) + (c->nranks > 1 ? 1 : 0);
-    if (c->P.pair32) {
-      if (c->nranks > 1) LAUNCH(c, (k_step<1, 1, 4, 0, 1>), grid, STEP_THREADS, c->d, a);
-      else LAUNCH(c, (k_step<1, 0, 4, 0, 1>), grid, STEP_THREADS, c->d, a);
-    } else if (c->nranks > 1) LAUNCH(c, (k_step<1, 1>), grid, STEP_THREADS, c->d, a);
-    else LAUNCH(c, (k_step<1, 0>), grid, STEP_THREADS, c->d, a);
-    return;
-  }
-  const StepKernel sk = plain_step_kernel(c, step_variant());
+  const StepKernel sk = step_kernel(c, ev);
   a.rdp1 = c->cur + 1;
   if (c->timing && !c->capturing) time_mark(c, sk.name);
   sk.fn<<<step_grid(c, sk), sk.threads, 0, c->stream>>>(c->d, a);
@@ -1315,6 +1278,24 @@ extern "C" int le_compute_forces(le_ctx *c, double *f, le_thermo *out) {
     CK(cudaMemcpyAsync(f, c->d.fout, sizeof(double) * 3 * c->N, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
   }
+  return LE_OK;
+}
+
+/* the same forces through the PLAIN instantiation of the step kernel (no energy / virial tally) -- the one every
+ * production timestep runs -- so that the per-atom force parity tests reach it too */
+extern "C" int le_compute_forces_plain(le_ctx *c, double *f) {
+  if (!c || !f) return LE_EINVAL;
+  int r = ensure_ready(c); if (r) return r;
+  enqueue_rebuild(c, true);
+  c->lists_valid = true;
+  r = push_run_state(c, c->ntimestep, c->ntimestep); if (r) return r;
+  StepArgs a; memset(&a, 0, sizeof a);
+  a.write_force = 1;
+  if (c->nranks > 1) CK(cudaMemsetAsync(c->d.fout, 0, sizeof(double) * 3 * c->N, c->stream));   // owned rows only are written
+  launch_step(c, a, false);
+  r = sync_and_check(c); if (r) return r;
+  CK(cudaMemcpyAsync(f, c->d.fout, sizeof(double) * 3 * c->N, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   return LE_OK;
 }
 
@@ -1362,7 +1343,6 @@ extern "C" int le_run(le_ctx *c, int64_t nsteps) {
     a.do_final = (s > begin);
     a.do_initial = (s < end);
     a.langevin = c->langevin_on;
-    { static const int skip = getenv("LE_STEP_SKIP") ? atoi(getenv("LE_STEP_SKIP")) : 0; a.skip = skip & (15 | 32); if (skip & 16) a.langevin = 0; }
     bool ev = false;
     if (want_thermo(s)) {
       if (used_slots == THERMO_SLOTS) {
@@ -1485,11 +1465,12 @@ extern "C" int le_download_v(le_ctx *c, double *v) {
   if (!c->atoms_loaded) return fail(c, LE_ESTATE, "no atoms");
   cudaSetDevice(c->device);
   int n; int r = fetch_nown(c, &n); if (r) return r;
-  std::vector<float4> hv(n);
+  std::vector<float4> hv(n); std::vector<int4> hp(n);
   CK(cudaMemcpyAsync(hv.data(), c->d.vel + c->d.own0, sizeof(float4) * n, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(hp.data(), c->d.pos[c->cur] + c->d.own0, sizeof(int4) * n, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   for (int k = 0; k < n; k++) {
-    const int t = h_float_as_int(hv[k].w) - 1;
+    const int t = (hp[k].w >> 3) - 1;
     v[3 * t] = hv[k].x; v[3 * t + 1] = hv[k].y; v[3 * t + 2] = hv[k].z;
   }
   return LE_OK;
@@ -1525,6 +1506,7 @@ extern "C" int le_download_owned(le_ctx *c, int *n_out, int *tag, double *x, int
   if (!c->atoms_loaded) return fail(c, LE_ESTATE, "no atoms");
   cudaSetDevice(c->device);
   int r = ensure_staging(c); if (r) return r;
+  if ((r = push_params(c))) return r;     // k_pack_owned dequantises with the constant block, which all contexts of the process share
   int n; r = fetch_nown(c, &n); if (r) return r;
   LAUNCH(c, k_pack_owned, grid_for(n, 256), 256, c->d, tag ? c->st_tag : nullptr, x ? c->st_x : nullptr, image ? c->st_img : nullptr, v ? c->st_v : nullptr);
   if (tag) CK(cudaMemcpyAsync(tag, c->st_tag, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
@@ -1570,30 +1552,49 @@ extern "C" int le_download_neighlist(le_ctx *c, int half, int64_t *offsets, int 
   if (!c) return LE_EINVAL;
   if (!c->lists_valid) return fail(c, LE_ESTATE, "no neighbor list has been built yet");
   cudaSetDevice(c->device);
-  const int n = c->N, cap = c->d.cap;
-  std::vector<unsigned> cnt(cap); std::vector<int4> hp(cap); std::vector<int> hmap;
-  int r = fetch_map(c, hmap); if (r) return r;
-  CK(cudaMemcpyAsync(cnt.data(), c->d.counts, sizeof(unsigned) * cap, cudaMemcpyDeviceToHost, c->stream));
+  const int n = c->N, cap = c->d.cap, own0 = c->d.own0, tcap = c->d.tcap;
+  int nown; int r = fetch_nown(c, &nown); if (r) return r;
+  const int ntiles = (nown + TILE - 1) / TILE;
+  std::vector<unsigned> tcnt(std::max(ntiles, 1)); std::vector<int4> hp(cap); std::vector<float4> hv(cap); std::vector<int> hmap;
+  r = fetch_map(c, hmap); if (r) return r;
+  CK(cudaMemcpyAsync(tcnt.data(), c->d.tile_cnt, sizeof(unsigned) * ntiles, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(hv.data(), c->d.vel, sizeof(float4) * cap, cudaMemcpyDeviceToHost, c->stream));
   // positions at the last rebuild: the coordinates the list was built on
   CK(cudaMemcpyAsync(hp.data(), c->d.pos_hold, sizeof(int4) * cap, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  int maxc = 0;
-  for (int t = 0; t < n; t++) { const int k = hmap[t]; if (k >= c->d.own0 && k < c->d.gr0) maxc = std::max(maxc, (int)(cnt[k] & 0xff)); }
-  std::vector<unsigned> rows((size_t)std::max(maxc, 1) * cap);
-  CK(cudaMemcpyAsync(rows.data(), c->d.neigh, sizeof(unsigned) * (size_t)maxc * cap, cudaMemcpyDeviceToHost, c->stream));
+  // the tiles' runs (one strided copy: the used prefix of every run)
+  unsigned maxc = 1;
+  for (int t = 0; t < ntiles; t++) maxc = std::max(maxc, tcnt[t]);
+  std::vector<unsigned> runs((size_t)std::max(ntiles, 1) * maxc);
+  if (ntiles > 0)
+    CK(cudaMemcpy2DAsync(runs.data(), sizeof(unsigned) * maxc, c->d.nbr, sizeof(unsigned) * tcap, sizeof(unsigned) * maxc, ntiles,
+                         cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  // the device keeps full rows; which atom of a pair the reference's half list stores it on is derived here with
+  // start of every owned slot's entries inside its tile's run: exclusive sum of the aux counts over the tile
+  std::vector<int> start(cap, 0);
+  for (int t = 0; t < ntiles; t++) {
+    int o = 0;
+    for (int l = 0; l < TILE && t * TILE + l < nown; l++) {
+      const int k = own0 + t * TILE + l;
+      start[k] = o;
+      o += (int)AUX_NN((unsigned)h_float_as_int(hv[k].w));
+    }
+    if ((unsigned)o != tcnt[t]) return fail(c, LE_ERUN, "internal: tile %d holds %u entries, its atoms count %d", t, tcnt[t], o);
+  }
+  // the device keeps the full list; which atom of a pair the reference's half list stores it on is derived here with
   // the same arithmetic the device uses for the (t,t+2) pairs (le_pair_stored_on_i).  Rows of atoms owned by
   // another GPU stay empty.
   int64_t o = 0;
   for (int t = 0; t < n; t++) {
     const int k = hmap[t];
     if (offsets) offsets[t] = o;
-    if (k < c->d.own0 || k >= c->d.gr0) continue;
-    const int cc = cnt[k] & 0xff;
+    if (k < own0 || k >= own0 + nown) continue;
+    const int cc = (int)AUX_NN((unsigned)h_float_as_int(hv[k].w));
+    const int tile = (k - own0) / TILE, lane = (k - own0) % TILE;
     const unsigned ui[3] = {(unsigned)hp[k].x, (unsigned)hp[k].y, (unsigned)hp[k].z};
     for (int q = 0; q < cc; q++) {
-      const unsigned e = rows[(size_t)q * cap + k];
+      const unsigned e = runs[(size_t)tile * maxc + start[k] + q];
+      if ((int)((e >> NEIGH_IDX_BITS) & 31u) != lane) return fail(c, LE_ERUN, "internal: entry %d of atom %d carries owner lane %u", q, t + 1, (e >> NEIGH_IDX_BITS) & 31u);
       const int4 pj = hp[e & NEIGH_IDX_MASK];
       const int tj = pj.w >> 3;
       if (half) {
@@ -1682,7 +1683,7 @@ extern "C" int le_run_timed(le_ctx *c, int64_t nsteps, double *kstep_us) {
 extern "C" const char *le_step_kernel_name(le_ctx *c) {
   if (!c) return "";
   static thread_local std::string name;
-  name = plain_step_kernel(c, step_variant()).name;           // "(kernel<...>)" as the timing marks spell it
+  name = step_kernel(c, false).name;                          // "(kernel<...>)" as the timing marks spell it
   if (name.size() >= 2 && name.front() == '(' && name.back() == ')') name = name.substr(1, name.size() - 2);
   return name.c_str();
 }

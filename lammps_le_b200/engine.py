@@ -72,7 +72,7 @@ def load_library():
         "le_upload_topology": [P, pi, pi, pi, pi, pi], "le_set_positions": [P, pd, pi], "le_set_velocities": [P, pd],
         "le_run": [P, I64], "le_run_timed": [P, I64, pd], "le_force_rebuild": [P], "le_run_le_event": [P, I],
         "le_fix_rng_reset": [P, I, I, I64], "le_fix_rng_consumed": [P, I, C.POINTER(I64)],
-        "le_compute_forces": [P, pd, C.POINTER(Thermo)], "le_natoms": [P], "le_download_x": [P, pd, pi],
+        "le_compute_forces": [P, pd, C.POINTER(Thermo)], "le_compute_forces_plain": [P, pd], "le_natoms": [P], "le_download_x": [P, pd, pi],
         "le_download_v": [P, pd], "le_download_types": [P, pi], "le_download_topology": [P, pi, pi, pi, pi, pi],
         "le_download_neighlist": [P, I, C.POINTER(I64), pi, C.POINTER(I64)],
         "le_download_bondlist": [P, pi, C.POINTER(I64)], "le_thermo_count": [P],
@@ -274,6 +274,12 @@ class Engine:
         t = Thermo()
         self._ck(self.lib.le_compute_forces(self._h, _pd(f), C.byref(t)))
         return f, t.as_dict()
+
+    def compute_forces_plain(self):
+        """forces from the plain instantiation of the step kernel (the one production timesteps run)"""
+        f = np.zeros((self.natoms, 3))
+        self._ck(self.lib.le_compute_forces_plain(self._h, _pd(f)))
+        return f
 
     # ---- results ----
     @property

@@ -25,6 +25,9 @@ def has_gpu():
     return _has_gpu()
 
 
-def pytest_collection_modifyitems(config, items):
-    # a `-m gpu` run on a box without a device must fail loudly rather than silently pass or skip
-    pass
+def pytest_runtest_setup(item):
+    """A gpu-marked test on a box without a CUDA device must fail loudly rather than pass or skip (the product has no
+    CPU fallback to test): `pytest -m gpu` on a CPU-only box is an error report, `pytest -m "not gpu"` is the CPU suite."""
+    if item.get_closest_marker("gpu") and not _has_gpu():
+        pytest.fail("this test needs a CUDA device and none is visible (torch.cuda.is_available() is False); "
+                    "run `pytest -m 'not gpu'` on a CPU-only box", pytrace=False)

@@ -127,8 +127,6 @@ def test_deck_dump_custom(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="`velocity all create` in le_deck was wired after the last GPU call of round 1 (the host function is checked "
-                          "against the reference on the CPU, tests/test_velocity_create.py): first GPU run pending", strict=False)
 def test_deck_velocity_create(tmp_path):
     """velocity all create 1.0 seed before `run 0`: the temperature of step 0 is the requested one, as in the reference"""
     z = np.load(os.path.join(GOLD, "bench_chain.npz"))
@@ -143,7 +141,6 @@ def test_deck_velocity_create(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="thermo_style custom in le_deck was added after the last GPU call of round 1: first GPU run pending", strict=False)
 def test_deck_thermo_style_custom(tmp_path):
     """thermo_style custom step temp pe ke etotal bonds atoms vol: the reference's column titles and consistent values"""
     z = np.load(os.path.join(GOLD, "bench_chain.npz"))
@@ -164,8 +161,6 @@ def test_deck_thermo_style_custom(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="compute property/local + dump local in le_deck were added after the last GPU call of round 1 (the bond order "
-                          "is checked against the reference on the CPU, tests/test_property_local.py): first GPU run pending", strict=False)
 def test_deck_dump_local_bonds(tmp_path):
     """compute b all property/local batom1 batom2 btype + dump ... local: one entry per bond in the reference's format"""
     z = np.load(os.path.join(GOLD, "bench_chain.npz"))

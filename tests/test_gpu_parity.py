@@ -126,8 +126,6 @@ def test_le_replay_live_reference():
     assert not problems, "USER-LE replay mismatches: %s" % problems[:5]
 
 
-@pytest.mark.xfail(reason="added after the last GPU call of round 1 (the oracle restatement passes these traces on the CPU, "
-                          "tests/test_oracle.py): first GPU run pending", strict=False)
 @pytest.mark.parametrize("name", ["closed", "open"])
 def test_le_replay_live_reference_barrier_variants(name):
     """fully closed (p_through 0, CTCF every 100 beads) and fully transparent (p_through 1) barriers, dense event cadence"""
