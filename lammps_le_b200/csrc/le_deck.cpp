@@ -311,7 +311,18 @@ void write_dumps(Deck &d, long long step) {
       // dump local (src/dump_local.cpp:254-282, :380-395): one entry per bond, values with "%g " / the index with "%d "
       if (nrows < 0) {
         std::vector<int> nb(n), bt((size_t)n * d.bpa), ba((size_t)n * d.bpa);
-        ck(d, le_download_topology(d.ctx, nb.data(), bt.data(), ba.data(), nullptr, nullptr));
+        if (d.newton_bond) {
+          // newton_bond on: the reference stores a bond with the FIRST atom of its data-file line only
+          // (Atom::data_bonds, src/atom.cpp:1261-1278); the engine's tables hold every bond on both atoms, so the
+          // reference's per-atom tables are rebuilt from the file's lines (static topology: the USER-LE fixes need newton_bond off)
+          std::fill(nb.begin(), nb.end(), 0);
+          for (int k = 0; k < d.nbonds; k++) {
+            const int a = d.b1[k] - 1;
+            if (nb[a] < d.bpa) { bt[(size_t)a * d.bpa + nb[a]] = d.btype[k]; ba[(size_t)a * d.bpa + nb[a]] = d.b2[k]; nb[a]++; }
+          }
+        } else {
+          ck(d, le_download_topology(d.ctx, nb.data(), bt.data(), ba.data(), nullptr, nullptr));
+        }
         nrows = le_host_property_local_bonds(n, d.bpa, nb.data(), bt.data(), ba.data(), d.newton_bond, nullptr);
         rows.resize((size_t)std::max(nrows, 1LL) * 3);
         le_host_property_local_bonds(n, d.bpa, nb.data(), bt.data(), ba.data(), d.newton_bond, rows.data());

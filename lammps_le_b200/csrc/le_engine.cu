@@ -67,6 +67,7 @@ struct le_ctx {
   int64_t ntimestep;
   int cur;              // position buffer holding the current coordinates
   bool atoms_loaded, topo_loaded, lists_valid, params_dirty;
+  int scan_items;       // cells per thread of k_scan_cells
   bool topo_dirty;      // the tag-ordered topology tables changed since the last k_topo_pack
   Dev d;
   Params P;
@@ -497,7 +498,16 @@ static int setup_cells(le_ctx *c, double cutneighmax) {
     else { d.cell_abs[k] = 1; d.cell_span[k] = nc[k]; }
   }
   d.ncells = d.nlx * nc[1] * nc[2] + 3;
-  d.nscanblocks = ((d.nlx - 2 * d.halo) * nc[1] * nc[2] + SCAN_TILE - 1) / SCAN_TILE;
+  {
+    // scan tiles: SCAN_BLOCK threads x `scan_items` consecutive cells each, sized so that all tiles are resident at once
+    // (two 1024-thread blocks per SM)
+    const long long ncell_own = (long long)(d.nlx - 2 * d.halo) * nc[1] * nc[2];
+    const long long slots = (long long)std::max(c->sm_count, 1) * 2;
+    long long items = (ncell_own + slots * SCAN_BLOCK - 1) / (slots * SCAN_BLOCK);
+    items = std::min<long long>(std::max<long long>(items, 1), SCAN_MAXITEMS);
+    c->scan_items = (int)items;
+    d.nscanblocks = (int)((ncell_own + items * SCAN_BLOCK - 1) / (items * SCAN_BLOCK));
+  }
   return LE_OK;
 }
 
@@ -1044,7 +1054,7 @@ static int build_queue_depth(const le_ctx *c) {
   double cn = 0.0;
   for (int k = 0; k < c->ntypes * c->ntypes; k++) cn = std::max(cn, sqrt(c->P.cutneighsq[k]));
   const double expect = (double)c->N / vol * 4.18879 * cn * cn * cn + 3.0;
-  return expect > 9.0 ? 28 : 16;
+  return expect > 9.0 ? 40 : 16;
 }
 
 // the tag-ordered topology tables -> the 64-byte digests the list build reads
@@ -1064,7 +1074,7 @@ static void enqueue_rebuild(le_ctx *c, bool direct) {
     LAUNCH(c, k_rb_post_inbox, 1, 1, d, c->rb);
     LAUNCH(c, k_inbox, grid_for(2 * d.inbox_cap, 256), 256, d, c->rb);
   }
-  LAUNCH(c, k_scan_cells, d.nscanblocks, SCAN_BLOCK, d);
+  LAUNCH(c, k_scan_cells, d.nscanblocks, SCAN_BLOCK, d, c->scan_items);
   LAUNCH(c, k_cell_scatter, grid_for(nslots, 256), 256, d);
   LAUNCH(c, k_permute, grid_for(nslots, 256), 256, d);
   if (dd) {
@@ -1074,8 +1084,9 @@ static void enqueue_rebuild(le_ctx *c, bool direct) {
   }
   {
     const int g = grid_for(nslots, BUILD_THREADS);
-    if (build_queue_depth(c) > 16) LAUNCH(c, (k_build3<28, 4>), g, BUILD_THREADS, d);
-    else LAUNCH(c, (k_build3<16, 8>), g, BUILD_THREADS, d);
+    const bool uni = c->P.pair_uniform != 0;
+    if (build_queue_depth(c) > 16) { if (uni) LAUNCH(c, (k_build3<40, 4, 1>), g, BUILD_THREADS, d); else LAUNCH(c, (k_build3<40, 4, 0>), g, BUILD_THREADS, d); }
+    else { if (uni) LAUNCH(c, (k_build3<16, 8, 1>), g, BUILD_THREADS, d); else LAUNCH(c, (k_build3<16, 8, 0>), g, BUILD_THREADS, d); }
   }
   if (direct) { LAUNCH(c, k_after_build, 1, 1, d); c->direct_builds++; }
 }

@@ -1,7 +1,8 @@
 // le_sort.cuh -- rebuild, part 1b: the cell sort of the owned atoms (after k_cell_count / k_inbox of le_md.cuh).
 //
-//   k_scan_cells    exclusive scan of the per-cell counts -> cell_start, ONE launch (decoupled look-back over
-//                   4096-cell tiles handed out by ticket; the round-1 engine took three launches and 20 us for it)
+//   k_scan_cells    exclusive scan of the per-cell counts -> cell_start, ONE launch (4096-cell tiles handed out by
+//                   ticket, every tile sums the published sums of its predecessors; the round-1 engine took three
+//                   launches and 20 us for it)
 //   k_cell_scatter  old slot i -> record {i, tag, cell start, cell end} at cell_start[c] + (arrival rank in the cell)
 //   k_permute       record k -> final slot = cell start + rank of its TAG among the cell's members (the local order must
 //                   not depend on the order in which the atomics of k_cell_count happened to be served), and the move
@@ -12,8 +13,7 @@
 #include "le_common.cuh"
 
 #define SCAN_BLOCK 1024
-#define SCAN_ITEMS 4                          // consecutive cells per thread
-#define SCAN_TILE (SCAN_BLOCK * SCAN_ITEMS)
+#define SCAN_MAXITEMS 16                      // consecutive cells per thread: chosen by the host so that all tiles run in ONE wave
 
 __device__ __forceinline__ int own_cell_first(const Dev &d) { return cell_slot(d, d.halo, 0, 0); }
 __device__ __forceinline__ int own_cell_count(const Dev &d) { return (d.nlx - 2 * d.halo) * d.ncell[1] * d.ncell[2]; }
@@ -46,11 +46,8 @@ __device__ __forceinline__ int block_excl_scan(int v, int *total) {
   return base + inc - v;
 }
 
-// state word of one scan tile: epoch << 34 | flag << 32 | value; flag 1 = the tile's own sum, 2 = inclusive prefix.
-// The epoch (rebuilds so far) makes the words of earlier rebuilds read as "not there yet": nothing is reset.
-__device__ __forceinline__ unsigned long long scan_word(unsigned epoch, unsigned flag, unsigned value) {
-  return ((unsigned long long)(epoch & 0x3fffffffu) << 34) | ((unsigned long long)flag << 32) | value;
-}
+// state word of one scan tile: epoch << 32 | the tile's own sum.  The epoch (launches of this kernel so far) makes the
+// words of earlier rebuilds read as "not there yet": nothing is reset between rebuilds.
 __device__ __forceinline__ unsigned long long ld_gpu(const unsigned long long *p) {
   unsigned long long v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -60,53 +57,43 @@ __device__ __forceinline__ void st_gpu(unsigned long long *p, unsigned long long
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_cells(Dev d) {
-  __shared__ int s_tile, s_excl;
+// One launch, one wave: every block (a tile of SCAN_BLOCK * items cells, handed out by ticket so that a block only ever
+// waits for tiles that are already running) publishes the sum of its tile, then adds up the sums of ALL its
+// predecessors -- one thread per predecessor, one memory round trip -- instead of chaining inclusive prefixes from tile
+// to tile.  `items` is sized by the host so that the grid fits the GPU in a single wave (a second wave of a few blocks
+// doubled the kernel's duration).
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_cells(Dev d, int items) {
+  __shared__ int s_tile;
   __shared__ unsigned s_epoch;
   Ctrl *c = d.ctrl;
   if (threadIdx.x == 0) {
-    s_epoch = (unsigned)c->nbuilds_scan + 1u;               // read before this launch's last block bumps it
-    s_tile = (int)atomicAdd(&c->scan_ticket, 1u);           // tiles in the order the blocks really start: a block only
-  }                                                         // ever waits for tiles that are already running
+    s_epoch = c->nbuilds_scan + 1u;                         // read before this launch's last block bumps it
+    s_tile = (int)atomicAdd(&c->scan_ticket, 1u);
+  }
   __syncthreads();
   const int tile = s_tile;
   const unsigned epoch = s_epoch;
   const int n = own_cell_count(d), first = own_cell_first(d);
-  const int idx = (tile * SCAN_BLOCK + threadIdx.x) * SCAN_ITEMS;
-  int v[SCAN_ITEMS], tsum = 0;
+  const int idx = (tile * SCAN_BLOCK + threadIdx.x) * items;
+  int v[SCAN_MAXITEMS], tsum = 0;
 #pragma unroll
-  for (int q = 0; q < SCAN_ITEMS; q++) { v[q] = (idx + q < n) ? d.cell_count[first + idx + q] : 0; tsum += v[q]; }
+  for (int q = 0; q < SCAN_MAXITEMS; q++) { v[q] = (q < items && idx + q < n) ? d.cell_count[first + idx + q] : 0; tsum += v[q]; }
   int total;
   const int ex = block_excl_scan(tsum, &total);
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    if (lane == 0) st_gpu(&d.scan_state[tile], scan_word(epoch, tile == 0 ? 2u : 1u, (unsigned)total));
-    // look back over the predecessors, 32 at a time, nearest first
-    int excl = 0;
-    for (int p = tile - 1; p >= 0; p -= 32) {
-      const int t = p - lane;
-      unsigned long long w = scan_word(epoch, 2u, 0u);      // before tile 0: prefix 0
-      if (t >= 0) {
-        do { w = ld_gpu(&d.scan_state[t]); } while ((unsigned)(w >> 34) != (epoch & 0x3fffffffu) || ((w >> 32) & 3u) == 0u);
-      }
-      const unsigned full = __ballot_sync(0xffffffffu, ((w >> 32) & 3u) == 2u);
-      const int stop = full ? __ffs(full) - 1 : 31;         // nearest predecessor that already knows its prefix
-      int val = (lane <= stop) ? (int)(unsigned)w : 0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-      excl += val;
-      if (full) break;
-    }
-    if (lane == 0) {
-      if (tile > 0) st_gpu(&d.scan_state[tile], scan_word(epoch, 2u, (unsigned)(excl + total)));
-      s_excl = excl;
-    }
+  if (threadIdx.x == 0) st_gpu(&d.scan_state[tile], ((unsigned long long)epoch << 32) | (unsigned)total);
+  // the sums of the tiles before this one
+  int before = 0;
+  for (int p = threadIdx.x; p < tile; p += SCAN_BLOCK) {
+    unsigned long long w;
+    do { w = ld_gpu(&d.scan_state[p]); } while ((unsigned)(w >> 32) != epoch);
+    before += (int)(unsigned)w;
   }
-  __syncthreads();
-  int run = d.own0 + s_excl + ex;
+  int excl;
+  block_excl_scan(before, &excl);
+  int run = d.own0 + excl + ex;
 #pragma unroll
-  for (int q = 0; q < SCAN_ITEMS; q++)
-    if (idx + q < n) {
+  for (int q = 0; q < SCAN_MAXITEMS; q++)
+    if (q < items && idx + q < n) {
       d.cell_start[first + idx + q] = run;
       d.cell_count[first + idx + q] = 0;
       run += v[q];
@@ -114,8 +101,8 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_cells(Dev d) {
   if (threadIdx.x == 0) {
     if (tile == (int)gridDim.x - 1) {
       // the owned population after migration; the sentinel slot behind the owned region closes its last cell
-      c->nown = s_excl + total;
-      d.cell_start[first + n] = d.own0 + s_excl + total;
+      c->nown = excl + total;
+      d.cell_start[first + n] = d.own0 + excl + total;
     }
     __threadfence();
     if (atomicAdd(&c->scan_done, 1u) == gridDim.x - 1) { c->scan_done = 0; c->scan_ticket = 0; c->nbuilds_scan++; }

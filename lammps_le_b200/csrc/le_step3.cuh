@@ -11,9 +11,9 @@
 //   * PAIRS are evaluated pair-parallel: the tile's list is one flat run of (owner lane, neighbor slot) entries
 //     (k_build3), lane l takes entries l, l+32, ...: every lane busy whatever the spread of neighbor counts, the run is
 //     read as whole 128-byte lines (4 n_full bytes per atom instead of four ELL rows), the neighbor gathers of a round
-//     are 32 independent loads.  The WCA term is fp32 on exact fixed-point differences (listed pairs are never bonded
-//     under special_bonds 0 x x, so there is no FENE/WCA cancellation to protect); the lane parks its term in shared
-//     memory and the OWNER adds its terms in list order -- a fixed order, so results are reproducible run to run;
+//     are 32 independent loads.  The WCA term is fp64 on exact fixed-point differences (see pair3); the lane parks its
+//     term in shared memory and the OWNER adds its terms in list order -- a fixed order, so results are reproducible
+//     run to run;
 //   * BONDS stay lane-per-owner (two to three per bead, no spread) and fp64: FENE and its WCA core cancel to a tenth
 //     of their size;
 //   * the displacement test of Neighbor::check_distance reads pos_hold only for atoms whose accumulated path length
@@ -38,28 +38,31 @@ __device__ __forceinline__ double le_rcp2(double x) {   // 1/x to full double ac
 
 struct EvAcc { double evdwl, ebond, v[6], warn; };
 
-// WCA term of one list entry, fp32 (PairLJCut::compute, pair_lj_cut.cpp:102-118): force ON THE OWNER (position po) from
-// the neighbor pj.  A dead entry (beyond the run, or outside the cutoff) yields an exact zero.
+// WCA term of one list entry, fp64 (PairLJCut::compute, pair_lj_cut.cpp:102-118): force ON THE OWNER (position po) from
+// the neighbor pj, written to (tx, ty, tz).  A dead entry (beyond the run, or outside the cutoff) yields an exact zero.
+// fp32 pair terms were measured (round 2): 2.6 % faster, but the per-atom force error reaches 1.3e-5 of the rms force
+// in a dense melt (five r^-14 terms of 30..50 per atom against a net force of 15): the 1e-5 bar needs fp64 here, and
+// on this kernel -- bound by instruction issue, fp64 pipe at 10 % -- an fp64 instruction costs the same issue slot.
 template <int EV, int UNI>
-__device__ __forceinline__ float4 pair3(const int4 po, const int4 pj, unsigned e, bool live, float sx, float sy, float sz, int nt, EvAcc &A) {
-  const float dxf = __fmul_rn((float)(int)((unsigned)po.x - (unsigned)pj.x), sx);
-  const float dyf = __fmul_rn((float)(int)((unsigned)po.y - (unsigned)pj.y), sy);
-  const float dzf = __fmul_rn((float)(int)((unsigned)po.z - (unsigned)pj.z), sz);
-  const float rsqf = __fmaf_rn(dzf, dzf, __fmaf_rn(dxf, dxf, __fmul_rn(dyf, dyf)));
+__device__ __forceinline__ void pair3(double &tx, double &ty, double &tz, const int4 po, const int4 pj, unsigned e, bool live, int nt, EvAcc &A) {
+  const double dy = __dmul_rn((double)((int)((unsigned)po.y - (unsigned)pj.y)), c_P.scale[1]);
+  const double dx = __dmul_rn((double)((int)((unsigned)po.x - (unsigned)pj.x)), c_P.scale[0]);
+  const double dz = __dmul_rn((double)((int)((unsigned)po.z - (unsigned)pj.z)), c_P.scale[2]);
+  const double rsq = __fma_rn(dz, dz, __fma_rn(dx, dx, __dmul_rn(dy, dy)));
   const int tp = UNI ? 0 : (po.w & 7) * nt + (pj.w & 7);
-  const bool in = live && rsqf < c_P.cutsq[tp];
-  const float r2inv = __frcp_rn(in ? rsqf : 1.0f);
-  const float r6inv = __fmul_rn(__fmul_rn(r2inv, r2inv), r2inv);
-  const float factor = UNI ? 1.0f : c_P.special_lj[e >> 30];
-  float fpair = __fmul_rn(__fmul_rn(r6inv, __fmaf_rn(c_P.lj1[tp], r6inv, -c_P.lj2[tp])), r2inv);
+  const bool in = live && rsq < c_P.cutsq_d[tp];
+  const double r2inv = le_rcp2(in ? rsq : 1.0);
+  const double r6inv = __dmul_rn(r2inv, __dmul_rn(r2inv, r2inv));
+  double fpair = __dmul_rn(r2inv, __dmul_rn(r6inv, __fma_rn(r6inv, c_P.lj1_d[tp], -c_P.lj2_d[tp])));
+  const double factor = UNI ? 1.0 : (double)c_P.special_lj[e >> 30];
   if (!UNI) fpair *= factor;
-  if (!in) fpair = 0.f;
+  if (!in) fpair = 0.0;
   if (EV && in) {
-    A.evdwl += (double)(factor * (r6inv * (c_P.lj3[tp] * r6inv - c_P.lj4[tp]) - c_P.offset[tp]));
-    A.v[0] += (double)(dxf * dxf * fpair); A.v[1] += (double)(dyf * dyf * fpair); A.v[2] += (double)(dzf * dzf * fpair);
-    A.v[3] += (double)(dxf * dyf * fpair); A.v[4] += (double)(dxf * dzf * fpair); A.v[5] += (double)(dyf * dzf * fpair);
+    A.evdwl += factor * (r6inv * (c_P.lj3_d[tp] * r6inv - c_P.lj4_d[tp]) - c_P.offset_d[tp]);
+    A.v[0] += dx * dx * fpair; A.v[1] += dy * dy * fpair; A.v[2] += dz * dz * fpair;
+    A.v[3] += dx * dy * fpair; A.v[4] += dx * dz * fpair; A.v[5] += dy * dz * fpair;
   }
-  return make_float4(__fmul_rn(dxf, fpair), __fmul_rn(dyf, fpair), __fmul_rn(dzf, fpair), 0.f);
+  tx = __dmul_rn(dx, fpair); ty = __dmul_rn(dy, fpair); tz = __dmul_rn(dz, fpair);
 }
 
 // harmonic bond (bond_harmonic.cpp:71-80), kept out of line: sqrt and a division in fp64 are long code and
@@ -175,7 +178,7 @@ __device__ __forceinline__ int step3_tile_of(const Step3Order &o, int g) {
 template <int EV, int DD, int UNI>
 __global__ void __launch_bounds__(STEP3_THREADS, EV ? 2 : 4) k_step3(Dev d, StepArgs a) {
   __shared__ int4 s_pos[STEP3_WARPS][TILE];
-  __shared__ float4 s_f[STEP3_WARPS][STEP3_CH * TILE];
+  __shared__ double s_fx[STEP3_WARPS][STEP3_CH * TILE], s_fy[STEP3_WARPS][STEP3_CH * TILE], s_fz[STEP3_WARPS][STEP3_CH * TILE];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cap = d.cap;
   Ctrl *__restrict__ ctrl = d.ctrl;
@@ -233,21 +236,22 @@ __global__ void __launch_bounds__(STEP3_THREADS, EV ? 2 : 4) k_step3(Dev d, Step
     const int4 pb2 = __ldg(&posr[2 < nb ? (int)(eb2 & BOND_IDX_MASK) : i]);
 
     // ---- pairs: STEP3_CH rounds per pass; the owner adds its terms in list order after each pass ----
-    float px = 0.f, py = 0.f, pz = 0.f;
+    double fx = 0.0, fy = 0.0, fz = 0.0;
+    double *__restrict__ sfx = s_fx[wib], *__restrict__ sfy = s_fy[wib], *__restrict__ sfz = s_fz[wib];
     {
-      s_f[wib][lane] = pair3<EV, UNI>(s_pos[wib][(e0 >> NEIGH_IDX_BITS) & 31], pj0, e0, l0, sx, sy, sz, nt, A);
-      s_f[wib][TILE + lane] = pair3<EV, UNI>(s_pos[wib][(e1 >> NEIGH_IDX_BITS) & 31], pj1, e1, l1, sx, sy, sz, nt, A);
+      pair3<EV, UNI>(sfx[lane], sfy[lane], sfz[lane], s_pos[wib][(e0 >> NEIGH_IDX_BITS) & 31], pj0, e0, l0, nt, A);
+      pair3<EV, UNI>(sfx[TILE + lane], sfy[TILE + lane], sfz[TILE + lane], s_pos[wib][(e1 >> NEIGH_IDX_BITS) & 31], pj1, e1, l1, nt, A);
       if (cnt > 2 * TILE) {                                   // warp-uniform
         const bool l2 = (unsigned)(2 * TILE + lane) < cnt, l3 = (unsigned)(3 * TILE + lane) < cnt;
         const unsigned e2 = l2 ? __ldg(&run[2 * TILE + lane]) : 0u, e3 = l3 ? __ldg(&run[3 * TILE + lane]) : 0u;
         const int4 pj2 = __ldg(&posr[l2 ? (int)(e2 & NEIGH_IDX_MASK) : i]);
         const int4 pj3 = __ldg(&posr[l3 ? (int)(e3 & NEIGH_IDX_MASK) : i]);
-        s_f[wib][2 * TILE + lane] = pair3<EV, UNI>(s_pos[wib][(e2 >> NEIGH_IDX_BITS) & 31], pj2, e2, l2, sx, sy, sz, nt, A);
-        s_f[wib][3 * TILE + lane] = pair3<EV, UNI>(s_pos[wib][(e3 >> NEIGH_IDX_BITS) & 31], pj3, e3, l3, sx, sy, sz, nt, A);
+        pair3<EV, UNI>(sfx[2 * TILE + lane], sfy[2 * TILE + lane], sfz[2 * TILE + lane], s_pos[wib][(e2 >> NEIGH_IDX_BITS) & 31], pj2, e2, l2, nt, A);
+        pair3<EV, UNI>(sfx[3 * TILE + lane], sfy[3 * TILE + lane], sfz[3 * TILE + lane], s_pos[wib][(e3 >> NEIGH_IDX_BITS) & 31], pj3, e3, l3, nt, A);
       }
       __syncwarp();
       const int hi = min(off + nn, STEP3_CH * TILE);
-      for (int k = off; k < hi; k++) { const float4 f = s_f[wib][k]; px += f.x; py += f.y; pz += f.z; }
+      for (int k = off; k < hi; k++) { fx += sfx[k]; fy += sfy[k]; fz += sfz[k]; }
       __syncwarp();
     }
 #pragma unroll 1
@@ -259,15 +263,14 @@ __global__ void __launch_bounds__(STEP3_THREADS, EV ? 2 : 4) k_step3(Dev d, Step
       for (int r = 0; r < STEP3_CH; r++) pj[r] = __ldg(&posr[lv[r] ? (int)(e[r] & NEIGH_IDX_MASK) : i]);
 #pragma unroll
       for (int r = 0; r < STEP3_CH; r++)
-        s_f[wib][r * TILE + lane] = pair3<EV, UNI>(s_pos[wib][(e[r] >> NEIGH_IDX_BITS) & 31], pj[r], e[r], lv[r], sx, sy, sz, nt, A);
+        pair3<EV, UNI>(sfx[r * TILE + lane], sfy[r * TILE + lane], sfz[r * TILE + lane], s_pos[wib][(e[r] >> NEIGH_IDX_BITS) & 31], pj[r], e[r], lv[r], nt, A);
       __syncwarp();
       const int lo = max(off, (int)base), hi = min(off + nn, (int)base + STEP3_CH * TILE);
-      for (int k = lo; k < hi; k++) { const float4 f = s_f[wib][k - (int)base]; px += f.x; py += f.y; pz += f.z; }
+      for (int k = lo; k < hi; k++) { fx += sfx[k - (int)base]; fy += sfy[k - (int)base]; fz += sfz[k - (int)base]; }
       __syncwarp();
     }
 
     // ---- bonds, fp64, lane per owner ----
-    double fx = (double)px, fy = (double)py, fz = (double)pz;
     if (0 < nb) bond3<EV>(fx, fy, fz, ctrl, pi, pb0, eb0, tag, A);
     if (1 < nb) bond3<EV>(fx, fy, fz, ctrl, pi, pb1, eb1, tag, A);
     if (2 < nb) bond3<EV>(fx, fy, fz, ctrl, pi, pb2, eb2, tag, A);
