@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(STEP3_THREADS, EV ? 2 : 4) k_step3(Dev d, Step
     float4 vi = d.vel[i];
     const unsigned cnt = __ldg(&d.tile_cnt[tile]);
     const unsigned *__restrict__ run = d.nbr + (size_t)tile * tcap;
-    const unsigned e0 = __ldg(&run[lane]), e1 = __ldg(&run[TILE + lane]);      // tcap >= 128
+    const unsigned e0 = __ldg(&run[lane]), e1 = __ldg(&run[TILE + lane]), e2 = __ldg(&run[2 * TILE + lane]);   // tcap >= 128
     const unsigned eb0 = __ldg(&bondrow[i]);
     const unsigned eb1 = d.bpa > 1 ? __ldg(&bondrow[(size_t)cap + i]) : 0u;
     const unsigned eb2 = d.bpa > 2 ? __ldg(&bondrow[(size_t)2 * cap + i]) : 0u;
@@ -228,9 +228,10 @@ __global__ void __launch_bounds__(STEP3_THREADS, EV ? 2 : 4) k_step3(Dev d, Step
     const int off = inc - nn;
     __syncwarp();
     // ---- level 2: the gathers of the first two rounds and of the bond partners ----
-    const bool l0 = (unsigned)lane < cnt, l1 = (unsigned)(TILE + lane) < cnt;
+    const bool l0 = (unsigned)lane < cnt, l1 = (unsigned)(TILE + lane) < cnt, l2 = (unsigned)(2 * TILE + lane) < cnt;
     const int4 pj0 = __ldg(&posr[l0 ? (int)(e0 & NEIGH_IDX_MASK) : i]);
     const int4 pj1 = __ldg(&posr[l1 ? (int)(e1 & NEIGH_IDX_MASK) : i]);
+    const int4 pj2 = __ldg(&posr[l2 ? (int)(e2 & NEIGH_IDX_MASK) : i]);
     const int4 pb0 = __ldg(&posr[0 < nb ? (int)(eb0 & BOND_IDX_MASK) : i]);
     const int4 pb1 = __ldg(&posr[1 < nb ? (int)(eb1 & BOND_IDX_MASK) : i]);
     const int4 pb2 = __ldg(&posr[2 < nb ? (int)(eb2 & BOND_IDX_MASK) : i]);
@@ -241,16 +242,17 @@ __global__ void __launch_bounds__(STEP3_THREADS, EV ? 2 : 4) k_step3(Dev d, Step
     {
       pair3<EV, UNI>(sfx[lane], sfy[lane], sfz[lane], s_pos[wib][(e0 >> NEIGH_IDX_BITS) & 31], pj0, e0, l0, nt, A);
       pair3<EV, UNI>(sfx[TILE + lane], sfy[TILE + lane], sfz[TILE + lane], s_pos[wib][(e1 >> NEIGH_IDX_BITS) & 31], pj1, e1, l1, nt, A);
-      if (cnt > 2 * TILE) {                                   // warp-uniform
-        const bool l2 = (unsigned)(2 * TILE + lane) < cnt, l3 = (unsigned)(3 * TILE + lane) < cnt;
-        const unsigned e2 = l2 ? __ldg(&run[2 * TILE + lane]) : 0u, e3 = l3 ? __ldg(&run[3 * TILE + lane]) : 0u;
-        const int4 pj2 = __ldg(&posr[l2 ? (int)(e2 & NEIGH_IDX_MASK) : i]);
-        const int4 pj3 = __ldg(&posr[l3 ? (int)(e3 & NEIGH_IDX_MASK) : i]);
+      if (cnt > 2 * TILE)                                     // warp-uniform (the third round's loads were issued with the first two)
         pair3<EV, UNI>(sfx[2 * TILE + lane], sfy[2 * TILE + lane], sfz[2 * TILE + lane], s_pos[wib][(e2 >> NEIGH_IDX_BITS) & 31], pj2, e2, l2, nt, A);
+      if (cnt > 3 * TILE) {
+        const bool l3 = (unsigned)(3 * TILE + lane) < cnt;
+        const unsigned e3 = l3 ? __ldg(&run[3 * TILE + lane]) : 0u;
+        const int4 pj3 = __ldg(&posr[l3 ? (int)(e3 & NEIGH_IDX_MASK) : i]);
         pair3<EV, UNI>(sfx[3 * TILE + lane], sfy[3 * TILE + lane], sfz[3 * TILE + lane], s_pos[wib][(e3 >> NEIGH_IDX_BITS) & 31], pj3, e3, l3, nt, A);
       }
       __syncwarp();
       const int hi = min(off + nn, STEP3_CH * TILE);
+#pragma unroll 1
       for (int k = off; k < hi; k++) { fx += sfx[k]; fy += sfy[k]; fz += sfz[k]; }
       __syncwarp();
     }
