@@ -12,8 +12,8 @@ One bench "step" = `--md-steps` MD timesteps (default 500 = one full USER-LE cyc
 value      whole-job atom-steps/s with all state resident in HBM when the timed region starts
 e2e        same metric through the C ABI with HOST buffers: every step uploads positions+velocities from
            pinned host memory, runs, and downloads positions
-roofline   fused step kernel (k_step2p, le_step2.cuh): algorithmic bytes (72.1 + 4 nbar per atom-step, nbar measured)
-           / CUDA-event time of the step loop, against MEASURED_PEAKS.json hbm_gbs
+roofline   fused step kernel (k_step3, le_step3.cuh): algorithmic bytes (72.1 + 4 nbar per atom-step, nbar measured)
+           / its live CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
 cpu_baseline  the compiled reference (oracle/_ref, threaded USER-OMP build when present, up to 16 host threads) on a
               bounded sample of the same workload
 """
@@ -102,7 +102,11 @@ REF_LE_LINES = ["fix loop all extrusion 500 1 2 3 0.5 2 4",
                 "fix unloading all ex_unload 100 2 0.5 prob 0.05 456456"]
 
 
-NCU_TRAFFIC_PER_LAUNCH = 99.2e6   # bytes: 87.8 MB read + 11.4 MB written per k_step2p launch at 1M beads (ncu --set full, profiles/r01_ncu_full_kstep2p.txt)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_step3<0,0,1> launch at 1M beads from the committed ncu --set full
+# capture (profiles/r02_ncu_full_kstep3_kbuild3.txt): an OFFLINE figure of this kernel on this workload (ncu cannot run inside
+# the bench; it replays every launch with a flushed L2, so this is cold-cache traffic).  Printed only for the configuration
+# it was captured on (1 GPU, 1M beads, this kernel), null otherwise.
+NCU_TRAFFIC = {"kernel": "k_step3<0,0,1>", "bytes": 59.5e6, "source": "profiles/r02_ncu_full_kstep3_kbuild3.txt"}
 LE_HALO = 6.0   # ghost shell for USER-LE on several GPUs: longest extruder bond (FENE R0 = 4) + one backbone bond (1.5) + skin (4 cell layers here)
 
 
@@ -118,10 +122,28 @@ def prepared_engine(n_beads, n_ext, seed, device, relax_steps, dd=None):
     return s, e
 
 
+def reference_deck_tail(md_steps_per_seg, nseg_warm, nseg_timed):
+    """fixes + run segments of the reference deck; the window is placed so that the timed segments hold a `fix extrusion`
+    event (step 501) next to the ex_unload / ex_load events (502/503, 602/603, ...), like one bench step of our arm"""
+    start = 490 - nseg_warm * md_steps_per_seg
+    deck = ["reset_timestep %d" % max(start, 0), "fix 1 all nve", "fix 2 all langevin 1.0 1.0 1.0 904297"] + REF_LE_LINES
+    deck += ["thermo_style custom step temp epair emol bonds", "thermo 1000000", "timestep 0.005"]
+    deck += ["run %d" % md_steps_per_seg] * (nseg_warm + nseg_timed)
+    return deck
+
+
+def parse_segments(out, n, nseg_skip, nseg_timed):
+    import re
+    loops = [(float(a), int(b)) for a, b in re.findall(r"Loop time of ([0-9.eE+-]+) on \d+ procs for (\d+) steps", out)]
+    timed = loops[-nseg_timed:] if nseg_timed else loops[nseg_skip:]
+    tsum = sum(t for t, _ in timed)
+    steps = sum(k for _, k in timed)
+    return n * steps / tsum, tsum / max(len(timed), 1), steps
+
+
 def reference_rate(s, x, image, v, topo, md_steps_per_seg, nseg_warm, nseg_timed, workdir=None, threads=1):
-    """atom-steps/s of oracle/_ref/lmp_ref on the same (relaxed) state; window placed so that one ex_unload
-    and one ex_load event fall inside the timed segments and no fix extrusion event does.
-    threads > 1: the threaded build of the reference (oracle/_ref/omp, USER-OMP styles via `-sf omp`)."""
+    """atom-steps/s of the compiled reference (oracle/_ref) started from a GIVEN state (the cpu_baseline leg of our arm:
+    the same relaxed state the GPU is running).  threads > 1: the threaded build (oracle/_ref/omp, USER-OMP styles)."""
     from oracle import refio
     wd = workdir or tempfile.mkdtemp(prefix="le_bench_ref_")
     n = len(s["types"])
@@ -136,20 +158,32 @@ def reference_rate(s, x, image, v, topo, md_steps_per_seg, nseg_warm, nseg_timed
     rows = np.asarray(rows)
     s2["bonds"] = (rows[:, 0].astype(np.int32), rows[:, 1].astype(np.int32), rows[:, 2].astype(np.int32))
     refio.write_data_file(os.path.join(wd, "data.le"), s2)
-    deck = refio.deck_header(s2, "data.le", sort=True)
-    start = 100 - nseg_warm * md_steps_per_seg
-    deck += ["reset_timestep %d" % max(start, 0), "fix 1 all nve", "fix 2 all langevin 1.0 1.0 1.0 904297"] + REF_LE_LINES
-    deck += ["thermo_style custom step temp epair emol bonds", "thermo 1000000", "timestep 0.005"]
-    deck += ["run %d" % md_steps_per_seg] * (nseg_warm + nseg_timed)
+    deck = refio.deck_header(s2, "data.le", sort=True) + reference_deck_tail(md_steps_per_seg, nseg_warm, nseg_timed)
     t0 = time.time()
     out, _ = refio.run_reference(deck, workdir=wd, harness=False, timeout=3000, threads=threads)
     wall = time.time() - t0
-    import re
-    loops = [(float(a), int(b)) for a, b in re.findall(r"Loop time of ([0-9.eE+-]+) on \d+ procs for (\d+) steps", out)]
-    timed = loops[nseg_warm:]
-    tsum = sum(t for t, _ in timed)
-    steps = sum(k for _, k in timed)
-    return n * steps / tsum, tsum / max(len(timed), 1), wall, steps
+    rate, t_seg, steps = parse_segments(out, n, nseg_warm, nseg_timed)
+    return rate, t_seg, wall, steps
+
+
+def reference_rate_own_start(s, md_steps_per_seg, nseg_warm, nseg_timed, relax_steps, workdir=None, threads=1):
+    """the reference arm proper: generator output -> the reference's OWN relaxation (minimize, then a push-off run with
+    fix nve/limit + fix langevin) -> the timed segments, all inside one lmp_ref process; nothing of the CUDA engine is
+    loaded or run"""
+    from oracle import refio
+    wd = workdir or tempfile.mkdtemp(prefix="le_bench_ref_")
+    n = len(s["types"])
+    refio.write_data_file(os.path.join(wd, "data.le"), s)
+    deck = refio.deck_header(s, "data.le", sort=True)
+    deck += ["thermo 1000000", "minimize 1e-4 1e-6 60 600", "reset_timestep 0", "velocity all create 1.0 12345",
+             "fix r1 all nve/limit 0.05", "fix r2 all langevin 1.0 1.0 1.0 4711", "timestep 0.005", "run %d" % relax_steps,
+             "unfix r1", "unfix r2"]
+    deck += reference_deck_tail(md_steps_per_seg, nseg_warm, nseg_timed)
+    t0 = time.time()
+    out, _ = refio.run_reference(deck, workdir=wd, harness=False, timeout=3000, threads=threads)
+    wall = time.time() - t0
+    rate, t_seg, steps = parse_segments(out, n, 0, nseg_timed)
+    return rate, t_seg, wall, steps
 
 
 def reference_threads():
@@ -211,7 +245,7 @@ def run_ours(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     t_gpu, t_wall = float(tmax[0]), float(tmax[1])
     total_atom_steps = world * n_beads * md * args.steps
-    value = total_atom_steps / t_gpu
+    value = total_atom_steps / t_wall          # wall clock between the two barriers (max over ranks); t_gpu = the engines' own CUDA-event time
 
     # ---- live duration of the dominant kernel: a short run with direct launches and CUDA events around k_step<0>
     # on the engine's own stream (steps without USER-LE event) ----
@@ -259,12 +293,12 @@ def run_ours(args):
     bytes_step = 72.1 + 4.0 * nbar_half                      # SURVEY.md 8(d) algorithmic bytes per atom-step
     bytes_amort = bytes_step + (40.0 + 4.0 * nbar_half) / kint
     peak, how = measured_peak_gbs()
-    whole_step = bytes_amort * n_beads * steps_timed / t_gpu / 1e9        # per GPU, everything amortised (rebuilds, USER-LE)
+    whole_step = bytes_amort * n_beads * steps_timed / t_wall / 1e9       # per GPU, everything amortised (rebuilds, USER-LE)
     achieved = bytes_step * n_beads / (kstep_us * 1e-6) / 1e9             # the step kernel alone: algorithmic bytes / its duration
     line = {
         "metric": "atom-steps/s", "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t_gpu / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32 pair math / f64 accumulation / 32-bit fixed-point positions", "data": "synthetic",
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_wall / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 pair + bond terms on exact 32-bit fixed-point differences / f32 thermostat + integration", "data": "synthetic",
         "config": {"workload": WORKLOAD if n_beads == 1000000 else "same model, %d beads, %d extruders" % (n_beads, n_ext),
                    "beads_per_gpu": n_beads, "md_steps_per_step": md, "nbar_half": nbar_half, "nbar_full": nbar_full,
                    "steps_per_rebuild": kint, "l2_note": "working set (%.0f MB per GPU) vs 126 MB L2: inputs %s L2" % (
@@ -276,12 +310,14 @@ def run_ours(args):
         "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_TRAFFIC_PER_LAUNCH if n_beads == 1000000 else None, "peak_source": how,
+                     "traffic": NCU_TRAFFIC["bytes"] if (n_beads == 1000000 and world == 1 and Engine.step_kernel_name(e) == NCU_TRAFFIC["kernel"]) else None,
+                     "peak_source": how,
                      "kernel": Engine.step_kernel_name(e), "kernel_us": kstep_us, "bytes_per_atom_step": bytes_step,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_step2p<0,256,0,0> launch, ncu --set full, profiles/r01_ncu_full_kstep2p.txt",
+                     "traffic_source": "offline: dram__bytes_read.sum + dram__bytes_write.sum of one %s launch under ncu --set full (flushed L2), %s; null when the run is not that configuration" % (NCU_TRAFFIC["kernel"], NCU_TRAFFIC["source"]),
                      "whole_step": {"achieved": whole_step, "frac": whole_step / peak, "bytes_per_atom_step": bytes_amort,
                                     "note": "72.1 + 4 nbar + (40 + 4 nbar)/K bytes per atom-step over the whole timed loop (rebuilds and USER-LE included)"}},
-        "wall_s": t_wall, "user_le_ms_per_md_step": le_ms / steps_timed,
+        "wall_s": t_wall, "gpu_event_s": t_gpu, "user_le_ms_per_md_step": le_ms / steps_timed,
+        "e2e_note": "one bench step = %d MD timesteps in ONE le_run call; the e2e copies (le_upload_owned / le_download_owned of all owned atoms, pinned host memory) happen once per bench step, i.e. once per %d MD steps" % (md, md),
         "le_events": {"shifts": st1["extrusion_shifts"] - st0["extrusion_shifts"], "loads": st1["loads"] - st0["loads"],
                       "unloads": st1["unloads"] - st0["unloads"]},
     }
@@ -297,7 +333,7 @@ def run_ours(args):
                 rate, _, wall_ref, nst = reference_rate(s, xo, im, e.velocities(), topo, seg, 1, 5, threads=nthr)
                 line["cpu_baseline"] = {"value": rate, "unit": "atom-steps/s", "cores": nthr, "kind": "reference",
                                         "sample": "%d MD steps of the same relaxed state in the compiled reference (oracle/_ref, 1 MPI rank: USER-LE "
-                                                  "is only defined on one rank; %s), window holds one ex_unload and one ex_load event, %.0f s wall "
+                                                  "is only defined on one rank; %s), window holds one fix extrusion event and the ex_unload / ex_load events next to it, %.0f s wall "
                                                   "incl. setup" % (nst, "%d OpenMP threads, USER-OMP pair/bond/neighbor/nve styles, fix langevin and "
                                                   "the USER-LE fixes serial" % nthr if nthr > 1 else "serial build", wall_ref)}
             else:
@@ -318,47 +354,27 @@ def run_reference_arm(args):
     if rank != 0:
         return
     from oracle import refio
-    from lammps_le_b200 import systems
     n_beads, n_ext = args.beads, args.extruders
     if not refio.have_reference():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built on this box"}))
         return
-    # the same relaxed start as our arm (the relaxation is set-up, not the thing measured)
-    try:
-        s, e = prepared_engine(n_beads, n_ext, 12345, 0, args.relax)
-        x, im = e.positions()
-        v = e.velocities()
-        topo = e.topology()
-        e.close()
-        prep = "relaxed with the CUDA engine's push-off run"
-    except Exception:
-        s = build_system(n_beads, n_ext, 12345)
-        x, im, v = s["x"], s["image"], systems.maxwell_velocities(n_beads, 1.0, np.ones(n_beads), 12345)
-        topo = None
-        prep = "unrelaxed generator output"
-    if topo is None:
-        bt, a1, a2 = s["bonds"]
-        n = n_beads
-        nb = np.zeros(n, np.int32)
-        btab = np.zeros((n, 4), np.int32)
-        atab = np.zeros((n, 4), np.int32)
-        for t, a, b in zip(bt, a1, a2):
-            for p, q in ((a, b), (b, a)):
-                btab[p - 1, nb[p - 1]] = t
-                atab[p - 1, nb[p - 1]] = q
-                nb[p - 1] += 1
-        topo = {"num_bond": nb, "bond_type": btab, "bond_atom": atab}
+    # the generator is host-only (libleb200_host.so, plain g++): the CUDA engine is neither loaded nor run in this arm; the start
+    # state is relaxed by the reference's own minimize + push-off run inside the same lmp_ref process that is then timed
+    s = build_system(n_beads, n_ext, 12345)
     seg = max(4, int(2.0e6 / n_beads * 8))
     nthr = reference_threads()
-    rate, t_seg, wall, nst = reference_rate(s, x, im, v, topo, seg, args.warmup, args.steps, threads=nthr)
+    rate, t_seg, wall, nst = reference_rate_own_start(s, seg, args.warmup, args.steps, max(100, args.relax // 5), threads=nthr)
     line = {"impl": "reference", "metric": "atom-steps/s", "value": rate, "unit": "atom-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_seg, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD if n_beads == 1000000 else "same model, %d beads, %d extruders" % (n_beads, n_ext),
-                       "md_steps_per_step": seg, "parallelism": "1 MPI rank (serial stubs), %d OpenMP thread(s)" % nthr},
+                       "md_steps_per_step": seg, "parallelism": "1 MPI rank (serial stubs), %d OpenMP thread(s), g++ -O3" % nthr},
             "cpu_baseline": {"value": rate, "unit": "atom-steps/s", "cores": nthr, "kind": "reference",
-                             "sample": "%d MD steps in %d `run` segments, %s; window holds one ex_unload + one ex_load event; "
-                                       "Loop time of each segment as LAMMPS prints it" % (nst, args.steps, prep)},
+                             "sample": "%d MD steps in %d `run` segments of the compiled reference (oracle/_ref/omp: -O3, USER-OMP pair/bond/"
+                                       "neighbor/nve styles; fix langevin and the USER-LE fixes are serial), start state relaxed by the reference "
+                                       "itself (minimize + %d steps of fix nve/limit); the timed window holds one fix extrusion event and the "
+                                       "ex_unload / ex_load events next to it; Loop time of each segment as LAMMPS prints it; %.0f s wall in all"
+                                       % (nst, args.steps, max(100, args.relax // 5), wall)},
             "e2e": {"value": rate, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 

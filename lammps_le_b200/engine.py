@@ -103,6 +103,33 @@ def load_library():
     return lib
 
 
+_hostlib = None
+
+
+def load_host_library():
+    """the host-only helpers (le_gen_*, le_host_*): libleb200_host.so (plain g++, no CUDA) so that making synthetic inputs
+    does not load the CUDA engine; falls back to the full library when only that has been built"""
+    global _hostlib
+    if _hostlib is not None:
+        return _hostlib
+    path = os.path.join(_HERE, "libleb200_host.so")
+    if not os.path.exists(path):
+        _hostlib = load_library()
+        return _hostlib
+    lib = C.CDLL(path)
+    I, D, I64 = C.c_int, C.c_double, C.c_int64
+    pd, pi = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    lib.le_gen_saw_chains.argtypes = [I, I, D, D, D, C.c_uint64, pd, pi]
+    lib.le_gen_lattice_melt.argtypes = [I, I, D, pd, pd, pi]
+    lib.le_host_velocity_create.argtypes = [I, pi, pd, pd, D, I, I, I, I, pd]
+    lib.le_host_property_local_bonds.argtypes = [I, I, pi, pi, pi, I, pi]
+    lib.le_host_property_local_bonds.restype = I64
+    for n in ("le_gen_saw_chains", "le_gen_lattice_melt", "le_host_velocity_create"):
+        getattr(lib, n).restype = I
+    _hostlib = lib
+    return lib
+
+
 def _pd(a):
     return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
 
@@ -414,7 +441,7 @@ def pack_image(ixyz):
 
 def property_local_bonds(num_bond, bond_type, bond_atom, newton_bond=0):
     """rows (batom1, batom2, btype) of `compute property/local batom1 batom2 btype` in the reference's order"""
-    lib = load_library()
+    lib = load_host_library()
     nb = np.ascontiguousarray(num_bond, dtype=np.int32)
     bt = np.ascontiguousarray(bond_type, dtype=np.int32)
     ba = np.ascontiguousarray(bond_atom, dtype=np.int32)
@@ -428,7 +455,7 @@ def property_local_bonds(num_bond, bond_type, bond_atom, newton_bond=0):
 def velocity_create(types, masses, t_desired, seed, dist="uniform", mom=True, loop="all", x=None):
     """`velocity all create T seed dist ... mom ... loop ...` (Velocity::create, src/velocity.cpp:162-401) on the host:
     returns v[n,3] in tag order for Engine.set_velocities."""
-    lib = load_library()
+    lib = load_host_library()
     types = np.ascontiguousarray(types, dtype=np.int32)
     masses = np.ascontiguousarray(masses, dtype=np.float64)
     n = len(types)
@@ -443,7 +470,7 @@ def velocity_create(types, masses, t_desired, seed, dist="uniform", mom=True, lo
 
 def gen_saw_chains(n, nchains, L, step=0.97, rmin=0.9, seed=12345):
     """Self-avoiding walk(s) wrapped into [0,L)^3: returns x[n,3], image[n]."""
-    lib = load_library()
+    lib = load_host_library()
     x = np.zeros((n, 3))
     im = np.zeros(n, dtype=np.int32)
     rc = lib.le_gen_saw_chains(n, nchains, L, step, rmin, seed, _pd(x), _pi(im))
@@ -453,7 +480,7 @@ def gen_saw_chains(n, nchains, L, step=0.97, rmin=0.9, seed=12345):
 
 
 def gen_lattice_melt(nchains, length, rho=0.8442):
-    lib = load_library()
+    lib = load_host_library()
     n = nchains * length
     x = np.zeros((n, 3))
     im = np.zeros(n, dtype=np.int32)
