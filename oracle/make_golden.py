@@ -22,13 +22,13 @@ if ROOT not in sys.path:
 from oracle import refio  # noqa: E402
 
 
-def le_trace(system, steps, le_lines, workdir=None, minimize=True, dt=0.005, langevin_seed=904297, damp=1.0):
+def le_trace(system, steps, le_lines, workdir=None, minimize=True, dt=0.005, langevin_seed=904297, damp=1.0, min_args="1e-6 1e-8 2000 20000"):
     """Run the reference with the three USER-LE fixes and le/snap fixes around them; returns (pre, post)."""
     wd = workdir or tempfile.mkdtemp(prefix="le_trace_")
     refio.write_data_file(os.path.join(wd, "data.le"), system)
     deck = refio.deck_header(system, "data.le")
     if minimize:
-        deck += ["minimize 1e-6 1e-8 2000 20000", "reset_timestep 0"]
+        deck += ["minimize " + min_args, "reset_timestep 0"]
     deck += ["fix 1 all nve", "fix 2 all langevin 1.0 1.0 %g %d" % (damp, langevin_seed)]
     deck += le_lines
     deck += ["thermo_style custom step temp epair emol bonds f_loop[1] f_loading[1] f_unloading[1]", "thermo 500",
@@ -40,13 +40,13 @@ def le_trace(system, steps, le_lines, workdir=None, minimize=True, dt=0.005, lan
     return pre, post, out
 
 
-def force_case(system, workdir=None, minimize=True, velocities=False):
+def force_case(system, workdir=None, minimize=True, velocities=False, min_args="1e-4 1e-6 200 2000"):
     """run 0 of the reference without thermostat: forces, energies, virial, lists on grid-snapped positions."""
     wd = workdir or tempfile.mkdtemp(prefix="le_force_")
     refio.write_data_file(os.path.join(wd, "data.le"), system)
     deck = refio.deck_header(system, "data.le")
     if minimize:
-        deck += ["minimize 1e-4 1e-6 200 2000", "reset_timestep 0"]
+        deck += ["minimize " + min_args, "reset_timestep 0"]
     if velocities:
         deck += ["velocity all create 1.0 4928459 dist gaussian"]
     deck += ["fix s0 all le/snap dummy.bin pre grid", "fix 1 all nve",

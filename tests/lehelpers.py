@@ -69,6 +69,20 @@ def compare_neighlists(off_a, ent_a, off_b, ent_b):
     return bad
 
 
+def neighlists_equal_as_sets(off_a, ent_a, off_b, ent_b):
+    """vectorised form of compare_neighlists for large systems: per-atom entry SETS are equal iff the (row, entry) pairs
+    agree after sorting (a list never holds an entry twice); returns the number of differing pairs"""
+    def pairs(off, ent):
+        off = np.asarray(off, dtype=np.int64)
+        rows = np.repeat(np.arange(len(off) - 1, dtype=np.int64), np.diff(off))
+        key = rows * (1 << 32) + (np.asarray(ent).astype(np.int64) & 0xFFFFFFFF)
+        return np.sort(key)
+    a, b = pairs(off_a, ent_a), pairs(off_b, ent_b)
+    if len(a) != len(b):
+        return abs(len(a) - len(b)) + int(len(np.setxor1d(a, b)))
+    return int((a != b).sum())
+
+
 def special_tiers(nspecial, special):
     out = []
     for t in range(len(nspecial)):

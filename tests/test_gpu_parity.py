@@ -160,3 +160,67 @@ def test_forces_live_reference_chain_and_melt():
     check_lists(e, rec)
     check_forces(e, rec, rec["thermo"])
     e.close()
+
+
+BENCH_BONDS = {1: ("fene", (30.0, 1.5, 1.0, 1.0)), 2: ("fene", (10.0, 4.0, 1.0, 1.0))}
+
+
+def test_bench_workload_at_one_million_beads_against_the_reference():
+    """The system bench.py times (10^6-bead chain, 10^4 FENE(10,4) extruders, random barriers) against the compiled
+    reference at full size: half neighbor list, bondlist, step-0 forces / energies / virial from BOTH instantiations of
+    the step kernel, and one replayed event of each USER-LE fix."""
+    _need_ref()
+    import tempfile
+    from lammps_le_b200 import systems
+    from oracle.make_golden import force_case, le_trace
+    n = 1000000
+    s = systems.chromatin_chain(n, n // 100, rho=0.2, seed=12345, barriers="random", extruder_bond=systems.EXTRUDER_FENE)
+    with tempfile.TemporaryDirectory(prefix="le_1m_") as wd:
+        rec = force_case(s, workdir=wd, min_args="1e-4 1e-6 30 300")
+    e = H.engine_from_record(rec, BENCH_BONDS, positions="x")
+    e.force_rebuild()
+    off, ent = e.neighlist(half=True)
+    assert len(ent) == len(rec["neigh_entries"]), "half list size %d vs reference %d" % (len(ent), len(rec["neigh_entries"]))
+    assert H.neighlists_equal_as_sets(off, ent, rec["neigh_offsets"], rec["neigh_entries"]) == 0
+    bl = e.bondlist()
+    assert bl.shape == rec["bondlist"].shape and (bl == rec["bondlist"]).all()
+    err = check_forces(e, rec, rec["thermo"])
+    fp = e.compute_forces_plain()
+    fr = rec["f"]
+    mag = np.sqrt((fr ** 2).sum(1))
+    rel = (np.sqrt(((fp - fr) ** 2).sum(1)) / np.maximum(mag, np.sqrt((mag ** 2).mean()))).max()
+    assert rel <= FORCE_RTOL, "plain step kernel: max per-atom relative force error %.3g" % rel
+    e.close()
+    # one event of each fix at this size (steps 1, 2, 3 of a run from the minimised state), replayed from the reference's pre-state
+    with tempfile.TemporaryDirectory(prefix="le_1m_") as wd:
+        lines = H.le_deck_lines()
+        pre, post, _ = le_trace(s, 3, lines, workdir=wd, min_args="1e-4 1e-6 30 300")
+    assert sorted(a["which"] for a in pre) == [1, 2, 3]
+    problems = []
+    from oracle import refio
+    for a, b in zip(pre, post):
+        e = H.engine_from_record(a, BENCH_BONDS, positions="xhold")
+        H.define_le_fixes(e)
+        e.force_rebuild()
+        off, ent = e.neighlist(half=True)
+        if H.neighlists_equal_as_sets(off, ent, a["neigh_offsets"], a["neigh_entries"]):
+            problems.append(("lists", a["step"]))
+        e.set_positions(a["x"], a["image"])
+        w = a["which"]
+        e.fix_rng_reset(H.WHICH[w], H.LE_DECK[H.SEED_KEY[w]]["seed"], refio.draws_consumed(a["rngc"][H.RNG_SLOT[w]]))
+        e.run_le_event(H.WHICH[w])
+        got = e.topology()
+        for key in ("num_bond", "bond_type", "bond_atom", "nspecial"):
+            mask = slice(None)
+            if key in ("bond_type", "bond_atom"):
+                m = np.arange(b[key].shape[1])[None, :] < b["num_bond"][:, None]
+                if ((got[key] != b[key]) & m).any():
+                    problems.append((key, w))
+            elif (got[key] != b[key]).any():
+                problems.append((key, w))
+        if (e.types() != b["type"]).any():
+            problems.append(("type", w))
+        if e.fix_rng_consumed(H.WHICH[w]) != refio.draws_consumed(b["rngc"][H.RNG_SLOT[w]]):
+            problems.append(("draws", w))
+        e.close()
+    assert not problems, problems
