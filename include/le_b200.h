@@ -60,6 +60,11 @@ typedef struct le_thermo {
   double virial[6];         /* pair + bond virial, xx yy zz xy xz yz (not normalised) */
   int64_t nbonds;           /* atom->nbonds */
   int64_t fene_warnings;    /* "FENE bond too long" occurrences in this force evaluation */
+  /* the USER-LE fixes' global vectors as `thermo_style custom ... f_ID[1] f_ID[2]` prints them on this step
+   * (compute_vector: src/USER-LE/fix_extrusion.cpp:1496-1501, fix_ex_unload.cpp:839-843, fix_ex_load.cpp:1451-1455):
+   * index 0 fix extrusion, 1 fix ex_unload, 2 fix ex_load; f1 = bonds of the fix's last event, f2 = cumulative -- except
+   * le_f2[0], which is 0 as in the reference (FixExtrusion never accumulates its total; le_stats.extrusion_shifts does) */
+  int64_t le_f1[3], le_f2[3];
 } le_thermo;
 
 /* run statistics, the numbers the reference prints in Finish::end (src/finish.cpp) */
@@ -152,6 +157,20 @@ int le_compute_forces(le_ctx *c, double *f, le_thermo *out);
 /* the same forces from the plain (no energy / virial tally) instantiation of the step kernel, the one production
  * timesteps run; f[N*3] */
 int le_compute_forces_plain(le_ctx *c, double *f);
+
+/* `minimize etol ftol maxiter maxeval` (src/minimize.cpp:31-60) with min_style cg and the quadratic line search, the
+ * reference's defaults (MinCG::iterate src/min_cg.cpp:35-200, MinLineSearch::linemin_quadratic src/min_linesearch.cpp:325-505);
+ * the numbers Finish::end prints under "Minimization stats" (src/finish.cpp:192-218) come back in *out (may be NULL).
+ * Energies per atom (thermo_modify norm yes).  Velocities are not touched; the timestep advances by the iterations. */
+typedef struct le_min_result {
+  int stop;                 /* index into Min::stopstrings (src/min.cpp:1058-1073): 0 max iterations, 1 max force evaluations,
+                               2 energy tolerance, 3 force tolerance, 4 not downhill, 5 alpha is zero, 6 forces are zero, 7 quadratic factors */
+  int niter, neval;
+  double einitial, eprevious, efinal;
+  double fnorm2_init, fnorm2_final, fnorminf_init, fnorminf_final, alpha_final;
+} le_min_result;
+int le_minimize(le_ctx *c, double etol, double ftol, int maxiter, int maxeval, le_min_result *out);
+const char *le_min_stop_string(int stop);
 
 /* ---- results --------------------------------------------------------------------------- */
 int le_natoms(const le_ctx *c);

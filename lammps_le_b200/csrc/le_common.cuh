@@ -209,8 +209,10 @@ struct Dev {
   double *fout;     // [N][3] optional force output (tag order)
 };
 
-#define LE_THERMO_W 16
-// thermo slot layout: 0 ke(sum m v^2) 1 evdwl 2 ebond 3..8 virial 9 fene warnings
+#define LE_THERMO_W 24
+// thermo slot layout: 0 ke(sum m v^2) 1 evdwl 2 ebond 3..8 virial 9 fene warnings | snapshot at that force evaluation (not
+// summed over GPUs: the USER-LE state is replicated): 16 atom->nbonds, 17..19 f_ID[1] of extrusion / ex_unload / ex_load
+// (bonds of the fix's last event), 20..22 f_ID[2] (cumulative)
 
 // one translation unit (le_engine.cu) includes this header; the block is refreshed before every use
 __constant__ Params c_P;

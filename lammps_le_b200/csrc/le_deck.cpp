@@ -13,7 +13,8 @@
 //   pair_coeff I J eps sigma [rc] | bond_style fene|harmonic|hybrid ... | bond_coeff N [style] ...
 //   fix ID all nve | nve/limit X | langevin T0 T1 damp seed | extrusion ... | ex_load ... | ex_unload ...
 //   unfix ID | timestep dt | reset_timestep N | thermo N | thermo_modify ... | run N
-//   thermo_style one | custom step elapsed dt time atoms temp press pe ke etotal evdwl epair ebond emol vol density lx ly lz bonds
+//   thermo_style one | custom step elapsed dt time atoms temp press pe ke etotal evdwl epair ebond emol vol density lx ly lz bonds f_ID[1|2]
+//   minimize etol ftol maxiter maxeval | min_style cg
 //   velocity all create T seed [dist uniform|gaussian] [mom yes|no] [loop all|local|geom]
 //   write_data F | dump ID all custom N F cols | undump ID | log/echo/print (ignored or echoed)
 //   compute ID all property/local batom1 batom2 btype | dump ID all local N F [index] c_ID[k] ... (the loops)
@@ -60,7 +61,9 @@ struct Deck {
   struct Dump { std::string id, file; int every; std::vector<std::string> cols; FILE *fp; bool local = false; std::vector<int> lcols; };   // lcols: 0 = index, k = k-th attribute of the compute
   std::map<std::string, std::vector<std::string>> prop_local;   // compute ID all property/local batom1|batom2|btype ...
   std::vector<Dump> dumps;                             // dump ID all custom N file cols...
-  std::vector<int> thermo_cols;                        // thermo_style custom: indices into THERMO_FIELDS (empty = style one)
+  std::vector<int> thermo_cols;                        // thermo_style custom: indices into THERMO_FIELDS (empty = style one); 1000 + k = thermo_fix_cols[k]
+  struct FixCol { std::string id; int idx; std::string title; };
+  std::vector<FixCol> thermo_fix_cols;                 // f_ID[k] columns
   bool echo = false;
 };
 
@@ -234,13 +237,24 @@ const ThermoField THERMO_FIELDS[] = {
 
 void thermo_style(Deck &d, const Words &w) {
   if (w.size() < 2) die("Illegal thermo_style command");
-  d.thermo_cols.clear();
+  d.thermo_cols.clear(); d.thermo_fix_cols.clear();
   if (w[1] == "one") return;                                // the default line: step temp epair emol etotal press
   if (w[1] != "custom") die("Illegal thermo_style command (only one | custom)");
   if (w.size() < 3) die("Illegal thermo style custom command");
   for (size_t k = 2; k < w.size(); k++) {
     int found = -1;
     for (size_t q = 0; q < sizeof(THERMO_FIELDS) / sizeof(THERMO_FIELDS[0]); q++) if (w[k] == THERMO_FIELDS[q].key) found = (int)q;
+    if (found < 0 && w[k].size() > 5 && w[k].compare(0, 2, "f_") == 0 && w[k].back() == ']') {
+      // f_ID[k]: global vector of a fix (Thermo::parse_fields / evaluate_keyword, src/thermo.cpp:882-962, :1526); the fixes
+      // of this path with one are the three USER-LE fixes: [1] bonds of the last event, [2] cumulative.  The fix is
+      // looked up when the line is printed, so the ID may be defined after the thermo_style line, as in LAMMPS decks.
+      const size_t br = w[k].find('[');
+      if (br == std::string::npos) die("Unknown keyword in thermo_style custom command: " + w[k]);
+      const int idx = inum(w[k].substr(br + 1, w[k].size() - br - 2));
+      if (idx < 1 || idx > 2) die("Thermo fix vector is accessed out-of-range");
+      d.thermo_fix_cols.push_back({w[k].substr(2, br - 2), idx, w[k]});
+      found = 1000 + (int)d.thermo_fix_cols.size() - 1;
+    }
     if (found < 0) die("Unknown keyword in thermo_style custom command: " + w[k]);
     d.thermo_cols.push_back(found);
   }
@@ -250,7 +264,14 @@ void print_thermo(Deck &d, int first) {
   const int n = le_thermo_count(d.ctx);
   std::vector<int> cols = d.thermo_cols;
   if (cols.empty()) cols = {0, 5, 11, 13, 9, 6};            // step temp epair emol etotal press
-  for (int q : cols) std::printf("%s ", THERMO_FIELDS[q].title);
+  std::vector<int> fix_slot(d.thermo_fix_cols.size(), -1);   // 0 extrusion, 1 ex_unload, 2 ex_load
+  for (size_t k = 0; k < d.thermo_fix_cols.size(); k++) {
+    const auto it = d.fix_style.find(d.thermo_fix_cols[k].id);
+    if (it == d.fix_style.end()) die("Could not find thermo fix ID " + d.thermo_fix_cols[k].id);
+    fix_slot[k] = it->second == "extrusion" ? 0 : it->second == "ex_unload" ? 1 : it->second == "ex_load" ? 2 : -1;
+    if (fix_slot[k] < 0) die("Thermo fix does not compute vector");
+  }
+  for (int q : cols) std::printf("%s ", q >= 1000 ? d.thermo_fix_cols[q - 1000].title.c_str() : THERMO_FIELDS[q].title);
   std::printf("\n");
   double vol = 1.0, mtot = 0.0;
   for (int k = 0; k < 3; k++) vol *= d.hi[k] - d.lo[k];
@@ -266,6 +287,11 @@ void print_thermo(Deck &d, int first) {
     last = t.step;
     for (int q : cols) {
       long long iv = 0; double fv = 0.0;
+      if (q >= 1000) {                                       // fix vectors print as floating point, like every f_ID[k]
+        const Deck::FixCol &fc = d.thermo_fix_cols[q - 1000];
+        std::printf("%12.8g ", (double)(fc.idx == 1 ? t.le_f1[fix_slot[q - 1000]] : t.le_f2[fix_slot[q - 1000]]));
+        continue;
+      }
       switch (q) {
         case 0: iv = t.step; break;
         case 1: iv = t.step - step0; break;
@@ -594,6 +620,20 @@ void execute_cmd(Deck &d, const Words &w) {
   } else if (c == "fix") fix(d, w);
   else if (c == "unfix") unfix(d, w);
   else if (c == "timestep") { if (w.size() != 2) die("Illegal timestep command"); d.dt = num(w[1]); }
+  else if (c == "minimize") {
+    // minimize etol ftol maxiter maxeval (src/minimize.cpp:31-60); min_style cg / quadratic line search, the defaults
+    if (w.size() != 5) die("Illegal minimize command");
+    init(d);
+    le_min_result R;
+    ck(d, le_minimize(d.ctx, num(w[1]), num(w[2]), inum(w[3]), inum(w[4]), &R));
+    std::printf("Step PotEng \n%8lld %12.8g \n%8lld %12.8g \n", (long long)le_timestep(d.ctx) - R.niter, R.einitial, (long long)le_timestep(d.ctx), R.efinal);
+    std::printf("Loop time of minimize for %d steps with %d atoms\n\nMinimization stats:\n  Stopping criterion = %s\n"
+                "  Energy initial, next-to-last, final = \n    %18.15g %18.15g %18.15g\n  Force two-norm initial, final = %.8g %.8g\n"
+                "  Force max component initial, final = %.8g %.8g\n  Final line search alpha, max atom move = %.8g %.8g\n"
+                "  Iterations, force evaluations = %d %d\n\n", R.niter, d.natoms, le_min_stop_string(R.stop), R.einitial, R.eprevious, R.efinal,
+                R.fnorm2_init, R.fnorm2_final, R.fnorminf_init, R.fnorminf_final, R.alpha_final, R.alpha_final * R.fnorminf_final, R.niter, R.neval);
+  }
+  else if (c == "min_style") { if (w.size() < 2 || w[1] != "cg") die("only min_style cg is provided"); }
   else if (c == "reset_timestep") { if (w.size() != 2 || !d.ctx) die("Illegal reset_timestep command"); ck(d, le_reset_timestep(d.ctx, std::strtoll(w[1].c_str(), nullptr, 10))); }
   else if (c == "thermo") { if (w.size() != 2) die("Illegal thermo command"); d.thermo_every = inum(w[1]); }
   else if (c == "dump") {

@@ -11,6 +11,7 @@
 #include "le_build3.cuh"
 #include "le_step3.cuh"
 #include "le_fix.cuh"
+#include "le_min.cuh"
 
 #include <math.h>
 #include <stdarg.h>
@@ -1250,7 +1251,11 @@ static void thermo_from_slot(le_ctx *c, const double *s, int64_t step, le_thermo
   for (int k = 0; k < 6; k++) t->virial[k] = s[3 + k];
   t->press = (s[0] + s[3] + s[4] + s[5]) / (3.0 * vol);     // ComputePressure::compute_scalar, nktv2p = 1
   t->fene_warnings = (int64_t)llround(s[9]);
-  t->nbonds = c->nbonds;
+  t->nbonds = c->topo_loaded ? (int64_t)llround(s[16]) : c->nbonds;
+  for (int q = 0; q < 3; q++) { t->le_f1[q] = (int64_t)llround(s[17 + q]); t->le_f2[q] = (int64_t)llround(s[20 + q]); }
+  // FixExtrusion never adds to breakcounttotal (src/USER-LE/fix_extrusion.cpp:139 sets it to 0, :1500 returns it, nothing in
+  // between touches it): f_loop[2] reads 0 in the reference for ever; le_stats.extrusion_shifts keeps the real total
+  t->le_f2[0] = 0;
 }
 
 // one force evaluation + integration; the host's record of the buffer parity (c->cur) is what the kernel will find
@@ -1308,6 +1313,151 @@ extern "C" int le_compute_forces_plain(le_ctx *c, double *f) {
   CK(cudaMemcpyAsync(f, c->d.fout, sizeof(double) * 3 * c->N, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return LE_OK;
+}
+
+// ---- minimize ---------------------------------------------------------------------------------------------
+// One energy / force evaluation at the current positions: list rebuild, then the tallying step kernel without
+// integration (Min::energy_force, src/min.cpp:502-560; the reference reneighbors when its displacement test fires,
+// rebuilding every time is the conservative form).  *e = evdwl + ebond (total, not normalised).
+static int min_eval(le_ctx *c, double *e) {
+  enqueue_rebuild(c, true);
+  c->lists_valid = true;
+  CK(cudaMemsetAsync(c->d.thermo, 0, sizeof(double) * LE_THERMO_W, c->stream));
+  StepArgs a; memset(&a, 0, sizeof a);
+  a.slot = 0; a.write_force = 1;
+  launch_step(c, a, true);
+  CK(cudaMemcpyAsync(c->h_thermo, c->d.thermo, sizeof(double) * LE_THERMO_W, cudaMemcpyDeviceToHost, c->stream));
+  int r = sync_and_check(c); if (r) return r;
+  *e = c->h_thermo[1] + c->h_thermo[2];
+  return LE_OK;
+}
+
+static int min_dots(le_ctx *c, const double *g, const double *h, double *dev6, double out[6]) {
+  CK(cudaMemsetAsync(dev6, 0, 6 * sizeof(double), c->stream));
+  LAUNCH(c, k_min_dots, std::min(grid_for(3 * c->N, 256), c->sm_count * 8), 256, 3 * c->N, (const double *)c->d.fout, g, h, dev6);
+  CK(cudaMemcpyAsync(out, dev6, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return LE_OK;
+}
+
+/* `minimize etol ftol maxiter maxeval` with min_style cg, the quadratic line search and dmax = 0.1 (the defaults of the
+ * reference, src/min.cpp:64-75): Polak-Ribiere conjugate gradients (MinCG::iterate, src/min_cg.cpp:35-200) over
+ * MinLineSearch::linemin_quadratic (src/min_linesearch.cpp:325-505).  Energies are compared per atom (thermo_modify norm
+ * yes, the lj default), forces as the squared two-norm, exactly as there.  The timestep advances by the number of
+ * iterations.  One GPU. */
+extern "C" int le_minimize(le_ctx *c, double etol, double ftol, int maxiter, int maxeval, le_min_result *out) {
+  if (!c) return LE_EINVAL;
+  if (etol < 0.0 || ftol < 0.0 || maxiter < 0 || maxeval < 0) return fail(c, LE_EINVAL, "Illegal minimize command");
+  if (c->nranks > 1) return fail(c, LE_ESTATE, "minimize is not provided on several GPUs: minimise on one GPU, then distribute");
+  int r = ensure_ready(c); if (r) return r;
+  const int n = c->N, n3 = 3 * n;
+  const double natoms = (double)n;
+  const double ALPHA_MAX = 1.0, ALPHA_REDUCE = 0.5, BACKTRACK_SLOPE = 0.4, QUADRATIC_TOL = 0.1, EMACH = 1.0e-8, EPS_QUAD = 1.0e-28;
+  const double EPS_ENERGY = 1.0e-8, dmax = 0.1;
+  double *g = nullptr, *h = nullptr, *dev6 = nullptr; int4 *x0 = nullptr; int *img0 = nullptr;
+  auto cleanup = [&]() { cudaFree(g); cudaFree(h); cudaFree(dev6); cudaFree(x0); cudaFree(img0); };
+  if (cudaMalloc(&g, sizeof(double) * n3) != cudaSuccess || cudaMalloc(&h, sizeof(double) * n3) != cudaSuccess ||
+      cudaMalloc(&dev6, 6 * sizeof(double)) != cudaSuccess || cudaMalloc(&x0, sizeof(int4) * n) != cudaSuccess ||
+      cudaMalloc(&img0, sizeof(int) * n) != cudaSuccess) { cleanup(); return fail(c, LE_ENOMEM, "cudaMalloc failed in le_minimize"); }
+  const int gN = std::min(grid_for(n, 256), c->sm_count * 8), g3 = std::min(grid_for(n3, 256), c->sm_count * 8);
+  le_min_result R; memset(&R, 0, sizeof R);
+  double dots[6];
+  double ecurrent, eprevious;
+  r = push_run_state(c, c->ntimestep, c->ntimestep); if (r) { cleanup(); return r; }
+  if ((r = min_eval(c, &ecurrent))) { cleanup(); return r; }           // Min::setup
+  ecurrent /= natoms;
+  R.einitial = eprevious = ecurrent;
+  R.neval = 0; R.niter = 0;
+  LAUNCH(c, k_min_dir, g3, 256, n3, (const double *)c->d.fout, g, h, 0.0);   // h = g = f
+  if ((r = min_dots(c, g, h, dev6, dots))) { cleanup(); return r; }
+  double gg = dots[0];
+  R.fnorm2_init = sqrt(dots[0]); R.fnorminf_init = __builtin_bit_cast(double, __builtin_bit_cast(unsigned long long, dots[5]));
+  double alpha_final = 0.0;
+  int stop = 0;      // index into Min::stopstrings
+  // x <- x0 + alpha h, then energy and forces there (alpha_step with resetflag 1)
+  auto alpha_step = [&](double alpha, double *e) -> int {
+    LAUNCH(c, k_min_move, gN, 256, c->d, (const int4 *)x0, (const int *)img0, (const double *)h, alpha);
+    R.neval++;
+    int rr = min_eval(c, e); if (rr) return rr;
+    *e /= natoms;
+    return LE_OK;
+  };
+  enum { MAXITER = 0, MAXEVAL, ETOL, FTOL, DOWNHILL, ZEROALPHA, ZEROFORCE, ZEROQUAD };
+  bool done = false;
+  for (int iter = 0; iter < maxiter && !done; iter++) {
+    c->ntimestep++;
+    R.niter++;
+    eprevious = ecurrent;
+    // ---- linemin_quadratic ----
+    int lfail = 0;
+    {
+      const double eoriginal = ecurrent;
+      if ((r = min_dots(c, g, h, dev6, dots))) { cleanup(); return r; }
+      const double fdothall = dots[2] / natoms;
+      const double hmaxall = __builtin_bit_cast(double, __builtin_bit_cast(unsigned long long, dots[4]));
+      if (fdothall <= 0.0) lfail = DOWNHILL;
+      else if (hmaxall == 0.0) lfail = ZEROFORCE;
+      else {
+        const double alphamax = std::min(ALPHA_MAX, dmax / hmaxall);
+        LAUNCH(c, k_min_save, gN, 256, c->d, x0, img0);
+        double alpha = alphamax, fhprev = fdothall, engprev = eoriginal, alphaprev = 0.0;
+        for (;;) {
+          if ((r = alpha_step(alpha, &ecurrent))) { cleanup(); return r; }
+          if ((r = min_dots(c, g, h, dev6, dots))) { cleanup(); return r; }
+          const double fh = dots[2] / natoms;
+          const double delfh = fh - fhprev;
+          if (fabs(fh) < EPS_QUAD || fabs(delfh) < EPS_QUAD) {
+            LAUNCH(c, k_min_move, gN, 256, c->d, (const int4 *)x0, (const int *)img0, (const double *)h, 0.0);
+            ecurrent = eoriginal; lfail = ZEROQUAD; break;
+          }
+          const double relerr = fabs(1.0 - (0.5 * (alpha - alphaprev) * (fh + fhprev) + ecurrent) / engprev);
+          const double alpha0 = alpha - (alpha - alphaprev) * fh / delfh;
+          if (relerr <= QUADRATIC_TOL && alpha0 > 0.0 && alpha0 < alphamax) {
+            if ((r = alpha_step(alpha0, &ecurrent))) { cleanup(); return r; }
+            if (ecurrent - eoriginal < EMACH) { alpha_final = alpha0; break; }
+          }
+          const double de_ideal = -BACKTRACK_SLOPE * alpha * fdothall;
+          const double de = ecurrent - eoriginal;
+          if (de <= de_ideal) { alpha_final = alpha; break; }
+          fhprev = fh; engprev = ecurrent; alphaprev = alpha;
+          alpha *= ALPHA_REDUCE;
+          if (alpha <= 0.0 || de_ideal >= -EMACH) {
+            LAUNCH(c, k_min_move, gN, 256, c->d, (const int4 *)x0, (const int *)img0, (const double *)h, 0.0);
+            ecurrent = eoriginal; lfail = ZEROALPHA; break;
+          }
+        }
+      }
+    }
+    if (lfail) { stop = lfail; done = true; break; }
+    if (R.neval >= maxeval) { stop = MAXEVAL; done = true; break; }
+    if (fabs(ecurrent - eprevious) < etol * 0.5 * (fabs(ecurrent) + fabs(eprevious) + EPS_ENERGY)) { stop = ETOL; done = true; break; }
+    if ((r = min_dots(c, g, h, dev6, dots))) { cleanup(); return r; }
+    if (ftol > 0.0 && dots[0] < ftol * ftol) { stop = FTOL; done = true; break; }
+    // Polak-Ribiere: beta = max(0, (f.f - f.g) / g.g)
+    const double beta = std::max(0.0, (dots[0] - dots[1]) / gg);
+    gg = dots[0];
+    LAUNCH(c, k_min_dir, g3, 256, n3, (const double *)c->d.fout, g, h, beta);
+    if ((r = min_dots(c, g, h, dev6, dots))) { cleanup(); return r; }
+    if (dots[3] <= 0.0) LAUNCH(c, k_min_copy, g3, 256, n3, (const double *)g, h);     // not downhill: restart from the gradient
+  }
+  if (!done) stop = MAXITER;
+  // the state the run leaves behind: forces / lists at the final positions
+  double efinal;
+  if ((r = min_eval(c, &efinal))) { cleanup(); return r; }
+  if ((r = min_dots(c, g, h, dev6, dots))) { cleanup(); return r; }
+  R.efinal = efinal / natoms; R.eprevious = eprevious;
+  R.fnorm2_final = sqrt(dots[0]); R.fnorminf_final = __builtin_bit_cast(double, __builtin_bit_cast(unsigned long long, dots[5]));
+  R.alpha_final = alpha_final; R.stop = stop;
+  cleanup();
+  if (out) *out = R;
+  return LE_OK;
+}
+
+extern "C" const char *le_min_stop_string(int stop) {
+  static const char *strings[] = {"max iterations", "max force evaluations", "energy tolerance", "force tolerance",
+                                  "search direction is not downhill", "linesearch alpha is zero", "forces are zero",
+                                  "quadratic factors are zero"};
+  return (stop >= 0 && stop < 8) ? strings[stop] : "unknown";
 }
 
 #include "le_fix_host.inl"
@@ -1669,12 +1819,12 @@ extern "C" int le_get_thermo(const le_ctx *c, int index, le_thermo *out) {
 
 /* raw tallies behind thermo record `index` on THIS GPU: 0 sum m v^2, 1 evdwl, 2 ebond, 3..8 virial, 9 FENE warnings.
  * Multi-GPU callers sum them over ranks and normalise as thermo_from_slot does. */
-extern "C" int le_get_thermo_sums(const le_ctx *c, int index, double *out16) {
+extern "C" int le_get_thermo_sums(const le_ctx *c, int index, double *out16) {   /* the 16 summable tallies */
   if (!c || !out16) return LE_EINVAL;
   const int n = (int)c->thermo_sums.size();
   if (index < 0) index += n;
   if (index < 0 || index >= n) return LE_EINVAL;
-  for (int k = 0; k < LE_THERMO_W; k++) out16[k] = c->thermo_sums[index][k];
+  for (int k = 0; k < 16; k++) out16[k] = c->thermo_sums[index][k];
   return LE_OK;
 }
 
@@ -1701,7 +1851,7 @@ extern "C" const char *le_step_kernel_name(le_ctx *c) {
 
 extern "C" int le_get_force_sums(const le_ctx *c, double *out16) {
   if (!c || !out16 || c->force_sums.size() != LE_THERMO_W) return LE_EINVAL;
-  for (int k = 0; k < LE_THERMO_W; k++) out16[k] = c->force_sums[k];
+  for (int k = 0; k < 16; k++) out16[k] = c->force_sums[k];
   return LE_OK;
 }
 

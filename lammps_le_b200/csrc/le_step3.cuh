@@ -352,6 +352,12 @@ __global__ void __launch_bounds__(STEP3_THREADS, EV ? 2 : 4) k_step3(Dev d, Step
   }
 
   if (EV) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {      // what `thermo_style custom ... bonds f_ID[k]` prints on this step
+      double *sl = d.thermo + (size_t)a.slot * LE_THERMO_W;
+      sl[16] = (double)ctrl->nbonds;
+#pragma unroll
+      for (int q = 0; q < 3; q++) { sl[17 + q] = (double)ctrl->le_count[q]; sl[20 + q] = (double)ctrl->le_count[4 + q]; }
+    }
     double acc[10];
     acc[0] = ke; acc[1] = 0.5 * A.evdwl; acc[2] = 0.5 * A.ebond;
 #pragma unroll

@@ -28,12 +28,18 @@ class LeError(RuntimeError):
 class Thermo(C.Structure):
     _fields_ = [("step", C.c_int64), ("temp", C.c_double), ("epair", C.c_double), ("emol", C.c_double),
                 ("etotal", C.c_double), ("press", C.c_double), ("ke", C.c_double), ("virial", C.c_double * 6),
-                ("nbonds", C.c_int64), ("fene_warnings", C.c_int64)]
+                ("nbonds", C.c_int64), ("fene_warnings", C.c_int64), ("le_f1", C.c_int64 * 3), ("le_f2", C.c_int64 * 3)]
 
     def as_dict(self):
         return {"step": self.step, "temp": self.temp, "epair": self.epair, "emol": self.emol,
                 "etotal": self.etotal, "press": self.press, "ke": self.ke, "virial": list(self.virial),
-                "nbonds": self.nbonds, "fene_warnings": self.fene_warnings}
+                "nbonds": self.nbonds, "fene_warnings": self.fene_warnings, "le_f1": list(self.le_f1), "le_f2": list(self.le_f2)}
+
+
+class MinResult(C.Structure):
+    _fields_ = [("stop", C.c_int), ("niter", C.c_int), ("neval", C.c_int), ("einitial", C.c_double), ("eprevious", C.c_double),
+                ("efinal", C.c_double), ("fnorm2_init", C.c_double), ("fnorm2_final", C.c_double), ("fnorminf_init", C.c_double),
+                ("fnorminf_final", C.c_double), ("alpha_final", C.c_double)]
 
 
 class Stats(C.Structure):
@@ -72,6 +78,7 @@ def load_library():
         "le_upload_topology": [P, pi, pi, pi, pi, pi], "le_set_positions": [P, pd, pi], "le_set_velocities": [P, pd],
         "le_run": [P, I64], "le_run_timed": [P, I64, pd], "le_force_rebuild": [P], "le_run_le_event": [P, I],
         "le_fix_rng_reset": [P, I, I, I64], "le_fix_rng_consumed": [P, I, C.POINTER(I64)],
+        "le_minimize": [P, D, D, I, I, C.POINTER(MinResult)],
         "le_compute_forces": [P, pd, C.POINTER(Thermo)], "le_compute_forces_plain": [P, pd], "le_natoms": [P], "le_download_x": [P, pd, pi],
         "le_download_v": [P, pd], "le_download_types": [P, pi], "le_download_topology": [P, pi, pi, pi, pi, pi],
         "le_download_neighlist": [P, I, C.POINTER(I64), pi, C.POINTER(I64)],
@@ -95,6 +102,8 @@ def load_library():
     lib.le_version.restype = C.c_char_p
     lib.le_host_property_local_bonds.argtypes = [I, I, pi, pi, pi, I, pi]
     lib.le_host_property_local_bonds.restype = I64
+    lib.le_min_stop_string.argtypes = [I]
+    lib.le_min_stop_string.restype = C.c_char_p
     lib.le_step_kernel_name.argtypes = [P]
     lib.le_step_kernel_name.restype = C.c_char_p
     lib.le_timestep.argtypes = [P]
@@ -301,6 +310,14 @@ class Engine:
         t = Thermo()
         self._ck(self.lib.le_compute_forces(self._h, _pd(f), C.byref(t)))
         return f, t.as_dict()
+
+    def minimize(self, etol, ftol, maxiter, maxeval):
+        """`minimize etol ftol maxiter maxeval` (min_style cg, quadratic line search); returns the "Minimization stats" """
+        r = MinResult()
+        self._ck(self.lib.le_minimize(self._h, float(etol), float(ftol), int(maxiter), int(maxeval), C.byref(r)))
+        out = {n: getattr(r, n) for n, _ in r._fields_}
+        out["stop_string"] = self.lib.le_min_stop_string(r.stop).decode()
+        return out
 
     def compute_forces_plain(self):
         """forces from the plain instantiation of the step kernel (the one production timesteps run)"""
