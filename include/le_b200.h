@@ -130,7 +130,8 @@ int le_upload_atoms(le_ctx *c, int n, const int *tag, const int *type, const dou
 /* read_data "Bonds" section: each bond once; stored on both atoms in file order, then
  * the 1-2/1-3/1-4 special lists are built as Special::build does (src/special.cpp:55-154). */
 int le_upload_bonds(le_ctx *c, int nbonds, const int *btype, const int *atom1, const int *atom2);
-/* raw per-atom tables exactly as the reference holds them (state replay) */
+/* raw per-atom tables exactly as the reference holds them (state replay, read_restart); nspecial == special == NULL:
+ * the special lists are built from the bond tables as read_restart does (Special::build) */
 int le_upload_topology(le_ctx *c, const int *num_bond, const int *bond_type, const int *bond_atom,
                        const int *nspecial, const int *special);
 /* overwrite positions only (x[N*3], image may be NULL = keep); neighbor/bond lists are NOT rebuilt,

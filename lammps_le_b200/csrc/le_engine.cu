@@ -9,7 +9,9 @@
 #include "le_md.cuh"
 #include "le_sort.cuh"
 #include "le_build3.cuh"
+#include "le_build4.cuh"
 #include "le_step3.cuh"
+#include "le_step4.cuh"
 #include "le_fix.cuh"
 #include "le_min.cuh"
 
@@ -70,6 +72,8 @@ struct le_ctx {
   bool atoms_loaded, topo_loaded, lists_valid, params_dirty;
   int scan_items;       // cells per thread of k_scan_cells
   bool topo_dirty;      // the tag-ordered topology tables changed since the last k_topo_pack
+  int build_variant;    // 3 = k_build3 (default), 4 = k_build4 (LE_BUILD_VARIANT, A/B measurements)
+  int step_variant;     // 4 = k_step4 (default), 3 = k_step3 (LE_STEP_VARIANT, A/B measurements)
   Dev d;
   Params P;
   std::vector<void *> allocs;
@@ -123,7 +127,7 @@ static void time_report(le_ctx *c) {
     // average launch-to-next-launch time of the plain step kernel (le_run_timed)
     double sum = 0; int n = 0;
     for (size_t k = 0; k + 1 < c->tm_used; k++)
-      if (!strncmp(c->tm_name[k], "(k_step3<0", 10)) { float ms = 0.f; cudaEventElapsedTime(&ms, c->tm_ev[k], c->tm_ev[k + 1]); sum += ms; n++; }
+      if (!strncmp(c->tm_name[k], "(k_step", 7) && !strncmp(c->tm_name[k] + 8, "<0", 2)) { float ms = 0.f; cudaEventElapsedTime(&ms, c->tm_ev[k], c->tm_ev[k + 1]); sum += ms; n++; }
     c->kstep_avg_ms = n ? sum / n : 0.0;
   }
   if (c->timing_quiet) { c->tm_used = 0; c->tm_name.clear(); return; }
@@ -203,6 +207,8 @@ extern "C" int le_create(le_ctx **out, int device, const double boxlo[3], const 
   if (cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || c->sm_count < 1) c->sm_count = 148;
   c->le_ev_used = 0;
   { const char *tm = getenv("LE_B200_TIMING"); c->timing = tm && tm[0] == '1'; c->tm_used = 0; }
+  { const char *bv = getenv("LE_BUILD_VARIANT"); c->build_variant = bv ? atoi(bv) : 3; }
+  { const char *sv = getenv("LE_STEP_VARIANT"); c->step_variant = sv ? atoi(sv) : 4; }
   c->timing_quiet = false; c->force_direct = false; c->kstep_avg_ms = 0.0;
   for (int k = 0; k < 3; k++) {
     c->lo[k] = boxlo[k]; c->hi[k] = boxhi[k]; c->periodic[k] = periodic[k];
@@ -904,23 +910,12 @@ static int upload_topology_host(le_ctx *c, const std::vector<int> &nb, const std
   return LE_OK;
 }
 
-extern "C" int le_upload_bonds(le_ctx *c, int nbonds, const int *btype, const int *atom1, const int *atom2) {
-  if (!c) return LE_EINVAL;
-  if (!c->atoms_loaded) return fail(c, LE_ESTATE, "upload atoms before bonds");
+// special lists from the per-atom bond tables: 1-2 = bond partners; 1-3 = partners of partners; 1-4 = partners of 1-3; each
+// tier without self and without anything already listed (Special::build + combine, src/special.cpp:55-154,611-762);
+// tiers whose weight (and every later one) is 1.0 are not built at all (special.cpp:92-101,111-121)
+static int build_special_host(le_ctx *c, const std::vector<int> &nb, const std::vector<int> &ba, std::vector<int> &ns, std::vector<int> &sp) {
   const int n = c->N, bpa = c->bpa, ms = c->maxspecial;
-  std::vector<int> nb(n, 0), bt((size_t)n * bpa, 0), ba((size_t)n * bpa, 0), ns((size_t)n * 3, 0), sp((size_t)n * ms, 0);
-  // Atom::data_bonds with newton_bond off (src/atom.cpp:1261-1278): each bond goes to both atoms, file order
-  for (int k = 0; k < nbonds; k++) {
-    const int a = atom1[k], b = atom2[k], t = btype[k];
-    if (a < 1 || a > n || b < 1 || b > n || a == b) return fail(c, LE_EINVAL, "Invalid atom ID in Bonds section of data file");
-    if (t < 1 || t > c->nbondtypes) return fail(c, LE_EINVAL, "Invalid bond type in Bonds section of data file");
-    if (nb[a - 1] >= bpa || nb[b - 1] >= bpa) return fail(c, LE_EINVAL, "bonds per atom exceed bond_per_atom=%d", bpa);
-    bt[(size_t)(a - 1) * bpa + nb[a - 1]] = t; ba[(size_t)(a - 1) * bpa + nb[a - 1]] = b; nb[a - 1]++;
-    bt[(size_t)(b - 1) * bpa + nb[b - 1]] = t; ba[(size_t)(b - 1) * bpa + nb[b - 1]] = a; nb[b - 1]++;
-  }
-  // special lists: 1-2 = bond partners; 1-3 = partners of partners; 1-4 = partners of 1-3; each tier without
-  // self and without anything already listed (Special::build + combine, src/special.cpp:55-154,611-762)
-  // tiers whose weight (and every later one) is 1.0 are not built at all (special.cpp:92-101,111-121)
+  ns.assign((size_t)n * 3, 0); sp.assign((size_t)n * ms, 0);
   const int ntier = (c->special_lj[2] == 1.0 && c->special_lj[3] == 1.0) ? 1 : (c->special_lj[3] == 1.0 ? 2 : 3);
   std::vector<int> tmp;
   for (int i = 0; i < n; i++) {
@@ -936,6 +931,24 @@ extern "C" int le_upload_bonds(le_ctx *c, int nbonds, const int *btype, const in
     ns[(size_t)i * 3] = n1; ns[(size_t)i * 3 + 1] = n2; ns[(size_t)i * 3 + 2] = n3;
     for (int a = 0; a < n3; a++) sp[(size_t)i * ms + a] = tmp[a];
   }
+  return LE_OK;
+}
+
+extern "C" int le_upload_bonds(le_ctx *c, int nbonds, const int *btype, const int *atom1, const int *atom2) {
+  if (!c) return LE_EINVAL;
+  if (!c->atoms_loaded) return fail(c, LE_ESTATE, "upload atoms before bonds");
+  const int n = c->N, bpa = c->bpa, ms = c->maxspecial;
+  std::vector<int> nb(n, 0), bt((size_t)n * bpa, 0), ba((size_t)n * bpa, 0), ns((size_t)n * 3, 0), sp((size_t)n * ms, 0);
+  // Atom::data_bonds with newton_bond off (src/atom.cpp:1261-1278): each bond goes to both atoms, file order
+  for (int k = 0; k < nbonds; k++) {
+    const int a = atom1[k], b = atom2[k], t = btype[k];
+    if (a < 1 || a > n || b < 1 || b > n || a == b) return fail(c, LE_EINVAL, "Invalid atom ID in Bonds section of data file");
+    if (t < 1 || t > c->nbondtypes) return fail(c, LE_EINVAL, "Invalid bond type in Bonds section of data file");
+    if (nb[a - 1] >= bpa || nb[b - 1] >= bpa) return fail(c, LE_EINVAL, "bonds per atom exceed bond_per_atom=%d", bpa);
+    bt[(size_t)(a - 1) * bpa + nb[a - 1]] = t; ba[(size_t)(a - 1) * bpa + nb[a - 1]] = b; nb[a - 1]++;
+    bt[(size_t)(b - 1) * bpa + nb[b - 1]] = t; ba[(size_t)(b - 1) * bpa + nb[b - 1]] = a; nb[b - 1]++;
+  }
+  { int rs = build_special_host(c, nb, ba, ns, sp); if (rs) return rs; }
   return upload_topology_host(c, nb, bt, ba, ns, sp);
 }
 
@@ -945,11 +958,19 @@ extern "C" int le_upload_topology(le_ctx *c, const int *num_bond, const int *bon
   const size_t n = c->N;
   for (size_t k = 0; k < n; k++) {
     if (num_bond[k] < 0 || num_bond[k] > c->bpa) return fail(c, LE_EINVAL, "num_bond out of range for atom %zu", k + 1);
-    if (nspecial[3 * k + 2] > c->maxspecial || nspecial[3 * k] > nspecial[3 * k + 1] || nspecial[3 * k + 1] > nspecial[3 * k + 2])
+    if (nspecial && (nspecial[3 * k + 2] > c->maxspecial || nspecial[3 * k] > nspecial[3 * k + 1] || nspecial[3 * k + 1] > nspecial[3 * k + 2]))
       return fail(c, LE_EINVAL, "nspecial out of range for atom %zu", k + 1);
   }
   std::vector<int> nb(num_bond, num_bond + n), bt(bond_type, bond_type + n * c->bpa), ba(bond_atom, bond_atom + n * c->bpa);
-  std::vector<int> ns(nspecial, nspecial + n * 3), sp(special, special + n * c->maxspecial);
+  std::vector<int> ns, sp;
+  if (nspecial && special) { ns.assign(nspecial, nspecial + n * 3); sp.assign(special, special + n * c->maxspecial); }
+  else {
+    // a restart file carries the per-atom bond tables but no special lists: read_restart rebuilds them (src/read_restart.cpp:520-530)
+    for (size_t k = 0; k < n; k++)
+      for (int m = 0; m < nb[k]; m++)
+        if (ba[k * c->bpa + m] < 1 || ba[k * c->bpa + m] > (int)n) return fail(c, LE_EINVAL, "bond partner of atom %zu out of range", k + 1);
+    int rs = build_special_host(c, nb, ba, ns, sp); if (rs) return rs;
+  }
   return upload_topology_host(c, nb, bt, ba, ns, sp);
 }
 
@@ -1031,18 +1052,27 @@ static bool step_uniform(const le_ctx *c) {
 
 static StepKernel step_kernel(const le_ctx *c, bool ev) {
   const bool dd = c->nranks > 1, uni = step_uniform(c);
-  if (ev) {
-    if (dd) return uni ? StepKernel{(step_fn_t)k_step3<1, 1, 1>, STEP3_THREADS, "(k_step3<1,1,1>)", 2} : StepKernel{(step_fn_t)k_step3<1, 1, 0>, STEP3_THREADS, "(k_step3<1,1,0>)", 2};
-    return uni ? StepKernel{(step_fn_t)k_step3<1, 0, 1>, STEP3_THREADS, "(k_step3<1,0,1>)", 2} : StepKernel{(step_fn_t)k_step3<1, 0, 0>, STEP3_THREADS, "(k_step3<1,0,0>)", 2};
+  if (c->step_variant == 3) {
+    if (ev) {
+      if (dd) return uni ? StepKernel{(step_fn_t)k_step3<1, 1, 1>, STEP3_THREADS, "(k_step3<1,1,1>)", 2} : StepKernel{(step_fn_t)k_step3<1, 1, 0>, STEP3_THREADS, "(k_step3<1,1,0>)", 2};
+      return uni ? StepKernel{(step_fn_t)k_step3<1, 0, 1>, STEP3_THREADS, "(k_step3<1,0,1>)", 2} : StepKernel{(step_fn_t)k_step3<1, 0, 0>, STEP3_THREADS, "(k_step3<1,0,0>)", 2};
+    }
+    if (dd) return uni ? StepKernel{(step_fn_t)k_step3<0, 1, 1>, STEP3_THREADS, "(k_step3<0,1,1>)", 4} : StepKernel{(step_fn_t)k_step3<0, 1, 0>, STEP3_THREADS, "(k_step3<0,1,0>)", 4};
+    return uni ? StepKernel{(step_fn_t)k_step3<0, 0, 1>, STEP3_THREADS, "(k_step3<0,0,1>)", 4} : StepKernel{(step_fn_t)k_step3<0, 0, 0>, STEP3_THREADS, "(k_step3<0,0,0>)", 4};
   }
-  if (dd) return uni ? StepKernel{(step_fn_t)k_step3<0, 1, 1>, STEP3_THREADS, "(k_step3<0,1,1>)", 4} : StepKernel{(step_fn_t)k_step3<0, 1, 0>, STEP3_THREADS, "(k_step3<0,1,0>)", 4};
-  return uni ? StepKernel{(step_fn_t)k_step3<0, 0, 1>, STEP3_THREADS, "(k_step3<0,0,1>)", 4} : StepKernel{(step_fn_t)k_step3<0, 0, 0>, STEP3_THREADS, "(k_step3<0,0,0>)", 4};
+  if (ev) {
+    if (dd) return uni ? StepKernel{(step_fn_t)k_step4<1, 1, 1>, STEP4_THREADS, "(k_step4<1,1,1>)", 4} : StepKernel{(step_fn_t)k_step4<1, 1, 0>, STEP4_THREADS, "(k_step4<1,1,0>)", 4};
+    return uni ? StepKernel{(step_fn_t)k_step4<1, 0, 1>, STEP4_THREADS, "(k_step4<1,0,1>)", 4} : StepKernel{(step_fn_t)k_step4<1, 0, 0>, STEP4_THREADS, "(k_step4<1,0,0>)", 4};
+  }
+  if (dd) return uni ? StepKernel{(step_fn_t)k_step4<0, 1, 1>, STEP4_THREADS, "(k_step4<0,1,1>)", 7} : StepKernel{(step_fn_t)k_step4<0, 1, 0>, STEP4_THREADS, "(k_step4<0,1,0>)", 7};
+  return uni ? StepKernel{(step_fn_t)k_step4<0, 0, 1>, STEP4_THREADS, "(k_step4<0,0,1>)", 7} : StepKernel{(step_fn_t)k_step4<0, 0, 0>, STEP4_THREADS, "(k_step4<0,0,0>)", 7};
 }
 
 // one wave of resident blocks (persistent grid over the tiles), fewer when there are fewer tiles
 static int step_grid(const le_ctx *c, const StepKernel &sk) {
   const int tiles = (c->d.gr0 - c->d.own0 + TILE - 1) / TILE + 2;
-  const int g = (tiles + STEP3_WARPS - 1) / STEP3_WARPS;
+  const int wpb = sk.threads / 32;
+  const int g = (tiles + wpb - 1) / wpb;
   return std::max(1, std::min(g, c->sm_count * sk.wave_blocks));
 }
 
@@ -1083,7 +1113,10 @@ static void enqueue_rebuild(le_ctx *c, bool direct) {
     LAUNCH(c, k_rb_post_ghosts, 1, 1, d);
     LAUNCH(c, k_ghost_map, grid_for(2 * d.own0, 256), 256, d);
   }
-  {
+  if (c->build_variant != 3) {
+    const int g = grid_for(nslots, B4_THREADS);
+    if (c->P.pair_uniform) LAUNCH(c, k_build4<1>, g, B4_THREADS, d); else LAUNCH(c, k_build4<0>, g, B4_THREADS, d);
+  } else {
     const int g = grid_for(nslots, BUILD_THREADS);
     const bool uni = c->P.pair_uniform != 0;
     if (build_queue_depth(c) > 16) { if (uni) LAUNCH(c, (k_build3<40, 4, 1>), g, BUILD_THREADS, d); else LAUNCH(c, (k_build3<40, 4, 0>), g, BUILD_THREADS, d); }

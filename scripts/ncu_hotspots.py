@@ -5,7 +5,7 @@ executions, warp-level instruction count, and the instructions that collect the 
 import collections, csv, io, subprocess, sys
 rep, rx, warps = sys.argv[1], sys.argv[2], float(sys.argv[3])
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "--kernel-name", "regex:" + rx],
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass", "--kernel-name", "regex:k_"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 blocks, cur, hdr, name = [], None, None, None
@@ -16,6 +16,7 @@ for r in rows:
         hdr = r; continue
     if cur is not None and r:
         cur.append(r)
+blocks = [x for x in blocks if __import__("re").search(rx, x[0])]
 name, b = blocks[0]
 ie, at, sm = hdr.index("Instructions Executed"), hdr.index("Avg. Threads Executed"), hdr.index("# Samples")
 tot = sum(int(r[ie]) for r in b); ts = sum(int(r[sm]) for r in b)

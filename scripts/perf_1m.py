@@ -38,14 +38,13 @@ print("graphs: %.4f ms/step over %d steps, %d rebuilds (every %.2f steps), nbar_
     steps / max(1, st["neigh_builds"] - st0["neigh_builds"]), st["full_entries"] / n, e.thermo(-1)["temp"]), flush=True)
 us = e.run_timed(steps)
 print("direct: step kernel %.2f us" % us, flush=True)
-# in-graph cost split: no rebuild at all (every = 10^6) against a rebuild on every step (check no)
-e.set_neighbor(0.4, 1000000, 0, 1)
-e.run(64)
-e.run(steps)
-t_none = e.stats()["last_run_gpu_ms"] / steps
+# in-graph cost of a rebuild: a rebuild on every step (check no) against the normal cadence K: t_all - t = rebuild (1 - 1/K)
+t_norm = st["last_run_gpu_ms"] / steps
+K = steps / max(1, st["neigh_builds"] - st0["neigh_builds"])
 e.set_neighbor(0.4, 1, 0, 0)
 e.run(64)
 e.run(steps)
 t_all = e.stats()["last_run_gpu_ms"] / steps
-print("in-graph: step without rebuild %.2f us, with a rebuild every step %.2f us -> rebuild %.2f us" % (1e3 * t_none, 1e3 * t_all, 1e3 * (t_all - t_none)), flush=True)
+rb = (t_all - t_norm) / (1.0 - 1.0 / K)
+print("in-graph: rebuild every step %.2f us/step, normal %.2f us/step -> rebuild %.2f us, step without rebuild %.2f us" % (1e3 * t_all, 1e3 * t_norm, 1e3 * rb, 1e3 * (t_all - rb)), flush=True)
 e.close()
