@@ -10,6 +10,7 @@
 #include "le_sort.cuh"
 #include "le_build3.cuh"
 #include "le_build4.cuh"
+#include "le_build5.cuh"
 #include "le_step3.cuh"
 #include "le_step4.cuh"
 #include "le_fix.cuh"
@@ -72,7 +73,7 @@ struct le_ctx {
   bool atoms_loaded, topo_loaded, lists_valid, params_dirty;
   int scan_items;       // cells per thread of k_scan_cells
   bool topo_dirty;      // the tag-ordered topology tables changed since the last k_topo_pack
-  int build_variant;    // 3 = k_build3 (default), 4 = k_build4 (LE_BUILD_VARIANT, A/B measurements)
+  int build_variant;    // 3 = k_build3 (default), 5 = k_build5, 4 = k_build4 (LE_BUILD_VARIANT, A/B measurements)
   int step_variant;     // 4 = k_step4 (default), 3 = k_step3 (LE_STEP_VARIANT, A/B measurements)
   Dev d;
   Params P;
@@ -1113,7 +1114,12 @@ static void enqueue_rebuild(le_ctx *c, bool direct) {
     LAUNCH(c, k_rb_post_ghosts, 1, 1, d);
     LAUNCH(c, k_ghost_map, grid_for(2 * d.own0, 256), 256, d);
   }
-  if (c->build_variant != 3) {
+  if (c->build_variant == 5) {
+    const int g = grid_for(nslots, BUILD_THREADS);
+    const bool uni = c->P.pair_uniform != 0;
+    if (build_queue_depth(c) > 16) { if (uni) LAUNCH(c, (k_build5<36, 4, 1>), g, BUILD_THREADS, d); else LAUNCH(c, (k_build5<36, 4, 0>), g, BUILD_THREADS, d); }
+    else { if (uni) LAUNCH(c, (k_build5<16, 8, 1>), g, BUILD_THREADS, d); else LAUNCH(c, (k_build5<16, 8, 0>), g, BUILD_THREADS, d); }
+  } else if (c->build_variant == 4) {
     const int g = grid_for(nslots, B4_THREADS);
     if (c->P.pair_uniform) LAUNCH(c, k_build4<1>, g, B4_THREADS, d); else LAUNCH(c, k_build4<0>, g, B4_THREADS, d);
   } else {
