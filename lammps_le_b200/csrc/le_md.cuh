@@ -100,8 +100,11 @@ __device__ __forceinline__ void decide_body(const Dev &d, cudaGraphConditionalHa
       }
     }
   }
-  if (r) { moved = 0; ago = 0; c->nbuilds++; }
-  *reinterpret_cast<int4 *>(c) = make_int4(moved, 0, r, ago);
+  if (r) { ago = 0; c->nbuilds++; }
+  // `moved` is the state of THIS step (Neighbor::check_distance looks at the displacements only on the steps where
+  // delay / every allow a rebuild, neighbor.cpp:1943-1947): the step kernel re-tests every atom whose bound has reached
+  // skin/2 on every step, so the flag is cleared here and an atom that moved out and back in does not trigger later
+  *reinterpret_cast<int4 *>(c) = make_int4(0, 0, r, ago);
   if (use_handle) cudaGraphSetConditional(handle, r ? 1u : 0u);
 }
 

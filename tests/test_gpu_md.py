@@ -140,6 +140,31 @@ def test_owned_bulk_exchange_roundtrip():
 
 
 @pytest.mark.gpu
+def test_two_live_engines_with_different_boxes():
+    """the constant parameter block is one symbol per process and device: every entry point must refresh it, so a second
+    context with another box cannot leak its mapping into the first one's downloads"""
+    from lammps_le_b200 import systems
+    sa = systems.chromatin_chain(3000, 30, rho=0.2, seed=3)
+    sb = systems.chromatin_chain(24000, 240, rho=0.05, seed=4)
+    assert abs(sa["box"][1][0] - sb["box"][1][0]) > 1.0
+    a = systems.make_engine(sa, velocities=np.zeros((3000, 3)))
+    xa0, ia0 = a.positions()
+    b = systems.make_engine(sb, velocities=np.zeros((24000, 3)))
+    b.fix_nve(True); b.run(5)                         # b's parameters are now the ones in constant memory
+    bufs = a.owned_buffers(pinned=False)
+    n = a.download_owned(bufs)
+    tag, xb, imb, vb = bufs
+    assert n == 3000 and (xb[:n] == xa0[tag[:n] - 1]).all()
+    xa1, _ = a.positions()
+    assert (xa1 == xa0).all()
+    f, _ = a.compute_forces()
+    b.run(3)
+    f2, _ = a.compute_forces()
+    assert np.array_equal(f, f2)
+    a.close(); b.close()
+
+
+@pytest.mark.gpu
 def test_device_observables_match_host():
     """le_observables (Rg, contact counts, loop-size histogram on the GPU) against numpy on downloaded state"""
     s = systems.chromatin_chain(6000, 80, rho=0.2, seed=9, extruder_bond=systems.EXTRUDER_FENE)
