@@ -20,27 +20,28 @@
 #include "le_common.cuh"
 
 // ---- topology digest -----------------------------------------------------------------------------------------
+__device__ __forceinline__ void topo_pack_one(const Dev &d, int t) {   // t = tag - 1
+  const int nb = d.num_bond[t];
+  const int *ns = d.nspecial + (size_t)t * 3;
+  const int n1 = ns[0], n2 = ns[1], n3 = ns[2];
+  const int nscan = c_P.nscan_tier == 0 ? 0 : c_P.nscan_tier == 1 ? n1 : c_P.nscan_tier == 2 ? n2 : n3;
+  TopoRec r;
+  r.hdr = (unsigned)nb | ((unsigned)nscan << 8) | ((unsigned)n1 << 16) | ((unsigned)n2 << 24);
+  unsigned bt = 0;
+  const int *ba = d.bond_atom + (size_t)t * d.bpa, *bty = d.bond_type + (size_t)t * d.bpa;
+  for (int m = 0; m < nb && m < 8; m++) bt |= ((unsigned)(bty[m] - 1) & 15u) << (4 * m);
+  r.btypes = bt;
+#pragma unroll
+  for (int m = 0; m < 4; m++) r.batom[m] = (m < nb) ? ba[m] : 0;
+  const int *sp = d.special + (size_t)t * d.maxspecial;
+#pragma unroll
+  for (int q = 0; q < TOPO_NSPEC; q++) r.spec[q] = (q < n3) ? sp[q] : 0;
+  int4 *out = reinterpret_cast<int4 *>(d.topo + t);
+  const int4 *in = reinterpret_cast<const int4 *>(&r);
+  out[0] = in[0]; out[1] = in[1]; out[2] = in[2]; out[3] = in[3];
+}
 __global__ void k_topo_pack(Dev d) {
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < d.N; t += gridDim.x * blockDim.x) {
-    const int nb = d.num_bond[t];
-    const int *ns = d.nspecial + (size_t)t * 3;
-    const int n1 = ns[0], n2 = ns[1], n3 = ns[2];
-    const int nscan = c_P.nscan_tier == 0 ? 0 : c_P.nscan_tier == 1 ? n1 : c_P.nscan_tier == 2 ? n2 : n3;
-    TopoRec r;
-    r.hdr = (unsigned)nb | ((unsigned)nscan << 8) | ((unsigned)n1 << 16) | ((unsigned)n2 << 24);
-    unsigned bt = 0;
-    const int *ba = d.bond_atom + (size_t)t * d.bpa, *bty = d.bond_type + (size_t)t * d.bpa;
-    for (int m = 0; m < nb && m < 8; m++) bt |= ((unsigned)(bty[m] - 1) & 15u) << (4 * m);
-    r.btypes = bt;
-#pragma unroll
-    for (int m = 0; m < 4; m++) r.batom[m] = (m < nb) ? ba[m] : 0;
-    const int *sp = d.special + (size_t)t * d.maxspecial;
-#pragma unroll
-    for (int q = 0; q < TOPO_NSPEC; q++) r.spec[q] = (q < n3) ? sp[q] : 0;
-    int4 *out = reinterpret_cast<int4 *>(d.topo + t);
-    const int4 *in = reinterpret_cast<const int4 *>(&r);
-    out[0] = in[0]; out[1] = in[1]; out[2] = in[2]; out[3] = in[3];
-  }
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < d.N; t += gridDim.x * blockDim.x) topo_pack_one(d, t);
 }
 
 // NPair::find_special (src/npair.h:112-136) on the digest: the first four specials sit in registers

@@ -17,6 +17,7 @@
 // Everything here is indexed by tag (t-1); positions are reached through the tag map.
 #pragma once
 #include "le_common.cuh"
+#include "le_build3.cuh"   // topo_pack_one
 #include <algorithm>
 #include <vector>
 
@@ -547,7 +548,13 @@ __global__ void k_le_topo_detect(Dev d, const int *marks, int mode, const int *g
 }
 __global__ void k_le_topo_rebuild(Dev d, const int *list, int *nlist) {
   const int n = *nlist;
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) rebuild_special_one(d, list[k]);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    rebuild_special_one(d, list[k]);
+    // the atom's digest for the list build follows its tables at once: every atom whose bond or special tables an event
+    // changed is on one of the event's lists (the end points of a broken / created bond carry a mark themselves), so no
+    // sweep over all tags is needed after an event
+    topo_pack_one(d, list[k] - 1);
+  }
 }
 __global__ void k_le_topo_reset(int *nlist) { *nlist = 0; }
 

@@ -208,7 +208,7 @@ static int enqueue_load(le_ctx *c) {
 // Modify::post_integrate on timestep `step`: each fix checks its own gate
 // (fix_extrusion.cpp:265 `ntimestep % nevery - 1`, fix_ex_unload.cpp:178 `- 2`, fix_ex_load.cpp:338 `- 3`)
 static int enqueue_le_events(le_ctx *c, int64_t step) {
-  bool any = false;
+  bool any = false; (void)any;
   for (int which : c->fix_order) {
     int r = LE_OK;
     if (which == LE_FIX_EXTRUSION && c->fx.on && (step % c->fx.nevery - 1) == 0) { r = enqueue_extrusion(c); any = true; }
@@ -216,9 +216,7 @@ static int enqueue_le_events(le_ctx *c, int64_t step) {
     else if (which == LE_FIX_EX_LOAD && c->fl.on && (step % c->fl.nevery - 3) == 0) { r = enqueue_load(c); any = true; }
     if (r) return r;
   }
-  // the bond / special tables may have changed: refresh the digests before the rebuild the fixes have forced (the rebuild
-  // kernels themselves sit in a captured graph)
-  if (any) enqueue_topo_pack(c);
+  // the digests of the atoms an event touched were refreshed by its topology sweeps (k_le_topo_rebuild)
   return LE_OK;
 }
 
@@ -231,6 +229,5 @@ extern "C" int le_run_le_event(le_ctx *c, int which) {
   else if (which == LE_FIX_EX_LOAD) { if (!c->fl.on) return fail(c, LE_ESTATE, "fix ex_load not defined"); r = enqueue_load(c); }
   else return fail(c, LE_EINVAL, "unknown fix");
   if (r) return r;
-  enqueue_topo_pack(c);
   return sync_and_check(c);
 }

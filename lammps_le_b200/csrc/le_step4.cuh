@@ -27,7 +27,7 @@ struct __align__(16) Step4Smem {
 };
 
 template <int EV, int DD, int UNI>
-__global__ void __launch_bounds__(STEP4_THREADS, EV ? 4 : 7) k_step4(Dev d, StepArgs a) {
+__global__ void __launch_bounds__(STEP4_THREADS, EV ? 4 : (DD ? 6 : 7)) k_step4(Dev d, StepArgs a) {   // (the slab form needs 80 registers to stay free of spills)
   __shared__ Step4Smem s_all[STEP4_WARPS];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Step4Smem &S = s_all[wib];
