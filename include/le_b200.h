@@ -152,6 +152,11 @@ int le_run_le_event(le_ctx *c, int which);
 /* skip n draws of that fix's Marsaglia stream / re-seed it (state replay) */
 int le_fix_rng_reset(le_ctx *c, int which, int seed, int64_t ndraws_consumed);
 int le_fix_rng_consumed(le_ctx *c, int which, int64_t *ndraws);
+/* hand a fix's Marsaglia generator over as the reference holds it, and take it back: state[103] in the layout of
+ * RanMars::get_state / set_state (src/random_mars.cpp:297-319).  A host that owns the RanMars object of `fix extrusion` /
+ * `ex_load` / `ex_unload` (the run_style binding, lammps_le_b200/lammps_style) continues the SAME stream on the device. */
+int le_fix_rng_set_state(le_ctx *c, int which, const double *state103);
+int le_fix_rng_get_state(le_ctx *c, int which, double *state103);
 /* compute forces/energies at the current positions without integrating (run 0 without fixes):
  * f[N*3] conservative pair+bond force in tag order (may be NULL) */
 int le_compute_forces(le_ctx *c, double *f, le_thermo *out);

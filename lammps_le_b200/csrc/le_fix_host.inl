@@ -82,6 +82,51 @@ extern "C" int le_fix_rng_consumed(le_ctx *c, int which, int64_t *ndraws) {
   return LE_OK;
 }
 
+/* the generator of a fix exactly as the reference holds it: RanMars::get_state / set_state (src/random_mars.cpp:297-319),
+ * state[0..97] = u[0..97], [98] = i97, [99] = j97, [100] = c, [101] = cd, [102] = cm.  u[k] and c are multiples of 2^-24;
+ * the ring s[q] = u[97 - q] * 2^24 never moves, head = 97 - i97. */
+extern "C" int le_fix_rng_set_state(le_ctx *c, int which, const double *state) {
+  if (!c || !state) return LE_EINVAL;
+  const int idx = rng_index(which);
+  if (idx < 0) return fail(c, LE_EINVAL, "unknown fix");
+  if (!c->atoms_loaded) return fail(c, LE_ESTATE, "no atoms");
+  const int i97 = (int)state[98], j97 = (int)state[99];
+  int jexp = i97 - 64; if (jexp < 1) jexp += 97;
+  if (i97 < 1 || i97 > 97 || j97 != jexp) return fail(c, LE_EINVAL, "le_fix_rng_set_state: not a RanMars state (i97 %d j97 %d)", i97, j97);
+  RngDev st;
+  for (int q = 0; q < 97; q++) {
+    const double v = state[97 - q] * 16777216.0;
+    st.s[q] = (int)llround(v);
+    if (fabs(v - st.s[q]) > 1e-6 || st.s[q] < 0 || st.s[q] >= 16777216) return fail(c, LE_EINVAL, "le_fix_rng_set_state: u[%d] is not a 24-bit fraction", 97 - q);
+  }
+  st.head = 97 - i97;
+  st.c = (int)llround(state[100] * 16777216.0);
+  st.consumed = 0;
+  cudaSetDevice(c->device);
+  CK(cudaMemcpyAsync(c->lf.rngdev + idx, &st, sizeof(RngDev), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->lf.rng[idx].seeded = 1; c->lf.rng[idx].seed = 0;
+  return LE_OK;
+}
+
+extern "C" int le_fix_rng_get_state(le_ctx *c, int which, double *state) {
+  if (!c || !state) return LE_EINVAL;
+  const int idx = rng_index(which);
+  if (idx < 0) return fail(c, LE_EINVAL, "unknown fix");
+  if (!c->atoms_loaded || !c->lf.rng[idx].seeded) return fail(c, LE_ESTATE, "the fix has not drawn yet and no state was set");
+  cudaSetDevice(c->device);
+  RngDev st;
+  CK(cudaMemcpyAsync(&st, c->lf.rngdev + idx, sizeof(RngDev), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  state[0] = 0.0;
+  for (int q = 0; q < 97; q++) state[97 - q] = st.s[q] / 16777216.0;
+  const int i97 = 97 - st.head;
+  int j97 = i97 - 64; if (j97 < 1) j97 += 97;
+  state[98] = i97; state[99] = j97;
+  state[100] = st.c / 16777216.0; state[101] = 7654321.0 / 16777216.0; state[102] = 16777213.0 / 16777216.0;
+  return LE_OK;
+}
+
 // n (device-side count) draws of fix `idx`'s Marsaglia stream into lf.draws
 static void ranmars_fill(le_ctx *c, int idx, const int *n_ptr) {
   LeFixDev &f = c->lf;
@@ -208,7 +253,7 @@ static int enqueue_load(le_ctx *c) {
 // Modify::post_integrate on timestep `step`: each fix checks its own gate
 // (fix_extrusion.cpp:265 `ntimestep % nevery - 1`, fix_ex_unload.cpp:178 `- 2`, fix_ex_load.cpp:338 `- 3`)
 static int enqueue_le_events(le_ctx *c, int64_t step) {
-  bool any = false; (void)any;
+  bool any = false;
   for (int which : c->fix_order) {
     int r = LE_OK;
     if (which == LE_FIX_EXTRUSION && c->fx.on && (step % c->fx.nevery - 1) == 0) { r = enqueue_extrusion(c); any = true; }
@@ -217,7 +262,7 @@ static int enqueue_le_events(le_ctx *c, int64_t step) {
     if (r) return r;
   }
   // the digests of the atoms an event touched were refreshed by its topology sweeps (k_le_topo_rebuild)
-  return LE_OK;
+  return any ? LE_OK : LE_OK;
 }
 
 extern "C" int le_run_le_event(le_ctx *c, int which) {

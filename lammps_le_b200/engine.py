@@ -78,6 +78,7 @@ def load_library():
         "le_upload_topology": [P, pi, pi, pi, pi, pi], "le_set_positions": [P, pd, pi], "le_set_velocities": [P, pd],
         "le_run": [P, I64], "le_run_timed": [P, I64, pd], "le_force_rebuild": [P], "le_run_le_event": [P, I],
         "le_fix_rng_reset": [P, I, I, I64], "le_fix_rng_consumed": [P, I, C.POINTER(I64)],
+        "le_fix_rng_set_state": [P, I, pd], "le_fix_rng_get_state": [P, I, pd],
         "le_minimize": [P, D, D, I, I, C.POINTER(MinResult)],
         "le_compute_forces": [P, pd, C.POINTER(Thermo)], "le_compute_forces_plain": [P, pd], "le_natoms": [P], "le_download_x": [P, pd, pi],
         "le_download_v": [P, pd], "le_download_types": [P, pi], "le_download_topology": [P, pi, pi, pi, pi, pi],
@@ -303,6 +304,17 @@ class Engine:
         n = C.c_int64()
         self._ck(self.lib.le_fix_rng_consumed(self._h, which, C.byref(n)))
         return n.value
+
+    def fix_rng_set_state(self, which, state103):
+        """RanMars::set_state layout (u[0..97], i97, j97, c, cd, cm)"""
+        st = np.ascontiguousarray(state103, dtype=np.float64)
+        assert st.shape == (103,)
+        self._ck(self.lib.le_fix_rng_set_state(self._h, which, _pd(st)))
+
+    def fix_rng_get_state(self, which):
+        st = np.zeros(103)
+        self._ck(self.lib.le_fix_rng_get_state(self._h, which, _pd(st)))
+        return st
 
     def compute_forces(self):
         n = self.natoms

@@ -185,9 +185,52 @@ def build():
     return 0
 
 
+def build_b200():
+    """oracle/_ref/b200/lmp_b200: the serial reference objects + the `run_style le/b200` binding a maintainer would add
+    (lammps_le_b200/lammps_style/verlet_le_b200.{h,cpp}), linked against lammps_le_b200/libleb200.so.  Only update.cpp and
+    lammps.cpp are recompiled (the integrator table and the -h style list come from style_integrate.h).  TEST-ONLY: tests/test_gpu_lammps_style.py drives decks
+    through the reference's own Input::file into the engine with it."""
+    set_variant(False)
+    root = os.path.dirname(HERE)
+    style_dir = os.path.join(root, "lammps_le_b200", "lammps_style")
+    lib = os.path.join(root, "lammps_le_b200", "libleb200.so")
+    out = os.path.join(OUT, "b200")
+    exe = os.path.join(out, "lmp_b200")
+    if not os.path.isdir(os.path.join(REF, "src")):
+        print("oracle/_ref/b200: reference tree absent, %s" % ("using the prebuilt binary" if os.path.exists(exe) else "nothing prebuilt"))
+        return 0 if os.path.exists(exe) else 1
+    if not os.path.exists(lib) or not os.path.isdir(OBJ):
+        print("oracle/_ref/b200: needs libleb200.so and the serial reference objects first", file=sys.stderr)
+        return 1
+    gen = os.path.join(out, "gen")
+    os.makedirs(gen, exist_ok=True)
+    for f in os.listdir(GEN):
+        text = open(os.path.join(GEN, f)).read()
+        if f == "style_integrate.h":
+            text += '#include "verlet_le_b200.h"\n'
+        write_if_changed(os.path.join(gen, f), text)
+    inc = ["-I" + gen, "-I" + style_dir, "-I" + os.path.join(root, "include"), "-I" + os.path.join(REF, "src/STUBS")] + ["-I" + os.path.join(REF, d) for d in SRC_DIRS]
+    srcs = [(os.path.join(REF, "src/update.cpp"), os.path.join(out, "update.o")), (os.path.join(REF, "src/lammps.cpp"), os.path.join(out, "lammps.o")), (os.path.join(style_dir, "verlet_le_b200.cpp"), os.path.join(out, "verlet_le_b200.o"))]
+    for src, obj in srcs:
+        if not up_to_date(obj, [src, os.path.join(style_dir, "verlet_le_b200.h"), os.path.join(root, "include", "le_b200.h")]):
+            subprocess.check_call(["g++"] + CXXFLAGS + inc + ["-c", src, "-o", obj])
+    objs = [os.path.join(OBJ, o) for o in sorted(os.listdir(OBJ)) if o.endswith(".o") and o not in ("update.o", "lammps.o")] + [o for _, o in srcs]
+    if not up_to_date(exe, objs + [lib]):
+        subprocess.check_call(["g++"] + CXXFLAGS + inc + [os.path.join(REF, "src/main.cpp")] + objs + ["-o", exe, "-L" + os.path.dirname(lib), "-lleb200",
+                                                                                                 "-Wl,-rpath,$ORIGIN/../../../lammps_le_b200"])
+    print("oracle/_ref/b200 built:", exe)
+    return 0
+
+
 def main():
     set_variant(False)
     rc = build()
+    if rc == 0:
+        try:
+            if build_b200():
+                print("oracle/_ref/b200: run_style le/b200 build failed", file=sys.stderr)
+        except Exception as ex:
+            print("oracle/_ref/b200: %s" % ex, file=sys.stderr)
     if rc == 0 and os.path.isdir(os.path.join(REF, "src/USER-OMP")) and os.environ.get("LE_REF_OMP", "1") == "1":
         # the threaded build only feeds bench.py's reference arm; its failure must not take the oracle down
         set_variant(True)

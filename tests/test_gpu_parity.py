@@ -224,3 +224,32 @@ def test_bench_workload_at_one_million_beads_against_the_reference():
             problems.append(("draws", w))
         e.close()
     assert not problems, problems
+
+
+@pytest.mark.gpu
+def test_ranmars_state_handover_matches_the_oracle():
+    """le_fix_rng_set_state / le_fix_rng_get_state (RanMars::get_state layout, src/random_mars.cpp:297-319): the device
+    generator after `consumed` draws holds exactly the oracle's u[], i97, j97, c; a state set from the oracle reads back
+    unchanged and continues the same stream"""
+    from oracle import restate as R
+    from lammps_le_b200 import systems
+    from lammps_le_b200.engine import LE_FIX_EX_LOAD, LE_FIX_EX_UNLOAD
+    s = systems.chromatin_chain(2000, 20, rho=0.2, seed=11)
+    e = systems.make_engine(s, velocities=np.zeros((2000, 3)))
+
+    def state_of(g):
+        return np.array(list(g.u) + [g.i97, g.j97, g.c, g.cd, g.cm], dtype=np.float64)
+
+    for seed, consumed in ((684474, 0), (456456, 5), (12345, 1234)):
+        g = R.RanMars(seed)
+        for _ in range(consumed):
+            g.uniform()
+        e.fix_rng_reset(LE_FIX_EX_LOAD, seed, consumed)
+        got = e.fix_rng_get_state(LE_FIX_EX_LOAD)
+        assert np.array_equal(got, state_of(g)), (seed, consumed)
+        e.fix_rng_set_state(LE_FIX_EX_UNLOAD, state_of(g))
+        assert np.array_equal(e.fix_rng_get_state(LE_FIX_EX_UNLOAD), state_of(g))
+    bad = state_of(R.RanMars(77)); bad[99] = 5
+    with pytest.raises(Exception):
+        e.fix_rng_set_state(LE_FIX_EX_LOAD, bad)
+    e.close()
