@@ -1,7 +1,7 @@
 /* run_style le/b200 -- the LAMMPS-side binding of libleb200.so (include/le_b200.h): an integrator style that hands the
    whole timestep loop of a chromatin + loop-extrusion deck to the B200 engine, the way src/KOKKOS/verlet_kokkos.cpp
-   replaces Verlet.  A maintainer drops this pair of files into src/USER-LE/ (tests build it against the reference sources
-   into oracle/_ref/b200/lmp_b200, oracle/build_ref.py).  Everything the engine needs is read from the objects the input
+   replaces Verlet.  A maintainer drops this pair of files into src/USER-LE/ (the repository's tests build it against the
+   reference sources).  Everything the engine needs is read from the objects the input
    script has already built (Force, Modify, Neighbor, Atom); the deck itself only gains the line `run_style le/b200`. */
 #ifdef INTEGRATE_CLASS
 
