@@ -12,7 +12,7 @@ One bench "step" = `--md-steps` MD timesteps (default 500 = one full USER-LE cyc
 value      whole-job atom-steps/s with all state resident in HBM when the timed region starts
 e2e        same metric through the C ABI with HOST buffers: every step uploads positions+velocities from
            pinned host memory, runs, and downloads positions
-roofline   fused step kernel (k_step3, le_step3.cuh): algorithmic bytes (72.1 + 4 nbar per atom-step, nbar measured)
+roofline   fused step kernel (k_step4, le_step4.cuh): algorithmic bytes (72.1 + 4 nbar per atom-step, nbar measured)
            / its live CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
 cpu_baseline  the compiled reference (oracle/_ref, threaded USER-OMP build when present, up to 16 host threads) on a
               bounded sample of the same workload
@@ -102,11 +102,11 @@ REF_LE_LINES = ["fix loop all extrusion 500 1 2 3 0.5 2 4",
                 "fix unloading all ex_unload 100 2 0.5 prob 0.05 456456"]
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_step3<0,0,1> launch at 1M beads from the committed ncu --set full
-# capture (profiles/r02_ncu_full_kstep3_kbuild3.txt): an OFFLINE figure of this kernel on this workload (ncu cannot run inside
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_step4<0,0,1> launch at 1M beads from the committed ncu --set full
+# capture (profiles/r02_ncu_full_kstep4_kbuild3.txt): an OFFLINE figure of this kernel on this workload (ncu cannot run inside
 # the bench; it replays every launch with a flushed L2, so this is cold-cache traffic).  Printed only for the configuration
 # it was captured on (1 GPU, 1M beads, this kernel), null otherwise.
-NCU_TRAFFIC = {"kernel": "k_step3<0,0,1>", "bytes": 59.5e6, "source": "profiles/r02_ncu_full_kstep3_kbuild3.txt"}
+NCU_TRAFFIC = {"kernel": "k_step4<0,0,1>", "bytes": 55.3e6, "source": "profiles/r02_ncu_full_kstep4_kbuild3.txt"}
 LE_HALO = 6.0   # ghost shell for USER-LE on several GPUs: longest extruder bond (FENE R0 = 4) + one backbone bond (1.5) + skin (4 cell layers here)
 
 
