@@ -42,6 +42,10 @@ struct LeFixDev {
   int *flag, *scan, *scan2, *ndraw, *tasks, *blocksum;
   unsigned char *done;
   int *counters;        // [16] device counters
+  int *mark_list;       // [2][mark_cap] tags of the end points of the bonds an event broke ([0]) / created ([1])
+  int *mark_n;          // [0], [1]: entries of the two lists; [2]: stamp of the current topology sweep
+  int *infl_stamp;      // [N] last sweep that looked at the atom (every candidate is tested once per sweep)
+  int mark_cap;
   double *draws;
   int draws_cap;
   int *rm_base;         // [193] raw values ahead of the current state (k_ranmars_base)
@@ -77,6 +81,8 @@ static int le_fix_alloc(LeFixDev &f, int n, int maxspecial, std::vector<void *> 
   r |= A((void **)&f.tasks, n1 * 4); r |= A((void **)&f.blocksum, (n1 / 1024 + 2) * 4);
   r |= A((void **)&f.done, n1);
   r |= A((void **)&f.counters, 16 * 4);
+  f.mark_cap = 2 * n + 16;
+  r |= A((void **)&f.mark_list, (size_t)2 * f.mark_cap * 4); r |= A((void **)&f.mark_n, 4 * 4); r |= A((void **)&f.infl_stamp, n1 * 4);
   f.draws_cap = 2 * n + 64;
   r |= A((void **)&f.draws, (size_t)f.draws_cap * 8);
   r |= A((void **)&f.rngdev, 3 * sizeof(RngDev));
@@ -515,35 +521,63 @@ __device__ void rebuild_special_one(const Dev &d, int t) {
   for (int i = cn1; i < cn3; i++) sl[i] = copy[i];
 }
 
+// an end point of a broken (which 0) / created (which 1) bond joins the event's list of marked atoms
+__device__ __forceinline__ void le_mark(const LeFixDev &f, int which, int tag) {
+  const int q = atomicAdd(&f.mark_n[which], 1);
+  if (q < f.mark_cap) f.mark_list[(size_t)which * f.mark_cap + q] = tag;
+}
+
 // update_topology sweeps (fix_extrusion.cpp:924-1002, fix_ex_load.cpp:700-751, fix_ex_unload.cpp:417-463).
 // mode 0: broken bonds, marks = final_remove: influenced if endpoint, or BOTH ends of one broken bond are in
 //         the full special list;  mode 1: created bonds, marks = final_add: endpoint, or EITHER end among 1-2/1-3.
-// Two kernels: a light sweep over all tags that only DETECTS the influenced atoms and appends them to a list
-// (few registers, full occupancy, streams the tables once), then rebuild_special_one over that short list (the
+// Two kernels: k_le_topo_detect collects the influenced atoms in a list, then rebuild_special_one runs over that list (the
 // rebuilds commute: each writes only its own atom's 1-3/1-4 tiers and reads only 1-2 tiers, which no rebuild
 // touches).
-__global__ void k_le_topo_detect(Dev d, const int *marks, int mode, const int *gate, int *list, int *nlist) {
-  if (gate && *gate == 0) return;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) {
-    bool infl = marks[i] != 0;
-    if (!infl) {
-      const int *sl = d.special + (size_t)i * d.maxspecial;
-      if (mode == 0) {
-        const int n = d.nspecial[(size_t)i * 3 + 2];
-        for (int k = 0; k < n && !infl; k++) {
-          const int s = sl[k];
-          const int p = marks[s - 1];
-          if (p == 0) continue;
-          int found = 0;
-          for (int q = 0; q < n; q++) if (sl[q] == s || sl[q] == p) found++;
-          if (found == 2) infl = true;
-        }
-      } else {
-        const int n = d.nspecial[(size_t)i * 3 + 1];
-        for (int k = 0; k < n; k++) if (marks[sl[k] - 1] != 0) { infl = true; break; }
-      }
+// the influence test of one atom (tag i + 1), exactly as the reference's sweeps state it
+__device__ __forceinline__ bool le_influenced(const Dev &d, const int *marks, int mode, int i) {
+  if (marks[i] != 0) return true;
+  const int *sl = d.special + (size_t)i * d.maxspecial;
+  if (mode == 0) {
+    const int n = d.nspecial[(size_t)i * 3 + 2];
+    for (int k = 0; k < n; k++) {
+      const int s = sl[k];
+      const int p = marks[s - 1];
+      if (p == 0) continue;
+      int found = 0;
+      for (int q = 0; q < n; q++) if (sl[q] == s || sl[q] == p) found++;
+      if (found == 2) return true;
     }
-    if (infl) list[atomicAdd(nlist, 1)] = i + 1;
+  } else {
+    const int n = d.nspecial[(size_t)i * 3 + 1];
+    for (int k = 0; k < n; k++) if (marks[sl[k] - 1] != 0) return true;
+  }
+  return false;
+}
+// Detection without a sweep over all tags: an atom can only be influenced if a marked atom (an end point of a broken /
+// created bond) is on its special list, and special lists are mutual -- so the candidates are the marked atoms, the atoms
+// on their special lists and (a margin for lists that an earlier sweep of the same event has already rebuilt on one side
+// only) the atoms on THOSE lists.  Every candidate is put to the reference's own test once (stamp per sweep).  At the
+// 10^6-bead bench an event marks ~10^3 atoms: 10^5 tests instead of a pass over N (x GPUs, the logic is replicated).
+__global__ void k_le_topo_detect(Dev d, LeFixDev f, const int *marks, int mode, const int *gate, int *list, int *nlist) {
+  if (gate && *gate == 0) return;
+  const int nm = min(f.mark_n[mode], f.mark_cap), stamp = f.mark_n[2];
+  const int *ml = f.mark_list + (size_t)mode * f.mark_cap;
+  auto visit = [&](int tag) {
+    if (atomicExch(&f.infl_stamp[tag - 1], stamp) == stamp) return;      // somebody has tested this atom in this sweep
+    if (le_influenced(d, marks, mode, tag - 1)) list[atomicAdd(nlist, 1)] = tag;
+  };
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < nm; m += gridDim.x * blockDim.x) {
+    const int t = ml[m];
+    visit(t);
+    const int *s1 = d.special + (size_t)(t - 1) * d.maxspecial;
+    const int n1 = d.nspecial[(size_t)(t - 1) * 3 + 2];
+    for (int a = 0; a < n1; a++) {
+      const int u = s1[a];
+      visit(u);
+      const int *s2 = d.special + (size_t)(u - 1) * d.maxspecial;
+      const int n2 = d.nspecial[(size_t)(u - 1) * 3 + 2];
+      for (int b = 0; b < n2; b++) visit(s2[b]);
+    }
   }
 }
 __global__ void k_le_topo_rebuild(Dev d, const int *list, int *nlist) {
@@ -556,7 +590,7 @@ __global__ void k_le_topo_rebuild(Dev d, const int *list, int *nlist) {
     topo_pack_one(d, list[k] - 1);
   }
 }
-__global__ void k_le_topo_reset(int *nlist) { *nlist = 0; }
+__global__ void k_le_topo_reset(int *nlist, int *mark_n) { *nlist = 0; mark_n[2]++; }
 
 // ------------------------------------------------------------------------------------------------
 // fix extrusion
@@ -573,6 +607,7 @@ __global__ void k_ext_init(LeView V, int btype) {
     f.to_add[i] = 0; f.to_remove[i] = 0; f.final_add[i] = 0; f.final_remove[i] = 0;
     f.distsq[i] = LE_BIG; f.claim[i] = ~0ull; f.partner[i] = 0;
     if (i < 16) f.counters[i] = 0;
+    if (i < 2) f.mark_n[i] = 0;
   }
 }
 
@@ -767,6 +802,7 @@ struct BreakTask {
       delete_bond_slot(d, ti, r);
       special_remove12(d, ti, r);
       f.final_remove[ti - 1] = r; f.final_remove[r - 1] = ti;
+      le_mark(f, 0, ti); le_mark(f, 0, r);
       if (ti < r) atomicAdd(&f.counters[CNT_NBREAK], 1);
     }
   }
@@ -790,6 +826,7 @@ __global__ void k_ext_create(LeView V, int btype) {
       d.num_bond[i] = nb + 1;
       special_insert12(d, ti, tj);
       f.final_add[i] = tj; f.final_add[tj - 1] = ti;
+      le_mark(f, 1, ti); le_mark(f, 1, tj);
       if (ti < tj) atomicAdd(&f.counters[CNT_NCREATE], 1);
     }
   }
@@ -864,6 +901,7 @@ __global__ void k_unl_candidates(LeView V, UnloadArgs A) {
     f.final_remove[i] = 0; f.final_add[i] = 0;
     f.flag[i] = partner != 0;
     if (i < 16) f.counters[i] = 0;
+    if (i < 2) f.mark_n[i] = 0;
   }
 }
 
@@ -886,6 +924,7 @@ __global__ void k_unl_break(LeView V, UnloadArgs A) {
     delete_bond_slot(d, ti, p);
     special_remove12(d, ti, p);
     f.final_remove[i] = p; f.final_remove[p - 1] = ti;
+    le_mark(f, 0, ti); le_mark(f, 0, p);
     if (ti < p) atomicAdd(&f.counters[CNT_NBREAK], 1);
   }
 }
@@ -903,6 +942,7 @@ __global__ void k_load_init(LeView V, int btype) {
     f.partner[i] = 0; f.final_add[i] = 0; f.final_remove[i] = 0;
     f.distsq[i] = LE_BIG; f.claim[i] = ~0ull;
     if (i < 16) f.counters[i] = 0;
+    if (i < 2) f.mark_n[i] = 0;
   }
 }
 
@@ -1044,6 +1084,7 @@ __global__ void k_load_create(LeView V, LoadArgs A) {
       if (k >= 0) { int4 *pp = &d.pos[V.cur()][k]; pp->w = (pp->w & ~7) | (nty - 1); }
     }
     f.final_add[i] = p; f.final_add[p - 1] = ti;
+    le_mark(f, 1, ti); le_mark(f, 1, p);
     if (ti < p) atomicAdd(&f.counters[CNT_NCREATE], 1);
   }
 }

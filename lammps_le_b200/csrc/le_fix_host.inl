@@ -168,13 +168,13 @@ static void run_executor(le_ctx *c, const Task &T, unsigned base) {
   LAUNCH(c, k_exec_finish<Task>, 1, LE_EXEC_THREADS, T, f.claim, f.done, (const int *)f.exec_rem, base);
 }
 
-// update_topology sweep: detect the influenced atoms (light, all tags), rebuild their special lists (short list)
+// update_topology sweep: detect the influenced atoms (around the marked end points), rebuild their special lists
 static void topo_sweep(le_ctx *c, const int *marks, int mode) {
   LeFixDev &f = c->lf;
   int *nlist = f.counters + CNT_NLIST;
   const int *gate = (const int *)(f.counters + CNT_TOTAL);
-  LAUNCH(c, k_le_topo_reset, 1, 1, nlist);
-  LAUNCH(c, k_le_topo_detect, std::min(grid_for(c->N, 256), 148 * 8), 256, c->d, marks, mode, gate, f.tasks, nlist);
+  LAUNCH(c, k_le_topo_reset, 1, 1, nlist, f.mark_n);
+  LAUNCH(c, k_le_topo_detect, 148, 128, c->d, f, marks, mode, gate, f.tasks, nlist);
   LAUNCH(c, k_le_topo_rebuild, 296, 128, c->d, (const int *)f.tasks, nlist);
 }
 
