@@ -566,18 +566,17 @@ __global__ void k_le_topo_detect(Dev d, LeFixDev f, const int *marks, int mode, 
     if (atomicExch(&f.infl_stamp[tag - 1], stamp) == stamp) return;      // somebody has tested this atom in this sweep
     if (le_influenced(d, marks, mode, tag - 1)) list[atomicAdd(nlist, 1)] = tag;
   };
-  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < nm; m += gridDim.x * blockDim.x) {
-    const int t = ml[m];
-    visit(t);
-    const int *s1 = d.special + (size_t)(t - 1) * d.maxspecial;
-    const int n1 = d.nspecial[(size_t)(t - 1) * 3 + 2];
-    for (int a = 0; a < n1; a++) {
-      const int u = s1[a];
-      visit(u);
-      const int *s2 = d.special + (size_t)(u - 1) * d.maxspecial;
-      const int n2 = d.nspecial[(size_t)(u - 1) * 3 + 2];
-      for (int b = 0; b < n2; b++) visit(s2[b]);
-    }
+  // one thread per (marked atom, entry of its special list): the thread visits that atom and walks ITS special list
+  const int per = d.maxspecial + 1;
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < nm * per; w += gridDim.x * blockDim.x) {
+    const int t = ml[w / per], a = w % per - 1;
+    if (a < 0) { visit(t); continue; }
+    if (a >= d.nspecial[(size_t)(t - 1) * 3 + 2]) continue;
+    const int u = d.special[(size_t)(t - 1) * d.maxspecial + a];
+    visit(u);
+    const int *s2 = d.special + (size_t)(u - 1) * d.maxspecial;
+    const int n2 = d.nspecial[(size_t)(u - 1) * 3 + 2];
+    for (int b = 0; b < n2; b++) visit(s2[b]);
   }
 }
 __global__ void k_le_topo_rebuild(Dev d, const int *list, int *nlist) {

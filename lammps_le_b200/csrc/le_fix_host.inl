@@ -174,7 +174,7 @@ static void topo_sweep(le_ctx *c, const int *marks, int mode) {
   int *nlist = f.counters + CNT_NLIST;
   const int *gate = (const int *)(f.counters + CNT_TOTAL);
   LAUNCH(c, k_le_topo_reset, 1, 1, nlist, f.mark_n);
-  LAUNCH(c, k_le_topo_detect, 148, 128, c->d, f, marks, mode, gate, f.tasks, nlist);
+  LAUNCH(c, k_le_topo_detect, 296, 256, c->d, f, marks, mode, gate, f.tasks, nlist);
   LAUNCH(c, k_le_topo_rebuild, 296, 128, c->d, (const int *)f.tasks, nlist);
 }
 
