@@ -67,7 +67,6 @@ struct Params {
   // pair lj/cut (PairLJCut::init_one, src/pair_lj_cut.cpp:512-535)
   int ntypes, nbondtypes;
   int pair_uniform;     // every type pair has the same lj/cut coefficients -> table index 0
-  int pair32;           // WCA pair terms in fp32 (fp32 partial sum of an atom's pair forces, then fp64 with the bonds); LE_PAIR_FP32=1
   double cutneighsq[LE_MAXT * LE_MAXT];
   float cutneighmaxsq_f;
   float cutsq[LE_MAXT * LE_MAXT], lj1[LE_MAXT * LE_MAXT], lj2[LE_MAXT * LE_MAXT];
