@@ -225,6 +225,11 @@ int le_observables(le_ctx *c, int ns, const int *s_list, double rc, int btype, i
  *   le_dd_get_handle  after le_upload_atoms: 64-byte CUDA IPC handle of this GPU's peer-visible arena
  *   le_dd_connect     handles of all ranks (all-gathered by the caller, e.g. torch.distributed), rank-major */
 int le_dd_init(le_ctx *c, int rank, int nranks, double halo_distance);
+/* slab cuts at upload: 1 (default) = where the cumulative atom count crosses r N / P (`balance 1.0 shift x`, src/balance.cpp),
+ * 0 = equal-width slabs (the reference's bricks without a balance command).  `fix balance` (src/fix_balance.cpp:191-270) is
+ * the host sequence DDEngine.rebalance(): imbalance factor from the owned counts, then a fresh context cut from the CURRENT
+ * configuration with the whole state carried over. */
+int le_dd_balance(le_ctx *c, int mode);
 int le_dd_get_handle(le_ctx *c, void *handle64);
 int le_dd_connect(le_ctx *c, const void *handles);
 /* raw per-GPU tallies behind a thermo record / the last le_compute_forces: [16] = sum m v^2, evdwl, ebond,

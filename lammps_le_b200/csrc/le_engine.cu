@@ -100,6 +100,7 @@ struct le_ctx {
   int nranks, rank;
   double halo_dist;
   std::vector<int> xcut;                // slab boundaries in x-cells, [nranks + 1]; empty = equal numbers of cell layers
+  int dd_balance;                       // 1: cuts by cumulative atom count at upload (`balance 1.0 shift x`), 0: equal-width slabs (no balance command)
   void *arena; size_t arena_bytes;      // peer-visible allocation (CUDA IPC): pos, pos_hold, cell_start, inbox, flags, geo
   void *peer_base[LE_MAXRANKS];
   bool peers_open;
@@ -239,6 +240,7 @@ extern "C" int le_create(le_ctx **out, int device, const double boxlo[3], const 
   c->x_plain[0] = c->x_plain[1] = nullptr; c->x_tail[0] = c->x_tail[1] = nullptr;
   c->direct_launches = c->graph_node_launches = c->direct_builds = 0;
   memset(&c->gkey, 0, sizeof c->gkey);
+  c->dd_balance = 1;
   c->nranks = 1; c->rank = 0; c->halo_dist = 0.0; c->arena = nullptr; c->arena_bytes = 0; c->peers_open = false; c->rb = nullptr;
   memset(c->peer_base, 0, sizeof c->peer_base);
   c->st_tag = c->st_img = nullptr; c->st_x = c->st_v = nullptr;
@@ -735,7 +737,7 @@ extern "C" int le_upload_atoms(le_ctx *c, int n, const int *tag, const int *type
       for (int rk = 1; rk < Pn; rk++) {
         const long long target = (long long)n * rk / Pn;
         while (xq < ncx && cum + per_layer[xq] <= target) cum += per_layer[xq++];
-        int cut = xq;
+        int cut = c->dd_balance ? xq : (int)((long long)rk * ncx / Pn);       // (no balance command: equal-width bricks, src/comm.cpp)
         cut = std::max(cut, c->xcut[rk - 1] + wmin);
         cut = std::min(cut, ncx - (Pn - rk) * wmin);
         c->xcut[rk] = cut;
@@ -868,6 +870,15 @@ extern "C" int le_dd_get_handle(le_ctx *c, void *handle64) {
   CK(cudaIpcGetMemHandle(&h, c->arena));
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   memcpy(handle64, &h, 64);
+  return LE_OK;
+}
+
+/* 0 = equal-width slabs (the reference's decomposition without a `balance` command), 1 = cuts where the cumulative atom count
+ * of the uploaded configuration crosses r N / P (`balance 1.0 shift x`, src/balance.cpp; default).  Before le_upload_atoms. */
+extern "C" int le_dd_balance(le_ctx *c, int mode) {
+  if (!c) return LE_EINVAL;
+  if (c->atoms_loaded) return fail(c, LE_ESTATE, "le_dd_balance must precede le_upload_atoms");
+  c->dd_balance = mode ? 1 : 0;
   return LE_OK;
 }
 

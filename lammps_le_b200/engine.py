@@ -88,7 +88,7 @@ def load_library():
         "le_gen_saw_chains": [I, I, D, D, D, C.c_uint64, pd, pi], "le_gen_lattice_melt": [I, I, D, pd, pd, pi],
         "le_observables": [P, I, pi, D, I, I, I, pd, C.POINTER(I64), C.POINTER(I64)],
         "le_local_capacity": [P], "le_download_owned": [P, pi, pi, pd, pi, pd], "le_upload_owned": [P, I, pi, pd, pi, pd],
-        "le_dd_init": [P, I, I, D], "le_dd_get_handle": [P, C.c_void_p], "le_dd_connect": [P, C.c_void_p],
+        "le_dd_init": [P, I, I, D], "le_dd_balance": [P, I], "le_dd_get_handle": [P, C.c_void_p], "le_dd_connect": [P, C.c_void_p],
         "le_get_thermo_sums": [P, I, pd], "le_get_force_sums": [P, pd],
         "le_host_velocity_create": [I, pi, pd, pd, D, I, I, I, I, pd],
     }
@@ -156,6 +156,18 @@ def _i32(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
 
 
+def _journaled(fn):
+    """record a settings / fix call so that the context can be rebuilt with the same script (DDEngine.rebalance)"""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        out = fn(self, *args, **kwargs)
+        self._journal.append((fn.__name__, args, kwargs))
+        return out
+    return wrapper
+
+
 class Engine:
     """One simulation context on one GPU (the reference's `LAMMPS` object for this path)."""
 
@@ -172,6 +184,7 @@ class Engine:
             raise LeError(rc, msg)
         self.boxlo, self.boxhi = np.array(lo), np.array(hi)
         self.bpa, self.maxspecial, self.ntypes = 4, 16, 1
+        self._journal = getattr(self, "_journal", [])
 
     def close(self):
         if getattr(self, "_h", None):
@@ -189,11 +202,13 @@ class Engine:
             raise LeError(rc, self.lib.le_last_error(self._h).decode())
 
     # ---- settings ----
+    @_journaled
     def set_types(self, masses, nbondtypes):
         m = _f64(masses)
         self.ntypes = len(m)
         self._ck(self.lib.le_set_types(self._h, len(m), _pd(m), nbondtypes))
 
+    @_journaled
     def set_pair_lj(self, epsilon, sigma, cut, shift=True):
         """epsilon/sigma/cut: scalars (all pairs) or ntypes x ntypes matrices."""
         nt = self.ntypes
@@ -201,58 +216,73 @@ class Engine:
                    for a in (epsilon, sigma, cut)]
         self._ck(self.lib.le_set_pair_lj(self._h, nt, _pd(e), _pd(s), _pd(c), 1 if shift else 0))
 
+    @_journaled
     def set_bond(self, btype, style, params):
         style = {"fene": LE_BOND_FENE, "harmonic": LE_BOND_HARMONIC, "none": LE_BOND_NONE}.get(style, style)
         p = np.zeros(4)
         p[:len(params)] = params
         self._ck(self.lib.le_set_bond(self._h, btype, style, _pd(p)))
 
+    @_journaled
     def set_special(self, lj):
         a = _f64(lj)
         self._ck(self.lib.le_set_special(self._h, _pd(a)))
 
+    @_journaled
     def set_neighbor(self, skin, every=1, delay=10, check=1):
         self._ck(self.lib.le_set_neighbor(self._h, skin, every, delay, check))
 
+    @_journaled
     def set_neighbor_capacity(self, n):
         self._ck(self.lib.le_set_neighbor_capacity(self._h, n))
 
+    @_journaled
     def set_newton(self, pair=1, bond=0):
         self._ck(self.lib.le_set_newton(self._h, pair, bond))
 
+    @_journaled
     def set_capacity(self, bond_per_atom, maxspecial):
         self._ck(self.lib.le_set_capacity(self._h, bond_per_atom, maxspecial))
         self.bpa, self.maxspecial = bond_per_atom, maxspecial
 
+    @_journaled
     def set_timestep(self, dt):
         self._ck(self.lib.le_set_timestep(self._h, dt))
 
     def reset_timestep(self, step):
         self._ck(self.lib.le_reset_timestep(self._h, step))
 
+    @_journaled
     def thermo_every(self, n):
         self._ck(self.lib.le_thermo_every(self._h, n))
 
     # ---- fixes ----
+    @_journaled
     def fix_nve(self, enable=True):
         self._ck(self.lib.le_fix_nve(self._h, 1 if enable else 0))
 
+    @_journaled
     def fix_nve_limit(self, xmax):
         self._ck(self.lib.le_fix_nve_limit(self._h, xmax))
 
+    @_journaled
     def fix_langevin(self, t_start, t_stop, damp, seed):
         self._ck(self.lib.le_fix_langevin(self._h, t_start, t_stop, damp, seed))
 
+    @_journaled
     def fix_extrusion(self, nevery, neutral, left, right, p_through, btype, roadblock=-1, seed=12345):
         self._ck(self.lib.le_fix_extrusion(self._h, nevery, neutral, left, right, p_through, btype, roadblock, seed))
 
+    @_journaled
     def fix_ex_load(self, nevery, itype, jtype, rc, btype, prob=1.0, seed=12345, iparam=(0, 0), jparam=(0, 0)):
         self._ck(self.lib.le_fix_ex_load(self._h, nevery, itype, jtype, rc, btype, prob, seed,
                                          iparam[0], iparam[1], jparam[0], jparam[1]))
 
+    @_journaled
     def fix_ex_unload(self, nevery, btype, rc, prob=1.0, seed=12345):
         self._ck(self.lib.le_fix_ex_unload(self._h, nevery, btype, rc, prob, seed))
 
+    @_journaled
     def unfix(self, which):
         self._ck(self.lib.le_unfix(self._h, which))
 

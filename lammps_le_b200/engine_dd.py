@@ -49,10 +49,58 @@ def merge_csr(parts):
 
 
 class DDEngine(Engine):
-    def __init__(self, boxlo, boxhi, periodic=(1, 1, 1), device=0, rank=0, world=1, halo=0.0, group=None):
+    def __init__(self, boxlo, boxhi, periodic=(1, 1, 1), device=0, rank=0, world=1, halo=0.0, group=None, balance=True):
         super().__init__(boxlo, boxhi, periodic, device)
         self.rank, self.world, self.group = rank, world, group
+        self._ctor = (boxlo, boxhi, periodic, device, float(halo))
         self._ck(self.lib.le_dd_init(self._h, rank, world, float(halo)))
+        if not balance:
+            self._ck(self.lib.le_dd_balance(self._h, 0))     # equal-width slabs, as the reference without a balance command
+
+    # ---- load balance ----
+    def owned_counts(self):
+        """atoms every GPU owns right now (length `world`)"""
+        n = np.zeros(self.world, dtype=np.int64)
+        n[self.rank] = self.download_owned(self.owned_buffers(pinned=False))
+        return self._allreduce(n)
+
+    def imbalance(self):
+        """max / mean of the owned counts: the `imbalance factor` of the reference's balance command (src/balance.cpp:245-300)"""
+        c = self.owned_counts().astype(np.float64)
+        return float(c.max() / c.mean())
+
+    def rebalance(self, thresh=1.0):
+        """Dynamic load balance in the sense of `fix balance N thresh shift x ...` (src/fix_balance.cpp:191-270, src/balance.cpp):
+        when the imbalance factor exceeds `thresh`, the slab cuts are placed anew where the cumulative atom count of the CURRENT
+        configuration crosses r N / P.  The cuts are part of the device layout (slab widths size the peer arenas and the ghost
+        regions), so the context is rebuilt from the recorded settings / fixes and the state is carried over: positions, image
+        flags, velocities, types, the per-atom bond and special tables (extruder bonds included), the Marsaglia state of each
+        USER-LE fix and the timestep.  Collective; returns (imbalance before, imbalance after) -- equal when nothing was done."""
+        before = self.imbalance()
+        if self.world == 1 or before <= thresh:
+            return before, before
+        x, im = self.positions()
+        v, ty, topo, step = self.velocities(), self.types(), self.topology(), int(self.timestep)
+        rng = {}
+        for which in (1, 2, 3):
+            try:
+                rng[which] = self.fix_rng_get_state(which)
+            except Exception:
+                pass
+        journal = list(self._journal)
+        self.barrier()
+        self.close()
+        boxlo, boxhi, periodic, device, halo = self._ctor
+        self._journal = []
+        DDEngine.__init__(self, boxlo, boxhi, periodic, device, self.rank, self.world, halo, self.group)
+        for name, args, kwargs in journal:
+            getattr(self, name)(*args, **kwargs)
+        self.upload_atoms(ty, x, v, im)
+        self.upload_topology(topo["num_bond"], topo["bond_type"], topo["bond_atom"], topo["nspecial"], topo["special"])
+        for which, st in rng.items():
+            self.fix_rng_set_state(which, st)
+        self.reset_timestep(step)
+        return before, self.imbalance()
 
     # ---- plumbing ----
     def _allreduce(self, a):

@@ -44,3 +44,16 @@ def test_dd_matches_single_gpu(world):
 def test_dd_melt_matches_single_gpu():
     """BASELINE configs[2] (bench/in.chain.scaled): the dense FENE melt replicated along x, one replica per GPU"""
     _run_dd(2, 29711, [0, 300, "melt"])
+
+
+@pytest.mark.gpu
+def test_dynamic_rebalance_keeps_the_trajectory():
+    """`fix balance` (src/fix_balance.cpp:191-270): equal-width slabs over a chain that crowds one part of the box, re-cut by atom
+    count in the middle of the run; trajectory and USER-LE topology equal the single-GPU run (scripts/dd_balance_check.py)"""
+    env = dict(os.environ)
+    if _ngpu() < 2:
+        env["LE_DD_SHARE_GPU"] = "1"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29721", os.path.join(ROOT, "scripts", "dd_balance_check.py"), "40000", "150"]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=1500, env=env)
+    assert "DD BALANCE CHECK PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
