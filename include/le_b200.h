@@ -246,6 +246,34 @@ int le_gen_saw_chains(int n, int nchains, double L, double step, double rmin, ui
 int le_gen_lattice_melt(int nchains, int len, double rho, double *L, double *x, int *image);
 
 /* ---- `velocity all create T seed ...` (host only) ------------------------------------------------ */
+/* ---- restart files (host only): the reference's binary format for this path -- write_restart / read_restart with units lj,
+ * atom_style bond, pair lj/cut, bond fene | harmonic | hybrid (src/write_restart.cpp:205-600, src/read_restart.cpp, lmprestart.h).
+ * The file carries the per-atom bond tables (extruder bonds included) but no special lists: after reading, hand the tables to
+ * le_upload_topology with NULL specials (Special::build, as read_restart does).  Pair matrices are indexed (i-1)*ntypes + (j-1),
+ * i <= j, as PairLJCut::write_restart stores them; bond_style hybrid stores its sub-style names only (BondHybrid::write_restart). */
+#define LE_RESTART_MAXT 8
+typedef struct le_restart_header {
+  int64_t ntimestep, natoms, nbonds;
+  int ntypes, nbondtypes, bond_per_atom, extra_bond_per_atom, maxspecial;
+  int newton_pair, newton_bond, periodic[3], nprocs_file, atom_sortfreq;
+  double boxlo[3], boxhi[3], special_lj[3], dt, comm_cutoff;
+  double mass[LE_RESTART_MAXT];
+  char version[32], units[16], atom_style[16], pair_style[32], bond_style[32];
+  double cut_global; int offset_flag, mix_flag, tail_flag;
+  int pair_setflag[LE_RESTART_MAXT * LE_RESTART_MAXT];
+  double pair_eps[LE_RESTART_MAXT * LE_RESTART_MAXT], pair_sigma[LE_RESTART_MAXT * LE_RESTART_MAXT], pair_cut[LE_RESTART_MAXT * LE_RESTART_MAXT];
+  int bond_coeffs_stored;
+  double bond_k[LE_RESTART_MAXT], bond_r0[LE_RESTART_MAXT], bond_eps[LE_RESTART_MAXT], bond_sigma[LE_RESTART_MAXT];
+  int nhybrid; char hybrid_styles[4][16];
+} le_restart_header;
+int le_host_restart_read_header(const char *path, le_restart_header *h, char *err, int errlen);
+/* atoms in file order; bond_type / bond_atom are [natoms][bond_per_atom]; any output may be NULL */
+int le_host_restart_read_atoms(const char *path, int *tag, int *type, int *image, int *molecule, double *x, double *v,
+                               int *num_bond, int *bond_type, int *bond_atom, char *err, int errlen);
+int le_host_restart_write(const char *path, const le_restart_header *h, const int *tag, const int *type, const int *image,
+                          const int *molecule, const double *x, const double *v, const int *num_bond, const int *bond_type,
+                          const int *bond_atom, char *err, int errlen);
+
 /* Velocity::create (src/velocity.cpp:162-401) for all atoms of a 3-d system in tag order: Park-Miller draws
  * (src/random_park.cpp) in the reference's order, 1/sqrt(mass) scaling, `mom yes` momentum zeroing, rescale to t_desired
  * with 3N-3 degrees of freedom (compute temp).  loop: 0 = all, 1 = local (one rank), 2 = geom (x[n*3] needed: the generator

@@ -12,7 +12,7 @@
 //   neighbor S bin | neigh_modify every|delay|check ... | pair_style lj/cut RC | pair_modify shift yes|no
 //   pair_coeff I J eps sigma [rc] | bond_style fene|harmonic|hybrid ... | bond_coeff N [style] ...
 //   fix ID all nve | nve/limit X | langevin T0 T1 damp seed | extrusion ... | ex_load ... | ex_unload ...
-//   unfix ID | timestep dt | reset_timestep N | thermo N | thermo_modify ... | run N
+//   unfix ID | timestep dt | reset_timestep N | thermo N | thermo_modify ... | run N | read_restart file | write_restart file
 //   thermo_style one | custom step elapsed dt time atoms temp press pe ke etotal evdwl epair ebond emol vol density lx ly lz bonds f_ID[1|2]
 //   minimize etol ftol maxiter maxeval | min_style cg
 //   velocity all create T seed [dist uniform|gaussian] [mom yes|no] [loop all|local|geom]
@@ -47,6 +47,9 @@ struct Deck {
   std::vector<double> x, v, mass;
   bool have_v = false, uploaded = false;
   int bpa = 1;                                         // bond_per_atom the context was sized with
+  // read_restart: the per-atom bond tables as the file holds them (slot order kept), sizes from its header
+  bool from_restart = false; int r_bpa = 0, r_maxspecial = 0; long long r_step = 0;
+  std::vector<int> r_nb, r_bt, r_ba;
   // settings
   double special[3] = {0.0, 0.0, 0.0};
   int newton_pair = 1, newton_bond = 1;
@@ -207,6 +210,16 @@ void init(Deck &d) {
   ck(d, le_set_neighbor(d.ctx, d.skin, d.every, d.delay, d.check));
   ck(d, le_set_timestep(d.ctx, d.dt));
   ck(d, le_thermo_every(d.ctx, d.thermo_every));
+  if (!d.uploaded && d.from_restart) {
+    d.bpa = d.r_bpa;
+    ck(d, le_set_capacity(d.ctx, d.bpa, std::max(d.r_maxspecial, 4)));
+    ck(d, le_upload_atoms(d.ctx, d.natoms, d.tag.data(), d.type.data(), d.x.data(), d.v.data(), d.image.data()));
+    // the special lists are not in a restart file: Special::build from the bond tables (src/read_restart.cpp:520-530)
+    if (d.newton_bond) ck(d, le_upload_bonds(d.ctx, d.nbonds, d.btype.data(), d.b1.data(), d.b2.data()));
+    else ck(d, le_upload_topology(d.ctx, d.r_nb.data(), d.r_bt.data(), d.r_ba.data(), nullptr, nullptr));
+    ck(d, le_reset_timestep(d.ctx, d.r_step));
+    d.uploaded = true;
+  }
   if (!d.uploaded) {
     // bond_per_atom / maxspecial as ReadData sizes them: the largest count in the file plus the "extra" head room
     std::vector<int> nb(d.natoms + 1, 0);
@@ -455,6 +468,113 @@ void write_data(Deck &d, const Words &w) {
   std::fclose(f);
 }
 
+// ---- read_restart / write_restart (src/read_restart.cpp, src/write_restart.cpp; the format lives in le_restart.cpp) ----------
+void read_restart(Deck &d, const Words &w) {
+  if (w.size() != 2) die("Illegal read_restart command");
+  if (d.ctx) die("Cannot read_restart after simulation box is defined");
+  le_restart_header h;
+  char err[256] = "";
+  if (le_host_restart_read_header(w[1].c_str(), &h, err, sizeof err)) die(err);
+  const int n = (int)h.natoms, bpa = std::max(h.bond_per_atom, 1);
+  std::vector<int> tag(n), type(n), image(n), mol(n), nb(n), bt((size_t)n * bpa, 0), ba((size_t)n * bpa, 0);
+  std::vector<double> x((size_t)3 * n), v((size_t)3 * n);
+  if (le_host_restart_read_atoms(w[1].c_str(), tag.data(), type.data(), image.data(), mol.data(), x.data(), v.data(), nb.data(), bt.data(), ba.data(), err, sizeof err)) die(err);
+  d.natoms = n; d.ntypes = h.ntypes; d.nbondtypes = h.nbondtypes; d.nbonds = (int)h.nbonds;
+  for (int q = 0; q < 3; q++) { d.lo[q] = h.boxlo[q]; d.hi[q] = h.boxhi[q]; d.special[q] = h.special_lj[q]; }
+  d.mass.assign(h.mass, h.mass + h.ntypes);
+  d.newton_pair = h.newton_pair; d.newton_bond = h.newton_bond; d.dt = h.dt;
+  // file order -> tag order
+  d.tag.resize(n); d.mol.resize(n); d.type.resize(n); d.image.resize(n); d.x.resize((size_t)3 * n); d.v.resize((size_t)3 * n);
+  d.r_nb.assign(n, 0); d.r_bt.assign((size_t)n * bpa, 0); d.r_ba.assign((size_t)n * bpa, 0);
+  for (int k = 0; k < n; k++) {
+    const int t = tag[k] - 1;
+    if (t < 0 || t >= n) die("Did not assign all restart atoms correctly");
+    d.tag[t] = t + 1; d.mol[t] = mol[k]; d.type[t] = type[k]; d.image[t] = image[k];
+    for (int q = 0; q < 3; q++) { d.x[3 * (size_t)t + q] = x[3 * (size_t)k + q]; d.v[3 * (size_t)t + q] = v[3 * (size_t)k + q]; }
+    d.r_nb[t] = nb[k];
+    for (int m = 0; m < nb[k]; m++) { d.r_bt[(size_t)t * bpa + m] = bt[(size_t)k * bpa + m]; d.r_ba[(size_t)t * bpa + m] = ba[(size_t)k * bpa + m]; }
+  }
+  d.btype.clear(); d.b1.clear(); d.b2.clear();
+  for (int t = 0; t < n; t++)
+    for (int m = 0; m < d.r_nb[t]; m++) {
+      const int p = d.r_ba[(size_t)t * bpa + m];
+      if (h.newton_bond || t + 1 < p) { d.btype.push_back(d.r_bt[(size_t)t * bpa + m]); d.b1.push_back(t + 1); d.b2.push_back(p); }
+    }
+  d.nbonds = (int)d.btype.size();
+  d.have_v = true; d.from_restart = true; d.r_bpa = bpa; d.r_maxspecial = h.maxspecial; d.r_step = h.ntimestep;
+  d.extra_bond = h.extra_bond_per_atom;
+  // force field as the file stores it
+  const int nt = h.ntypes;
+  d.eps.assign((size_t)nt * nt, 0.0); d.sigma = d.eps; d.cut = d.eps; d.coeff_set.assign(d.eps.size(), 0);
+  if (!std::strcmp(h.pair_style, "lj/cut")) {
+    d.pair_set = true; d.pair_cut = h.cut_global; d.shift = h.offset_flag;
+    for (int a = 0; a < nt; a++)
+      for (int b = a; b < nt; b++)
+        if (h.pair_setflag[a * nt + b]) {
+          d.eps[a * nt + b] = d.eps[b * nt + a] = h.pair_eps[a * nt + b]; d.sigma[a * nt + b] = d.sigma[b * nt + a] = h.pair_sigma[a * nt + b];
+          d.cut[a * nt + b] = d.cut[b * nt + a] = h.pair_cut[a * nt + b]; d.coeff_set[a * nt + b] = d.coeff_set[b * nt + a] = 1;
+        }
+  }
+  d.bond_styles.clear(); d.bond_coeff.clear();
+  if (!std::strcmp(h.bond_style, "hybrid")) { d.bond_styles.push_back("hybrid"); for (int m = 0; m < h.nhybrid; m++) d.bond_styles.push_back(h.hybrid_styles[m]); }   // bond_coeff must follow (BondHybrid::write_restart keeps the names only)
+  else if (h.bond_style[0]) {
+    d.bond_styles.push_back(h.bond_style);
+    const int sid = bond_style_id(h.bond_style);
+    for (int t = 0; t < h.nbondtypes; t++)
+      d.bond_coeff[t + 1] = {sid, sid == LE_BOND_FENE ? std::vector<double>{h.bond_k[t], h.bond_r0[t], h.bond_eps[t], h.bond_sigma[t]} : std::vector<double>{h.bond_k[t], h.bond_r0[t]}};
+  }
+  const int per[3] = {h.periodic[0], h.periodic[1], h.periodic[2]};
+  int rc = le_create(&d.ctx, 0, d.lo, d.hi, per);
+  if (rc) die(d.ctx ? le_last_error(d.ctx) : "no CUDA device (there is no CPU fallback)");
+  std::printf("  restoring atom style bond from restart\n  %d atoms\n  %d bonds\n", d.natoms, d.nbonds);
+}
+
+void write_restart(Deck &d, const Words &w) {
+  if (w.size() != 2) die("Illegal write_restart command");
+  if (!d.uploaded) init(d);
+  const int n = d.natoms, bpa = d.bpa;
+  le_restart_header h;
+  std::memset(&h, 0, sizeof h);
+  std::vector<double> x((size_t)3 * n), v((size_t)3 * n);
+  std::vector<int> im(n), ty(n), nb(n), bt((size_t)n * bpa), ba((size_t)n * bpa), tag(n), mol(n);
+  ck(d, le_download_x(d.ctx, x.data(), im.data()));
+  ck(d, le_download_v(d.ctx, v.data()));
+  ck(d, le_download_types(d.ctx, ty.data()));
+  ck(d, le_download_topology(d.ctx, nb.data(), bt.data(), ba.data(), nullptr, nullptr));
+  std::vector<int> mol_by_tag(n + 1, 0);
+  for (int k = 0; k < n; k++) mol_by_tag[d.tag[k]] = d.mol[k];
+  long long nbonds = 0;
+  for (int t = 0; t < n; t++) { tag[t] = t + 1; mol[t] = mol_by_tag[t + 1]; for (int m = 0; m < nb[t]; m++) if (d.newton_bond || t + 1 < ba[(size_t)t * bpa + m]) nbonds++; }
+  h.ntimestep = le_timestep(d.ctx); h.natoms = n; h.nbonds = nbonds;
+  h.ntypes = d.ntypes; h.nbondtypes = d.nbondtypes; h.bond_per_atom = bpa; h.extra_bond_per_atom = d.extra_bond; h.maxspecial = d.from_restart ? d.r_maxspecial : 2 + d.extra_special;
+  h.newton_pair = d.newton_pair; h.newton_bond = d.newton_bond; h.atom_sortfreq = 1000;
+  for (int q = 0; q < 3; q++) { h.periodic[q] = 1; h.boxlo[q] = d.lo[q]; h.boxhi[q] = d.hi[q]; h.special_lj[q] = d.special[q]; }
+  h.dt = d.dt;
+  for (int t = 0; t < d.ntypes && t < LE_RESTART_MAXT; t++) h.mass[t] = d.mass[t];
+  std::snprintf(h.units, sizeof h.units, "lj"); std::snprintf(h.pair_style, sizeof h.pair_style, "lj/cut");
+  h.cut_global = d.pair_cut; h.offset_flag = d.shift; h.mix_flag = 0; h.tail_flag = 0;
+  const int nt = d.ntypes;
+  for (int a = 0; a < nt; a++)
+    for (int b = a; b < nt; b++) {
+      const int k = a * nt + b;
+      h.pair_setflag[k] = d.coeff_set[k] ? 1 : 0; h.pair_eps[k] = d.eps[k]; h.pair_sigma[k] = d.sigma[k]; h.pair_cut[k] = d.cut[k];
+    }
+  if (!d.bond_styles.empty() && d.bond_styles[0] != "hybrid") {
+    std::snprintf(h.bond_style, sizeof h.bond_style, "%s", d.bond_styles[0].c_str());
+    for (auto &kv : d.bond_coeff) {
+      const int t = kv.first - 1; const std::vector<double> &p = kv.second.second;
+      if (t < 0 || t >= LE_RESTART_MAXT) continue;
+      h.bond_k[t] = p.size() > 0 ? p[0] : 0; h.bond_r0[t] = p.size() > 1 ? p[1] : 0; h.bond_eps[t] = p.size() > 2 ? p[2] : 0; h.bond_sigma[t] = p.size() > 3 ? p[3] : 0;
+    }
+  } else if (d.bond_styles.size() > 1) {
+    std::snprintf(h.bond_style, sizeof h.bond_style, "hybrid");
+    h.nhybrid = (int)std::min<size_t>(d.bond_styles.size() - 1, 4);
+    for (int m = 0; m < h.nhybrid; m++) std::snprintf(h.hybrid_styles[m], sizeof h.hybrid_styles[m], "%s", d.bond_styles[m + 1].c_str());
+  }
+  char err[256] = "";
+  if (le_host_restart_write(w[1].c_str(), &h, tag.data(), ty.data(), im.data(), mol.data(), x.data(), v.data(), nb.data(), bt.data(), ba.data(), err, sizeof err)) die(err);
+}
+
 void expand_types(const std::string &s, int n, int &a, int &b) {     // utils::bounds: "*", "N", "N*", "*M", "N*M"
   const size_t star = s.find('*');
   if (star == std::string::npos) { a = b = inum(s); }
@@ -578,6 +698,7 @@ void execute_cmd(Deck &d, const Words &w) {
     else if (w.size() == 5 && w[1] == "lj/coul") { for (int k = 0; k < 3; k++) d.special[k] = num(w[2 + k]); }
     else die("Illegal special_bonds command");
   } else if (c == "read_data") read_data(d, w);
+  else if (c == "read_restart") read_restart(d, w);
   else if (c == "mass") { if (w.size() != 3 || d.mass.empty()) die("Illegal mass command"); int a, b; expand_types(w[1], d.ntypes, a, b); for (int t = a; t <= b; t++) d.mass[t - 1] = num(w[2]); }
   else if (c == "neighbor") { if (w.size() != 3 || w[2] != "bin") die("Illegal neighbor command (only bin)"); d.skin = num(w[1]); }
   else if (c == "neigh_modify") {
@@ -684,6 +805,7 @@ void execute_cmd(Deck &d, const Words &w) {
   else if (c == "velocity") velocity(d, w);
   else if (c == "run") run(d, w);
   else if (c == "write_data") write_data(d, w);
+  else if (c == "write_restart") write_restart(d, w);
   else die("Unknown command: " + c);
 }
 

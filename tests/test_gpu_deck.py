@@ -177,3 +177,32 @@ def test_deck_dump_local_bonds(tmp_path):
     assert lines[8] == "ITEM: ENTRIES index c_b[1] c_b[2] c_b[3] "
     first = [float(v) for v in lines[9].split()]
     assert first == [1.0, 1.0, 2.0, 1.0]
+
+
+@pytest.mark.gpu
+def test_restart_files_through_le_deck(tmp_path):
+    """read_restart of a file the compiled reference wrote (tests/golden/ref_restart_small.bin: chain with extruder bonds): the step-0
+    thermo line of `run 0` equals the energies of the same state uploaded through the Python binding; after a run, write_restart ->
+    read_restart in a second le_deck process continues with identical thermo (the bond tables incl. extruder bonds survive)."""
+    import shutil
+    from lammps_le_b200 import restart as RS
+    shutil.copy(os.path.join(GOLD, "ref_restart_small.bin"), tmp_path / "ref.restart")
+    exe = os.path.join(ROOT, "lammps_le_b200", "le_deck")
+    common = "neighbor 0.4 bin\nneigh_modify every 1 delay 0 check yes\nthermo_style custom step temp epair emol bonds\nthermo 20\n"
+    (tmp_path / "in.a").write_text("read_restart ref.restart\n" + common + "fix 1 all nve\nrun 40\nwrite_restart mid.restart\nrun 20\n")
+    (tmp_path / "in.b").write_text("read_restart mid.restart\n" + common + "fix 1 all nve\nrun 20\n")
+    ra = subprocess.run([exe, "-in", "in.a"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert ra.returncode == 0, ra.stdout[-2000:] + ra.stderr[-2000:]
+    rb = subprocess.run([exe, "-in", "in.b"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert rb.returncode == 0, rb.stdout[-2000:] + rb.stderr[-2000:]
+    rows = lambda out: [np.array([[float(v) for v in r.split()] for r in body.splitlines()])
+                        for body in re.findall(r"Step Temp E_pair E_mol Bonds \n(.*?)\nLoop time", out, re.S)]
+    a, b = rows(ra.stdout), rows(rb.stdout)
+    info, atoms = RS.read_restart(os.path.join(GOLD, "ref_restart_small.bin"))
+    assert a[0][0, 0] == info["ntimestep"] and a[0][0, 4] == info["nbonds"]
+    e = RS.engine_from_restart(info, atoms)
+    _, th = e.compute_forces()
+    e.close()
+    assert abs(a[0][0, 2] - th["epair"]) < 1e-6 * max(1.0, abs(th["epair"])) and abs(a[0][0, 3] - th["emol"]) < 1e-6 * abs(th["emol"])
+    # the second process starts where the first one wrote the file and prints what the first one printed from there on
+    assert np.array_equal(a[1][0], b[0][0]) and np.allclose(a[1], b[0], rtol=2e-6, atol=1e-9), (a[1], b[0])
