@@ -121,6 +121,9 @@ int le_fix_ex_load(le_ctx *c, int nevery, int itype, int jtype, double rc, int b
                    int seed, int imaxbond, int inewtype, int jmaxbond, int jnewtype);
 /* fix ID all ex_unload N btype Rmax prob f seed */
 int le_fix_ex_unload(le_ctx *c, int nevery, int btype, double rc, double prob, int seed);
+/* fix ID all bond/break N bondtype Rmax prob f seed (src/MC/fix_bond_break.cpp, the ancestor of ex_unload: same body, step gate
+ * `ntimestep % N` instead of `ntimestep % N - 2`); takes the ex_unload slot (unfix: LE_FIX_EX_UNLOAD) */
+int le_fix_bond_break(le_ctx *c, int nevery, int btype, double rmax, double prob, int seed);
 int le_unfix(le_ctx *c, int which);                         /* unfix */
 
 /* ---- atoms and topology ---------------------------------------------------------------- */

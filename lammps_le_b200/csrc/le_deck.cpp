@@ -281,7 +281,7 @@ void print_thermo(Deck &d, int first) {
   for (size_t k = 0; k < d.thermo_fix_cols.size(); k++) {
     const auto it = d.fix_style.find(d.thermo_fix_cols[k].id);
     if (it == d.fix_style.end()) die("Could not find thermo fix ID " + d.thermo_fix_cols[k].id);
-    fix_slot[k] = it->second == "extrusion" ? 0 : it->second == "ex_unload" ? 1 : it->second == "ex_load" ? 2 : -1;
+    fix_slot[k] = it->second == "extrusion" ? 0 : (it->second == "ex_unload" || it->second == "bond/break") ? 1 : it->second == "ex_load" ? 2 : -1;
     if (fix_slot[k] < 0) die("Thermo fix does not compute vector");
   }
   for (int q : cols) std::printf("%s ", q >= 1000 ? d.thermo_fix_cols[q - 1000].title.c_str() : THERMO_FIELDS[q].title);
@@ -614,6 +614,14 @@ void fix(Deck &d, const Words &w) {
       else die("Illegal fix ex_unload command");
     }
     ck(d, le_fix_ex_unload(d.ctx, inum(w[4]), inum(w[5]), num(w[6]), prob, seed));
+  } else if (st == "bond/break") {       // fix ID all bond/break N bondtype Rmax [prob f seed]   (src/MC/fix_bond_break.cpp:40-90)
+    need(7);
+    double prob = 1.0; int seed = 12345;
+    for (size_t k = 7; k < w.size();) {
+      if (w[k] == "prob" && k + 2 < w.size()) { prob = num(w[k + 1]); seed = inum(w[k + 2]); k += 3; }
+      else die("Illegal fix bond/break command");
+    }
+    ck(d, le_fix_bond_break(d.ctx, inum(w[4]), inum(w[5]), num(w[6]), prob, seed));
   } else die("Unknown fix style " + st);
   d.fix_style[w[1]] = st;
 }
@@ -624,7 +632,7 @@ void unfix(Deck &d, const Words &w) {
   if (st == "nve" || st == "nve/limit") ck(d, le_fix_nve(d.ctx, 0));
   else if (st == "extrusion") ck(d, le_unfix(d.ctx, LE_FIX_EXTRUSION));
   else if (st == "ex_load") ck(d, le_unfix(d.ctx, LE_FIX_EX_LOAD));
-  else if (st == "ex_unload") ck(d, le_unfix(d.ctx, LE_FIX_EX_UNLOAD));
+  else if (st == "ex_unload" || st == "bond/break") ck(d, le_unfix(d.ctx, LE_FIX_EX_UNLOAD));
   else if (st == "langevin") die("unfix of fix langevin is not supported");
   d.fix_style.erase(w[1]);
 }

@@ -31,7 +31,7 @@ static inline int h_float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; 
 
 struct FixExtrusionCfg { int on, nevery, neutral, left, right, btype, roadblock, seed; double p; };
 struct FixExLoadCfg { int on, nevery, itype, jtype, btype, seed, imax, inew, jmax, jnew; double rc, prob; };
-struct FixExUnloadCfg { int on, nevery, btype, seed; double rc, prob; };
+struct FixExUnloadCfg { int on, nevery, btype, seed, phase; double rc, prob; };   // phase: 2 = fix ex_unload, 0 = its ancestor fix bond/break
 
 #define PLAIN_UNROLL 8      // timesteps per launch of the steady-state graph
 
@@ -449,9 +449,22 @@ extern "C" int le_fix_ex_unload(le_ctx *c, int nevery, int btype, double rc, dou
   if (btype < 1 || btype > c->nbondtypes) return fail(c, LE_EINVAL, "Invalid bond type in fix ex_unload command");
   if (rc < 0.0) return fail(c, LE_EINVAL, "Illegal fix ex_unload command");
   if (prob < 0.0 || prob > 1.0 || seed <= 0) return fail(c, LE_EINVAL, "Illegal fix ex_unload command");
-  c->fu.on = 1; c->fu.nevery = nevery; c->fu.btype = btype; c->fu.rc = rc; c->fu.prob = prob; c->fu.seed = seed;
+  c->fu.on = 1; c->fu.nevery = nevery; c->fu.btype = btype; c->fu.rc = rc; c->fu.prob = prob; c->fu.seed = seed; c->fu.phase = 2;
   c->lf.rng[1].seeded = 0;
   if (std::find(c->fix_order.begin(), c->fix_order.end(), LE_FIX_EX_UNLOAD) == c->fix_order.end()) c->fix_order.push_back(LE_FIX_EX_UNLOAD);
+  return LE_OK;
+}
+
+/* fix ID all bond/break N bondtype Rmax [prob f seed] (src/MC/fix_bond_break.cpp): the ancestor of fix ex_unload -- the same
+ * post_integrate body; the only difference is the step gate, `ntimestep % nevery` there (fix_bond_break.cpp:178) against
+ * `ntimestep % nevery - 2` in fix_ex_unload.cpp:178.  It occupies the ex_unload slot (one of the two per context). */
+extern "C" int le_fix_bond_break(le_ctx *c, int nevery, int btype, double rmax, double prob, int seed) {
+  if (!c) return LE_EINVAL;
+  if (nevery <= 0 || rmax < 0.0 || prob < 0.0 || prob > 1.0 || seed <= 0) return fail(c, LE_EINVAL, "Illegal fix bond/break command");
+  if (btype < 1 || btype > c->nbondtypes) return fail(c, LE_EINVAL, "Invalid bond type in fix bond/break command");
+  const int r = le_fix_ex_unload(c, nevery, btype, rmax, prob, seed);
+  if (r) return r;
+  c->fu.phase = 0;
   return LE_OK;
 }
 
@@ -1521,7 +1534,7 @@ static void le_mark(le_ctx *c) {
 // does any USER-LE fix fire in Modify::post_integrate of timestep `step`?
 static bool le_event_at(const le_ctx *c, int64_t step) {
   if (c->fx.on && (step % c->fx.nevery - 1) == 0) return true;
-  if (c->fu.on && (step % c->fu.nevery - 2) == 0) return true;
+  if (c->fu.on && (step % c->fu.nevery - c->fu.phase) == 0) return true;
   if (c->fl.on && (step % c->fl.nevery - 3) == 0) return true;
   return false;
 }

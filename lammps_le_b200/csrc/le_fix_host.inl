@@ -257,7 +257,7 @@ static int enqueue_le_events(le_ctx *c, int64_t step) {
   for (int which : c->fix_order) {
     int r = LE_OK;
     if (which == LE_FIX_EXTRUSION && c->fx.on && (step % c->fx.nevery - 1) == 0) { r = enqueue_extrusion(c); any = true; }
-    else if (which == LE_FIX_EX_UNLOAD && c->fu.on && (step % c->fu.nevery - 2) == 0) { r = enqueue_unload(c); any = true; }
+    else if (which == LE_FIX_EX_UNLOAD && c->fu.on && (step % c->fu.nevery - c->fu.phase) == 0) { r = enqueue_unload(c); any = true; }
     else if (which == LE_FIX_EX_LOAD && c->fl.on && (step % c->fl.nevery - 3) == 0) { r = enqueue_load(c); any = true; }
     if (r) return r;
   }

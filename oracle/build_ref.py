@@ -32,6 +32,9 @@ GEN = os.path.join(OUT, "gen")
 OBJ = os.path.join(OUT, "obj")
 
 SRC_DIRS = ["src", "src/MOLECULE", "src/USER-LE"]
+# single styles from packages that are not compiled as a whole: fix bond/break (src/MC), the ancestor of fix ex_unload -- the
+# checker for le_fix_bond_break (tests/test_gpu_md.py)
+EXTRA_STYLES = [("src/MC", "fix_bond_break")]
 CXXFLAGS = ["-O2", "-std=c++11", "-fPIC", "-DLAMMPS_SMALLBIG", "-DLAMMPS_EXCEPTIONS",
             "-ffp-contract=off", "-w"]
 OMP = False      # second build (oracle/_ref/omp/): the same sources + the USER-OMP styles whose base style is compiled, -fopenmp
@@ -83,11 +86,15 @@ def up_to_date(target, deps):
     return all(os.path.getmtime(d) <= t for d in deps if os.path.exists(d))
 
 
+CHANGED_STYLE_LISTS = []
+
+
 def write_if_changed(path, text):
     if os.path.exists(path) and open(path).read() == text:
         return
     with open(path, "w") as f:
         f.write(text)
+    CHANGED_STYLE_LISTS.append(os.path.basename(path))
 
 
 def gen_headers():
@@ -96,6 +103,7 @@ def gen_headers():
     for d in SRC_DIRS:
         p = os.path.join(REF, d)
         headers += [os.path.join(p, h) for h in sorted(os.listdir(p)) if h.endswith(".h") and (d != "src/USER-OMP" or omp_file_wanted(h))]
+    headers += [os.path.join(REF, d, b + ".h") for d, b in EXTRA_STYLES]
     first_lines = {}
     for h in headers:
         with open(h, errors="replace") as f:
@@ -128,6 +136,7 @@ def gen_headers():
 def includes():
     inc = ["-I" + GEN, "-I" + os.path.join(REF, "src/STUBS")]
     inc += ["-I" + os.path.join(REF, d) for d in SRC_DIRS]
+    inc += ["-I" + os.path.join(REF, d) for d in sorted({d for d, _ in EXTRA_STYLES})]
     return inc
 
 
@@ -148,13 +157,22 @@ def build():
         print("oracle/_ref: reference tree absent and nothing prebuilt", file=sys.stderr)
         return 1
     os.makedirs(OBJ, exist_ok=True)
+    del CHANGED_STYLE_LISTS[:]
     gen_headers()
+    # the objects that include a style list do not notice its change through their own source's time stamp
+    users = {"style_fix.h": ["modify.o", "lammps.o"], "style_integrate.h": ["update.o", "lammps.o"]}
+    for lst in CHANGED_STYLE_LISTS:
+        for o in users.get(lst, []):
+            if os.path.exists(os.path.join(OBJ, o)):
+                os.remove(os.path.join(OBJ, o))
     jobs = []
     for d in SRC_DIRS:
         p = os.path.join(REF, d)
         for s in sorted(os.listdir(p)):
             if s.endswith(".cpp") and s != "main.cpp" and (d != "src/USER-OMP" or omp_file_wanted(s)):
                 jobs.append((os.path.join(p, s), os.path.join(OBJ, s[:-4] + ".o"), "g++"))
+    for d, b in EXTRA_STYLES:
+        jobs.append((os.path.join(REF, d, b + ".cpp"), os.path.join(OBJ, b + ".o"), "g++"))
     jobs.append((os.path.join(REF, "src/STUBS/mpi.c"), os.path.join(OBJ, "mpi_stubs.o"), "gcc"))
     nthreads = int(os.environ.get("LE_BUILD_JOBS", str(os.cpu_count() or 4)))
     failed = []
@@ -210,9 +228,11 @@ def build_b200():
             text += '#include "verlet_le_b200.h"\n'
         write_if_changed(os.path.join(gen, f), text)
     inc = ["-I" + gen, "-I" + style_dir, "-I" + os.path.join(root, "include"), "-I" + os.path.join(REF, "src/STUBS")] + ["-I" + os.path.join(REF, d) for d in SRC_DIRS]
+    inc += ["-I" + os.path.join(REF, d) for d in sorted({d for d, _ in EXTRA_STYLES})]
+    gen_files = [os.path.join(gen, f) for f in os.listdir(gen)]
     srcs = [(os.path.join(REF, "src/update.cpp"), os.path.join(out, "update.o")), (os.path.join(REF, "src/lammps.cpp"), os.path.join(out, "lammps.o")), (os.path.join(style_dir, "verlet_le_b200.cpp"), os.path.join(out, "verlet_le_b200.o"))]
     for src, obj in srcs:
-        if not up_to_date(obj, [src, os.path.join(style_dir, "verlet_le_b200.h"), os.path.join(root, "include", "le_b200.h")]):
+        if not up_to_date(obj, [src, os.path.join(style_dir, "verlet_le_b200.h"), os.path.join(root, "include", "le_b200.h")] + gen_files):
             subprocess.check_call(["g++"] + CXXFLAGS + inc + ["-c", src, "-o", obj])
     objs = [os.path.join(OBJ, o) for o in sorted(os.listdir(OBJ)) if o.endswith(".o") and o not in ("update.o", "lammps.o")] + [o for _, o in srcs]
     if not up_to_date(exe, objs + [lib]):

@@ -196,3 +196,38 @@ def test_device_observables_match_host():
     hist = np.bincount(np.minimum(sizes // 4, 15), minlength=16)
     assert (o["loop_hist"] == hist).all() and o["nloops"] == len(sizes)
     e.close()
+
+
+@pytest.mark.gpu
+def test_fix_bond_break_matches_the_reference():
+    """fix bond/break (src/MC/fix_bond_break.cpp, the ancestor of fix ex_unload: same body, events on multiples of N): bond counts and
+    the fix's counters after every event equal a run of the compiled reference from the same state"""
+    import os
+    import re
+    import tempfile
+    from oracle import refio
+    from lammps_le_b200 import systems
+    if not refio.have_reference():
+        pytest.skip("oracle/_ref not present on this box")
+    n = 3000
+    s = systems.chromatin_chain(n, 90, rho=0.2, seed=21, barriers="random", extruder_bond=systems.EXTRUDER_FENE)
+    v = systems.maxwell_velocities(n, 1.0, np.ones(n), 5)
+    e = systems.make_engine(s, velocities=v, dt=0.005)
+    x, im = e.positions()                                   # the engine's grid-snapped start, handed to the reference
+    s2 = dict(s); s2["x"], s2["image"], s2["v"] = x, im, v
+    wd = tempfile.mkdtemp(prefix="le_bb_")
+    refio.write_data_file(os.path.join(wd, "data.le"), s2)
+    deck = refio.deck_header(s2, "data.le", sort=False) + ["fix 1 all nve", "fix br all bond/break 10 2 1.2 prob 0.5 456456", "timestep 0.005",
+                                                          "thermo_style custom step bonds f_br[1] f_br[2]", "thermo 10", "run 40"]
+    out, _ = refio.run_reference(deck, workdir=wd, harness=False)
+    ref = np.array([[float(q) for q in r.split()] for r in re.search(r"Step Bonds f_br\[1\] f_br\[2\] \n(.*?)\nLoop time", out, re.S).group(1).splitlines()])
+    e.fix_nve(True)
+    e.fix_bond_break(10, 2, 1.2, 0.5, 456456)
+    e.thermo_every(10)
+    e.run(40)
+    th = e.thermo()
+    got = np.array([[t["step"], t["nbonds"], t["le_f1"][1], t["le_f2"][1]] for t in th], dtype=float)
+    e.close()
+    assert ref.shape == got.shape == (5, 4), (ref, got)
+    assert ref[-1, 3] > 5, "the run must break bonds"
+    assert np.array_equal(ref, got), (ref, got)
