@@ -218,8 +218,12 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     n_beads, n_ext, md = args.beads, args.extruders, args.md_steps
-    # weak scaling: ONE system of world x n_beads beads (world x n_ext extruders), cut into x-slabs, one per GPU;
+    # weak scaling (default): ONE system of world x n_beads beads (world x n_ext extruders), cut into x-slabs, one per GPU;
+    # strong scaling (--scaling strong, BASELINE configs[3]): ONE system of n_beads beads over all GPUs.
     # halo positions travel as peer stores from the integrator, atoms migrate at every reneighboring
+    strong = args.scaling == "strong"
+    if strong:
+        n_beads, n_ext = n_beads // world, n_ext // world          # per GPU; the system holds world x that
     dd = dict(rank=rank, world=world, halo=LE_HALO, group=group) if world > 1 else None
     s, e = prepared_engine(n_beads * world, n_ext * world, 12345, local, args.relax, dd)
     for _ in range(args.warmup):
@@ -297,9 +301,10 @@ def run_ours(args):
     achieved = bytes_step * n_beads / (kstep_us * 1e-6) / 1e9             # the step kernel alone: algorithmic bytes / its duration
     line = {
         "metric": "atom-steps/s", "value": value, "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * t_wall / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_wall / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64 pair + bond terms on exact 32-bit fixed-point differences / f32 thermostat + integration", "data": "synthetic",
-        "config": {"workload": WORKLOAD if n_beads == 1000000 else "same model, %d beads, %d extruders" % (n_beads, n_ext),
+        "config": {"workload": (WORKLOAD if n_beads * (world if strong else 1) == 1000000 else "same model, %d beads, %d extruders" % (n_beads, n_ext))
+                   + (" -- ONE system over %d GPUs (BASELINE configs[3], strong scaling)" % world if strong else ""),
                    "beads_per_gpu": n_beads, "md_steps_per_step": md, "nbar_half": nbar_half, "nbar_full": nbar_full,
                    "steps_per_rebuild": kint, "l2_note": "working set (%.0f MB per GPU) vs 126 MB L2: inputs %s L2" % (
                        n_beads * (32 + 16 + 16 + 4 * nbar_full + 12 + 4) / 1e6, "exceed" if n_beads >= 1000000 else "fit in"),
@@ -390,6 +395,8 @@ def main():
     ap.add_argument("--md-steps", type=int, default=500)
     ap.add_argument("--relax", type=int, default=1500)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --beads per GPU (one system of N x beads); strong: --beads in all (BASELINE configs[3]: one 1M-bead chain over N GPUs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
