@@ -145,6 +145,9 @@ int le_set_velocities(le_ctx *c, const double *v);
 /* ---- run ------------------------------------------------------------------------------- */
 int le_run(le_ctx *c, int64_t nsteps);                      /* run N */
 int le_force_rebuild(le_ctx *c);                            /* Neighbor::build(1) now */
+/* run N start S stop E (src/run.cpp:90-120): the next le_run calls are segments of one run S..E -- fix langevin's temperature
+ * ramp spans S..E instead of restarting per segment (a front end that cuts a run at dump steps); stop <= start: off */
+int le_set_run_span(le_ctx *c, int64_t start, int64_t stop);
 /* le_run with direct launches and an event before every launch; *kstep_us = average duration of the plain step
  * kernel (launch to next launch on the stream), for live roofline measurements */
 int le_run_timed(le_ctx *c, int64_t nsteps, double *kstep_us);

@@ -407,7 +407,22 @@ void write_dumps(Deck &d, long long step) {
 void run(Deck &d, const Words &w) {
   if (w.size() < 2) die("Illegal run command");
   const long long n = std::strtoll(w[1].c_str(), nullptr, 10);
+  // run N keyword value ...: `start` / `stop` are honoured (the span of the Langevin ramp); upto, pre, post, every are not built
+  long long span_start = -1, span_stop = -1;
+  for (size_t k = 2; k < w.size(); k += 2) {
+    if (k + 1 >= w.size()) die("Illegal run command");
+    if (w[k] == "start") span_start = std::strtoll(w[k + 1].c_str(), nullptr, 10);
+    else if (w[k] == "stop") span_stop = std::strtoll(w[k + 1].c_str(), nullptr, 10);
+    else die("run keyword '" + w[k] + "' is not supported by le_deck (start and stop are)");
+  }
   init(d);
+  {
+    // every le_run below is a segment of THIS run: the ramp of fix langevin goes over the whole of it (Update::beginstep/endstep)
+    const long long now = le_timestep(d.ctx);
+    const long long b = span_start >= 0 ? span_start : now, e = span_stop >= 0 ? span_stop : now + n;
+    if (b > now || e < now + n) die("Run command start/stop value is after/before start/end of run");
+    ck(d, le_set_run_span(d.ctx, b, e));
+  }
   const int first = le_thermo_count(d.ctx);
   const auto t0 = std::chrono::steady_clock::now();
   if (d.dumps.empty()) ck(d, le_run(d.ctx, n));
@@ -423,6 +438,7 @@ void run(Deck &d, const Words &w) {
       write_dumps(d, step);
     }
   }
+  ck(d, le_set_run_span(d.ctx, 0, 0));
   const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   print_thermo(d, first);
   le_stats st; ck(d, le_get_stats(d.ctx, &st));

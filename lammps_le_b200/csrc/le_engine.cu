@@ -100,6 +100,7 @@ struct le_ctx {
   int nranks, rank;
   double halo_dist;
   std::vector<int> xcut;                // slab boundaries in x-cells, [nranks + 1]; empty = equal numbers of cell layers
+  int span_on; int64_t span_begin, span_end;   // le_set_run_span
   int dd_balance;                       // 1: cuts by cumulative atom count at upload (`balance 1.0 shift x`), 0: equal-width slabs (no balance command)
   void *arena; size_t arena_bytes;      // peer-visible allocation (CUDA IPC): pos, pos_hold, cell_start, inbox, flags, geo
   void *peer_base[LE_MAXRANKS];
@@ -240,7 +241,7 @@ extern "C" int le_create(le_ctx **out, int device, const double boxlo[3], const 
   c->x_plain[0] = c->x_plain[1] = nullptr; c->x_tail[0] = c->x_tail[1] = nullptr;
   c->direct_launches = c->graph_node_launches = c->direct_builds = 0;
   memset(&c->gkey, 0, sizeof c->gkey);
-  c->dd_balance = 1;
+  c->dd_balance = 1; c->span_on = 0; c->span_begin = c->span_end = 0;
   c->nranks = 1; c->rank = 0; c->halo_dist = 0.0; c->arena = nullptr; c->arena_bytes = 0; c->peers_open = false; c->rb = nullptr;
   memset(c->peer_base, 0, sizeof c->peer_base);
   c->st_tag = c->st_img = nullptr; c->st_x = c->st_v = nullptr;
@@ -1291,6 +1292,15 @@ static int ensure_ready(le_ctx *c) {
   return push_params(c);
 }
 
+/* `run N start S stop E`: the following le_run calls are segments of ONE run from timestep S to E (Update::beginstep /
+ * endstep, src/run.cpp:90-120): fix langevin's Tstart -> Tstop ramp spans S..E instead of restarting in every segment.
+ * start > stop switches it off again. */
+extern "C" int le_set_run_span(le_ctx *c, int64_t start, int64_t stop) {
+  if (!c) return LE_EINVAL;
+  c->span_on = stop > start; c->span_begin = start; c->span_end = stop;
+  return LE_OK;
+}
+
 extern "C" int le_force_rebuild(le_ctx *c) {
   if (!c) return LE_EINVAL;
   int r = ensure_ready(c); if (r) return r;
@@ -1332,8 +1342,9 @@ static void launch_step(le_ctx *c, StepArgs a, bool ev) {
 }
 
 // Update::ntimestep / beginstep / endstep of the run that starts now -> device control block
-static int push_run_state(le_ctx *c, int64_t begin, int64_t end) {
-  long long v[3] = {begin, begin, end > begin ? end : begin + 1};
+static int push_run_state(le_ctx *c, int64_t begin, int64_t end, int64_t step = -1) {
+  if (step < 0) step = begin;
+  long long v[3] = {step, begin, end > begin ? end : begin + 1};
   CK(cudaMemcpyAsync(&c->d.ctrl->step, v, sizeof v, cudaMemcpyHostToDevice, c->stream));
   return LE_OK;
 }
@@ -1579,7 +1590,9 @@ extern "C" int le_run(le_ctx *c, int64_t nsteps) {
     return LE_OK;
   };
   CK(cudaMemsetAsync(d.thermo, 0, sizeof(double) * LE_THERMO_W * THERMO_SLOTS, c->stream));
-  if ((r = push_run_state(c, begin, end))) return r;
+  // `run N start S stop E` (src/run.cpp:90-120): Update::beginstep / endstep of the whole script-level run -- the span the
+  // Langevin ramp is taken over -- when this le_run is one segment of it (le_set_run_span)
+  if ((r = push_run_state(c, c->span_on ? c->span_begin : begin, c->span_on ? c->span_end : end, begin))) return r;
   // Verlet::setup: full rebuild, then forces at the current positions
   enqueue_rebuild(c, true);
   c->lists_valid = true;

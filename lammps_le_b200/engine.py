@@ -76,7 +76,7 @@ def load_library():
         "le_fix_ex_load": [P, I, I, I, D, I, D, I, I, I, I, I], "le_fix_ex_unload": [P, I, I, D, D, I], "le_fix_bond_break": [P, I, I, D, D, I],
         "le_unfix": [P, I], "le_upload_atoms": [P, I, pi, pi, pd, pd, pi], "le_upload_bonds": [P, I, pi, pi, pi],
         "le_upload_topology": [P, pi, pi, pi, pi, pi], "le_set_positions": [P, pd, pi], "le_set_velocities": [P, pd],
-        "le_run": [P, I64], "le_run_timed": [P, I64, pd], "le_force_rebuild": [P], "le_run_le_event": [P, I],
+        "le_run": [P, I64], "le_set_run_span": [P, I64, I64], "le_run_timed": [P, I64, pd], "le_force_rebuild": [P], "le_run_le_event": [P, I],
         "le_fix_rng_reset": [P, I, I, I64], "le_fix_rng_consumed": [P, I, C.POINTER(I64)],
         "le_fix_rng_set_state": [P, I, pd], "le_fix_rng_get_state": [P, I, pd],
         "le_minimize": [P, D, D, I, I, C.POINTER(MinResult)],
@@ -315,6 +315,10 @@ class Engine:
     # ---- run ----
     def run(self, nsteps):
         self._ck(self.lib.le_run(self._h, nsteps))
+
+    def set_run_span(self, start, stop):
+        """`run N start S stop E`: the next run() calls are segments of one run S..E (span of the Langevin ramp); stop <= start: off"""
+        self._ck(self.lib.le_set_run_span(self._h, start, stop))
 
     def run_timed(self, nsteps):
         """run with direct launches; returns the average duration (us) of the plain step kernel"""

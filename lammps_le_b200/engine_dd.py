@@ -17,7 +17,8 @@ from .engine import Engine, Thermo, _pd, _pi  # noqa: F401
 
 
 def slab_of_cells(ncx, world):
-    """[X0, X1) of every rank: the split le_engine.cu:setup_cells uses"""
+    """[X0, X1) of every rank for EQUAL-WIDTH slabs: the split le_engine.cu:setup_cells uses when no cuts by atom count exist
+    (le_dd_balance(ctx, 0) / DDEngine(balance=False)); the default places the cuts by the cumulative atom count instead"""
     return [(r * ncx // world, (r + 1) * ncx // world) for r in range(world)]
 
 

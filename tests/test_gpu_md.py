@@ -231,3 +231,36 @@ def test_fix_bond_break_matches_the_reference():
     assert ref.shape == got.shape == (5, 4), (ref, got)
     assert ref[-1, 3] > 5, "the run must break bonds"
     assert np.array_equal(ref, got), (ref, got)
+
+
+@pytest.mark.gpu
+def test_langevin_ramp_spans_the_segments_of_one_run():
+    """a run cut into segments (le_deck does that at dump steps) must not restart fix langevin's Tstart -> Tstop
+    ramp in every segment: le_set_run_span (`run N start S stop E`, src/run.cpp:90-120).  With the span the segmented run stays
+    within 1e-3 of the uncut one (what remains is Verlet::setup re-evaluating the drag with the updated velocity at every
+    segment start, as the reference does); without it the temperature is a sawtooth and the trajectories part."""
+    from lammps_le_b200 import systems
+    n = 4000
+    s = systems.chromatin_chain(n, 40, rho=0.2, seed=8)
+    e = systems.make_engine(s, velocities=systems.maxwell_velocities(n, 1.0, np.ones(n), 2), dt=0.005)
+    systems.relax(e, steps=400)
+    x, im = e.positions(); v = e.velocities(); e.close()
+    s = dict(s); s["x"], s["image"] = x, im
+
+    def traj(segments, span):
+        e = systems.make_engine(s, velocities=v, dt=0.005)
+        e.fix_nve(True)
+        e.fix_langevin(0.5, 1.5, 1.0, 4242)
+        if span:
+            e.set_run_span(0, sum(segments))
+        for k in segments:
+            e.run(k)
+        out = e.positions()[0]
+        e.close()
+        return out
+
+    L = s["box"][1][0]
+    dist = lambda a, b: np.abs(((a - b) + L / 2) % L - L / 2).max()
+    whole, cut, saw = traj([120], False), traj([40, 40, 40], True), traj([40, 40, 40], False)
+    assert dist(whole, cut) < 2e-3, dist(whole, cut)
+    assert dist(whole, saw) > 20 * dist(whole, cut), (dist(whole, saw), dist(whole, cut))
