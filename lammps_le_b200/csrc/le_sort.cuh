@@ -13,7 +13,7 @@
 #include "le_common.cuh"
 
 #define SCAN_BLOCK 1024
-#define SCAN_MAXITEMS 16                      // consecutive cells per thread: chosen by the host so that all tiles run in ONE wave
+#define SCAN_MAXITEMS 8                       // rows of 32 cells per warp: chosen by the host so that all tiles run in ONE wave when they can
 
 __device__ __forceinline__ int own_cell_first(const Dev &d) { return cell_slot(d, d.halo, 0, 0); }
 __device__ __forceinline__ int own_cell_count(const Dev &d) { return (d.nlx - 2 * d.halo) * d.ncell[1] * d.ncell[2]; }
@@ -62,9 +62,10 @@ __device__ __forceinline__ void st_gpu(unsigned long long *p, unsigned long long
 // predecessors -- one thread per predecessor, one memory round trip -- instead of chaining inclusive prefixes from tile
 // to tile.  `items` is sized by the host so that the grid fits the GPU in a single wave (a second wave of a few blocks
 // doubled the kernel's duration).
-__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_cells(Dev d, int items) {
+__global__ void __launch_bounds__(SCAN_BLOCK, 2) k_scan_cells(Dev d, int items) {
   __shared__ int s_tile;
   __shared__ unsigned s_epoch;
+  __shared__ int s_wtot[32];
   Ctrl *c = d.ctrl;
   if (threadIdx.x == 0) {
     s_epoch = c->nbuilds_scan + 1u;                         // read before this launch's last block bumps it
@@ -74,13 +75,44 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_cells(Dev d, int items) {
   const int tile = s_tile;
   const unsigned epoch = s_epoch;
   const int n = own_cell_count(d), first = own_cell_first(d);
-  const int idx = (tile * SCAN_BLOCK + threadIdx.x) * items;
-  int v[SCAN_MAXITEMS], tsum = 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // a warp owns 32 * items consecutive cells as `items` rows of 32: every load and store of a row is one coalesced 128-byte
+  // line (the first form gave every thread `items` consecutive cells: each of its loads and stores touched 32 lines)
+  const int wbase = (tile * SCAN_BLOCK + warp * 32) * items;
+  int ex[SCAN_MAXITEMS], wtot = 0;                          // ex[q]: exclusive prefix of this lane's cell of row q inside the warp
 #pragma unroll
-  for (int q = 0; q < SCAN_MAXITEMS; q++) { v[q] = (q < items && idx + q < n) ? d.cell_count[first + idx + q] : 0; tsum += v[q]; }
-  int total;
-  const int ex = block_excl_scan(tsum, &total);
-  if (threadIdx.x == 0) st_gpu(&d.scan_state[tile], ((unsigned long long)epoch << 32) | (unsigned)total);
+  for (int q = 0; q < SCAN_MAXITEMS; q++) {
+    const int idx = wbase + q * 32 + lane;
+    ex[q] = (q < items && idx < n) ? d.cell_count[first + idx] : 0;
+  }
+#pragma unroll
+  for (int q = 0; q < SCAN_MAXITEMS; q++) {
+    const int v = ex[q];
+    int x = v;
+    if (q < items) {
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += t;
+      }
+    }
+    ex[q] = wtot + x - v;
+    wtot += __shfl_sync(0xffffffffu, x, 31);
+  }
+  if (lane == 0) s_wtot[warp] = wtot;
+  __syncthreads();
+  if (warp == 0) {                                          // exclusive scan of the 32 warp totals; lane 31 keeps the tile's sum
+    int w = s_wtot[lane], x = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += t;
+    }
+    s_wtot[lane] = x - w;
+    if (lane == 31) st_gpu(&d.scan_state[tile], ((unsigned long long)epoch << 32) | (unsigned)x);
+  }
+  __syncthreads();
+  const int warp_excl = s_wtot[warp];
   // the sums of the tiles before this one
   int before = 0;
   for (int p = threadIdx.x; p < tile; p += SCAN_BLOCK) {
@@ -90,20 +122,22 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_cells(Dev d, int items) {
   }
   int excl;
   block_excl_scan(before, &excl);
-  int run = d.own0 + excl + ex;
+  const int base = d.own0 + excl + warp_excl;
 #pragma unroll
-  for (int q = 0; q < SCAN_MAXITEMS; q++)
-    if (q < items && idx + q < n) {
-      d.cell_start[first + idx + q] = run;
-      d.cell_count[first + idx + q] = 0;
-      run += v[q];
+  for (int q = 0; q < SCAN_MAXITEMS; q++) {
+    const int idx = wbase + q * 32 + lane;
+    if (q < items && idx < n) {
+      d.cell_start[first + idx] = base + ex[q];
+      d.cell_count[first + idx] = 0;
     }
+  }
+  if (tile == (int)gridDim.x - 1 && threadIdx.x == SCAN_BLOCK - 1) {
+    // the owned population after migration; the sentinel slot behind the owned region closes its last cell
+    const int total = warp_excl + wtot;                     // (warp 31: the tile's sum)
+    c->nown = excl + total;
+    d.cell_start[first + n] = d.own0 + excl + total;
+  }
   if (threadIdx.x == 0) {
-    if (tile == (int)gridDim.x - 1) {
-      // the owned population after migration; the sentinel slot behind the owned region closes its last cell
-      c->nown = excl + total;
-      d.cell_start[first + n] = d.own0 + excl + total;
-    }
     __threadfence();
     if (atomicAdd(&c->scan_done, 1u) == gridDim.x - 1) { c->scan_done = 0; c->scan_ticket = 0; c->nbuilds_scan++; }
   }
