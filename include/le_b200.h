@@ -65,6 +65,7 @@ typedef struct le_thermo {
    * index 0 fix extrusion, 1 fix ex_unload, 2 fix ex_load; f1 = bonds of the fix's last event, f2 = cumulative -- except
    * le_f2[0], which is 0 as in the reference (FixExtrusion never accumulates its total; le_stats.extrusion_shifts does) */
   int64_t le_f1[3], le_f2[3];
+  double eangle;            /* angle energy per atom (part of emol) */
 } le_thermo;
 
 /* run statistics, the numbers the reference prints in Finish::end (src/finish.cpp) */
@@ -96,6 +97,12 @@ int le_set_pair_lj(le_ctx *c, int ntypes, const double *epsilon, const double *s
                    const double *cut, int shift_flag);
 /* bond_coeff: fene params = {K, R0, epsilon, sigma}; harmonic params = {K, r0, -, -} */
 int le_set_bond(le_ctx *c, int btype, int style, const double params[4]);
+/* angle_style cosine (src/MOLECULE/angle_cosine.cpp:47-170; chain stiffness): le_set_angle_types = the data file's
+ * `N angle types`; angle_coeff: cosine params = {K, -, -, -}; le_upload_angles = the "Angles" section (type a1 a2 a3, a2 centre) */
+enum { LE_ANGLE_NONE_STYLE = 0, LE_ANGLE_COSINE_STYLE = 1 };
+int le_set_angle_types(le_ctx *c, int nangletypes);
+int le_set_angle(le_ctx *c, int atype, int style, const double params[4]);
+int le_upload_angles(le_ctx *c, int nangles, const int *atype, const int *a1, const int *a2, const int *a3);
 int le_set_special(le_ctx *c, const double lj[3]);          /* special_bonds lj a b c (fene = 0 1 1) */
 int le_set_neighbor(le_ctx *c, double skin, int every, int delay, int check);
 int le_set_neighbor_capacity(le_ctx *c, int max_neighbors_per_atom);  /* neigh_modify one (full rows) */

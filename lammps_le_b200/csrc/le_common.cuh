@@ -84,6 +84,8 @@ struct Params {
   double bk_d[LE_MAXB], br0_d[LE_MAXB], beps_d[LE_MAXB], bsig_d[LE_MAXB];
   double br0sq_d[LE_MAXB], binvr0sq_d[LE_MAXB], bsig2_d[LE_MAXB], bcore_d[LE_MAXB];  // R0^2, 1/R0^2, sigma^2, 2^(1/3) sigma^2
   double beps48_d[LE_MAXB];   // 48 epsilon (k_step2)
+  int astyle[LE_MAXB];        // angle styles by angle type (0 none, 1 cosine)
+  double ak_d[LE_MAXB];       // angle cosine: K
   // fp32 brackets around cutneighsq: below lo a pair is certainly listed, above hi certainly not; only the
   // sliver in between needs the reference's fp64 arithmetic (k_build)
   float cutneigh_lo[LE_MAXT * LE_MAXT], cutneigh_hi[LE_MAXT * LE_MAXT];
@@ -203,13 +205,17 @@ struct Dev {
   int ncells;         // local cell slots incl. region sentinels: nlx*ncy*ncz + 3
   int nscanblocks;
   int cell_span[3], cell_abs[3];  // per-dim stencil span / "visit all cells" (k_build)
+  // angles (tag order, replicated): ang[nangles] = {type, a1, a2, a3}; per atom the angles it takes part in
+  int nangles, apa;
+  int4 *ang; int *ang_cnt, *ang_idx;
+  double *fang;     // [cap][3] angle force of the owned atoms (k_angle -> step kernel)
   Ctrl *ctrl;
   double *thermo;   // [slots][LE_THERMO_W]
   double *fout;     // [N][3] optional force output (tag order)
 };
 
 #define LE_THERMO_W 24
-// thermo slot layout: 0 ke(sum m v^2) 1 evdwl 2 ebond 3..8 virial 9 fene warnings | snapshot at that force evaluation (not
+// thermo slot layout: 0 ke(sum m v^2) 1 evdwl 2 ebond 3..8 virial 9 fene warnings 10 eangle | snapshot at that force evaluation (not
 // summed over GPUs: the USER-LE state is replicated): 16 atom->nbonds, 17..19 f_ID[1] of extrusion / ex_unload / ex_load
 // (bonds of the fix's last event), 20..22 f_ID[2] (cumulative)
 

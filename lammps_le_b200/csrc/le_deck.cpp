@@ -44,8 +44,11 @@ struct Deck {
   int natoms = 0, nbonds = 0, ntypes = 0, nbondtypes = 0, extra_bond = 0, extra_special = 0;
   double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
   std::vector<int> tag, mol, type, image, btype, b1, b2;
+  int nangles = 0, nangletypes = 0;                    // atom_style angle | molecular: the Angles section, angle_style cosine
+  std::vector<int> atype, a1, a2, a3;
+  std::string angle_style; std::map<int, double> angle_k;
   std::vector<double> x, v, mass;
-  bool have_v = false, uploaded = false;
+  bool have_v = false, uploaded = false, angles_uploaded = false;
   int bpa = 1;                                         // bond_per_atom the context was sized with
   // read_restart: the per-atom bond tables as the file holds them (slot order kept), sizes from its header
   bool from_restart = false; int r_bpa = 0, r_maxspecial = 0; long long r_step = 0;
@@ -115,8 +118,11 @@ void read_data(Deck &d, const Words &w) {
     else if (t.size() == 4 && t[2] == "xlo") { d.lo[0] = num(t[0]); d.hi[0] = num(t[1]); }
     else if (t.size() == 4 && t[2] == "ylo") { d.lo[1] = num(t[0]); d.hi[1] = num(t[1]); }
     else if (t.size() == 4 && t[2] == "zlo") { d.lo[2] = num(t[0]); d.hi[2] = num(t[1]); }
-    else if (t.size() >= 2 && (t[1] == "angles" || t[1] == "dihedrals" || t[1] == "impropers")) { if (inum(t[0])) die("only atom_style bond data files are supported"); }
-    else if (t.size() >= 3 && (t[1] == "angle" || t[1] == "dihedral" || t[1] == "improper")) {}
+    else if (t.size() == 2 && t[1] == "angles") d.nangles = inum(t[0]);
+    else if (t.size() == 3 && t[1] == "angle" && t[2] == "types") d.nangletypes = inum(t[0]);
+    else if (t.size() >= 2 && (t[1] == "dihedrals" || t[1] == "impropers")) { if (inum(t[0])) die("dihedrals / impropers are outside this path (atom_style bond | angle)"); }
+    else if (t.size() >= 3 && (t[1] == "dihedral" || t[1] == "improper")) {}
+    else if (t.size() == 5 && t[1] == "extra" && t[2] == "angle") {}
     else die("Unknown identifier in data file: " + t[0]);
   };
   auto finish_section = [&]() {
@@ -147,7 +153,10 @@ void read_data(Deck &d, const Words &w) {
     } else if (section == "Bonds") {
       if ((int)rows.size() != d.nbonds) die("Bonds assigned incorrectly");
       for (auto &r : rows) { d.btype.push_back(inum(r[1])); d.b1.push_back(inum(r[2])); d.b2.push_back(inum(r[3])); }
-    } else if (section == "Bond Coeffs" || section == "Pair Coeffs" || section == "PairIJ Coeffs") {
+    } else if (section == "Angles") {
+      if ((int)rows.size() != d.nangles) die("Angles assigned incorrectly");
+      for (auto &r : rows) { if (r.size() < 5) die("Incorrect format in Angles section of data file"); d.atype.push_back(inum(r[1])); d.a1.push_back(inum(r[2])); d.a2.push_back(inum(r[3])); d.a3.push_back(inum(r[4])); }
+    } else if (section == "Bond Coeffs" || section == "Angle Coeffs" || section == "Pair Coeffs" || section == "PairIJ Coeffs") {
       // coefficients in the data file need the styles to be defined first; the decks on this path set them in the script
     } else if (!section.empty()) die("Unknown section in data file: " + section);
     rows.clear();
@@ -186,6 +195,12 @@ int bond_style_id(const std::string &s) {
 void init(Deck &d) {
   if (!d.ctx) die("Run command before simulation box is defined");
   ck(d, le_set_types(d.ctx, d.ntypes, d.mass.data(), d.nbondtypes));
+  if (d.nangletypes > 0) {
+    // angle_style cosine + angle_coeff N K (src/MOLECULE/angle_cosine.cpp:140-170)
+    ck(d, le_set_angle_types(d.ctx, d.nangletypes));
+    if ((int)d.angle_k.size() < d.nangletypes && d.nangles > 0) die("All angle coeffs are not set");
+    for (auto &kv : d.angle_k) { const double p[4] = {kv.second, 0, 0, 0}; ck(d, le_set_angle(d.ctx, kv.first, LE_ANGLE_COSINE_STYLE, p)); }
+  }
   if (!d.pair_set) die("Pair style is not defined");
   // Pair::mix_* geometric for lj units default (src/pair.cpp:577-607) for pairs without an explicit pair_coeff
   std::vector<double> e = d.eps, s = d.sigma, c = d.cut;
@@ -236,6 +251,11 @@ void init(Deck &d) {
     ck(d, le_upload_bonds(d.ctx, d.nbonds, d.btype.data(), d.b1.data(), d.b2.data()));
     d.uploaded = true;
   }
+  if (d.nangles > 0 && !d.angles_uploaded) {
+    if (d.angle_style.empty()) die("Angle style is not defined");
+    ck(d, le_upload_angles(d.ctx, d.nangles, d.atype.data(), d.a1.data(), d.a2.data(), d.a3.data()));
+    d.angles_uploaded = true;
+  }
 }
 
 // thermo_style one | custom kw ...: the keywords of src/thermo.cpp:700-860 this path can fill, with the reference's
@@ -246,7 +266,7 @@ const ThermoField THERMO_FIELDS[] = {
     {"temp", "Temp", false}, {"press", "Press", false}, {"pe", "PotEng", false}, {"ke", "KinEng", false}, {"etotal", "TotEng", false},
     {"evdwl", "E_vdwl", false}, {"epair", "E_pair", false}, {"ebond", "E_bond", false}, {"emol", "E_mol", false},
     {"vol", "Volume", false}, {"density", "Density", false}, {"lx", "Lx", false}, {"ly", "Ly", false}, {"lz", "Lz", false},
-    {"bonds", "Bonds", true}};
+    {"bonds", "Bonds", true}, {"eangle", "E_angle", false}};
 
 void thermo_style(Deck &d, const Words &w) {
   if (w.size() < 2) die("Illegal thermo_style command");
@@ -317,7 +337,9 @@ void print_thermo(Deck &d, int first) {
         case 8: fv = t.ke / d.natoms; break;
         case 9: fv = t.etotal; break;
         case 10: case 11: fv = t.epair; break;
-        case 12: case 13: fv = t.emol; break;
+        case 12: fv = t.emol - t.eangle; break;
+        case 13: fv = t.emol; break;
+        case 20: fv = t.eangle; break;
         case 14: fv = vol; break;
         case 15: fv = mtot / vol; break;
         case 16: case 17: case 18: fv = d.hi[q - 16] - d.lo[q - 16]; break;
@@ -466,8 +488,10 @@ void write_data(Deck &d, const Words &w) {
   for (int t = 0; t < n; t++) for (int m = 0; m < nb[t]; m++) if (t + 1 < ba[(size_t)t * bpa + m]) nbonds++;
   FILE *f = std::fopen(w[1].c_str(), "w");
   if (!f) die("Cannot open data file " + w[1]);
-  std::fprintf(f, "LAMMPS data file via write_data, le_b200, timestep = %lld\n\n%d atoms\n%d atom types\n%lld bonds\n%d bond types\n\n",
+  std::fprintf(f, "LAMMPS data file via write_data, le_b200, timestep = %lld\n\n%d atoms\n%d atom types\n%lld bonds\n%d bond types\n",
                (long long)le_timestep(d.ctx), n, d.ntypes, nbonds, d.nbondtypes);
+  if (d.nangletypes > 0) std::fprintf(f, "%d angles\n%d angle types\n", d.nangles, d.nangletypes);
+  std::fprintf(f, "\n");
   std::fprintf(f, "%.16e %.16e xlo xhi\n%.16e %.16e ylo yhi\n%.16e %.16e zlo zhi\n\nMasses\n\n", d.lo[0], d.hi[0], d.lo[1], d.hi[1], d.lo[2], d.hi[2]);
   for (int t = 0; t < d.ntypes; t++) std::fprintf(f, "%d %.10g\n", t + 1, d.mass[t]);
   std::fprintf(f, "\nAtoms # bond\n\n");
@@ -481,6 +505,10 @@ void write_data(Deck &d, const Words &w) {
   for (int t = 0; t < n; t++)
     for (int m = 0; m < nb[t]; m++)
       if (t + 1 < ba[(size_t)t * bpa + m]) std::fprintf(f, "%lld %d %d %d\n", ++id, bt[(size_t)t * bpa + m], t + 1, ba[(size_t)t * bpa + m]);
+  if (d.nangles > 0) {
+    std::fprintf(f, "\nAngles\n\n");
+    for (int k = 0; k < d.nangles; k++) std::fprintf(f, "%d %d %d %d %d\n", k + 1, d.atype[k], d.a1[k], d.a2[k], d.a3[k]);
+  }
   std::fclose(f);
 }
 
@@ -588,6 +616,7 @@ void write_restart(Deck &d, const Words &w) {
     for (int m = 0; m < h.nhybrid; m++) std::snprintf(h.hybrid_styles[m], sizeof h.hybrid_styles[m], "%s", d.bond_styles[m + 1].c_str());
   }
   char err[256] = "";
+  if (d.nangles > 0) die("write_restart: atom_style angle is not written by this path (atom_style bond is)");
   if (le_host_restart_write(w[1].c_str(), &h, tag.data(), ty.data(), im.data(), mol.data(), x.data(), v.data(), nb.data(), bt.data(), ba.data(), err, sizeof err)) die(err);
 }
 
@@ -708,7 +737,13 @@ void velocity(Deck &d, const Words &w) {
 void execute_cmd(Deck &d, const Words &w) {
   const std::string &c = w[0];
   if (c == "units") { if (w.size() < 2 || w[1] != "lj") die("only units lj is supported"); }
-  else if (c == "atom_style") { if (w.size() < 2 || w[1] != "bond") die("only atom_style bond is supported"); }
+  else if (c == "atom_style") { if (w.size() < 2 || (w[1] != "bond" && w[1] != "angle" && w[1] != "molecular")) die("atom_style bond, angle and molecular (without dihedrals) are supported"); }
+  else if (c == "angle_style") { if (w.size() != 2 || (w[1] != "cosine" && w[1] != "none")) die("Unknown angle style " + (w.size() > 1 ? w[1] : std::string())); d.angle_style = w[1]; }
+  else if (c == "angle_coeff") {
+    if (d.angle_style != "cosine" || w.size() != 3) die("Incorrect args for angle coefficients");
+    int a, b; expand_types(w[1], d.nangletypes, a, b);
+    for (int t = a; t <= b; t++) d.angle_k[t] = num(w[2]);
+  }
   else if (c == "atom_modify" || c == "comm_modify" || c == "log" || c == "echo" || c == "thermo_modify" || c == "processors") {}
   else if (c == "thermo_style") thermo_style(d, w);
   else if (c == "print") { for (size_t k = 1; k < w.size(); k++) std::printf("%s%s", w[k].c_str(), k + 1 < w.size() ? " " : "\n"); }

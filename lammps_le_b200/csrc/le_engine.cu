@@ -13,6 +13,7 @@
 #include "le_build5.cuh"
 #include "le_step3.cuh"
 #include "le_step4.cuh"
+#include "le_angle.cuh"
 #include "le_fix.cuh"
 #include "le_min.cuh"
 
@@ -51,6 +52,8 @@ struct le_ctx {
   int pair_set, shift_flag;
   int bstyle[LE_MAXB];
   double bparam[LE_MAXB][4];
+  int nangletypes, astyle[LE_MAXB];     // angle_style cosine (le_angle.cuh)
+  double aparam[LE_MAXB][4];
   double special_lj[4];
   double skin;
   int every, delay, check;
@@ -220,6 +223,7 @@ extern "C" int le_create(le_ctx **out, int device, const double boxlo[3], const 
   for (int k = 0; k < LE_MAXT; k++) c->mass[k] = 1.0;
   c->pair_set = 0; c->shift_flag = 0;
   memset(c->bstyle, 0, sizeof c->bstyle);
+  c->nangletypes = 0; memset(c->astyle, 0, sizeof c->astyle); memset(c->aparam, 0, sizeof c->aparam);
   memset(c->bparam, 0, sizeof c->bparam);
   c->special_lj[0] = 1.0; c->special_lj[1] = 0.0; c->special_lj[2] = 0.0; c->special_lj[3] = 0.0;
   c->skin = 0.3; c->every = 1; c->delay = 10; c->check = 1;   // LAMMPS defaults for units lj
@@ -319,6 +323,63 @@ extern "C" int le_set_bond(le_ctx *c, int btype, int style, const double params[
   c->bstyle[btype - 1] = style;
   for (int k = 0; k < 4; k++) c->bparam[btype - 1][k] = params ? params[k] : 0.0;
   c->params_dirty = true;
+  return LE_OK;
+}
+
+/* angle_style cosine + angle_coeff (src/MOLECULE/angle_cosine.cpp:140-170): nangletypes from the data file's `N angle types` */
+extern "C" int le_set_angle_types(le_ctx *c, int nangletypes) {
+  if (!c) return LE_EINVAL;
+  if (nangletypes < 0 || nangletypes > LE_MAXB) return fail(c, LE_EINVAL, "nangletypes must be 0..%d", LE_MAXB);
+  c->nangletypes = nangletypes; c->params_dirty = true;
+  return LE_OK;
+}
+extern "C" int le_set_angle(le_ctx *c, int atype, int style, const double params[4]) {
+  if (!c || !params) return LE_EINVAL;
+  if (atype < 1 || atype > c->nangletypes) return fail(c, LE_EINVAL, "Incorrect args for angle coefficients");
+  if (style != LE_ANGLE_NONE && style != LE_ANGLE_COSINE) return fail(c, LE_EINVAL, "Unknown angle style");
+  c->astyle[atype - 1] = style;
+  for (int k = 0; k < 4; k++) c->aparam[atype - 1][k] = params[k];
+  c->params_dirty = true;
+  return LE_OK;
+}
+
+/* read_data "Angles" section: type a1 a2 a3 (a2 the centre), every angle once.  Held by tag, replicated on every GPU. */
+extern "C" int le_upload_angles(le_ctx *c, int nangles, const int *atype, const int *a1, const int *a2, const int *a3) {
+  if (!c) return LE_EINVAL;
+  if (!c->atoms_loaded) return fail(c, LE_ESTATE, "upload atoms before angles");
+  if (nangles < 0 || (nangles && (!atype || !a1 || !a2 || !a3))) return LE_EINVAL;
+  cudaSetDevice(c->device);
+  const int n = c->N;
+  std::vector<int4> ang(std::max(nangles, 1));
+  std::vector<int> cnt(n, 0);
+  for (int k = 0; k < nangles; k++) {
+    if (atype[k] < 1 || atype[k] > c->nangletypes) return fail(c, LE_EINVAL, "Invalid angle type in Angles section of data file");
+    const int t[3] = {a1[k], a2[k], a3[k]};
+    for (int q = 0; q < 3; q++) if (t[q] < 1 || t[q] > n) return fail(c, LE_EINVAL, "Invalid atom ID in Angles section of data file");
+    if (t[0] == t[1] || t[1] == t[2] || t[0] == t[2]) return fail(c, LE_EINVAL, "Invalid atom ID in Angles section of data file");
+    ang[k] = make_int4(atype[k], t[0], t[1], t[2]);
+    for (int q = 0; q < 3; q++) cnt[t[q] - 1]++;
+  }
+  int apa = 1;
+  for (int t = 0; t < n; t++) apa = std::max(apa, cnt[t]);
+  std::vector<int> idx((size_t)n * apa, 0), fill(n, 0);
+  for (int k = 0; k < nangles; k++) {
+    const int t[3] = {a1[k], a2[k], a3[k]};
+    for (int q = 0; q < 3; q++) idx[(size_t)(t[q] - 1) * apa + fill[t[q] - 1]++] = k;     // ascending angle id
+  }
+  Dev &d = c->d;
+  int r;
+  if ((r = dalloc(c, &d.ang, ang.size()))) return r;
+  if ((r = dalloc(c, &d.ang_cnt, (size_t)n))) return r;
+  if ((r = dalloc(c, &d.ang_idx, idx.size()))) return r;
+  if (!d.fang && (r = dalloc(c, &d.fang, (size_t)3 * d.cap))) return r;
+  CK(cudaMemcpyAsync(d.ang, ang.data(), sizeof(int4) * ang.size(), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d.ang_cnt, cnt.data(), sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d.ang_idx, idx.data(), sizeof(int) * idx.size(), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemsetAsync(d.fang, 0, sizeof(double) * 3 * d.cap, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  d.nangles = nangles; d.apa = apa;
+  c->graphs_ok = false;
   return LE_OK;
 }
 
@@ -602,6 +663,7 @@ static int build_params(le_ctx *c) {
     if (P.special_flag[k] != 1) P.nscan_tier = k;
   }
   for (int k = 0; k < nt; k++) { P.mass[k] = (float)c->mass[k]; P.dtfm[k] = (float)(0.5 * c->dt / c->mass[k]); }
+  for (int k = 0; k < LE_MAXB; k++) { P.astyle[k] = k < c->nangletypes ? c->astyle[k] : 0; P.ak_d[k] = c->aparam[k][0]; }
   for (int k = 0; k < c->nbondtypes; k++) {
     P.bstyle[k] = c->bstyle[k];
     P.bk[k] = (float)c->bparam[k][0]; P.br0[k] = (float)c->bparam[k][1];
@@ -1200,6 +1262,17 @@ static int graph_add_unit(le_ctx *c, cudaGraph_t g, cudaGraphNode_t *tail, int a
     StepArgs a; memset(&a, 0, sizeof a);
     a.do_final = 1; a.do_initial = 1; a.langevin = c->langevin_on;
     a.rdp1 = step_rd + 1;
+    if (d.nangles > 0) {
+      int rdp1 = a.rdp1, slot0 = 0;
+      void *aargs[] = {&d, &rdp1, &slot0};
+      kp = cudaKernelNodeParams{};
+      kp.func = (void *)k_angle<0>; kp.gridDim = dim3(std::min(grid_for(d.gr0 - d.own0, 256), c->sm_count * 8));
+      kp.blockDim = dim3(256); kp.kernelParams = aargs;
+      cudaGraphNode_t na;
+      CKG(cudaGraphAddKernelNode(&na, g, &nc, 1, &kp));
+      nc = na;
+      a.angles = 1;
+    }
     void *sargs[] = {&d, &a};
     kp = cudaKernelNodeParams{};
     const StepKernel sk = step_kernel(c, false);
@@ -1319,8 +1392,9 @@ static void thermo_from_slot(le_ctx *c, const double *s, int64_t step, le_thermo
   t->ke = 0.5 * s[0];
   t->temp = dof > 0 ? s[0] / dof : 0.0;                      // ComputeTemp::compute_scalar, boltz = mvv2e = 1
   t->epair = s[1] / n;
-  t->emol = s[2] / n;
-  t->etotal = (0.5 * s[0] + s[1] + s[2]) / n;
+  t->emol = (s[2] + s[10]) / n;                              // E_mol = bond + angle (src/thermo.cpp:1640-1660)
+  t->eangle = s[10] / n;
+  t->etotal = (0.5 * s[0] + s[1] + s[2] + s[10]) / n;
   for (int k = 0; k < 6; k++) t->virial[k] = s[3 + k];
   t->press = (s[0] + s[3] + s[4] + s[5]) / (3.0 * vol);     // ComputePressure::compute_scalar, nktv2p = 1
   t->fene_warnings = (int64_t)llround(s[9]);
@@ -1336,6 +1410,11 @@ static void thermo_from_slot(le_ctx *c, const double *s, int64_t step, le_thermo
 static void launch_step(le_ctx *c, StepArgs a, bool ev) {
   const StepKernel sk = step_kernel(c, ev);
   a.rdp1 = c->cur + 1;
+  if (c->d.nangles > 0) {                       // angle forces of this configuration -> Dev::fang (le_angle.cuh)
+    const int g = std::min(grid_for(c->d.gr0 - c->d.own0, 256), c->sm_count * 8);
+    if (ev) LAUNCH(c, k_angle<1>, g, 256, c->d, a.rdp1, a.slot); else LAUNCH(c, k_angle<0>, g, 256, c->d, a.rdp1, 0);
+    a.angles = 1;
+  }
   if (c->timing && !c->capturing) time_mark(c, sk.name);
   sk.fn<<<step_grid(c, sk), sk.threads, 0, c->stream>>>(c->d, a);
   if (!c->capturing) c->direct_launches++;
@@ -1402,7 +1481,7 @@ static int min_eval(le_ctx *c, double *e) {
   launch_step(c, a, true);
   CK(cudaMemcpyAsync(c->h_thermo, c->d.thermo, sizeof(double) * LE_THERMO_W, cudaMemcpyDeviceToHost, c->stream));
   int r = sync_and_check(c); if (r) return r;
-  *e = c->h_thermo[1] + c->h_thermo[2];
+  *e = c->h_thermo[1] + c->h_thermo[2] + c->h_thermo[10];      // evdwl + ebond + eangle
   return LE_OK;
 }
 

@@ -15,6 +15,7 @@ struct StepArgs {
   int write_force;    // store the conservative force of every atom in fout (tag order)
   int langevin;       // add drag + noise
   int rdp1;           // 1 + position buffer holding the current coordinates when the host knows it, 0 = read Ctrl::cur
+  int angles;         // add the angle forces k_angle left in Dev::fang
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(STEP4_THREADS, EV ? 4 : (DD ? 6 : 7)) k_step4(
       bond3<EV>(fx, fy, fz, ctrl, pi, __ldg(&posr[e & BOND_IDX_MASK]), e, tag, A);
     }
     if (!valid) continue;                                      // (no warp-level operation below this line)
+    if (a.angles) { fx += d.fang[3 * (size_t)i]; fy += d.fang[3 * (size_t)i + 1]; fz += d.fang[3 * (size_t)i + 2]; }   // angle_style cosine (le_angle.cuh)
 
     if (a.write_force) {
       double *fo = d.fout + (size_t)(tag - 1) * 3;

@@ -28,12 +28,13 @@ class LeError(RuntimeError):
 class Thermo(C.Structure):
     _fields_ = [("step", C.c_int64), ("temp", C.c_double), ("epair", C.c_double), ("emol", C.c_double),
                 ("etotal", C.c_double), ("press", C.c_double), ("ke", C.c_double), ("virial", C.c_double * 6),
-                ("nbonds", C.c_int64), ("fene_warnings", C.c_int64), ("le_f1", C.c_int64 * 3), ("le_f2", C.c_int64 * 3)]
+                ("nbonds", C.c_int64), ("fene_warnings", C.c_int64), ("le_f1", C.c_int64 * 3), ("le_f2", C.c_int64 * 3), ("eangle", C.c_double)]
 
     def as_dict(self):
         return {"step": self.step, "temp": self.temp, "epair": self.epair, "emol": self.emol,
                 "etotal": self.etotal, "press": self.press, "ke": self.ke, "virial": list(self.virial),
-                "nbonds": self.nbonds, "fene_warnings": self.fene_warnings, "le_f1": list(self.le_f1), "le_f2": list(self.le_f2)}
+                "nbonds": self.nbonds, "fene_warnings": self.fene_warnings, "le_f1": list(self.le_f1), "le_f2": list(self.le_f2),
+                "eangle": self.eangle}
 
 
 class MinResult(C.Structure):
@@ -68,7 +69,7 @@ def load_library():
     pd, pi = C.POINTER(C.c_double), C.POINTER(C.c_int)
     sig = {
         "le_create": [C.POINTER(P), I, pd, pd, pi], "le_set_types": [P, I, pd, I],
-        "le_set_pair_lj": [P, I, pd, pd, pd, I], "le_set_bond": [P, I, I, pd], "le_set_special": [P, pd],
+        "le_set_pair_lj": [P, I, pd, pd, pd, I], "le_set_bond": [P, I, I, pd], "le_set_special": [P, pd], "le_set_angle_types": [P, I], "le_set_angle": [P, I, I, pd], "le_upload_angles": [P, I, pi, pi, pi, pi],
         "le_set_neighbor": [P, D, I, I, I], "le_set_neighbor_capacity": [P, I], "le_set_newton": [P, I, I],
         "le_set_capacity": [P, I, I], "le_set_timestep": [P, D], "le_reset_timestep": [P, I64],
         "le_thermo_every": [P, I], "le_fix_nve": [P, I], "le_fix_nve_limit": [P, D],
@@ -224,6 +225,18 @@ class Engine:
         self._ck(self.lib.le_set_bond(self._h, btype, style, _pd(p)))
 
     @_journaled
+    def set_angle_types(self, nangletypes):
+        self._ck(self.lib.le_set_angle_types(self._h, nangletypes))
+
+    @_journaled
+    def set_angle(self, atype, style, params):
+        """angle_coeff: style "cosine" with params (K,)"""
+        style = {"cosine": 1, "none": 0}.get(style, style)
+        p = np.zeros(4)
+        p[:len(params)] = params
+        self._ck(self.lib.le_set_angle(self._h, atype, style, _pd(p)))
+
+    @_journaled
     def set_special(self, lj):
         a = _f64(lj)
         self._ck(self.lib.le_set_special(self._h, _pd(a)))
@@ -299,6 +312,11 @@ class Engine:
     def upload_bonds(self, btype, atom1, atom2):
         b, a1, a2 = _i32(btype), _i32(atom1), _i32(atom2)
         self._ck(self.lib.le_upload_bonds(self._h, len(b), _pi(b), _pi(a1), _pi(a2)))
+
+    def upload_angles(self, atype, a1, a2, a3):
+        """the data file's Angles section: type, end, centre, end (1-based tags), every angle once"""
+        t, x1, x2, x3 = _i32(atype), _i32(a1), _i32(a2), _i32(a3)
+        self._ck(self.lib.le_upload_angles(self._h, len(t), _pi(t), _pi(x1), _pi(x2), _pi(x3)))
 
     def upload_topology(self, num_bond, bond_type, bond_atom, nspecial, special):
         a = [_i32(q) for q in (num_bond, bond_type, bond_atom, nspecial, special)]

@@ -27,7 +27,7 @@ def finalize_thermo(sums, natoms, volume, step=0, nbonds=0):
     n = float(natoms)
     dof = 3.0 * n - 3.0
     return {"step": step, "ke": 0.5 * sums[0], "temp": sums[0] / dof if dof > 0 else 0.0, "epair": sums[1] / n,
-            "emol": sums[2] / n, "etotal": (0.5 * sums[0] + sums[1] + sums[2]) / n, "virial": list(sums[3:9]),
+            "emol": (sums[2] + sums[10]) / n, "eangle": sums[10] / n, "etotal": (0.5 * sums[0] + sums[1] + sums[2] + sums[10]) / n, "virial": list(sums[3:9]),
             "press": (sums[0] + sums[3] + sums[4] + sums[5]) / (3.0 * volume), "fene_warnings": int(round(sums[9])),
             "nbonds": nbonds}
 

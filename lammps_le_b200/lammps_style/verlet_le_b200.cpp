@@ -10,6 +10,7 @@
 #include "bond_fene.h"
 #include "bond_harmonic.h"
 #include "bond_hybrid.h"
+#include "angle_cosine.h"
 #include "fix_langevin.h"
 #include "fix_nve_limit.h"
 #include "fix_extrusion.h"
@@ -20,6 +21,7 @@
 #undef protected
 
 #include "verlet_le_b200.h"
+#include "angle.h"
 #include "atom.h"
 #include "comm.h"
 #include "compute.h"
@@ -63,8 +65,10 @@ void VerletLEB200::init()
   Integrate::init();
   if (comm->nprocs != 1) error->all(FLERR, "run_style le/b200: one MPI rank per engine context (several GPUs: le_dd_init, INTEGRATION.md section 5)");
   if (domain->triclinic) error->all(FLERR, "run_style le/b200 requires an orthogonal box");
-  if (strcmp(atom->atom_style, "bond") != 0) error->all(FLERR, "run_style le/b200 requires atom_style bond");
-  if (force->angle || force->dihedral || force->improper || force->kspace) error->all(FLERR, "run_style le/b200 supports pair lj/cut + bond fene/harmonic only");
+  if (strcmp(atom->atom_style, "bond") != 0 && strcmp(atom->atom_style, "angle") != 0)
+    error->all(FLERR, "run_style le/b200 requires atom_style bond or angle");
+  if (force->angle && strcmp(force->angle_style, "cosine") != 0) error->all(FLERR, "run_style le/b200 supports angle_style cosine only");
+  if (force->dihedral || force->improper || force->kspace) error->all(FLERR, "run_style le/b200 supports pair lj/cut + bond fene/harmonic + angle cosine only");
 }
 
 /* translate the script's settings; called at every setup() because fixes and coefficients may change between runs */
@@ -107,6 +111,12 @@ void VerletLEB200::create_context()
       for (int t = 1; t <= atom->nbondtypes; t++) { const int m = h->map[t]; if (m >= 0) one(h->styles[m], h->keywords[m], t); }
     } else
       for (int t = 1; t <= atom->nbondtypes; t++) one(force->bond, force->bond_style, t);
+  }
+  // angle_style cosine
+  if (force->angle) {
+    AngleCosine *ac = (AngleCosine *) force->angle;
+    check(le_set_angle_types(ctx, atom->nangletypes));
+    for (int t = 1; t <= atom->nangletypes; t++) { const double prm[4] = {ac->k[t], 0.0, 0.0, 0.0}; check(le_set_angle(ctx, t, LE_ANGLE_COSINE_STYLE, prm)); }
   }
   check(le_set_special(ctx, force->special_lj + 1));
   check(le_set_newton(ctx, force->newton_pair, force->newton_bond));
@@ -180,6 +190,17 @@ void VerletLEB200::push_state()
     check(le_upload_bonds(ctx, (int) b_t.size(), b_t.data(), b_1.data(), b_2.data()));
   } else
     check(le_upload_topology(ctx, nb.data(), bt.data(), ba.data(), ns.data(), sp.data()));
+  if (force->angle && atom->nangles > 0) {
+    // every angle once: Atom holds it on all three atoms under newton_bond off, on the centre atom only under newton_bond on
+    // (Atom::data_angles, src/atom.cpp:1297-1340) -- the centre's copy is there in both cases
+    std::vector<int> at, a1, a2, a3;
+    for (int i = 0; i < n; i++)
+      for (int m = 0; m < atom->num_angle[i]; m++)
+        if (atom->angle_atom2[i][m] == atom->tag[i]) {
+          at.push_back(atom->angle_type[i][m]); a1.push_back(atom->angle_atom1[i][m]); a2.push_back(atom->angle_atom2[i][m]); a3.push_back(atom->angle_atom3[i][m]);
+        }
+    check(le_upload_angles(ctx, (int) at.size(), at.data(), a1.data(), a2.data(), a3.data()));
+  }
   check(le_reset_timestep(ctx, update->ntimestep));
   // the fixes' Marsaglia generators move to the device in their current state (the constructors of ex_load / ex_unload keep
   // the seed in a local variable, fix_ex_unload.cpp:66, so the state is the only complete record) and come back in pull_state
@@ -229,7 +250,8 @@ void VerletLEB200::publish_thermo(const le_thermo &t)
 {
   const double n = (double) atom->natoms;
   if (force->pair) { force->pair->eng_vdwl = t.epair * n; force->pair->eng_coul = 0.0; for (int q = 0; q < 6; q++) force->pair->virial[q] = t.virial[q]; }
-  if (force->bond) { force->bond->energy = t.emol * n; for (int q = 0; q < 6; q++) force->bond->virial[q] = 0.0; }
+  if (force->bond) { force->bond->energy = (t.emol - t.eangle) * n; for (int q = 0; q < 6; q++) force->bond->virial[q] = 0.0; }
+  if (force->angle) { force->angle->energy = t.eangle * n; for (int q = 0; q < 6; q++) force->angle->virial[q] = 0.0; }
   atom->nbonds = t.nbonds;
   update->eflag_global = update->vflag_global = update->ntimestep;
   if (fix_ext) { ((FixExtrusion *) fix_ext)->breakcount = (int) t.le_f1[0]; ((FixExtrusion *) fix_ext)->breakcounttotal = (int) t.le_f2[0]; }

@@ -3,7 +3,7 @@
 
 TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
     python oracle/extract_ref_yaml.py
-reads  unittest/force-styles/tests/{mol-pair-lj_cut,bond-fene,bond-harmonic}.yaml + in.fourmol/data.fourmol
+reads  unittest/force-styles/tests/{mol-pair-lj_cut,bond-fene,bond-harmonic,angle-cosine}.yaml + in.fourmol/data.fourmol
 writes tests/golden/ref_yaml_<name>.npz  (inputs in tag order + the yaml's init_forces / energies / stress)
        tests/golden/ranmars_ref.npz      (first draws of RanMars for the seeds the decks use, from oracle/_ref)
 The numbers are the reference's published known answers (yaml `epsilon` 5e-14 / 2.5e-13); nothing is recomputed here.
@@ -44,13 +44,14 @@ def read_fourmol():
     x = np.array([[float(r[4]), float(r[5]), float(r[6])] for r in atoms])
     typ = np.array([int(r[2]) for r in atoms], dtype=np.int32)
     bonds = [(int(r[1]), int(r[2]), int(r[3])) for r in sect["Bonds"]]
+    angles = np.array([[int(r[1]), int(r[2]), int(r[3]), int(r[4])] for r in sect["Angles"]], dtype=np.int32)   # type a1 a2 a3
     bpa = 6
     nb = np.zeros(n, np.int32); bt = np.zeros((n, bpa), np.int32); ba = np.zeros((n, bpa), np.int32)
     for t, a, b in bonds:       # newton_bond off layout: every bond on both atoms (Atom::data_bonds src/atom.cpp:1261-1278)
         for p, q in ((a, b), (b, a)):
             bt[p - 1, nb[p - 1]] = t; ba[p - 1, nb[p - 1]] = q; nb[p - 1] += 1
     boxlo = np.array([box[k][0] for k in "xyz"]); boxhi = np.array([box[k][1] for k in "xyz"])
-    return dict(x=x, type=typ, num_bond=nb, bond_type=bt, bond_atom=ba, boxlo=boxlo, boxhi=boxhi)
+    return dict(x=x, type=typ, num_bond=nb, bond_type=bt, bond_atom=ba, boxlo=boxlo, boxhi=boxhi, angles=angles)
 
 
 def block(y, key, cols):
@@ -87,6 +88,13 @@ def main():
         np.savez_compressed(os.path.join(GOLD, "ref_yaml_%s.npz" % name), **base, bond_coeff=coeff,
                             init_forces=block(y, "init_forces", 3), init_energy=np.array(float(y["init_energy"])),
                             init_stress=block(y, "init_stress", 6)[0], yaml_epsilon=np.array(float(y["epsilon"])))
+    # angle cosine (chain stiffness)
+    y = yaml.safe_load(open(os.path.join(TESTS, "angle-cosine.yaml")))
+    assert y["input_file"] == "in.fourmol" and y["angle_style"] == "cosine"
+    coeff = np.array([[float(v) for v in ln.split()[1:]] for ln in y["angle_coeff"].strip().splitlines()])
+    np.savez_compressed(os.path.join(GOLD, "ref_yaml_angle-cosine.npz"), **base, angle_coeff=coeff,
+                        init_forces=block(y, "init_forces", 3), init_energy=np.array(float(y["init_energy"])),
+                        init_stress=block(y, "init_stress", 6)[0], yaml_epsilon=np.array(float(y["epsilon"])))
     # RanMars known answers from the compiled reference
     harness = os.path.join(HERE, "_ref", "ref_harness")
     seeds = [12345, 684474, 456456, 904297, 1, 900000000]

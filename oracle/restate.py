@@ -103,6 +103,42 @@ def pair_rsq(xi, xj, L):
 
 
 # ------------------------------------------------------------------------------------------------------------
+# angle cosine -- AngleCosine::compute src/MOLECULE/angle_cosine.cpp:47-140 (E = K (1 + cos theta))
+# ------------------------------------------------------------------------------------------------------------
+def angle_cosine(x, L, a1, a2, a3, atype, k_of_type):
+    """forces / energy / virial of the angles (a1, a2, a3): 0-based indices, a2 the centre; atype 1-based; k_of_type {type: K}.
+    Arms are taken to the closest image of the end atoms as seen from the centre (the reference's ghost atoms)."""
+    n = len(x)
+    f = np.zeros((n, 3))
+    e = 0.0
+    vir = np.zeros(6)
+    for m in range(len(a1)):
+        i1, i2, i3 = int(a1[m]), int(a2[m]), int(a3[m])
+        _, d1, _ = pair_rsq(x[i1], x[i2], L)          # x[i1] - x[i2] with i2 shifted to i1's image: the arm del1
+        _, d2, _ = pair_rsq(x[i3], x[i2], L)
+        rsq1 = d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2]
+        rsq2 = d2[0] * d2[0] + d2[1] * d2[1] + d2[2] * d2[2]
+        r1, r2 = math.sqrt(rsq1), math.sqrt(rsq2)
+        c = d1[0] * d2[0] + d1[1] * d2[1] + d1[2] * d2[2]
+        c /= r1 * r2
+        c = min(1.0, max(-1.0, c))
+        kk = k_of_type[int(atype[m])]
+        e += kk * (1.0 + c)
+        a11 = kk * c / rsq1
+        a12 = -kk / (r1 * r2)
+        a22 = kk * c / rsq2
+        f1 = a11 * d1 + a12 * d2
+        f3 = a22 * d2 + a12 * d1
+        f[i1] += f1
+        f[i2] -= f1 + f3
+        f[i3] += f3
+        # ev_tally (src/angle.cpp:236-270): v = del1 * f1 + del2 * f3
+        vir += np.array([d1[0] * f1[0] + d2[0] * f3[0], d1[1] * f1[1] + d2[1] * f3[1], d1[2] * f1[2] + d2[2] * f3[2],
+                         d1[0] * f1[1] + d2[0] * f3[1], d1[0] * f1[2] + d2[0] * f3[2], d1[1] * f1[2] + d2[1] * f3[2]])
+    return f, e, vir
+
+
+# ------------------------------------------------------------------------------------------------------------
 # pair lj/cut -- PairLJCut::init_one src/pair_lj_cut.cpp:512-535, compute :68-140
 # ------------------------------------------------------------------------------------------------------------
 def lj_coeffs(eps, sigma, rc, shift):

@@ -206,3 +206,67 @@ def test_restart_files_through_le_deck(tmp_path):
     assert abs(a[0][0, 2] - th["epair"]) < 1e-6 * max(1.0, abs(th["epair"])) and abs(a[0][0, 3] - th["emol"]) < 1e-6 * abs(th["emol"])
     # the second process starts where the first one wrote the file and prints what the first one printed from there on
     assert np.array_equal(a[1][0], b[0][0]) and np.allclose(a[1], b[0], rtol=2e-6, atol=1e-9), (a[1], b[0])
+
+
+@pytest.mark.gpu
+def test_angle_cosine_deck_matches_the_reference(tmp_path):
+    """atom_style angle + angle_style cosine (chain stiffness): the same input script and data file through
+    le_deck and through the compiled reference -- thermo columns incl. E_angle at step 0 to print precision, over a short NVE run to 2e-5.
+    (comm_modify cutoff: the reference needs the end atoms of every angle among its ghosts, 2 bonds = up to 3 sigma away; with the
+    default 1.52 it silently tallies a few boundary angles against the wrong image.)"""
+    from oracle import refio
+    if not refio.have_reference():
+        pytest.skip("oracle/_ref not present on this box")
+    from lammps_le_b200 import systems
+    n = 2000
+    s = systems.chromatin_chain(n, 20, rho=0.2, seed=17, extruder_bond=systems.EXTRUDER_FENE)
+    e = systems.make_engine(s, velocities=systems.maxwell_velocities(n, 1.0, np.ones(n), 6), dt=0.005)
+    systems.relax(e, steps=500)
+    x, im = e.positions(); v = e.velocities(); e.close()
+    img = np.stack([(im & 1023) - 512, ((im >> 10) & 1023) - 512, ((im >> 20) & 1023) - 512], axis=1)
+    bt, b1, b2 = s["bonds"]
+    lo, hi = s["box"]
+    with open(tmp_path / "data.angle", "w") as f:
+        f.write("chain with stiffness\n\n%d atoms\n%d bonds\n%d angles\n\n4 atom types\n2 bond types\n2 angle types\n\n" % (n, len(bt), n - 2))
+        for k, ax in enumerate("xyz"):
+            f.write("%.17g %.17g %slo %shi\n" % (lo[k], hi[k], ax, ax))
+        f.write("\nMasses\n\n1 1\n2 1\n3 1\n4 1\n\nAtoms # angle\n\n")
+        f.write("\n".join("%d 1 %d %.17g %.17g %.17g %d %d %d" % (t + 1, s["types"][t], *x[t], *img[t]) for t in range(n)))
+        f.write("\n\nVelocities\n\n" + "\n".join("%d %.17g %.17g %.17g" % (t + 1, *v[t]) for t in range(n)))
+        f.write("\n\nBonds\n\n" + "\n".join("%d %d %d %d" % (k + 1, bt[k], b1[k], b2[k]) for k in range(len(bt))))
+        f.write("\n\nAngles\n\n" + "\n".join("%d %d %d %d %d" % (c - 1, 1 + c % 2, c - 1, c, c + 1) for c in range(2, n)) + "\n")
+    deck = """units lj
+atom_style angle
+newton on off
+special_bonds fene
+atom_modify sort 0 0
+read_data data.angle
+neighbor 0.4 bin
+neigh_modify every 1 delay 0 check yes
+comm_modify cutoff 5.0
+bond_style fene
+bond_coeff 1 30.0 1.5 1.0 1.0
+bond_coeff 2 10.0 4.0 1.0 1.0
+angle_style cosine
+angle_coeff 1 2.0
+angle_coeff 2 0.75
+pair_style lj/cut 1.12246
+pair_modify shift yes
+pair_coeff * * 1.0 1.0 1.12246
+fix 1 all nve
+thermo_style custom step temp epair emol eangle etotal press
+thermo 10
+timestep 0.005
+run 30
+"""
+    (tmp_path / "in.angle").write_text(deck)
+    exe = os.path.join(ROOT, "lammps_le_b200", "le_deck")
+    r = subprocess.run([exe, "-in", "in.angle"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out, _ = refio.run_reference(deck.splitlines(), workdir=str(tmp_path), harness=False)
+    rows = lambda o: np.array([[float(q) for q in ln.split()] for ln in re.search(r"Step Temp E_pair E_mol E_angle TotEng Press \n(.*?)\nLoop time", o, re.S).group(1).splitlines()])
+    a, b = rows(r.stdout), rows(out)
+    assert a.shape == b.shape == (4, 7) and (a[:, 0] == b[:, 0]).all()
+    assert b[0, 4] > 0.05, "the deck must have angle energy"
+    rel = np.abs(a[:, 1:] - b[:, 1:]) / np.maximum(np.abs(b[:, 1:]), 1e-3)
+    assert rel[0].max() < 2e-6 and rel.max() < 2e-5, (a, b)

@@ -81,3 +81,53 @@ def test_chromatin_deck_with_user_le_fixes(tmp_path):
     # loaded minus unloaded extruders = change of the bond count, row by row (Thermo's own `bonds` keyword and the fixes' vectors)
     assert (bonds - nb0 == th[:, 7] - th[:, 8] + (bonds[0] - nb0 - th[0, 7] + th[0, 8])).all()
     assert th[-1, 7] > 0 and np.isfinite(th).all() and abs(th[-1, 1] - 1.0) < 0.2
+
+
+def test_angle_cosine_deck_through_the_binding(tmp_path):
+    """atom_style angle + angle_style cosine through run_style le/b200: E_angle of the reference's own Thermo follows the engine and
+    equals stock run_style verlet of the same binary at step 0 (2e-6) and over a short NVE run (2e-5)"""
+    need_exe()
+    from lammps_le_b200 import systems
+    n = 1500
+    s = systems.chromatin_chain(n, 0, rho=0.2, seed=23)
+    x, im = s["x"], s["image"]
+    img = np.stack([(im & 1023) - 512, ((im >> 10) & 1023) - 512, ((im >> 20) & 1023) - 512], axis=1)
+    bt, b1, b2 = s["bonds"]
+    lo, hi = s["box"]
+    with open(tmp_path / "data.angle", "w") as f:
+        f.write("chain with stiffness\n\n%d atoms\n%d bonds\n%d angles\n\n4 atom types\n2 bond types\n1 angle types\n\n" % (n, len(bt), n - 2))
+        for k, ax in enumerate("xyz"):
+            f.write("%.17g %.17g %slo %shi\n" % (lo[k], hi[k], ax, ax))
+        f.write("\nMasses\n\n1 1\n2 1\n3 1\n4 1\n\nAtoms # angle\n\n")
+        f.write("\n".join("%d 1 %d %.17g %.17g %.17g %d %d %d" % (t + 1, s["types"][t], *x[t], *img[t]) for t in range(n)))
+        f.write("\n\nBonds\n\n" + "\n".join("%d %d %d %d" % (k + 1, bt[k], b1[k], b2[k]) for k in range(len(bt))))
+        f.write("\n\nAngles\n\n" + "\n".join("%d 1 %d %d %d" % (c - 1, c - 1, c, c + 1) for c in range(2, n)) + "\n")
+    base = """units lj
+atom_style angle
+newton on off
+special_bonds fene
+atom_modify sort 0 0
+read_data data.angle
+neighbor 0.4 bin
+neigh_modify every 1 delay 0 check yes
+comm_modify cutoff 5.0
+bond_style fene
+bond_coeff * 30.0 1.5 1.0 1.0
+angle_style cosine
+angle_coeff 1 1.5
+pair_style lj/cut 1.12246
+pair_modify shift yes
+pair_coeff * * 1.0 1.0 1.12246
+velocity all create 1.0 4711
+fix 1 all nve/limit 0.02
+thermo_style custom step temp epair emol eangle etotal
+thermo 10
+timestep 0.002
+%s
+run 30
+"""
+    a = thermo_rows(run_lmp(base % "", tmp_path))[0][1]
+    b = thermo_rows(run_lmp(base % "run_style le/b200", tmp_path))[0][1]
+    assert a.shape == b.shape == (4, 6) and a[0, 4] > 0.05
+    rel = np.abs(a[:, 1:] - b[:, 1:]) / np.maximum(np.abs(a[:, 1:]), 1e-3)
+    assert rel[0].max() < 2e-6 and rel.max() < 5e-5, (a, b)

@@ -264,3 +264,56 @@ def test_langevin_ramp_spans_the_segments_of_one_run():
     whole, cut, saw = traj([120], False), traj([40, 40, 40], True), traj([40, 40, 40], False)
     assert dist(whole, cut) < 2e-3, dist(whole, cut)
     assert dist(whole, saw) > 20 * dist(whole, cut), (dist(whole, saw), dist(whole, cut))
+
+
+@pytest.mark.gpu
+def test_angle_cosine_matches_the_oracle_and_conserves_energy():
+    """angle_style cosine (src/MOLECULE/angle_cosine.cpp:47-140): forces / energies of a relaxed chain with a
+    stiffness term against the oracle restatement (itself pinned on the reference's angle-cosine.yaml), then NVE energy conservation
+    with the angle energy in E_mol"""
+    from oracle import restate as R
+    from lammps_le_b200 import systems
+    n = 3000
+    s = systems.chromatin_chain(n, 30, rho=0.2, seed=13)
+    e = systems.make_engine(s, velocities=systems.maxwell_velocities(n, 1.0, np.ones(n), 4), dt=0.005)
+    systems.relax(e, steps=500)
+    a2 = np.arange(2, n, dtype=np.int32)                      # every interior bead is the centre of one angle
+    ty = np.where(a2 % 2 == 0, 1, 2).astype(np.int32)
+    e.set_angle_types(2)
+    e.set_angle(1, "cosine", (3.0,)); e.set_angle(2, "cosine", (1.5,))
+    e.upload_angles(ty, a2 - 1, a2, a2 + 1)
+    f, th = e.compute_forces()
+    fp = e.compute_forces_plain()
+    assert np.array_equal(f, fp)
+    x, _ = e.positions()
+    L = np.asarray(s["box"][1]) - np.asarray(s["box"][0])
+    topo = e.topology()
+    rows = R.half_neighbor_list(x, np.asarray(s["box"][0]), np.asarray(s["box"][1]), 1.12246 + 0.4, topo["nspecial"], topo["special"])
+    pi = np.array([t for t in range(n) for _ in rows[t]], dtype=int)
+    pj = np.array([(w & R.NEIGHMASK) - 1 for t in range(n) for w in rows[t]], dtype=int)
+    fo, evdwl, _ = R.pair_lj_cut(x, L, pi, pj, np.zeros(len(pi), int), R.lj_coeffs(1.0, 1.0, 1.12246, True))
+    b1, b2, bt = R.unique_bonds(topo["num_bond"], topo["bond_type"], topo["bond_atom"])
+    fb, ebond, _, _ = R.bond_forces(x, L, b1, b2, bt, s["bond_coeffs"])
+    fa, eang, _ = R.angle_cosine(x, L, a2 - 2, a2 - 1, a2, ty, {1: 3.0, 2: 1.5})
+    ft = fo + fb + fa
+    mag = np.sqrt((ft ** 2).sum(1))
+    rel = (np.sqrt(((f - ft) ** 2).sum(1)) / np.maximum(mag, np.sqrt((mag ** 2).mean()))).max()
+    assert rel <= 1e-5, "max per-atom relative force error %.3g" % rel
+    assert abs(th["eangle"] * n - eang) <= 1e-9 * abs(eang) and abs(th["emol"] * n - (ebond + eang)) <= 1e-9 * abs(ebond + eang)
+    assert abs(th["epair"] * n - evdwl) <= 1e-6 * max(abs(evdwl), 1.0)
+    # let the chain settle with its new stiffness under the thermostat, then check NVE conservation with the angle energy in E_mol
+    e.fix_nve_limit(0.05); e.fix_langevin(1.0, 1.0, 1.0, 99)
+    e.run(600)
+    e2 = systems.make_engine(dict(s, x=e.positions()[0], image=e.positions()[1]), velocities=e.velocities(), dt=0.005)
+    e2.set_angle_types(2)
+    e2.set_angle(1, "cosine", (3.0,)); e2.set_angle(2, "cosine", (1.5,))
+    e2.upload_angles(ty, a2 - 1, a2, a2 + 1)
+    e2.fix_nve(True)
+    e2.thermo_every(100)
+    e2.run(1000)
+    th = e2.thermo()
+    et = np.array([t["etotal"] for t in th])
+    assert sum(t["fene_warnings"] for t in th) == 0
+    assert np.abs(et - et[0]).max() < 2e-3 * abs(et[0]), et
+    assert th[-1]["eangle"] > 0.1
+    e.close(); e2.close()

@@ -124,6 +124,17 @@ def test_reference_unit_vectors_lj_cut():
     assert np.abs(vir - c["init_stress"]).max() <= 5e-13 * np.abs(c["init_stress"]).max()
 
 
+def test_reference_unit_vectors_angle_cosine():
+    """unittest/force-styles/tests/angle-cosine.yaml: init_forces / init_energy / init_stress of the 29-atom molecule"""
+    c = _yaml_case("angle-cosine")
+    L = c["boxhi"] - c["boxlo"]
+    ang = c["angles"]
+    f, e, vir = R.angle_cosine(c["x"], L, ang[:, 1] - 1, ang[:, 2] - 1, ang[:, 3] - 1, ang[:, 0], {t + 1: k[0] for t, k in enumerate(c["angle_coeff"])})
+    assert np.abs(f - c["init_forces"]).max() <= 5e-13 * max(1.0, np.abs(c["init_forces"]).max())
+    assert abs(e - c["init_energy"]) <= 5e-13 * abs(c["init_energy"])
+    assert np.abs(vir - c["init_stress"]).max() <= 5e-13 * np.abs(c["init_stress"]).max()
+
+
 @pytest.mark.parametrize("name", ["bond-fene", "bond-harmonic"])
 def test_reference_unit_vectors_bonds(name):
     """unittest/force-styles/tests/bond-fene.yaml / bond-harmonic.yaml: init_forces / init_energy / init_stress"""
