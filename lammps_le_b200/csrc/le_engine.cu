@@ -11,6 +11,7 @@
 #include "le_build3.cuh"
 #include "le_build4.cuh"
 #include "le_build5.cuh"
+#include "le_build6.cuh"
 #include "le_step3.cuh"
 #include "le_step4.cuh"
 #include "le_angle.cuh"
@@ -76,7 +77,8 @@ struct le_ctx {
   bool atoms_loaded, topo_loaded, lists_valid, params_dirty;
   int scan_items;       // cells per thread of k_scan_cells
   bool topo_dirty;      // the tag-ordered topology tables changed since the last k_topo_pack
-  int build_variant;    // 3 = k_build3 (default), 5 = k_build5, 4 = k_build4 (LE_BUILD_VARIANT, A/B measurements)
+  int build_variant;    // 3 = k_build3 (default), 6 = k_build6, 5 = k_build5, 4 = k_build4 (LE_BUILD_VARIANT, A/B measurements)
+  int ell_rows;         // rows of Dev::nbr_ell
   int step_variant;     // 4 = k_step4 (default), 3 = k_step3 (LE_STEP_VARIANT, A/B measurements)
   Dev d;
   Params P;
@@ -866,7 +868,8 @@ extern "C" int le_upload_atoms(le_ctx *c, int n, const int *tag, const int *type
   d.tcap = TILE * c->maxneigh;
   if ((r = dalloc(c, &d.tile_cnt, (size_t)(cap / TILE) + 2))) return r;
   if ((r = dalloc(c, &d.nbr, ((size_t)(d.gr0 - d.own0) / TILE + 2) * d.tcap))) return r;
-  if ((r = dalloc(c, &d.nbr_ell, (size_t)cap * std::max(c->maxneigh - 15, 1)))) return r;   // rows beyond the smallest shared-memory queue
+  c->ell_rows = c->build_variant == 6 ? 2 * c->maxneigh : std::max(c->maxneigh - 15, 1);   // rows beyond the smallest shared-memory queue (k_build6: two rows per raw entry)
+  if ((r = dalloc(c, &d.nbr_ell, (size_t)cap * c->ell_rows))) return r;
   if ((r = dalloc(c, &d.bondrow, (size_t)cap * c->bpa))) return r;
   if ((r = dalloc(c, &d.topo, (size_t)n))) return r;
   if ((r = dalloc(c, &d.order2, (size_t)cap))) return r;
@@ -1201,7 +1204,12 @@ static void enqueue_rebuild(le_ctx *c, bool direct) {
     LAUNCH(c, k_rb_post_ghosts, 1, 1, d);
     LAUNCH(c, k_ghost_map, grid_for(2 * d.own0, 256), 256, d);
   }
-  if (c->build_variant == 5) {
+  if (c->build_variant == 6 && !(d.cell_abs[0] | d.cell_abs[1] | d.cell_abs[2])) {
+    const int g = grid_for(nslots, B6_THREADS);
+    const bool uni = c->P.pair_uniform != 0;
+    if (build_queue_depth(c) > 16) { if (uni) LAUNCH(c, (k_build6<40, 4, 1>), g, B6_THREADS, d, c->ell_rows); else LAUNCH(c, (k_build6<40, 4, 0>), g, B6_THREADS, d, c->ell_rows); }
+    else { if (uni) LAUNCH(c, (k_build6<16, 8, 1>), g, B6_THREADS, d, c->ell_rows); else LAUNCH(c, (k_build6<16, 8, 0>), g, B6_THREADS, d, c->ell_rows); }
+  } else if (c->build_variant == 5) {
     const int g = grid_for(nslots, BUILD_THREADS);
     const bool uni = c->P.pair_uniform != 0;
     if (build_queue_depth(c) > 16) { if (uni) LAUNCH(c, (k_build5<36, 4, 1>), g, BUILD_THREADS, d); else LAUNCH(c, (k_build5<36, 4, 0>), g, BUILD_THREADS, d); }

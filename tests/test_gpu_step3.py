@@ -106,3 +106,66 @@ def test_dense_tiles_against_the_oracle():
     rel = (np.sqrt(((f - fo) ** 2).sum(1)) / np.maximum(mag, np.sqrt((mag ** 2).mean()))).max()
     assert rel <= 1e-5, "max per-atom relative force error %.3g" % rel
     assert abs(th["epair"] * n - evdwl) <= 1e-5 * abs(evdwl) and abs(th["emol"] * n - ebond) <= 1e-5 * abs(ebond)
+
+
+def _with_build_variant(variant, fn):
+    old = os.environ.get("LE_BUILD_VARIANT")
+    os.environ["LE_BUILD_VARIANT"] = str(variant)          # read by le_create
+    try:
+        return fn()
+    finally:
+        if old is None:
+            del os.environ["LE_BUILD_VARIANT"]
+        else:
+            os.environ["LE_BUILD_VARIANT"] = old
+
+
+def _lists_of(system, v):
+    e = systems.make_engine(system, velocities=v)
+    e.force_rebuild()
+    off, ent = e.neighlist(half=False)     # the full list, every atom's entries in the order the step kernel adds them
+    bl = e.bondlist()
+    f = e.compute_forces_plain()
+    e.close()
+    return off, ent, bl, f
+
+
+def _dense_core_in_a_dilute_box():
+    """a lattice melt (rho 0.84; the snake path never leaves its box) inside a box of 1.6 x its side: the global density
+    picks the 16-deep shared-memory queue of the list build, the core screens ~15 candidates per atom -> the scratch-row
+    path beyond the queue"""
+    s = dict(systems.fene_melt(nchains=30, length=100))
+    lo, hi = s["box"]
+    L = np.asarray(hi) - np.asarray(lo)
+    s["box"] = (np.asarray(lo) - 0.3 * L, np.asarray(hi) + 0.3 * L)
+    return s
+
+
+@pytest.mark.parametrize("variant", [6])
+@pytest.mark.parametrize("case", ["chain", "melt", "dense_core"])
+def test_build_variants_give_identical_lists(case, variant):
+    """k_build6 (tile-centred windows, LE_BUILD_VARIANT=6; measured slower, kept as the second implementation the default
+    is checked against) and k_build3: the full list word for word IN ORDER, the bond list, the forces and a trajectory
+    across several rebuilds bit for bit"""
+    if case == "chain":
+        n = 20000
+        s, v = relaxed(systems.chromatin_chain(n, 200, rho=0.2, seed=7), n, 300)
+    elif case == "melt":
+        s = systems.fene_melt(nchains=40, length=100)
+        n = len(s["types"])
+        s, v = relaxed(s, n, 300)
+    else:
+        s = _dense_core_in_a_dilute_box()
+        n = len(s["types"])
+        v = np.zeros((n, 3))
+    a = _with_build_variant(3, lambda: _lists_of(s, v))
+    b = _with_build_variant(variant, lambda: _lists_of(s, v))
+    assert a[1].size > n // 2
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), "full lists differ (%d / %d entries)" % (a[1].size, b[1].size)
+    assert np.array_equal(a[2], b[2]), "bond lists differ"
+    assert np.array_equal(a[3], b[3]), "forces differ"
+    if case != "dense_core":                 # (the lattice start overlaps: no dynamics there)
+        ta = _with_build_variant(3, lambda: trajectory(s, v, True, 120, False))
+        tb = _with_build_variant(variant, lambda: trajectory(s, v, True, 120, False))
+        assert ta[2] > 3 and ta[2] == tb[2]
+        assert np.array_equal(ta[0][0], tb[0][0]) and np.array_equal(ta[1], tb[1]), "trajectories differ"
