@@ -131,6 +131,12 @@ int le_fix_ex_unload(le_ctx *c, int nevery, int btype, double rc, double prob, i
 /* fix ID all bond/break N bondtype Rmax prob f seed (src/MC/fix_bond_break.cpp, the ancestor of ex_unload: same body, step gate
  * `ntimestep % N` instead of `ntimestep % N - 2`); takes the ex_unload slot (unfix: LE_FIX_EX_UNLOAD) */
 int le_fix_bond_break(le_ctx *c, int nevery, int btype, double rmax, double prob, int seed);
+/* fix ID all bond/create N itype jtype Rmin bondtype iparam imax inew jparam jmax jnew prob f seed (src/MC/fix_bond_create.cpp:41-200,
+ * 349-629, the ancestor of ex_load: events on `ntimestep % N == 0`, partner = the closest eligible listed neighbor within Rmin
+ * without the loop-extrusion rules, bond counts taken once in the first run's setup); takes the ex_load slot (unfix:
+ * LE_FIX_EX_LOAD; thermo f_ID[k] = slot 2).  inew / jnew < 1 = keep the type.  newton_bond must be off. */
+int le_fix_bond_create(le_ctx *c, int nevery, int itype, int jtype, double rmin, int btype, double prob,
+                       int seed, int imaxbond, int inewtype, int jmaxbond, int jnewtype);
 int le_unfix(le_ctx *c, int which);                         /* unfix */
 
 /* ---- atoms and topology ---------------------------------------------------------------- */

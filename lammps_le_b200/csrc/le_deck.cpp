@@ -11,7 +11,7 @@
 //   read_data F [extra/bond/per/atom N] [extra/special/per/atom N] | mass T M
 //   neighbor S bin | neigh_modify every|delay|check ... | pair_style lj/cut RC | pair_modify shift yes|no
 //   pair_coeff I J eps sigma [rc] | bond_style fene|harmonic|hybrid ... | bond_coeff N [style] ...
-//   fix ID all nve | nve/limit X | langevin T0 T1 damp seed | extrusion ... | ex_load ... | ex_unload ...
+//   fix ID all nve | nve/limit X | langevin T0 T1 damp seed | extrusion ... | ex_load ... | ex_unload ... | bond/break ... | bond/create ...
 //   unfix ID | timestep dt | reset_timestep N | thermo N | thermo_modify ... | run N | read_restart file | write_restart file
 //   thermo_style one | custom step elapsed dt time atoms temp press pe ke etotal evdwl epair ebond emol vol density lx ly lz bonds f_ID[1|2]
 //   minimize etol ftol maxiter maxeval | min_style cg
@@ -301,7 +301,7 @@ void print_thermo(Deck &d, int first) {
   for (size_t k = 0; k < d.thermo_fix_cols.size(); k++) {
     const auto it = d.fix_style.find(d.thermo_fix_cols[k].id);
     if (it == d.fix_style.end()) die("Could not find thermo fix ID " + d.thermo_fix_cols[k].id);
-    fix_slot[k] = it->second == "extrusion" ? 0 : (it->second == "ex_unload" || it->second == "bond/break") ? 1 : it->second == "ex_load" ? 2 : -1;
+    fix_slot[k] = it->second == "extrusion" ? 0 : (it->second == "ex_unload" || it->second == "bond/break") ? 1 : (it->second == "ex_load" || it->second == "bond/create") ? 2 : -1;
     if (fix_slot[k] < 0) die("Thermo fix does not compute vector");
   }
   for (int q : cols) std::printf("%s ", q >= 1000 ? d.thermo_fix_cols[q - 1000].title.c_str() : THERMO_FIELDS[q].title);
@@ -667,6 +667,16 @@ void fix(Deck &d, const Words &w) {
       else die("Illegal fix bond/break command");
     }
     ck(d, le_fix_bond_break(d.ctx, inum(w[4]), inum(w[5]), num(w[6]), prob, seed));
+  } else if (st == "bond/create") {      // fix ID all bond/create N itype jtype Rmin bondtype [iparam M T] [jparam M T] [prob f seed]   (src/MC/fix_bond_create.cpp:41-150)
+    need(9);
+    double prob = 1.0; int seed = 12345, imax = 0, inew = inum(w[5]), jmax = 0, jnew = inum(w[6]);
+    for (size_t k = 9; k < w.size();) {
+      if (w[k] == "prob" && k + 2 < w.size()) { prob = num(w[k + 1]); seed = inum(w[k + 2]); k += 3; }
+      else if (w[k] == "iparam" && k + 2 < w.size()) { imax = inum(w[k + 1]); inew = inum(w[k + 2]); k += 3; }
+      else if (w[k] == "jparam" && k + 2 < w.size()) { jmax = inum(w[k + 1]); jnew = inum(w[k + 2]); k += 3; }
+      else die("Illegal fix bond/create command");       // (atype / dtype / itype / aconstrain: angles and dihedrals are not created here)
+    }
+    ck(d, le_fix_bond_create(d.ctx, inum(w[4]), inum(w[5]), inum(w[6]), num(w[7]), inum(w[8]), prob, seed, imax, inew, jmax, jnew));
   } else die("Unknown fix style " + st);
   d.fix_style[w[1]] = st;
 }
@@ -676,7 +686,7 @@ void unfix(Deck &d, const Words &w) {
   const std::string st = d.fix_style[w[1]];
   if (st == "nve" || st == "nve/limit") ck(d, le_fix_nve(d.ctx, 0));
   else if (st == "extrusion") ck(d, le_unfix(d.ctx, LE_FIX_EXTRUSION));
-  else if (st == "ex_load") ck(d, le_unfix(d.ctx, LE_FIX_EX_LOAD));
+  else if (st == "ex_load" || st == "bond/create") ck(d, le_unfix(d.ctx, LE_FIX_EX_LOAD));
   else if (st == "ex_unload" || st == "bond/break") ck(d, le_unfix(d.ctx, LE_FIX_EX_UNLOAD));
   else if (st == "langevin") die("unfix of fix langevin is not supported");
   d.fix_style.erase(w[1]);

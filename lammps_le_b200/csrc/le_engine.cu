@@ -32,7 +32,7 @@ static inline int h_float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; 
 #define THERMO_SLOTS 4096
 
 struct FixExtrusionCfg { int on, nevery, neutral, left, right, btype, roadblock, seed; double p; };
-struct FixExLoadCfg { int on, nevery, itype, jtype, btype, seed, imax, inew, jmax, jnew; double rc, prob; };
+struct FixExLoadCfg { int on, nevery, itype, jtype, btype, seed, imax, inew, jmax, jnew, phase, create, counted; double rc, prob; };   // phase 3 = fix ex_load; phase 0 + create = its ancestor fix bond/create
 struct FixExUnloadCfg { int on, nevery, btype, seed, phase; double rc, prob; };   // phase: 2 = fix ex_unload, 0 = its ancestor fix bond/break
 
 #define PLAIN_UNROLL 8      // timesteps per launch of the steady-state graph
@@ -502,6 +502,7 @@ extern "C" int le_fix_ex_load(le_ctx *c, int nevery, int itype, int jtype, doubl
   if (itype == jtype && (imax != jmax || inew != jnew)) return fail(c, LE_EINVAL, "Inconsistent iparam/jparam values in fix ex_load command");
   c->fl.on = 1; c->fl.nevery = nevery; c->fl.itype = itype; c->fl.jtype = jtype; c->fl.rc = rc; c->fl.btype = btype;
   c->fl.prob = prob; c->fl.seed = seed; c->fl.imax = imax; c->fl.inew = inew; c->fl.jmax = jmax; c->fl.jnew = jnew;
+  c->fl.phase = 3; c->fl.create = 0; c->fl.counted = 0;
   c->lf.rng[2].seeded = 0;
   if (std::find(c->fix_order.begin(), c->fix_order.end(), LE_FIX_EX_LOAD) == c->fix_order.end()) c->fix_order.push_back(LE_FIX_EX_LOAD);
   return LE_OK;
@@ -529,6 +530,27 @@ extern "C" int le_fix_bond_break(le_ctx *c, int nevery, int btype, double rmax, 
   const int r = le_fix_ex_unload(c, nevery, btype, rmax, prob, seed);
   if (r) return r;
   c->fu.phase = 0;
+  return LE_OK;
+}
+
+/* fix ID all bond/create N itype jtype Rmin bondtype [iparam M T] [jparam M T] [prob f seed] (src/MC/fix_bond_create.cpp): the
+ * ancestor of fix ex_load.  Against its descendant: events on multiples of N (fix_bond_create.cpp:356), no loop-extrusion rules
+ * in the partner search -- the closest eligible listed neighbor wins (:427-473) --, bond counts taken once at the first run's
+ * setup (:302-345).  Creation, special lists, type changes, counters and the forced rebuild are the shared body.  It occupies
+ * the ex_load slot (one of the two per context); newton_bond must be off (bonds are stored with both atoms). */
+extern "C" int le_fix_bond_create(le_ctx *c, int nevery, int itype, int jtype, double rmin, int btype, double prob, int seed,
+                                  int imax, int inew, int jmax, int jnew) {
+  if (!c) return LE_EINVAL;
+  if (nevery <= 0 || rmin < 0.0 || prob < 0.0 || prob > 1.0 || seed <= 0 || imax < 0 || jmax < 0) return fail(c, LE_EINVAL, "Illegal fix bond/create command");
+  if (itype < 1 || itype > c->ntypes || jtype < 1 || jtype > c->ntypes || inew > c->ntypes || jnew > c->ntypes)
+    return fail(c, LE_EINVAL, "Invalid atom type in fix bond/create command");
+  if (btype < 1 || btype > c->nbondtypes) return fail(c, LE_EINVAL, "Invalid bond type in fix bond/create command");
+  if (c->newton_bond) return fail(c, LE_EINVAL, "fix bond/create: newton_bond on is not supported by this engine (use newton on off)");
+  if (itype == jtype && ((imax != jmax) || ((inew < 1 ? itype : inew) != (jnew < 1 ? jtype : jnew))))
+    return fail(c, LE_EINVAL, "Inconsistent iparam/jparam values in fix bond/create command");
+  const int r = le_fix_ex_load(c, nevery, itype, jtype, rmin, btype, prob, seed, imax, inew, jmax, jnew);
+  if (r) return r;
+  c->fl.phase = 0; c->fl.create = 1; c->fl.counted = 0;
   return LE_OK;
 }
 
@@ -1633,7 +1655,7 @@ static void le_mark(le_ctx *c) {
 static bool le_event_at(const le_ctx *c, int64_t step) {
   if (c->fx.on && (step % c->fx.nevery - 1) == 0) return true;
   if (c->fu.on && (step % c->fu.nevery - c->fu.phase) == 0) return true;
-  if (c->fl.on && (step % c->fl.nevery - 3) == 0) return true;
+  if (c->fl.on && (step % c->fl.nevery - c->fl.phase) == 0) return true;
   return false;
 }
 
@@ -1684,6 +1706,7 @@ extern "C" int le_run(le_ctx *c, int64_t nsteps) {
   enqueue_rebuild(c, true);
   c->lists_valid = true;
   c->le_ev_used = 0;
+  enqueue_bond_create_setup(c);
   CK(cudaEventRecord(c->ev0, c->stream));
   if ((r = force_eval(begin))) return r;
   int64_t s = begin;

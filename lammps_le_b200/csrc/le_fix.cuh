@@ -36,6 +36,7 @@ struct RngHost { int seeded; int seed; };
 struct LeFixDev {
   int N;
   int *bondcount, *to_add, *to_remove, *final_add, *final_remove, *partner;
+  int *bc_keep;         // fix bond/create: its bond counts between events (bondcount is scratch the other fixes recount)
   double *distsq, *prob;
   unsigned long long *claim;   // ordered executor: (~round << 32) | priority of the best claimant of a bead
   int *exec_rem;               // [LE_EXEC_ROUNDS + 1] "tasks were left over after round r"
@@ -73,7 +74,7 @@ static int le_fix_alloc(LeFixDev &f, int n, int maxspecial, std::vector<void *> 
   };
   const size_t n1 = (size_t)n + 2;
   int r = 0;
-  r |= A((void **)&f.bondcount, n1 * 4); r |= A((void **)&f.to_add, n1 * 4); r |= A((void **)&f.to_remove, n1 * 4);
+  r |= A((void **)&f.bondcount, n1 * 4); r |= A((void **)&f.bc_keep, n1 * 4); r |= A((void **)&f.to_add, n1 * 4); r |= A((void **)&f.to_remove, n1 * 4);
   r |= A((void **)&f.final_add, n1 * 4); r |= A((void **)&f.final_remove, n1 * 4); r |= A((void **)&f.partner, n1 * 4);
   r |= A((void **)&f.distsq, n1 * 8); r |= A((void **)&f.prob, n1 * 8);
   r |= A((void **)&f.claim, n1 * 8); r |= A((void **)&f.exec_rem, 64 * 4); r |= A((void **)&f.flag, n1 * 4); r |= A((void **)&f.scan, n1 * 4);
@@ -931,13 +932,17 @@ __global__ void k_unl_break(LeView V, UnloadArgs A) {
 // ------------------------------------------------------------------------------------------------
 // fix ex_load (fix_ex_load.cpp:329-655)
 // ------------------------------------------------------------------------------------------------
-__global__ void k_load_init(LeView V, int btype) {
+// recount: fix ex_load counts the bonds of its type afresh in every event (fix_ex_load.cpp:352-366); fix bond/create counts
+// once, in the setup of its first run, and from then on only adds what it creates itself (fix_bond_create.cpp:302-345, 576)
+__global__ void k_load_init(LeView V, int btype, int recount) {
   const Dev &d = V.d; const LeFixDev &f = V.f;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) {
-    int bc = 0;
-    const int nb = d.num_bond[i];
-    for (int m = 0; m < nb; m++) if (d.bond_type[(size_t)i * d.bpa + m] == btype) bc++;
-    f.bondcount[i] = bc;
+    if (recount) {
+      int bc = 0;
+      const int nb = d.num_bond[i];
+      for (int m = 0; m < nb; m++) if (d.bond_type[(size_t)i * d.bpa + m] == btype) bc++;
+      f.bondcount[i] = bc;
+    }
     f.partner[i] = 0; f.final_add[i] = 0; f.final_remove[i] = 0;
     f.distsq[i] = LE_BIG; f.claim[i] = ~0ull;
     if (i < 16) f.counters[i] = 0;
@@ -1043,6 +1048,99 @@ __global__ void k_load_scan_runs(LeView V) {
       if (rsq < f.distsq[lo - 1]) { f.partner[lo - 1] = hi; f.distsq[lo - 1] = rsq; }
       if (rsq < f.distsq[hi - 1]) { f.partner[hi - 1] = lo; f.distsq[hi - 1] = rsq; }
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fix bond/create (src/MC/fix_bond_create.cpp:349-629), the ancestor of fix ex_load: the same event without the loop-extrusion
+// rules (|tag difference| == 2, free middle bead, two backbone bonds), so ANY listed pair within the cutoff can bond and the
+// partner of an atom is simply its closest eligible neighbor -- a minimum, not a traversal: no runs, no ordered executor.
+// The list the fix walks is the pair list of the last rebuild (an occasional copy) with the
+// CURRENT coordinates.  One warp per tile of the full list, lane = owned atom: for every entry the lane works out which end
+// the reference's HALF list stores the pair on (le_pair_stored_on_i: the type / bond-count test of fix_bond_create.cpp:432-441
+// is not symmetric when both types are equal but the limits differ, and the 1-2 check :447-449 reads the list owner's
+// specials), measures the distance as that visit does -- owner minus stored neighbor, a periodic ghost shifted by the image
+// found at the last rebuild -- and keeps the smallest (ties, which need two bit-equal squared distances, go to the lower
+// partner tag; the reference would keep the pair it visits first).  Measured by the owner of each atom, collected by tag on
+// every GPU like the records of the other fixes.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_bcreate_geo(LeView V, LoadArgs A) {
+  const Dev &d = V.d; const LeFixDev &f = V.f;
+  const int lane = threadIdx.x & 31;
+  const int nown = d.ctrl->nown, own_end = d.own0 + nown, stamp = (int)d.ctrl->le_epoch;
+  const int ntiles = (nown + TILE - 1) / TILE;
+  const int nt = c_P.ntypes;
+  for (int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < ntiles; tile += (gridDim.x * blockDim.x) >> 5) {
+    const int k = d.own0 + tile * TILE + lane;
+    const bool valid = k < own_end;
+    const int nn = valid ? (int)AUX_NN(__float_as_uint(d.vel[k].w)) : 0;
+    int inc = nn;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += v;
+    }
+    if (!valid || nn == 0) continue;
+    const unsigned *__restrict__ run = d.nbr + (size_t)tile * d.tcap + (inc - nn);
+    const int4 hi_ = d.pos_hold[k];
+    const int ti = hi_.w >> 3;
+    const unsigned ui[3] = {(unsigned)hi_.x, (unsigned)hi_.y, (unsigned)hi_.z};
+    double xi[3];
+    raw_xyz(V, ti, xi);
+    const int type_i = type_of(V, ti), bc_i = f.bondcount[ti - 1];
+    int best = 0; double best_rsq = LE_BIG;
+    for (int q = 0; q < nn; q++) {
+      const int j = (int)(run[q] & NEIGH_IDX_MASK);
+      const int4 hj = d.pos_hold[j];
+      const int tj = hj.w >> 3;
+      const unsigned uj[3] = {(unsigned)hj.x, (unsigned)hj.y, (unsigned)hj.z};
+      int ghost;
+      const bool on_i = le_pair_stored_on_i(c_P, ui, uj, ti, tj, &ghost);
+      const int type_j = type_of(V, tj), bc_j = f.bondcount[tj - 1];
+      // (itype, bondcount) of the list owner / of the stored neighbor
+      const int ot = on_i ? type_i : type_j, nty = on_i ? type_j : type_i, obc = on_i ? bc_i : bc_j, nbc = on_i ? bc_j : bc_i;
+      int possible = 0;
+      if (ot == A.itype && nty == A.jtype) {
+        if ((A.imax == 0 || obc < A.imax) && (A.jmax == 0 || nbc < A.jmax)) possible = 1;
+      } else if (ot == A.jtype && nty == A.itype) {
+        if ((A.jmax == 0 || obc < A.jmax) && (A.imax == 0 || nbc < A.imax)) possible = 1;
+      }
+      if (!possible) continue;
+      const int otag = on_i ? ti : tj, ntag = on_i ? tj : ti;
+      const int *sl = d.special + (size_t)(otag - 1) * d.maxspecial;
+      const int n1 = d.nspecial[(size_t)(otag - 1) * 3];
+      for (int m = 0; m < n1; m++) if (sl[m] == ntag) possible = 0;
+      if (!possible) continue;
+      double xj[3];
+      raw_xyz(V, tj, xj);
+      double rsq;
+      if (!ghost) rsq = on_i ? dist2(xi, xj) : dist2(xj, xi);
+      else {
+        // the stored neighbor is a periodic ghost: its coordinate is the owned atom's plus the shift of the image that was
+        // closest to the list owner at the last rebuild (AtomVec::pack_border / pack_comm: x + pbc * prd)
+        double xo[3], xn[3];
+        for (int a = 0; a < 3; a++) {
+          xo[a] = on_i ? xi[a] : xj[a];
+          xn[a] = on_i ? xj[a] : xi[a];
+          const int sh = on_i ? le_image_shift(ui[a], uj[a]) : le_image_shift(uj[a], ui[a]);
+          if (sh) xn[a] = __dadd_rn(xn[a], (double)sh * c_P.L[a]);
+        }
+        rsq = dist2(xo, xn);
+      }
+      if (rsq >= A.cutsq) continue;
+      if (rsq < best_rsq || (rsq == best_rsq && tj < best)) { best = tj; best_rsq = rsq; }
+    }
+    if (best) geo_store(d, ti - 1, best, stamp, 1, &best_rsq);
+  }
+  (void)nt;
+}
+
+__global__ void k_bcreate_collect(LeView V) {
+  const Dev &d = V.d; const LeFixDev &f = V.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < d.N; i += gridDim.x * blockDim.x) {
+    const bool fresh = geo_fresh(V, i);
+    f.partner[i] = fresh ? f.geo_i[(size_t)i * LE_GEO_I] : 0;
+    f.distsq[i] = fresh ? f.geo[(size_t)i * LE_GEO_D] : LE_BIG;
   }
 }
 

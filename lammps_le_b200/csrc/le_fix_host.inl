@@ -230,24 +230,43 @@ static int enqueue_load(le_ctx *c) {
   {
     const int k = (c->fl.itype - 1) * c->ntypes + (c->fl.jtype - 1);
     if (!c->pair_set || c->fl.rc * c->fl.rc > c->cut[k] * c->cut[k])
-      return fail(c, LE_EINVAL, "Fix ex_load cutoff is longer than pairwise cutoff");
+      return fail(c, LE_EINVAL, c->fl.create ? "Fix bond/create cutoff is longer than pairwise cutoff" : "Fix ex_load cutoff is longer than pairwise cutoff");
   }
   LeFixDev &f = c->lf;
   LeView V{c->d, f};
   LoadArgs A{c->fl.btype, c->fl.itype, c->fl.jtype, c->fl.imax, c->fl.inew, c->fl.jmax, c->fl.jnew, c->fl.rc * c->fl.rc, c->fl.prob};
   const int g = grid_for(c->N, 256);
   LAUNCH(c, k_le_begin, 1, 1, c->d);
-  LAUNCH(c, k_load_init, g, 256, V, A.btype);
-  LAUNCH(c, k_load_geo, grid_for(c->d.gr0 - c->d.own0, 256), 256, V, A);
-  LAUNCH(c, k_le_exchange, 1, 1, c->d);
-  LAUNCH(c, k_load_eligible, g, 256, V);
-  LAUNCH(c, k_load_scan_runs, g, 256, V);
+  if (c->fl.create) {
+    // fix bond/create: bond counts from the first run's setup (enqueue_bond_create_setup), partner = closest eligible neighbor
+    cudaMemcpyAsync(f.bondcount, f.bc_keep, sizeof(int) * c->N, cudaMemcpyDeviceToDevice, c->stream);
+    LAUNCH(c, k_load_init, g, 256, V, A.btype, 0);
+    LAUNCH(c, k_bcreate_geo, std::min(grid_for(c->d.gr0 - c->d.own0, 128), c->sm_count * 16), 128, V, A);
+    LAUNCH(c, k_le_exchange, 1, 1, c->d);
+    LAUNCH(c, k_bcreate_collect, g, 256, V);
+  } else {
+    LAUNCH(c, k_load_init, g, 256, V, A.btype, 1);
+    LAUNCH(c, k_load_geo, grid_for(c->d.gr0 - c->d.own0, 256), 256, V, A);
+    LAUNCH(c, k_le_exchange, 1, 1, c->d);
+    LAUNCH(c, k_load_eligible, g, 256, V);
+    LAUNCH(c, k_load_scan_runs, g, 256, V);
+  }
   LAUNCH(c, k_load_flag_partners, g, 256, f, c->N);
   if (A.fraction < 1.0) draw_for_flagged(c, 2, A.fraction);
   LAUNCH(c, k_load_create, g, 256, V, A);
+  if (c->fl.create) cudaMemcpyAsync(f.bc_keep, f.bondcount, sizeof(int) * c->N, cudaMemcpyDeviceToDevice, c->stream);
   LAUNCH(c, k_le_finish, 1, 1, c->d, f, 3);
   topo_sweep(c, (const int *)f.final_add, 1);
   return LE_OK;
+}
+
+// FixBondCreate::setup (fix_bond_create.cpp:302-345): the bonds of the fix's type are counted once, when its first run starts
+static void enqueue_bond_create_setup(le_ctx *c) {
+  if (!c->fl.on || !c->fl.create || c->fl.counted) return;
+  LeView V{c->d, c->lf};
+  LAUNCH(c, k_load_init, grid_for(c->N, 256), 256, V, c->fl.btype, 1);
+  cudaMemcpyAsync(c->lf.bc_keep, c->lf.bondcount, sizeof(int) * c->N, cudaMemcpyDeviceToDevice, c->stream);
+  c->fl.counted = 1;
 }
 
 // Modify::post_integrate on timestep `step`: each fix checks its own gate
@@ -256,9 +275,19 @@ static int enqueue_le_events(le_ctx *c, int64_t step) {
   bool any = false;
   for (int which : c->fix_order) {
     int r = LE_OK;
+    const bool fires = (which == LE_FIX_EXTRUSION && c->fx.on && (step % c->fx.nevery - 1) == 0) ||
+                       (which == LE_FIX_EX_UNLOAD && c->fu.on && (step % c->fu.nevery - c->fu.phase) == 0) ||
+                       (which == LE_FIX_EX_LOAD && c->fl.on && (step % c->fl.nevery - c->fl.phase) == 0);
+    if (fires && any && c->nranks > 1) {
+      // a second event on the same timestep (fix bond/create and fix bond/break share their steps): its owners store their
+      // geometry records into the same per-tag slots of every GPU, so nobody may start before every GPU has read the records of
+      // the event before -- one more flag round (events on different timesteps are separated by the per-step rounds)
+      LAUNCH(c, k_le_begin, 1, 1, c->d);
+      LAUNCH(c, k_le_exchange, 1, 1, c->d);
+    }
     if (which == LE_FIX_EXTRUSION && c->fx.on && (step % c->fx.nevery - 1) == 0) { r = enqueue_extrusion(c); any = true; }
     else if (which == LE_FIX_EX_UNLOAD && c->fu.on && (step % c->fu.nevery - c->fu.phase) == 0) { r = enqueue_unload(c); any = true; }
-    else if (which == LE_FIX_EX_LOAD && c->fl.on && (step % c->fl.nevery - 3) == 0) { r = enqueue_load(c); any = true; }
+    else if (which == LE_FIX_EX_LOAD && c->fl.on && (step % c->fl.nevery - c->fl.phase) == 0) { r = enqueue_load(c); any = true; }
     if (r) return r;
   }
   // the digests of the atoms an event touched were refreshed by its topology sweeps (k_le_topo_rebuild)

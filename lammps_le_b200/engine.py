@@ -75,6 +75,7 @@ def load_library():
         "le_thermo_every": [P, I], "le_fix_nve": [P, I], "le_fix_nve_limit": [P, D],
         "le_fix_langevin": [P, D, D, D, I], "le_fix_extrusion": [P, I, I, I, I, D, I, I, I],
         "le_fix_ex_load": [P, I, I, I, D, I, D, I, I, I, I, I], "le_fix_ex_unload": [P, I, I, D, D, I], "le_fix_bond_break": [P, I, I, D, D, I],
+        "le_fix_bond_create": [P, I, I, I, D, I, D, I, I, I, I, I],
         "le_unfix": [P, I], "le_upload_atoms": [P, I, pi, pi, pd, pd, pi], "le_upload_bonds": [P, I, pi, pi, pi],
         "le_upload_topology": [P, pi, pi, pi, pi, pi], "le_set_positions": [P, pd, pi], "le_set_velocities": [P, pd],
         "le_run": [P, I64], "le_set_run_span": [P, I64, I64], "le_run_timed": [P, I64, pd], "le_force_rebuild": [P], "le_run_le_event": [P, I],
@@ -299,6 +300,13 @@ class Engine:
     def fix_bond_break(self, nevery, btype, rmax, prob=1.0, seed=12345):
         """fix bond/break (src/MC/fix_bond_break.cpp): fix ex_unload's body on steps that are multiples of nevery"""
         self._ck(self.lib.le_fix_bond_break(self._h, nevery, btype, rmax, prob, seed))
+
+    @_journaled
+    def fix_bond_create(self, nevery, itype, jtype, rmin, btype, prob=1.0, seed=12345, iparam=(0, 0), jparam=(0, 0)):
+        """fix bond/create (src/MC/fix_bond_create.cpp): fix ex_load's ancestor -- the closest eligible listed neighbor within
+        rmin, no loop-extrusion rules, events on steps that are multiples of nevery"""
+        self._ck(self.lib.le_fix_bond_create(self._h, nevery, itype, jtype, rmin, btype, prob, seed,
+                                             iparam[0], iparam[1], jparam[0], jparam[1]))
 
     @_journaled
     def unfix(self, which):

@@ -32,9 +32,10 @@ GEN = os.path.join(OUT, "gen")
 OBJ = os.path.join(OUT, "obj")
 
 SRC_DIRS = ["src", "src/MOLECULE", "src/USER-LE"]
-# single styles from packages that are not compiled as a whole: fix bond/break (src/MC), the ancestor of fix ex_unload -- the
-# checker for le_fix_bond_break (tests/test_gpu_md.py)
-EXTRA_STYLES = [("src/MC", "fix_bond_break")]
+# single styles from packages that are not compiled as a whole: fix bond/break and fix bond/create (src/MC), the ancestors of fix
+# ex_unload and fix ex_load -- the
+# checkers for le_fix_bond_break and le_fix_bond_create (tests/test_gpu_md.py)
+EXTRA_STYLES = [("src/MC", "fix_bond_break"), ("src/MC", "fix_bond_create")]
 CXXFLAGS = ["-O2", "-std=c++11", "-fPIC", "-DLAMMPS_SMALLBIG", "-DLAMMPS_EXCEPTIONS",
             "-ffp-contract=off", "-w"]
 OMP = False      # second build (oracle/_ref/omp/): the same sources + the USER-OMP styles whose base style is compiled, -fopenmp

@@ -14,6 +14,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 400
 rank, world, local, group = init_process_group()
 melt = len(sys.argv) > 3 and sys.argv[3] == "melt"
+mc = len(sys.argv) > 3 and sys.argv[3] == "mc"      # fix bond/create + fix bond/break (src/MC) instead of the three USER-LE fixes
 if melt:
     # BASELINE configs[2], bench/in.chain.scaled: the 32,000-bead FENE melt of bench/data.chain replicated `world` times along x
     z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "bench_chain.npz"))
@@ -30,6 +31,8 @@ else:
     s = systems.chromatin_chain(n, n // 100, rho=0.2, seed=12345, barriers="random", extruder_bond=systems.EXTRUDER_FENE)
     v = systems.maxwell_velocities(n, 1.0, np.ones(n), 1)
     halo = 6.2
+    if mc:
+        s["bond_per_atom"] = 6      # two backbone bonds + up to two extruder bonds + two created ones
 dd = systems.make_engine(s, device=local, velocities=v, dd=dict(rank=rank, world=world, halo=halo, group=group))
 ref = systems.make_engine(s, device=local, velocities=v) if rank == 0 else None
 ok = True
@@ -93,18 +96,24 @@ if melt:
 # USER-LE events on the decomposed system: the decision logic is replicated, the geometry comes from the owners
 for e in (dd, ref):
     if e is None: continue
-    e.fix_extrusion(200, 1, 2, 3, 0.5, 2, 4, 12345)
-    e.fix_ex_load(100, 1, 1, 1.12, 2, 0.02, 684474, (1, 1), (1, 1))
-    e.fix_ex_unload(100, 2, 0.5, 0.05, 456456)
+    if mc:
+        e.fix_bond_create(10, 1, 1, 1.05, 2, 0.5, 684474, (2, 4), (2, 4))
+        e.fix_bond_break(10, 2, 1.25, 0.5, 456456)
+    else:
+        e.fix_extrusion(200, 1, 2, 3, 0.5, 2, 4, 12345)
+        e.fix_ex_load(100, 1, 1, 1.12, 2, 0.02, 684474, (1, 1), (1, 1))
+        e.fix_ex_unload(100, 2, 0.5, 0.05, 456456)
     e.reset_timestep(0)
-le_steps = 650
+le_steps = 120 if mc else 650
 dd.run(le_steps)
 st = dd.stats(); topo = dd.topology(); ty = dd.types(); x, im = dd.positions()
 if rank == 0:
     ref.run(le_steps)
     st2 = ref.stats(); topo2 = ref.topology(); ty2 = ref.types(); x2, im2 = ref.positions()
     res = H.compare_topology(topo, topo2)
-    report("USER-LE topology after %d steps" % le_steps, not any(res.values()) and (ty == ty2).all(),
+    if mc:
+        report("bonds were created and broken", st2["loads"] > 50 and st2["unloads"] > 5, "%d / %d" % (st2["loads"], st2["unloads"]))
+    report("%s topology after %d steps" % ("bond/create + bond/break" if mc else "USER-LE", le_steps), not any(res.values()) and (ty == ty2).all(),
            "shifts %d/%d loads %d/%d unloads %d/%d %s" % (st["extrusion_shifts"], st2["extrusion_shifts"], st["loads"], st2["loads"],
                                                         st["unloads"], st2["unloads"], {k: v for k, v in res.items() if v}))
     L = s["box"][1][0]

@@ -47,6 +47,14 @@ def test_dd_melt_matches_single_gpu():
 
 
 @pytest.mark.gpu
+def test_dd_bond_create_and_break_match_single_gpu():
+    """fix bond/create + fix bond/break (src/MC, the ancestors of ex_load / ex_unload) on two slabs: the owner of an atom measures its
+    closest eligible neighbor (ghosts included), every GPU decides from the same records -- topology, types and counters equal the
+    single-GPU run"""
+    _run_dd(2, 29715, [40000, 100, "mc"])
+
+
+@pytest.mark.gpu
 def test_dynamic_rebalance_keeps_the_trajectory():
     """`fix balance` (src/fix_balance.cpp:191-270): equal-width slabs over a chain that crowds one part of the box, re-cut by atom
     count in the middle of the run; trajectory and USER-LE topology equal the single-GPU run (scripts/dd_balance_check.py)"""

@@ -234,6 +234,58 @@ def test_fix_bond_break_matches_the_reference():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("through", ["abi", "le_deck"])
+def test_fix_bond_create_matches_the_reference(through, tmp_path):
+    """fix bond/create (src/MC/fix_bond_create.cpp, the ancestor of fix ex_load: the closest eligible listed neighbor within Rmin, no
+    loop-extrusion rules, events on multiples of N): bond counts and the fix's counters after every event equal a run of the compiled
+    reference from the same state.  `abi`: prob 0.5 (the Marsaglia stream), two bonds per bead, then the bead changes type;
+    `le_deck`: the reference's own input lines through the C++ front end, every pair within reach bonds (fraction 1)."""
+    import os
+    import re
+    import subprocess
+    from oracle import refio
+    from lammps_le_b200 import systems
+    if not refio.have_reference():
+        pytest.skip("oracle/_ref not present on this box")
+    n = 3000
+    s = systems.chromatin_chain(n, 90, rho=0.2, seed=21, barriers="random", extruder_bond=systems.EXTRUDER_FENE)
+    v = systems.maxwell_velocities(n, 1.0, np.ones(n), 5)
+    e = systems.make_engine(s, velocities=v, dt=0.005)
+    x, im = e.positions()                                   # the engine's grid-snapped start, handed to the reference
+    s2 = dict(s); s2["x"], s2["image"], s2["v"] = x, im, v
+    wd = str(tmp_path)
+    refio.write_data_file(os.path.join(wd, "data.le"), s2)
+    fixline = ("fix cr all bond/create 10 1 1 1.05 2 prob 0.5 456456 iparam 2 4 jparam 2 4" if through == "abi"
+               else "fix cr all bond/create 5 1 1 1.0 2")
+    deck = refio.deck_header(s2, "data.le", sort=False) + ["fix 1 all nve", fixline, "timestep 0.005",
+                                                          "thermo_style custom step bonds f_cr[1] f_cr[2]", "thermo 10", "run 40"]
+    out, _ = refio.run_reference(deck, workdir=wd, harness=False)
+    table = lambda o: np.array([[float(q) for q in r.split()] for r in re.search(r"Step Bonds f_cr\[1\] f_cr\[2\] \n(.*?)\nLoop time", o, re.S).group(1).splitlines()])
+    ref = table(out)
+    if through == "abi":
+        e.fix_nve(True)
+        e.fix_bond_create(10, 1, 1, 1.05, 2, 0.5, 456456, (2, 4), (2, 4))
+        e.thermo_every(10)
+        e.run(40)
+        got = np.array([[t["step"], t["nbonds"], t["le_f1"][2], t["le_f2"][2]] for t in e.thermo()], dtype=float)
+        types = e.types() if hasattr(e, "types") else None
+        e.close()
+        if types is not None:
+            assert (types == 4).sum() > (s["types"] == 4).sum(), "beads with two created bonds must have changed type"
+    else:
+        e.close()
+        with open(os.path.join(wd, "in.create"), "w") as f:
+            f.write("\n".join(deck) + "\n")
+        r = subprocess.run([os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lammps_le_b200", "le_deck"), "-in", "in.create"],
+                           cwd=wd, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        got = table(r.stdout)
+    assert ref.shape == got.shape == (5, 4), (ref, got)
+    assert ref[-1, 3] > 100, "the run must create bonds"
+    assert np.array_equal(ref, got), (ref, got)
+
+
+@pytest.mark.gpu
 def test_langevin_ramp_spans_the_segments_of_one_run():
     """a run cut into segments (le_deck does that at dump steps) must not restart fix langevin's Tstart -> Tstop
     ramp in every segment: le_set_run_span (`run N start S stop E`, src/run.cpp:90-120).  With the span the segmented run stays
