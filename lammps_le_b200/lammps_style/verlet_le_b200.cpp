@@ -16,6 +16,10 @@
 #include "fix_extrusion.h"
 #include "fix_ex_load.h"
 #include "fix_ex_unload.h"
+#ifdef LE_B200_WITH_MC          // the MC package is installed: the ancestors of ex_load / ex_unload run on the engine too
+#include "fix_bond_create.h"
+#include "fix_bond_break.h"
+#endif
 #include "random_mars.h"
 #undef private
 #undef protected
@@ -127,7 +131,7 @@ void VerletLEB200::create_context()
 
   // fixes, in the order Modify calls them (the USER-LE fixes do nothing under newton_bond on, SURVEY.md section 0: the
   // engine refuses that combination with its own message)
-  has_le = 0; fix_ext = fix_load = fix_unload = nullptr;
+  has_le = 0; fix_ext = fix_load = fix_unload = nullptr; load_is_mc = unload_is_mc = 0;
   for (int i = 0; i < modify->nfix; i++) {
     Fix *f = modify->fix[i];
     if (strcmp(f->style, "nve") == 0) check(le_fix_nve(ctx, 1));
@@ -150,8 +154,38 @@ void VerletLEB200::create_context()
       FixExUnload *x = (FixExUnload *) f;
       check(le_fix_ex_unload(ctx, x->nevery, x->btype, sqrt(x->cutsq), x->fraction, 12345));
       has_le = 1; fix_unload = f;
+#ifdef LE_B200_WITH_MC
+    } else if (strcmp(f->style, "bond/create") == 0) {     // takes the engine's ex_load slot
+      FixBondCreate *x = (FixBondCreate *) f;
+      if (fix_load) error->all(FLERR, "run_style le/b200: one of fix ex_load / fix bond/create per run");
+      if (x->atype || x->dtype || x->itype || x->constrainflag) error->all(FLERR, "run_style le/b200: fix bond/create without atype / dtype / itype / aconstrain");
+      check(le_fix_bond_create(ctx, x->nevery, x->iatomtype, x->jatomtype, sqrt(x->cutsq), x->btype, x->fraction, 12345,
+                               x->imaxbond, x->inewtype, x->jmaxbond, x->jnewtype));
+      has_le = 1; fix_load = f; load_is_mc = 1;
+    } else if (strcmp(f->style, "bond/break") == 0) {      // takes the engine's ex_unload slot
+      FixBondBreak *x = (FixBondBreak *) f;
+      if (fix_unload) error->all(FLERR, "run_style le/b200: one of fix ex_unload / fix bond/break per run");
+      check(le_fix_bond_break(ctx, x->nevery, x->btype, sqrt(x->cutsq), x->fraction, 12345));
+      has_le = 1; fix_unload = f; unload_is_mc = 1;
+#endif
     } else error->all(FLERR, "run_style le/b200 does not support this fix style");
   }
+}
+
+// the Marsaglia generator / the counters of whichever fix sits in the ex_load and ex_unload slots
+RanMars *VerletLEB200::load_rng()
+{
+#ifdef LE_B200_WITH_MC
+  if (load_is_mc) return ((FixBondCreate *) fix_load)->random;
+#endif
+  return ((FixExLoad *) fix_load)->random;
+}
+RanMars *VerletLEB200::unload_rng()
+{
+#ifdef LE_B200_WITH_MC
+  if (unload_is_mc) return ((FixBondBreak *) fix_unload)->random;
+#endif
+  return ((FixExUnload *) fix_unload)->random;
 }
 
 void VerletLEB200::push_state()
@@ -206,8 +240,8 @@ void VerletLEB200::push_state()
   // the seed in a local variable, fix_ex_unload.cpp:66, so the state is the only complete record) and come back in pull_state
   double st[103];
   if (fix_ext) { ((FixExtrusion *) fix_ext)->random->get_state(st); check(le_fix_rng_set_state(ctx, LE_FIX_EXTRUSION, st)); }
-  if (fix_unload) { ((FixExUnload *) fix_unload)->random->get_state(st); check(le_fix_rng_set_state(ctx, LE_FIX_EX_UNLOAD, st)); }
-  if (fix_load) { ((FixExLoad *) fix_load)->random->get_state(st); check(le_fix_rng_set_state(ctx, LE_FIX_EX_LOAD, st)); }
+  if (fix_unload) { unload_rng()->get_state(st); check(le_fix_rng_set_state(ctx, LE_FIX_EX_UNLOAD, st)); }
+  if (fix_load) { load_rng()->get_state(st); check(le_fix_rng_set_state(ctx, LE_FIX_EX_LOAD, st)); }
 }
 
 void VerletLEB200::pull_state(int forces)
@@ -238,8 +272,8 @@ void VerletLEB200::pull_state(int forces)
   }
   double st[103];
   if (fix_ext) { check(le_fix_rng_get_state(ctx, LE_FIX_EXTRUSION, st)); ((FixExtrusion *) fix_ext)->random->set_state(st); }
-  if (fix_unload) { check(le_fix_rng_get_state(ctx, LE_FIX_EX_UNLOAD, st)); ((FixExUnload *) fix_unload)->random->set_state(st); }
-  if (fix_load) { check(le_fix_rng_get_state(ctx, LE_FIX_EX_LOAD, st)); ((FixExLoad *) fix_load)->random->set_state(st); }
+  if (fix_unload) { check(le_fix_rng_get_state(ctx, LE_FIX_EX_UNLOAD, st)); unload_rng()->set_state(st); }
+  if (fix_load) { check(le_fix_rng_get_state(ctx, LE_FIX_EX_LOAD, st)); load_rng()->set_state(st); }
   (void) forces;
 }
 
@@ -255,8 +289,12 @@ void VerletLEB200::publish_thermo(const le_thermo &t)
   atom->nbonds = t.nbonds;
   update->eflag_global = update->vflag_global = update->ntimestep;
   if (fix_ext) { ((FixExtrusion *) fix_ext)->breakcount = (int) t.le_f1[0]; ((FixExtrusion *) fix_ext)->breakcounttotal = (int) t.le_f2[0]; }
-  if (fix_unload) { ((FixExUnload *) fix_unload)->breakcount = (int) t.le_f1[1]; ((FixExUnload *) fix_unload)->breakcounttotal = (int) t.le_f2[1]; }
-  if (fix_load) { ((FixExLoad *) fix_load)->createcount = (int) t.le_f1[2]; ((FixExLoad *) fix_load)->createcounttotal = (int) t.le_f2[2]; }
+#ifdef LE_B200_WITH_MC
+  if (fix_unload && unload_is_mc) { ((FixBondBreak *) fix_unload)->breakcount = (int) t.le_f1[1]; ((FixBondBreak *) fix_unload)->breakcounttotal = (int) t.le_f2[1]; }
+  if (fix_load && load_is_mc) { ((FixBondCreate *) fix_load)->createcount = (int) t.le_f1[2]; ((FixBondCreate *) fix_load)->createcounttotal = (int) t.le_f2[2]; }
+#endif
+  if (fix_unload && !unload_is_mc) { ((FixExUnload *) fix_unload)->breakcount = (int) t.le_f1[1]; ((FixExUnload *) fix_unload)->breakcounttotal = (int) t.le_f2[1]; }
+  if (fix_load && !load_is_mc) { ((FixExLoad *) fix_load)->createcount = (int) t.le_f1[2]; ((FixExLoad *) fix_load)->createcounttotal = (int) t.le_f2[2]; }
 }
 
 void VerletLEB200::setup(int flag)

@@ -34,6 +34,9 @@ class VerletLEB200 : public Integrate {
   int device;
   int has_le;                      // a USER-LE fix is defined: bonds, specials and types come back after every segment
   class Fix *fix_ext, *fix_load, *fix_unload;
+  int load_is_mc, unload_is_mc;      // the slot holds fix bond/create / fix bond/break (MC package) instead of the USER-LE fix
+  class RanMars *load_rng();
+  class RanMars *unload_rng();
 
   void check(int rc);
   void create_context();           // Force / Modify / Neighbor settings -> le_set_* / le_fix_*

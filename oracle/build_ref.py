@@ -234,7 +234,7 @@ def build_b200():
     srcs = [(os.path.join(REF, "src/update.cpp"), os.path.join(out, "update.o")), (os.path.join(REF, "src/lammps.cpp"), os.path.join(out, "lammps.o")), (os.path.join(style_dir, "verlet_le_b200.cpp"), os.path.join(out, "verlet_le_b200.o"))]
     for src, obj in srcs:
         if not up_to_date(obj, [src, os.path.join(style_dir, "verlet_le_b200.h"), os.path.join(root, "include", "le_b200.h")] + gen_files):
-            subprocess.check_call(["g++"] + CXXFLAGS + inc + ["-c", src, "-o", obj])
+            subprocess.check_call(["g++"] + CXXFLAGS + ["-DLE_B200_WITH_MC"] + inc + ["-c", src, "-o", obj])
     objs = [os.path.join(OBJ, o) for o in sorted(os.listdir(OBJ)) if o.endswith(".o") and o not in ("update.o", "lammps.o")] + [o for _, o in srcs]
     if not up_to_date(exe, objs + [lib]):
         subprocess.check_call(["g++"] + CXXFLAGS + inc + [os.path.join(REF, "src/main.cpp")] + objs + ["-o", exe, "-L" + os.path.dirname(lib), "-lleb200",

@@ -131,3 +131,28 @@ run 30
     assert a.shape == b.shape == (4, 6) and a[0, 4] > 0.05
     rel = np.abs(a[:, 1:] - b[:, 1:]) / np.maximum(np.abs(a[:, 1:]), 1e-3)
     assert rel[0].max() < 2e-6 and rel.max() < 5e-5, (a, b)
+
+
+def test_mc_fixes_through_the_binding_match_run_style_verlet(tmp_path):
+    """fix bond/create + fix bond/break (src/MC, the ancestors of ex_load / ex_unload) in a deck the reference's Input::file parses:
+    `run_style le/b200` against stock `run_style verlet` of the SAME binary -- Thermo's `bonds` and the four f_ID[k] columns row for row
+    (NVE, grid-snapped start: both integrate the same doubles)"""
+    need_exe()
+    from lammps_le_b200 import systems
+    from oracle import refio
+    n = 3000
+    s = systems.chromatin_chain(n, 90, rho=0.2, seed=21, barriers="random", extruder_bond=systems.EXTRUDER_FENE)
+    v = systems.maxwell_velocities(n, 1.0, np.ones(n), 5)
+    e = systems.make_engine(s, velocities=v, dt=0.005)
+    x, im = e.positions()
+    e.close()
+    s2 = dict(s); s2["x"], s2["image"], s2["v"] = x, im, v
+    refio.write_data_file(str(tmp_path / "data.le"), s2)
+    base = "\n".join(refio.deck_header(s2, "data.le", sort=False) + [
+        "fix 1 all nve", "fix cr all bond/create 10 1 1 1.05 2 prob 0.5 684474 iparam 2 4 jparam 2 4", "fix br all bond/break 10 2 1.2 prob 0.5 456456",
+        "timestep 0.005", "%s", "thermo_style custom step bonds f_cr[1] f_cr[2] f_br[1] f_br[2]", "thermo 10", "run 40"]) + "\n"
+    a = thermo_rows(run_lmp(base % "", tmp_path))[-1][1]
+    b = thermo_rows(run_lmp(base % "run_style le/b200", tmp_path))[-1][1]
+    assert a.shape == b.shape == (5, 6), (a, b)
+    assert a[-1, 3] > 100 and a[-1, 5] > 5, "the run must create and break bonds"
+    assert np.array_equal(a, b), (a, b)
