@@ -755,6 +755,8 @@ void execute_cmd(Deck &d, const Words &w) {
     for (int t = a; t <= b; t++) d.angle_k[t] = num(w[2]);
   }
   else if (c == "atom_modify" || c == "comm_modify" || c == "log" || c == "echo" || c == "thermo_modify" || c == "processors") {}
+  else if (c == "balance" || c == "comm_style") {}       // one process, one GPU: nothing to cut (the slab engine re-cuts through DDEngine.rebalance, DESIGN 6b;
+                                                         // `fix balance` is NOT accepted: even on one process it forces a reneighboring every N steps, src/fix_balance.cpp:236)
   else if (c == "thermo_style") thermo_style(d, w);
   else if (c == "print") { for (size_t k = 1; k < w.size(); k++) std::printf("%s%s", w[k].c_str(), k + 1 < w.size() ? " " : "\n"); }
   else if (c == "newton") {
