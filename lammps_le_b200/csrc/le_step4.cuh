@@ -7,7 +7,8 @@
 // constants under a 64-register cap) and 165 in the bonds.
 //   * parked terms as {x,y} + {z}: two shared loads per term instead of three; the owner adds its first four terms
 //     with predicated straight-line code (a bead of a dilute chain has 2.2 listed neighbors), a loop only beyond that;
-//   * 128-thread blocks: the register budget can sit between the 64 / 80 steps of 256-thread blocks;
+//   * 128-thread blocks: the register budget can sit between the 64 / 80 steps of 256-thread blocks; the velocity is fetched
+//     after the forces (only its aux word is needed before), which brings the UNI kernel to 64 registers: 8 resident blocks;
 //   * the third bond slot and the third/fourth list round are fetched only by warps that have them;
 //   * the step's path length for the displacement bound is the 1-norm of the step (>= the 2-norm: still an upper
 //     bound of the displacement), no square root.
@@ -27,7 +28,7 @@ struct __align__(16) Step4Smem {
 };
 
 template <int EV, int DD, int UNI>
-__global__ void __launch_bounds__(STEP4_THREADS, EV ? 4 : (DD ? 6 : 7)) k_step4(Dev d, StepArgs a) {   // (the slab form needs 80 registers to stay free of spills)
+__global__ void __launch_bounds__(STEP4_THREADS, EV ? 4 : (DD ? 6 : (UNI ? 8 : 7))) k_step4(Dev d, StepArgs a) {   // (one coefficient set: 64 registers without spills -> 8 blocks/SM; the slab form needs 80)
   __shared__ Step4Smem s_all[STEP4_WARPS];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Step4Smem &S = s_all[wib];
@@ -57,13 +58,12 @@ __global__ void __launch_bounds__(STEP4_THREADS, EV ? 4 : (DD ? 6 : 7)) k_step4(
     const int i = valid ? i0 + lane : own_end - 1;            // lanes beyond the end shadow the last atom (loads only)
     // ---- level 1: everything addressed by the tile / the atom ----
     const int4 pi = posr[i];
-    float4 vi = d.vel[i];
+    const unsigned aux = __float_as_uint(d.vel[i].w);          // counts + displacement bound now; the velocity itself is fetched after the forces (3 registers less across the tile)
     const unsigned cnt = __ldg(&d.tile_cnt[tile]);
     const unsigned *__restrict__ run = d.nbr + (size_t)tile * tcap;
     const unsigned e0 = __ldg(&run[lane]), e1 = __ldg(&run[TILE + lane]);   // tcap >= 128
     const unsigned eb0 = __ldg(&bondrow[i]);
     const unsigned eb1 = d.bpa > 1 ? __ldg(&bondrow[(size_t)cap + i]) : 0u;
-    const unsigned aux = __float_as_uint(vi.w);
     const int nn = valid ? (int)AUX_NN(aux) : 0, nb = valid ? (int)AUX_NB(aux) : 0;
     const int ti = pi.w & 7, tag = pi.w >> 3;
     S.pos[lane] = pi;
@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(STEP4_THREADS, EV ? 4 : (DD ? 6 : 7)) k_step4(
       bond3<EV>(fx, fy, fz, ctrl, pi, __ldg(&posr[e & BOND_IDX_MASK]), e, tag, A);
     }
     if (!valid) continue;                                      // (no warp-level operation below this line)
+    float4 vi = d.vel[i];
     if (a.angles) { fx += d.fang[3 * (size_t)i]; fy += d.fang[3 * (size_t)i + 1]; fz += d.fang[3 * (size_t)i + 2]; }   // angle_style cosine (le_angle.cuh)
 
     if (a.write_force) {
