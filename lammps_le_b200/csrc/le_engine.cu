@@ -1177,7 +1177,7 @@ static StepKernel step_kernel(const le_ctx *c, bool ev) {
     if (dd) return uni ? StepKernel{(step_fn_t)k_step4<1, 1, 1>, STEP4_THREADS, "(k_step4<1,1,1>)", 4} : StepKernel{(step_fn_t)k_step4<1, 1, 0>, STEP4_THREADS, "(k_step4<1,1,0>)", 4};
     return uni ? StepKernel{(step_fn_t)k_step4<1, 0, 1>, STEP4_THREADS, "(k_step4<1,0,1>)", 4} : StepKernel{(step_fn_t)k_step4<1, 0, 0>, STEP4_THREADS, "(k_step4<1,0,0>)", 4};
   }
-  if (dd) return uni ? StepKernel{(step_fn_t)k_step4<0, 1, 1>, STEP4_THREADS, "(k_step4<0,1,1>)", 6} : StepKernel{(step_fn_t)k_step4<0, 1, 0>, STEP4_THREADS, "(k_step4<0,1,0>)", 6};
+  if (dd) return uni ? StepKernel{(step_fn_t)k_step4<0, 1, 1>, STEP4_THREADS, "(k_step4<0,1,1>)", 7} : StepKernel{(step_fn_t)k_step4<0, 1, 0>, STEP4_THREADS, "(k_step4<0,1,0>)", 6};
   const char *wb = getenv("LE_STEP_WAVE");     // (A/B: resident blocks per SM of the plain kernel's persistent grid)
   return uni ? StepKernel{(step_fn_t)k_step4<0, 0, 1>, STEP4_THREADS, "(k_step4<0,0,1>)", wb ? atoi(wb) : 8} : StepKernel{(step_fn_t)k_step4<0, 0, 0>, STEP4_THREADS, "(k_step4<0,0,0>)", 7};
 }

@@ -28,7 +28,7 @@ struct __align__(16) Step4Smem {
 };
 
 template <int EV, int DD, int UNI>
-__global__ void __launch_bounds__(STEP4_THREADS, EV ? 4 : (DD ? 6 : (UNI ? 8 : 7))) k_step4(Dev d, StepArgs a) {   // (one coefficient set: 64 registers without spills -> 8 blocks/SM; the slab form needs 80)
+__global__ void __launch_bounds__(STEP4_THREADS, EV ? 4 : (DD ? (UNI ? 7 : 6) : (UNI ? 8 : 7))) k_step4(Dev d, StepArgs a) {   // (one coefficient set: 64 registers without spills -> 8 blocks/SM; its slab form 71 -> 7)
   __shared__ Step4Smem s_all[STEP4_WARPS];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   Step4Smem &S = s_all[wib];
@@ -42,9 +42,14 @@ __global__ void __launch_bounds__(STEP4_THREADS, EV ? 4 : (DD ? 6 : (UNI ? 8 : 7
   const int nt = c_P.ntypes;
   const int tcap = d.tcap;
   const long long step = ctrl->step;
-  Step3Order ord;
+  __shared__ Step3Order s_ord;                                   // (shared memory: five registers less across the tile loop of the slab form)
   int ntiles = (own_end - d.own0 + TILE - 1) >> 5;
-  if (DD) { ord = step3_order(d, own_end); ntiles = ord.total; }
+  if (DD) {
+    if (threadIdx.x == 0) s_ord = step3_order(d, own_end);
+    __syncthreads();
+    ntiles = s_ord.total;
+  }
+  const Step3Order &ord = s_ord;
 
   EvAcc A;
   double ke = 0.0;
