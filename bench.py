@@ -106,7 +106,7 @@ REF_LE_LINES = ["fix loop all extrusion 500 1 2 3 0.5 2 4",
 # capture (profiles/r02_ncu_full_kstep4_kbuild3.txt): an OFFLINE figure of this kernel on this workload (ncu cannot run inside
 # the bench; it replays every launch with a flushed L2, so this is cold-cache traffic).  Printed only for the configuration
 # it was captured on (1 GPU, 1M beads, this kernel), null otherwise.
-NCU_TRAFFIC = {"kernel": "k_step4<0,0,1>", "bytes": 55.3e6, "source": "profiles/r02_ncu_full_kstep4_kbuild3.txt"}
+NCU_TRAFFIC = {"kernel": "k_step4<0,0,1>", "bytes": 55.9e6, "source": "profiles/r02_ncu_full_kstep4_8blocks.txt"}
 LE_HALO = 6.0   # ghost shell for USER-LE on several GPUs: longest extruder bond (FENE R0 = 4) + one backbone bond (1.5) + skin (4 cell layers here)
 
 
