@@ -300,7 +300,7 @@ extern "C" int le_run_le_event(le_ctx *c, int which) {
   if (!c->lists_valid) return fail(c, LE_ESTATE, "no neighbor/bond lists: call le_force_rebuild or le_run first");
   if (which == LE_FIX_EXTRUSION) { if (!c->fx.on) return fail(c, LE_ESTATE, "fix extrusion not defined"); r = enqueue_extrusion(c); }
   else if (which == LE_FIX_EX_UNLOAD) { if (!c->fu.on) return fail(c, LE_ESTATE, "fix ex_unload not defined"); r = enqueue_unload(c); }
-  else if (which == LE_FIX_EX_LOAD) { if (!c->fl.on) return fail(c, LE_ESTATE, "fix ex_load not defined"); r = enqueue_load(c); }
+  else if (which == LE_FIX_EX_LOAD) { if (!c->fl.on) return fail(c, LE_ESTATE, "fix ex_load not defined"); enqueue_bond_create_setup(c); r = enqueue_load(c); }
   else return fail(c, LE_EINVAL, "unknown fix");
   if (r) return r;
   return sync_and_check(c);

@@ -38,6 +38,7 @@
 #include "fix_ex_load.h"
 #include "fix_ex_unload.h"
 #include "fix_extrusion.h"
+#include "fix_bond_create.h"      // src/MC: the ancestor of fix ex_load (compiled in by oracle/build_ref.py, EXTRA_STYLES)
 #include "force.h"
 #include "input.h"
 #include "lammps.h"
@@ -75,13 +76,14 @@ Fix *find_fix(LAMMPS *lmp, const char *style) {
 
 int rng_c(RanMars *r) { return r ? (int)llround(r->c * 16777216.0) : -1; }
 
-// which USER-LE fix fires on this timestep (0 none, 1 extrusion, 2 unload, 3 load)
+// which USER-LE fix fires on this timestep (0 none, 1 extrusion, 2 unload, 3 load / fix bond/create)
 int firing(LAMMPS *lmp) {
   const bigint n = lmp->update->ntimestep;
   int which = 0, count = 0;
   if (Fix *f = find_fix(lmp, "extrusion")) if (n % f->nevery - 1 == 0) { which = 1; count++; }
   if (Fix *f = find_fix(lmp, "ex_unload")) if (n % f->nevery - 2 == 0) { which = 2; count++; }
   if (Fix *f = find_fix(lmp, "ex_load")) if (n % f->nevery - 3 == 0) { which = 3; count++; }
+  if (Fix *f = find_fix(lmp, "bond/create")) if (n % f->nevery == 0) { which = 3; count++; }   // (records as fix 3: it is ex_load's ancestor)
   if (count > 1) lmp->error->all(FLERR, "le/snap: two USER-LE fixes fire on the same step; choose other periods");
   return which;
 }
@@ -100,10 +102,11 @@ void write_record(LAMMPS *lmp, FILE *fp, int kind, int which, bool lists, bool f
   FixExLoad *fl = (FixExLoad *)find_fix(lmp, "ex_load");
   h.rngc[0] = fe ? rng_c(fe->random) : -1;
   h.rngc[1] = fu ? rng_c(fu->random) : -1;
-  h.rngc[2] = fl ? rng_c(fl->random) : -1;
+  FixBondCreate *fc = (FixBondCreate *)find_fix(lmp, "bond/create");
+  h.rngc[2] = fl ? rng_c(fl->random) : fc ? rng_c(fc->random) : -1;
   h.counters[0] = fe ? fe->breakcount : 0;
   h.counters[1] = fu ? fu->breakcount : 0;
-  h.counters[2] = fl ? fl->createcount : 0;
+  h.counters[2] = fl ? fl->createcount : fc ? fc->createcount : 0;
   h.counters[3] = (int)atom->nbonds;
   h.has_force = forces ? 1 : 0;
   if (forces) {

@@ -698,13 +698,18 @@ def fix_ex_unload(S, rng, btype, rc, fraction, bondlist=None):
 # ------------------------------------------------------------------------------------------------------------
 # fix ex_load -- FixExLoad::post_integrate src/USER-LE/fix_ex_load.cpp:329-655
 # ------------------------------------------------------------------------------------------------------------
-def fix_ex_load(S, rng, itype, jtype, rc, btype, fraction, imax, inew, jmax, jnew, neigh_offsets, neigh_entries):
+def fix_ex_load(S, rng, itype, jtype, rc, btype, fraction, imax, inew, jmax, jnew, neigh_offsets, neigh_entries, ancestor=False, bc=None):
     """neigh_*: the half pair list of the last rebuild in the reference's order (CSR, tag order, entries =
-    partner tag | special bits)"""
+    partner tag | special bits).
+    ancestor=True: fix bond/create (src/MC/fix_bond_create.cpp:349-629), the fix ex_load was derived from -- the same loops
+    without the loop-extrusion rules of fix_ex_load.cpp:470-484 (so a periodic ghost can be a partner: its coordinate is the
+    owned atom's plus the shift of the image found at the last rebuild), with `bc`, the bond counts the fix took in the setup
+    of its first run (fix_bond_create.cpp:302-345) and has only added its own creations to since (:576), updated in place"""
     n = len(S["num_bond"])
     x, L, typ, nb = S["x"], S["L"], S["type"], S["num_bond"]
     cutsq = rc * rc
-    bc = _bondcount(S, btype, False)
+    if bc is None:
+        bc = _bondcount(S, btype, False)
     partner = np.zeros(n + 2, int); distsq = np.full(n + 2, BIG)
     for i in range(n):
         it = typ[i]
@@ -720,20 +725,21 @@ def fix_ex_load(S, rng, itype, jtype, rc, btype, fraction, imax, inew, jmax, jne
                 possible = (jmax == 0 or bc[i] < jmax) and (imax == 0 or bc[j] < imax)
             if not possible:
                 continue
-            if abs(i - j) != 2:
-                continue
-            mid = (i + j) // 2
-            if partner[mid] != 0:
-                continue
-            if nb[i] != 2:
-                continue
-            if ghost or nb[j] != 2:       # a ghost's num_bond is never communicated and reads 0 (atom_vec_bond.cpp:41)
-                continue
-            if nb[mid] != 2:
-                continue
+            if not ancestor:
+                if abs(i - j) != 2:
+                    continue
+                mid = (i + j) // 2
+                if partner[mid] != 0:
+                    continue
+                if nb[i] != 2:
+                    continue
+                if ghost or nb[j] != 2:       # a ghost's num_bond is never communicated and reads 0 (atom_vec_bond.cpp:41)
+                    continue
+                if nb[mid] != 2:
+                    continue
             if (S["special"][i, :S["nspecial"][i, 0]] == j + 1).any():
                 continue
-            d = x[i] - x[j]
+            d = x[i] - (x[j] + s * L if (ancestor and ghost) else x[j])
             rsq = d[0] * d[0] + d[1] * d[1] + d[2] * d[2]
             if rsq >= cutsq:
                 continue
@@ -759,7 +765,7 @@ def fix_ex_load(S, rng, itype, jtype, rc, btype, fraction, imax, inew, jmax, jne
             if (prob[i] if i < j else prob[j]) >= fraction:
                 continue
         if nb[i] == bpa:
-            raise RuntimeError("New bond exceeded bonds per atom in fix ex_load")
+            raise RuntimeError("New bond exceeded bonds per atom in fix %s" % ("bond/create" if ancestor else "ex_load"))
         S["bond_type"][i, nb[i]] = btype
         S["bond_atom"][i, nb[i]] = j + 1
         nb[i] += 1

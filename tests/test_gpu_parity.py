@@ -142,6 +142,36 @@ def test_le_replay_live_reference_barrier_variants(name):
     assert not problems, "USER-LE replay mismatches: %s" % problems[:5]
 
 
+def test_bond_create_replay_live_reference():
+    """fix bond/create event by event: every recorded event of a run of the compiled reference replayed from its pre-state on the
+    GPU -- bond rows, special lists, types, created-bond counter and Marsaglia draws equal the reference's post-state (the same
+    trace pins the restatement on the CPU, tests/test_oracle.py)"""
+    _need_ref()
+    from oracle import refio
+    from lammps_le_b200.engine import LE_FIX_EX_LOAD
+    from tests.test_oracle import BOND_CREATE_CFG as cfg, bond_create_trace
+    pre, post = bond_create_trace()
+    problems, created = [], 0
+    for a, b in zip(pre, post):
+        e = H.engine_from_record(a, CHROMATIN_BONDS, positions="xhold")
+        e.fix_bond_create(cfg["nevery"], cfg["itype"], cfg["jtype"], cfg["rc"], cfg["btype"], cfg["prob"], cfg["seed"], cfg["iparam"], cfg["jparam"])
+        e.force_rebuild()
+        e.set_positions(a["x"], a["image"])
+        e.fix_rng_reset(LE_FIX_EX_LOAD, cfg["seed"], refio.draws_consumed(a["rngc"][2]))
+        e.run_le_event(LE_FIX_EX_LOAD)        # (bond counts = those of the pre-state: the trace holds no other fix that changes bonds)
+        res = H.compare_topology(e.topology(), b)
+        res["type"] = int((e.types() != b["type"]).sum())
+        res["draws"] = int(e.fix_rng_consumed(LE_FIX_EX_LOAD) != refio.draws_consumed(b["rngc"][2]))
+        res["counter"] = int(e.stats()["last_loads"] != b["counters"][2])
+        created += b["counters"][2]
+        hard = {k: v for k, v in res.items() if k != "special_exact" and v}
+        if hard:
+            problems.append((a["step"], hard))
+        e.close()
+    assert created > 40
+    assert not problems, "fix bond/create replay mismatches: %s" % problems[:5]
+
+
 def test_forces_live_reference_chain_and_melt():
     _need_ref()
     from lammps_le_b200 import systems
