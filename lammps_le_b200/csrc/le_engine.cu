@@ -9,8 +9,6 @@
 #include "le_md.cuh"
 #include "le_sort.cuh"
 #include "le_build3.cuh"
-#include "le_build4.cuh"
-#include "le_build5.cuh"
 #include "le_build6.cuh"
 #include "le_step3.cuh"
 #include "le_step4.cuh"
@@ -77,7 +75,7 @@ struct le_ctx {
   bool atoms_loaded, topo_loaded, lists_valid, params_dirty;
   int scan_items;       // cells per thread of k_scan_cells
   bool topo_dirty;      // the tag-ordered topology tables changed since the last k_topo_pack
-  int build_variant;    // 3 = k_build3 (default), 6 = k_build6, 5 = k_build5, 4 = k_build4 (LE_BUILD_VARIANT, A/B measurements)
+  int build_variant;    // 3 = k_build3 (default), 6 = k_build6 (LE_BUILD_VARIANT: the second implementation the tests compare the default with)
   int ell_rows;         // rows of Dev::nbr_ell
   int step_variant;     // 4 = k_step4 (default), 3 = k_step3 (LE_STEP_VARIANT, A/B measurements)
   Dev d;
@@ -1232,14 +1230,6 @@ static void enqueue_rebuild(le_ctx *c, bool direct) {
     const bool uni = c->P.pair_uniform != 0;
     if (build_queue_depth(c) > 16) { if (uni) LAUNCH(c, (k_build6<40, 4, 1>), g, B6_THREADS, d, c->ell_rows); else LAUNCH(c, (k_build6<40, 4, 0>), g, B6_THREADS, d, c->ell_rows); }
     else { if (uni) LAUNCH(c, (k_build6<16, 8, 1>), g, B6_THREADS, d, c->ell_rows); else LAUNCH(c, (k_build6<16, 8, 0>), g, B6_THREADS, d, c->ell_rows); }
-  } else if (c->build_variant == 5) {
-    const int g = grid_for(nslots, BUILD_THREADS);
-    const bool uni = c->P.pair_uniform != 0;
-    if (build_queue_depth(c) > 16) { if (uni) LAUNCH(c, (k_build5<36, 4, 1>), g, BUILD_THREADS, d); else LAUNCH(c, (k_build5<36, 4, 0>), g, BUILD_THREADS, d); }
-    else { if (uni) LAUNCH(c, (k_build5<16, 8, 1>), g, BUILD_THREADS, d); else LAUNCH(c, (k_build5<16, 8, 0>), g, BUILD_THREADS, d); }
-  } else if (c->build_variant == 4) {
-    const int g = grid_for(nslots, B4_THREADS);
-    if (c->P.pair_uniform) LAUNCH(c, k_build4<1>, g, B4_THREADS, d); else LAUNCH(c, k_build4<0>, g, B4_THREADS, d);
   } else {
     const int g = grid_for(nslots, BUILD_THREADS);
     const bool uni = c->P.pair_uniform != 0;
