@@ -96,6 +96,30 @@ def unpack_trace(npz):
     return pre, post
 
 
+BOND_CREATE_CFG = dict(nevery=20, itype=1, jtype=1, rc=1.05, btype=2, prob=0.5, seed=456456, iparam=(2, 4), jparam=(2, 4))
+
+
+def bond_create_trace(nbeads=1200, steps=200, cfg=BOND_CREATE_CFG):
+    """a run of the compiled reference with fix bond/create (src/MC, the ancestor of fix ex_load) between two le/snap fixes:
+    (pre, post) records of every event"""
+    from lammps_le_b200 import systems
+    s = systems.chromatin_chain(nbeads, nbeads * 3 // 100, rho=0.2, seed=11, barriers="random", extruder_bond=systems.EXTRUDER_FENE)
+    wd = tempfile.mkdtemp(prefix="le_bc_trace_")
+    refio.write_data_file(os.path.join(wd, "data.le"), s)
+    deck = refio.deck_header(s, "data.le") + [
+        "minimize 1e-6 1e-8 2000 20000", "reset_timestep 0", "fix 1 all nve", "fix 2 all langevin 1.0 1.0 1.0 904297",
+        "fix s0 all le/snap pre.bin pre grid",
+        "fix cr all bond/create %d %d %d %g %d prob %g %d iparam %d %d jparam %d %d" % (
+            cfg["nevery"], cfg["itype"], cfg["jtype"], cfg["rc"], cfg["btype"], cfg["prob"], cfg["seed"], *cfg["iparam"], *cfg["jparam"]),
+        "fix s1 all le/snap post.bin post",
+        "thermo_style custom step temp bonds f_cr[1] f_cr[2]", "thermo 100", "timestep 0.005", "run %d" % steps]
+    refio.run_reference(deck, workdir=wd)
+    pre = refio.read_records(os.path.join(wd, "pre.bin"))
+    post = refio.read_records(os.path.join(wd, "post.bin"))
+    assert len(pre) == len(post) == steps // cfg["nevery"]
+    return pre, post
+
+
 def main():
     from lammps_le_b200 import systems
     from tests.lehelpers import le_deck_lines
@@ -122,6 +146,12 @@ def main():
                         energy=np.array(rec["energy"]), bpa=np.array(rec["bpa"]), maxspecial=np.array(rec["maxspecial"]),
                         thermo=np.array([rec["thermo"][k] for k in ("Temp", "E_pair", "E_mol", "TotEng", "Press")]))
     print("forces_chain written")
+    # fix bond/create: four events of a 600-bead run (the later ones see beads that already carry created bonds and beads that have
+    # changed type)
+    pre, post = bond_create_trace(600, 200)
+    keep = [1, 2, 5, 9]
+    np.savez_compressed(os.path.join(gold, "bond_create_trace_small.npz"), **pack_trace([pre[k] for k in keep], [post[k] for k in keep]))
+    print("bond_create_trace_small: %d of %d events kept, %d bonds created in them" % (len(keep), len(pre), sum(post[k]["counters"][2] for k in keep)))
 
 
 if __name__ == "__main__":

@@ -142,15 +142,19 @@ def test_le_replay_live_reference_barrier_variants(name):
     assert not problems, "USER-LE replay mismatches: %s" % problems[:5]
 
 
-def test_bond_create_replay_live_reference():
-    """fix bond/create event by event: every recorded event of a run of the compiled reference replayed from its pre-state on the
-    GPU -- bond rows, special lists, types, created-bond counter and Marsaglia draws equal the reference's post-state (the same
-    trace pins the restatement on the CPU, tests/test_oracle.py)"""
-    _need_ref()
+@pytest.mark.parametrize("source", ["golden", "live"])
+def test_bond_create_replay(source):
+    """fix bond/create event by event: recorded events of the compiled reference (golden fixture / every event of a fresh run)
+    replayed from their pre-states on the GPU -- bond rows, special lists, types, created-bond counter and Marsaglia draws equal the
+    reference's post-state (the same traces pin the restatement on the CPU, tests/test_oracle.py)"""
     from oracle import refio
     from lammps_le_b200.engine import LE_FIX_EX_LOAD
-    from tests.test_oracle import BOND_CREATE_CFG as cfg, bond_create_trace
-    pre, post = bond_create_trace()
+    from oracle.make_golden import BOND_CREATE_CFG as cfg, bond_create_trace, unpack_trace
+    if source == "golden":
+        pre, post = unpack_trace(np.load(os.path.join(GOLD, "bond_create_trace_small.npz")))
+    else:
+        _need_ref()
+        pre, post = bond_create_trace()
     problems, created = [], 0
     for a, b in zip(pre, post):
         e = H.engine_from_record(a, CHROMATIN_BONDS, positions="xhold")
@@ -168,7 +172,7 @@ def test_bond_create_replay_live_reference():
         if hard:
             problems.append((a["step"], hard))
         e.close()
-    assert created > 40
+    assert created > (40 if source == "live" else 20)
     assert not problems, "fix bond/create replay mismatches: %s" % problems[:5]
 
 

@@ -290,40 +290,28 @@ def test_lists_and_forces_match_live_reference_on_a_dense_melt():
     assert np.abs(vb - rec["virial_bond"]).max() <= 1e-9 * np.abs(rec["virial_bond"]).max()
 
 
-BOND_CREATE_CFG = dict(nevery=20, itype=1, jtype=1, rc=1.05, btype=2, prob=0.5, seed=456456, iparam=(2, 4), jparam=(2, 4))
+from oracle.make_golden import BOND_CREATE_CFG, bond_create_trace, unpack_trace as _unpack_trace  # noqa: E402
 
 
-def bond_create_trace(nbeads=1200, steps=200):
-    """a run of the compiled reference with fix bond/create between two le/snap fixes: (pre, post) records of every event"""
-    import tempfile
-    from lammps_le_b200 import systems
-    cfg = BOND_CREATE_CFG
-    s = systems.chromatin_chain(nbeads, nbeads * 3 // 100, rho=0.2, seed=11, barriers="random", extruder_bond=systems.EXTRUDER_FENE)
-    wd = tempfile.mkdtemp(prefix="le_bc_trace_")
-    refio.write_data_file(os.path.join(wd, "data.le"), s)
-    deck = refio.deck_header(s, "data.le") + [
-        "minimize 1e-6 1e-8 2000 20000", "reset_timestep 0", "fix 1 all nve", "fix 2 all langevin 1.0 1.0 1.0 904297",
-        "fix s0 all le/snap pre.bin pre grid",
-        "fix cr all bond/create %d %d %d %g %d prob %g %d iparam %d %d jparam %d %d" % (
-            cfg["nevery"], cfg["itype"], cfg["jtype"], cfg["rc"], cfg["btype"], cfg["prob"], cfg["seed"], *cfg["iparam"], *cfg["jparam"]),
-        "fix s1 all le/snap post.bin post",
-        "thermo_style custom step temp bonds f_cr[1] f_cr[2]", "thermo 100", "timestep 0.005", "run %d" % steps]
-    refio.run_reference(deck, workdir=wd)
-    pre = refio.read_records(os.path.join(wd, "pre.bin"))
-    post = refio.read_records(os.path.join(wd, "post.bin"))
-    assert len(pre) == len(post) == steps // cfg["nevery"]
-    return pre, post
-
-
-def test_bond_create_replay_live_reference():
-    """fix bond/create (src/MC/fix_bond_create.cpp, the ancestor of fix ex_load; SURVEY.md 8f rank 4): the restatement -- fix_ex_load's
-    loops without the loop-extrusion rules, bond counts kept from the first run's setup -- against every event of a run of the
-    compiled reference: bond rows, special lists in exact order, types, created-bond counter and Marsaglia draws"""
+def _bond_create_events(source):
+    if source == "golden":
+        return _unpack_trace(np.load(os.path.join(GOLD, "bond_create_trace_small.npz")))
     if not refio.have_reference():
         pytest.skip("oracle/_ref not built")
+    return bond_create_trace()
+
+
+@pytest.mark.parametrize("source", ["golden", "live"])
+def test_bond_create_replay(source):
+    """fix bond/create (src/MC/fix_bond_create.cpp, the ancestor of fix ex_load; SURVEY.md 8f rank 4): the restatement -- fix_ex_load's
+    loops without the loop-extrusion rules, bond counts kept from the first run's setup -- against recorded events of the compiled
+    reference (golden: tests/golden/bond_create_trace_small.npz, made by oracle/make_golden.py; live: every event of a fresh run):
+    bond rows, special lists in exact order, types, created-bond counter and Marsaglia draws"""
     cfg = BOND_CREATE_CFG
-    pre, post = bond_create_trace()
-    bc = R._bondcount(R.copy_state(pre[0]), cfg["btype"], False)      # FixBondCreate::setup: nothing changes bonds before the first event
+    pre, post = _bond_create_events(source)
+    # FixBondCreate::setup counts once and the fix then adds only its own creations; no other fix changes bonds in these traces, so the
+    # counts at any event equal a recount of its pre-state (golden: the kept events are not consecutive) -- carried along in the live run
+    bc = R._bondcount(R.copy_state(pre[0]), cfg["btype"], False) if source == "live" else None
     created = 0
     for a, b in zip(pre, post):
         assert a["which"] == 3
@@ -337,5 +325,5 @@ def test_bond_create_replay_live_reference():
         assert cnt == b["counters"][2]
         assert rng.c24() == b["rngc"][2], "draw count differs at step %d" % a["step"]
         created += cnt
-    assert created > 40, "the run must create bonds"
+    assert created > (40 if source == "live" else 20), "the events must create bonds"
     assert (post[-1]["type"] == 4).sum() > (pre[0]["type"] == 4).sum(), "beads with two created bonds change type"
