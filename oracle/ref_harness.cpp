@@ -38,7 +38,8 @@
 #include "fix_ex_load.h"
 #include "fix_ex_unload.h"
 #include "fix_extrusion.h"
-#include "fix_bond_create.h"      // src/MC: the ancestor of fix ex_load (compiled in by oracle/build_ref.py, EXTRA_STYLES)
+#include "fix_bond_create.h"      // src/MC: the ancestors of fix ex_load / fix ex_unload (compiled in by oracle/build_ref.py, EXTRA_STYLES)
+#include "fix_bond_break.h"
 #include "force.h"
 #include "input.h"
 #include "lammps.h"
@@ -76,7 +77,7 @@ Fix *find_fix(LAMMPS *lmp, const char *style) {
 
 int rng_c(RanMars *r) { return r ? (int)llround(r->c * 16777216.0) : -1; }
 
-// which USER-LE fix fires on this timestep (0 none, 1 extrusion, 2 unload, 3 load / fix bond/create)
+// which USER-LE fix fires on this timestep (0 none, 1 extrusion, 2 unload / fix bond/break, 3 load / fix bond/create)
 int firing(LAMMPS *lmp) {
   const bigint n = lmp->update->ntimestep;
   int which = 0, count = 0;
@@ -84,6 +85,7 @@ int firing(LAMMPS *lmp) {
   if (Fix *f = find_fix(lmp, "ex_unload")) if (n % f->nevery - 2 == 0) { which = 2; count++; }
   if (Fix *f = find_fix(lmp, "ex_load")) if (n % f->nevery - 3 == 0) { which = 3; count++; }
   if (Fix *f = find_fix(lmp, "bond/create")) if (n % f->nevery == 0) { which = 3; count++; }   // (records as fix 3: it is ex_load's ancestor)
+  if (Fix *f = find_fix(lmp, "bond/break")) if (n % f->nevery == 0) { which = 2; count++; }    // (records as fix 2: ex_unload's ancestor)
   if (count > 1) lmp->error->all(FLERR, "le/snap: two USER-LE fixes fire on the same step; choose other periods");
   return which;
 }
@@ -101,11 +103,12 @@ void write_record(LAMMPS *lmp, FILE *fp, int kind, int which, bool lists, bool f
   FixExUnload *fu = (FixExUnload *)find_fix(lmp, "ex_unload");
   FixExLoad *fl = (FixExLoad *)find_fix(lmp, "ex_load");
   h.rngc[0] = fe ? rng_c(fe->random) : -1;
-  h.rngc[1] = fu ? rng_c(fu->random) : -1;
+  FixBondBreak *fb = (FixBondBreak *)find_fix(lmp, "bond/break");
+  h.rngc[1] = fu ? rng_c(fu->random) : fb ? rng_c(fb->random) : -1;
   FixBondCreate *fc = (FixBondCreate *)find_fix(lmp, "bond/create");
   h.rngc[2] = fl ? rng_c(fl->random) : fc ? rng_c(fc->random) : -1;
   h.counters[0] = fe ? fe->breakcount : 0;
-  h.counters[1] = fu ? fu->breakcount : 0;
+  h.counters[1] = fu ? fu->breakcount : fb ? fb->breakcount : 0;
   h.counters[2] = fl ? fl->createcount : fc ? fc->createcount : 0;
   h.counters[3] = (int)atom->nbonds;
   h.has_force = forces ? 1 : 0;

@@ -327,3 +327,36 @@ def test_bond_create_replay(source):
         created += cnt
     assert created > (40 if source == "live" else 20), "the events must create bonds"
     assert (post[-1]["type"] == 4).sum() > (pre[0]["type"] == 4).sum(), "beads with two created bonds change type"
+
+
+def test_bond_break_replay_live_reference():
+    """fix bond/break (src/MC/fix_bond_break.cpp, the ancestor of fix ex_unload: the same post_integrate body on multiples of N):
+    the restatement of ex_unload against every event of a run of the compiled reference that breaks stretched extruder bonds"""
+    if not refio.have_reference():
+        pytest.skip("oracle/_ref not built")
+    import tempfile
+    from lammps_le_b200 import systems
+    cfg = dict(nevery=10, btype=2, rc=1.2, prob=0.5, seed=456456)
+    s = systems.chromatin_chain(1500, 60, rho=0.2, seed=21, barriers="random", extruder_bond=systems.EXTRUDER_FENE)
+    wd = tempfile.mkdtemp(prefix="le_bb_trace_")
+    refio.write_data_file(os.path.join(wd, "data.le"), s)
+    deck = refio.deck_header(s, "data.le") + [
+        "fix 1 all nve/limit 0.05", "fix 2 all langevin 1.0 1.0 1.0 904297", "fix s0 all le/snap pre.bin pre grid",
+        "fix br all bond/break %d %d %g prob %g %d" % (cfg["nevery"], cfg["btype"], cfg["rc"], cfg["prob"], cfg["seed"]),
+        "fix s1 all le/snap post.bin post", "thermo_style custom step temp bonds f_br[1] f_br[2]", "thermo 100", "timestep 0.005", "run 60"]
+    refio.run_reference(deck, workdir=wd)
+    pre = refio.read_records(os.path.join(wd, "pre.bin"))
+    post = refio.read_records(os.path.join(wd, "post.bin"))
+    assert len(pre) == len(post) == 6
+    broken = 0
+    for a, b in zip(pre, post):
+        assert a["which"] == 2
+        S = R.copy_state(a)
+        rng = R.RanMars(cfg["seed"]).skip(refio.draws_consumed(a["rngc"][1]))
+        cnt = R.fix_ex_unload(S, rng, cfg["btype"], cfg["rc"], cfg["prob"])
+        res = H.compare_topology(S, b)
+        assert not any(res.values()), "event step %d: %s" % (a["step"], res)
+        assert cnt == b["counters"][1]
+        assert rng.c24() == b["rngc"][1], "draw count differs at step %d" % a["step"]
+        broken += cnt
+    assert broken > 5, "the run must break bonds"
